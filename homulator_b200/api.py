@@ -1,0 +1,399 @@
+"""ctypes binding of libhomulator_b200.so + host-side mirror of the reference's operation objects.
+
+The reference exposes `OP(label, maxLevel, currentLevel, alpha, Config*, Arch*)` + `simulate()` for
+OP in {HMULT, HROTATE, HADD, PMULT, PADD} (reference include/Operation.h:200-319).  The classes at the
+bottom keep that constructor shape; `simulate()` runs the operation on seeded synthetic data on the GPU
+and returns measured microseconds and the reference-shaped instruction counts.
+"""
+import ctypes as C
+import math
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+HML_MAX_STAGES = 48
+
+
+class HmlError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("homulator_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class _StageCount(C.Structure):
+    _fields_ = [("label", C.c_char * 48), ("opcode", C.c_char * 16), ("limb_ops", C.c_uint64), ("instructions", C.c_uint64)]
+
+
+class _Counts(C.Structure):
+    _fields_ = [("ntt", C.c_uint64), ("intt", C.c_uint64), ("mult", C.c_uint64), ("bconv_step2", C.c_uint64),
+                ("automorph", C.c_uint64), ("total", C.c_uint64), ("driver_total", C.c_uint64), ("n_stages", C.c_uint32),
+                ("stages", _StageCount * HML_MAX_STAGES)]
+
+
+class _ExecCounts(C.Structure):
+    _fields_ = [("ntt_limbs", C.c_uint64), ("intt_limbs", C.c_uint64), ("ewe_limbs", C.c_uint64),
+                ("bconv_limb_macs", C.c_uint64), ("automorph_limbs", C.c_uint64), ("kernel_launches", C.c_uint64)]
+
+
+def lib_path():
+    return os.path.join(HERE, "libhomulator_b200.so")
+
+
+# every symbol include/homulator_b200.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "hml_ctx_create", "hml_ctx_create_params", "hml_ctx_destroy", "hml_last_error", "hml_last_create_error",
+    "hml_ring_degree", "hml_n_moduli", "hml_get_moduli", "hml_get_roots", "hml_dev_alloc", "hml_dev_free", "hml_h2d",
+    "hml_d2h", "hml_sync", "hml_ntt", "hml_intt", "hml_ewe", "hml_automorph", "hml_bconv", "hml_keyswitch", "hml_rescale",
+    "hml_hmult", "hml_hrotate", "hml_hadd", "hml_pmult", "hml_padd", "hml_hmult_batch", "hml_hrotate_batch",
+    "hml_hmult_host", "hml_hrotate_host", "hml_host_alloc_pinned", "hml_host_free_pinned", "hml_trace_counts",
+    "hml_get_counts", "hml_exec_counts_get", "hml_exec_counts_reset", "hml_cli_main",
+]
+
+
+def load_library():
+    """Load the in-tree C-ABI library (building it first when a toolkit is present).  Raises if absent."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        from .build import build
+        build()
+    L = C.CDLL(path)
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    L.hml_ctx_create.argtypes = [C.c_char_p, u32, u32, i32, C.POINTER(vp)]
+    L.hml_ctx_create_params.argtypes = [u32, u32, u32, u32, u32, i32, C.POINTER(vp)]
+    L.hml_ctx_destroy.argtypes = [vp]
+    L.hml_ctx_destroy.restype = None
+    L.hml_last_error.argtypes = [vp]
+    L.hml_last_error.restype = C.c_char_p
+    L.hml_last_create_error.restype = C.c_char_p
+    L.hml_ring_degree.argtypes = [vp]
+    L.hml_ring_degree.restype = u32
+    L.hml_n_moduli.argtypes = [vp]
+    L.hml_n_moduli.restype = u32
+    L.hml_get_moduli.argtypes = [vp, C.POINTER(u64), u32]
+    L.hml_get_roots.argtypes = [vp, C.POINTER(u64), u32]
+    L.hml_ntt.argtypes = [vp, vp, vp, C.POINTER(u32), u32, vp]
+    L.hml_intt.argtypes = [vp, vp, vp, C.POINTER(u32), u32, vp]
+    L.hml_ewe.argtypes = [vp, vp, vp, vp, vp, i32, vp, C.POINTER(u32), u32, vp]
+    L.hml_automorph.argtypes = [vp, vp, vp, u64, u32, vp]
+    L.hml_bconv.argtypes = [vp, vp, C.POINTER(u32), u32, vp, C.POINTER(u32), u32, vp]
+    L.hml_keyswitch.argtypes = [vp, u32, vp, vp, u32, vp, vp, vp]
+    L.hml_rescale.argtypes = [vp, u32, vp, vp, vp]
+    L.hml_hmult.argtypes = [vp, u32, vp, vp, vp, u32, vp, vp]
+    L.hml_hrotate.argtypes = [vp, u32, vp, vp, u32, u64, vp, vp]
+    for f in ("hml_hadd", "hml_pmult", "hml_padd"):
+        getattr(L, f).argtypes = [vp, u32, vp, vp, vp, vp]
+    L.hml_hmult_batch.argtypes = [vp, u32, u32, vp, vp, vp, u32, vp, vp]
+    L.hml_hrotate_batch.argtypes = [vp, u32, u32, vp, vp, u32, u64, vp, vp]
+    L.hml_hmult_host.argtypes = [vp, u32, u32, vp, vp, vp, u32, vp]
+    L.hml_hrotate_host.argtypes = [vp, u32, u32, vp, vp, u32, u64, vp]
+    L.hml_host_alloc_pinned.argtypes = [vp, u64, C.POINTER(vp)]
+    L.hml_host_free_pinned.argtypes = [vp, vp]
+    L.hml_trace_counts.argtypes = [C.c_char_p, u32, u32, u32, u32, u32, u32, u32, C.POINTER(_Counts)]
+    L.hml_get_counts.argtypes = [vp, C.c_char_p, u32, C.POINTER(_Counts)]
+    L.hml_exec_counts_get.argtypes = [vp, C.POINTER(_ExecCounts)]
+    L.hml_exec_counts_reset.argtypes = [vp]
+    L.hml_cli_main.argtypes = [i32, C.POINTER(C.c_char_p)]
+    _LIB = L
+    return L
+
+
+def _counts_to_dict(c):
+    return {
+        "NTT": c.ntt, "INTT": c.intt, "MULT": c.mult, "BCONV_STEP2": c.bconv_step2, "AUTO": c.automorph,
+        "total": c.total, "driverTotal": c.driver_total,
+        "stages": [{"label": c.stages[i].label.decode(), "opcode": c.stages[i].opcode.decode(),
+                    "limb_ops": c.stages[i].limb_ops, "instructions": c.stages[i].instructions} for i in range(c.n_stages)],
+    }
+
+
+def trace_counts(op, N, batch_size, max_level, L, alpha, bconv_high=2, bconv_width=6):
+    """Reference-shaped instruction counts of one op (pure host code in the library; no GPU needed)."""
+    lib = load_library()
+    c = _Counts()
+    rc = lib.hml_trace_counts(op.encode(), N, batch_size, max_level, L, alpha, bconv_high, bconv_width, C.byref(c))
+    if rc:
+        raise HmlError(rc, lib.hml_last_create_error().decode())
+    return _counts_to_dict(c)
+
+
+def algorithmic_words(op, L, alpha):
+    """Algorithmic traffic of one op in limb-sized words W = 8N bytes (unfused schedule)."""
+    E, beta = L + alpha, math.ceil(L / alpha)
+    ks = 2 * L + 2 * L + beta * E + 2 * beta * E + (3 * beta + 2) * E + 4 * alpha + 4 * alpha + 2 * (alpha + L) + 4 * L + 6 * L
+    if op == "keyswitch":
+        return ks
+    if op == "hmult":
+        return ks + 7 * L + 6 * L + 2 * (4 + 5 * (L - 1))
+    if op == "hrotate":
+        return ks + 4 * L + 3 * L
+    if op in ("hadd", "pmult", "padd"):
+        return 6 * L
+    if op in ("ntt", "intt", "auto"):
+        return 2
+    raise ValueError(op)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda or not t.is_contiguous() or t.element_size() != 8:
+        raise ValueError("expected a contiguous 64-bit CUDA tensor")
+    return t.data_ptr()
+
+
+def _u32arr(v):
+    return (C.c_uint32 * len(v))(*[int(x) for x in v])
+
+
+class Context:
+    """One hml_ctx: replaces `new Config(path)` + `new Arch(config)` (reference bench_micro24.cpp:16-27)."""
+
+    def __init__(self, cfg_path=None, max_level=None, alpha=None, device=0, N=None, element_bit_width=36, batch_size=256):
+        import torch
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        if not torch.cuda.is_available():
+            raise HmlError(3, "no CUDA device: homulator_b200 has no CPU fallback")
+        if cfg_path is not None:
+            rc = self.lib.hml_ctx_create(str(cfg_path).encode(), max_level, alpha, device, C.byref(self.h))
+        else:
+            rc = self.lib.hml_ctx_create_params(N, element_bit_width, min(batch_size, N), max_level, alpha, device, C.byref(self.h))
+        if rc:
+            raise HmlError(rc, self.lib.hml_last_create_error().decode())
+        self.device = torch.device("cuda", device)
+        self.N = self.lib.hml_ring_degree(self.h)
+        self.max_level, self.alpha = max_level, alpha
+        n = self.lib.hml_n_moduli(self.h)
+        buf = (C.c_uint64 * n)()
+        self._chk(self.lib.hml_get_moduli(self.h, buf, n))
+        self.moduli = [int(x) for x in buf]
+        self._chk(self.lib.hml_get_roots(self.h, buf, n))
+        self.psi = [int(x) for x in buf]
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.hml_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc:
+            raise HmlError(rc, self.lib.hml_last_error(self.h).decode())
+
+    def _stream(self):
+        import torch
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def ext_mod_idx(self, L):
+        return list(range(L)) + [self.max_level + j for j in range(self.alpha)]
+
+    def beta(self, L):
+        return -(-L // self.alpha)
+
+    def empty(self, *shape):
+        import torch
+        return torch.empty(*shape, dtype=torch.int64, device=self.device)
+
+    # ---- primitives (one per reference instruction class)
+    def ntt(self, x, mod_idx, out=None, inverse=False):
+        out = self.empty(*x.shape) if out is None else out
+        n = len(mod_idx)
+        assert x.numel() == n * self.N
+        f = self.lib.hml_intt if inverse else self.lib.hml_ntt
+        self._chk(f(self.h, _ptr(x), _ptr(out), _u32arr(mod_idx), n, self._stream()))
+        return out
+
+    def intt(self, x, mod_idx, out=None):
+        return self.ntt(x, mod_idx, out, inverse=True)
+
+    def ewe(self, x1, x2, x3, x4, mod_idx, subtract=False, out=None):
+        ref = x1 if x1 is not None else x3
+        out = self.empty(*ref.shape) if out is None else out
+        self._chk(self.lib.hml_ewe(self.h, _ptr(x1), _ptr(x2), _ptr(x3), _ptr(x4), int(subtract), _ptr(out),
+                                   _u32arr(mod_idx), len(mod_idx), self._stream()))
+        return out
+
+    def automorph(self, x, galois_elt, out=None):
+        out = self.empty(*x.shape) if out is None else out
+        self._chk(self.lib.hml_automorph(self.h, _ptr(x), _ptr(out), galois_elt, x.numel() // self.N, self._stream()))
+        return out
+
+    def bconv(self, x, src_idx, dst_idx, out=None):
+        out = self.empty(len(dst_idx), self.N) if out is None else out
+        self._chk(self.lib.hml_bconv(self.h, _ptr(x), _u32arr(src_idx), len(src_idx), _ptr(out), _u32arr(dst_idx),
+                                     len(dst_idx), self._stream()))
+        return out
+
+    # ---- sub-operations and operations
+    def keyswitch(self, L, d, evk, evk_q_limbs=None):
+        o0, o1 = self.empty(L, self.N), self.empty(L, self.N)
+        self._chk(self.lib.hml_keyswitch(self.h, L, _ptr(d), _ptr(evk), evk_q_limbs or L, _ptr(o0), _ptr(o1), self._stream()))
+        return o0, o1
+
+    def rescale(self, L, x):
+        out = self.empty(L - 1, self.N)
+        self._chk(self.lib.hml_rescale(self.h, L, _ptr(x), _ptr(out), self._stream()))
+        return out
+
+    def hmult(self, L, ct_a, ct_b, evk, evk_q_limbs=None, out=None):
+        out = self.empty(2, L - 1, self.N) if out is None else out
+        self._chk(self.lib.hml_hmult(self.h, L, _ptr(ct_a), _ptr(ct_b), _ptr(evk), evk_q_limbs or L, _ptr(out), self._stream()))
+        return out
+
+    def hrotate(self, L, ct, rotkey, galois_elt=5, evk_q_limbs=None, out=None):
+        out = self.empty(2, L, self.N) if out is None else out
+        self._chk(self.lib.hml_hrotate(self.h, L, _ptr(ct), _ptr(rotkey), evk_q_limbs or L, galois_elt, _ptr(out), self._stream()))
+        return out
+
+    def hadd(self, L, a, b, out=None):
+        out = self.empty(2, L, self.N) if out is None else out
+        self._chk(self.lib.hml_hadd(self.h, L, _ptr(a), _ptr(b), _ptr(out), self._stream()))
+        return out
+
+    def pmult(self, L, ct, pt, out=None):
+        out = self.empty(2, L, self.N) if out is None else out
+        self._chk(self.lib.hml_pmult(self.h, L, _ptr(ct), _ptr(pt), _ptr(out), self._stream()))
+        return out
+
+    def padd(self, L, ct, pt, out=None):
+        out = self.empty(2, L, self.N) if out is None else out
+        self._chk(self.lib.hml_padd(self.h, L, _ptr(ct), _ptr(pt), _ptr(out), self._stream()))
+        return out
+
+    def hmult_batch(self, L, ct_a, ct_b, evk, evk_q_limbs=None, out=None):
+        n = ct_a.shape[0]
+        out = self.empty(n, 2, L - 1, self.N) if out is None else out
+        self._chk(self.lib.hml_hmult_batch(self.h, L, n, _ptr(ct_a), _ptr(ct_b), _ptr(evk), evk_q_limbs or L, _ptr(out), self._stream()))
+        return out
+
+    def hrotate_batch(self, L, ct, rotkey, galois_elt=5, evk_q_limbs=None, out=None):
+        n = ct.shape[0]
+        out = self.empty(n, 2, L, self.N) if out is None else out
+        self._chk(self.lib.hml_hrotate_batch(self.h, L, n, _ptr(ct), _ptr(rotkey), evk_q_limbs or L, galois_elt, _ptr(out), self._stream()))
+        return out
+
+    def hmult_host(self, L, ct_a_host, ct_b_host, evk_dev, out_host, evk_q_limbs=None):
+        """ct_*_host / out_host: CPU tensors (pinned for full speed) [n][2][L][N] / [n][2][L-1][N]."""
+        n = ct_a_host.shape[0]
+        self._chk(self.lib.hml_hmult_host(self.h, L, n, ct_a_host.data_ptr(), ct_b_host.data_ptr(), _ptr(evk_dev),
+                                          evk_q_limbs or L, out_host.data_ptr()))
+        return out_host
+
+    def hrotate_host(self, L, ct_host, rotkey_dev, out_host, galois_elt=5, evk_q_limbs=None):
+        n = ct_host.shape[0]
+        self._chk(self.lib.hml_hrotate_host(self.h, L, n, ct_host.data_ptr(), _ptr(rotkey_dev), evk_q_limbs or L, galois_elt,
+                                            out_host.data_ptr()))
+        return out_host
+
+    def counts(self, op, L):
+        c = _Counts()
+        rc = self.lib.hml_get_counts(self.h, op.encode(), L, C.byref(c))
+        if rc:
+            raise HmlError(rc, self.lib.hml_last_create_error().decode())
+        return _counts_to_dict(c)
+
+    def exec_counts(self, reset=False):
+        e = _ExecCounts()
+        self._chk(self.lib.hml_exec_counts_get(self.h, C.byref(e)))
+        if reset:
+            self._chk(self.lib.hml_exec_counts_reset(self.h))
+        return {k: getattr(e, k) for k, _ in _ExecCounts._fields_}
+
+    # ---- seeded synthetic operands
+    def uniform(self, mod_idx, tensor_id, lead=()):
+        """int64 CUDA tensor [*lead, len(mod_idx), N] of uniform residues, generated on the device."""
+        import torch
+        g = torch.Generator(device=self.device)
+        g.manual_seed(0x486F6D75 + 7919 * tensor_id)
+        n_lead = 1
+        for d in lead:
+            n_lead *= d
+        out = self.empty(n_lead, len(mod_idx), self.N)
+        for i, mi in enumerate(mod_idx):
+            out[:, i].random_(0, self.moduli[mi], generator=g)
+        return out.view(*lead, len(mod_idx), self.N)
+
+
+class _Op:
+    """Mirror of the reference's op objects: OP(label, maxLevel, currentLevel, alpha, cfg, arch)."""
+    name = None
+
+    def __init__(self, label, max_level, current_level, alpha, cfg, arch=None, device=0):
+        self.label, self.L = label, current_level
+        self.ctx = cfg if isinstance(cfg, Context) else Context(cfg, max_level, alpha, device)
+        self.counts = self.ctx.counts(self.name, current_level)  # the reference builds its trace in the constructor
+
+    def _operands(self):
+        c, L = self.ctx, self.L
+        q = list(range(L))
+        ct_a = c.uniform(q, 1, lead=(2,))
+        ct_b = c.uniform(q, 2, lead=(2,))
+        key = c.uniform(c.ext_mod_idx(L), 3, lead=(c.beta(L), 2)) if self.name in ("hmult", "hrotate") else None
+        return ct_a, ct_b, key
+
+    def execute(self, *args, **kw):
+        raise NotImplementedError
+
+    def simulate(self, iters=10, warmup=3):
+        """Run on seeded synthetic data; returns dict(us_median=..., counts=...)."""
+        import torch
+        ct_a, ct_b, key = self._operands()
+        args = {"hmult": (ct_a, ct_b, key), "hrotate": (ct_a, key), "hadd": (ct_a, ct_b), "pmult": (ct_a, ct_b[0]),
+                "padd": (ct_a, ct_b[0])}[self.name]
+        for _ in range(warmup):
+            self.execute(*args)
+        torch.cuda.synchronize()
+        times = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.execute(*args)
+            e1.record()
+            e1.synchronize()
+            times.append(e0.elapsed_time(e1) * 1e3)
+        times.sort()
+        return {"op": self.name, "us_median": times[len(times) // 2], "us_min": times[0], "counts": self.counts}
+
+
+class HMULT(_Op):
+    name = "hmult"
+
+    def execute(self, ct_a, ct_b, evk, evk_q_limbs=None):
+        return self.ctx.hmult(self.L, ct_a, ct_b, evk, evk_q_limbs)
+
+
+class HROTATE(_Op):
+    name = "hrotate"
+
+    def execute(self, ct, rotkey, galois_elt=5, evk_q_limbs=None):
+        return self.ctx.hrotate(self.L, ct, rotkey, galois_elt, evk_q_limbs)
+
+
+class HADD(_Op):
+    name = "hadd"
+
+    def execute(self, a, b):
+        return self.ctx.hadd(self.L, a, b)
+
+
+class PMULT(_Op):
+    name = "pmult"
+
+    def execute(self, ct, pt):
+        return self.ctx.pmult(self.L, ct, pt)
+
+
+class PADD(_Op):
+    name = "padd"
+
+    def execute(self, ct, pt):
+        return self.ctx.padd(self.L, ct, pt)

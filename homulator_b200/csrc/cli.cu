@@ -1,0 +1,215 @@
+// `Homulator.run <configfile> <operationName> <maxExecutionLevel> <currentLevel> <alpha> [cluster] [--flags]`
+// Drop-in for the reference's only executable (reference bench_test/bench_micro24.cpp:5-52): same
+// positional arguments, same operation names, same config dump; but instead of building an instruction
+// stream and clocking a pipeline model (reference src/Operation.cpp:1025-1112) it executes the operation on
+// seeded synthetic data on the GPU and reports measured time, the reference-shaped instruction counts and
+// the HBM roofline fraction.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <string>
+#include <vector>
+
+#include "context.h"
+
+using namespace hml;
+
+__global__ void k_fill_uniform(u64 *out, size_t n_per_limb, int n_limbs_total, const u64 *limb_q, u64 seed) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_per_limb) return;
+  const int limb = blockIdx.y;
+  u64 z = seed + 0x9E3779B97F4A7C15ull * ((u64)limb * n_per_limb + i + 1);  // splitmix64
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  out[(size_t)limb * n_per_limb + i] = z % limb_q[limb];
+  (void)n_limbs_total;
+}
+
+__global__ void k_flush(u64 *buf, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) buf[i] = i;
+}
+
+// Algorithmic traffic in limb-sized words W = 8N bytes (each stage reads each distinct input
+// limb once and writes each output limb once, unfused).
+static double ks_words(double L, double A) {
+  const double E = L + A, beta = std::ceil(L / A);
+  return 2 * L + 2 * L + beta * E + 2 * beta * E + (3 * beta + 2) * E + 4 * A + 4 * A + 2 * (A + L) + 4 * L + 6 * L;
+}
+static double op_words(const std::string &op, double L, double A) {
+  if (op == "hmult") return ks_words(L, A) + 7 * L + 6 * L + 2 * (4 + 5 * (L - 1));
+  if (op == "hrotate") return ks_words(L, A) + 4 * L + 3 * L;
+  if (op == "pmult" || op == "padd") return 2 * 3 * L;  // plaintext limb is re-read for the second component
+  return 2 * 3 * L;
+}
+
+static int fill(hml_ctx *ctx, u64 *dev, const std::vector<u64> &limb_mod, u64 seed) {
+  u64 *dq = nullptr;
+  cudaMalloc(&dq, limb_mod.size() * 8);
+  cudaMemcpy(dq, limb_mod.data(), limb_mod.size() * 8, cudaMemcpyHostToDevice);
+  const size_t N = ctx->p.N;
+  k_fill_uniform<<<dim3((unsigned)((N + 255) / 256), (unsigned)limb_mod.size()), 256>>>(dev, N, (int)limb_mod.size(), dq, seed);
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaFree(dq);
+  return e == cudaSuccess ? 0 : 1;
+}
+
+extern "C" int hml_cli_main(int argc, char **argv) {
+  if (argc < 6) {
+    fprintf(stderr, "Usage: %s <configfile> <operationName> <maxExecutionLevel> <currentLevel> <alpha> [cluster]"
+                    " [--iters K] [--warmup W] [--rot R] [--device D] [--no-flush]\n", argv[0]);
+    return 1;
+  }
+  const std::string path = argv[1], op = argv[2];
+  const uint32_t maxl = (uint32_t)std::atoi(argv[3]), L = (uint32_t)std::atoi(argv[4]), alpha = (uint32_t)std::atoi(argv[5]);
+  int iters = 20, warmup = 3, rot = 1, device = 0, flush = 1, argi = 6;
+  long cluster = -1;
+  if (argi < argc && argv[argi][0] != '-') cluster = std::atol(argv[argi++]);  // accepted like the reference (bench_micro24.cpp:23-25)
+  for (; argi < argc; ++argi) {
+    const std::string f = argv[argi];
+    auto val = [&](int &dst) { if (argi + 1 < argc) dst = std::atoi(argv[++argi]); };
+    if (f == "--iters") val(iters);
+    else if (f == "--warmup") val(warmup);
+    else if (f == "--rot") val(rot);
+    else if (f == "--device") val(device);
+    else if (f == "--no-flush") flush = 0;
+  }
+  CfgFile cfg;
+  std::string err;
+  if (!cfg.load(path, err)) {
+    fprintf(stderr, "Error opening config file.\n%s\n", err.c_str());
+    return 2;
+  }
+  fputs(cfg.dump().c_str(), stdout);  // dumped before the cluster override, like the reference
+  if (!(op == "hmult" || op == "hrotate" || op == "hadd" || op == "pmult" || op == "padd")) {
+    // reference bench_micro24.cpp:49-51: message on stdout, exit status 0
+    printf("Error operation requirement, please double confirm!\n");
+    return 0;
+  }
+  hml_ctx *ctx = nullptr;
+  int rc = hml_ctx_create(path.c_str(), maxl, alpha, device, &ctx);
+  if (rc) {
+    fprintf(stderr, "homulator_b200: cannot create context: %s\n", hml_last_create_error());
+    return 3;
+  }
+  if (cluster >= 0) ctx->cfg.set("cluster", (uint32_t)cluster);
+  hml_counts cnt;
+  rc = hml_get_counts(ctx, op.c_str(), L, &cnt);
+  if (rc) {
+    fprintf(stderr, "homulator_b200: %s\n", hml_last_create_error());
+    hml_ctx_destroy(ctx);
+    return 4;
+  }
+  const Params &p = ctx->p;
+  const size_t N = p.N;
+  const uint32_t beta = p.beta(L), E = L + alpha;
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  // ---- seeded synthetic operands: uniform residues per limb
+  std::vector<u64> ct_mod, key_mod, pt_mod;
+  for (int k = 0; k < 2; ++k) for (uint32_t i = 0; i < L; ++i) ct_mod.push_back(p.mod[i]);
+  for (uint32_t i = 0; i < L; ++i) pt_mod.push_back(p.mod[i]);
+  for (uint32_t j = 0; j < beta * 2; ++j) for (uint32_t e = 0; e < E; ++e) key_mod.push_back(p.mod[p.ext_mod(L, e)]);
+  uint64_t *a = nullptr, *b = nullptr, *key = nullptr, *out = nullptr;
+  u64 *flushbuf = nullptr;
+  const u64 seed = 0x486F6D756C61746Full;
+  cudaMalloc(&a, ct_mod.size() * N * 8);
+  cudaMalloc(&b, ct_mod.size() * N * 8);
+  cudaMalloc(&out, ct_mod.size() * N * 8);
+  int bad = fill(ctx, (u64 *)a, ct_mod, seed + 1);
+  if (op == "pmult" || op == "padd") bad |= fill(ctx, (u64 *)b, pt_mod, seed + 2);
+  else bad |= fill(ctx, (u64 *)b, ct_mod, seed + 2);
+  if (op == "hmult" || op == "hrotate") {
+    cudaMalloc(&key, key_mod.size() * N * 8);
+    bad |= fill(ctx, (u64 *)key, key_mod, seed + 3);
+  }
+  const size_t flush_words = (size_t)256 << 17;  // 256 MiB > L2
+  if (flush) cudaMalloc(&flushbuf, flush_words * 8);
+  if (bad || cudaGetLastError() != cudaSuccess) {
+    fprintf(stderr, "homulator_b200: device allocation / fill failed\n");
+    return 5;
+  }
+  u64 g = 1;
+  for (int r = 0; r < rot; ++r) g = (g * 5) % (2 * N);
+  auto run = [&]() -> int {
+    if (op == "hmult") return hml_hmult(ctx, L, a, b, key, L, out, nullptr);
+    if (op == "hrotate") return hml_hrotate(ctx, L, a, key, L, g, out, nullptr);
+    if (op == "hadd") return hml_hadd(ctx, L, a, b, out, nullptr);
+    if (op == "pmult") return hml_pmult(ctx, L, a, b, out, nullptr);
+    return hml_padd(ctx, L, a, b, out, nullptr);
+  };
+  std::string OP = op;
+  std::transform(OP.begin(), OP.end(), OP.begin(), ::toupper);
+  printf("\n\nWelcome! Start executing %s on %s (%d SMs)!\n\n", OP.c_str(), prop.name, prop.multiProcessorCount);
+  time_t t0 = time(nullptr);
+  printf("Start time: %s\n", ctime(&t0));
+  for (int i = 0; i < warmup; ++i)
+    if ((rc = run())) break;
+  if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = HML_ERR_CUDA;
+  if (rc) {
+    fprintf(stderr, "homulator_b200: %s failed: %s\n", op.c_str(), hml_last_error(ctx));
+    return 6;
+  }
+  hml_exec_counts_reset(ctx);
+  run();
+  hml_exec_counts ex;
+  hml_exec_counts_get(ctx, &ex);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  std::vector<float> us;
+  for (int i = 0; i < iters; ++i) {
+    if (flush) k_flush<<<1184, 256>>>(flushbuf, flush_words);
+    cudaEventRecord(e0);
+    run();
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    us.push_back(ms * 1000.f);
+  }
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    fprintf(stderr, "homulator_b200: CUDA failure during the timed runs\n");
+    return 6;
+  }
+  std::sort(us.begin(), us.end());
+  const double med = us.empty() ? 0 : us[us.size() / 2], mn = us.empty() ? 0 : us.front();
+  const double words = op_words(op, L, alpha), bytes = words * 8.0 * N;
+  const double gbs = med > 0 ? bytes / (med * 1e-6) / 1e9 : 0;
+  const double peak = 6546.2;  // measured copy bandwidth of this pool's B200s (MEASURED_PEAKS.json)
+  time_t t1 = time(nullptr);
+  printf("\n\nCompleted!\n");
+  printf("%s executed\t%.2f us (median of %d, min %.2f us, L2 %s between runs)\n\n", OP.c_str(), med, iters, mn,
+         flush ? "flushed" : "not flushed");
+  printf("End time: %s\n", ctime(&t1));
+  printf("Reference-trace instruction counts (one instruction = %u coefficients of one limb):\n", p.batch_size);
+  printf("=====================================\n");
+  printf("%-34s %-12s %10s %12s\n", "stage", "opcode", "limb-ops", "instructions");
+  for (uint32_t i = 0; i < cnt.n_stages; ++i)
+    printf("%-34s %-12s %10llu %12llu\n", cnt.stages[i].label, cnt.stages[i].opcode, (unsigned long long)cnt.stages[i].limb_ops,
+           (unsigned long long)cnt.stages[i].instructions);
+  printf("NTT :\t%llu\nINTT :\t%llu\nMULT :\t%llu\nBCONV_STEP2 :\t%llu\nAUTO :\t%llu\nTOTAL :\t%llu\ndriverTotal :\t%llu\n",
+         (unsigned long long)cnt.ntt, (unsigned long long)cnt.intt, (unsigned long long)cnt.mult, (unsigned long long)cnt.bconv_step2,
+         (unsigned long long)cnt.automorph, (unsigned long long)cnt.total, (unsigned long long)cnt.driver_total);
+  printf("=====================================\n");
+  printf("Executed on the GPU (limb-ops; deltas vs the trace are SURVEY.md 3.5 D1-D3):\n");
+  printf("NTT_limbs :\t%llu\nINTT_limbs :\t%llu\nEWE_limbs :\t%llu\nBCONV_limb_MACs :\t%llu\nAUTO_limbs :\t%llu\nkernel_launches :\t%llu\n",
+         (unsigned long long)ex.ntt_limbs, (unsigned long long)ex.intt_limbs, (unsigned long long)ex.ewe_limbs,
+         (unsigned long long)ex.bconv_limb_macs, (unsigned long long)ex.automorph_limbs, (unsigned long long)ex.kernel_launches);
+  printf("Algorithmic traffic :\t%.0f W = %.4e B -> %.1f GB/s = %.1f%% of measured HBM peak (%.1f GB/s)\n", words, bytes, gbs,
+         100.0 * gbs / peak, peak);
+  printf("{\"op\": \"%s\", \"N\": %u, \"maxLevel\": %u, \"L\": %u, \"alpha\": %u, \"us_median\": %.3f, \"us_min\": %.3f, \"iters\": %d, "
+         "\"l2_flushed\": %s, \"algorithmic_bytes\": %.0f, \"achieved_gbs\": %.2f, \"hbm_frac_of_measured\": %.4f, "
+         "\"trace\": {\"NTT\": %llu, \"INTT\": %llu, \"MULT\": %llu, \"BCONV_STEP2\": %llu, \"AUTO\": %llu, \"total\": %llu, \"driverTotal\": %llu}, "
+         "\"executed\": {\"ntt_limbs\": %llu, \"intt_limbs\": %llu, \"ewe_limbs\": %llu, \"bconv_limb_macs\": %llu, \"auto_limbs\": %llu, "
+         "\"kernel_launches\": %llu}, \"gpu\": \"%s\"}\n",
+         op.c_str(), p.N, maxl, L, alpha, med, mn, iters, flush ? "true" : "false", bytes, gbs, gbs / peak,
+         (unsigned long long)cnt.ntt, (unsigned long long)cnt.intt, (unsigned long long)cnt.mult, (unsigned long long)cnt.bconv_step2,
+         (unsigned long long)cnt.automorph, (unsigned long long)cnt.total, (unsigned long long)cnt.driver_total,
+         (unsigned long long)ex.ntt_limbs, (unsigned long long)ex.intt_limbs, (unsigned long long)ex.ewe_limbs,
+         (unsigned long long)ex.bconv_limb_macs, (unsigned long long)ex.automorph_limbs, (unsigned long long)ex.kernel_launches, prop.name);
+  cudaFree(a); cudaFree(b); cudaFree(out); cudaFree(key); cudaFree(flushbuf);
+  hml_ctx_destroy(ctx);
+  return 0;
+}

@@ -1,0 +1,748 @@
+// hml_ctx: tables, per-level constants, workspace, and the composition of the reference's ops out of the
+// kernels in ntt.cu / ewe.cu.  Stage order follows the reference's constructors:
+//   KeySwitch  reference src/Operation.cpp:9-54      Rescale  :741-911
+//   HMULT      :913-1023      HROTATE :1271-1358      HADD :1114-1176   PMULT :1453-1523   PADD :1618-1680
+#include "context.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "planner.h"
+
+using namespace hml;
+
+static thread_local std::string g_create_err;
+
+#define CU_TRY(ctx, call)                                                                          \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                             \
+      return HML_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+static int fail(hml_ctx *ctx, int code, const std::string &msg) {
+  ctx->err = msg;
+  return code;
+}
+
+static double2 mk_cst(u64 c, u64 q) { return make_double2((double)c, (double)c / (double)q); }
+
+template <class T>
+static int upload(hml_ctx *ctx, const std::vector<T> &h, T **dev) {
+  CU_TRY(ctx, cudaMalloc((void **)dev, std::max<size_t>(1, h.size()) * sizeof(T)));
+  if (!h.empty()) CU_TRY(ctx, cudaMemcpy(*dev, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return HML_OK;
+}
+
+static void split12(u64 h, double *out3) {
+  out3[0] = (double)(h & 0xFFF);
+  out3[1] = (double)((h >> 12) & 0xFFF);
+  out3[2] = (double)(h >> 24);
+}
+
+// ------------------------------------------------------------------------------------------------ creation
+static int ctx_init_device(hml_ctx *ctx) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    ctx->err = std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e);
+    return HML_ERR_CUDA;
+  }
+  if (ctx->device < 0 || ctx->device >= ndev) return fail(ctx, HML_ERR_INVALID, "device index out of range");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const Params &p = ctx->p;
+  const size_t N = p.N, nm = p.n_mod();
+  std::vector<double2> f(nm * N), iv(nm * N);
+  std::vector<ModConst> mc(nm);
+  std::vector<u64> tw;
+  for (uint32_t i = 0; i < nm; ++i) {
+    const u64 q = p.mod[i];
+    const double qd = (double)q;
+    p.twiddles(i, false, tw);
+    for (size_t k = 0; k < N; ++k) f[i * N + k] = make_double2((double)tw[k], (double)tw[k] / qd);
+    p.twiddles(i, true, tw);
+    for (size_t k = 0; k < N; ++k) iv[i * N + k] = make_double2((double)tw[k], (double)tw[k] / qd);
+    mc[i].q = qd; mc[i].qinv = 1.0 / qd;
+    mc[i].ninv = (double)p.n_inv[i]; mc[i].ninv_q = (double)p.n_inv[i] / qd;
+    mc[i].qi = q; mc[i].pad = 0;
+  }
+  int rc;
+  if ((rc = upload(ctx, f, &ctx->tw_fwd))) return rc;
+  if ((rc = upload(ctx, iv, &ctx->tw_inv))) return rc;
+  if ((rc = upload(ctx, mc, &ctx->mc))) return rc;
+  ctx->tabs.fwd = ctx->tw_fwd; ctx->tabs.inv = ctx->tw_inv; ctx->tabs.mc = ctx->mc;
+  return HML_OK;
+}
+
+extern "C" int hml_ctx_create_params(uint32_t N, uint32_t element_bit_width, uint32_t batch_size, uint32_t max_level,
+                                     uint32_t alpha, int device, hml_ctx **out) {
+  if (!out) { g_create_err = "out is null"; return HML_ERR_INVALID; }
+  *out = nullptr;
+  hml_ctx *ctx = new hml_ctx();
+  ctx->device = device;
+  std::string err;
+  if (!ctx->p.init(N, element_bit_width, batch_size, max_level, alpha, err)) {
+    g_create_err = err; delete ctx; return HML_ERR_UNSUPPORTED;
+  }
+  if (max_level + alpha > NTT_MAX_LIMBS) {
+    g_create_err = "maxLevel + alpha > 128 is not supported"; delete ctx; return HML_ERR_UNSUPPORTED;
+  }
+  int rc = ctx_init_device(ctx);
+  if (rc) { g_create_err = ctx->err; hml_ctx_destroy(ctx); return rc; }
+  *out = ctx;
+  return HML_OK;
+}
+
+extern "C" int hml_ctx_create(const char *cfg_path, uint32_t max_level, uint32_t alpha, int device, hml_ctx **out) {
+  if (!out || !cfg_path) { g_create_err = "null argument"; return HML_ERR_INVALID; }
+  *out = nullptr;
+  CfgFile cfg;
+  std::string err;
+  if (!cfg.load(cfg_path, err)) { g_create_err = err; return HML_ERR_CONFIG; }
+  uint32_t N, bs, w;
+  if (!cfg.get("N", N) || !cfg.get("batchSize", bs) || !cfg.get("elementBitWidth", w)) {
+    g_create_err = "Can not find this key! (N, batchSize and elementBitWidth are required)";
+    return HML_ERR_CONFIG;
+  }
+  int rc = hml_ctx_create_params(N, w, bs, max_level, alpha, device, out);
+  if (rc) return rc;
+  (*out)->cfg = cfg; (*out)->has_cfg = true;
+  (*out)->p.bconv_high = cfg.get_or("bconv_num_high", 2);
+  (*out)->p.bconv_width = cfg.get_or("bconv_num_width", 6);
+  return HML_OK;
+}
+
+static void free_level(LevelConsts &lc) {
+  cudaFree(lc.modup_scale); cudaFree(lc.moddown_scale); cudaFree(lc.down_hat3); cudaFree(lc.pinv); cudaFree(lc.qlinv);
+  for (double *p : lc.up_hat3) cudaFree(p);
+}
+
+extern "C" void hml_ctx_destroy(hml_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (auto &kv : ctx->levels) free_level(kv.second);
+  for (auto &kv : ctx->bconv_cache) { cudaFree(kv.second.step1); cudaFree(kv.second.hat3); }
+  cudaFree(ctx->tw_fwd); cudaFree(ctx->tw_inv); cudaFree(ctx->mc); cudaFree(ctx->ws); cudaFree(ctx->stage);
+  if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+  if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
+  if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+  delete ctx;
+}
+
+extern "C" const char *hml_last_error(const hml_ctx *ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+extern "C" const char *hml_last_create_error(void) { return g_create_err.c_str(); }
+extern "C" uint32_t hml_ring_degree(const hml_ctx *ctx) { return ctx->p.N; }
+extern "C" uint32_t hml_n_moduli(const hml_ctx *ctx) { return ctx->p.n_mod(); }
+extern "C" int hml_get_moduli(const hml_ctx *ctx, uint64_t *out, uint32_t cap) {
+  if (!ctx || !out || cap < ctx->p.n_mod()) return HML_ERR_INVALID;
+  for (uint32_t i = 0; i < ctx->p.n_mod(); ++i) out[i] = ctx->p.mod[i];
+  return HML_OK;
+}
+extern "C" int hml_get_roots(const hml_ctx *ctx, uint64_t *out, uint32_t cap) {
+  if (!ctx || !out || cap < ctx->p.n_mod()) return HML_ERR_INVALID;
+  for (uint32_t i = 0; i < ctx->p.n_mod(); ++i) out[i] = ctx->p.psi[i];
+  return HML_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ memory helpers
+extern "C" int hml_dev_alloc(hml_ctx *ctx, uint64_t n_words, uint64_t **out) {
+  if (!ctx || !out) return HML_ERR_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaMalloc((void **)out, std::max<uint64_t>(1, n_words) * 8));
+  return HML_OK;
+}
+extern "C" int hml_dev_free(hml_ctx *ctx, uint64_t *ptr) { CU_TRY(ctx, cudaFree(ptr)); return HML_OK; }
+extern "C" int hml_h2d(hml_ctx *ctx, uint64_t *dst, const uint64_t *src, uint64_t n, void *stream) {
+  CU_TRY(ctx, cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return HML_OK;
+}
+extern "C" int hml_d2h(hml_ctx *ctx, uint64_t *dst, const uint64_t *src, uint64_t n, void *stream) {
+  CU_TRY(ctx, cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return HML_OK;
+}
+extern "C" int hml_sync(hml_ctx *ctx, void *stream) { CU_TRY(ctx, cudaStreamSynchronize((cudaStream_t)stream)); return HML_OK; }
+extern "C" int hml_host_alloc_pinned(hml_ctx *ctx, uint64_t n_words, uint64_t **out) {
+  CU_TRY(ctx, cudaMallocHost((void **)out, std::max<uint64_t>(1, n_words) * 8));
+  return HML_OK;
+}
+extern "C" int hml_host_free_pinned(hml_ctx *ctx, uint64_t *ptr) { CU_TRY(ctx, cudaFreeHost(ptr)); return HML_OK; }
+
+static int ensure_ws(hml_ctx *ctx, size_t words) {
+  if (ctx->ws_words >= words) return HML_OK;
+  // growing the workspace must not race with work already queued on it
+  CU_TRY(ctx, cudaDeviceSynchronize());
+  if (ctx->ws) CU_TRY(ctx, cudaFree(ctx->ws));
+  ctx->ws = nullptr; ctx->ws_words = 0;
+  CU_TRY(ctx, cudaMalloc((void **)&ctx->ws, words * 8));
+  ctx->ws_words = words;
+  return HML_OK;
+}
+
+static int check_launch(hml_ctx *ctx, const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { ctx->err = std::string(what) + ": " + cudaGetErrorString(e); return HML_ERR_CUDA; }
+  return HML_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ per-level constants
+static int get_level(hml_ctx *ctx, uint32_t L, LevelConsts **out) {
+  auto it = ctx->levels.find(L);
+  if (it != ctx->levels.end()) { *out = &it->second; return HML_OK; }
+  const Params &p = ctx->p;
+  const uint32_t A = p.alpha, E = L + A, beta = p.beta(L);
+  LevelConsts lc;
+  lc.L = L; lc.beta = beta; lc.E = E;
+  memset(&lc.q_lm, 0, sizeof(LimbMap)); memset(&lc.p_lm, 0, sizeof(LimbMap));
+  for (uint32_t i = 0; i < L; ++i) { lc.q_lm.mod[i] = i; lc.q_lm.pos[i] = i; }
+  for (uint32_t j = 0; j < A; ++j) { lc.p_lm.mod[j] = p.max_level + j; lc.p_lm.pos[j] = L + j; }
+  int rc;
+  // ---- ModUp
+  std::vector<double2> up_scale(L);
+  LimbMap flat; memset(&flat, 0, sizeof(flat));
+  int nflat = 0;
+  for (uint32_t j = 0; j < beta; ++j) {
+    const uint32_t lo = j * A, aj = p.digit_size(L, j);
+    std::vector<uint32_t> src, dst;
+    for (uint32_t i = 0; i < aj; ++i) src.push_back(lo + i);
+    LimbMap dlm; memset(&dlm, 0, sizeof(dlm));
+    for (uint32_t e = 0; e < E; ++e) {
+      if (e >= lo && e < lo + aj) continue;
+      dlm.mod[dst.size()] = p.ext_mod(L, e);
+      dst.push_back(p.ext_mod(L, e));
+      flat.mod[nflat] = p.ext_mod(L, e); flat.pos[nflat] = j * E + e;
+      if (++nflat == NTT_MAX_LIMBS) { lc.up_ntt_lm.push_back(flat); lc.up_ntt_n.push_back(nflat); nflat = 0; memset(&flat, 0, sizeof(flat)); }
+    }
+    BConvTable bt;
+    make_bconv_table(p, src, dst, bt);
+    for (uint32_t i = 0; i < aj; ++i) {
+      const u64 q = p.mod[lo + i];
+      up_scale[lo + i] = mk_cst(h_mulmod(p.n_inv[lo + i], bt.hat_inv[i], q), q);
+    }
+    std::vector<double> h3(bt.hat.size() * 3);
+    for (size_t k = 0; k < bt.hat.size(); ++k) split12(bt.hat[k], &h3[k * 3]);
+    double *d3 = nullptr;
+    if ((rc = upload(ctx, h3, &d3))) return rc;
+    lc.up_hat3.push_back(d3);
+    lc.up_dst.push_back(dlm);
+  }
+  if (nflat) { lc.up_ntt_lm.push_back(flat); lc.up_ntt_n.push_back(nflat); }
+  if ((rc = upload(ctx, up_scale, &lc.modup_scale))) return rc;
+  // ---- ModDown
+  {
+    std::vector<uint32_t> src, dst;
+    for (uint32_t j = 0; j < A; ++j) src.push_back(p.max_level + j);
+    for (uint32_t i = 0; i < L; ++i) dst.push_back(i);
+    BConvTable bt;
+    make_bconv_table(p, src, dst, bt);
+    std::vector<double2> sc(A), pinv(L);
+    for (uint32_t j = 0; j < A; ++j) {
+      const u64 q = p.mod[p.max_level + j];
+      sc[j] = mk_cst(h_mulmod(p.n_inv[p.max_level + j], bt.hat_inv[j], q), q);
+    }
+    for (uint32_t i = 0; i < L; ++i) {
+      const u64 q = p.mod[i];
+      u64 P = 1;
+      for (uint32_t j = 0; j < A; ++j) P = h_mulmod(P, p.mod[p.max_level + j] % q, q);
+      pinv[i] = mk_cst(h_invmod(P, q), q);
+    }
+    std::vector<double> h3(bt.hat.size() * 3);
+    for (size_t k = 0; k < bt.hat.size(); ++k) split12(bt.hat[k], &h3[k * 3]);
+    if ((rc = upload(ctx, sc, &lc.moddown_scale))) return rc;
+    if ((rc = upload(ctx, h3, &lc.down_hat3))) return rc;
+    if ((rc = upload(ctx, pinv, &lc.pinv))) return rc;
+  }
+  // ---- Rescale
+  {
+    std::vector<double2> ql(L > 1 ? L - 1 : 0);
+    for (uint32_t l = 0; l + 1 < L; ++l) ql[l] = mk_cst(h_invmod(p.mod[L - 1] % p.mod[l], p.mod[l]), p.mod[l]);
+    if ((rc = upload(ctx, ql, &lc.qlinv))) return rc;
+  }
+  auto ins = ctx->levels.emplace(L, lc);
+  *out = &ins.first->second;
+  return HML_OK;
+}
+
+static int check_level(hml_ctx *ctx, uint32_t L, uint32_t min_level) {
+  if (!ctx) return HML_ERR_INVALID;
+  if (L < min_level || L > ctx->p.max_level) return fail(ctx, HML_ERR_INVALID, "currentLevel out of range");
+  return HML_OK;
+}
+
+static void id_map(LimbMap &lm, const uint32_t *mod_idx, uint32_t n) {
+  memset(&lm, 0, sizeof(lm));
+  for (uint32_t i = 0; i < n; ++i) { lm.mod[i] = (uint16_t)mod_idx[i]; lm.pos[i] = (uint16_t)i; }
+}
+
+// ------------------------------------------------------------------------------------------------ primitives
+static int ntt_api(hml_ctx *ctx, bool inverse, const uint64_t *in, uint64_t *out, const uint32_t *mod_idx, uint32_t n_limbs,
+                   void *stream) {
+  if (!ctx || !in || !out || !mod_idx) return HML_ERR_INVALID;
+  const size_t N = ctx->p.N;
+  for (uint32_t i = 0; i < n_limbs; ++i)
+    if (mod_idx[i] >= ctx->p.n_mod()) return fail(ctx, HML_ERR_INVALID, "modulus index out of range");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  for (uint32_t off = 0; off < n_limbs; off += NTT_MAX_LIMBS) {
+    const uint32_t n = std::min<uint32_t>(NTT_MAX_LIMBS, n_limbs - off);
+    LimbMap lm;
+    id_map(lm, mod_idx + off, n);
+    NttLaunch l{};
+    l.in = (const u64 *)in + off * N; l.out = (u64 *)out + off * N;
+    l.in_limb_stride = l.out_limb_stride = N; l.n_limbs = n; l.n_polys = 1; l.post_scale = nullptr;
+    if (inverse) launch_ntt_inverse(ctx->tabs, ctx->p.logN, lm, l, (cudaStream_t)stream);
+    else launch_ntt_forward(ctx->tabs, ctx->p.logN, lm, l, (cudaStream_t)stream);
+    ctx->exec.kernel_launches += ctx->p.logN <= 12 ? 1 : 2;
+  }
+  (inverse ? ctx->exec.intt_limbs : ctx->exec.ntt_limbs) += n_limbs;
+  return check_launch(ctx, inverse ? "intt" : "ntt");
+}
+extern "C" int hml_ntt(hml_ctx *ctx, const uint64_t *in, uint64_t *out, const uint32_t *mod_idx, uint32_t n, void *s) {
+  return ntt_api(ctx, false, in, out, mod_idx, n, s);
+}
+extern "C" int hml_intt(hml_ctx *ctx, const uint64_t *in, uint64_t *out, const uint32_t *mod_idx, uint32_t n, void *s) {
+  return ntt_api(ctx, true, in, out, mod_idx, n, s);
+}
+
+extern "C" int hml_ewe(hml_ctx *ctx, const uint64_t *x1, const uint64_t *x2, const uint64_t *x3, const uint64_t *x4,
+                       int subtract, uint64_t *out, const uint32_t *mod_idx, uint32_t n_limbs, void *stream) {
+  if (!ctx || !out || !mod_idx) return HML_ERR_INVALID;
+  if ((x2 && !x1) || (x4 && !x3)) return fail(ctx, HML_ERR_INVALID, "a multiplier needs its multiplicand");
+  const size_t N = ctx->p.N;
+  for (uint32_t i = 0; i < n_limbs; ++i)
+    if (mod_idx[i] >= ctx->p.n_mod()) return fail(ctx, HML_ERR_INVALID, "modulus index out of range");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  for (uint32_t off = 0; off < n_limbs; off += NTT_MAX_LIMBS) {
+    const uint32_t n = std::min<uint32_t>(NTT_MAX_LIMBS, n_limbs - off);
+    LimbMap lm;
+    id_map(lm, mod_idx + off, n);
+    auto sh = [&](const uint64_t *p) { return p ? (const u64 *)p + off * N : nullptr; };
+    launch_ewe(ctx->mc, lm, (int)N, (int)n, sh(x1), sh(x2), sh(x3), sh(x4), subtract, (u64 *)out + off * N, (cudaStream_t)stream);
+    ctx->exec.kernel_launches++;
+  }
+  ctx->exec.ewe_limbs += n_limbs;
+  return check_launch(ctx, "ewe");
+}
+
+extern "C" int hml_automorph(hml_ctx *ctx, const uint64_t *in, uint64_t *out, uint64_t g, uint32_t n_limbs, void *stream) {
+  if (!ctx || !in || !out || in == out) return HML_ERR_INVALID;
+  if (!(g & 1)) return fail(ctx, HML_ERR_INVALID, "galois element must be odd");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  for (uint32_t off = 0; off < n_limbs; off += 32768) {
+    const uint32_t n = std::min<uint32_t>(32768, n_limbs - off);
+    launch_automorph(ctx->p.logN, n, (const u64 *)in + (size_t)off * ctx->p.N, (u64 *)out + (size_t)off * ctx->p.N, g, (cudaStream_t)stream);
+    ctx->exec.kernel_launches++;
+  }
+  ctx->exec.automorph_limbs += n_limbs;
+  return check_launch(ctx, "automorph");
+}
+
+extern "C" int hml_bconv(hml_ctx *ctx, const uint64_t *in, const uint32_t *src_idx, uint32_t n_src, uint64_t *out,
+                         const uint32_t *dst_idx, uint32_t n_dst, void *stream) {
+  if (!ctx || !in || !out || !src_idx || !dst_idx || !n_src || !n_dst) return HML_ERR_INVALID;
+  if (n_src > NTT_MAX_LIMBS || n_dst > NTT_MAX_LIMBS) return fail(ctx, HML_ERR_UNSUPPORTED, "more than 128 limbs in one conversion");
+  for (uint32_t i = 0; i < n_src; ++i) if (src_idx[i] >= ctx->p.n_mod()) return fail(ctx, HML_ERR_INVALID, "modulus index out of range");
+  for (uint32_t i = 0; i < n_dst; ++i) if (dst_idx[i] >= ctx->p.n_mod()) return fail(ctx, HML_ERR_INVALID, "modulus index out of range");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  std::vector<uint32_t> key(src_idx, src_idx + n_src);
+  key.push_back(0xFFFFFFFFu);
+  key.insert(key.end(), dst_idx, dst_idx + n_dst);
+  auto it = ctx->bconv_cache.find(key);
+  if (it == ctx->bconv_cache.end()) {
+    BConvTable bt;
+    make_bconv_table(ctx->p, std::vector<uint32_t>(src_idx, src_idx + n_src), std::vector<uint32_t>(dst_idx, dst_idx + n_dst), bt);
+    std::vector<double2> s1(n_src);
+    for (uint32_t i = 0; i < n_src; ++i) s1[i] = mk_cst(bt.hat_inv[i], ctx->p.mod[src_idx[i]]);
+    std::vector<double> h3(bt.hat.size() * 3);
+    for (size_t k = 0; k < bt.hat.size(); ++k) split12(bt.hat[k], &h3[k * 3]);
+    DevBConv d;
+    int rc;
+    if ((rc = upload(ctx, s1, &d.step1))) return rc;
+    if ((rc = upload(ctx, h3, &d.hat3))) return rc;
+    it = ctx->bconv_cache.emplace(key, d).first;
+  }
+  LimbMap slm, dlm;
+  id_map(slm, src_idx, n_src);
+  id_map(dlm, dst_idx, n_dst);
+  BConvArgs a{};
+  a.in = (const u64 *)in; a.out = (u64 *)out; a.step1 = it->second.step1; a.hat3 = it->second.hat3;
+  a.N = ctx->p.N; a.n_src = n_src; a.n_dst = n_dst; a.n_batches = 1; a.out_gap_start = n_dst; a.out_gap_len = 0;
+  launch_bconv(ctx->mc, slm, dlm, a, (cudaStream_t)stream);
+  ctx->exec.kernel_launches++;
+  ctx->exec.ewe_limbs += n_src;  // step 1
+  ctx->exec.bconv_limb_macs += (uint64_t)n_src * n_dst;
+  return check_launch(ctx, "bconv");
+}
+
+// ------------------------------------------------------------------------------------------------ key switch
+static size_t ks_ws_words(const Params &p, uint32_t L) {
+  const size_t N = p.N, E = L + p.alpha;
+  return N * (L + (size_t)p.beta(L) * E + 2 * E + 2 * (size_t)L);
+}
+
+// d [L][N] -> out_c = KS_c(d) (+ add_c).  `ws` must hold ks_ws_words().
+static int ks_run(hml_ctx *ctx, uint32_t L, const u64 *d, const u64 *evk, uint32_t evk_q_limbs, u64 *out0, u64 *out1,
+                  const u64 *add0, const u64 *add1, u64 *ws, cudaStream_t s) {
+  const Params &p = ctx->p;
+  if (evk_q_limbs < L || evk_q_limbs > p.max_level) return fail(ctx, HML_ERR_INVALID, "evk_q_limbs must be in [L, maxLevel]");
+  LevelConsts *lc;
+  int rc = get_level(ctx, L, &lc);
+  if (rc) return rc;
+  const size_t N = p.N;
+  const uint32_t A = p.alpha, E = L + A, beta = lc->beta;
+  u64 *yb = ws, *ext = yb + (size_t)L * N, *acc = ext + (size_t)beta * E * N, *vb = acc + 2 * (size_t)E * N;
+  const int logN = p.logN, npass = logN <= 12 ? 1 : 2;
+  // K1 + K2 (reference :63-135): INTT of the input, digit scaling folded into the N^-1 multiply
+  {
+    NttLaunch l{};
+    l.in = d; l.out = yb; l.in_limb_stride = l.out_limb_stride = N; l.n_limbs = L; l.n_polys = 1; l.post_scale = lc->modup_scale;
+    launch_ntt_inverse(ctx->tabs, logN, lc->q_lm, l, s);
+    ctx->exec.intt_limbs += L; ctx->exec.ewe_limbs += 0; ctx->exec.kernel_launches += npass;
+  }
+  // K3 (reference :137-188): convert every digit to the limbs of the extended basis it does not own
+  for (uint32_t j = 0; j < beta; ++j) {
+    const uint32_t lo = j * A, aj = p.digit_size(L, j);
+    BConvArgs a{};
+    a.in = yb + (size_t)lo * N; a.out = ext + (size_t)j * E * N; a.step1 = nullptr; a.hat3 = lc->up_hat3[j];
+    a.N = N; a.n_src = aj; a.n_dst = E - aj; a.n_batches = 1; a.out_gap_start = lo; a.out_gap_len = aj;
+    launch_bconv(ctx->mc, lc->q_lm, lc->up_dst[j], a, s);
+    ctx->exec.bconv_limb_macs += (uint64_t)aj * (E - aj); ctx->exec.kernel_launches++;
+  }
+  // K4 (reference :190-292): NTT of the converted limbs.  The digit's own limbs are the untouched input
+  // (delta D3: the reference also counts an NTT for those).
+  for (size_t c = 0; c < lc->up_ntt_lm.size(); ++c) {
+    NttLaunch l{};
+    l.in = ext; l.out = ext; l.in_limb_stride = l.out_limb_stride = N; l.n_limbs = lc->up_ntt_n[c]; l.n_polys = 1;
+    launch_ntt_forward(ctx->tabs, logN, lc->up_ntt_lm[c], l, s);
+    ctx->exec.ntt_limbs += lc->up_ntt_n[c]; ctx->exec.kernel_launches += npass;
+  }
+  // K5 (reference :294-414): inner product with the key
+  {
+    InnerArgs a{};
+    a.d = d; a.ext = ext; a.evk = evk; a.acc = acc; a.N = N; a.L = L; a.alpha = A; a.beta = beta;
+    a.max_level = p.max_level; a.evk_q_limbs = evk_q_limbs;
+    launch_inner_product(ctx->mc, a, s);
+    ctx->exec.ewe_limbs += 2ull * E * beta; ctx->exec.kernel_launches++;
+  }
+  // K6 + K7 (reference :417-487): INTT of the P-limbs of both accumulators, in place, BConv step 1 folded in
+  {
+    NttLaunch l{};
+    l.in = acc; l.out = acc; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)E * N;
+    l.n_limbs = A; l.n_polys = 2; l.post_scale = lc->moddown_scale;
+    launch_ntt_inverse(ctx->tabs, logN, lc->p_lm, l, s);
+    ctx->exec.intt_limbs += 2 * A; ctx->exec.kernel_launches += npass;
+  }
+  // K8 (reference :489-519): P -> Q_L
+  {
+    BConvArgs a{};
+    a.in = acc + (size_t)L * N; a.out = vb; a.in_batch_stride = (long long)E * N; a.out_batch_stride = (long long)L * N;
+    a.step1 = nullptr; a.hat3 = lc->down_hat3; a.N = N; a.n_src = A; a.n_dst = L; a.n_batches = 2;
+    a.out_gap_start = L; a.out_gap_len = 0;
+    launch_bconv(ctx->mc, lc->p_lm, lc->q_lm, a, s);
+    ctx->exec.bconv_limb_macs += 2ull * A * L; ctx->exec.kernel_launches++;
+  }
+  // K9 (reference :521-546, emitted with opcode INTT — delta D1): forward NTT of the converted limbs
+  {
+    NttLaunch l{};
+    l.in = vb; l.out = vb; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)L * N;
+    l.n_limbs = L; l.n_polys = 2;
+    launch_ntt_forward(ctx->tabs, logN, lc->q_lm, l, s);
+    ctx->exec.ntt_limbs += 2 * L; ctx->exec.kernel_launches += npass;
+  }
+  // K10 (reference :548-590) (+ the caller's addend: HMULT add :967-1005 / HROTATE add :1339-1357)
+  for (int c = 0; c < 2; ++c) {
+    SubMulArgs a{};
+    a.x = acc + (size_t)c * E * N; a.y = vb + (size_t)c * L * N; a.z = c ? add1 : add0; a.out = c ? out1 : out0;
+    a.cst = lc->pinv; a.N = N; a.n_limbs = L; a.n_polys = 1;
+    launch_sub_mul_add(ctx->mc, lc->q_lm, a, s);
+    ctx->exec.ewe_limbs += L + (a.z ? L : 0); ctx->exec.kernel_launches++;
+  }
+  return check_launch(ctx, "keyswitch");
+}
+
+extern "C" int hml_keyswitch(hml_ctx *ctx, uint32_t L, const uint64_t *d, const uint64_t *evk, uint32_t evk_q_limbs,
+                             uint64_t *out0, uint64_t *out1, void *stream) {
+  int rc = check_level(ctx, L, 1);
+  if (rc) return rc;
+  if (!d || !evk || !out0 || !out1) return fail(ctx, HML_ERR_INVALID, "null buffer");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if ((rc = ensure_ws(ctx, ks_ws_words(ctx->p, L)))) return rc;
+  return ks_run(ctx, L, (const u64 *)d, (const u64 *)evk, evk_q_limbs, (u64 *)out0, (u64 *)out1, nullptr, nullptr, ctx->ws,
+                (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ rescale
+static size_t rs_ws_words(const Params &p, uint32_t L, uint32_t n_polys) { return (size_t)p.N * n_polys * L; }
+
+// in: n_polys polys of L limbs (stride in_poly_stride) -> out: n_polys polys of L-1 limbs
+static int rescale_run(hml_ctx *ctx, uint32_t L, const u64 *in, long long in_poly_stride, uint32_t n_polys, u64 *out,
+                       long long out_poly_stride, u64 *ws, cudaStream_t s) {
+  const Params &p = ctx->p;
+  LevelConsts *lc;
+  int rc = get_level(ctx, L, &lc);
+  if (rc) return rc;
+  const size_t N = p.N;
+  const int logN = p.logN, npass = logN <= 12 ? 1 : 2;
+  u64 *rb = ws, *rh = ws + (size_t)n_polys * N;  // rb [n_polys][N], rh [n_polys][L-1][N]
+  {  // INTT of the dropped limb (reference :766-805)
+    LimbMap lm; memset(&lm, 0, sizeof(lm));
+    lm.mod[0] = L - 1; lm.pos[0] = 0;
+    NttLaunch l{};
+    l.in = in + (size_t)(L - 1) * N; l.out = rb; l.in_limb_stride = l.out_limb_stride = N;
+    l.in_poly_stride = in_poly_stride; l.out_poly_stride = N; l.n_limbs = 1; l.n_polys = n_polys;
+    launch_ntt_inverse(ctx->tabs, logN, lm, l, s);
+    ctx->exec.intt_limbs += n_polys; ctx->exec.kernel_launches += npass;
+  }
+  {  // NTT of that polynomial under each remaining modulus (reference :807-822 counts ONE; delta D2)
+    NttLaunch l{};
+    l.in = rb; l.out = rh; l.in_limb_stride = 0; l.out_limb_stride = N; l.in_poly_stride = N;
+    l.out_poly_stride = (long long)(L - 1) * N; l.n_limbs = L - 1; l.n_polys = n_polys;
+    launch_ntt_forward(ctx->tabs, logN, lc->q_lm, l, s);
+    ctx->exec.ntt_limbs += (uint64_t)n_polys * (L - 1); ctx->exec.kernel_launches += npass;
+  }
+  {  // sub + mul (reference :825-911), one fused pass
+    SubMulArgs a{};
+    a.x = in; a.y = rh; a.z = nullptr; a.out = out; a.x_poly_stride = in_poly_stride; a.y_poly_stride = (long long)(L - 1) * N;
+    a.out_poly_stride = out_poly_stride; a.cst = lc->qlinv; a.N = N; a.n_limbs = L - 1; a.n_polys = n_polys;
+    launch_sub_mul_add(ctx->mc, lc->q_lm, a, s);
+    ctx->exec.ewe_limbs += 2ull * n_polys * (L - 1); ctx->exec.kernel_launches++;
+  }
+  return check_launch(ctx, "rescale");
+}
+
+extern "C" int hml_rescale(hml_ctx *ctx, uint32_t L, const uint64_t *in, uint64_t *out, void *stream) {
+  int rc = check_level(ctx, L, 2);
+  if (rc) return rc;
+  if (!in || !out) return fail(ctx, HML_ERR_INVALID, "null buffer");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if ((rc = ensure_ws(ctx, rs_ws_words(ctx->p, L, 1)))) return rc;
+  return rescale_run(ctx, L, (const u64 *)in, 0, 1, (u64 *)out, 0, ctx->ws, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ top-level ops
+static size_t hmult_ws_words(const Params &p, uint32_t L) {
+  return (size_t)p.N * 5 * L + std::max(ks_ws_words(p, L), rs_ws_words(p, L, 2));
+}
+
+static int hmult_run(hml_ctx *ctx, uint32_t L, const u64 *ct_a, const u64 *ct_b, const u64 *evk, uint32_t evk_q_limbs,
+                     u64 *ct_out, cudaStream_t s) {
+  const size_t N = ctx->p.N, PL = N * L;
+  u64 *d0 = ctx->ws, *d1 = d0 + PL, *d2 = d1 + PL, *cb = d2 + PL, *rest = cb + 2 * PL;
+  launch_tensor3(ctx->mc, (int)N, (int)L, ct_a, ct_a + PL, ct_b, ct_b + PL, d0, d1, d2, s);  // reference :592-739
+  ctx->exec.ewe_limbs += 3ull * L; ctx->exec.kernel_launches++;
+  int rc = ks_run(ctx, L, d2, evk, evk_q_limbs, cb, cb + PL, d0, d1, rest, s);
+  if (rc) return rc;
+  return rescale_run(ctx, L, cb, (long long)PL, 2, ct_out, (long long)(L - 1) * N, rest, s);
+}
+
+extern "C" int hml_hmult(hml_ctx *ctx, uint32_t L, const uint64_t *ct_a, const uint64_t *ct_b, const uint64_t *evk,
+                         uint32_t evk_q_limbs, uint64_t *ct_out, void *stream) {
+  int rc = check_level(ctx, L, 2);
+  if (rc) return rc;
+  if (!ct_a || !ct_b || !evk || !ct_out) return fail(ctx, HML_ERR_INVALID, "null buffer");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if ((rc = ensure_ws(ctx, hmult_ws_words(ctx->p, L)))) return rc;
+  return hmult_run(ctx, L, (const u64 *)ct_a, (const u64 *)ct_b, (const u64 *)evk, evk_q_limbs, (u64 *)ct_out, (cudaStream_t)stream);
+}
+
+static size_t hrot_ws_words(const Params &p, uint32_t L) { return (size_t)p.N * 2 * L + ks_ws_words(p, L); }
+
+static int hrot_run(hml_ctx *ctx, uint32_t L, const u64 *ct, const u64 *rk, uint32_t evk_q_limbs, u64 g, u64 *ct_out,
+                    cudaStream_t s) {
+  const size_t N = ctx->p.N, PL = N * L;
+  u64 *sb = ctx->ws, *rest = sb + 2 * PL;
+  launch_automorph(ctx->p.logN, 2 * L, ct, sb, g, s);  // reference :1302-1319
+  ctx->exec.automorph_limbs += 2ull * L; ctx->exec.kernel_launches++;
+  // reference :1326-1357 key-switches AUTOOutput(0) and adds AUTOOutput(1) (naming only, delta D4):
+  // textbook = key-switch sigma(c1), add sigma(c0) to the first output
+  return ks_run(ctx, L, sb + PL, rk, evk_q_limbs, ct_out, ct_out + PL, sb, nullptr, rest, s);
+}
+
+extern "C" int hml_hrotate(hml_ctx *ctx, uint32_t L, const uint64_t *ct, const uint64_t *rotkey, uint32_t evk_q_limbs,
+                           uint64_t galois_elt, uint64_t *ct_out, void *stream) {
+  int rc = check_level(ctx, L, 1);
+  if (rc) return rc;
+  if (!ct || !rotkey || !ct_out) return fail(ctx, HML_ERR_INVALID, "null buffer");
+  if (!(galois_elt & 1)) return fail(ctx, HML_ERR_INVALID, "galois element must be odd");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if ((rc = ensure_ws(ctx, hrot_ws_words(ctx->p, L)))) return rc;
+  return hrot_run(ctx, L, (const u64 *)ct, (const u64 *)rotkey, evk_q_limbs, galois_elt, (u64 *)ct_out, (cudaStream_t)stream);
+}
+
+static int ew_ct_op(hml_ctx *ctx, uint32_t L, const uint64_t *a, const uint64_t *b, bool b_is_pt, bool mul, uint64_t *out, void *stream) {
+  int rc = check_level(ctx, L, 1);
+  if (rc) return rc;
+  if (!a || !b || !out) return fail(ctx, HML_ERR_INVALID, "null buffer");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  LevelConsts *lc;
+  if ((rc = get_level(ctx, L, &lc))) return rc;
+  const size_t N = ctx->p.N, PL = N * L;
+  for (int k = 0; k < 2; ++k) {
+    const u64 *x = (const u64 *)a + k * PL, *y = (const u64 *)b + (b_is_pt ? 0 : k * PL);
+    if (mul) launch_ewe(ctx->mc, lc->q_lm, (int)N, (int)L, x, y, nullptr, nullptr, 0, (u64 *)out + k * PL, (cudaStream_t)stream);
+    else launch_ewe(ctx->mc, lc->q_lm, (int)N, (int)L, x, nullptr, y, nullptr, 0, (u64 *)out + k * PL, (cudaStream_t)stream);
+    ctx->exec.ewe_limbs += L; ctx->exec.kernel_launches++;
+  }
+  return check_launch(ctx, "ewe op");
+}
+extern "C" int hml_hadd(hml_ctx *ctx, uint32_t L, const uint64_t *a, const uint64_t *b, uint64_t *out, void *s) {
+  return ew_ct_op(ctx, L, a, b, false, false, out, s);
+}
+extern "C" int hml_pmult(hml_ctx *ctx, uint32_t L, const uint64_t *ct, const uint64_t *pt, uint64_t *out, void *s) {
+  return ew_ct_op(ctx, L, ct, pt, true, true, out, s);
+}
+extern "C" int hml_padd(hml_ctx *ctx, uint32_t L, const uint64_t *ct, const uint64_t *pt, uint64_t *out, void *s) {
+  return ew_ct_op(ctx, L, ct, pt, true, false, out, s);
+}
+
+// ------------------------------------------------------------------------------------------------ batched
+extern "C" int hml_hmult_batch(hml_ctx *ctx, uint32_t L, uint32_t n, const uint64_t *ct_a, const uint64_t *ct_b,
+                               const uint64_t *evk, uint32_t evk_q_limbs, uint64_t *ct_out, void *stream) {
+  int rc = check_level(ctx, L, 2);
+  if (rc) return rc;
+  if (!ct_a || !ct_b || !evk || !ct_out) return fail(ctx, HML_ERR_INVALID, "null buffer");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if ((rc = ensure_ws(ctx, hmult_ws_words(ctx->p, L)))) return rc;
+  const size_t N = ctx->p.N, in_w = 2 * N * L, out_w = 2 * N * (L - 1);
+  for (uint32_t i = 0; i < n; ++i)
+    if ((rc = hmult_run(ctx, L, (const u64 *)ct_a + i * in_w, (const u64 *)ct_b + i * in_w, (const u64 *)evk, evk_q_limbs,
+                        (u64 *)ct_out + i * out_w, (cudaStream_t)stream)))
+      return rc;
+  return HML_OK;
+}
+
+extern "C" int hml_hrotate_batch(hml_ctx *ctx, uint32_t L, uint32_t n, const uint64_t *ct, const uint64_t *rotkey,
+                                 uint32_t evk_q_limbs, uint64_t galois_elt, uint64_t *ct_out, void *stream) {
+  int rc = check_level(ctx, L, 1);
+  if (rc) return rc;
+  if (!ct || !rotkey || !ct_out) return fail(ctx, HML_ERR_INVALID, "null buffer");
+  if (!(galois_elt & 1)) return fail(ctx, HML_ERR_INVALID, "galois element must be odd");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if ((rc = ensure_ws(ctx, hrot_ws_words(ctx->p, L)))) return rc;
+  const size_t w = 2 * (size_t)ctx->p.N * L;
+  for (uint32_t i = 0; i < n; ++i)
+    if ((rc = hrot_run(ctx, L, (const u64 *)ct + i * w, (const u64 *)rotkey, evk_q_limbs, galois_elt, (u64 *)ct_out + i * w,
+                       (cudaStream_t)stream)))
+      return rc;
+  return HML_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ host-buffer API
+// Three streams (copy-in, compute, copy-out) and two staging slots: the H2D of item i+1 and the D2H of
+// item i-1 overlap the kernels of item i.
+static int host_pipeline(hml_ctx *ctx, bool is_mult, uint32_t L, uint32_t n, const uint64_t *a_host, const uint64_t *b_host,
+                         const uint64_t *key_dev, uint32_t evk_q_limbs, uint64_t g, uint64_t *out_host) {
+  int rc = check_level(ctx, L, is_mult ? 2 : 1);
+  if (rc) return rc;
+  if (!a_host || (is_mult && !b_host) || !key_dev || !out_host) return fail(ctx, HML_ERR_INVALID, "null buffer");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if ((rc = ensure_ws(ctx, is_mult ? hmult_ws_words(ctx->p, L) : hrot_ws_words(ctx->p, L)))) return rc;
+  const size_t N = ctx->p.N, in_w = 2 * N * L, out_w = 2 * N * (is_mult ? L - 1 : L);
+  const size_t slot_w = (is_mult ? 2 : 1) * in_w + out_w;
+  if (ctx->stage_words < 2 * slot_w) {
+    CU_TRY(ctx, cudaDeviceSynchronize());
+    if (ctx->stage) CU_TRY(ctx, cudaFree(ctx->stage));
+    ctx->stage = nullptr; ctx->stage_words = 0;
+    CU_TRY(ctx, cudaMalloc((void **)&ctx->stage, 2 * slot_w * 8));
+    ctx->stage_words = 2 * slot_w;
+  }
+  if (!ctx->s_in) {
+    CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+    CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+  }
+  cudaEvent_t ev_in[2], ev_comp[2], ev_out[2];
+  for (int k = 0; k < 2; ++k) {
+    CU_TRY(ctx, cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
+    CU_TRY(ctx, cudaEventCreateWithFlags(&ev_comp[k], cudaEventDisableTiming));
+    CU_TRY(ctx, cudaEventCreateWithFlags(&ev_out[k], cudaEventDisableTiming));
+  }
+  rc = HML_OK;
+  for (uint32_t i = 0; i < n && rc == HML_OK; ++i) {
+    const int k = i & 1;
+    u64 *sa = ctx->stage + k * slot_w, *sb = sa + in_w, *so = sa + (is_mult ? 2 : 1) * in_w;
+    if (i >= 2) cudaStreamWaitEvent(ctx->s_in, ev_comp[k], 0);  // slot inputs free once item i-2 has been computed
+    cudaMemcpyAsync(sa, a_host + i * in_w, in_w * 8, cudaMemcpyHostToDevice, ctx->s_in);
+    if (is_mult) cudaMemcpyAsync(sb, b_host + i * in_w, in_w * 8, cudaMemcpyHostToDevice, ctx->s_in);
+    cudaEventRecord(ev_in[k], ctx->s_in);
+    cudaStreamWaitEvent(ctx->s_comp, ev_in[k], 0);
+    if (i >= 2) cudaStreamWaitEvent(ctx->s_comp, ev_out[k], 0);  // slot output free once item i-2 has been copied out
+    rc = is_mult ? hmult_run(ctx, L, sa, sb, (const u64 *)key_dev, evk_q_limbs, so, ctx->s_comp)
+                 : hrot_run(ctx, L, sa, (const u64 *)key_dev, evk_q_limbs, g, so, ctx->s_comp);
+    cudaEventRecord(ev_comp[k], ctx->s_comp);
+    cudaStreamWaitEvent(ctx->s_out, ev_comp[k], 0);
+    cudaMemcpyAsync(out_host + i * out_w, so, out_w * 8, cudaMemcpyDeviceToHost, ctx->s_out);
+    cudaEventRecord(ev_out[k], ctx->s_out);
+  }
+  cudaError_t e1 = cudaStreamSynchronize(ctx->s_in), e2 = cudaStreamSynchronize(ctx->s_comp), e3 = cudaStreamSynchronize(ctx->s_out);
+  for (int k = 0; k < 2; ++k) { cudaEventDestroy(ev_in[k]); cudaEventDestroy(ev_comp[k]); cudaEventDestroy(ev_out[k]); }
+  if (rc) return rc;
+  for (cudaError_t e : {e1, e2, e3})
+    if (e != cudaSuccess) return fail(ctx, HML_ERR_CUDA, std::string("host pipeline: ") + cudaGetErrorString(e));
+  return HML_OK;
+}
+
+extern "C" int hml_hmult_host(hml_ctx *ctx, uint32_t L, uint32_t n, const uint64_t *a, const uint64_t *b, const uint64_t *evk_dev,
+                              uint32_t evk_q_limbs, uint64_t *out) {
+  if (!ctx) return HML_ERR_INVALID;
+  return host_pipeline(ctx, true, L, n, a, b, evk_dev, evk_q_limbs, 0, out);
+}
+extern "C" int hml_hrotate_host(hml_ctx *ctx, uint32_t L, uint32_t n, const uint64_t *ct, const uint64_t *rk_dev,
+                                uint32_t evk_q_limbs, uint64_t g, uint64_t *out) {
+  if (!ctx) return HML_ERR_INVALID;
+  if (!(g & 1)) return fail(ctx, HML_ERR_INVALID, "galois element must be odd");
+  return host_pipeline(ctx, false, L, n, ct, nullptr, rk_dev, evk_q_limbs, g, out);
+}
+
+// ------------------------------------------------------------------------------------------------ counts
+extern "C" int hml_trace_counts(const char *op, uint32_t N, uint32_t batch_size, uint32_t max_level, uint32_t L, uint32_t alpha,
+                                uint32_t bconv_high, uint32_t bconv_width, hml_counts *out) {
+  if (!op || !out) return HML_ERR_INVALID;
+  TraceShape s{N, batch_size, max_level, L, alpha, bconv_high, bconv_width};
+  std::vector<StageCount> st;
+  std::string err;
+  memset(out, 0, sizeof(*out));
+  if (!trace_op(op, s, st, err)) {
+    g_create_err = err;
+    const std::string o(op);
+    const bool known = o == "hmult" || o == "hrotate" || o == "hadd" || o == "pmult" || o == "padd";
+    return known ? HML_ERR_INVALID : HML_ERR_OP;
+  }
+  const uint64_t bc = s.batch_count();
+  out->n_stages = (uint32_t)std::min<size_t>(st.size(), HML_MAX_STAGES);
+  for (size_t i = 0; i < st.size(); ++i) {
+    const uint64_t ins = st[i].limb_ops * bc;
+    if (st[i].opcode == "NTT") out->ntt += ins;
+    else if (st[i].opcode == "INTT") out->intt += ins;
+    else if (st[i].opcode == "MULT") out->mult += ins;
+    else if (st[i].opcode == "BCONV_STEP2") out->bconv_step2 += ins;
+    else if (st[i].opcode == "AUTO") out->automorph += ins;
+    if (i < HML_MAX_STAGES) {
+      snprintf(out->stages[i].label, sizeof(out->stages[i].label), "%s", st[i].label.c_str());
+      snprintf(out->stages[i].opcode, sizeof(out->stages[i].opcode), "%s", st[i].opcode.c_str());
+      out->stages[i].limb_ops = st[i].limb_ops;
+      out->stages[i].instructions = ins;
+    }
+  }
+  out->total = out->ntt + out->intt + out->mult + out->bconv_step2 + out->automorph;
+  out->driver_total = out->total - out->bconv_step2 + (uint64_t)bconv_high * bconv_width * out->bconv_step2;
+  return HML_OK;
+}
+
+extern "C" int hml_get_counts(const hml_ctx *ctx, const char *op, uint32_t L, hml_counts *out) {
+  if (!ctx) return HML_ERR_INVALID;
+  const Params &p = ctx->p;
+  return hml_trace_counts(op, p.N, p.batch_size, p.max_level, L, p.alpha, p.bconv_high, p.bconv_width, out);
+}
+
+extern "C" int hml_exec_counts_get(const hml_ctx *ctx, hml_exec_counts *out) {
+  if (!ctx || !out) return HML_ERR_INVALID;
+  *out = ctx->exec;
+  return HML_OK;
+}
+extern "C" int hml_exec_counts_reset(hml_ctx *ctx) {
+  if (!ctx) return HML_ERR_INVALID;
+  memset(&ctx->exec, 0, sizeof(ctx->exec));
+  return HML_OK;
+}

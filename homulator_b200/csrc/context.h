@@ -1,0 +1,68 @@
+// Internal definition of hml_ctx: device tables, per-level constants, workspace, op composition.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/homulator_b200.h"
+#include "config.h"
+#include "ewe.cuh"
+#include "ntt.cuh"
+#include "params.h"
+
+namespace hml {
+
+// Per-level constants of the key-switch / rescale pipeline (SURVEY.md Appendix A "Constant tables").
+struct LevelConsts {
+  uint32_t L = 0, beta = 0, E = 0;
+  // K1+K2 fused: INTT post-scale  N^-1 * (D_j/q_i)^-1 mod q_i  for every input limb i (digit j = i / alpha)
+  double2 *modup_scale = nullptr;            // [L]
+  // K3: per digit, the conversion matrix to the E - a_j other limbs, split in 12-bit pieces
+  std::vector<double *> up_hat3;             // [beta] -> [a_j][E - a_j][3]
+  std::vector<LimbMap> up_dst;               // modulus of each output limb (gap-free numbering)
+  // K4: one flat launch list over all (digit, non-own limb) pairs
+  std::vector<LimbMap> up_ntt_lm;            // chunks of <= NTT_MAX_LIMBS
+  std::vector<int> up_ntt_n;
+  // K6+K7 fused: INTT post-scale N^-1 * (P/p_j)^-1 mod p_j;  K8 matrix [alpha][L][3];  K10 constant P^-1 mod q_i
+  double2 *moddown_scale = nullptr;          // [alpha]
+  double *down_hat3 = nullptr;
+  double2 *pinv = nullptr;                   // [L]
+  // Rescale: q_{L-1}^-1 mod q_l
+  double2 *qlinv = nullptr;                  // [L-1]
+  LimbMap q_lm;                              // limbs 0..L-1 -> moduli q_0..q_{L-1}, pos = limb
+  LimbMap p_lm;                              // limbs 0..alpha-1 -> moduli p_j, pos = L + j (inside an [E][N] buffer)
+};
+
+struct DevBConv {  // cached tables of an arbitrary (src, dst) conversion for the primitive entry point
+  double2 *step1 = nullptr;
+  double *hat3 = nullptr;
+};
+
+}  // namespace hml
+
+struct hml_ctx {
+  hml::Params p;
+  int device = 0;
+  std::string err;
+  hml::CfgFile cfg;
+  bool has_cfg = false;
+
+  double2 *tw_fwd = nullptr, *tw_inv = nullptr;
+  hml::ModConst *mc = nullptr;
+  hml::NttTables tabs{};
+
+  std::map<uint32_t, hml::LevelConsts> levels;
+  std::map<std::vector<uint32_t>, hml::DevBConv> bconv_cache;
+
+  hml::u64 *ws = nullptr;  // workspace, grown on demand
+  size_t ws_words = 0;
+
+  hml_exec_counts exec{};
+
+  // host-buffer API: staging buffers + streams
+  cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+  hml::u64 *stage = nullptr;
+  size_t stage_words = 0;
+};

@@ -1,0 +1,234 @@
+// See ewe.cuh.  All kernels are streaming (HBM-bound) except base conversion (FP64-pipe bound).
+#include "ewe.cuh"
+
+namespace hml {
+
+constexpr int EW_THREADS = 256;  // 2 coefficients per thread, 16-byte accesses
+
+__device__ __forceinline__ ulonglong2 ld2(const u64 *p, size_t i2) { return __ldg(reinterpret_cast<const ulonglong2 *>(p) + i2); }
+__device__ __forceinline__ void st2(u64 *p, size_t i2, u64 a, u64 b) { reinterpret_cast<ulonglong2 *>(p)[i2] = make_ulonglong2(a, b); }
+__device__ __forceinline__ u64 finish(double v, const ModConst &m) { return f64_to_canonical(reduce_signed(v, m.q, m.qinv), m.qi); }
+
+static inline dim3 ew_grid(int N, int ny, int nz = 1) { return dim3((N / 2 + EW_THREADS - 1) / EW_THREADS, ny, nz); }
+
+// ------------------------------------------------------------------------------------------------ generic EWE
+__global__ void __launch_bounds__(EW_THREADS) k_ewe(const ModConst *__restrict__ mc, LimbMap lm, int N, const u64 *x1,
+                                                    const u64 *x2, const u64 *x3, const u64 *x4, int subtract, u64 *out) {
+  const int i2 = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (i2 >= N / 2) return;
+  const int limb = blockIdx.y;
+  const ModConst m = mc[lm.mod[limb]];
+  const size_t o = (size_t)limb * (N / 2) + i2;
+  double p0 = 0, p1 = 0, s0 = 0, s1 = 0;
+  if (x1) {
+    ulonglong2 a = ld2(x1, o);
+    p0 = u64_to_f64(a.x); p1 = u64_to_f64(a.y);
+    if (x2) {
+      ulonglong2 b = ld2(x2, o);
+      p0 = mulmod_var(p0, u64_to_f64(b.x), m.q, m.qinv);
+      p1 = mulmod_var(p1, u64_to_f64(b.y), m.q, m.qinv);
+    }
+  }
+  if (x3) {
+    ulonglong2 a = ld2(x3, o);
+    s0 = u64_to_f64(a.x); s1 = u64_to_f64(a.y);
+    if (x4) {
+      ulonglong2 b = ld2(x4, o);
+      s0 = mulmod_var(s0, u64_to_f64(b.x), m.q, m.qinv);
+      s1 = mulmod_var(s1, u64_to_f64(b.y), m.q, m.qinv);
+    }
+  }
+  if (subtract) { s0 = -s0; s1 = -s1; }
+  st2(out, o, finish(p0 + s0, m), finish(p1 + s1, m));
+}
+
+void launch_ewe(const ModConst *mc, const LimbMap &lm, int N, int n_limbs, const u64 *x1, const u64 *x2, const u64 *x3,
+                const u64 *x4, int subtract, u64 *out, cudaStream_t s) {
+  k_ewe<<<ew_grid(N, n_limbs), EW_THREADS, 0, s>>>(mc, lm, N, x1, x2, x3, x4, subtract, out);
+}
+
+// ------------------------------------------------------------------------------------------------ tensor product
+__global__ void __launch_bounds__(EW_THREADS) k_tensor3(const ModConst *__restrict__ mc, int N, const u64 *a0, const u64 *a1,
+                                                        const u64 *b0, const u64 *b1, u64 *d0, u64 *d1, u64 *d2) {
+  const int i2 = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (i2 >= N / 2) return;
+  const int limb = blockIdx.y;  // limbs 0..L-1 are moduli q_0..q_{L-1}
+  const ModConst m = mc[limb];
+  const size_t o = (size_t)limb * (N / 2) + i2;
+  const ulonglong2 A0 = ld2(a0, o), A1 = ld2(a1, o), B0 = ld2(b0, o), B1 = ld2(b1, o);
+  u64 r0[2], r1[2], r2[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const double x0 = u64_to_f64(k ? A0.y : A0.x), x1 = u64_to_f64(k ? A1.y : A1.x);
+    const double y0 = u64_to_f64(k ? B0.y : B0.x), y1 = u64_to_f64(k ? B1.y : B1.x);
+    r0[k] = f64_to_canonical(mulmod_var(x0, y0, m.q, m.qinv), m.qi);
+    r1[k] = finish(mulmod_var(x0, y1, m.q, m.qinv) + mulmod_var(x1, y0, m.q, m.qinv), m);
+    r2[k] = f64_to_canonical(mulmod_var(x1, y1, m.q, m.qinv), m.qi);
+  }
+  st2(d0, o, r0[0], r0[1]);
+  st2(d1, o, r1[0], r1[1]);
+  st2(d2, o, r2[0], r2[1]);
+}
+
+void launch_tensor3(const ModConst *mc, int N, int L, const u64 *a0, const u64 *a1, const u64 *b0, const u64 *b1, u64 *d0,
+                    u64 *d1, u64 *d2, cudaStream_t s) {
+  k_tensor3<<<ew_grid(N, L), EW_THREADS, 0, s>>>(mc, N, a0, a1, b0, b1, d0, d1, d2);
+}
+
+// ------------------------------------------------------------------------------------------------ key-switch inner product
+__global__ void __launch_bounds__(EW_THREADS) k_inner(const ModConst *__restrict__ mc, InnerArgs a) {
+  const int i2 = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (i2 >= a.N / 2) return;
+  const int e = blockIdx.y, E = a.L + a.alpha;
+  const int mi = e < a.L ? e : a.max_level + (e - a.L);
+  const int kl = e < a.L ? e : a.evk_q_limbs + (e - a.L);
+  const int evk_limbs = a.evk_q_limbs + a.alpha;
+  const ModConst m = mc[mi];
+  const size_t n2 = a.N / 2;
+  double s00 = 0, s01 = 0, s10 = 0, s11 = 0;  // [component][coefficient]
+  for (int j = 0; j < a.beta; ++j) {
+    const bool own = (e >= j * a.alpha) && (e < (j + 1) * a.alpha) && (e < a.L);
+    const u64 *tp = own ? a.d + (size_t)e * a.N : a.ext + ((size_t)j * E + e) * a.N;
+    const ulonglong2 t = ld2(tp, i2);
+    const ulonglong2 k0 = ld2(a.evk, (((size_t)j * 2 + 0) * evk_limbs + kl) * n2 + i2);
+    const ulonglong2 k1 = ld2(a.evk, (((size_t)j * 2 + 1) * evk_limbs + kl) * n2 + i2);
+    const double t0 = u64_to_f64(t.x), t1 = u64_to_f64(t.y);
+    s00 += mulmod_var(t0, u64_to_f64(k0.x), m.q, m.qinv);
+    s01 += mulmod_var(t1, u64_to_f64(k0.y), m.q, m.qinv);
+    s10 += mulmod_var(t0, u64_to_f64(k1.x), m.q, m.qinv);
+    s11 += mulmod_var(t1, u64_to_f64(k1.y), m.q, m.qinv);
+  }
+  st2(a.acc, ((size_t)0 * E + e) * n2 + i2, finish(s00, m), finish(s01, m));
+  st2(a.acc, ((size_t)1 * E + e) * n2 + i2, finish(s10, m), finish(s11, m));
+}
+
+void launch_inner_product(const ModConst *mc, const InnerArgs &a, cudaStream_t s) {
+  k_inner<<<ew_grid(a.N, a.L + a.alpha), EW_THREADS, 0, s>>>(mc, a);
+}
+
+// ------------------------------------------------------------------------------------------------ (x - y) * c (+ z)
+__global__ void __launch_bounds__(EW_THREADS) k_sub_mul_add(const ModConst *__restrict__ mc, LimbMap lm, SubMulArgs a) {
+  const int i2 = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (i2 >= a.N / 2) return;
+  const int limb = blockIdx.y, poly = blockIdx.z;
+  const ModConst m = mc[lm.mod[limb]];
+  const double2 c = a.cst[limb];
+  const size_t o = (size_t)limb * (a.N / 2) + i2;
+  const ulonglong2 x = ld2(a.x + poly * a.x_poly_stride, o), y = ld2(a.y + poly * a.y_poly_stride, o);
+  double r0 = mulmod_const(u64_to_f64(x.x) - u64_to_f64(y.x), c.x, c.y, m.q);
+  double r1 = mulmod_const(u64_to_f64(x.y) - u64_to_f64(y.y), c.x, c.y, m.q);
+  if (a.z) {
+    const ulonglong2 z = ld2(a.z + poly * a.z_poly_stride, o);
+    r0 += u64_to_f64(z.x);
+    r1 += u64_to_f64(z.y);
+  }
+  st2(a.out + poly * a.out_poly_stride, o, finish(r0, m), finish(r1, m));
+}
+
+void launch_sub_mul_add(const ModConst *mc, const LimbMap &lm, const SubMulArgs &a, cudaStream_t s) {
+  k_sub_mul_add<<<ew_grid(a.N, a.n_limbs, a.n_polys), EW_THREADS, 0, s>>>(mc, lm, a);
+}
+
+// ------------------------------------------------------------------------------------------------ automorphism
+__global__ void __launch_bounds__(EW_THREADS) k_automorph(int logN, const u64 *__restrict__ in, u64 *__restrict__ out, unsigned g) {
+  const unsigned N = 1u << logN;
+  const unsigned k = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (k >= N) return;
+  const unsigned j = __brev(k) >> (32 - logN);
+  const unsigned e = (g * (2u * j + 1u)) & (2u * N - 1u);  // low bits of the product are exact
+  const unsigned ks = __brev((e - 1u) >> 1) >> (32 - logN);
+  const size_t base = (size_t)blockIdx.y << logN;
+  out[base + k] = __ldg(&in[base + ks]);
+}
+
+void launch_automorph(int logN, int n_limbs, const u64 *in, u64 *out, u64 g, cudaStream_t s) {
+  const unsigned N = 1u << logN;
+  k_automorph<<<dim3((N + EW_THREADS - 1) / EW_THREADS, n_limbs), EW_THREADS, 0, s>>>(logN, in, out, (unsigned)(g & (2ull * N - 1)));
+}
+
+// ------------------------------------------------------------------------------------------------ base conversion
+constexpr int BC_THREADS = 128;  // 2 coefficients per thread
+constexpr int BC_OT = 8;         // output limbs per CTA
+
+template <bool STEP1>
+__global__ void __launch_bounds__(BC_THREADS) k_bconv(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BConvArgs a) {
+  extern __shared__ double hs[];  // [n_src][BC_OT][3]
+  __shared__ double qs[BC_OT], qinvs[BC_OT];
+  __shared__ u64 qis[BC_OT];
+  const int t0 = blockIdx.y * BC_OT;
+  const int nt = min(BC_OT, a.n_dst - t0);
+  for (int idx = threadIdx.x; idx < a.n_src * BC_OT * 3; idx += BC_THREADS) {
+    const int i = idx / (BC_OT * 3), rem = idx % (BC_OT * 3), o = rem / 3, k = rem % 3;
+    hs[idx] = o < nt ? a.hat3[((size_t)i * a.n_dst + t0 + o) * 3 + k] : 0.0;
+  }
+  if (threadIdx.x < BC_OT) {
+    const ModConst m = mc[dst_lm.mod[min(t0 + (int)threadIdx.x, a.n_dst - 1)]];
+    qs[threadIdx.x] = m.q; qinvs[threadIdx.x] = m.qinv; qis[threadIdx.x] = m.qi;
+  }
+  __syncthreads();
+  const int i2 = blockIdx.x * BC_THREADS + threadIdx.x;
+  if (i2 >= a.N / 2) return;
+  const size_t n2 = a.N / 2;
+  const u64 *in = a.in + (size_t)blockIdx.z * a.in_batch_stride;
+  u64 *out = a.out + (size_t)blockIdx.z * a.out_batch_stride;
+  double acc[BC_OT][3][2];
+#pragma unroll
+  for (int o = 0; o < BC_OT; ++o)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) acc[o][k][0] = acc[o][k][1] = 0.0;
+  for (int i = 0; i < a.n_src; ++i) {
+    const ulonglong2 xv = ld2(in, (size_t)i * n2 + i2);
+    double y0 = u64_to_f64(xv.x), y1 = u64_to_f64(xv.y);
+    if (STEP1) {
+      const ModConst m = mc[src_lm.mod[i]];
+      const double2 sc = a.step1[i];
+      y0 = canonicalize(mulmod_const(y0, sc.x, sc.y, m.q), m.q);
+      y1 = canonicalize(mulmod_const(y1, sc.x, sc.y, m.q), m.q);
+    }
+    const double *h = hs + i * (BC_OT * 3);
+#pragma unroll
+    for (int o = 0; o < BC_OT; ++o)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double hv = h[o * 3 + k];
+        acc[o][k][0] = __fma_rn(y0, hv, acc[o][k][0]);
+        acc[o][k][1] = __fma_rn(y1, hv, acc[o][k][1]);
+      }
+    // each term is < 2^36 * 2^12; fold every 16 sources so the exact sums stay below 2^53
+    if ((i & 15) == 15 && i + 1 < a.n_src) {
+#pragma unroll
+      for (int o = 0; o < BC_OT; ++o)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          acc[o][k][0] = reduce_signed(acc[o][k][0], qs[o], qinvs[o]);
+          acc[o][k][1] = reduce_signed(acc[o][k][1], qs[o], qinvs[o]);
+        }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < BC_OT; ++o) {
+    if (o < nt) {
+      const double q = qs[o], qinv = qinvs[o];
+      u64 r[2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        // value = S2*2^24 + S1*2^12 + S0 (mod q), folded top-down; every intermediate is an exact integer < 2^53
+        double v = reduce_signed(acc[o][2][c], q, qinv);
+        v = reduce_signed(__fma_rn(v, 4096.0, acc[o][1][c]), q, qinv);
+        v = reduce_signed(__fma_rn(v, 4096.0, acc[o][0][c]), q, qinv);
+        r[c] = f64_to_canonical(v, qis[o]);
+      }
+      const int t = t0 + o, slot = t < a.out_gap_start ? t : t + a.out_gap_len;
+      st2(out, (size_t)slot * n2 + i2, r[0], r[1]);
+    }
+  }
+}
+
+void launch_bconv(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, cudaStream_t s) {
+  const dim3 grid((a.N / 2 + BC_THREADS - 1) / BC_THREADS, (a.n_dst + BC_OT - 1) / BC_OT, a.n_batches);
+  const size_t smem = (size_t)a.n_src * BC_OT * 3 * sizeof(double);
+  if (a.step1) k_bconv<true><<<grid, BC_THREADS, smem, s>>>(mc, src_lm, dst_lm, a);
+  else k_bconv<false><<<grid, BC_THREADS, smem, s>>>(mc, src_lm, dst_lm, a);
+}
+
+}  // namespace hml

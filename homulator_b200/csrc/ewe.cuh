@@ -1,0 +1,62 @@
+// Element-wise (EWE), automorphism and base-conversion kernels.  sm_100a, FP64 datapath (modarith.cuh).
+//
+// Reference instruction classes executed here:
+//   MULT         InsGen::GenEWE   reference src/InsGen.cpp:77-125   (unit EWE,   src/Components.cpp:8-169)
+//   AUTO         InsGen::GenAUTO  reference src/InsGen.cpp:46-71    (unit AUTOU, src/Components.cpp:173-266)
+//   BCONV_STEP2  InsGen::GenBCONV reference src/InsGen.cpp:263-313  (unit BCONVU, src/Components.cpp:268-362)
+#pragma once
+#include "modarith.cuh"
+#include "ntt.cuh"
+
+namespace hml {
+
+// out = x1*x2 (+|-) x3*x4 per limb; null operands as in hml_ewe().  All [n_limbs][N].
+void launch_ewe(const ModConst *mc, const LimbMap &lm, int N, int n_limbs, const u64 *x1, const u64 *x2, const u64 *x3,
+                const u64 *x4, int subtract, u64 *out, cudaStream_t s);
+
+// TensorCompute (reference src/Operation.cpp:592-739): d0 = a0*b0, d1 = a0*b1 + a1*b0, d2 = a1*b1; limbs 0..L-1
+void launch_tensor3(const ModConst *mc, int N, int L, const u64 *a0, const u64 *a1, const u64 *b0, const u64 *b1,
+                    u64 *d0, u64 *d1, u64 *d2, cudaStream_t s);
+
+// Key-switch inner product (reference src/Operation.cpp:294-414, emitted as MULT):
+//   acc[c][e] = sum_j t_j[e] * evk[j][c][evk_limb(e)]  for the E = L + alpha extended limbs.
+// t_j[e] is d[e] (the untouched evaluation-form input) when limb e belongs to digit j, else ext[j][e].
+struct InnerArgs {
+  const u64 *d;     // [L][N]
+  const u64 *ext;   // [beta][E][N]
+  const u64 *evk;   // [beta][2][evk_limbs][N]
+  u64 *acc;         // [2][E][N]
+  int N, L, alpha, beta, max_level, evk_q_limbs;
+};
+void launch_inner_product(const ModConst *mc, const InnerArgs &a, cudaStream_t s);
+
+// out = (x - y) * c (+ z) per limb:  ModDownSub (+ HMULT add)  reference src/Operation.cpp:548-590, :967-1005
+// and Rescale sub+mul  reference src/Operation.cpp:825-911.  cst[limb] = (c, RN(c/q)).  n_polys via strides.
+struct SubMulArgs {
+  const u64 *x, *y, *z;   // z may be null
+  u64 *out;
+  long long x_poly_stride, y_poly_stride, z_poly_stride, out_poly_stride;
+  const double2 *cst;     // [n_limbs]
+  int N, n_limbs, n_polys;
+};
+void launch_sub_mul_add(const ModConst *mc, const LimbMap &lm, const SubMulArgs &a, cudaStream_t s);
+
+// out[k] = in[k'],  2*brv(k')+1 = g*(2*brv(k)+1) mod 2N, for n_limbs limbs
+void launch_automorph(int logN, int n_limbs, const u64 *in, u64 *out, u64 g, cudaStream_t s);
+
+// Fast base conversion.  in [n_src][N] coefficient form.  If step1 != nullptr the per-source scaling
+// y_i = in_i * hat_inv_i mod s_i is applied inside (step1[i] = (hat_inv_i, RN(hat_inv_i / s_i)));
+// otherwise `in` must already hold y_i (the fused pipeline folds it into the preceding INTT).
+// hat3: [n_src][n_dst][3] the matrix (D/s_i mod t) split into three 12-bit pieces, as doubles.
+struct BConvArgs {
+  const u64 *in;
+  u64 *out;
+  long long in_batch_stride, out_batch_stride;  // grid.z batches (e.g. the two key-switch accumulators)
+  const double2 *step1;   // [n_src] or null
+  const double *hat3;     // [n_src][n_dst][3]
+  int N, n_src, n_dst, n_batches;
+  int out_gap_start, out_gap_len;  // output limb t is stored at slot t (t < gap_start) or t + gap_len
+};
+void launch_bconv(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, cudaStream_t s);
+
+}  // namespace hml

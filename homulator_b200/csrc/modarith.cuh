@@ -1,0 +1,87 @@
+// Device-side modular arithmetic for word sizes <= 36 bits, carried out on B200's FP64 pipe.
+//
+// Why FP64: measured on B200 (profiles/microbench/butterfly_bench.cu, profiles/microbench_r1.txt)
+//   IMAD.WIDE.U32 / IMAD.HI.U32   32 lane-ops/clk/SM      IMAD (32-bit)   64
+//   IADD3 / LOP3                 128                      DFMA            64
+// A 64-bit Shoup butterfly needs ~10 wide IMADs (870 G butterflies/s measured); the same butterfly on
+// doubles holding exact integers needs 8 DP ops (2027 G butterflies/s measured, 2.3x).  B200 (sm_100a)
+// keeps the full-rate FP64 pipe (B300 does not), so this is a B200-specific choice.
+//
+// Representation: a residue is a double holding an exact integer, either canonical [0,q) or "signed
+// lazy" with |v| < 2^51.  Every operation below is EXACT (no rounding ever reaches a result):
+//   * products a*b are split error-free: h = RN(a*b), l = fma(a,b,-h)  (l is always representable)
+//   * the quotient estimate qh = rint(a*b/q) is off by at most +-1/2 + 2^-9, so the remainder
+//     r = fma(-qh, q, h) + l is an integer of magnitude < 0.51*q + 2^25 < 2^53: exact.
+// Requirements, enforced at context creation: q < 2^36, and the caller keeps |inputs| < 2^44.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace hml {
+
+typedef unsigned long long u64;
+
+// 1.5 * 2^52: adding it to x (|x| < 2^51) rounds x to the nearest integer in the low mantissa bits
+#define HML_MAGIC 6755399441055744.0
+
+// ---- integer <-> double (exact for 0 <= x < 2^52)
+__device__ __forceinline__ double u64_to_f64(u64 x) {
+  // (2^52 | x) reinterpreted is exactly 2^52 + x
+  return __longlong_as_double((long long)(x | 0x4330000000000000ull)) - 4503599627370496.0;
+}
+// signed lazy value (|v| < 2^51, integer) -> canonical [0,q) as u64.  v must already satisfy |v| < q.
+__device__ __forceinline__ u64 f64_to_canonical(double v, u64 q) {
+  long long s = __double_as_longlong(v + HML_MAGIC) - 0x4338000000000000ll;  // exact signed integer
+  return (u64)(s + ((s >> 63) & (long long)q));
+}
+__device__ __forceinline__ double canonicalize(double v, double q) { return v < 0.0 ? v + q : v; }
+
+// ---- v mod q, result in [-q/2 - eps, q/2 + eps]  (|v| < 2^51)
+__device__ __forceinline__ double reduce_signed(double v, double q, double qinv) {
+  double qh = __fma_rn(v, qinv, HML_MAGIC) - HML_MAGIC;
+  return __fma_rn(-qh, q, v);
+}
+
+// ---- a*w mod q with a precomputed wq = RN(w/q) (Shoup-style constant multiplier); signed result, |r| <= 0.51 q
+__device__ __forceinline__ double mulmod_const(double a, double w, double wq, double q) {
+  double qh = __fma_rn(a, wq, HML_MAGIC) - HML_MAGIC;
+  double h = __dmul_rn(a, w);
+  double l = __fma_rn(a, w, -h);
+  double r = __fma_rn(-qh, q, h);
+  return __dadd_rn(r, l);
+}
+
+// ---- a*b mod q, both variable; qinv = RN(1/q); signed result, |r| <= 0.51 q.  |a*b| < 2^88.
+__device__ __forceinline__ double mulmod_var(double a, double b, double q, double qinv) {
+  double h = __dmul_rn(a, b);
+  double l = __fma_rn(a, b, -h);
+  double qh = __fma_rn(h, qinv, HML_MAGIC) - HML_MAGIC;
+  double r = __fma_rn(-qh, q, h);
+  return __dadd_rn(r, l);
+}
+
+// ---- Cooley-Tukey (forward) butterfly: (x, y) -> (x + y*w, x - y*w), growth +0.51q per stage
+__device__ __forceinline__ void ct_butterfly(double &x, double &y, double w, double wq, double q) {
+  double t = mulmod_const(y, w, wq, q);
+  double X = x;
+  x = __dadd_rn(X, t);
+  y = __dsub_rn(X, t);
+}
+// ---- Gentleman-Sande (inverse) butterfly: (x, y) -> (x + y, (x - y)*w); x doubles, y resets to <= 0.51q
+__device__ __forceinline__ void gs_butterfly(double &x, double &y, double w, double wq, double q) {
+  double d = __dsub_rn(x, y);
+  x = __dadd_rn(x, y);
+  y = mulmod_const(d, w, wq, q);
+}
+
+// per-modulus constants kept in device memory
+struct ModConst {
+  double q;       // modulus as double
+  double qinv;    // RN(1/q)
+  double ninv;    // N^-1 mod q
+  double ninv_q;  // RN(ninv / q)
+  u64 qi;         // modulus as integer
+  u64 pad;
+};
+
+}  // namespace hml

@@ -1,0 +1,368 @@
+// See ntt.cuh for the algorithm.  sm_100a only.
+#include "ntt.cuh"
+
+namespace hml {
+
+// ------------------------------------------------------------------------------------------------
+// A "round" = S consecutive radix-2 stages (S <= 3) of a length-2^LOGR sub-NTT, starting at stage ST,
+// executed on 8 register-resident points per thread.  Thread unit u in [0, 2^LOGR / 8) owns 8/2^S
+// butterfly groups of 2^S points each; register r = (group gi, point kk).
+// ------------------------------------------------------------------------------------------------
+template <int LOGR, int ST, int S>
+struct Round {
+  static constexpr int TL = (1 << LOGR) >> (ST + S);  // smallest butterfly distance in the round
+  static constexpr int G = 8 >> S;                    // groups per thread
+  __device__ static __forceinline__ int point(int u, int r) {
+    const int gi = r >> S, kk = r & ((1 << S) - 1);
+    const int g = u * G + gi;
+    const int hi = g / TL, lo = g % TL;
+    return hi * (TL << S) + kk * TL + lo;
+  }
+};
+
+// twiddle index of the butterfly whose lower point is p, at stage i of a sub-NTT whose twiddle block
+// starts at tw_base (1 for the column pass; R1 + row for the row pass): (tw_base << i) + p / (2t)
+// One stage of a round: JS = position in the 3-stage register pattern (distance 4 >> JS).
+template <int LOGR, int ST, int S, int JS, bool INV>
+__device__ __forceinline__ void round_stage(double (&a)[8], int u, const double2 *__restrict__ tw, unsigned tw_base, double q) {
+  using RD = Round<LOGR, ST, S>;
+  constexpr int h = 4 >> JS, i = ST + JS - (3 - S);
+#pragma unroll
+  for (int sg = 0; sg < (1 << JS); ++sg) {
+    const int r0 = sg << (3 - JS);
+    const int p0 = RD::point(u, r0);
+    const double2 w = __ldg(&tw[(tw_base << i) + (p0 >> (LOGR - i))]);
+#pragma unroll
+    for (int o = 0; o < h; ++o) {
+      if constexpr (INV) gs_butterfly(a[r0 + o], a[r0 + o + h], w.x, w.y, q);
+      else ct_butterfly(a[r0 + o], a[r0 + o + h], w.x, w.y, q);
+    }
+  }
+}
+
+template <int LOGR, int ST, int S>
+__device__ __forceinline__ void ct_round(double (&a)[8], int u, const double2 *__restrict__ tw, unsigned tw_base, double q) {
+  if constexpr (S >= 3) round_stage<LOGR, ST, S, 0, false>(a, u, tw, tw_base, q);
+  if constexpr (S >= 2) round_stage<LOGR, ST, S, 1, false>(a, u, tw, tw_base, q);
+  round_stage<LOGR, ST, S, 2, false>(a, u, tw, tw_base, q);
+}
+
+template <int LOGR, int ST, int S>
+__device__ __forceinline__ void gs_round(double (&a)[8], int u, const double2 *__restrict__ tw, unsigned tw_base, double q) {
+  round_stage<LOGR, ST, S, 2, true>(a, u, tw, tw_base, q);
+  if constexpr (S >= 2) round_stage<LOGR, ST, S, 1, true>(a, u, tw, tw_base, q);
+  if constexpr (S >= 3) round_stage<LOGR, ST, S, 0, true>(a, u, tw, tw_base, q);
+}
+
+// round split of a length-2^LOGR sub-NTT: S1 = 3, then S2, S3 (S3 may be 0)
+template <int LOGR> struct Split {
+  static constexpr int S1 = 3;
+  static constexpr int S2 = (LOGR <= 6) ? (LOGR - 3) : (LOGR - 3 + 1) / 2;
+  static constexpr int S3 = LOGR - 3 - S2;
+};
+
+struct LimbCtx {
+  const u64 *in;
+  u64 *out;
+  const double2 *tw;
+  double q, qinv;
+  u64 qi;
+  int limb;
+};
+
+__device__ __forceinline__ LimbCtx limb_ctx(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, bool inverse) {
+  LimbCtx c;
+  const int y = blockIdx.y;
+  c.limb = y % l.n_limbs;
+  const int poly = y / l.n_limbs;
+  const int mi = lm.mod[c.limb];
+  const ModConst mc = t.mc[mi];
+  c.q = mc.q; c.qinv = mc.qinv; c.qi = mc.qi;
+  c.tw = (inverse ? t.inv : t.fwd) + ((size_t)mi << logN);
+  const long long slot = lm.pos[c.limb];
+  c.in = l.in + (long long)poly * l.in_poly_stride + slot * l.in_limb_stride;
+  c.out = l.out + (long long)poly * l.out_poly_stride + slot * l.out_limb_stride;
+  return c;
+}
+
+// ================================================================================ forward, columns
+template <int LOGR1>
+__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_fwd_cols(NttTables t, int logN, LimbMap lm, NttLaunch l) {
+  constexpr int R1 = 1 << LOGR1, C = NTT_TILE / R1, R2 = 1 << NTT_ROW_LOG;
+  using SP = Split<LOGR1>;
+  extern __shared__ double sm[];
+  const LimbCtx lc = limb_ctx(t, logN, lm, l, false);
+  const int c = threadIdx.x % C, u = threadIdx.x / C;
+  const int col = blockIdx.x * C + c;
+  double a[8];
+  {
+    using RD = Round<LOGR1, 0, SP::S1>;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) a[r] = u64_to_f64(__ldg(&lc.in[(size_t)RD::point(u, r) * R2 + col]));
+    ct_round<LOGR1, 0, SP::S1>(a, u, lc.tw, 1u, lc.q);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sm[RD::point(u, r) * C + c] = a[r];
+  }
+  __syncthreads();
+  double *outd = reinterpret_cast<double *>(lc.out);
+  if constexpr (SP::S3 == 0) {
+    using RD = Round<LOGR1, SP::S1, SP::S2>;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(u, r) * C + c];
+    ct_round<LOGR1, SP::S1, SP::S2>(a, u, lc.tw, 1u, lc.q);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) outd[(size_t)RD::point(u, r) * R2 + col] = a[r];
+  } else {
+    {
+      using RD = Round<LOGR1, SP::S1, SP::S2>;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(u, r) * C + c];
+      ct_round<LOGR1, SP::S1, SP::S2>(a, u, lc.tw, 1u, lc.q);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) sm[RD::point(u, r) * C + c] = a[r];
+    }
+    __syncthreads();
+    using RD = Round<LOGR1, SP::S1 + SP::S2, SP::S3>;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(u, r) * C + c];
+    ct_round<LOGR1, SP::S1 + SP::S2, SP::S3>(a, u, lc.tw, 1u, lc.q);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) outd[(size_t)RD::point(u, r) * R2 + col] = a[r];
+  }
+}
+
+// ================================================================================ forward, rows
+// 16 contiguous rows of 256 per CTA.  smem [256][17]: point-major, row (=sub-NTT id) minor.
+constexpr int ROWS = NTT_TILE >> NTT_ROW_LOG;  // 16
+constexpr int RP = ROWS + 1;                   // pitch
+
+__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_fwd_rows(NttTables t, int logN, LimbMap lm, NttLaunch l) {
+  constexpr int LR = NTT_ROW_LOG, R2 = 1 << LR;
+  __shared__ double sm[R2 * RP];
+  const LimbCtx lc = limb_ctx(t, logN, lm, l, false);
+  const unsigned R1 = 1u << (logN - LR);
+  const int row0 = blockIdx.x * ROWS;
+  double a[8];
+  const double *ind = reinterpret_cast<const double *>(lc.out);  // pass 1 left raw doubles in `out`
+  {  // round (0,3): one warp per row, coalesced
+    const int u = threadIdx.x % 32, n = threadIdx.x / 32;
+    using RD = Round<LR, 0, 3>;
+    const size_t base = (size_t)(row0 + n) * R2;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) a[r] = ind[base + RD::point(u, r)];
+    ct_round<LR, 0, 3>(a, u, lc.tw, R1 + row0 + n, lc.q);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sm[RD::point(u, r) * RP + n] = a[r];
+  }
+  __syncthreads();
+  const int c = threadIdx.x % ROWS, u = threadIdx.x / ROWS;
+  {
+    using RD = Round<LR, 3, 3>;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(u, r) * RP + c];
+    ct_round<LR, 3, 3>(a, u, lc.tw, R1 + row0 + c, lc.q);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sm[RD::point(u, r) * RP + c] = a[r];
+  }
+  __syncthreads();
+  {
+    using RD = Round<LR, 6, 2>;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(u, r) * RP + c];
+    ct_round<LR, 6, 2>(a, u, lc.tw, R1 + row0 + c, lc.q);
+    u64 *smu = reinterpret_cast<u64 *>(sm);
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      smu[RD::point(u, r) * RP + c] = f64_to_canonical(reduce_signed(a[r], lc.q, lc.qinv), lc.qi);
+  }
+  __syncthreads();
+  {  // coalesced store, one warp per row
+    const int uu = threadIdx.x % 32, n = threadIdx.x / 32;
+    const u64 *smu = reinterpret_cast<const u64 *>(sm);
+    const size_t base = (size_t)(row0 + n) * R2;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) lc.out[base + r * 32 + uu] = smu[(r * 32 + uu) * RP + n];
+  }
+}
+
+// ================================================================================ inverse, rows (first)
+__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_inv_rows(NttTables t, int logN, LimbMap lm, NttLaunch l) {
+  constexpr int LR = NTT_ROW_LOG, R2 = 1 << LR;
+  __shared__ double sm[R2 * RP];
+  const LimbCtx lc = limb_ctx(t, logN, lm, l, true);
+  const unsigned R1 = 1u << (logN - LR);
+  const int row0 = blockIdx.x * ROWS;
+  double a[8];
+  {
+    const int uu = threadIdx.x % 32, n = threadIdx.x / 32;
+    const size_t base = (size_t)(row0 + n) * R2;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sm[(r * 32 + uu) * RP + n] = u64_to_f64(__ldg(&lc.in[base + r * 32 + uu]));
+  }
+  __syncthreads();
+  const int c = threadIdx.x % ROWS, u = threadIdx.x / ROWS;
+  {
+    using RD = Round<LR, 6, 2>;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(u, r) * RP + c];
+    gs_round<LR, 6, 2>(a, u, lc.tw, R1 + row0 + c, lc.q);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sm[RD::point(u, r) * RP + c] = a[r];
+  }
+  __syncthreads();
+  {
+    using RD = Round<LR, 3, 3>;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(u, r) * RP + c];
+    gs_round<LR, 3, 3>(a, u, lc.tw, R1 + row0 + c, lc.q);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sm[RD::point(u, r) * RP + c] = a[r];
+  }
+  __syncthreads();
+  {
+    const int uu = threadIdx.x % 32, n = threadIdx.x / 32;
+    using RD = Round<LR, 0, 3>;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(uu, r) * RP + n];
+    gs_round<LR, 0, 3>(a, uu, lc.tw, R1 + row0 + n, lc.q);
+    double *outd = reinterpret_cast<double *>(lc.out);
+    const size_t base = (size_t)(row0 + n) * R2;
+    // the sums have grown to <= 2^8 q: bring them back to |v| <= q/2 before the column pass doubles them again
+#pragma unroll
+    for (int r = 0; r < 8; ++r) outd[base + RD::point(uu, r)] = reduce_signed(a[r], lc.q, lc.qinv);
+  }
+}
+
+// ================================================================================ inverse, columns (second)
+template <int LOGR1>
+__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_inv_cols(NttTables t, int logN, LimbMap lm, NttLaunch l) {
+  constexpr int R1 = 1 << LOGR1, C = NTT_TILE / R1, R2 = 1 << NTT_ROW_LOG;
+  using SP = Split<LOGR1>;
+  extern __shared__ double sm[];
+  const LimbCtx lc = limb_ctx(t, logN, lm, l, true);
+  const int c = threadIdx.x % C, u = threadIdx.x / C;
+  const int col = blockIdx.x * C + c;
+  const double *ind = reinterpret_cast<const double *>(lc.out);
+  double a[8];
+  if constexpr (SP::S3 != 0) {
+    {
+      using RD = Round<LOGR1, SP::S1 + SP::S2, SP::S3>;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) a[r] = ind[(size_t)RD::point(u, r) * R2 + col];
+      gs_round<LOGR1, SP::S1 + SP::S2, SP::S3>(a, u, lc.tw, 1u, lc.q);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) sm[RD::point(u, r) * C + c] = a[r];
+    }
+    __syncthreads();
+    using RD = Round<LOGR1, SP::S1, SP::S2>;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(u, r) * C + c];
+    gs_round<LOGR1, SP::S1, SP::S2>(a, u, lc.tw, 1u, lc.q);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sm[RD::point(u, r) * C + c] = a[r];
+  } else {
+    using RD = Round<LOGR1, SP::S1, SP::S2>;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) a[r] = ind[(size_t)RD::point(u, r) * R2 + col];
+    gs_round<LOGR1, SP::S1, SP::S2>(a, u, lc.tw, 1u, lc.q);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sm[RD::point(u, r) * C + c] = a[r];
+  }
+  __syncthreads();
+  using RD = Round<LOGR1, 0, SP::S1>;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(u, r) * C + c];
+  gs_round<LOGR1, 0, SP::S1>(a, u, lc.tw, 1u, lc.q);
+  double2 sc;
+  if (l.post_scale) sc = l.post_scale[lc.limb];
+  else { const ModConst mc = t.mc[lm.mod[lc.limb]]; sc = make_double2(mc.ninv, mc.ninv_q); }
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+    lc.out[(size_t)RD::point(u, r) * R2 + col] = f64_to_canonical(mulmod_const(a[r], sc.x, sc.y, lc.q), lc.qi);
+}
+
+// ================================================================================ small N (<= 4096): one CTA per limb
+__global__ void __launch_bounds__(256) ntt_small(NttTables t, int logN, LimbMap lm, NttLaunch l, int inverse) {
+  extern __shared__ double sm[];
+  const LimbCtx lc = limb_ctx(t, logN, lm, l, inverse != 0);
+  const int N = 1 << logN, half = N >> 1;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sm[i] = u64_to_f64(__ldg(&lc.in[i]));
+  __syncthreads();
+  if (!inverse) {
+    for (int s = 0; s < logN; ++s) {
+      const int tt = N >> (s + 1);
+      for (int b = threadIdx.x; b < half; b += blockDim.x) {
+        const int grp = b / tt, j = b % tt, i0 = grp * 2 * tt + j;
+        const double2 w = __ldg(&lc.tw[(1 << s) + grp]);
+        double x = sm[i0], y = sm[i0 + tt];
+        ct_butterfly(x, y, w.x, w.y, lc.q);
+        sm[i0] = x; sm[i0 + tt] = y;
+      }
+      __syncthreads();
+    }
+    for (int i = threadIdx.x; i < N; i += blockDim.x)
+      lc.out[i] = f64_to_canonical(reduce_signed(sm[i], lc.q, lc.qinv), lc.qi);
+  } else {
+    for (int s = logN - 1; s >= 0; --s) {
+      const int tt = N >> (s + 1);
+      for (int b = threadIdx.x; b < half; b += blockDim.x) {
+        const int grp = b / tt, j = b % tt, i0 = grp * 2 * tt + j;
+        const double2 w = __ldg(&lc.tw[(1 << s) + grp]);
+        double x = sm[i0], y = sm[i0 + tt];
+        gs_butterfly(x, y, w.x, w.y, lc.q);
+        if (((logN - s) & 3) == 0) { x = reduce_signed(x, lc.q, lc.qinv); }  // bound the doubling every 4 stages
+        sm[i0] = x; sm[i0 + tt] = y;
+      }
+      __syncthreads();
+    }
+    double2 sc;
+    if (l.post_scale) sc = l.post_scale[lc.limb];
+    else { const ModConst mc = t.mc[lm.mod[lc.limb]]; sc = make_double2(mc.ninv, mc.ninv_q); }
+    for (int i = threadIdx.x; i < N; i += blockDim.x)
+      lc.out[i] = f64_to_canonical(mulmod_const(sm[i], sc.x, sc.y, lc.q), lc.qi);
+  }
+}
+
+// ================================================================================ host launchers
+template <int LOGR1>
+static void launch_fwd_t(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
+  constexpr int C = NTT_TILE >> LOGR1;
+  const dim3 g1((1 << NTT_ROW_LOG) / C, l.n_limbs * l.n_polys), g2((1 << LOGR1) / ROWS, l.n_limbs * l.n_polys);
+  ntt_fwd_cols<LOGR1><<<g1, NTT_THREADS, NTT_TILE * sizeof(double), s>>>(t, logN, lm, l);
+  ntt_fwd_rows<<<g2, NTT_THREADS, 0, s>>>(t, logN, lm, l);
+}
+template <int LOGR1>
+static void launch_inv_t(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
+  constexpr int C = NTT_TILE >> LOGR1;
+  const dim3 g1((1 << LOGR1) / ROWS, l.n_limbs * l.n_polys), g2((1 << NTT_ROW_LOG) / C, l.n_limbs * l.n_polys);
+  ntt_inv_rows<<<g1, NTT_THREADS, 0, s>>>(t, logN, lm, l);
+  ntt_inv_cols<LOGR1><<<g2, NTT_THREADS, NTT_TILE * sizeof(double), s>>>(t, logN, lm, l);
+}
+
+void launch_ntt_forward(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
+  if (logN <= 12) {
+    ntt_small<<<dim3(1, l.n_limbs * l.n_polys), 256, sizeof(double) << logN, s>>>(t, logN, lm, l, 0);
+    return;
+  }
+  switch (logN - NTT_ROW_LOG) {
+    case 5: launch_fwd_t<5>(t, logN, lm, l, s); break;
+    case 6: launch_fwd_t<6>(t, logN, lm, l, s); break;
+    case 7: launch_fwd_t<7>(t, logN, lm, l, s); break;
+    case 8: launch_fwd_t<8>(t, logN, lm, l, s); break;
+  }
+}
+
+void launch_ntt_inverse(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
+  if (logN <= 12) {
+    ntt_small<<<dim3(1, l.n_limbs * l.n_polys), 256, sizeof(double) << logN, s>>>(t, logN, lm, l, 1);
+    return;
+  }
+  switch (logN - NTT_ROW_LOG) {
+    case 5: launch_inv_t<5>(t, logN, lm, l, s); break;
+    case 6: launch_inv_t<6>(t, logN, lm, l, s); break;
+    case 7: launch_inv_t<7>(t, logN, lm, l, s); break;
+    case 8: launch_inv_t<8>(t, logN, lm, l, s); break;
+  }
+}
+
+}  // namespace hml

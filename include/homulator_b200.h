@@ -1,0 +1,182 @@
+/*
+ * homulator_b200 — C ABI of the B200-native RNS-CKKS primitive datapath.
+ *
+ * The reference (FHE-ACCELE/Homulator) has NO plugin / FFI interface: its boundary is the CLI
+ * (reference bench_test/bench_micro24.cpp:5-52) wrapping five C++ op objects
+ *     OP(std::string label, uint32_t maxLevel, uint32_t currentLevel, uint32_t alpha, Config*, Arch*)
+ *     bool OP::simulate()                OP in {HMULT, HROTATE, HADD, PMULT, PADD}
+ * (reference include/Operation.h:200-203, 229-232, 258-261, 287-290, 316-319), whose constructors
+ * decompose the op into NTT / INTT / MULT(EWE) / BCONV_STEP2 / AUTO instruction streams
+ * (reference src/Operation.cpp, src/InsGen.cpp) that the rest of the reference only *times*.
+ * This ABI is the boundary a maintainer would bind in their place: the same ops, executed on real
+ * data on the GPU, plus the per-op instruction counts of the reference's trace.
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the boundary: every call returns an hml_status; the message for the
+ *     last failure is hml_last_error(ctx) (hml_last_create_error() when no ctx exists yet).
+ *   - a ctx is bound to one CUDA device and is NOT thread-safe (the reference is single-threaded and
+ *     not re-entrant either: globals at reference src/Instruction.cpp:3, src/Operation.cpp:7).
+ *   - all polynomial buffers are DEVICE pointers to uint64_t (reference include/Context.h:8
+ *     `DataType = uint64_t`), caller-owned, residues < 2^elementBitWidth, layout [.. ][limb][N],
+ *     a ciphertext is [2][L][N] (c0 limbs, then c1 limbs), in EVALUATION form:
+ *         slot k of limb i holds a(psi_i^(2*bitrev(k)+1)) mod q_i      (bitrev over log2 N bits)
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous.
+ *   - modulus indices: 0..maxLevel-1 are q_i, maxLevel..maxLevel+alpha-1 are p_j.  The moduli are all
+ *     primes = 1 (mod 2N) in (2^(w-1), 2^w), w = elementBitWidth, scanned downward from 2^w.
+ *   - evaluation / rotation key layout: [beta][2][evk_q_limbs + alpha][N], Q-limbs first then the alpha
+ *     P-limbs; evk_q_limbs is L (the compact per-level layout the reference allocates,
+ *     reference src/Operation.cpp:300-304 `IP_Key{c}_{j}` of Level+Alpha limbs) or maxLevel.
+ *   - there is NO CPU fallback: every compute entry point fails with HML_ERR_CUDA when no device
+ *     is usable.
+ */
+#ifndef HOMULATOR_B200_H
+#define HOMULATOR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hml_ctx hml_ctx;
+
+typedef enum {
+  HML_OK = 0,
+  HML_ERR_INVALID = 1,     /* bad argument (level out of range, null pointer, ...) */
+  HML_ERR_CONFIG = 2,      /* config file missing / key missing (reference: uncaught runtime_error, Config.h:14-20) */
+  HML_ERR_CUDA = 3,        /* CUDA runtime failure, or no device */
+  HML_ERR_UNSUPPORTED = 4, /* parameter outside what the kernels implement */
+  HML_ERR_OP = 5           /* unknown operation name (reference: bench_micro24.cpp:49-51) */
+} hml_status;
+
+/* ------------------------------------------------------------------ context
+ * Replaces `new Config(path)` + `new Arch(config)` (reference bench_micro24.cpp:16-27).  Reads N,
+ * elementBitWidth, batchSize, bconv_num_high/width from the .cfg (format of reference src/Config.cpp:16-37);
+ * every other key is accepted and ignored.  maxLevel and alpha are CLI arguments in the reference. */
+int hml_ctx_create(const char *cfg_path, uint32_t max_level, uint32_t alpha, int device, hml_ctx **out);
+int hml_ctx_create_params(uint32_t N, uint32_t element_bit_width, uint32_t batch_size, uint32_t max_level,
+                          uint32_t alpha, int device, hml_ctx **out);
+void hml_ctx_destroy(hml_ctx *ctx);
+const char *hml_last_error(const hml_ctx *ctx);
+const char *hml_last_create_error(void);
+
+uint32_t hml_ring_degree(const hml_ctx *ctx);
+uint32_t hml_n_moduli(const hml_ctx *ctx);
+int hml_get_moduli(const hml_ctx *ctx, uint64_t *out, uint32_t cap); /* q_0.., then p_0.. */
+int hml_get_roots(const hml_ctx *ctx, uint64_t *out, uint32_t cap);  /* psi per modulus */
+
+/* device-memory helpers so a host without the CUDA runtime (cgo / JNI / ctypes) can drive the library */
+int hml_dev_alloc(hml_ctx *ctx, uint64_t n_words, uint64_t **out);
+int hml_dev_free(hml_ctx *ctx, uint64_t *ptr);
+int hml_h2d(hml_ctx *ctx, uint64_t *dst_dev, const uint64_t *src_host, uint64_t n_words, void *stream);
+int hml_d2h(hml_ctx *ctx, uint64_t *dst_host, const uint64_t *src_dev, uint64_t n_words, void *stream);
+int hml_sync(hml_ctx *ctx, void *stream);
+
+/* ------------------------------------------------------------------ primitives
+ * One entry point per instruction class of the reference (reference include/Instruction.h:6-20; only
+ * NTT, INTT, MULT, BCONV_STEP2, AUTO are ever generated).  Each call processes n_limbs whole limbs
+ * (= n_limbs * N/batchSize reference instructions). mod_idx is a HOST array of n_limbs modulus indices. */
+
+/* replaces InsGen::GenNTT(ntt=true/false)  (reference src/InsGen.cpp:17-44).  in == out allowed. */
+int hml_ntt(hml_ctx *ctx, const uint64_t *in, uint64_t *out, const uint32_t *mod_idx, uint32_t n_limbs, void *stream);
+int hml_intt(hml_ctx *ctx, const uint64_t *in, uint64_t *out, const uint32_t *mod_idx, uint32_t n_limbs, void *stream);
+
+/* replaces InsGen::GenEWE (reference src/InsGen.cpp:77-125): out = x1*x2 (+|-) x3*x4 mod m per limb.
+ * NULL x2/x4: multiplier 1.  NULL x1/x3: that product is absent (the reference's "address 0",
+ * src/mem.cpp:30).  Each operand is [n_limbs][N]. */
+int hml_ewe(hml_ctx *ctx, const uint64_t *x1, const uint64_t *x2, const uint64_t *x3, const uint64_t *x4, int subtract,
+            uint64_t *out, const uint32_t *mod_idx, uint32_t n_limbs, void *stream);
+
+/* replaces InsGen::GenAUTO (reference src/InsGen.cpp:46-71): out[k] = in[k'],
+ * 2*bitrev(k')+1 = galois_elt*(2*bitrev(k)+1) mod 2N, on n_limbs evaluation-form limbs. in != out. */
+int hml_automorph(hml_ctx *ctx, const uint64_t *in, uint64_t *out, uint64_t galois_elt, uint32_t n_limbs, void *stream);
+
+/* replaces BConv step 1 (a MULT in the reference, src/Operation.cpp:104-135, :447-487) + step 2
+ * (InsGen::GenBCONV, src/InsGen.cpp:263-313): in [n_src][N] coefficient form over moduli src_idx,
+ * out [n_dst][N]: out_m = sum_i [in_i * (D/s_i)^-1]_{s_i} * [D/s_i]_m mod m, no overflow correction. */
+int hml_bconv(hml_ctx *ctx, const uint64_t *in, const uint32_t *src_idx, uint32_t n_src, uint64_t *out,
+              const uint32_t *dst_idx, uint32_t n_dst, void *stream);
+
+/* ------------------------------------------------------------------ sub-operations */
+/* replaces KeySwitch::KeySwitch (reference src/Operation.cpp:9-54, stages :63-590).
+ * d [L][N] -> out0,out1 [L][N]. */
+int hml_keyswitch(hml_ctx *ctx, uint32_t L, const uint64_t *d, const uint64_t *evk, uint32_t evk_q_limbs,
+                  uint64_t *out0, uint64_t *out1, void *stream);
+/* replaces Rescale::Rescale (reference src/Operation.cpp:741-911): in [L][N] -> out [L-1][N]. */
+int hml_rescale(hml_ctx *ctx, uint32_t L, const uint64_t *in, uint64_t *out, void *stream);
+
+/* ------------------------------------------------------------------ operations (reference include/Operation.h) */
+/* HMULT (reference src/Operation.cpp:913-1023): tensor + keyswitch(relinearise) + add + rescale x2.
+ * ct_a, ct_b [2][L][N]; ct_out [2][L-1][N].  Requires L >= 2 (the reference segfaults at L=1). */
+int hml_hmult(hml_ctx *ctx, uint32_t L, const uint64_t *ct_a, const uint64_t *ct_b, const uint64_t *evk,
+              uint32_t evk_q_limbs, uint64_t *ct_out, void *stream);
+/* HROTATE (reference src/Operation.cpp:1271-1358): automorphism of both polys + keyswitch + add.
+ * The reference takes no rotation amount; galois_elt is the one addition (5^r mod 2N; r=1 -> 5).
+ * ct [2][L][N] -> ct_out [2][L][N] = (sigma(c0) + ks0, ks1), ks = KeySwitch(sigma(c1)). */
+int hml_hrotate(hml_ctx *ctx, uint32_t L, const uint64_t *ct, const uint64_t *rotkey, uint32_t evk_q_limbs,
+                uint64_t galois_elt, uint64_t *ct_out, void *stream);
+/* HADD / PMULT / PADD (reference src/Operation.cpp:1114-1176, :1453-1523, :1618-1680).  pt is [L][N].
+ * PADD adds the plaintext to BOTH components, as the reference's trace does (:1650-1672). */
+int hml_hadd(hml_ctx *ctx, uint32_t L, const uint64_t *ct_a, const uint64_t *ct_b, uint64_t *ct_out, void *stream);
+int hml_pmult(hml_ctx *ctx, uint32_t L, const uint64_t *ct, const uint64_t *pt, uint64_t *ct_out, void *stream);
+int hml_padd(hml_ctx *ctx, uint32_t L, const uint64_t *ct, const uint64_t *pt, uint64_t *ct_out, void *stream);
+
+/* Batched, data-parallel over independent ciphertexts sharing one key (BASELINE.json configs[3]).
+ * ct_a, ct_b [n][2][L][N]; ct_out [n][2][L-1][N] (hmult) / [n][2][L][N] (hrotate). */
+int hml_hmult_batch(hml_ctx *ctx, uint32_t L, uint32_t n, const uint64_t *ct_a, const uint64_t *ct_b,
+                    const uint64_t *evk, uint32_t evk_q_limbs, uint64_t *ct_out, void *stream);
+int hml_hrotate_batch(hml_ctx *ctx, uint32_t L, uint32_t n, const uint64_t *ct, const uint64_t *rotkey,
+                      uint32_t evk_q_limbs, uint64_t galois_elt, uint64_t *ct_out, void *stream);
+
+/* Host-buffer variants (the "call a user makes" with data in host memory): pinned or pageable HOST
+ * pointers for the ciphertexts, key resident on the device.  Copies are pipelined against compute on
+ * internal streams; the call returns when ct_out_host is complete. */
+int hml_hmult_host(hml_ctx *ctx, uint32_t L, uint32_t n, const uint64_t *ct_a_host, const uint64_t *ct_b_host,
+                   const uint64_t *evk_dev, uint32_t evk_q_limbs, uint64_t *ct_out_host);
+int hml_hrotate_host(hml_ctx *ctx, uint32_t L, uint32_t n, const uint64_t *ct_host, const uint64_t *rotkey_dev,
+                     uint32_t evk_q_limbs, uint64_t galois_elt, uint64_t *ct_out_host);
+int hml_host_alloc_pinned(hml_ctx *ctx, uint64_t n_words, uint64_t **out);
+int hml_host_free_pinned(hml_ctx *ctx, uint64_t *ptr);
+
+/* ------------------------------------------------------------------ the count contract
+ * Instruction counts of the reference's InsGen trace for one op (what `new OP(...)` generates,
+ * reference src/Operation.cpp), computed by walking the same stage list.  One instruction = batchSize
+ * coefficients of one limb (reference src/InsGen.cpp:9-13); limb_ops = instructions / (N/batchSize).
+ * Pure host code: needs no device, so hml_trace_counts can be called without a ctx. */
+#define HML_MAX_STAGES 48
+typedef struct {
+  char label[48];        /* stage label as embedded in the reference's Instruction::Name */
+  char opcode[16];       /* NTT | INTT | MULT | BCONV_STEP2 | AUTO */
+  uint64_t limb_ops;
+  uint64_t instructions;
+} hml_stage_count;
+typedef struct {
+  uint64_t ntt, intt, mult, bconv_step2, automorph;
+  uint64_t total;        /* sum of the five */
+  uint64_t driver_total; /* Driver::getTotalIns(): BCONV replicated bconv_num_high*bconv_num_width times (Driver.h:307-320) */
+  uint32_t n_stages;
+  hml_stage_count stages[HML_MAX_STAGES];
+} hml_counts;
+int hml_trace_counts(const char *op, uint32_t N, uint32_t batch_size, uint32_t max_level, uint32_t L,
+                     uint32_t alpha, uint32_t bconv_high, uint32_t bconv_width, hml_counts *out);
+int hml_get_counts(const hml_ctx *ctx, const char *op, uint32_t L, hml_counts *out);
+
+/* Limb-ops the GPU schedule actually EXECUTED since the last reset, per kernel class, so the deltas
+ * against the reference trace are explicit rather than folded in. */
+typedef struct {
+  uint64_t ntt_limbs, intt_limbs, ewe_limbs, bconv_limb_macs, automorph_limbs;
+  uint64_t kernel_launches;
+} hml_exec_counts;
+int hml_exec_counts_get(const hml_ctx *ctx, hml_exec_counts *out);
+int hml_exec_counts_reset(hml_ctx *ctx);
+
+/* ------------------------------------------------------------------ the CLI as a library call
+ * `Homulator.run <configfile> <operationName> <maxExecutionLevel> <currentLevel> <alpha> [cluster] [--flags]`
+ * (reference bench_test/bench_micro24.cpp:5-52).  Runs the op on seeded synthetic data on `device`,
+ * prints the config dump, timings, counts and one JSON line to stdout.  Returns the process exit code. */
+int hml_cli_main(int argc, char **argv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -43,7 +43,7 @@ static const char *kStageLabels[] = {
     "_ModDownBConvStep1_Level(", "_ModDownBConvStep2_", "ModDown_NTT(",
     "_KeySwitchFinalOutput_Level(", "_HMULTHadd_Level(", "_Rescale_INTT(",
     "_Rescale_NTT_level(", "_Rescale_Sub_Level(", "_Rescale_Mul_Level(",
-    "_HROTATE_HADD_Level(", "_HADD_Level(", "_HMULT_level(", "_PADD_level(",
+    "_HROTATE_HADD_Level(", "_HADD_Level(", "_HMULT_level(", "_PADD_Level(",
 };
 
 template <class OP>

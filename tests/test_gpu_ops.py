@@ -1,0 +1,161 @@
+"""GPU parity, composite ops: keyswitch / rescale / hmult / hrotate / hadd / pmult / padd against the oracle,
+bit-exact, at small sizes (both oracle tiers) and at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import homulator_b200 as hml  # noqa: E402
+from gpu_common import to_dev, to_host  # noqa: E402
+from orc import Oracle, uniform_limbs  # noqa: E402
+
+
+def make_case(o, L, evk_q, seed, n_ct=2):
+    N, ML = o.N, o.max_level
+    beta = -(-L // o.alpha)
+    cts = [uniform_limbs(o.moduli[:L], N, seed + k, lead=(2,)) for k in range(n_ct)]
+    evk = uniform_limbs(o.moduli[:evk_q] + o.moduli[ML:], N, seed + 9, lead=(beta, 2))
+    return cts, evk
+
+
+# (N, maxLevel, L, alpha): beta = 1, L % alpha != 0, L < alpha, L = 1 (hrotate only), several digits
+SMALL = [(16, 6, 6, 2), (16, 6, 5, 2), (16, 5, 2, 3), (64, 4, 4, 4), (256, 7, 7, 3), (1024, 3, 1, 2), (4096, 9, 8, 3)]
+
+
+@pytest.mark.parametrize("N,ML,L,A", SMALL)
+def test_keyswitch_and_hrotate_small(N, ML, L, A):
+    ctx, o = hml.Context(N=N, max_level=ML, alpha=A), Oracle(N, 36, ML, A)
+    for evk_q in sorted({L, ML}):
+        (ct, _), evk = make_case(o, L, evk_q, 500)
+        for direct in ((0, 1) if N <= 256 else (0,)):
+            o.set_direct(direct)
+            w0, w1 = o.keyswitch(L, ct[0], evk, evk_q)
+            g0, g1 = ctx.keyswitch(L, to_dev(ct[0]), to_dev(evk), evk_q)
+            assert np.array_equal(to_host(g0), w0) and np.array_equal(to_host(g1), w1)
+            for g in (5, 2 * N - 1):
+                want = o.hrotate(L, ct, evk, evk_q, g)
+                got = to_host(ctx.hrotate(L, to_dev(ct), to_dev(evk), g, evk_q))
+                assert np.array_equal(got, want)
+        o.set_direct(0)
+
+
+@pytest.mark.parametrize("N,ML,L,A", [c for c in SMALL if c[2] >= 2])
+def test_rescale_and_hmult_small(N, ML, L, A):
+    ctx, o = hml.Context(N=N, max_level=ML, alpha=A), Oracle(N, 36, ML, A)
+    (a, b), evk = make_case(o, L, L, 600)
+    assert np.array_equal(to_host(ctx.rescale(L, to_dev(a[0]))), o.rescale(L, a[0]))
+    for direct in ((0, 1) if N <= 256 else (0,)):
+        o.set_direct(direct)
+        want = o.hmult(L, a, b, evk, L)
+        got = to_host(ctx.hmult(L, to_dev(a), to_dev(b), to_dev(evk)))
+        assert np.array_equal(got, want)
+    o.set_direct(0)
+
+
+def test_hadd_pmult_padd():
+    N, ML, A, L = 4096, 5, 2, 4
+    ctx, o = hml.Context(N=N, max_level=ML, alpha=A), Oracle(N, 36, ML, A)
+    (a, b), _ = make_case(o, L, L, 700)
+    pt = b[0]
+    assert np.array_equal(to_host(ctx.hadd(L, to_dev(a), to_dev(b))), o.hadd(L, a, b))
+    assert np.array_equal(to_host(ctx.pmult(L, to_dev(a), to_dev(pt))), o.pmult(L, a, pt))
+    assert np.array_equal(to_host(ctx.padd(L, to_dev(a), to_dev(pt))), o.padd(L, a, pt))
+
+
+def test_evk_all_zero_gives_zero_keyswitch():
+    N, ML, A, L = 8192, 6, 2, 5
+    ctx = hml.Context(N=N, max_level=ML, alpha=A)
+    d = ctx.uniform(list(range(L)), 1)
+    evk = torch.zeros(3, 2, L + A, N, dtype=torch.int64, device="cuda")
+    o0, o1 = ctx.keyswitch(L, d, evk)
+    assert int(o0.abs().max()) == 0 and int(o1.abs().max()) == 0
+
+
+@pytest.fixture(scope="module")
+def north_star():
+    Oracle.set_threads(0)  # all host cores for the checker; results do not depend on it (tests/test_oracle.py)
+    ctx, o = hml.Context(N=65536, max_level=45, alpha=15), Oracle(65536, 36, 45, 15)
+    (a, b), evk = make_case(o, 35, 35, 800)
+    yield ctx, o, a, b, evk
+    Oracle.set_threads(1)
+
+
+def test_hmult_north_star_bit_exact(north_star):
+    """BASELINE.json configs[0]: hmult, config_4.cfg, maxLevel 45, L 35, alpha 15."""
+    ctx, o, a, b, evk = north_star
+    want = o.hmult(35, a, b, evk, 35)
+    got = to_host(ctx.hmult(35, to_dev(a), to_dev(b), to_dev(evk)))
+    assert got.shape == (2, 34, 65536)
+    assert np.array_equal(got, want)
+    # executed-vs-trace bookkeeping: D3 elides 35 NTTs, D2 adds 66, D1 relabels 70
+    ctx.exec_counts(reset=True)
+    ctx.hmult(35, to_dev(a), to_dev(b), to_dev(evk))
+    ex = ctx.exec_counts()
+    assert ex["ntt_limbs"] == 115 + 70 + 68 and ex["intt_limbs"] == 35 + 30 + 2
+    assert ex["bconv_limb_macs"] == 2325
+    tr = ctx.counts("hmult", 35)
+    assert (tr["NTT"] + tr["INTT"]) // 256 == 289
+
+
+def test_hrotate_north_star_bit_exact(north_star):
+    """BASELINE.json configs[1]: hrotate, config_4.cfg, maxLevel 45, L 35, alpha 15, r=1 (g=5)."""
+    ctx, o, a, b, evk = north_star
+    want = o.hrotate(35, a, evk, 35, 5)
+    got = to_host(ctx.hrotate(35, to_dev(a), to_dev(evk), 5))
+    assert np.array_equal(got, want)
+
+
+def test_hmult_full_level_key_layout(north_star):
+    """key laid out for maxLevel (evk_q_limbs = 45) used at L = 20: beta = 2, last digit short."""
+    ctx, o, a, b, _ = north_star
+    L = 20
+    evk = uniform_limbs(o.moduli, 65536, 900, lead=(2, 2))
+    a20, b20 = np.ascontiguousarray(a[:, :L]), np.ascontiguousarray(b[:, :L])
+    want = o.hmult(L, a20, b20, evk, 45)
+    got = to_host(ctx.hmult(L, to_dev(a20), to_dev(b20), to_dev(evk), evk_q_limbs=45))
+    assert np.array_equal(got, want)
+
+
+def test_parameter_set_A_N15_beta1():
+    """BASELINE.json configs[2]: config_4_N15.cfg (N=32768), maxLevel 28, alpha 28, levels 28 / 14 / 2."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    Oracle.set_threads(0)
+    ctx, o = hml.Context(os.path.join(root, "config", "config_4_N15.cfg"), 28, 28), Oracle(32768, 36, 28, 28)
+    assert ctx.N == 32768
+    for L in (28, 14, 2):
+        (a, b), evk = make_case(o, L, L, 1000 + L)
+        want = o.hmult(L, a, b, evk, L)
+        got = to_host(ctx.hmult(L, to_dev(a), to_dev(b), to_dev(evk)))
+        assert np.array_equal(got, want), L
+    Oracle.set_threads(1)
+
+
+def test_batch_and_host_paths_equal_single_calls(north_star):
+    ctx, o, a, b, evk = north_star
+    L, n = 35, 3
+    A = torch.stack([to_dev(a), to_dev(b), to_dev(a)])
+    B = torch.stack([to_dev(b), to_dev(b), to_dev(a)])
+    K = to_dev(evk)
+    singles = torch.stack([ctx.hmult(L, A[i], B[i], K) for i in range(n)])
+    assert torch.equal(ctx.hmult_batch(L, A, B, K), singles)
+    ah, bh = A.cpu().pin_memory(), B.cpu().pin_memory()
+    oh = torch.empty(n, 2, L - 1, 65536, dtype=torch.int64).pin_memory()
+    ctx.hmult_host(L, ah, bh, K, oh)
+    assert torch.equal(oh, singles.cpu())
+    rs = torch.stack([ctx.hrotate(L, A[i], K, 5) for i in range(n)])
+    assert torch.equal(ctx.hrotate_batch(L, A, K, 5), rs)
+    rh = torch.empty(n, 2, L, 65536, dtype=torch.int64).pin_memory()
+    ctx.hrotate_host(L, ah, K, rh, 5)
+    assert torch.equal(rh, rs.cpu())
+
+
+def test_op_objects_mirror_reference_constructor(north_star):
+    ctx, *_ = north_star
+    op = hml.HMULT("test_hmult", 45, 35, 15, ctx)
+    assert op.counts["total"] == 834560 and op.counts["driverTotal"] == 7381760
+    r = op.simulate(iters=2, warmup=1)
+    assert r["us_median"] > 0
+    rot = hml.HROTATE("test_hrotate", 45, 35, 15, ctx)
+    assert rot.counts["AUTO"] == 17920 and rot.counts["total"] == 780800

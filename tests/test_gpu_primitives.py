@@ -1,0 +1,142 @@
+"""GPU parity, primitives: every kernel class against the scalar oracle, bit-exact, through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import homulator_b200 as hml  # noqa: E402
+from gpu_common import to_dev, to_host  # noqa: E402
+from orc import Oracle, uniform_limbs  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def big():
+    """north-star parameter set: N=2^16, 36-bit words, maxLevel 45, alpha 15"""
+    return hml.Context(N=65536, max_level=45, alpha=15), Oracle(65536, 36, 45, 15)
+
+
+def test_moduli_and_roots_match_oracle(big):
+    ctx, o = big
+    assert ctx.moduli == o.moduli
+    assert ctx.psi == o.psi
+
+
+@pytest.mark.parametrize("logN", [4, 5, 8, 11, 12, 13, 14, 15, 16])
+def test_ntt_intt_all_sizes(logN):
+    N = 1 << logN
+    ml, al = 5, 3
+    ctx, o = hml.Context(N=N, max_level=ml, alpha=al), Oracle(N, 36, ml, al)
+    assert ctx.moduli == o.moduli
+    idx = list(range(ml + al))
+    x = uniform_limbs(o.moduli, N, 100 + logN)
+    # edge values: zeros, q-1, 1
+    x[0, :4] = 0
+    x[1, :4] = o.moduli[1] - 1
+    x[2, :] = o.moduli[2] - 1
+    want = np.stack([o.ntt(i, x[i]) for i in idx])
+    got = to_host(ctx.ntt(to_dev(x), idx))
+    assert np.array_equal(got, want)
+    back = to_host(ctx.intt(to_dev(want), idx))
+    assert np.array_equal(back, x)
+    want_i = np.stack([o.intt(i, x[i]) for i in idx])
+    assert np.array_equal(to_host(ctx.intt(to_dev(x), idx)), want_i)
+    # in place
+    d = to_dev(x)
+    ctx.ntt(d, idx, out=d)
+    assert np.array_equal(to_host(d), want)
+
+
+def test_ntt_north_star_all_60_moduli(big):
+    ctx, o = big
+    idx = list(range(60))
+    x = uniform_limbs(o.moduli, 65536, 7)
+    got = to_host(ctx.ntt(to_dev(x), idx))
+    for i in (0, 1, 17, 34, 44, 45, 59):
+        assert np.array_equal(got[i], o.ntt(i, x[i])), i
+    # every limb: round trip + Horner spot check of the definition a(psi^(2 brv(k)+1)) on random slots
+    assert np.array_equal(to_host(ctx.intt(to_dev(got), idx)), x)
+    rng = np.random.default_rng(1)
+    for i in idx:
+        m, psi = o.moduli[i], o.psi[i]
+        for k in rng.integers(0, 65536, 2):
+            brv = int(format(int(k), "016b")[::-1], 2)
+            pt = pow(psi, 2 * brv + 1, m)
+            acc = 0
+            for c in x[i][::-1]:
+                acc = (acc * pt + int(c)) % m
+            assert int(got[i][k]) == acc
+
+
+def test_ntt_repeated_moduli_and_more_than_128_limbs():
+    N = 256
+    ctx, o = hml.Context(N=N, max_level=4, alpha=2), Oracle(N, 36, 4, 2)
+    idx = [i % 6 for i in range(300)]
+    x = np.stack([uniform_limbs([o.moduli[i]], N, 1000 + k)[0] for k, i in enumerate(idx)])
+    got = to_host(ctx.ntt(to_dev(x), idx))
+    for k in (0, 127, 128, 255, 256, 299):
+        assert np.array_equal(got[k], o.ntt(idx[k], x[k]))
+
+
+@pytest.mark.parametrize("N", [16, 4096, 65536])
+def test_ewe_variants(N):
+    ctx, o = hml.Context(N=N, max_level=4, alpha=2), Oracle(N, 36, 4, 2)
+    idx = [0, 3, 5]
+    xs = [np.stack([uniform_limbs([o.moduli[i]], N, 200 + 10 * k + i)[0] for i in idx]) for k in range(4)]
+    xs[0][0, :3] = 0
+    xs[1][1, :3] = o.moduli[3] - 1
+    d = [to_dev(x) for x in xs]
+    cases = [((0, 1, 2, 3), False), ((0, 1, 2, 3), True), ((0, None, 2, None), False), ((0, None, 2, None), True),
+             ((0, 1, None, None), False), ((0, 1, 2, None), False), ((0, None, None, None), False)]
+    for sel, sub in cases:
+        args = [d[s] if s is not None else None for s in sel]
+        got = to_host(ctx.ewe(*args, idx, subtract=sub))
+        for r, i in enumerate(idx):
+            hargs = [xs[s][r] if s is not None else None for s in sel]
+            assert np.array_equal(got[r], o.ewe(i, *hargs, sub=sub)), (sel, sub, i)
+
+
+@pytest.mark.parametrize("N,g", [(16, 5), (4096, 25), (65536, 5), (65536, 2 * 65536 - 1), (65536, pow(5, 77, 2 * 65536))])
+def test_automorphism(N, g):
+    ctx, o = hml.Context(N=N, max_level=3, alpha=1), Oracle(N, 36, 3, 1)
+    x = uniform_limbs(o.moduli, N, 300)
+    got = to_host(ctx.automorph(to_dev(x), g))
+    for i in range(4):
+        assert np.array_equal(got[i], o.automorph_eval(g, x[i]))
+    # against the coefficient-domain definition, through the GPU NTT
+    idx = list(range(4))
+    coeff = np.stack([o.automorph_coeff(i, g, x[i]) for i in idx])
+    a = to_host(ctx.automorph(ctx.ntt(to_dev(x), idx), g))
+    b = to_host(ctx.ntt(to_dev(coeff), idx))
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("N,ml,al,src,dst", [
+    (16, 6, 3, [1, 2, 4], [0, 3, 5, 6, 7, 8]),
+    (4096, 6, 3, [0], [1, 2, 3, 4, 5, 6, 7, 8]),
+    (65536, 45, 15, list(range(15)), list(range(15, 35)) + list(range(45, 60))),  # ModUp digit 0 at L=35
+    (65536, 45, 15, list(range(30, 35)), list(range(30)) + list(range(45, 60))),  # short last digit
+    (65536, 45, 15, list(range(45, 60)), list(range(35))),                        # ModDown
+    (32768, 28, 28, list(range(28)), list(range(28, 56))),                        # parameter set A: 28 sources
+])
+def test_bconv(N, ml, al, src, dst):
+    ctx, o = hml.Context(N=N, max_level=ml, alpha=al), Oracle(N, 36, ml, al)
+    x = np.stack([uniform_limbs([o.moduli[i]], N, 400 + i)[0] for i in src])
+    x[0, :2] = o.moduli[src[0]] - 1
+    got = to_host(ctx.bconv(to_dev(x), src, dst))
+    check = range(len(dst)) if N <= 4096 else (0, 1, len(dst) // 2, len(dst) - 1)
+    for t in check:
+        assert np.array_equal(got[t], o.bconv(src, dst[t], x)), dst[t]
+
+
+def test_errors_are_reported_not_raised_across_the_abi(big):
+    ctx, _ = big
+    x = ctx.empty(1, 65536)
+    with pytest.raises(hml.HmlError):
+        ctx.ntt(x, [60])  # modulus index out of range
+    with pytest.raises(hml.HmlError):
+        ctx.automorph(x, 4)  # even galois element
+    with pytest.raises(hml.HmlError):
+        ctx.hmult(1, x, x, x)  # L < 2
+    with pytest.raises(hml.HmlError):
+        ctx.hmult(46, x, x, x)  # L > maxLevel
