@@ -1,0 +1,299 @@
+#!/usr/bin/env python3
+"""bench.py — hmult latency/throughput at N=2^16, l=35, alpha=15 (BASELINE.json north-star config) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B]           # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]                  # CPU reference arm
+
+A "step" is one pass of the hot path over one batch of synthetic input: B independent hmult
+(config_4.cfg, maxLevel 45, currentLevel 35, alpha 15) per GPU, all B ciphertext pairs distinct and resident
+in HBM (2*B*36.7 MB of input per GPU, far larger than L2, so no L2 flush is needed between steps).
+`value` = microseconds per hmult over the whole job (all ranks), lower is better.  One process per GPU,
+independent ciphertexts sharded across ranks, no data-path collective ("scaling": "weak").
+
+The JSON line also carries: `e2e` (same metric through the host-buffer C-ABI call, H2D/D2H inside the timed
+region), `roofline` (the forward-NTT kernel pair timed alone with CUDA events), `cpu_baseline` (the scalar
+oracle port timed on one host core on a bounded sample), `extra` (single-op latencies with L2 flushed,
+hrotate, NTT limbs/s, the reference's published-by-survey simulator figures).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CFG = os.path.join(ROOT, "config", "config_4.cfg")
+N_RING, MAX_LEVEL, LEVEL, ALPHA = 65536, 45, 35, 15
+METRIC = "hmult_us_N65536_l35_alpha15"
+WORKLOAD = "hmult config_4.cfg maxLevel=45 currentLevel=35 alpha=15 (BASELINE.json configs[0]/[3])"
+
+
+def measured_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_port_sample(n_ops, threads):
+    """Time the scalar oracle port (oracle/oracle.c) on the same workload: n_ops hmult, `threads` host threads."""
+    from orc import Oracle, uniform_limbs
+    o = Oracle(N_RING, 36, MAX_LEVEL, ALPHA)
+    L = LEVEL
+    a = uniform_limbs(o.moduli[:L], N_RING, 1, lead=(2,))
+    b = uniform_limbs(o.moduli[:L], N_RING, 2, lead=(2,))
+    evk = uniform_limbs(o.moduli[:L] + o.moduli[MAX_LEVEL:], N_RING, 3, lead=(3, 2))
+    used = Oracle.set_threads(threads)
+    t0 = time.perf_counter()
+    for _ in range(n_ops):
+        o.hmult(L, a, b, evk, L)
+    dt = time.perf_counter() - t0
+    Oracle.set_threads(1)
+    return dt / n_ops * 1e6, used
+
+
+def run_reference(args):
+    """Reference arm.  The reference itself (a cycle simulator) computes no ciphertext values and its own run of this
+    config takes hours, so the CPU implementation of the path timed here is the scalar oracle
+    port with all host threads; each step is ONE hmult (bounded sample of the workload)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_port_sample(1, threads)
+    steps = max(1, args.steps)
+    us, used = cpu_port_sample(steps, threads)
+    sim = {}
+    run = os.path.join(ROOT, "oracle", "_ref", "count.run")
+    if os.path.exists(run):  # the reference's own instruction generation for this op (the part our planner replaces)
+        try:
+            line = subprocess.run([run, CFG, "hmult", str(MAX_LEVEL), str(LEVEL), str(ALPHA)], capture_output=True, text=True,
+                                  timeout=120).stdout.strip().splitlines()[-1]
+            sim["homulator_insgen_seconds"] = json.loads(line)["insgen_seconds"]
+        except Exception:
+            pass
+    line = {
+        "impl": "reference", "metric": METRIC, "value": us, "unit": "us", "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": us / 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64 (36-bit residues)", "data": "synthetic", "config": {"workload": WORKLOAD, "batch_per_step": 1},
+        "cpu_baseline": {"value": us, "unit": "us", "cores": used, "kind": "port",
+                         "sample": "%d hmult at the full config, oracle/oracle.c with OpenMP over limbs" % steps},
+        "e2e": {"value": us, "unit": "us", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "extra": sim,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32, help="hmult per GPU per step")
+    ap.add_argument("--e2e-batch", type=int, default=8, help="hmult per GPU per step on the host-buffer path")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import homulator_b200 as hml
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; homulator_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W = max(3, args.warmup)
+    K, B, L = max(1, args.steps), args.batch, LEVEL
+
+    ctx = hml.Context(CFG, MAX_LEVEL, ALPHA, device=local)
+    q = list(range(L))
+    evk = ctx.uniform(ctx.ext_mod_idx(L), 3, lead=(ctx.beta(L), 2))
+    ct_a = ctx.uniform(q, 10 + rank, lead=(B, 2))
+    ct_b = ctx.uniform(q, 1000 + rank, lead=(B, 2))
+    out = ctx.empty(B, 2, L - 1, N_RING)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (value)
+    for _ in range(W):
+        ctx.hmult_batch(L, ct_a, ct_b, evk, out=out)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ctx.exec_counts(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        ctx.hmult_batch(L, ct_a, ct_b, evk, out=out)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    sampler.stop_flag = True
+    launches = ctx.exec_counts()["kernel_launches"]
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    n_ops = K * B * world
+    us_per_op = ms_total * 1e3 / n_ops
+    sampler.join(timeout=2)
+
+    # ---------------- end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside)
+    Be = args.e2e_batch
+    ah = ct_a[:Be].cpu().pin_memory()
+    bh = ct_b[:Be].cpu().pin_memory()
+    oh = torch.empty(Be, 2, L - 1, N_RING, dtype=torch.int64).pin_memory()
+    for _ in range(2):
+        ctx.hmult_host(L, ah, bh, evk, oh)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        ctx.hmult_host(L, ah, bh, evk, oh)
+    barrier()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_us = float(e2e_ms.item()) * 1e3 / (K * Be * world)
+    e2e_ok = bool(torch.equal(oh.cuda(), out[:Be]))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------- roofline of the dominant kernel: forward NTT (column pass + row pass), timed alone
+    peak, peak_src = measured_peaks()
+    W_bytes = 8 * N_RING
+    n_limbs = 115  # the ModUp NTT launch of one key switch at (35, 15): the largest NTT launch of the step
+    idx = [ctx.ext_mod_idx(L)[i % (L + ALPHA)] for i in range(n_limbs)]
+    bufs = [ctx.uniform(idx, 50 + i) for i in range(4)]  # 4 x 60 MB > L2: every launch reads from HBM
+    dst = ctx.empty(n_limbs, N_RING)
+    for i in range(4):
+        ctx.ntt(bufs[i], idx, out=dst)
+    torch.cuda.synchronize()
+    reps = 20
+    e0.record()
+    for i in range(reps):
+        ctx.ntt(bufs[i % 4], idx, out=dst)
+    e1.record()
+    torch.cuda.synchronize()
+    ntt_ms = e0.elapsed_time(e1) / reps
+    ntt_bytes = 2.0 * W_bytes * n_limbs
+    ntt_gbs = ntt_bytes / (ntt_ms * 1e-3) / 1e9
+    ntt_limbs_per_s = n_limbs / (ntt_ms * 1e-3)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ntt_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
+
+    extra = {"ntt_limbs_per_s": ntt_limbs_per_s, "ntt_us_per_limb": ntt_ms * 1e3 / n_limbs, "e2e_matches_device_path": e2e_ok}
+    if not args.no_extra:
+        flush = torch.empty(64 << 20, dtype=torch.int64, device="cuda")  # 512 MiB
+
+        def lat(fn, iters=10):
+            ts = []
+            for _ in range(iters):
+                flush.fill_(1)
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                fn()
+                a1.record()
+                a1.synchronize()
+                ts.append(a0.elapsed_time(a1) * 1e3)
+            ts.sort()
+            return ts[len(ts) // 2]
+
+        o1, o2 = ctx.empty(2, L - 1, N_RING), ctx.empty(2, L, N_RING)
+        hm = lat(lambda: ctx.hmult(L, ct_a[0], ct_b[0], evk, out=o1))
+        hr = lat(lambda: ctx.hrotate(L, ct_a[0], evk, 5, out=o2))
+        aw_m, aw_r = hml.algorithmic_words("hmult", L, ALPHA), hml.algorithmic_words("hrotate", L, ALPHA)
+        extra.update({
+            "hmult_single_us_l2_flushed": hm, "hrotate_single_us_l2_flushed": hr,
+            "hmult_hbm_frac_unfused_bytes": aw_m * W_bytes / (hm * 1e-6) / 1e9 / peak,
+            "hrotate_hbm_frac_unfused_bytes": aw_r * W_bytes / (hr * 1e-6) / 1e9 / peak,
+            "hmult_batched_hbm_frac_unfused_bytes": aw_m * W_bytes / (us_per_op * 1e-6) / 1e9 / peak,
+            "homulator_simulated_cycles": "see BASELINE.md section 2 (L=35 run is multi-hour; hmult 45 2 15 = 18772 cycles)",
+        })
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, used = cpu_port_sample(3, 1)
+        cpu = {"value": v, "unit": "us", "cores": used, "kind": "port",
+               "sample": "3 hmult at the full config on one host core (oracle/oracle.c, scalar)"}
+
+    in_bytes = 2 * 2 * L * W_bytes * Be
+    out_bytes = 2 * (L - 1) * W_bytes * Be
+    line = {
+        "metric": METRIC, "value": us_per_op, "unit": "us", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64 residues (36-bit), arithmetic on the FP64 pipe", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu_per_step": B, "l2": "inputs larger than L2 (no flush)",
+                   "throughput_hmult_per_s": n_ops / (ms_total * 1e-3)},
+        "e2e": {"value": e2e_us, "unit": "us", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+                "batch_per_gpu_per_step": Be},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "roofline": {"bound": "hbm", "kernel": "ntt_fwd_cols + ntt_fwd_rows (forward NTT, 115 limbs)", "achieved": ntt_gbs,
+                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ntt_gbs / peak, "traffic": traffic,
+                     "algorithmic_bytes_per_launch": ntt_bytes},
+        "cpu_baseline": cpu,
+        "extra": extra,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

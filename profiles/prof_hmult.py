@@ -1,0 +1,39 @@
+"""Profiling driver: a few single hmult / hrotate at the north-star config, nothing else on the GPU.
+
+    python profiles/prof_hmult.py [hmult|hrotate|ntt] [n_warm] [n_prof]
+
+Used under ncu (see profiles/README.md); kernel names all live in namespace hml::.
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import homulator_b200 as hml  # noqa: E402
+
+op = sys.argv[1] if len(sys.argv) > 1 else "hmult"
+n_warm = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+n_prof = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+L, A = 35, 15
+ctx = hml.Context(os.path.join(ROOT, "config", "config_4.cfg"), 45, A)
+q = list(range(L))
+evk = ctx.uniform(ctx.ext_mod_idx(L), 3, lead=(3, 2))
+a = ctx.uniform(q, 1, lead=(2,))
+b = ctx.uniform(q, 2, lead=(2,))
+torch.cuda.synchronize()
+if op == "ntt":
+    idx = [ctx.ext_mod_idx(L)[i % 50] for i in range(115)]
+    x = ctx.uniform(idx, 5)
+    y = ctx.empty(115, ctx.N)
+    for _ in range(n_warm + n_prof):
+        ctx.ntt(x, idx, out=y)
+        ctx.intt(x, idx, out=y)
+else:
+    for _ in range(n_warm + n_prof):
+        if op == "hmult":
+            ctx.hmult(L, a, b, evk)
+        else:
+            ctx.hrotate(L, a, evk, 5)
+torch.cuda.synchronize()
+print("done", op)
