@@ -187,6 +187,16 @@ static int check_launch(hml_ctx *ctx, const char *what) {
   return HML_OK;
 }
 
+static void clear_map(LimbMap &lm) {
+  memset(&lm, 0, sizeof(lm));
+  memset(lm.skip, 0xFF, sizeof(lm.skip));
+}
+
+static void id_map(LimbMap &lm, const uint32_t *mod_idx, uint32_t n) {
+  clear_map(lm);
+  for (uint32_t i = 0; i < n; ++i) { lm.mod[i] = (uint16_t)mod_idx[i]; lm.pos[i] = (uint16_t)i; }
+}
+
 // ------------------------------------------------------------------------------------------------ per-level constants
 static int get_level(hml_ctx *ctx, uint32_t L, LevelConsts **out) {
   auto it = ctx->levels.find(L);
@@ -195,25 +205,25 @@ static int get_level(hml_ctx *ctx, uint32_t L, LevelConsts **out) {
   const uint32_t A = p.alpha, E = L + A, beta = p.beta(L);
   LevelConsts lc;
   lc.L = L; lc.beta = beta; lc.E = E;
-  memset(&lc.q_lm, 0, sizeof(LimbMap)); memset(&lc.p_lm, 0, sizeof(LimbMap));
+  clear_map(lc.q_lm); clear_map(lc.p_lm); clear_map(lc.ext_lm);
   for (uint32_t i = 0; i < L; ++i) { lc.q_lm.mod[i] = i; lc.q_lm.pos[i] = i; }
   for (uint32_t j = 0; j < A; ++j) { lc.p_lm.mod[j] = p.max_level + j; lc.p_lm.pos[j] = L + j; }
   int rc;
   // ---- ModUp
   std::vector<double2> up_scale(L);
-  LimbMap flat; memset(&flat, 0, sizeof(flat));
-  int nflat = 0;
+  for (uint32_t e = 0; e < E; ++e) {
+    lc.ext_lm.mod[e] = p.ext_mod(L, e); lc.ext_lm.pos[e] = e;
+    lc.ext_lm.skip[e] = e < L ? (uint8_t)(e / A) : 0xFF;  // digit j owns limbs [j*alpha, j*alpha + a_j)
+  }
   for (uint32_t j = 0; j < beta; ++j) {
     const uint32_t lo = j * A, aj = p.digit_size(L, j);
     std::vector<uint32_t> src, dst;
     for (uint32_t i = 0; i < aj; ++i) src.push_back(lo + i);
-    LimbMap dlm; memset(&dlm, 0, sizeof(dlm));
+    LimbMap dlm; clear_map(dlm);
     for (uint32_t e = 0; e < E; ++e) {
       if (e >= lo && e < lo + aj) continue;
       dlm.mod[dst.size()] = p.ext_mod(L, e);
       dst.push_back(p.ext_mod(L, e));
-      flat.mod[nflat] = p.ext_mod(L, e); flat.pos[nflat] = j * E + e;
-      if (++nflat == NTT_MAX_LIMBS) { lc.up_ntt_lm.push_back(flat); lc.up_ntt_n.push_back(nflat); nflat = 0; memset(&flat, 0, sizeof(flat)); }
     }
     BConvTable bt;
     make_bconv_table(p, src, dst, bt);
@@ -228,7 +238,6 @@ static int get_level(hml_ctx *ctx, uint32_t L, LevelConsts **out) {
     lc.up_hat3.push_back(d3);
     lc.up_dst.push_back(dlm);
   }
-  if (nflat) { lc.up_ntt_lm.push_back(flat); lc.up_ntt_n.push_back(nflat); }
   if ((rc = upload(ctx, up_scale, &lc.modup_scale))) return rc;
   // ---- ModDown
   {
@@ -269,11 +278,6 @@ static int check_level(hml_ctx *ctx, uint32_t L, uint32_t min_level) {
   if (!ctx) return HML_ERR_INVALID;
   if (L < min_level || L > ctx->p.max_level) return fail(ctx, HML_ERR_INVALID, "currentLevel out of range");
   return HML_OK;
-}
-
-static void id_map(LimbMap &lm, const uint32_t *mod_idx, uint32_t n) {
-  memset(&lm, 0, sizeof(lm));
-  for (uint32_t i = 0; i < n; ++i) { lm.mod[i] = (uint16_t)mod_idx[i]; lm.pos[i] = (uint16_t)i; }
 }
 
 // ------------------------------------------------------------------------------------------------ primitives
@@ -411,11 +415,12 @@ static int ks_run(hml_ctx *ctx, uint32_t L, const u64 *d, const u64 *evk, uint32
   }
   // K4 (reference :190-292): NTT of the converted limbs.  The digit's own limbs are the untouched input
   // (delta D3: the reference also counts an NTT for those).
-  for (size_t c = 0; c < lc->up_ntt_lm.size(); ++c) {
+  {
     NttLaunch l{};
-    l.in = ext; l.out = ext; l.in_limb_stride = l.out_limb_stride = N; l.n_limbs = lc->up_ntt_n[c]; l.n_polys = 1;
-    launch_ntt_forward(ctx->tabs, logN, lc->up_ntt_lm[c], l, s);
-    ctx->exec.ntt_limbs += lc->up_ntt_n[c]; ctx->exec.kernel_launches += npass;
+    l.in = ext; l.out = ext; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)E * N;
+    l.n_limbs = E; l.n_polys = beta;  // digit j skips the limbs it owns (LimbMap::skip)
+    launch_ntt_forward(ctx->tabs, logN, lc->ext_lm, l, s);
+    ctx->exec.ntt_limbs += (uint64_t)beta * E - L; ctx->exec.kernel_launches += npass;
   }
   // K5 (reference :294-414): inner product with the key
   {
@@ -486,7 +491,7 @@ static int rescale_run(hml_ctx *ctx, uint32_t L, const u64 *in, long long in_pol
   const int logN = p.logN, npass = logN <= 12 ? 1 : 2;
   u64 *rb = ws, *rh = ws + (size_t)n_polys * N;  // rb [n_polys][N], rh [n_polys][L-1][N]
   {  // INTT of the dropped limb (reference :766-805)
-    LimbMap lm; memset(&lm, 0, sizeof(lm));
+    LimbMap lm; clear_map(lm);
     lm.mod[0] = L - 1; lm.pos[0] = 0;
     NttLaunch l{};
     l.in = in + (size_t)(L - 1) * N; l.out = rb; l.in_limb_stride = l.out_limb_stride = N;

@@ -22,9 +22,8 @@ struct LevelConsts {
   // K3: per digit, the conversion matrix to the E - a_j other limbs, split in 12-bit pieces
   std::vector<double *> up_hat3;             // [beta] -> [a_j][E - a_j][3]
   std::vector<LimbMap> up_dst;               // modulus of each output limb (gap-free numbering)
-  // K4: one flat launch list over all (digit, non-own limb) pairs
-  std::vector<LimbMap> up_ntt_lm;            // chunks of <= NTT_MAX_LIMBS
-  std::vector<int> up_ntt_n;
+  // K4: limbs = the E extended limbs, polys = the beta digits, skip = the digit that owns the limb
+  LimbMap ext_lm;
   // K6+K7 fused: INTT post-scale N^-1 * (P/p_j)^-1 mod p_j;  K8 matrix [alpha][L][3];  K10 constant P^-1 mod q_i
   double2 *moddown_scale = nullptr;          // [alpha]
   double *down_hat3 = nullptr;

@@ -176,8 +176,12 @@ __global__ void __launch_bounds__(BC_THREADS) k_bconv(const ModConst *__restrict
   for (int o = 0; o < BC_OT; ++o)
 #pragma unroll
     for (int k = 0; k < 3; ++k) acc[o][k][0] = acc[o][k][1] = 0.0;
+  // software pipeline: the loads of sources i+1, i+2 are in flight while source i is accumulated
+  ulonglong2 pre0 = ld2(in, i2), pre1 = ld2(in, (size_t)min(1, a.n_src - 1) * n2 + i2);
   for (int i = 0; i < a.n_src; ++i) {
-    const ulonglong2 xv = ld2(in, (size_t)i * n2 + i2);
+    const ulonglong2 xv = pre0;
+    pre0 = pre1;
+    pre1 = ld2(in, (size_t)min(i + 2, a.n_src - 1) * n2 + i2);
     double y0 = u64_to_f64(xv.x), y1 = u64_to_f64(xv.y);
     if (STEP1) {
       const ModConst m = mc[src_lm.mod[i]];

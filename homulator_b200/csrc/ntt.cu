@@ -70,11 +70,10 @@ struct LimbCtx {
   int limb;
 };
 
-__device__ __forceinline__ LimbCtx limb_ctx(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, bool inverse) {
+__device__ __forceinline__ LimbCtx limb_ctx(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, bool inverse,
+                                            int limb, int poly) {
   LimbCtx c;
-  const int y = blockIdx.y;
-  c.limb = y % l.n_limbs;
-  const int poly = y / l.n_limbs;
+  c.limb = limb;
   const int mi = lm.mod[c.limb];
   const ModConst mc = t.mc[mi];
   c.q = mc.q; c.qinv = mc.qinv; c.qi = mc.qi;
@@ -91,7 +90,9 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_fwd_cols(NttTables t, int 
   constexpr int R1 = 1 << LOGR1, C = NTT_TILE / R1, R2 = 1 << NTT_ROW_LOG;
   using SP = Split<LOGR1>;
   extern __shared__ double sm[];
-  const LimbCtx lc = limb_ctx(t, logN, lm, l, false);
+  const int limb = blockIdx.y % l.n_limbs, poly = blockIdx.y / l.n_limbs;
+  if (poly == lm.skip[limb]) return;
+  const LimbCtx lc = limb_ctx(t, logN, lm, l, false, limb, poly);
   const int c = threadIdx.x % C, u = threadIdx.x / C;
   const int col = blockIdx.x * C + c;
   double a[8];
@@ -131,105 +132,113 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_fwd_cols(NttTables t, int 
   }
 }
 
-// ================================================================================ forward, rows
-// 16 contiguous rows of 256 per CTA.  smem [256][17]: point-major, row (=sub-NTT id) minor.
-constexpr int ROWS = NTT_TILE >> NTT_ROW_LOG;  // 16
-constexpr int RP = ROWS + 1;                   // pitch
+// ================================================================================ row passes: one warp per row
+// The last 8 forward stages (first 8 inverse stages) stay inside a contiguous 256-point row.  A warp owns a row:
+// lane l holds points kk*32 + l (kk = register index), so the three widest stages (t = 128, 64, 32) are
+// register-only and global accesses are 256-byte coalesced.  The five narrow stages (t = 16 .. 1) pair points in
+// different lanes; instead of shared memory each stage swaps HALF of every lane's registers with lane ^ t
+// (register bit 2 <-> lane bit b), after which each lane owns four complete butterflies (registers j, j+4).
+// The swaps are never undone: the logical point of (lane, register) is tracked in closed form
+//   stage b (= 4..0):  kk = (r & 3) | (lane bit 4) << 2,   lane-point bits: P_m = lane bit m-1 (m > b), P_b = r bit 2,
+//                      P_m = lane bit m (m < b)
+// and after the last stage registers (j, j+4) hold the adjacent points p, p+1 with
+//   p = ((j + 4*(lane>>4)) * 32 + 2*(lane & 15)),  i.e. 16-byte stores that tile two 256-byte segments per warp.
+// No shared memory, no block barrier.
+constexpr int ROW_WARPS = 8;  // rows per CTA
 
-__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_fwd_rows(NttTables t, int logN, LimbMap lm, NttLaunch l) {
-  constexpr int LR = NTT_ROW_LOG, R2 = 1 << LR;
-  __shared__ double sm[R2 * RP];
-  const LimbCtx lc = limb_ctx(t, logN, lm, l, false);
-  const unsigned R1 = 1u << (logN - LR);
-  const int row0 = blockIdx.x * ROWS;
-  double a[8];
-  const double *ind = reinterpret_cast<const double *>(lc.out);  // pass 1 left raw doubles in `out`
-  {  // round (0,3): one warp per row, coalesced
-    const int u = threadIdx.x % 32, n = threadIdx.x / 32;
-    using RD = Round<LR, 0, 3>;
-    const size_t base = (size_t)(row0 + n) * R2;
+__device__ __forceinline__ void swap_half(double (&a)[8], int b, bool upper) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) a[r] = ind[base + RD::point(u, r)];
-    ct_round<LR, 0, 3>(a, u, lc.tw, R1 + row0 + n, lc.q);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) sm[RD::point(u, r) * RP + n] = a[r];
-  }
-  __syncthreads();
-  const int c = threadIdx.x % ROWS, u = threadIdx.x / ROWS;
-  {
-    using RD = Round<LR, 3, 3>;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(u, r) * RP + c];
-    ct_round<LR, 3, 3>(a, u, lc.tw, R1 + row0 + c, lc.q);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) sm[RD::point(u, r) * RP + c] = a[r];
-  }
-  __syncthreads();
-  {
-    using RD = Round<LR, 6, 2>;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(u, r) * RP + c];
-    ct_round<LR, 6, 2>(a, u, lc.tw, R1 + row0 + c, lc.q);
-    u64 *smu = reinterpret_cast<u64 *>(sm);
-#pragma unroll
-    for (int r = 0; r < 8; ++r)
-      smu[RD::point(u, r) * RP + c] = f64_to_canonical(reduce_signed(a[r], lc.q, lc.qinv), lc.qi);
-  }
-  __syncthreads();
-  {  // coalesced store, one warp per row
-    const int uu = threadIdx.x % 32, n = threadIdx.x / 32;
-    const u64 *smu = reinterpret_cast<const u64 *>(sm);
-    const size_t base = (size_t)(row0 + n) * R2;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) lc.out[base + r * 32 + uu] = smu[(r * 32 + uu) * RP + n];
+  for (int j = 0; j < 4; ++j) {
+    const double send = upper ? a[j] : a[j + 4];
+    const double recv = __shfl_xor_sync(0xffffffffu, send, 1 << b);
+    if (upper) a[j] = recv; else a[j + 4] = recv;
   }
 }
 
-// ================================================================================ inverse, rows (first)
-__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_inv_rows(NttTables t, int logN, LimbMap lm, NttLaunch l) {
+// twiddle index of pair j at lane-stage b (NTT stage i = 7 - b): (tw_base << i) + kk * 2^(4-b) + ((lane & 15) >> b)
+__device__ __forceinline__ unsigned lane_stage_tw(unsigned tw_base, int b, int j, int lane) {
+  const int kk = j + ((lane >> 4) << 2);
+  return (tw_base << (7 - b)) + (kk << (4 - b)) + ((lane & 15) >> b);
+}
+
+// Polys that share the limb's modulus (the beta digits of ModUp, the two key-switch accumulators, the two
+// rescaled polys) are processed back to back by the same warp, so their twiddles (4 KB per row) hit L1.
+__global__ void __launch_bounds__(ROW_WARPS * 32, 4) ntt_fwd_rows(NttTables t, int logN, LimbMap lm, NttLaunch l) {
   constexpr int LR = NTT_ROW_LOG, R2 = 1 << LR;
-  __shared__ double sm[R2 * RP];
-  const LimbCtx lc = limb_ctx(t, logN, lm, l, true);
+  const int limb = blockIdx.y;
   const unsigned R1 = 1u << (logN - LR);
-  const int row0 = blockIdx.x * ROWS;
-  double a[8];
-  {
-    const int uu = threadIdx.x % 32, n = threadIdx.x / 32;
-    const size_t base = (size_t)(row0 + n) * R2;
+  const int lane = threadIdx.x & 31, row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const unsigned tw_base = R1 + row;
+  for (int poly = 0; poly < l.n_polys; ++poly) {
+    if (poly == lm.skip[limb]) continue;
+    const LimbCtx lc = limb_ctx(t, logN, lm, l, false, limb, poly);
+    const double *ind = reinterpret_cast<const double *>(lc.out) + (size_t)row * R2;  // pass 1 left raw doubles in `out`
+    double a[8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) sm[(r * 32 + uu) * RP + n] = u64_to_f64(__ldg(&lc.in[base + r * 32 + uu]));
+    for (int r = 0; r < 8; ++r) a[r] = ind[r * 32 + lane];
+    double2 w[4], wn[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wn[j] = __ldg(&lc.tw[lane_stage_tw(tw_base, 4, j, lane)]);
+    ct_round<LR, 0, 3>(a, lane, lc.tw, tw_base, lc.q);
+#pragma unroll
+    for (int b = 4; b >= 0; --b) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = wn[j];
+      if (b > 0) {  // next stage's twiddles are in flight during this stage's butterflies
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wn[j] = __ldg(&lc.tw[lane_stage_tw(tw_base, b - 1, j, lane)]);
+      }
+      swap_half(a, b, (lane >> b) & 1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ct_butterfly(a[j], a[j + 4], w[j].x, w[j].y, lc.q);
+    }
+    u64 *outp = lc.out + (size_t)row * R2 + (lane >> 4) * 128 + 2 * (lane & 15);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const u64 v0 = f64_to_canonical(reduce_signed(a[j], lc.q, lc.qinv), lc.qi);
+      const u64 v1 = f64_to_canonical(reduce_signed(a[j + 4], lc.q, lc.qinv), lc.qi);
+      *reinterpret_cast<ulonglong2 *>(outp + j * 32) = make_ulonglong2(v0, v1);
+    }
   }
-  __syncthreads();
-  const int c = threadIdx.x % ROWS, u = threadIdx.x / ROWS;
-  {
-    using RD = Round<LR, 6, 2>;
+}
+
+__global__ void __launch_bounds__(ROW_WARPS * 32, 4) ntt_inv_rows(NttTables t, int logN, LimbMap lm, NttLaunch l) {
+  constexpr int LR = NTT_ROW_LOG, R2 = 1 << LR;
+  const int limb = blockIdx.y;
+  const unsigned R1 = 1u << (logN - LR);
+  const int lane = threadIdx.x & 31, row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const unsigned tw_base = R1 + row;
+  for (int poly = 0; poly < l.n_polys; ++poly) {
+    if (poly == lm.skip[limb]) continue;
+    const LimbCtx lc = limb_ctx(t, logN, lm, l, true, limb, poly);
+    const u64 *inp = lc.in + (size_t)row * R2 + (lane >> 4) * 128 + 2 * (lane & 15);
+    double a[8];
+    double2 w[4], wn[4];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(u, r) * RP + c];
-    gs_round<LR, 6, 2>(a, u, lc.tw, R1 + row0 + c, lc.q);
+    for (int j = 0; j < 4; ++j) wn[j] = __ldg(&lc.tw[lane_stage_tw(tw_base, 0, j, lane)]);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) sm[RD::point(u, r) * RP + c] = a[r];
-  }
-  __syncthreads();
-  {
-    using RD = Round<LR, 3, 3>;
+    for (int j = 0; j < 4; ++j) {
+      const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(inp + j * 32));
+      a[j] = u64_to_f64(v.x);
+      a[j + 4] = u64_to_f64(v.y);
+    }
 #pragma unroll
-    for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(u, r) * RP + c];
-    gs_round<LR, 3, 3>(a, u, lc.tw, R1 + row0 + c, lc.q);
+    for (int b = 0; b <= 4; ++b) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) sm[RD::point(u, r) * RP + c] = a[r];
-  }
-  __syncthreads();
-  {
-    const int uu = threadIdx.x % 32, n = threadIdx.x / 32;
-    using RD = Round<LR, 0, 3>;
+      for (int j = 0; j < 4; ++j) w[j] = wn[j];
+      if (b < 4) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(uu, r) * RP + n];
-    gs_round<LR, 0, 3>(a, uu, lc.tw, R1 + row0 + n, lc.q);
-    double *outd = reinterpret_cast<double *>(lc.out);
-    const size_t base = (size_t)(row0 + n) * R2;
+        for (int j = 0; j < 4; ++j) wn[j] = __ldg(&lc.tw[lane_stage_tw(tw_base, b + 1, j, lane)]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gs_butterfly(a[j], a[j + 4], w[j].x, w[j].y, lc.q);
+      swap_half(a, b, (lane >> b) & 1);
+    }
+    gs_round<LR, 0, 3>(a, lane, lc.tw, tw_base, lc.q);
+    double *outd = reinterpret_cast<double *>(lc.out) + (size_t)row * R2;
     // the sums have grown to <= 2^8 q: bring them back to |v| <= q/2 before the column pass doubles them again
 #pragma unroll
-    for (int r = 0; r < 8; ++r) outd[base + RD::point(uu, r)] = reduce_signed(a[r], lc.q, lc.qinv);
+    for (int r = 0; r < 8; ++r) outd[r * 32 + lane] = reduce_signed(a[r], lc.q, lc.qinv);
   }
 }
 
@@ -239,7 +248,9 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_inv_cols(NttTables t, int 
   constexpr int R1 = 1 << LOGR1, C = NTT_TILE / R1, R2 = 1 << NTT_ROW_LOG;
   using SP = Split<LOGR1>;
   extern __shared__ double sm[];
-  const LimbCtx lc = limb_ctx(t, logN, lm, l, true);
+  const int limb = blockIdx.y % l.n_limbs, poly = blockIdx.y / l.n_limbs;
+  if (poly == lm.skip[limb]) return;
+  const LimbCtx lc = limb_ctx(t, logN, lm, l, true, limb, poly);
   const int c = threadIdx.x % C, u = threadIdx.x / C;
   const int col = blockIdx.x * C + c;
   const double *ind = reinterpret_cast<const double *>(lc.out);
@@ -284,7 +295,9 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_inv_cols(NttTables t, int 
 // ================================================================================ small N (<= 4096): one CTA per limb
 __global__ void __launch_bounds__(256) ntt_small(NttTables t, int logN, LimbMap lm, NttLaunch l, int inverse) {
   extern __shared__ double sm[];
-  const LimbCtx lc = limb_ctx(t, logN, lm, l, inverse != 0);
+  const int limb = blockIdx.y % l.n_limbs, poly = blockIdx.y / l.n_limbs;
+  if (poly == lm.skip[limb]) return;
+  const LimbCtx lc = limb_ctx(t, logN, lm, l, inverse != 0, limb, poly);
   const int N = 1 << logN, half = N >> 1;
   for (int i = threadIdx.x; i < N; i += blockDim.x) sm[i] = u64_to_f64(__ldg(&lc.in[i]));
   __syncthreads();
@@ -327,15 +340,15 @@ __global__ void __launch_bounds__(256) ntt_small(NttTables t, int logN, LimbMap 
 template <int LOGR1>
 static void launch_fwd_t(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
   constexpr int C = NTT_TILE >> LOGR1;
-  const dim3 g1((1 << NTT_ROW_LOG) / C, l.n_limbs * l.n_polys), g2((1 << LOGR1) / ROWS, l.n_limbs * l.n_polys);
+  const dim3 g1((1 << NTT_ROW_LOG) / C, l.n_limbs * l.n_polys), g2((1 << LOGR1) / ROW_WARPS, l.n_limbs);
   ntt_fwd_cols<LOGR1><<<g1, NTT_THREADS, NTT_TILE * sizeof(double), s>>>(t, logN, lm, l);
-  ntt_fwd_rows<<<g2, NTT_THREADS, 0, s>>>(t, logN, lm, l);
+  ntt_fwd_rows<<<g2, ROW_WARPS * 32, 0, s>>>(t, logN, lm, l);
 }
 template <int LOGR1>
 static void launch_inv_t(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
   constexpr int C = NTT_TILE >> LOGR1;
-  const dim3 g1((1 << LOGR1) / ROWS, l.n_limbs * l.n_polys), g2((1 << NTT_ROW_LOG) / C, l.n_limbs * l.n_polys);
-  ntt_inv_rows<<<g1, NTT_THREADS, 0, s>>>(t, logN, lm, l);
+  const dim3 g1((1 << LOGR1) / ROW_WARPS, l.n_limbs), g2((1 << NTT_ROW_LOG) / C, l.n_limbs * l.n_polys);
+  ntt_inv_rows<<<g1, ROW_WARPS * 32, 0, s>>>(t, logN, lm, l);
   ntt_inv_cols<LOGR1><<<g2, NTT_THREADS, NTT_TILE * sizeof(double), s>>>(t, logN, lm, l);
 }
 

@@ -28,6 +28,8 @@ constexpr int NTT_MAX_LIMBS = 128; // limbs (x polys) per launch
 struct LimbMap {
   uint16_t mod[NTT_MAX_LIMBS];  // modulus index of each limb of the launch
   uint16_t pos[NTT_MAX_LIMBS];  // NTT launches: limb slot inside the buffer (address = base + pos * limb_stride)
+  uint8_t skip[NTT_MAX_LIMBS];  // NTT launches: poly index NOT to transform for this limb (0xFF = none); used by
+                                // ModUp, where digit j's own limbs stay as they are
 };
 
 // Twiddle tables: per modulus, N entries of (w, RN(w/q)) as double2, index = bit-reversed exponent

@@ -22,7 +22,41 @@ evk = ctx.uniform(ctx.ext_mod_idx(L), 3, lead=(3, 2))
 a = ctx.uniform(q, 1, lead=(2,))
 b = ctx.uniform(q, 2, lead=(2,))
 torch.cuda.synchronize()
-if op == "ntt":
+def timeit(fn, reps=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / reps
+
+
+if op == "time":
+    idx = [ctx.ext_mod_idx(L)[i % 50] for i in range(115)]
+    xs = [ctx.uniform(idx, 5 + i) for i in range(4)]
+    y = ctx.empty(115, ctx.N)
+    k = [0]
+
+    def f_ntt():
+        k[0] += 1
+        ctx.ntt(xs[k[0] % 4], idx, out=y)
+
+    def f_intt():
+        k[0] += 1
+        ctx.intt(xs[k[0] % 4], idx, out=y)
+
+    t_ntt, t_intt = timeit(f_ntt), timeit(f_intt)
+    print("ntt  115 limbs: %.1f us = %.3f us/limb = %.2f Mlimb/s" % (t_ntt, t_ntt / 115, 115 / t_ntt))
+    print("intt 115 limbs: %.1f us = %.3f us/limb = %.2f Mlimb/s" % (t_intt, t_intt / 115, 115 / t_intt))
+    print("hmult   %.1f us" % timeit(lambda: ctx.hmult(L, a, b, evk)))
+    print("hrotate %.1f us" % timeit(lambda: ctx.hrotate(L, a, evk, 5)))
+    d = ctx.uniform(q, 9)
+    print("keyswitch %.1f us" % timeit(lambda: ctx.keyswitch(L, d, evk)))
+elif op == "ntt":
     idx = [ctx.ext_mod_idx(L)[i % 50] for i in range(115)]
     x = ctx.uniform(idx, 5)
     y = ctx.empty(115, ctx.N)
