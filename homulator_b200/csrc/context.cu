@@ -37,10 +37,41 @@ static int upload(hml_ctx *ctx, const std::vector<T> &h, T **dev) {
   return HML_OK;
 }
 
-static void split12(u64 h, double *out3) {
-  out3[0] = (double)(h & 0xFFF);
-  out3[1] = (double)((h >> 12) & 0xFFF);
-  out3[2] = (double)(h >> 24);
+// A base conversion prepared for launch: destination limbs split into chunks that fit kernel-parameter space
+// (n_src * chunk <= BCONV_MAX_PAIRS), each with its matrix in 12-bit pieces and its destination LimbMap.
+static void prepare_bconv(const BConvTable &bt, hml::HostBConv &out) {
+  const int ns = (int)bt.src.size(), nd = (int)bt.dst.size();
+  int chunk = BCONV_MAX_PAIRS / ns;
+  if (chunk >= nd) chunk = nd;
+  else chunk -= chunk % 7 ? chunk % 7 : 0;  // keep chunks a multiple of the tallest tile
+  out.n_src = ns; out.n_dst = nd;
+  out.chunks.clear();
+  for (int first = 0; first < nd; first += chunk) {
+    hml::HostBConvChunk ch;
+    ch.first = first; ch.count = std::min(chunk, nd - first);
+    memset(&ch.mat, 0, sizeof(ch.mat));
+    memset(&ch.dst_lm, 0, sizeof(ch.dst_lm));
+    for (int t = 0; t < ch.count; ++t) {
+      ch.dst_lm.mod[t] = (uint16_t)bt.dst[first + t];
+      for (int i = 0; i < ns; ++i) {
+        const u64 h = bt.hat[(size_t)i * nd + first + t];
+        double *d = &ch.mat.h[((size_t)i * ch.count + t) * 3];
+        d[0] = (double)(h & 0xFFF);
+        d[1] = (double)((h >> 12) & 0xFFF);
+        d[2] = (double)(h >> 24);
+      }
+    }
+    out.chunks.push_back(ch);
+  }
+}
+
+static void run_bconv(hml_ctx *ctx, const hml::HostBConv &hb, const LimbMap &src_lm, BConvArgs a, cudaStream_t s) {
+  for (const auto &ch : hb.chunks) {
+    a.n_src = hb.n_src; a.n_dst = ch.count; a.out_first = ch.first;
+    launch_bconv(ctx->mc, src_lm, ch.dst_lm, a, ch.mat, s);
+    ctx->exec.kernel_launches++;
+  }
+  ctx->exec.bconv_limb_macs += (uint64_t)hb.n_src * hb.n_dst * a.n_batches;
 }
 
 // ------------------------------------------------------------------------------------------------ creation
@@ -116,15 +147,14 @@ extern "C" int hml_ctx_create(const char *cfg_path, uint32_t max_level, uint32_t
 }
 
 static void free_level(LevelConsts &lc) {
-  cudaFree(lc.modup_scale); cudaFree(lc.moddown_scale); cudaFree(lc.down_hat3); cudaFree(lc.pinv); cudaFree(lc.qlinv);
-  for (double *p : lc.up_hat3) cudaFree(p);
+  cudaFree(lc.modup_scale); cudaFree(lc.moddown_scale); cudaFree(lc.pinv); cudaFree(lc.qlinv);
 }
 
 extern "C" void hml_ctx_destroy(hml_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   for (auto &kv : ctx->levels) free_level(kv.second);
-  for (auto &kv : ctx->bconv_cache) { cudaFree(kv.second.step1); cudaFree(kv.second.hat3); }
+  for (auto &kv : ctx->bconv_cache) cudaFree(kv.second.step1);
   cudaFree(ctx->tw_fwd); cudaFree(ctx->tw_inv); cudaFree(ctx->mc); cudaFree(ctx->ws); cudaFree(ctx->stage);
   if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
   if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
@@ -219,10 +249,8 @@ static int get_level(hml_ctx *ctx, uint32_t L, LevelConsts **out) {
     const uint32_t lo = j * A, aj = p.digit_size(L, j);
     std::vector<uint32_t> src, dst;
     for (uint32_t i = 0; i < aj; ++i) src.push_back(lo + i);
-    LimbMap dlm; clear_map(dlm);
     for (uint32_t e = 0; e < E; ++e) {
       if (e >= lo && e < lo + aj) continue;
-      dlm.mod[dst.size()] = p.ext_mod(L, e);
       dst.push_back(p.ext_mod(L, e));
     }
     BConvTable bt;
@@ -231,12 +259,8 @@ static int get_level(hml_ctx *ctx, uint32_t L, LevelConsts **out) {
       const u64 q = p.mod[lo + i];
       up_scale[lo + i] = mk_cst(h_mulmod(p.n_inv[lo + i], bt.hat_inv[i], q), q);
     }
-    std::vector<double> h3(bt.hat.size() * 3);
-    for (size_t k = 0; k < bt.hat.size(); ++k) split12(bt.hat[k], &h3[k * 3]);
-    double *d3 = nullptr;
-    if ((rc = upload(ctx, h3, &d3))) return rc;
-    lc.up_hat3.push_back(d3);
-    lc.up_dst.push_back(dlm);
+    lc.up.emplace_back();
+    prepare_bconv(bt, lc.up.back());
   }
   if ((rc = upload(ctx, up_scale, &lc.modup_scale))) return rc;
   // ---- ModDown
@@ -257,10 +281,8 @@ static int get_level(hml_ctx *ctx, uint32_t L, LevelConsts **out) {
       for (uint32_t j = 0; j < A; ++j) P = h_mulmod(P, p.mod[p.max_level + j] % q, q);
       pinv[i] = mk_cst(h_invmod(P, q), q);
     }
-    std::vector<double> h3(bt.hat.size() * 3);
-    for (size_t k = 0; k < bt.hat.size(); ++k) split12(bt.hat[k], &h3[k * 3]);
+    prepare_bconv(bt, lc.down);
     if ((rc = upload(ctx, sc, &lc.moddown_scale))) return rc;
-    if ((rc = upload(ctx, h3, &lc.down_hat3))) return rc;
     if ((rc = upload(ctx, pinv, &lc.pinv))) return rc;
   }
   // ---- Rescale
@@ -358,24 +380,19 @@ extern "C" int hml_bconv(hml_ctx *ctx, const uint64_t *in, const uint32_t *src_i
     make_bconv_table(ctx->p, std::vector<uint32_t>(src_idx, src_idx + n_src), std::vector<uint32_t>(dst_idx, dst_idx + n_dst), bt);
     std::vector<double2> s1(n_src);
     for (uint32_t i = 0; i < n_src; ++i) s1[i] = mk_cst(bt.hat_inv[i], ctx->p.mod[src_idx[i]]);
-    std::vector<double> h3(bt.hat.size() * 3);
-    for (size_t k = 0; k < bt.hat.size(); ++k) split12(bt.hat[k], &h3[k * 3]);
     DevBConv d;
     int rc;
     if ((rc = upload(ctx, s1, &d.step1))) return rc;
-    if ((rc = upload(ctx, h3, &d.hat3))) return rc;
+    prepare_bconv(bt, d.host);
     it = ctx->bconv_cache.emplace(key, d).first;
   }
-  LimbMap slm, dlm;
+  LimbMap slm;
   id_map(slm, src_idx, n_src);
-  id_map(dlm, dst_idx, n_dst);
   BConvArgs a{};
-  a.in = (const u64 *)in; a.out = (u64 *)out; a.step1 = it->second.step1; a.hat3 = it->second.hat3;
-  a.N = ctx->p.N; a.n_src = n_src; a.n_dst = n_dst; a.n_batches = 1; a.out_gap_start = n_dst; a.out_gap_len = 0;
-  launch_bconv(ctx->mc, slm, dlm, a, (cudaStream_t)stream);
-  ctx->exec.kernel_launches++;
+  a.in = (const u64 *)in; a.out = (u64 *)out; a.step1 = it->second.step1;
+  a.N = ctx->p.N; a.n_batches = 1; a.out_gap_start = n_dst; a.out_gap_len = 0;
+  run_bconv(ctx, it->second.host, slm, a, (cudaStream_t)stream);
   ctx->exec.ewe_limbs += n_src;  // step 1
-  ctx->exec.bconv_limb_macs += (uint64_t)n_src * n_dst;
   return check_launch(ctx, "bconv");
 }
 
@@ -408,10 +425,9 @@ static int ks_run(hml_ctx *ctx, uint32_t L, const u64 *d, const u64 *evk, uint32
   for (uint32_t j = 0; j < beta; ++j) {
     const uint32_t lo = j * A, aj = p.digit_size(L, j);
     BConvArgs a{};
-    a.in = yb + (size_t)lo * N; a.out = ext + (size_t)j * E * N; a.step1 = nullptr; a.hat3 = lc->up_hat3[j];
-    a.N = N; a.n_src = aj; a.n_dst = E - aj; a.n_batches = 1; a.out_gap_start = lo; a.out_gap_len = aj;
-    launch_bconv(ctx->mc, lc->q_lm, lc->up_dst[j], a, s);
-    ctx->exec.bconv_limb_macs += (uint64_t)aj * (E - aj); ctx->exec.kernel_launches++;
+    a.in = yb + (size_t)lo * N; a.out = ext + (size_t)j * E * N; a.step1 = nullptr;
+    a.N = N; a.n_batches = 1; a.out_gap_start = lo; a.out_gap_len = aj;
+    run_bconv(ctx, lc->up[j], lc->q_lm, a, s);
   }
   // K4 (reference :190-292): NTT of the converted limbs.  The digit's own limbs are the untouched input
   // (delta D3: the reference also counts an NTT for those).
@@ -442,10 +458,9 @@ static int ks_run(hml_ctx *ctx, uint32_t L, const u64 *d, const u64 *evk, uint32
   {
     BConvArgs a{};
     a.in = acc + (size_t)L * N; a.out = vb; a.in_batch_stride = (long long)E * N; a.out_batch_stride = (long long)L * N;
-    a.step1 = nullptr; a.hat3 = lc->down_hat3; a.N = N; a.n_src = A; a.n_dst = L; a.n_batches = 2;
+    a.step1 = nullptr; a.N = N; a.n_batches = 2;
     a.out_gap_start = L; a.out_gap_len = 0;
-    launch_bconv(ctx->mc, lc->p_lm, lc->q_lm, a, s);
-    ctx->exec.bconv_limb_macs += 2ull * A * L; ctx->exec.kernel_launches++;
+    run_bconv(ctx, lc->down, lc->p_lm, a, s);
   }
   // K9 (reference :521-546, emitted with opcode INTT — delta D1): forward NTT of the converted limbs
   {

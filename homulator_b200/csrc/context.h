@@ -14,19 +14,28 @@
 
 namespace hml {
 
+struct HostBConvChunk {
+  int first = 0, count = 0;   // destination limbs [first, first + count)
+  BConvMatrix mat;
+  LimbMap dst_lm;
+};
+struct HostBConv {
+  int n_src = 0, n_dst = 0;
+  std::vector<HostBConvChunk> chunks;
+};
+
 // Per-level constants of the key-switch / rescale pipeline (SURVEY.md Appendix A "Constant tables").
 struct LevelConsts {
   uint32_t L = 0, beta = 0, E = 0;
   // K1+K2 fused: INTT post-scale  N^-1 * (D_j/q_i)^-1 mod q_i  for every input limb i (digit j = i / alpha)
   double2 *modup_scale = nullptr;            // [L]
-  // K3: per digit, the conversion matrix to the E - a_j other limbs, split in 12-bit pieces
-  std::vector<double *> up_hat3;             // [beta] -> [a_j][E - a_j][3]
-  std::vector<LimbMap> up_dst;               // modulus of each output limb (gap-free numbering)
+  // K3: per digit, the conversion to the E - a_j other limbs (matrix in 12-bit pieces, kernel-parameter resident)
+  std::vector<HostBConv> up;                 // [beta]
   // K4: limbs = the E extended limbs, polys = the beta digits, skip = the digit that owns the limb
   LimbMap ext_lm;
   // K6+K7 fused: INTT post-scale N^-1 * (P/p_j)^-1 mod p_j;  K8 matrix [alpha][L][3];  K10 constant P^-1 mod q_i
   double2 *moddown_scale = nullptr;          // [alpha]
-  double *down_hat3 = nullptr;
+  HostBConv down;
   double2 *pinv = nullptr;                   // [L]
   // Rescale: q_{L-1}^-1 mod q_l
   double2 *qlinv = nullptr;                  // [L-1]
@@ -36,7 +45,7 @@ struct LevelConsts {
 
 struct DevBConv {  // cached tables of an arbitrary (src, dst) conversion for the primitive entry point
   double2 *step1 = nullptr;
-  double *hat3 = nullptr;
+  HostBConv host;
 };
 
 }  // namespace hml

@@ -147,92 +147,129 @@ void launch_automorph(int logN, int n_limbs, const u64 *in, u64 *out, u64 g, cud
 }
 
 // ------------------------------------------------------------------------------------------------ base conversion
-constexpr int BC_THREADS = 128;  // 2 coefficients per thread
-constexpr int BC_OT = 8;         // output limbs per CTA
+// One CTA = 256 coefficients (two per thread) x OT output limbs.  The inner loop is 3 DFMA per modular MAC
+// (12-bit-split matrix, exact double sums):
+//   * input words come through a 4-deep register ring (loads for sources i+1..i+4 in flight while source i is
+//     accumulated);
+//   * the matrix operand does not go through the LSU: the whole [n_src][n_dst][3] matrix travels in
+//     kernel-parameter space (constant bank, __grid_constant__, <= 30 KB), so each matrix word is a constant
+//     load feeding DFMA.  (A shared-memory broadcast costs one LSU wavefront per load and made an earlier
+//     version LSU-bound — profiles/README.md.)
+//   * the epilogue is branch-free with its moduli in shared memory, so the 2*OT dependent reduction chains
+//     interleave instead of running one after another behind a global load each.
+// OT is chosen by the launcher so that n_dst splits without padding (35 = 5x7, 45 = 9x5, 50 = 10x5).
+constexpr int BC_THREADS = 128;
+constexpr int BC_RING = 4;
 
-template <bool STEP1>
-__global__ void __launch_bounds__(BC_THREADS) k_bconv(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BConvArgs a) {
-  extern __shared__ double hs[];  // [n_src][BC_OT][3]
-  __shared__ double qs[BC_OT], qinvs[BC_OT];
-  __shared__ u64 qis[BC_OT];
-  const int t0 = blockIdx.y * BC_OT;
-  const int nt = min(BC_OT, a.n_dst - t0);
-  for (int idx = threadIdx.x; idx < a.n_src * BC_OT * 3; idx += BC_THREADS) {
-    const int i = idx / (BC_OT * 3), rem = idx % (BC_OT * 3), o = rem / 3, k = rem % 3;
-    hs[idx] = o < nt ? a.hat3[((size_t)i * a.n_dst + t0 + o) * 3 + k] : 0.0;
-  }
-  if (threadIdx.x < BC_OT) {
-    const ModConst m = mc[dst_lm.mod[min(t0 + (int)threadIdx.x, a.n_dst - 1)]];
+template <int OT, bool STEP1>
+__global__ void __launch_bounds__(BC_THREADS, 4) k_bconv(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BConvArgs a,
+                                                         const __grid_constant__ BConvMatrix mat) {
+  __shared__ double qs[OT], qinvs[OT];
+  __shared__ u64 qis[OT];
+  const int t0 = blockIdx.y * OT;
+  const int nt = min(OT, a.n_dst - t0);
+  if (threadIdx.x < OT) {
+    const ModConst m = mc[dst_lm.mod[min(t0 + (int)threadIdx.x, a.n_dst - 1)]];  // a padded tail repeats the last modulus
     qs[threadIdx.x] = m.q; qinvs[threadIdx.x] = m.qinv; qis[threadIdx.x] = m.qi;
   }
-  __syncthreads();
-  const int i2 = blockIdx.x * BC_THREADS + threadIdx.x;
-  if (i2 >= a.N / 2) return;
+  const int i2 = min(blockIdx.x * BC_THREADS + threadIdx.x, (unsigned)(a.N / 2 - 1));
+  const bool live = blockIdx.x * BC_THREADS + threadIdx.x < (unsigned)(a.N / 2);
   const size_t n2 = a.N / 2;
-  const u64 *in = a.in + (size_t)blockIdx.z * a.in_batch_stride;
+  const ulonglong2 *in = reinterpret_cast<const ulonglong2 *>(a.in + (size_t)blockIdx.z * a.in_batch_stride) + i2;
   u64 *out = a.out + (size_t)blockIdx.z * a.out_batch_stride;
-  double acc[BC_OT][3][2];
+  ulonglong2 ring[BC_RING];
 #pragma unroll
-  for (int o = 0; o < BC_OT; ++o)
+  for (int k = 0; k < BC_RING; ++k) ring[k] = __ldg(in + (size_t)min(k, a.n_src - 1) * n2);
+  __syncthreads();
+  double acc[OT][3][2];
+#pragma unroll
+  for (int o = 0; o < OT; ++o)
 #pragma unroll
     for (int k = 0; k < 3; ++k) acc[o][k][0] = acc[o][k][1] = 0.0;
-  // software pipeline: the loads of sources i+1, i+2 are in flight while source i is accumulated
-  ulonglong2 pre0 = ld2(in, i2), pre1 = ld2(in, (size_t)min(1, a.n_src - 1) * n2 + i2);
-  for (int i = 0; i < a.n_src; ++i) {
-    const ulonglong2 xv = pre0;
-    pre0 = pre1;
-    pre1 = ld2(in, (size_t)min(i + 2, a.n_src - 1) * n2 + i2);
-    double y0 = u64_to_f64(xv.x), y1 = u64_to_f64(xv.y);
-    if (STEP1) {
-      const ModConst m = mc[src_lm.mod[i]];
-      const double2 sc = a.step1[i];
-      y0 = canonicalize(mulmod_const(y0, sc.x, sc.y, m.q), m.q);
-      y1 = canonicalize(mulmod_const(y1, sc.x, sc.y, m.q), m.q);
-    }
-    const double *h = hs + i * (BC_OT * 3);
+  for (int i0 = 0; i0 < a.n_src; i0 += BC_RING) {
 #pragma unroll
-    for (int o = 0; o < BC_OT; ++o)
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const double hv = h[o * 3 + k];
-        acc[o][k][0] = __fma_rn(y0, hv, acc[o][k][0]);
-        acc[o][k][1] = __fma_rn(y1, hv, acc[o][k][1]);
-      }
-    // each term is < 2^36 * 2^12; fold every 16 sources so the exact sums stay below 2^53
-    if ((i & 15) == 15 && i + 1 < a.n_src) {
-#pragma unroll
-      for (int o = 0; o < BC_OT; ++o)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          acc[o][k][0] = reduce_signed(acc[o][k][0], qs[o], qinvs[o]);
-          acc[o][k][1] = reduce_signed(acc[o][k][1], qs[o], qinvs[o]);
+    for (int k = 0; k < BC_RING; ++k) {
+      const int i = i0 + k;
+      if (i < a.n_src) {
+        double y0 = u64_to_f64(ring[k].x), y1 = u64_to_f64(ring[k].y);
+        ring[k] = __ldg(in + (size_t)min(i + BC_RING, a.n_src - 1) * n2);
+        if (STEP1) {
+          const ModConst m = mc[src_lm.mod[i]];
+          const double2 sc = a.step1[i];
+          y0 = canonicalize(mulmod_const(y0, sc.x, sc.y, m.q), m.q);
+          y1 = canonicalize(mulmod_const(y1, sc.x, sc.y, m.q), m.q);
         }
+        const int hb = (i * a.n_dst + t0) * 3;  // uniform: matrix row of source i, first output of this tile
+#pragma unroll
+        for (int o = 0; o < OT; ++o)
+#pragma unroll
+          for (int kk = 0; kk < 3; ++kk) {
+            const double hv = mat.h[hb + o * 3 + kk];  // the struct's padding keeps a partial last tile in bounds
+            acc[o][kk][0] = __fma_rn(y0, hv, acc[o][kk][0]);
+            acc[o][kk][1] = __fma_rn(y1, hv, acc[o][kk][1]);
+          }
+        // each term is < 2^36 * 2^12; fold every 16 sources so the exact sums stay below 2^53
+        if ((i & 15) == 15 && i + 1 < a.n_src) {
+#pragma unroll
+          for (int o = 0; o < OT; ++o)
+#pragma unroll
+            for (int kk = 0; kk < 3; ++kk) {
+              acc[o][kk][0] = reduce_signed(acc[o][kk][0], qs[o], qinvs[o]);
+              acc[o][kk][1] = reduce_signed(acc[o][kk][1], qs[o], qinvs[o]);
+            }
+        }
+      }
     }
   }
+  // branch-free epilogue: all 2*OT reduction chains are independent and interleave; only the store is predicated
+  u64 r[OT][2];
 #pragma unroll
-  for (int o = 0; o < BC_OT; ++o) {
+  for (int o = 0; o < OT; ++o) {
+    const double q = qs[o], qinv = qinvs[o];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      // value = S2*2^24 + S1*2^12 + S0 (mod q), folded top-down; every intermediate is an exact integer < 2^53
+      double v = reduce_signed(acc[o][2][c], q, qinv);
+      v = reduce_signed(__fma_rn(v, 4096.0, acc[o][1][c]), q, qinv);
+      v = reduce_signed(__fma_rn(v, 4096.0, acc[o][0][c]), q, qinv);
+      r[o][c] = f64_to_canonical(v, qis[o]);
+    }
+  }
+  if (!live) return;
+#pragma unroll
+  for (int o = 0; o < OT; ++o) {
     if (o < nt) {
-      const double q = qs[o], qinv = qinvs[o];
-      u64 r[2];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        // value = S2*2^24 + S1*2^12 + S0 (mod q), folded top-down; every intermediate is an exact integer < 2^53
-        double v = reduce_signed(acc[o][2][c], q, qinv);
-        v = reduce_signed(__fma_rn(v, 4096.0, acc[o][1][c]), q, qinv);
-        v = reduce_signed(__fma_rn(v, 4096.0, acc[o][0][c]), q, qinv);
-        r[c] = f64_to_canonical(v, qis[o]);
-      }
-      const int t = t0 + o, slot = t < a.out_gap_start ? t : t + a.out_gap_len;
-      st2(out, (size_t)slot * n2 + i2, r[0], r[1]);
+      const int t = a.out_first + t0 + o, slot = t < a.out_gap_start ? t : t + a.out_gap_len;
+      st2(out, (size_t)slot * n2 + i2, r[o][0], r[o][1]);
     }
   }
 }
 
-void launch_bconv(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, cudaStream_t s) {
-  const dim3 grid((a.N / 2 + BC_THREADS - 1) / BC_THREADS, (a.n_dst + BC_OT - 1) / BC_OT, a.n_batches);
-  const size_t smem = (size_t)a.n_src * BC_OT * 3 * sizeof(double);
-  if (a.step1) k_bconv<true><<<grid, BC_THREADS, smem, s>>>(mc, src_lm, dst_lm, a);
-  else k_bconv<false><<<grid, BC_THREADS, smem, s>>>(mc, src_lm, dst_lm, a);
+int bconv_tile_height(int n_dst) {
+  // the tile height that wastes the fewest padded output limbs (ties -> the taller tile)
+  int best = 7, waste = 1 << 30;
+  for (int ot : {7, 6, 5}) {
+    const int w = (n_dst + ot - 1) / ot * ot - n_dst;
+    if (w < waste) { waste = w; best = ot; }
+  }
+  return best;
+}
+
+template <int OT>
+static void launch_bconv_t(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a,
+                           const BConvMatrix &mat, cudaStream_t s) {
+  const dim3 grid((a.N / 2 + BC_THREADS - 1) / BC_THREADS, (a.n_dst + OT - 1) / OT, a.n_batches);
+  if (a.step1) k_bconv<OT, true><<<grid, BC_THREADS, 0, s>>>(mc, src_lm, dst_lm, a, mat);
+  else k_bconv<OT, false><<<grid, BC_THREADS, 0, s>>>(mc, src_lm, dst_lm, a, mat);
+}
+
+void launch_bconv(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const BConvMatrix &mat,
+                  cudaStream_t s) {
+  switch (bconv_tile_height(a.n_dst)) {
+    case 7: launch_bconv_t<7>(mc, src_lm, dst_lm, a, mat, s); break;
+    case 6: launch_bconv_t<6>(mc, src_lm, dst_lm, a, mat, s); break;
+    default: launch_bconv_t<5>(mc, src_lm, dst_lm, a, mat, s); break;
+  }
 }
 
 }  // namespace hml

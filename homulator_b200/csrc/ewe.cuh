@@ -47,16 +47,23 @@ void launch_automorph(int logN, int n_limbs, const u64 *in, u64 *out, u64 g, cud
 // Fast base conversion.  in [n_src][N] coefficient form.  If step1 != nullptr the per-source scaling
 // y_i = in_i * hat_inv_i mod s_i is applied inside (step1[i] = (hat_inv_i, RN(hat_inv_i / s_i)));
 // otherwise `in` must already hold y_i (the fused pipeline folds it into the preceding INTT).
-// hat3: [n_src][n_dst][3] the matrix (D/s_i mod t) split into three 12-bit pieces, as doubles.
+// The matrix (D/s_i mod t), split into three 12-bit pieces as doubles, is passed BY VALUE in kernel-parameter
+// space: h[(i * n_dst + t) * 3 + k].  One launch handles n_src * n_dst <= BCONV_MAX_PAIRS (callers chunk n_dst).
+constexpr int BCONV_MAX_PAIRS = 1200;
+struct BConvMatrix {
+  double h[(BCONV_MAX_PAIRS + 8) * 3];  // + one padded tile row so a partial last tile reads zeros
+};
 struct BConvArgs {
   const u64 *in;
   u64 *out;
   long long in_batch_stride, out_batch_stride;  // grid.z batches (e.g. the two key-switch accumulators)
   const double2 *step1;   // [n_src] or null
-  const double *hat3;     // [n_src][n_dst][3]
   int N, n_src, n_dst, n_batches;
-  int out_gap_start, out_gap_len;  // output limb t is stored at slot t (t < gap_start) or t + gap_len
+  int out_first;                   // global index of this launch's first output limb (n_dst chunking)
+  int out_gap_start, out_gap_len;  // global output limb t is stored at slot t (t < gap_start) or t + gap_len
 };
-void launch_bconv(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, cudaStream_t s);
+int bconv_tile_height(int n_dst);
+void launch_bconv(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const BConvMatrix &mat,
+                  cudaStream_t s);
 
 }  // namespace hml
