@@ -31,6 +31,11 @@ class _Counts(C.Structure):
                 ("stages", _StageCount * HML_MAX_STAGES)]
 
 
+class _ShardInfo(C.Structure):
+    _fields_ = [("gather1_slots", C.c_uint32), ("gather2_slots", C.c_uint32), ("n_own_q", C.c_uint32), ("n_own_p", C.c_uint32),
+                ("own_q", C.c_uint32 * 128), ("own_p", C.c_uint32 * 128), ("owner", C.c_uint32 * 128), ("slot", C.c_uint32 * 128)]
+
+
 class _ExecCounts(C.Structure):
     _fields_ = [("ntt_limbs", C.c_uint64), ("intt_limbs", C.c_uint64), ("ewe_limbs", C.c_uint64),
                 ("bconv_limb_macs", C.c_uint64), ("automorph_limbs", C.c_uint64), ("kernel_launches", C.c_uint64)]
@@ -48,6 +53,7 @@ EXPORTS = [
     "hml_hmult", "hml_hrotate", "hml_hadd", "hml_pmult", "hml_padd", "hml_hmult_batch", "hml_hrotate_batch",
     "hml_hmult_host", "hml_hrotate_host", "hml_host_alloc_pinned", "hml_host_free_pinned", "hml_trace_counts",
     "hml_get_counts", "hml_exec_counts_get", "hml_exec_counts_reset", "hml_cli_main",
+    "hml_shard_layout", "hml_keyswitch_shard_begin", "hml_keyswitch_shard_mid", "hml_keyswitch_shard_end",
 ]
 
 
@@ -97,6 +103,10 @@ def load_library():
     L.hml_exec_counts_get.argtypes = [vp, C.POINTER(_ExecCounts)]
     L.hml_exec_counts_reset.argtypes = [vp]
     L.hml_cli_main.argtypes = [i32, C.POINTER(C.c_char_p)]
+    L.hml_shard_layout.argtypes = [u32, u32, u32, u32, C.POINTER(_ShardInfo)]
+    L.hml_keyswitch_shard_begin.argtypes = [vp, u32, u32, u32, vp, vp, vp]
+    L.hml_keyswitch_shard_mid.argtypes = [vp, u32, u32, u32, vp, vp, vp, vp, vp]
+    L.hml_keyswitch_shard_end.argtypes = [vp, u32, u32, u32, vp, vp, vp, vp]
     _LIB = L
     return L
 
@@ -118,6 +128,19 @@ def trace_counts(op, N, batch_size, max_level, L, alpha, bconv_high=2, bconv_wid
     if rc:
         raise HmlError(rc, lib.hml_last_create_error().decode())
     return _counts_to_dict(c)
+
+
+def shard_layout(L, alpha, rank, world):
+    """Ownership / gather-slot layout of the limb-sharded key switch (pure host code in the library)."""
+    lib = load_library()
+    s = _ShardInfo()
+    rc = lib.hml_shard_layout(L, alpha, rank, world, C.byref(s))
+    if rc:
+        raise HmlError(rc, "bad shard layout arguments")
+    E = L + alpha
+    return {"gather1_slots": s.gather1_slots, "gather2_slots": s.gather2_slots,
+            "own_q": [s.own_q[i] for i in range(s.n_own_q)], "own_p": [s.own_p[i] for i in range(s.n_own_p)],
+            "owner": [s.owner[e] for e in range(E)], "slot": [s.slot[e] for e in range(E)]}
 
 
 def algorithmic_words(op, L, alpha):
@@ -293,6 +316,22 @@ class Context:
         self._chk(self.lib.hml_hrotate_host(self.h, L, n, ct_host.data_ptr(), _ptr(rotkey_dev), evk_q_limbs or L, galois_elt,
                                             out_host.data_ptr()))
         return out_host
+
+    def keyswitch_sharded(self, L, d_own, evk_own, rank, world, all_gather):
+        """Limb-sharded key switch (SURVEY.md 8e mode 2).  `all_gather(buf)` must all-gather, in place along dim 0,
+        a tensor whose slice [rank] this rank has filled (torch.distributed.all_gather_into_tensor(buf, buf[rank]))."""
+        lay = shard_layout(L, self.alpha, rank, world)
+        nq = len(lay["own_q"])
+        g1 = self.empty(world, lay["gather1_slots"], self.N)
+        g2 = self.empty(world, 2, lay["gather2_slots"], self.N)
+        o0, o1 = self.empty(max(nq, 1), self.N), self.empty(max(nq, 1), self.N)
+        st = self._stream()
+        self._chk(self.lib.hml_keyswitch_shard_begin(self.h, L, rank, world, _ptr(d_own), _ptr(g1), st))
+        all_gather(g1)
+        self._chk(self.lib.hml_keyswitch_shard_mid(self.h, L, rank, world, _ptr(d_own), _ptr(g1), _ptr(evk_own), _ptr(g2), st))
+        all_gather(g2)
+        self._chk(self.lib.hml_keyswitch_shard_end(self.h, L, rank, world, _ptr(g2), _ptr(o0), _ptr(o1), st))
+        return o0[:nq], o1[:nq]
 
     def counts(self, op, L):
         c = _Counts()

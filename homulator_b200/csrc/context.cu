@@ -39,7 +39,8 @@ static int upload(hml_ctx *ctx, const std::vector<T> &h, T **dev) {
 
 // A base conversion prepared for launch: destination limbs split into chunks that fit kernel-parameter space
 // (n_src * chunk <= BCONV_MAX_PAIRS), each with its matrix in 12-bit pieces and its destination LimbMap.
-static void prepare_bconv(const BConvTable &bt, hml::HostBConv &out) {
+// dst_pos[t] = limb slot (in the output buffer) of destination t.
+static void prepare_bconv(const BConvTable &bt, const std::vector<uint32_t> &dst_pos, hml::HostBConv &out) {
   const int ns = (int)bt.src.size(), nd = (int)bt.dst.size();
   int chunk = BCONV_MAX_PAIRS / ns;
   if (chunk >= nd) chunk = nd;
@@ -53,6 +54,7 @@ static void prepare_bconv(const BConvTable &bt, hml::HostBConv &out) {
     memset(&ch.dst_lm, 0, sizeof(ch.dst_lm));
     for (int t = 0; t < ch.count; ++t) {
       ch.dst_lm.mod[t] = (uint16_t)bt.dst[first + t];
+      ch.dst_lm.pos[t] = (uint16_t)dst_pos[first + t];
       for (int i = 0; i < ns; ++i) {
         const u64 h = bt.hat[(size_t)i * nd + first + t];
         double *d = &ch.mat.h[((size_t)i * ch.count + t) * 3];
@@ -67,7 +69,7 @@ static void prepare_bconv(const BConvTable &bt, hml::HostBConv &out) {
 
 static void run_bconv(hml_ctx *ctx, const hml::HostBConv &hb, const LimbMap &src_lm, BConvArgs a, cudaStream_t s) {
   for (const auto &ch : hb.chunks) {
-    a.n_src = hb.n_src; a.n_dst = ch.count; a.out_first = ch.first;
+    a.n_src = hb.n_src; a.n_dst = ch.count;
     launch_bconv(ctx->mc, src_lm, ch.dst_lm, a, ch.mat, s);
     ctx->exec.kernel_launches++;
   }
@@ -155,6 +157,7 @@ extern "C" void hml_ctx_destroy(hml_ctx *ctx) {
   cudaSetDevice(ctx->device);
   for (auto &kv : ctx->levels) free_level(kv.second);
   for (auto &kv : ctx->bconv_cache) cudaFree(kv.second.step1);
+  for (auto &kv : ctx->shard_plans) { cudaFree(kv.second.scale1); cudaFree(kv.second.scale2); cudaFree(kv.second.pinv); }
   cudaFree(ctx->tw_fwd); cudaFree(ctx->tw_inv); cudaFree(ctx->mc); cudaFree(ctx->ws); cudaFree(ctx->stage);
   if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
   if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
@@ -247,11 +250,12 @@ static int get_level(hml_ctx *ctx, uint32_t L, LevelConsts **out) {
   }
   for (uint32_t j = 0; j < beta; ++j) {
     const uint32_t lo = j * A, aj = p.digit_size(L, j);
-    std::vector<uint32_t> src, dst;
+    std::vector<uint32_t> src, dst, dst_pos;
     for (uint32_t i = 0; i < aj; ++i) src.push_back(lo + i);
     for (uint32_t e = 0; e < E; ++e) {
       if (e >= lo && e < lo + aj) continue;
       dst.push_back(p.ext_mod(L, e));
+      dst_pos.push_back(e);
     }
     BConvTable bt;
     make_bconv_table(p, src, dst, bt);
@@ -260,7 +264,7 @@ static int get_level(hml_ctx *ctx, uint32_t L, LevelConsts **out) {
       up_scale[lo + i] = mk_cst(h_mulmod(p.n_inv[lo + i], bt.hat_inv[i], q), q);
     }
     lc.up.emplace_back();
-    prepare_bconv(bt, lc.up.back());
+    prepare_bconv(bt, dst_pos, lc.up.back());
   }
   if ((rc = upload(ctx, up_scale, &lc.modup_scale))) return rc;
   // ---- ModDown
@@ -281,7 +285,7 @@ static int get_level(hml_ctx *ctx, uint32_t L, LevelConsts **out) {
       for (uint32_t j = 0; j < A; ++j) P = h_mulmod(P, p.mod[p.max_level + j] % q, q);
       pinv[i] = mk_cst(h_invmod(P, q), q);
     }
-    prepare_bconv(bt, lc.down);
+    prepare_bconv(bt, dst, lc.down);
     if ((rc = upload(ctx, sc, &lc.moddown_scale))) return rc;
     if ((rc = upload(ctx, pinv, &lc.pinv))) return rc;
   }
@@ -383,14 +387,16 @@ extern "C" int hml_bconv(hml_ctx *ctx, const uint64_t *in, const uint32_t *src_i
     DevBConv d;
     int rc;
     if ((rc = upload(ctx, s1, &d.step1))) return rc;
-    prepare_bconv(bt, d.host);
+    std::vector<uint32_t> ident(n_dst);
+    for (uint32_t t = 0; t < n_dst; ++t) ident[t] = t;
+    prepare_bconv(bt, ident, d.host);
     it = ctx->bconv_cache.emplace(key, d).first;
   }
   LimbMap slm;
   id_map(slm, src_idx, n_src);
   BConvArgs a{};
   a.in = (const u64 *)in; a.out = (u64 *)out; a.step1 = it->second.step1;
-  a.N = ctx->p.N; a.n_batches = 1; a.out_gap_start = n_dst; a.out_gap_len = 0;
+  a.N = ctx->p.N; a.n_batches = 1;
   run_bconv(ctx, it->second.host, slm, a, (cudaStream_t)stream);
   ctx->exec.ewe_limbs += n_src;  // step 1
   return check_launch(ctx, "bconv");
@@ -426,7 +432,7 @@ static int ks_run(hml_ctx *ctx, uint32_t L, const u64 *d, const u64 *evk, uint32
     const uint32_t lo = j * A, aj = p.digit_size(L, j);
     BConvArgs a{};
     a.in = yb + (size_t)lo * N; a.out = ext + (size_t)j * E * N; a.step1 = nullptr;
-    a.N = N; a.n_batches = 1; a.out_gap_start = lo; a.out_gap_len = aj;
+    a.N = N; a.n_batches = 1;
     run_bconv(ctx, lc->up[j], lc->q_lm, a, s);
   }
   // K4 (reference :190-292): NTT of the converted limbs.  The digit's own limbs are the untouched input
@@ -440,10 +446,11 @@ static int ks_run(hml_ctx *ctx, uint32_t L, const u64 *d, const u64 *evk, uint32
   }
   // K5 (reference :294-414): inner product with the key
   {
+    LimbMap ip = lc->ext_lm;  // pos = limb index inside the key (Q-limbs first, then P-limbs after evk_q_limbs)
+    for (uint32_t e = 0; e < E; ++e) ip.pos[e] = (uint16_t)(e < L ? e : evk_q_limbs + (e - L));
     InnerArgs a{};
-    a.d = d; a.ext = ext; a.evk = evk; a.acc = acc; a.N = N; a.L = L; a.alpha = A; a.beta = beta;
-    a.max_level = p.max_level; a.evk_q_limbs = evk_q_limbs;
-    launch_inner_product(ctx->mc, a, s);
+    a.d = d; a.ext = ext; a.evk = evk; a.acc = acc; a.N = N; a.n_ext = E; a.beta = beta; a.evk_limbs = evk_q_limbs + A;
+    launch_inner_product(ctx->mc, ip, a, s);
     ctx->exec.ewe_limbs += 2ull * E * beta; ctx->exec.kernel_launches++;
   }
   // K6 + K7 (reference :417-487): INTT of the P-limbs of both accumulators, in place, BConv step 1 folded in
@@ -457,9 +464,8 @@ static int ks_run(hml_ctx *ctx, uint32_t L, const u64 *d, const u64 *evk, uint32
   // K8 (reference :489-519): P -> Q_L
   {
     BConvArgs a{};
-    a.in = acc + (size_t)L * N; a.out = vb; a.in_batch_stride = (long long)E * N; a.out_batch_stride = (long long)L * N;
+    a.in = acc; a.out = vb; a.in_batch_stride = (long long)E * N; a.out_batch_stride = (long long)L * N;  // p_lm.pos = L + j
     a.step1 = nullptr; a.N = N; a.n_batches = 2;
-    a.out_gap_start = L; a.out_gap_len = 0;
     run_bconv(ctx, lc->down, lc->p_lm, a, s);
   }
   // K9 (reference :521-546, emitted with opcode INTT — delta D1): forward NTT of the converted limbs
@@ -490,6 +496,234 @@ extern "C" int hml_keyswitch(hml_ctx *ctx, uint32_t L, const uint64_t *d, const 
   if ((rc = ensure_ws(ctx, ks_ws_words(ctx->p, L)))) return rc;
   return ks_run(ctx, L, (const u64 *)d, (const u64 *)evk, evk_q_limbs, (u64 *)out0, (u64 *)out1, nullptr, nullptr, ctx->ws,
                 (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ limb-sharded key switch
+// SURVEY.md 8e mode 2: one ciphertext, the E = L + alpha extended limbs partitioned over `world` GPUs.  Extended limb e
+// is owned by rank e % world — the reference's own rule for mapping limbs to clusters (reference include/Driver.h:158,
+// :178).  Every primitive except base conversion is limb-local; BConv needs all input limbs of a digit, so there is
+// exactly one all-gather before each conversion (the reference's analogue is its inter-cluster NoC fetch,
+// reference include/mem.h:612-621, src/mem.cpp:78-100):
+//   begin:  INTT (+ digit scaling) of the owned Q-limbs, written straight into this rank's slot of gather buffer 1
+//   [all-gather 1: world x ceil(L/world) limbs]
+//   mid:    BConv digit -> owned extended limbs, NTT, inner product with the owned key slices, INTT (+ scaling) of
+//           the owned P-limbs of both accumulators, copied into this rank's slot of gather buffer 2
+//   [all-gather 2: world x 2 x ceil(alpha/world) limbs]
+//   end:    BConv P -> owned Q-limbs, NTT, (acc - v) * P^-1 for the owned Q-limbs
+// The collective itself is issued by the caller (NCCL all-gather on the same stream; homulator_b200/api.py uses
+// torch.distributed) so the library stays free of a communicator dependency.
+static int get_shard_plan(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, ShardPlan **out) {
+  const uint64_t key = ((uint64_t)L << 32) | ((uint64_t)world << 16) | rank;
+  auto it = ctx->shard_plans.find(key);
+  if (it != ctx->shard_plans.end()) { *out = &it->second; return HML_OK; }
+  const Params &p = ctx->p;
+  const uint32_t A = p.alpha, E = L + A, beta = p.beta(L);
+  ShardPlan sp;
+  sp.L = L; sp.world = world; sp.rank = rank; sp.beta = beta;
+  sp.gq = (L + world - 1) / world; sp.gp = (A + world - 1) / world;
+  for (uint32_t e = 0; e < E; ++e)
+    if (e % world == rank) { (e < L ? sp.own_q : sp.own_p).push_back(e < L ? e : e - L); }
+  const uint32_t nq = sp.own_q.size(), np = sp.own_p.size(), ne = nq + np;
+  auto gpos1 = [&](uint32_t i) { return (i % world) * sp.gq + i / world; };                    // Q-limb i in gather buffer 1
+  auto gpos2 = [&](uint32_t j) { return ((L + j) % world) * 2 * sp.gp + ((L + j) / world - sp.first_p_slot((L + j) % world, L, world)); };
+  clear_map(sp.q_lm); clear_map(sp.p_lm); clear_map(sp.e_lm);
+  std::vector<double2> s1(nq), s2(np), pinv(nq);
+  for (uint32_t k = 0; k < nq; ++k) {
+    const uint32_t i = sp.own_q[k], j = i / A, lo = j * A, aj = p.digit_size(L, j);
+    const u64 q = p.mod[i];
+    sp.q_lm.mod[k] = i; sp.q_lm.pos[k] = k;
+    sp.e_lm.mod[k] = i; sp.e_lm.pos[k] = k; sp.e_lm.skip[k] = (uint8_t)j;
+    u64 hat = 1;  // (D_j / q_i)^-1 mod q_i
+    for (uint32_t t = lo; t < lo + aj; ++t) if (t != i) hat = h_mulmod(hat, p.mod[t] % q, q);
+    s1[k] = mk_cst(h_mulmod(p.n_inv[i], h_invmod(hat, q), q), q);
+    u64 P = 1;
+    for (uint32_t t = 0; t < A; ++t) P = h_mulmod(P, p.mod[p.max_level + t] % q, q);
+    pinv[k] = mk_cst(h_invmod(P, q), q);
+  }
+  for (uint32_t k = 0; k < np; ++k) {
+    const uint32_t j = sp.own_p[k], mi = p.max_level + j;
+    const u64 q = p.mod[mi];
+    sp.p_lm.mod[k] = mi; sp.p_lm.pos[k] = nq + k;
+    sp.e_lm.mod[nq + k] = mi; sp.e_lm.pos[nq + k] = nq + k;
+    u64 hat = 1;  // (P / p_j)^-1 mod p_j
+    for (uint32_t t = 0; t < A; ++t) if (t != j) hat = h_mulmod(hat, p.mod[p.max_level + t] % q, q);
+    s2[k] = mk_cst(h_mulmod(p.n_inv[mi], h_invmod(hat, q), q), q);
+  }
+  int rc;
+  if ((rc = upload(ctx, s1, &sp.scale1))) return rc;
+  if ((rc = upload(ctx, s2, &sp.scale2))) return rc;
+  if ((rc = upload(ctx, pinv, &sp.pinv))) return rc;
+  // ModUp conversions: digit j (all its limbs, read from gather buffer 1) -> owned extended limbs outside the digit
+  for (uint32_t j = 0; j < beta; ++j) {
+    const uint32_t lo = j * A, aj = p.digit_size(L, j);
+    std::vector<uint32_t> src, dst, dst_pos;
+    LimbMap slm; clear_map(slm);
+    for (uint32_t i = 0; i < aj; ++i) { src.push_back(lo + i); slm.mod[i] = lo + i; slm.pos[i] = gpos1(lo + i); }
+    for (uint32_t le = 0; le < ne; ++le) {
+      const uint32_t e = le < nq ? sp.own_q[le] : L + sp.own_p[le - nq];
+      if (e >= lo && e < lo + aj) continue;
+      dst.push_back(p.ext_mod(L, e)); dst_pos.push_back(le);
+    }
+    sp.up.emplace_back();
+    sp.up_src.push_back(slm);
+    if (!dst.empty()) {
+      BConvTable bt;
+      make_bconv_table(p, src, dst, bt);
+      prepare_bconv(bt, dst_pos, sp.up.back());
+    }
+  }
+  {  // ModDown conversion: all P-limbs (read from gather buffer 2) -> owned Q-limbs
+    std::vector<uint32_t> src, dst, dst_pos;
+    clear_map(sp.down_src);
+    for (uint32_t j = 0; j < A; ++j) { src.push_back(p.max_level + j); sp.down_src.mod[j] = p.max_level + j; sp.down_src.pos[j] = gpos2(j); }
+    for (uint32_t k = 0; k < nq; ++k) { dst.push_back(sp.own_q[k]); dst_pos.push_back(k); }
+    if (!dst.empty()) {
+      BConvTable bt;
+      make_bconv_table(p, src, dst, bt);
+      prepare_bconv(bt, dst_pos, sp.down);
+    }
+  }
+  auto ins = ctx->shard_plans.emplace(key, sp);
+  *out = &ins.first->second;
+  return HML_OK;
+}
+
+static size_t shard_ws_words(const Params &p, const ShardPlan &sp) {
+  const size_t ne = sp.own_q.size() + sp.own_p.size(), nq = sp.own_q.size();
+  return (size_t)p.N * ((size_t)sp.beta * ne + 2 * ne + 2 * nq);
+}
+
+static int shard_check(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world) {
+  int rc = check_level(ctx, L, 1);
+  if (rc) return rc;
+  if (world == 0 || rank >= world || world > 64) return fail(ctx, HML_ERR_INVALID, "bad rank / world");
+  return HML_OK;
+}
+
+extern "C" int hml_shard_layout(uint32_t L, uint32_t alpha, uint32_t rank, uint32_t world, hml_shard_info *out) {
+  if (!out || world == 0 || rank >= world || L == 0 || alpha == 0 || L + alpha > HML_MAX_SHARD_LIMBS) return HML_ERR_INVALID;
+  const uint32_t A = alpha, E = L + A;
+  memset(out, 0, sizeof(*out));
+  out->gather1_slots = (L + world - 1) / world;
+  out->gather2_slots = (A + world - 1) / world;
+  for (uint32_t e = 0; e < E; ++e) {
+    out->owner[e] = e % world;
+    if (e % world == rank) {
+      if (e < L) out->own_q[out->n_own_q++] = e; else out->own_p[out->n_own_p++] = e - L;
+    }
+    // slot of limb e inside its owner's contribution to the gather buffer
+    out->slot[e] = e < L ? e / world : (e / world - ShardPlan::first_p_slot(e % world, L, world));
+  }
+  return HML_OK;
+}
+
+extern "C" int hml_keyswitch_shard_begin(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, const uint64_t *d_own,
+                                         uint64_t *gather1, void *stream) {
+  int rc = shard_check(ctx, L, rank, world);
+  if (rc) return rc;
+  if (!d_own || !gather1) return fail(ctx, HML_ERR_INVALID, "null buffer");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  ShardPlan *sp;
+  if ((rc = get_shard_plan(ctx, L, rank, world, &sp))) return rc;
+  const size_t N = ctx->p.N;
+  const uint32_t nq = sp->own_q.size();
+  if (nq) {
+    NttLaunch l{};
+    l.in = (const u64 *)d_own; l.out = (u64 *)gather1 + (size_t)rank * sp->gq * N;
+    l.in_limb_stride = l.out_limb_stride = N; l.n_limbs = nq; l.n_polys = 1; l.post_scale = sp->scale1;
+    launch_ntt_inverse(ctx->tabs, ctx->p.logN, sp->q_lm, l, (cudaStream_t)stream);
+    ctx->exec.intt_limbs += nq; ctx->exec.kernel_launches += ctx->p.logN <= 12 ? 1 : 2;
+  }
+  return check_launch(ctx, "keyswitch shard begin");
+}
+
+extern "C" int hml_keyswitch_shard_mid(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, const uint64_t *d_own,
+                                       const uint64_t *gather1, const uint64_t *evk_own, uint64_t *gather2, void *stream) {
+  int rc = shard_check(ctx, L, rank, world);
+  if (rc) return rc;
+  if (!d_own || !gather1 || !evk_own || !gather2) return fail(ctx, HML_ERR_INVALID, "null buffer");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  ShardPlan *sp;
+  if ((rc = get_shard_plan(ctx, L, rank, world, &sp))) return rc;
+  if ((rc = ensure_ws(ctx, shard_ws_words(ctx->p, *sp)))) return rc;
+  const Params &p = ctx->p;
+  const size_t N = p.N;
+  const uint32_t nq = sp->own_q.size(), np = sp->own_p.size(), ne = nq + np, beta = sp->beta;
+  const int logN = p.logN, npass = logN <= 12 ? 1 : 2;
+  cudaStream_t s = (cudaStream_t)stream;
+  u64 *ext = ctx->ws, *acc = ext + (size_t)beta * ne * N;
+  if (ne == 0) return HML_OK;
+  for (uint32_t j = 0; j < beta; ++j) {
+    if (sp->up[j].chunks.empty()) continue;
+    BConvArgs a{};
+    a.in = (const u64 *)gather1; a.out = ext + (size_t)j * ne * N; a.step1 = nullptr; a.N = N; a.n_batches = 1;
+    run_bconv(ctx, sp->up[j], sp->up_src[j], a, s);
+  }
+  {
+    NttLaunch l{};
+    l.in = ext; l.out = ext; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)ne * N;
+    l.n_limbs = ne; l.n_polys = beta;
+    launch_ntt_forward(ctx->tabs, logN, sp->e_lm, l, s);
+    ctx->exec.ntt_limbs += (uint64_t)beta * ne - nq; ctx->exec.kernel_launches += npass;
+  }
+  {
+    InnerArgs a{};
+    a.d = (const u64 *)d_own; a.ext = ext; a.evk = (const u64 *)evk_own; a.acc = acc; a.N = N; a.n_ext = ne; a.beta = beta;
+    a.evk_limbs = ne;
+    launch_inner_product(ctx->mc, sp->e_lm, a, s);
+    ctx->exec.ewe_limbs += 2ull * ne * beta; ctx->exec.kernel_launches++;
+  }
+  if (np) {
+    NttLaunch l{};
+    l.in = acc; l.out = acc; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)ne * N;
+    l.n_limbs = np; l.n_polys = 2; l.post_scale = sp->scale2;
+    launch_ntt_inverse(ctx->tabs, logN, sp->p_lm, l, s);
+    ctx->exec.intt_limbs += 2 * np; ctx->exec.kernel_launches += npass;
+    // this rank's contribution to gather buffer 2: [2][gp][N] at slot `rank`
+    for (int c = 0; c < 2; ++c)
+      CU_TRY(ctx, cudaMemcpyAsync((u64 *)gather2 + ((size_t)rank * 2 + c) * sp->gp * N, acc + ((size_t)c * ne + nq) * N,
+                                  (size_t)np * N * 8, cudaMemcpyDeviceToDevice, s));
+  }
+  return check_launch(ctx, "keyswitch shard mid");
+}
+
+extern "C" int hml_keyswitch_shard_end(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, const uint64_t *gather2,
+                                       uint64_t *out0_own, uint64_t *out1_own, void *stream) {
+  int rc = shard_check(ctx, L, rank, world);
+  if (rc) return rc;
+  if (!gather2 || !out0_own || !out1_own) return fail(ctx, HML_ERR_INVALID, "null buffer");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  ShardPlan *sp;
+  if ((rc = get_shard_plan(ctx, L, rank, world, &sp))) return rc;
+  if ((rc = ensure_ws(ctx, shard_ws_words(ctx->p, *sp)))) return rc;
+  const Params &p = ctx->p;
+  const size_t N = p.N;
+  const uint32_t nq = sp->own_q.size(), np = sp->own_p.size(), ne = nq + np, beta = sp->beta;
+  const int logN = p.logN, npass = logN <= 12 ? 1 : 2;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (nq == 0) return HML_OK;
+  u64 *ext = ctx->ws, *acc = ext + (size_t)beta * ne * N, *vb = acc + 2 * (size_t)ne * N;
+  {
+    BConvArgs a{};
+    a.in = (const u64 *)gather2; a.out = vb; a.in_batch_stride = (long long)sp->gp * N; a.out_batch_stride = (long long)nq * N;
+    a.step1 = nullptr; a.N = N; a.n_batches = 2;
+    run_bconv(ctx, sp->down, sp->down_src, a, s);
+  }
+  {
+    NttLaunch l{};
+    l.in = vb; l.out = vb; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)nq * N;
+    l.n_limbs = nq; l.n_polys = 2;
+    launch_ntt_forward(ctx->tabs, logN, sp->q_lm, l, s);
+    ctx->exec.ntt_limbs += 2 * nq; ctx->exec.kernel_launches += npass;
+  }
+  for (int c = 0; c < 2; ++c) {
+    SubMulArgs a{};
+    a.x = acc + (size_t)c * ne * N; a.y = vb + (size_t)c * nq * N; a.z = nullptr; a.out = (u64 *)(c ? out1_own : out0_own);
+    a.cst = sp->pinv; a.N = N; a.n_limbs = nq; a.n_polys = 1;
+    launch_sub_mul_add(ctx->mc, sp->q_lm, a, s);
+    ctx->exec.ewe_limbs += nq; ctx->exec.kernel_launches++;
+  }
+  return check_launch(ctx, "keyswitch shard end");
 }
 
 // ------------------------------------------------------------------------------------------------ rescale

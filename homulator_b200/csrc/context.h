@@ -43,6 +43,22 @@ struct LevelConsts {
   LimbMap p_lm;                              // limbs 0..alpha-1 -> moduli p_j, pos = L + j (inside an [E][N] buffer)
 };
 
+// Plan of the limb-sharded key switch for one (level, rank, world): owned limbs, gather-buffer positions, constants.
+struct ShardPlan {
+  uint32_t L = 0, world = 1, rank = 0, beta = 0;
+  uint32_t gq = 0, gp = 0;                 // limb slots per rank in gather buffer 1 (Q) and 2 (P, per accumulator)
+  std::vector<uint32_t> own_q, own_p;      // owned Q-limb indices i, owned P-limb indices j (extended limb L + j)
+  LimbMap q_lm, p_lm, e_lm;                // owned Q / owned P (pos = nq + k inside the local [ne][N] buffers) / owned extended
+  double2 *scale1 = nullptr, *scale2 = nullptr, *pinv = nullptr;
+  std::vector<HostBConv> up;               // [beta]
+  std::vector<LimbMap> up_src;             // positions of the digit's limbs inside gather buffer 1
+  HostBConv down;
+  LimbMap down_src;                        // positions of the P-limbs inside gather buffer 2 (accumulator 0)
+  // rank r's owned P-limbs are the extended limbs e = L + j with e % world == r; its first such e sits at slot
+  // floor(e / world) counted over ALL its limbs, so subtract the number of Q-limbs it owns
+  static uint32_t first_p_slot(uint32_t r, uint32_t L, uint32_t world) { return L > r ? (L - r + world - 1) / world : 0; }
+};
+
 struct DevBConv {  // cached tables of an arbitrary (src, dst) conversion for the primitive entry point
   double2 *step1 = nullptr;
   HostBConv host;
@@ -63,6 +79,7 @@ struct hml_ctx {
 
   std::map<uint32_t, hml::LevelConsts> levels;
   std::map<std::vector<uint32_t>, hml::DevBConv> bconv_cache;
+  std::map<uint64_t, hml::ShardPlan> shard_plans;
 
   hml::u64 *ws = nullptr;  // workspace, grown on demand
   size_t ws_words = 0;

@@ -76,34 +76,31 @@ void launch_tensor3(const ModConst *mc, int N, int L, const u64 *a0, const u64 *
 }
 
 // ------------------------------------------------------------------------------------------------ key-switch inner product
-__global__ void __launch_bounds__(EW_THREADS) k_inner(const ModConst *__restrict__ mc, InnerArgs a) {
+__global__ void __launch_bounds__(EW_THREADS) k_inner(const ModConst *__restrict__ mc, LimbMap lm, InnerArgs a) {
   const int i2 = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i2 >= a.N / 2) return;
-  const int e = blockIdx.y, E = a.L + a.alpha;
-  const int mi = e < a.L ? e : a.max_level + (e - a.L);
-  const int kl = e < a.L ? e : a.evk_q_limbs + (e - a.L);
-  const int evk_limbs = a.evk_q_limbs + a.alpha;
-  const ModConst m = mc[mi];
+  const int e = blockIdx.y;
+  const ModConst m = mc[lm.mod[e]];
+  const int kl = lm.pos[e], own = lm.skip[e];
   const size_t n2 = a.N / 2;
   double s00 = 0, s01 = 0, s10 = 0, s11 = 0;  // [component][coefficient]
   for (int j = 0; j < a.beta; ++j) {
-    const bool own = (e >= j * a.alpha) && (e < (j + 1) * a.alpha) && (e < a.L);
-    const u64 *tp = own ? a.d + (size_t)e * a.N : a.ext + ((size_t)j * E + e) * a.N;
+    const u64 *tp = j == own ? a.d + (size_t)e * a.N : a.ext + ((size_t)j * a.n_ext + e) * a.N;
     const ulonglong2 t = ld2(tp, i2);
-    const ulonglong2 k0 = ld2(a.evk, (((size_t)j * 2 + 0) * evk_limbs + kl) * n2 + i2);
-    const ulonglong2 k1 = ld2(a.evk, (((size_t)j * 2 + 1) * evk_limbs + kl) * n2 + i2);
+    const ulonglong2 k0 = ld2(a.evk, (((size_t)j * 2 + 0) * a.evk_limbs + kl) * n2 + i2);
+    const ulonglong2 k1 = ld2(a.evk, (((size_t)j * 2 + 1) * a.evk_limbs + kl) * n2 + i2);
     const double t0 = u64_to_f64(t.x), t1 = u64_to_f64(t.y);
     s00 += mulmod_var(t0, u64_to_f64(k0.x), m.q, m.qinv);
     s01 += mulmod_var(t1, u64_to_f64(k0.y), m.q, m.qinv);
     s10 += mulmod_var(t0, u64_to_f64(k1.x), m.q, m.qinv);
     s11 += mulmod_var(t1, u64_to_f64(k1.y), m.q, m.qinv);
   }
-  st2(a.acc, ((size_t)0 * E + e) * n2 + i2, finish(s00, m), finish(s01, m));
-  st2(a.acc, ((size_t)1 * E + e) * n2 + i2, finish(s10, m), finish(s11, m));
+  st2(a.acc, ((size_t)0 * a.n_ext + e) * n2 + i2, finish(s00, m), finish(s01, m));
+  st2(a.acc, ((size_t)1 * a.n_ext + e) * n2 + i2, finish(s10, m), finish(s11, m));
 }
 
-void launch_inner_product(const ModConst *mc, const InnerArgs &a, cudaStream_t s) {
-  k_inner<<<ew_grid(a.N, a.L + a.alpha), EW_THREADS, 0, s>>>(mc, a);
+void launch_inner_product(const ModConst *mc, const LimbMap &lm, const InnerArgs &a, cudaStream_t s) {
+  k_inner<<<ew_grid(a.N, a.n_ext), EW_THREADS, 0, s>>>(mc, lm, a);
 }
 
 // ------------------------------------------------------------------------------------------------ (x - y) * c (+ z)
@@ -179,7 +176,7 @@ __global__ void __launch_bounds__(BC_THREADS, 4) k_bconv(const ModConst *__restr
   u64 *out = a.out + (size_t)blockIdx.z * a.out_batch_stride;
   ulonglong2 ring[BC_RING];
 #pragma unroll
-  for (int k = 0; k < BC_RING; ++k) ring[k] = __ldg(in + (size_t)min(k, a.n_src - 1) * n2);
+  for (int k = 0; k < BC_RING; ++k) ring[k] = __ldg(in + (size_t)src_lm.pos[min(k, a.n_src - 1)] * n2);
   __syncthreads();
   double acc[OT][3][2];
 #pragma unroll
@@ -192,7 +189,7 @@ __global__ void __launch_bounds__(BC_THREADS, 4) k_bconv(const ModConst *__restr
       const int i = i0 + k;
       if (i < a.n_src) {
         double y0 = u64_to_f64(ring[k].x), y1 = u64_to_f64(ring[k].y);
-        ring[k] = __ldg(in + (size_t)min(i + BC_RING, a.n_src - 1) * n2);
+        ring[k] = __ldg(in + (size_t)src_lm.pos[min(i + BC_RING, a.n_src - 1)] * n2);
         if (STEP1) {
           const ModConst m = mc[src_lm.mod[i]];
           const double2 sc = a.step1[i];
@@ -239,8 +236,7 @@ __global__ void __launch_bounds__(BC_THREADS, 4) k_bconv(const ModConst *__restr
 #pragma unroll
   for (int o = 0; o < OT; ++o) {
     if (o < nt) {
-      const int t = a.out_first + t0 + o, slot = t < a.out_gap_start ? t : t + a.out_gap_len;
-      st2(out, (size_t)slot * n2 + i2, r[o][0], r[o][1]);
+      st2(out, (size_t)dst_lm.pos[t0 + o] * n2 + i2, r[o][0], r[o][1]);
     }
   }
 }

@@ -18,17 +18,17 @@ void launch_ewe(const ModConst *mc, const LimbMap &lm, int N, int n_limbs, const
 void launch_tensor3(const ModConst *mc, int N, int L, const u64 *a0, const u64 *a1, const u64 *b0, const u64 *b1,
                     u64 *d0, u64 *d1, u64 *d2, cudaStream_t s);
 
-// Key-switch inner product (reference src/Operation.cpp:294-414, emitted as MULT):
-//   acc[c][e] = sum_j t_j[e] * evk[j][c][evk_limb(e)]  for the E = L + alpha extended limbs.
-// t_j[e] is d[e] (the untouched evaluation-form input) when limb e belongs to digit j, else ext[j][e].
+// Key-switch inner product (reference src/Operation.cpp:294-414, emitted as MULT) over n_ext extended limbs:
+//   acc[c][e] = sum_j t_j[e] * evk[j][c][lm.pos[e]],   modulus lm.mod[e]
+// t_j[e] is d[e] (the untouched evaluation-form input) when digit j owns limb e (j == lm.skip[e]), else ext[j][e].
 struct InnerArgs {
-  const u64 *d;     // [L][N]
-  const u64 *ext;   // [beta][E][N]
+  const u64 *d;     // [>= number of owned Q-limbs][N]
+  const u64 *ext;   // [beta][n_ext][N]
   const u64 *evk;   // [beta][2][evk_limbs][N]
-  u64 *acc;         // [2][E][N]
-  int N, L, alpha, beta, max_level, evk_q_limbs;
+  u64 *acc;         // [2][n_ext][N]
+  int N, n_ext, beta, evk_limbs;
 };
-void launch_inner_product(const ModConst *mc, const InnerArgs &a, cudaStream_t s);
+void launch_inner_product(const ModConst *mc, const LimbMap &lm, const InnerArgs &a, cudaStream_t s);
 
 // out = (x - y) * c (+ z) per limb:  ModDownSub (+ HMULT add)  reference src/Operation.cpp:548-590, :967-1005
 // and Rescale sub+mul  reference src/Operation.cpp:825-911.  cst[limb] = (c, RN(c/q)).  n_polys via strides.
@@ -59,9 +59,9 @@ struct BConvArgs {
   long long in_batch_stride, out_batch_stride;  // grid.z batches (e.g. the two key-switch accumulators)
   const double2 *step1;   // [n_src] or null
   int N, n_src, n_dst, n_batches;
-  int out_first;                   // global index of this launch's first output limb (n_dst chunking)
-  int out_gap_start, out_gap_len;  // global output limb t is stored at slot t (t < gap_start) or t + gap_len
 };
+// Source limb i is read at in + src_lm.pos[i] * N (modulus src_lm.mod[i], used by step 1 only); output limb t is
+// written at out + dst_lm.pos[t] * N with modulus dst_lm.mod[t].
 int bconv_tile_height(int n_dst);
 void launch_bconv(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const BConvMatrix &mat,
                   cudaStream_t s);

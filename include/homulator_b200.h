@@ -105,6 +105,34 @@ int hml_keyswitch(hml_ctx *ctx, uint32_t L, const uint64_t *d, const uint64_t *e
 /* replaces Rescale::Rescale (reference src/Operation.cpp:741-911): in [L][N] -> out [L-1][N]. */
 int hml_rescale(hml_ctx *ctx, uint32_t L, const uint64_t *in, uint64_t *out, void *stream);
 
+/* Limb-sharded key switch over `world` GPUs of one node (BASELINE.json configs[4], SURVEY.md 8e mode 2).
+ * Extended limb e (Q-limbs 0..L-1, then P-limbs) is owned by rank e % world — the rule the reference uses to map
+ * limbs to clusters (reference include/Driver.h:158,:178).  Every stage is limb-local except base conversion, so the
+ * caller performs one all-gather before each conversion (NCCL, same stream), between the three calls below; this is
+ * the GPU counterpart of the reference's inter-cluster NoC fetch (reference include/mem.h:612-621).
+ *   d_own    [n_own_q][N]              the owned Q-limbs of the input, ascending limb index
+ *   evk_own  [beta][2][n_own_e][N]     key slices for the owned extended limbs (owned Q-limbs, then owned P-limbs)
+ *   gather1  [world][gather1_slots][N] begin() fills slot `rank`; the caller all-gathers it in place
+ *   gather2  [world][2][gather2_slots][N] mid() fills slot `rank`; the caller all-gathers it in place
+ *   out*_own [n_own_q][N]              the owned Q-limbs of the two outputs
+ * hml_shard_layout reports ownership and slot numbers (pure host code). */
+#define HML_MAX_SHARD_LIMBS 128
+typedef struct {
+  uint32_t gather1_slots, gather2_slots;   /* ceil(L/world), ceil(alpha/world) */
+  uint32_t n_own_q, n_own_p;
+  uint32_t own_q[HML_MAX_SHARD_LIMBS];     /* owned Q-limb indices */
+  uint32_t own_p[HML_MAX_SHARD_LIMBS];     /* owned P-limb indices j (extended limb L + j) */
+  uint32_t owner[HML_MAX_SHARD_LIMBS];     /* owner rank of every extended limb */
+  uint32_t slot[HML_MAX_SHARD_LIMBS];      /* slot of extended limb e inside its owner's gather contribution */
+} hml_shard_info;
+int hml_shard_layout(uint32_t L, uint32_t alpha, uint32_t rank, uint32_t world, hml_shard_info *out);
+int hml_keyswitch_shard_begin(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, const uint64_t *d_own,
+                              uint64_t *gather1, void *stream);
+int hml_keyswitch_shard_mid(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, const uint64_t *d_own,
+                            const uint64_t *gather1, const uint64_t *evk_own, uint64_t *gather2, void *stream);
+int hml_keyswitch_shard_end(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, const uint64_t *gather2,
+                            uint64_t *out0_own, uint64_t *out1_own, void *stream);
+
 /* ------------------------------------------------------------------ operations (reference include/Operation.h) */
 /* HMULT (reference src/Operation.cpp:913-1023): tensor + keyswitch(relinearise) + add + rescale x2.
  * ct_a, ct_b [2][L][N]; ct_out [2][L-1][N].  Requires L >= 2 (the reference segfaults at L=1). */

@@ -1,0 +1,85 @@
+"""GPU parity of the limb-sharded key switch (SURVEY.md 8e mode 2).
+
+On one GPU the ranks are emulated one after another (a context per rank, the all-gathers done as device copies), so the
+sharded arithmetic is checked bit-exactly against the oracle on every box; with >= 2 GPUs the real NCCL path
+(tests/mp_sharded_keyswitch.py under torch.distributed.run) is exercised as well."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import homulator_b200 as hml  # noqa: E402
+from gpu_common import to_dev, to_host  # noqa: E402
+from orc import Oracle, uniform_limbs  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def sharded_keyswitch_emulated(ctxs, L, d, evk, world):
+    """d [L][N], evk [beta][2][L+alpha][N] numpy; returns (out0, out1) [L][N] assembled from all ranks."""
+    A, N = ctxs[0].alpha, ctxs[0].N
+    lays = [hml.shard_layout(L, A, r, world) for r in range(world)]
+    d_own, evk_own, g1, g2 = [], [], [], []
+    for r, lay in enumerate(lays):
+        own_e = lay["own_q"] + [L + j for j in lay["own_p"]]
+        d_own.append(to_dev(d[lay["own_q"]] if lay["own_q"] else np.zeros((1, N), dtype=np.uint64)))
+        evk_own.append(to_dev(evk[:, :, own_e]) if own_e else None)
+        g1.append(torch.zeros(world, lay["gather1_slots"], N, dtype=torch.int64, device="cuda"))
+        g2.append(torch.zeros(world, 2, lay["gather2_slots"], N, dtype=torch.int64, device="cuda"))
+    st = torch.cuda.current_stream().cuda_stream
+    for r, c in enumerate(ctxs):
+        c._chk(c.lib.hml_keyswitch_shard_begin(c.h, L, r, world, d_own[r].data_ptr(), g1[r].data_ptr(), st))
+    for r in range(world):  # all-gather 1
+        for s in range(world):
+            g1[r][s].copy_(g1[s][s])
+    for r, c in enumerate(ctxs):
+        if evk_own[r] is None:
+            continue
+        c._chk(c.lib.hml_keyswitch_shard_mid(c.h, L, r, world, d_own[r].data_ptr(), g1[r].data_ptr(), evk_own[r].data_ptr(),
+                                             g2[r].data_ptr(), st))
+    for r in range(world):  # all-gather 2
+        for s in range(world):
+            g2[r][s].copy_(g2[s][s])
+    out0, out1 = np.zeros((L, N), dtype=np.uint64), np.zeros((L, N), dtype=np.uint64)
+    for r, c in enumerate(ctxs):
+        nq = len(lays[r]["own_q"])
+        o0 = torch.zeros(max(nq, 1), N, dtype=torch.int64, device="cuda")
+        o1 = torch.zeros_like(o0)
+        c._chk(c.lib.hml_keyswitch_shard_end(c.h, L, r, world, g2[r].data_ptr(), o0.data_ptr(), o1.data_ptr(), st))
+        if nq:
+            out0[lays[r]["own_q"]] = to_host(o0)[:nq]
+            out1[lays[r]["own_q"]] = to_host(o1)[:nq]
+    return out0, out1
+
+
+@pytest.mark.parametrize("N,ML,L,A,world", [(256, 7, 7, 3, 2), (256, 7, 7, 3, 3), (1024, 6, 5, 2, 4), (64, 5, 2, 3, 2),
+                                             (4096, 4, 4, 4, 8), (8192, 9, 8, 3, 2), (65536, 45, 35, 15, 4)])
+def test_sharded_keyswitch_emulated_ranks(N, ML, L, A, world):
+    o = Oracle(N, 36, ML, A)
+    Oracle.set_threads(0)
+    beta = -(-L // A)
+    d = uniform_limbs(o.moduli[:L], N, 2000 + L)
+    evk = uniform_limbs(o.moduli[:L] + o.moduli[ML:], N, 2001, lead=(beta, 2))
+    want0, want1 = o.keyswitch(L, d, evk, L)
+    Oracle.set_threads(1)
+    ctxs = [hml.Context(N=N, max_level=ML, alpha=A) for _ in range(world)]
+    got0, got1 = sharded_keyswitch_emulated(ctxs, L, d, evk, world)
+    assert np.array_equal(got0, want0) and np.array_equal(got1, want1)
+    # world = 1 degenerates to the unsharded schedule
+    one0, one1 = sharded_keyswitch_emulated(ctxs[:1], L, d, evk, 1)
+    assert np.array_equal(one0, want0) and np.array_equal(one1, want1)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
+def test_sharded_keyswitch_nccl():
+    n = min(torch.cuda.device_count(), 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", "29531", os.path.join(ROOT, "tests", "mp_sharded_keyswitch.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "SHARDED_KS_OK" in r.stdout
