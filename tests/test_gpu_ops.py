@@ -159,3 +159,32 @@ def test_op_objects_mirror_reference_constructor(north_star):
     assert r["us_median"] > 0
     rot = hml.HROTATE("test_hrotate", 45, 35, 15, ctx)
     assert rot.counts["AUTO"] == 17920 and rot.counts["total"] == 780800
+
+
+def test_op_sequence_replay_matches_oracle():
+    """BASELINE.json configs[4]: synthetic rotation-heavy (baby-step/giant-step) sequence replayed as real kernels."""
+    from homulator_b200.replay import bsgs_trace, replay, trace_counts
+    N, ML, A, L = 2048, 6, 2, 5
+    ctx, o = hml.Context(N=N, max_level=ML, alpha=A), Oracle(N, 36, ML, A)
+    beta = -(-L // A)
+    trace = bsgs_trace(2, 2)
+    assert trace_counts(trace)["hmult"] == 1 and trace_counts(trace)["hrotate"] == 2
+    x = uniform_limbs(o.moduli[:L], N, 1, lead=(2,))
+    pts = {i: uniform_limbs(o.moduli[:L], N, 100 + i) for i in range(4)}
+    keys = {r: uniform_limbs(o.moduli[:L] + o.moduli[ML:], N, 200 + r, lead=(beta, 2)) for r in (1, 2)}
+    evk = uniform_limbs(o.moduli[:L] + o.moduli[ML:], N, 300, lead=(beta, 2))
+    env = replay(ctx, L, trace, to_dev(x), {k: to_dev(v) for k, v in pts.items()}, {k: to_dev(v) for k, v in keys.items()},
+                 to_dev(evk))
+    # the same trace on the oracle
+    h = {"x": x}
+    for op in trace:
+        if op[0] == "hrotate":
+            h[op[1]] = o.hrotate(L, h[op[2]], keys[op[3]], L, pow(5, op[3], 2 * N))
+        elif op[0] == "pmult":
+            h[op[1]] = o.pmult(L, h[op[2]], pts[op[3]])
+        elif op[0] == "hadd":
+            h[op[1]] = o.hadd(L, h[op[2]], h[op[3]])
+        elif op[0] == "hmult":
+            h[op[1]] = o.hmult(L, h[op[2]], h[op[3]], evk, L)
+    assert np.array_equal(to_host(env["y"]), h["y"])
+    assert np.array_equal(to_host(env["z"]), h["z"])
