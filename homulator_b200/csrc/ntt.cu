@@ -161,14 +161,73 @@ __device__ __forceinline__ unsigned lane_stage_tw(unsigned tw_base, int b, int j
   return (tw_base << (7 - b)) + (kk << (4 - b)) + ((lane & 15) >> b);
 }
 
+// ---- asynchronous bulk copy (TMA engine, no tensor map) global -> shared, completion on an mbarrier
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// The twiddles of the CTA's ROW_WARPS consecutive rows form ONE contiguous table segment per stage
+// ((R1 + row0) << i .. (R1 + row0 + 8) << i), so eight bulk copies bring all of them (32 KB) into shared memory
+// while the warps are still waiting for their data rows; every poly of the limb then reuses them.
+// Three mbarriers, small segments first: stages 0-4 (4 KB) land almost immediately, stages 5-6 (12 KB) and
+// stage 7 (16 KB) are only awaited right before the butterflies that need them.
+constexpr int ROW_TW_ENTRIES = ROW_WARPS * 255;
+__device__ __forceinline__ int row_tw_off(int i) { return ROW_WARPS * ((1 << i) - 1); }
+__device__ __forceinline__ int row_tw_bar(int i) { return i <= 4 ? 0 : (i <= 6 ? 1 : 2); }
+
+__device__ __forceinline__ void stage_row_twiddles(double2 *stw, unsigned long long *bar, const double2 *tw, unsigned tw_base0) {
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); mbar_init(bar + 2, 1); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, (ROW_WARPS * 16u) * 31);
+    mbar_expect_tx(bar + 1, (ROW_WARPS * 16u) * 96);
+    mbar_expect_tx(bar + 2, (ROW_WARPS * 16u) * 128);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      bulk_g2s(stw + row_tw_off(i), tw + ((size_t)tw_base0 << i), (ROW_WARPS * 16u) << i, bar + row_tw_bar(i));
+  }
+}
+
+// index inside the shared twiddle block: row-local w, lane-stage b (NTT stage i = 7 - b), butterfly pair j
+__device__ __forceinline__ int lane_stage_stw(int w, int b, int j, int lane) {
+  const int i = 7 - b, kk = j + ((lane >> 4) << 2);
+  return row_tw_off(i) + (w << i) + (kk << (4 - b)) + ((lane & 15) >> b);
+}
+
 // Polys that share the limb's modulus (the beta digits of ModUp, the two key-switch accumulators, the two
-// rescaled polys) are processed back to back by the same warp, so their twiddles (4 KB per row) hit L1.
+// rescaled polys) are processed back to back by the same warp with the same shared twiddles.
 __global__ void __launch_bounds__(ROW_WARPS * 32, 4) ntt_fwd_rows(NttTables t, int logN, LimbMap lm, NttLaunch l) {
   constexpr int LR = NTT_ROW_LOG, R2 = 1 << LR;
+  __shared__ __align__(16) double2 stw[ROW_TW_ENTRIES];
+  __shared__ __align__(8) unsigned long long bar[3];
   const int limb = blockIdx.y;
   const unsigned R1 = 1u << (logN - LR);
-  const int lane = threadIdx.x & 31, row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
-  const unsigned tw_base = R1 + row;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, row = blockIdx.x * ROW_WARPS + w;
+  stage_row_twiddles(stw, bar, t.fwd + ((size_t)lm.mod[limb] << logN), R1 + blockIdx.x * ROW_WARPS);
+  bool ready = false;
   for (int poly = 0; poly < l.n_polys; ++poly) {
     if (poly == lm.skip[limb]) continue;
     const LimbCtx lc = limb_ctx(t, logN, lm, l, false, limb, poly);
@@ -176,22 +235,35 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) ntt_fwd_rows(NttTables t, i
     double a[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) a[r] = ind[r * 32 + lane];
-    double2 w[4], wn[4];
+    if (!ready) mbar_wait(bar, 0);
+    {  // stages t = 128, 64, 32: register-only, twiddles broadcast from shared memory
+      const double2 w0 = stw[row_tw_off(0) + w];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) wn[j] = __ldg(&lc.tw[lane_stage_tw(tw_base, 4, j, lane)]);
-    ct_round<LR, 0, 3>(a, lane, lc.tw, tw_base, lc.q);
+      for (int o = 0; o < 4; ++o) ct_butterfly(a[o], a[o + 4], w0.x, w0.y, lc.q);
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const double2 w1 = stw[row_tw_off(1) + (w << 1) + g];
+#pragma unroll
+        for (int o = 0; o < 2; ++o) ct_butterfly(a[4 * g + o], a[4 * g + o + 2], w1.x, w1.y, lc.q);
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const double2 w2 = stw[row_tw_off(2) + (w << 2) + g];
+        ct_butterfly(a[2 * g], a[2 * g + 1], w2.x, w2.y, lc.q);
+      }
+    }
 #pragma unroll
     for (int b = 4; b >= 0; --b) {
+      if (!ready && b == 2) mbar_wait(bar + 1, 0);  // stages 5, 6
+      if (!ready && b == 0) mbar_wait(bar + 2, 0);  // stage 7
+      double2 tw4[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) w[j] = wn[j];
-      if (b > 0) {  // next stage's twiddles are in flight during this stage's butterflies
-#pragma unroll
-        for (int j = 0; j < 4; ++j) wn[j] = __ldg(&lc.tw[lane_stage_tw(tw_base, b - 1, j, lane)]);
-      }
+      for (int j = 0; j < 4; ++j) tw4[j] = stw[lane_stage_stw(w, b, j, lane)];
       swap_half(a, b, (lane >> b) & 1);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) ct_butterfly(a[j], a[j + 4], w[j].x, w[j].y, lc.q);
+      for (int j = 0; j < 4; ++j) ct_butterfly(a[j], a[j + 4], tw4[j].x, tw4[j].y, lc.q);
     }
+    ready = true;
     u64 *outp = lc.out + (size_t)row * R2 + (lane >> 4) * 128 + 2 * (lane & 15);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -200,46 +272,61 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) ntt_fwd_rows(NttTables t, i
       *reinterpret_cast<ulonglong2 *>(outp + j * 32) = make_ulonglong2(v0, v1);
     }
   }
+  if (!ready) { mbar_wait(bar, 0); mbar_wait(bar + 1, 0); mbar_wait(bar + 2, 0); }  // never exit with a bulk copy in flight
 }
 
 __global__ void __launch_bounds__(ROW_WARPS * 32, 4) ntt_inv_rows(NttTables t, int logN, LimbMap lm, NttLaunch l) {
   constexpr int LR = NTT_ROW_LOG, R2 = 1 << LR;
+  __shared__ __align__(16) double2 stw[ROW_TW_ENTRIES];
+  __shared__ __align__(8) unsigned long long bar[3];
   const int limb = blockIdx.y;
   const unsigned R1 = 1u << (logN - LR);
-  const int lane = threadIdx.x & 31, row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
-  const unsigned tw_base = R1 + row;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, row = blockIdx.x * ROW_WARPS + w;
+  stage_row_twiddles(stw, bar, t.inv + ((size_t)lm.mod[limb] << logN), R1 + blockIdx.x * ROW_WARPS);
+  bool ready = false;
   for (int poly = 0; poly < l.n_polys; ++poly) {
     if (poly == lm.skip[limb]) continue;
     const LimbCtx lc = limb_ctx(t, logN, lm, l, true, limb, poly);
     const u64 *inp = lc.in + (size_t)row * R2 + (lane >> 4) * 128 + 2 * (lane & 15);
     double a[8];
-    double2 w[4], wn[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) wn[j] = __ldg(&lc.tw[lane_stage_tw(tw_base, 0, j, lane)]);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(inp + j * 32));
       a[j] = u64_to_f64(v.x);
       a[j + 4] = u64_to_f64(v.y);
     }
+    if (!ready) { mbar_wait(bar + 2, 0); mbar_wait(bar + 1, 0); mbar_wait(bar, 0); ready = true; }  // the inverse starts with stage 7
 #pragma unroll
     for (int b = 0; b <= 4; ++b) {
+      double2 tw4[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) w[j] = wn[j];
-      if (b < 4) {
+      for (int j = 0; j < 4; ++j) tw4[j] = stw[lane_stage_stw(w, b, j, lane)];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) wn[j] = __ldg(&lc.tw[lane_stage_tw(tw_base, b + 1, j, lane)]);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) gs_butterfly(a[j], a[j + 4], w[j].x, w[j].y, lc.q);
+      for (int j = 0; j < 4; ++j) gs_butterfly(a[j], a[j + 4], tw4[j].x, tw4[j].y, lc.q);
       swap_half(a, b, (lane >> b) & 1);
     }
-    gs_round<LR, 0, 3>(a, lane, lc.tw, tw_base, lc.q);
+    {  // stages t = 32, 64, 128
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const double2 w2 = stw[row_tw_off(2) + (w << 2) + g];
+        gs_butterfly(a[2 * g], a[2 * g + 1], w2.x, w2.y, lc.q);
+      }
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const double2 w1 = stw[row_tw_off(1) + (w << 1) + g];
+#pragma unroll
+        for (int o = 0; o < 2; ++o) gs_butterfly(a[4 * g + o], a[4 * g + o + 2], w1.x, w1.y, lc.q);
+      }
+      const double2 w0 = stw[row_tw_off(0) + w];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) gs_butterfly(a[o], a[o + 4], w0.x, w0.y, lc.q);
+    }
     double *outd = reinterpret_cast<double *>(lc.out) + (size_t)row * R2;
     // the sums have grown to <= 2^8 q: bring them back to |v| <= q/2 before the column pass doubles them again
 #pragma unroll
     for (int r = 0; r < 8; ++r) outd[r * 32 + lane] = reduce_signed(a[r], lc.q, lc.qinv);
   }
+  if (!ready) { mbar_wait(bar, 0); mbar_wait(bar + 1, 0); mbar_wait(bar + 2, 0); }
 }
 
 // ================================================================================ inverse, columns (second)
