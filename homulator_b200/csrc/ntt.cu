@@ -3,6 +3,34 @@
 
 namespace hml {
 
+// ---- asynchronous bulk copy (TMA engine, no tensor map) global -> shared, completion on an mbarrier
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // A "round" = S consecutive radix-2 stages (S <= 3) of a length-2^LOGR sub-NTT, starting at stage ST,
 // executed on 8 register-resident points per thread.  Thread unit u in [0, 2^LOGR / 8) owns 8/2^S
@@ -23,7 +51,7 @@ struct Round {
 // twiddle index of the butterfly whose lower point is p, at stage i of a sub-NTT whose twiddle block
 // starts at tw_base (1 for the column pass; R1 + row for the row pass): (tw_base << i) + p / (2t)
 // One stage of a round: JS = position in the 3-stage register pattern (distance 4 >> JS).
-template <int LOGR, int ST, int S, int JS, bool INV>
+template <int LOGR, int ST, int S, int JS, bool INV, bool TW_SMEM>
 __device__ __forceinline__ void round_stage(double (&a)[8], int u, const double2 *__restrict__ tw, unsigned tw_base, double q) {
   using RD = Round<LOGR, ST, S>;
   constexpr int h = 4 >> JS, i = ST + JS - (3 - S);
@@ -31,7 +59,8 @@ __device__ __forceinline__ void round_stage(double (&a)[8], int u, const double2
   for (int sg = 0; sg < (1 << JS); ++sg) {
     const int r0 = sg << (3 - JS);
     const int p0 = RD::point(u, r0);
-    const double2 w = __ldg(&tw[(tw_base << i) + (p0 >> (LOGR - i))]);
+    const unsigned ti = (tw_base << i) + (p0 >> (LOGR - i));
+    const double2 w = TW_SMEM ? tw[ti] : __ldg(&tw[ti]);
 #pragma unroll
     for (int o = 0; o < h; ++o) {
       if constexpr (INV) gs_butterfly(a[r0 + o], a[r0 + o + h], w.x, w.y, q);
@@ -40,18 +69,18 @@ __device__ __forceinline__ void round_stage(double (&a)[8], int u, const double2
   }
 }
 
-template <int LOGR, int ST, int S>
+template <int LOGR, int ST, int S, bool TW_SMEM = false>
 __device__ __forceinline__ void ct_round(double (&a)[8], int u, const double2 *__restrict__ tw, unsigned tw_base, double q) {
-  if constexpr (S >= 3) round_stage<LOGR, ST, S, 0, false>(a, u, tw, tw_base, q);
-  if constexpr (S >= 2) round_stage<LOGR, ST, S, 1, false>(a, u, tw, tw_base, q);
-  round_stage<LOGR, ST, S, 2, false>(a, u, tw, tw_base, q);
+  if constexpr (S >= 3) round_stage<LOGR, ST, S, 0, false, TW_SMEM>(a, u, tw, tw_base, q);
+  if constexpr (S >= 2) round_stage<LOGR, ST, S, 1, false, TW_SMEM>(a, u, tw, tw_base, q);
+  round_stage<LOGR, ST, S, 2, false, TW_SMEM>(a, u, tw, tw_base, q);
 }
 
-template <int LOGR, int ST, int S>
+template <int LOGR, int ST, int S, bool TW_SMEM = false>
 __device__ __forceinline__ void gs_round(double (&a)[8], int u, const double2 *__restrict__ tw, unsigned tw_base, double q) {
-  round_stage<LOGR, ST, S, 2, true>(a, u, tw, tw_base, q);
-  if constexpr (S >= 2) round_stage<LOGR, ST, S, 1, true>(a, u, tw, tw_base, q);
-  if constexpr (S >= 3) round_stage<LOGR, ST, S, 0, true>(a, u, tw, tw_base, q);
+  round_stage<LOGR, ST, S, 2, true, TW_SMEM>(a, u, tw, tw_base, q);
+  if constexpr (S >= 2) round_stage<LOGR, ST, S, 1, true, TW_SMEM>(a, u, tw, tw_base, q);
+  if constexpr (S >= 3) round_stage<LOGR, ST, S, 0, true, TW_SMEM>(a, u, tw, tw_base, q);
 }
 
 // round split of a length-2^LOGR sub-NTT: S1 = 3, then S2, S3 (S3 may be 0)
@@ -89,10 +118,18 @@ template <int LOGR1>
 __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_fwd_cols(NttTables t, int logN, LimbMap lm, NttLaunch l) {
   constexpr int R1 = 1 << LOGR1, C = NTT_TILE / R1, R2 = 1 << NTT_ROW_LOG;
   using SP = Split<LOGR1>;
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];  // [R1][C] tile, then the R1 twiddles of the column pass
+  double2 *stw = reinterpret_cast<double2 *>(sm + NTT_TILE);
+  __shared__ __align__(8) unsigned long long bar;
   const int limb = blockIdx.y % l.n_limbs, poly = blockIdx.y / l.n_limbs;
   if (poly == lm.skip[limb]) return;
   const LimbCtx lc = limb_ctx(t, logN, lm, l, false, limb, poly);
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {  // every column shares the same 2^LOGR1 twiddles: one 4 KB bulk copy
+    mbar_expect_tx(&bar, R1 * 16u);
+    bulk_g2s(stw, lc.tw, R1 * 16u, &bar);
+  }
   const int c = threadIdx.x % C, u = threadIdx.x / C;
   const int col = blockIdx.x * C + c;
   double a[8];
@@ -100,7 +137,8 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_fwd_cols(NttTables t, int 
     using RD = Round<LOGR1, 0, SP::S1>;
 #pragma unroll
     for (int r = 0; r < 8; ++r) a[r] = u64_to_f64(__ldg(&lc.in[(size_t)RD::point(u, r) * R2 + col]));
-    ct_round<LOGR1, 0, SP::S1>(a, u, lc.tw, 1u, lc.q);
+    mbar_wait(&bar, 0);
+    ct_round<LOGR1, 0, SP::S1, true>(a, u, stw, 1u, lc.q);
 #pragma unroll
     for (int r = 0; r < 8; ++r) sm[RD::point(u, r) * C + c] = a[r];
   }
@@ -110,7 +148,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_fwd_cols(NttTables t, int 
     using RD = Round<LOGR1, SP::S1, SP::S2>;
 #pragma unroll
     for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(u, r) * C + c];
-    ct_round<LOGR1, SP::S1, SP::S2>(a, u, lc.tw, 1u, lc.q);
+    ct_round<LOGR1, SP::S1, SP::S2, true>(a, u, stw, 1u, lc.q);
 #pragma unroll
     for (int r = 0; r < 8; ++r) outd[(size_t)RD::point(u, r) * R2 + col] = a[r];
   } else {
@@ -118,7 +156,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_fwd_cols(NttTables t, int 
       using RD = Round<LOGR1, SP::S1, SP::S2>;
 #pragma unroll
       for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(u, r) * C + c];
-      ct_round<LOGR1, SP::S1, SP::S2>(a, u, lc.tw, 1u, lc.q);
+      ct_round<LOGR1, SP::S1, SP::S2, true>(a, u, stw, 1u, lc.q);
 #pragma unroll
       for (int r = 0; r < 8; ++r) sm[RD::point(u, r) * C + c] = a[r];
     }
@@ -126,7 +164,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_fwd_cols(NttTables t, int 
     using RD = Round<LOGR1, SP::S1 + SP::S2, SP::S3>;
 #pragma unroll
     for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(u, r) * C + c];
-    ct_round<LOGR1, SP::S1 + SP::S2, SP::S3>(a, u, lc.tw, 1u, lc.q);
+    ct_round<LOGR1, SP::S1 + SP::S2, SP::S3, true>(a, u, stw, 1u, lc.q);
 #pragma unroll
     for (int r = 0; r < 8; ++r) outd[(size_t)RD::point(u, r) * R2 + col] = a[r];
   }
@@ -159,34 +197,6 @@ __device__ __forceinline__ void swap_half(double (&a)[8], int b, bool upper) {
 __device__ __forceinline__ unsigned lane_stage_tw(unsigned tw_base, int b, int j, int lane) {
   const int kk = j + ((lane >> 4) << 2);
   return (tw_base << (7 - b)) + (kk << (4 - b)) + ((lane & 15) >> b);
-}
-
-// ---- asynchronous bulk copy (TMA engine, no tensor map) global -> shared, completion on an mbarrier
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
 }
 
 // The twiddles of the CTA's ROW_WARPS consecutive rows form ONE contiguous table segment per stage
@@ -334,10 +344,18 @@ template <int LOGR1>
 __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_inv_cols(NttTables t, int logN, LimbMap lm, NttLaunch l) {
   constexpr int R1 = 1 << LOGR1, C = NTT_TILE / R1, R2 = 1 << NTT_ROW_LOG;
   using SP = Split<LOGR1>;
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];  // [R1][C] tile, then the R1 twiddles of the column pass
+  double2 *stw = reinterpret_cast<double2 *>(sm + NTT_TILE);
+  __shared__ __align__(8) unsigned long long bar;
   const int limb = blockIdx.y % l.n_limbs, poly = blockIdx.y / l.n_limbs;
   if (poly == lm.skip[limb]) return;
   const LimbCtx lc = limb_ctx(t, logN, lm, l, true, limb, poly);
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {  // every column shares the same 2^LOGR1 twiddles: one 4 KB bulk copy
+    mbar_expect_tx(&bar, R1 * 16u);
+    bulk_g2s(stw, lc.tw, R1 * 16u, &bar);
+  }
   const int c = threadIdx.x % C, u = threadIdx.x / C;
   const int col = blockIdx.x * C + c;
   const double *ind = reinterpret_cast<const double *>(lc.out);
@@ -347,7 +365,8 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_inv_cols(NttTables t, int 
       using RD = Round<LOGR1, SP::S1 + SP::S2, SP::S3>;
 #pragma unroll
       for (int r = 0; r < 8; ++r) a[r] = ind[(size_t)RD::point(u, r) * R2 + col];
-      gs_round<LOGR1, SP::S1 + SP::S2, SP::S3>(a, u, lc.tw, 1u, lc.q);
+      mbar_wait(&bar, 0);
+      gs_round<LOGR1, SP::S1 + SP::S2, SP::S3, true>(a, u, stw, 1u, lc.q);
 #pragma unroll
       for (int r = 0; r < 8; ++r) sm[RD::point(u, r) * C + c] = a[r];
     }
@@ -355,14 +374,15 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_inv_cols(NttTables t, int 
     using RD = Round<LOGR1, SP::S1, SP::S2>;
 #pragma unroll
     for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(u, r) * C + c];
-    gs_round<LOGR1, SP::S1, SP::S2>(a, u, lc.tw, 1u, lc.q);
+    gs_round<LOGR1, SP::S1, SP::S2, true>(a, u, stw, 1u, lc.q);
 #pragma unroll
     for (int r = 0; r < 8; ++r) sm[RD::point(u, r) * C + c] = a[r];
   } else {
     using RD = Round<LOGR1, SP::S1, SP::S2>;
 #pragma unroll
     for (int r = 0; r < 8; ++r) a[r] = ind[(size_t)RD::point(u, r) * R2 + col];
-    gs_round<LOGR1, SP::S1, SP::S2>(a, u, lc.tw, 1u, lc.q);
+    mbar_wait(&bar, 0);
+    gs_round<LOGR1, SP::S1, SP::S2, true>(a, u, stw, 1u, lc.q);
 #pragma unroll
     for (int r = 0; r < 8; ++r) sm[RD::point(u, r) * C + c] = a[r];
   }
@@ -370,7 +390,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_inv_cols(NttTables t, int 
   using RD = Round<LOGR1, 0, SP::S1>;
 #pragma unroll
   for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(u, r) * C + c];
-  gs_round<LOGR1, 0, SP::S1>(a, u, lc.tw, 1u, lc.q);
+  gs_round<LOGR1, 0, SP::S1, true>(a, u, stw, 1u, lc.q);
   double2 sc;
   if (l.post_scale) sc = l.post_scale[lc.limb];
   else { const ModConst mc = t.mc[lm.mod[lc.limb]]; sc = make_double2(mc.ninv, mc.ninv_q); }
@@ -428,7 +448,7 @@ template <int LOGR1>
 static void launch_fwd_t(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
   constexpr int C = NTT_TILE >> LOGR1;
   const dim3 g1((1 << NTT_ROW_LOG) / C, l.n_limbs * l.n_polys), g2((1 << LOGR1) / ROW_WARPS, l.n_limbs);
-  ntt_fwd_cols<LOGR1><<<g1, NTT_THREADS, NTT_TILE * sizeof(double), s>>>(t, logN, lm, l);
+  ntt_fwd_cols<LOGR1><<<g1, NTT_THREADS, NTT_TILE * sizeof(double) + (16u << LOGR1), s>>>(t, logN, lm, l);
   ntt_fwd_rows<<<g2, ROW_WARPS * 32, 0, s>>>(t, logN, lm, l);
 }
 template <int LOGR1>
@@ -436,7 +456,7 @@ static void launch_inv_t(const NttTables &t, int logN, const LimbMap &lm, const 
   constexpr int C = NTT_TILE >> LOGR1;
   const dim3 g1((1 << LOGR1) / ROW_WARPS, l.n_limbs), g2((1 << NTT_ROW_LOG) / C, l.n_limbs * l.n_polys);
   ntt_inv_rows<<<g1, ROW_WARPS * 32, 0, s>>>(t, logN, lm, l);
-  ntt_inv_cols<LOGR1><<<g2, NTT_THREADS, NTT_TILE * sizeof(double), s>>>(t, logN, lm, l);
+  ntt_inv_cols<LOGR1><<<g2, NTT_THREADS, NTT_TILE * sizeof(double) + (16u << LOGR1), s>>>(t, logN, lm, l);
 }
 
 void launch_ntt_forward(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
