@@ -319,6 +319,7 @@ static int ntt_api(hml_ctx *ctx, bool inverse, const uint64_t *in, uint64_t *out
     LimbMap lm;
     id_map(lm, mod_idx + off, n);
     NttLaunch l{};
+    l.n_batch = 1;
     l.in = (const u64 *)in + off * N; l.out = (u64 *)out + off * N;
     l.in_limb_stride = l.out_limb_stride = N; l.n_limbs = n; l.n_polys = 1; l.post_scale = nullptr;
     if (inverse) launch_ntt_inverse(ctx->tabs, ctx->p.logN, lm, l, (cudaStream_t)stream);
@@ -408,9 +409,20 @@ static size_t ks_ws_words(const Params &p, uint32_t L) {
   return N * (L + (size_t)p.beta(L) * E + 2 * E + 2 * (size_t)L);
 }
 
-// d [L][N] -> out_c = KS_c(d) (+ add_c).  `ws` must hold ks_ws_words().
-static int ks_run(hml_ctx *ctx, uint32_t L, const u64 *d, const u64 *evk, uint32_t evk_q_limbs, u64 *out0, u64 *out1,
-                  const u64 *add0, const u64 *add1, u64 *ws, cudaStream_t s) {
+// Strided view of `nb` independent polynomials / ciphertext halves: item b lives at ptr + b * stride (words).
+struct BatchPtr {
+  const u64 *ptr;
+  long long stride;
+};
+struct BatchOut {
+  u64 *ptr;
+  long long stride;
+};
+
+// nb independent key switches sharing one key, one kernel launch per stage:
+// d[b] [L][N] -> out_c[b] = KS_c(d[b]) (+ add_c[b]).  `ws` must hold nb * ks_ws_words().
+static int ks_run(hml_ctx *ctx, uint32_t L, uint32_t nb, BatchPtr d, const u64 *evk, uint32_t evk_q_limbs, BatchOut out0,
+                  BatchOut out1, BatchPtr add0, BatchPtr add1, u64 *ws, cudaStream_t s) {
   const Params &p = ctx->p;
   if (evk_q_limbs < L || evk_q_limbs > p.max_level) return fail(ctx, HML_ERR_INVALID, "evk_q_limbs must be in [L, maxLevel]");
   LevelConsts *lc;
@@ -418,21 +430,24 @@ static int ks_run(hml_ctx *ctx, uint32_t L, const u64 *d, const u64 *evk, uint32
   if (rc) return rc;
   const size_t N = p.N;
   const uint32_t A = p.alpha, E = L + A, beta = lc->beta;
-  u64 *yb = ws, *ext = yb + (size_t)L * N, *acc = ext + (size_t)beta * E * N, *vb = acc + 2 * (size_t)E * N;
+  if (beta > 8) return fail(ctx, HML_ERR_UNSUPPORTED, "more than 8 key-switch digits (ceil(L/alpha) > 8)");
+  // workspace, every buffer batch-major: yb [nb][L] | ext [nb][beta][E] | acc [nb][2][E] | vb [nb][2][L]  (limbs of N words)
+  u64 *yb = ws, *ext = yb + (size_t)nb * L * N, *acc = ext + (size_t)nb * beta * E * N, *vb = acc + (size_t)nb * 2 * E * N;
   const int logN = p.logN, npass = logN <= 12 ? 1 : 2;
   // K1 + K2 (reference :63-135): INTT of the input, digit scaling folded into the N^-1 multiply
   {
     NttLaunch l{};
-    l.in = d; l.out = yb; l.in_limb_stride = l.out_limb_stride = N; l.n_limbs = L; l.n_polys = 1; l.post_scale = lc->modup_scale;
+    l.in = d.ptr; l.out = yb; l.in_limb_stride = l.out_limb_stride = N; l.n_limbs = L; l.n_polys = 1; l.post_scale = lc->modup_scale;
+    l.n_batch = nb; l.in_batch_stride = d.stride; l.out_batch_stride = (long long)L * N;
     launch_ntt_inverse(ctx->tabs, logN, lc->q_lm, l, s);
-    ctx->exec.intt_limbs += L; ctx->exec.ewe_limbs += 0; ctx->exec.kernel_launches += npass;
+    ctx->exec.intt_limbs += (uint64_t)nb * L; ctx->exec.kernel_launches += npass;
   }
   // K3 (reference :137-188): convert every digit to the limbs of the extended basis it does not own
   for (uint32_t j = 0; j < beta; ++j) {
-    const uint32_t lo = j * A, aj = p.digit_size(L, j);
+    const uint32_t lo = j * A;
     BConvArgs a{};
     a.in = yb + (size_t)lo * N; a.out = ext + (size_t)j * E * N; a.step1 = nullptr;
-    a.N = N; a.n_batches = 1;
+    a.N = N; a.n_batches = nb; a.in_batch_stride = (long long)L * N; a.out_batch_stride = (long long)beta * E * N;
     run_bconv(ctx, lc->up[j], lc->q_lm, a, s);
   }
   // K4 (reference :190-292): NTT of the converted limbs.  The digit's own limbs are the untouched input
@@ -441,48 +456,56 @@ static int ks_run(hml_ctx *ctx, uint32_t L, const u64 *d, const u64 *evk, uint32
     NttLaunch l{};
     l.in = ext; l.out = ext; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)E * N;
     l.n_limbs = E; l.n_polys = beta;  // digit j skips the limbs it owns (LimbMap::skip)
+    l.n_batch = nb; l.in_batch_stride = l.out_batch_stride = (long long)beta * E * N;
     launch_ntt_forward(ctx->tabs, logN, lc->ext_lm, l, s);
-    ctx->exec.ntt_limbs += (uint64_t)beta * E - L; ctx->exec.kernel_launches += npass;
+    ctx->exec.ntt_limbs += (uint64_t)nb * ((uint64_t)beta * E - L); ctx->exec.kernel_launches += npass;
   }
-  // K5 (reference :294-414): inner product with the key
+  // K5 (reference :294-414): inner product with the key (key words loaded once per batch)
   {
     LimbMap ip = lc->ext_lm;  // pos = limb index inside the key (Q-limbs first, then P-limbs after evk_q_limbs)
     for (uint32_t e = 0; e < E; ++e) ip.pos[e] = (uint16_t)(e < L ? e : evk_q_limbs + (e - L));
     InnerArgs a{};
-    a.d = d; a.ext = ext; a.evk = evk; a.acc = acc; a.N = N; a.n_ext = E; a.beta = beta; a.evk_limbs = evk_q_limbs + A;
+    a.d = d.ptr; a.ext = ext; a.evk = evk; a.acc = acc; a.N = N; a.n_ext = E; a.beta = beta; a.evk_limbs = evk_q_limbs + A;
+    a.n_batch = nb; a.d_batch_stride = d.stride; a.ext_batch_stride = (long long)beta * E * N; a.acc_batch_stride = 2ll * E * N;
     launch_inner_product(ctx->mc, ip, a, s);
-    ctx->exec.ewe_limbs += 2ull * E * beta; ctx->exec.kernel_launches++;
+    ctx->exec.ewe_limbs += 2ull * nb * E * beta; ctx->exec.kernel_launches++;
   }
   // K6 + K7 (reference :417-487): INTT of the P-limbs of both accumulators, in place, BConv step 1 folded in
   {
     NttLaunch l{};
     l.in = acc; l.out = acc; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)E * N;
-    l.n_limbs = A; l.n_polys = 2; l.post_scale = lc->moddown_scale;
+    l.n_limbs = A; l.n_polys = 2 * nb; l.post_scale = lc->moddown_scale;  // acc is [nb][2][E][N]: uniform poly stride
+    l.n_batch = 1;
     launch_ntt_inverse(ctx->tabs, logN, lc->p_lm, l, s);
-    ctx->exec.intt_limbs += 2 * A; ctx->exec.kernel_launches += npass;
+    ctx->exec.intt_limbs += 2ull * nb * A; ctx->exec.kernel_launches += npass;
   }
   // K8 (reference :489-519): P -> Q_L
   {
     BConvArgs a{};
     a.in = acc; a.out = vb; a.in_batch_stride = (long long)E * N; a.out_batch_stride = (long long)L * N;  // p_lm.pos = L + j
-    a.step1 = nullptr; a.N = N; a.n_batches = 2;
+    a.step1 = nullptr; a.N = N; a.n_batches = 2 * nb;
     run_bconv(ctx, lc->down, lc->p_lm, a, s);
   }
   // K9 (reference :521-546, emitted with opcode INTT — delta D1): forward NTT of the converted limbs
   {
     NttLaunch l{};
     l.in = vb; l.out = vb; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)L * N;
-    l.n_limbs = L; l.n_polys = 2;
+    l.n_limbs = L; l.n_polys = 2 * nb; l.n_batch = 1;
     launch_ntt_forward(ctx->tabs, logN, lc->q_lm, l, s);
-    ctx->exec.ntt_limbs += 2 * L; ctx->exec.kernel_launches += npass;
+    ctx->exec.ntt_limbs += 2ull * nb * L; ctx->exec.kernel_launches += npass;
   }
   // K10 (reference :548-590) (+ the caller's addend: HMULT add :967-1005 / HROTATE add :1339-1357)
   for (int c = 0; c < 2; ++c) {
+    const BatchPtr add = c ? add1 : add0;
+    const BatchOut out = c ? out1 : out0;
     SubMulArgs a{};
-    a.x = acc + (size_t)c * E * N; a.y = vb + (size_t)c * L * N; a.z = c ? add1 : add0; a.out = c ? out1 : out0;
-    a.cst = lc->pinv; a.N = N; a.n_limbs = L; a.n_polys = 1;
+    a.x = acc + (size_t)c * E * N; a.x_poly_stride = 2ll * E * N;
+    a.y = vb + (size_t)c * L * N; a.y_poly_stride = 2ll * L * N;
+    a.z = add.ptr; a.z_poly_stride = add.stride;
+    a.out = out.ptr; a.out_poly_stride = out.stride;
+    a.cst = lc->pinv; a.N = N; a.n_limbs = L; a.n_polys = nb;
     launch_sub_mul_add(ctx->mc, lc->q_lm, a, s);
-    ctx->exec.ewe_limbs += L + (a.z ? L : 0); ctx->exec.kernel_launches++;
+    ctx->exec.ewe_limbs += (uint64_t)nb * (L + (a.z ? L : 0)); ctx->exec.kernel_launches++;
   }
   return check_launch(ctx, "keyswitch");
 }
@@ -494,8 +517,8 @@ extern "C" int hml_keyswitch(hml_ctx *ctx, uint32_t L, const uint64_t *d, const 
   if (!d || !evk || !out0 || !out1) return fail(ctx, HML_ERR_INVALID, "null buffer");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   if ((rc = ensure_ws(ctx, ks_ws_words(ctx->p, L)))) return rc;
-  return ks_run(ctx, L, (const u64 *)d, (const u64 *)evk, evk_q_limbs, (u64 *)out0, (u64 *)out1, nullptr, nullptr, ctx->ws,
-                (cudaStream_t)stream);
+  return ks_run(ctx, L, 1, {(const u64 *)d, 0}, (const u64 *)evk, evk_q_limbs, {(u64 *)out0, 0}, {(u64 *)out1, 0}, {nullptr, 0},
+                {nullptr, 0}, ctx->ws, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------ limb-sharded key switch
@@ -629,6 +652,7 @@ extern "C" int hml_keyswitch_shard_begin(hml_ctx *ctx, uint32_t L, uint32_t rank
   const uint32_t nq = sp->own_q.size();
   if (nq) {
     NttLaunch l{};
+    l.n_batch = 1;
     l.in = (const u64 *)d_own; l.out = (u64 *)gather1 + (size_t)rank * sp->gq * N;
     l.in_limb_stride = l.out_limb_stride = N; l.n_limbs = nq; l.n_polys = 1; l.post_scale = sp->scale1;
     launch_ntt_inverse(ctx->tabs, ctx->p.logN, sp->q_lm, l, (cudaStream_t)stream);
@@ -661,6 +685,7 @@ extern "C" int hml_keyswitch_shard_mid(hml_ctx *ctx, uint32_t L, uint32_t rank, 
   }
   {
     NttLaunch l{};
+    l.n_batch = 1;
     l.in = ext; l.out = ext; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)ne * N;
     l.n_limbs = ne; l.n_polys = beta;
     launch_ntt_forward(ctx->tabs, logN, sp->e_lm, l, s);
@@ -669,12 +694,13 @@ extern "C" int hml_keyswitch_shard_mid(hml_ctx *ctx, uint32_t L, uint32_t rank, 
   {
     InnerArgs a{};
     a.d = (const u64 *)d_own; a.ext = ext; a.evk = (const u64 *)evk_own; a.acc = acc; a.N = N; a.n_ext = ne; a.beta = beta;
-    a.evk_limbs = ne;
+    a.evk_limbs = ne; a.n_batch = 1;
     launch_inner_product(ctx->mc, sp->e_lm, a, s);
     ctx->exec.ewe_limbs += 2ull * ne * beta; ctx->exec.kernel_launches++;
   }
   if (np) {
     NttLaunch l{};
+    l.n_batch = 1;
     l.in = acc; l.out = acc; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)ne * N;
     l.n_limbs = np; l.n_polys = 2; l.post_scale = sp->scale2;
     launch_ntt_inverse(ctx->tabs, logN, sp->p_lm, l, s);
@@ -711,6 +737,7 @@ extern "C" int hml_keyswitch_shard_end(hml_ctx *ctx, uint32_t L, uint32_t rank, 
   }
   {
     NttLaunch l{};
+    l.n_batch = 1;
     l.in = vb; l.out = vb; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)nq * N;
     l.n_limbs = nq; l.n_polys = 2;
     launch_ntt_forward(ctx->tabs, logN, sp->q_lm, l, s);
@@ -729,7 +756,7 @@ extern "C" int hml_keyswitch_shard_end(hml_ctx *ctx, uint32_t L, uint32_t rank, 
 // ------------------------------------------------------------------------------------------------ rescale
 static size_t rs_ws_words(const Params &p, uint32_t L, uint32_t n_polys) { return (size_t)p.N * n_polys * L; }
 
-// in: n_polys polys of L limbs (stride in_poly_stride) -> out: n_polys polys of L-1 limbs
+// in: n_polys polys of L limbs (uniform stride in_poly_stride) -> out: n_polys polys of L-1 limbs
 static int rescale_run(hml_ctx *ctx, uint32_t L, const u64 *in, long long in_poly_stride, uint32_t n_polys, u64 *out,
                        long long out_poly_stride, u64 *ws, cudaStream_t s) {
   const Params &p = ctx->p;
@@ -743,6 +770,7 @@ static int rescale_run(hml_ctx *ctx, uint32_t L, const u64 *in, long long in_pol
     LimbMap lm; clear_map(lm);
     lm.mod[0] = L - 1; lm.pos[0] = 0;
     NttLaunch l{};
+    l.n_batch = 1;
     l.in = in + (size_t)(L - 1) * N; l.out = rb; l.in_limb_stride = l.out_limb_stride = N;
     l.in_poly_stride = in_poly_stride; l.out_poly_stride = N; l.n_limbs = 1; l.n_polys = n_polys;
     launch_ntt_inverse(ctx->tabs, logN, lm, l, s);
@@ -750,6 +778,7 @@ static int rescale_run(hml_ctx *ctx, uint32_t L, const u64 *in, long long in_pol
   }
   {  // NTT of that polynomial under each remaining modulus (reference :807-822 counts ONE; delta D2)
     NttLaunch l{};
+    l.n_batch = 1;
     l.in = rb; l.out = rh; l.in_limb_stride = 0; l.out_limb_stride = N; l.in_poly_stride = N;
     l.out_poly_stride = (long long)(L - 1) * N; l.n_limbs = L - 1; l.n_polys = n_polys;
     launch_ntt_forward(ctx->tabs, logN, lc->q_lm, l, s);
@@ -775,19 +804,26 @@ extern "C" int hml_rescale(hml_ctx *ctx, uint32_t L, const uint64_t *in, uint64_
 }
 
 // ------------------------------------------------------------------------------------------------ top-level ops
-static size_t hmult_ws_words(const Params &p, uint32_t L) {
-  return (size_t)p.N * 5 * L + std::max(ks_ws_words(p, L), rs_ws_words(p, L, 2));
+// Batched ops run HML_BATCH_CHUNK ciphertexts per kernel launch: per-CTA set-up (twiddle staging, conversion matrices,
+// key words) is paid once per chunk instead of once per ciphertext and grids are large enough to hide launch tails.
+constexpr uint32_t HML_BATCH_CHUNK = 8;
+
+static size_t hmult_ws_words(const Params &p, uint32_t L, uint32_t nb) {
+  return (size_t)nb * ((size_t)p.N * 5 * L + std::max(ks_ws_words(p, L), rs_ws_words(p, L, 2)));
 }
 
-static int hmult_run(hml_ctx *ctx, uint32_t L, const u64 *ct_a, const u64 *ct_b, const u64 *evk, uint32_t evk_q_limbs,
+// nb ciphertext pairs [nb][2][L][N] -> [nb][2][L-1][N]
+static int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, const u64 *ct_b, const u64 *evk, uint32_t evk_q_limbs,
                      u64 *ct_out, cudaStream_t s) {
   const size_t N = ctx->p.N, PL = N * L;
-  u64 *d0 = ctx->ws, *d1 = d0 + PL, *d2 = d1 + PL, *cb = d2 + PL, *rest = cb + 2 * PL;
-  launch_tensor3(ctx->mc, (int)N, (int)L, ct_a, ct_a + PL, ct_b, ct_b + PL, d0, d1, d2, s);  // reference :592-739
-  ctx->exec.ewe_limbs += 3ull * L; ctx->exec.kernel_launches++;
-  int rc = ks_run(ctx, L, d2, evk, evk_q_limbs, cb, cb + PL, d0, d1, rest, s);
+  // d0 | d1 | d2 each [nb][L][N], cb [nb][2][L][N], then the key-switch / rescale workspace
+  u64 *d0 = ctx->ws, *d1 = d0 + nb * PL, *d2 = d1 + nb * PL, *cb = d2 + nb * PL, *rest = cb + 2 * nb * PL;
+  launch_tensor3(ctx->mc, (int)N, (int)L, ct_a, ct_a + PL, ct_b, ct_b + PL, d0, d1, d2, (int)nb, (long long)(2 * PL), (long long)PL, s);  // reference :592-739
+  ctx->exec.ewe_limbs += 3ull * nb * L; ctx->exec.kernel_launches++;
+  int rc = ks_run(ctx, L, nb, {d2, (long long)PL}, evk, evk_q_limbs, {cb, (long long)(2 * PL)}, {cb + PL, (long long)(2 * PL)}, {d0, (long long)PL},
+                  {d1, (long long)PL}, rest, s);
   if (rc) return rc;
-  return rescale_run(ctx, L, cb, (long long)PL, 2, ct_out, (long long)(L - 1) * N, rest, s);
+  return rescale_run(ctx, L, cb, (long long)PL, 2 * nb, ct_out, (long long)(L - 1) * N, rest, s);
 }
 
 extern "C" int hml_hmult(hml_ctx *ctx, uint32_t L, const uint64_t *ct_a, const uint64_t *ct_b, const uint64_t *evk,
@@ -796,21 +832,23 @@ extern "C" int hml_hmult(hml_ctx *ctx, uint32_t L, const uint64_t *ct_a, const u
   if (rc) return rc;
   if (!ct_a || !ct_b || !evk || !ct_out) return fail(ctx, HML_ERR_INVALID, "null buffer");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  if ((rc = ensure_ws(ctx, hmult_ws_words(ctx->p, L)))) return rc;
-  return hmult_run(ctx, L, (const u64 *)ct_a, (const u64 *)ct_b, (const u64 *)evk, evk_q_limbs, (u64 *)ct_out, (cudaStream_t)stream);
+  if ((rc = ensure_ws(ctx, hmult_ws_words(ctx->p, L, 1)))) return rc;
+  return hmult_run(ctx, L, 1, (const u64 *)ct_a, (const u64 *)ct_b, (const u64 *)evk, evk_q_limbs, (u64 *)ct_out, (cudaStream_t)stream);
 }
 
-static size_t hrot_ws_words(const Params &p, uint32_t L) { return (size_t)p.N * 2 * L + ks_ws_words(p, L); }
+static size_t hrot_ws_words(const Params &p, uint32_t L, uint32_t nb) { return (size_t)nb * ((size_t)p.N * 2 * L + ks_ws_words(p, L)); }
 
-static int hrot_run(hml_ctx *ctx, uint32_t L, const u64 *ct, const u64 *rk, uint32_t evk_q_limbs, u64 g, u64 *ct_out,
+// nb ciphertexts [nb][2][L][N] -> [nb][2][L][N]
+static int hrot_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct, const u64 *rk, uint32_t evk_q_limbs, u64 g, u64 *ct_out,
                     cudaStream_t s) {
   const size_t N = ctx->p.N, PL = N * L;
-  u64 *sb = ctx->ws, *rest = sb + 2 * PL;
-  launch_automorph(ctx->p.logN, 2 * L, ct, sb, g, s);  // reference :1302-1319
-  ctx->exec.automorph_limbs += 2ull * L; ctx->exec.kernel_launches++;
+  u64 *sb = ctx->ws, *rest = sb + 2 * nb * PL;  // sb [nb][2][L][N]
+  launch_automorph(ctx->p.logN, 2 * L * nb, ct, sb, g, s);  // reference :1302-1319
+  ctx->exec.automorph_limbs += 2ull * nb * L; ctx->exec.kernel_launches++;
   // reference :1326-1357 key-switches AUTOOutput(0) and adds AUTOOutput(1) (naming only, delta D4):
   // textbook = key-switch sigma(c1), add sigma(c0) to the first output
-  return ks_run(ctx, L, sb + PL, rk, evk_q_limbs, ct_out, ct_out + PL, sb, nullptr, rest, s);
+  return ks_run(ctx, L, nb, {sb + PL, (long long)(2 * PL)}, rk, evk_q_limbs, {ct_out, (long long)(2 * PL)}, {ct_out + PL, (long long)(2 * PL)}, {sb, (long long)(2 * PL)},
+                {nullptr, 0}, rest, s);
 }
 
 extern "C" int hml_hrotate(hml_ctx *ctx, uint32_t L, const uint64_t *ct, const uint64_t *rotkey, uint32_t evk_q_limbs,
@@ -820,8 +858,8 @@ extern "C" int hml_hrotate(hml_ctx *ctx, uint32_t L, const uint64_t *ct, const u
   if (!ct || !rotkey || !ct_out) return fail(ctx, HML_ERR_INVALID, "null buffer");
   if (!(galois_elt & 1)) return fail(ctx, HML_ERR_INVALID, "galois element must be odd");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  if ((rc = ensure_ws(ctx, hrot_ws_words(ctx->p, L)))) return rc;
-  return hrot_run(ctx, L, (const u64 *)ct, (const u64 *)rotkey, evk_q_limbs, galois_elt, (u64 *)ct_out, (cudaStream_t)stream);
+  if ((rc = ensure_ws(ctx, hrot_ws_words(ctx->p, L, 1)))) return rc;
+  return hrot_run(ctx, L, 1, (const u64 *)ct, (const u64 *)rotkey, evk_q_limbs, galois_elt, (u64 *)ct_out, (cudaStream_t)stream);
 }
 
 static int ew_ct_op(hml_ctx *ctx, uint32_t L, const uint64_t *a, const uint64_t *b, bool b_is_pt, bool mul, uint64_t *out, void *stream) {
@@ -857,12 +895,14 @@ extern "C" int hml_hmult_batch(hml_ctx *ctx, uint32_t L, uint32_t n, const uint6
   if (rc) return rc;
   if (!ct_a || !ct_b || !evk || !ct_out) return fail(ctx, HML_ERR_INVALID, "null buffer");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  if ((rc = ensure_ws(ctx, hmult_ws_words(ctx->p, L)))) return rc;
+  if ((rc = ensure_ws(ctx, hmult_ws_words(ctx->p, L, std::min(n, HML_BATCH_CHUNK))))) return rc;
   const size_t N = ctx->p.N, in_w = 2 * N * L, out_w = 2 * N * (L - 1);
-  for (uint32_t i = 0; i < n; ++i)
-    if ((rc = hmult_run(ctx, L, (const u64 *)ct_a + i * in_w, (const u64 *)ct_b + i * in_w, (const u64 *)evk, evk_q_limbs,
+  for (uint32_t i = 0; i < n; i += HML_BATCH_CHUNK) {
+    const uint32_t nb = std::min(HML_BATCH_CHUNK, n - i);
+    if ((rc = hmult_run(ctx, L, nb, (const u64 *)ct_a + i * in_w, (const u64 *)ct_b + i * in_w, (const u64 *)evk, evk_q_limbs,
                         (u64 *)ct_out + i * out_w, (cudaStream_t)stream)))
       return rc;
+  }
   return HML_OK;
 }
 
@@ -873,12 +913,14 @@ extern "C" int hml_hrotate_batch(hml_ctx *ctx, uint32_t L, uint32_t n, const uin
   if (!ct || !rotkey || !ct_out) return fail(ctx, HML_ERR_INVALID, "null buffer");
   if (!(galois_elt & 1)) return fail(ctx, HML_ERR_INVALID, "galois element must be odd");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  if ((rc = ensure_ws(ctx, hrot_ws_words(ctx->p, L)))) return rc;
+  if ((rc = ensure_ws(ctx, hrot_ws_words(ctx->p, L, std::min(n, HML_BATCH_CHUNK))))) return rc;
   const size_t w = 2 * (size_t)ctx->p.N * L;
-  for (uint32_t i = 0; i < n; ++i)
-    if ((rc = hrot_run(ctx, L, (const u64 *)ct + i * w, (const u64 *)rotkey, evk_q_limbs, galois_elt, (u64 *)ct_out + i * w,
+  for (uint32_t i = 0; i < n; i += HML_BATCH_CHUNK) {
+    const uint32_t nb = std::min(HML_BATCH_CHUNK, n - i);
+    if ((rc = hrot_run(ctx, L, nb, (const u64 *)ct + i * w, (const u64 *)rotkey, evk_q_limbs, galois_elt, (u64 *)ct_out + i * w,
                        (cudaStream_t)stream)))
       return rc;
+  }
   return HML_OK;
 }
 
@@ -891,7 +933,7 @@ static int host_pipeline(hml_ctx *ctx, bool is_mult, uint32_t L, uint32_t n, con
   if (rc) return rc;
   if (!a_host || (is_mult && !b_host) || !key_dev || !out_host) return fail(ctx, HML_ERR_INVALID, "null buffer");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  if ((rc = ensure_ws(ctx, is_mult ? hmult_ws_words(ctx->p, L) : hrot_ws_words(ctx->p, L)))) return rc;
+  if ((rc = ensure_ws(ctx, is_mult ? hmult_ws_words(ctx->p, L, 1) : hrot_ws_words(ctx->p, L, 1)))) return rc;
   const size_t N = ctx->p.N, in_w = 2 * N * L, out_w = 2 * N * (is_mult ? L - 1 : L);
   const size_t slot_w = (is_mult ? 2 : 1) * in_w + out_w;
   if (ctx->stage_words < 2 * slot_w) {
@@ -922,8 +964,8 @@ static int host_pipeline(hml_ctx *ctx, bool is_mult, uint32_t L, uint32_t n, con
     cudaEventRecord(ev_in[k], ctx->s_in);
     cudaStreamWaitEvent(ctx->s_comp, ev_in[k], 0);
     if (i >= 2) cudaStreamWaitEvent(ctx->s_comp, ev_out[k], 0);  // slot output free once item i-2 has been copied out
-    rc = is_mult ? hmult_run(ctx, L, sa, sb, (const u64 *)key_dev, evk_q_limbs, so, ctx->s_comp)
-                 : hrot_run(ctx, L, sa, (const u64 *)key_dev, evk_q_limbs, g, so, ctx->s_comp);
+    rc = is_mult ? hmult_run(ctx, L, 1, sa, sb, (const u64 *)key_dev, evk_q_limbs, so, ctx->s_comp)
+                 : hrot_run(ctx, L, 1, sa, (const u64 *)key_dev, evk_q_limbs, g, so, ctx->s_comp);
     cudaEventRecord(ev_comp[k], ctx->s_comp);
     cudaStreamWaitEvent(ctx->s_out, ev_comp[k], 0);
     cudaMemcpyAsync(out_host + i * out_w, so, out_w * 8, cudaMemcpyDeviceToHost, ctx->s_out);

@@ -15,8 +15,9 @@ void launch_ewe(const ModConst *mc, const LimbMap &lm, int N, int n_limbs, const
                 const u64 *x4, int subtract, u64 *out, cudaStream_t s);
 
 // TensorCompute (reference src/Operation.cpp:592-739): d0 = a0*b0, d1 = a0*b1 + a1*b0, d2 = a1*b1; limbs 0..L-1
+// n_batch ciphertext pairs: inputs advance by in_stride words per pair, outputs by out_stride.
 void launch_tensor3(const ModConst *mc, int N, int L, const u64 *a0, const u64 *a1, const u64 *b0, const u64 *b1,
-                    u64 *d0, u64 *d1, u64 *d2, cudaStream_t s);
+                    u64 *d0, u64 *d1, u64 *d2, int n_batch, long long in_stride, long long out_stride, cudaStream_t s);
 
 // Key-switch inner product (reference src/Operation.cpp:294-414, emitted as MULT) over n_ext extended limbs:
 //   acc[c][e] = sum_j t_j[e] * evk[j][c][lm.pos[e]],   modulus lm.mod[e]
@@ -26,7 +27,9 @@ struct InnerArgs {
   const u64 *ext;   // [beta][n_ext][N]
   const u64 *evk;   // [beta][2][evk_limbs][N]
   u64 *acc;         // [2][n_ext][N]
-  int N, n_ext, beta, evk_limbs;
+  int N, n_ext, beta, evk_limbs;   // beta <= 8
+  int n_batch;                     // ciphertexts sharing the key: d / ext / acc advance by the strides below
+  long long d_batch_stride, ext_batch_stride, acc_batch_stride;
 };
 void launch_inner_product(const ModConst *mc, const LimbMap &lm, const InnerArgs &a, cudaStream_t s);
 

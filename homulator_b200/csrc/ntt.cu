@@ -100,7 +100,7 @@ struct LimbCtx {
 };
 
 __device__ __forceinline__ LimbCtx limb_ctx(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, bool inverse,
-                                            int limb, int poly) {
+                                            int limb, int poly, int batch = 0) {
   LimbCtx c;
   c.limb = limb;
   const int mi = lm.mod[c.limb];
@@ -108,8 +108,8 @@ __device__ __forceinline__ LimbCtx limb_ctx(const NttTables &t, int logN, const 
   c.q = mc.q; c.qinv = mc.qinv; c.qi = mc.qi;
   c.tw = (inverse ? t.inv : t.fwd) + ((size_t)mi << logN);
   const long long slot = lm.pos[c.limb];
-  c.in = l.in + (long long)poly * l.in_poly_stride + slot * l.in_limb_stride;
-  c.out = l.out + (long long)poly * l.out_poly_stride + slot * l.out_limb_stride;
+  c.in = l.in + (long long)batch * l.in_batch_stride + (long long)poly * l.in_poly_stride + slot * l.in_limb_stride;
+  c.out = l.out + (long long)batch * l.out_batch_stride + (long long)poly * l.out_poly_stride + slot * l.out_limb_stride;
   return c;
 }
 
@@ -121,9 +121,9 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_fwd_cols(NttTables t, int 
   extern __shared__ __align__(16) double sm[];  // [R1][C] tile, then the R1 twiddles of the column pass
   double2 *stw = reinterpret_cast<double2 *>(sm + NTT_TILE);
   __shared__ __align__(8) unsigned long long bar;
-  const int limb = blockIdx.y % l.n_limbs, poly = blockIdx.y / l.n_limbs;
+  const int limb = blockIdx.y % l.n_limbs, poly = (blockIdx.y / l.n_limbs) % l.n_polys, batch = blockIdx.y / (l.n_limbs * l.n_polys);
   if (poly == lm.skip[limb]) return;
-  const LimbCtx lc = limb_ctx(t, logN, lm, l, false, limb, poly);
+  const LimbCtx lc = limb_ctx(t, logN, lm, l, false, limb, poly, batch);
   if (threadIdx.x == 0) mbar_init(&bar, 1);
   __syncthreads();
   if (threadIdx.x == 0) {  // every column shares the same 2^LOGR1 twiddles: one 4 KB bulk copy
@@ -229,7 +229,10 @@ __device__ __forceinline__ int lane_stage_stw(int w, int b, int j, int lane) {
 
 // Polys that share the limb's modulus (the beta digits of ModUp, the two key-switch accumulators, the two
 // rescaled polys) are processed back to back by the same warp with the same shared twiddles.
-__global__ void __launch_bounds__(ROW_WARPS * 32, 4) ntt_fwd_rows(NttTables t, int logN, LimbMap lm, NttLaunch l) {
+// PIPE: software-pipelined item loop (next item's row prefetched into registers; 3 CTAs/SM) for launches with
+// several items per limb; the plain variant keeps 4 CTAs/SM for single-item launches.
+template <bool PIPE>
+__global__ void __launch_bounds__(ROW_WARPS * 32, PIPE ? 3 : 4) ntt_fwd_rows(NttTables t, int logN, LimbMap lm, NttLaunch l) {
   constexpr int LR = NTT_ROW_LOG, R2 = 1 << LR;
   __shared__ __align__(16) double2 stw[ROW_TW_ENTRIES];
   __shared__ __align__(8) unsigned long long bar[3];
@@ -238,13 +241,36 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) ntt_fwd_rows(NttTables t, i
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, row = blockIdx.x * ROW_WARPS + w;
   stage_row_twiddles(stw, bar, t.fwd + ((size_t)lm.mod[limb] << logN), R1 + blockIdx.x * ROW_WARPS);
   bool ready = false;
-  for (int poly = 0; poly < l.n_polys; ++poly) {
-    if (poly == lm.skip[limb]) continue;
-    const LimbCtx lc = limb_ctx(t, logN, lm, l, false, limb, poly);
-    const double *ind = reinterpret_cast<const double *>(lc.out) + (size_t)row * R2;  // pass 1 left raw doubles in `out`
-    double a[8];
+  // items = (ciphertext b, poly p) pairs sharing this limb's modulus; the next item's row is in flight (registers)
+  // while the current one is transformed
+  const int skip = lm.skip[limb], n_items = l.n_polys * l.n_batch;
+  auto next_item = [&](int it) { ++it; while (it < n_items && (it % l.n_polys) == skip) ++it; return it; };
+  int item = next_item(-1);
+  double nx[PIPE ? 8 : 1];
+  if (PIPE && item < n_items) {
+    const LimbCtx lc0 = limb_ctx(t, logN, lm, l, false, limb, item % l.n_polys, item / l.n_polys);
+    const double *ind = reinterpret_cast<const double *>(lc0.out) + (size_t)row * R2;  // pass 1 left raw doubles in `out`
 #pragma unroll
-    for (int r = 0; r < 8; ++r) a[r] = ind[r * 32 + lane];
+    for (int r = 0; r < 8; ++r) nx[PIPE ? r : 0] = ind[r * 32 + lane];
+  }
+  while (item < n_items) {
+    const LimbCtx lc = limb_ctx(t, logN, lm, l, false, limb, item % l.n_polys, item / l.n_polys);
+    double a[8];
+    if (PIPE) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) a[r] = nx[PIPE ? r : 0];
+    } else {
+      const double *ind = reinterpret_cast<const double *>(lc.out) + (size_t)row * R2;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) a[r] = ind[r * 32 + lane];
+    }
+    item = next_item(item);
+    if (PIPE && item < n_items) {
+      const LimbCtx ln = limb_ctx(t, logN, lm, l, false, limb, item % l.n_polys, item / l.n_polys);
+      const double *ind = reinterpret_cast<const double *>(ln.out) + (size_t)row * R2;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) nx[PIPE ? r : 0] = ind[r * 32 + lane];
+    }
     if (!ready) mbar_wait(bar, 0);
     {  // stages t = 128, 64, 32: register-only, twiddles broadcast from shared memory
       const double2 w0 = stw[row_tw_off(0) + w];
@@ -285,7 +311,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) ntt_fwd_rows(NttTables t, i
   if (!ready) { mbar_wait(bar, 0); mbar_wait(bar + 1, 0); mbar_wait(bar + 2, 0); }  // never exit with a bulk copy in flight
 }
 
-__global__ void __launch_bounds__(ROW_WARPS * 32, 4) ntt_inv_rows(NttTables t, int logN, LimbMap lm, NttLaunch l) {
+template <bool PIPE>
+__global__ void __launch_bounds__(ROW_WARPS * 32, PIPE ? 3 : 4) ntt_inv_rows(NttTables t, int logN, LimbMap lm, NttLaunch l) {
   constexpr int LR = NTT_ROW_LOG, R2 = 1 << LR;
   __shared__ __align__(16) double2 stw[ROW_TW_ENTRIES];
   __shared__ __align__(8) unsigned long long bar[3];
@@ -294,16 +321,40 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) ntt_inv_rows(NttTables t, i
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, row = blockIdx.x * ROW_WARPS + w;
   stage_row_twiddles(stw, bar, t.inv + ((size_t)lm.mod[limb] << logN), R1 + blockIdx.x * ROW_WARPS);
   bool ready = false;
-  for (int poly = 0; poly < l.n_polys; ++poly) {
-    if (poly == lm.skip[limb]) continue;
-    const LimbCtx lc = limb_ctx(t, logN, lm, l, true, limb, poly);
-    const u64 *inp = lc.in + (size_t)row * R2 + (lane >> 4) * 128 + 2 * (lane & 15);
-    double a[8];
+  const int skip = lm.skip[limb], n_items = l.n_polys * l.n_batch;
+  auto next_item = [&](int it) { ++it; while (it < n_items && (it % l.n_polys) == skip) ++it; return it; };
+  int item = next_item(-1);
+  ulonglong2 nx[PIPE ? 4 : 1];
+  if (PIPE && item < n_items) {
+    const LimbCtx lc0 = limb_ctx(t, logN, lm, l, true, limb, item % l.n_polys, item / l.n_polys);
+    const u64 *inp = lc0.in + (size_t)row * R2 + (lane >> 4) * 128 + 2 * (lane & 15);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(inp + j * 32));
-      a[j] = u64_to_f64(v.x);
-      a[j + 4] = u64_to_f64(v.y);
+    for (int j = 0; j < 4; ++j) nx[PIPE ? j : 0] = __ldg(reinterpret_cast<const ulonglong2 *>(inp + j * 32));
+  }
+  while (item < n_items) {
+    const LimbCtx lc = limb_ctx(t, logN, lm, l, true, limb, item % l.n_polys, item / l.n_polys);
+    double a[8];
+    if (PIPE) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a[j] = u64_to_f64(nx[PIPE ? j : 0].x);
+        a[j + 4] = u64_to_f64(nx[PIPE ? j : 0].y);
+      }
+    } else {
+      const u64 *inp = lc.in + (size_t)row * R2 + (lane >> 4) * 128 + 2 * (lane & 15);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(inp + j * 32));
+        a[j] = u64_to_f64(v.x);
+        a[j + 4] = u64_to_f64(v.y);
+      }
+    }
+    item = next_item(item);
+    if (PIPE && item < n_items) {
+      const LimbCtx ln = limb_ctx(t, logN, lm, l, true, limb, item % l.n_polys, item / l.n_polys);
+      const u64 *inp = ln.in + (size_t)row * R2 + (lane >> 4) * 128 + 2 * (lane & 15);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) nx[PIPE ? j : 0] = __ldg(reinterpret_cast<const ulonglong2 *>(inp + j * 32));
     }
     if (!ready) { mbar_wait(bar + 2, 0); mbar_wait(bar + 1, 0); mbar_wait(bar, 0); ready = true; }  // the inverse starts with stage 7
 #pragma unroll
@@ -347,9 +398,9 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_inv_cols(NttTables t, int 
   extern __shared__ __align__(16) double sm[];  // [R1][C] tile, then the R1 twiddles of the column pass
   double2 *stw = reinterpret_cast<double2 *>(sm + NTT_TILE);
   __shared__ __align__(8) unsigned long long bar;
-  const int limb = blockIdx.y % l.n_limbs, poly = blockIdx.y / l.n_limbs;
+  const int limb = blockIdx.y % l.n_limbs, poly = (blockIdx.y / l.n_limbs) % l.n_polys, batch = blockIdx.y / (l.n_limbs * l.n_polys);
   if (poly == lm.skip[limb]) return;
-  const LimbCtx lc = limb_ctx(t, logN, lm, l, true, limb, poly);
+  const LimbCtx lc = limb_ctx(t, logN, lm, l, true, limb, poly, batch);
   if (threadIdx.x == 0) mbar_init(&bar, 1);
   __syncthreads();
   if (threadIdx.x == 0) {  // every column shares the same 2^LOGR1 twiddles: one 4 KB bulk copy
@@ -402,9 +453,9 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_inv_cols(NttTables t, int 
 // ================================================================================ small N (<= 4096): one CTA per limb
 __global__ void __launch_bounds__(256) ntt_small(NttTables t, int logN, LimbMap lm, NttLaunch l, int inverse) {
   extern __shared__ double sm[];
-  const int limb = blockIdx.y % l.n_limbs, poly = blockIdx.y / l.n_limbs;
+  const int limb = blockIdx.y % l.n_limbs, poly = (blockIdx.y / l.n_limbs) % l.n_polys, batch = blockIdx.y / (l.n_limbs * l.n_polys);
   if (poly == lm.skip[limb]) return;
-  const LimbCtx lc = limb_ctx(t, logN, lm, l, inverse != 0, limb, poly);
+  const LimbCtx lc = limb_ctx(t, logN, lm, l, inverse != 0, limb, poly, batch);
   const int N = 1 << logN, half = N >> 1;
   for (int i = threadIdx.x; i < N; i += blockDim.x) sm[i] = u64_to_f64(__ldg(&lc.in[i]));
   __syncthreads();
@@ -447,21 +498,23 @@ __global__ void __launch_bounds__(256) ntt_small(NttTables t, int logN, LimbMap 
 template <int LOGR1>
 static void launch_fwd_t(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
   constexpr int C = NTT_TILE >> LOGR1;
-  const dim3 g1((1 << NTT_ROW_LOG) / C, l.n_limbs * l.n_polys), g2((1 << LOGR1) / ROW_WARPS, l.n_limbs);
+  const dim3 g1((1 << NTT_ROW_LOG) / C, l.n_limbs * l.n_polys * l.n_batch), g2((1 << LOGR1) / ROW_WARPS, l.n_limbs);
   ntt_fwd_cols<LOGR1><<<g1, NTT_THREADS, NTT_TILE * sizeof(double) + (16u << LOGR1), s>>>(t, logN, lm, l);
-  ntt_fwd_rows<<<g2, ROW_WARPS * 32, 0, s>>>(t, logN, lm, l);
+  if (l.n_polys * l.n_batch >= 3) ntt_fwd_rows<true><<<g2, ROW_WARPS * 32, 0, s>>>(t, logN, lm, l);
+  else ntt_fwd_rows<false><<<g2, ROW_WARPS * 32, 0, s>>>(t, logN, lm, l);
 }
 template <int LOGR1>
 static void launch_inv_t(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
   constexpr int C = NTT_TILE >> LOGR1;
-  const dim3 g1((1 << LOGR1) / ROW_WARPS, l.n_limbs), g2((1 << NTT_ROW_LOG) / C, l.n_limbs * l.n_polys);
-  ntt_inv_rows<<<g1, ROW_WARPS * 32, 0, s>>>(t, logN, lm, l);
+  const dim3 g1((1 << LOGR1) / ROW_WARPS, l.n_limbs), g2((1 << NTT_ROW_LOG) / C, l.n_limbs * l.n_polys * l.n_batch);
+  if (l.n_polys * l.n_batch >= 3) ntt_inv_rows<true><<<g1, ROW_WARPS * 32, 0, s>>>(t, logN, lm, l);
+  else ntt_inv_rows<false><<<g1, ROW_WARPS * 32, 0, s>>>(t, logN, lm, l);
   ntt_inv_cols<LOGR1><<<g2, NTT_THREADS, NTT_TILE * sizeof(double) + (16u << LOGR1), s>>>(t, logN, lm, l);
 }
 
 void launch_ntt_forward(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
   if (logN <= 12) {
-    ntt_small<<<dim3(1, l.n_limbs * l.n_polys), 256, sizeof(double) << logN, s>>>(t, logN, lm, l, 0);
+    ntt_small<<<dim3(1, l.n_limbs * l.n_polys * l.n_batch), 256, sizeof(double) << logN, s>>>(t, logN, lm, l, 0);
     return;
   }
   switch (logN - NTT_ROW_LOG) {
@@ -474,7 +527,7 @@ void launch_ntt_forward(const NttTables &t, int logN, const LimbMap &lm, const N
 
 void launch_ntt_inverse(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
   if (logN <= 12) {
-    ntt_small<<<dim3(1, l.n_limbs * l.n_polys), 256, sizeof(double) << logN, s>>>(t, logN, lm, l, 1);
+    ntt_small<<<dim3(1, l.n_limbs * l.n_polys * l.n_batch), 256, sizeof(double) << logN, s>>>(t, logN, lm, l, 1);
     return;
   }
   switch (logN - NTT_ROW_LOG) {

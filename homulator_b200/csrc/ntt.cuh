@@ -46,6 +46,8 @@ struct NttLaunch {
   long long in_poly_stride, in_limb_stride;    // in_limb_stride = 0 broadcasts one source limb (rescale)
   long long out_poly_stride, out_limb_stride;
   int n_limbs, n_polys;
+  int n_batch;                                  // independent ciphertexts: item (b, p) lives at base + b * batch_stride + p * poly_stride
+  long long in_batch_stride, out_batch_stride;
   // inverse only: per-limb post-scale constant c (folded with N^-1 on the host): out = INTT(in) * c, canonical.
   const double2 *post_scale;  // [n_limbs] (c*ninv mod q, RN(that / q)) or nullptr for plain N^-1
 };
