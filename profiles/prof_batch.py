@@ -1,0 +1,23 @@
+"""Profiling driver for the batched path: hmult_batch over one chunk of 8 ciphertext pairs."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import homulator_b200 as hml  # noqa: E402
+
+n_warm = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+n_prof = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+L, A, B = 35, 15, 8
+ctx = hml.Context(os.path.join(ROOT, "config", "config_4.cfg"), 45, A)
+q = list(range(L))
+evk = ctx.uniform(ctx.ext_mod_idx(L), 3, lead=(3, 2))
+a = ctx.uniform(q, 1, lead=(B, 2))
+b = ctx.uniform(q, 2, lead=(B, 2))
+out = ctx.empty(B, 2, L - 1, ctx.N)
+torch.cuda.synchronize()
+for _ in range(n_warm + n_prof):
+    ctx.hmult_batch(L, a, b, evk, out=out)
+torch.cuda.synchronize()
+print("done")
