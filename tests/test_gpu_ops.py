@@ -188,3 +188,32 @@ def test_op_sequence_replay_matches_oracle():
             h[op[1]] = o.hmult(L, h[op[2]], h[op[3]], evk, L)
     assert np.array_equal(to_host(env["y"]), h["y"])
     assert np.array_equal(to_host(env["z"]), h["z"])
+
+
+@pytest.mark.parametrize("n", [1, 8, 11])
+def test_batch_chunking_small(n):
+    """hml_*_batch runs 8 ciphertexts per launch: cover a partial chunk, one full chunk and a full + partial chunk."""
+    N, ML, A, L = 2048, 7, 3, 7
+    ctx, o = hml.Context(N=N, max_level=ML, alpha=A), Oracle(N, 36, ML, A)
+    (a, b), evk = make_case(o, L, L, 1200)
+    q = list(range(L))
+    As = torch.stack([to_dev(a) if i % 2 == 0 else to_dev(b) for i in range(n)])
+    Bs = ctx.uniform(q, 77, lead=(n, 2))
+    K = to_dev(evk)
+    got = ctx.hmult_batch(L, As, Bs, K)
+    for i in (0, n // 2, n - 1):
+        want = o.hmult(L, to_host(As[i]), to_host(Bs[i]), evk, L)
+        assert np.array_equal(to_host(got[i]), want), i
+    rot = ctx.hrotate_batch(L, Bs, K, 25)
+    for i in (0, n - 1):
+        assert np.array_equal(to_host(rot[i]), o.hrotate(L, to_host(Bs[i]), evk, L, 25)), i
+
+
+def test_invalid_key_layout_is_rejected():
+    ctx = hml.Context(N=1024, max_level=6, alpha=2)
+    x = ctx.uniform(list(range(4)), 1, lead=(2,))
+    evk = ctx.uniform(ctx.ext_mod_idx(4), 2, lead=(2, 2))
+    with pytest.raises(hml.HmlError):
+        ctx.hmult(4, x, x, evk, evk_q_limbs=3)   # fewer Q-limbs in the key than the level needs
+    with pytest.raises(hml.HmlError):
+        ctx.hmult(4, x, x, evk, evk_q_limbs=7)   # more than maxLevel
