@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "planner.h"
@@ -806,7 +807,15 @@ extern "C" int hml_rescale(hml_ctx *ctx, uint32_t L, const uint64_t *in, uint64_
 // ------------------------------------------------------------------------------------------------ top-level ops
 // Batched ops run HML_BATCH_CHUNK ciphertexts per kernel launch: per-CTA set-up (twiddle staging, conversion matrices,
 // key words) is paid once per chunk instead of once per ciphertext and grids are large enough to hide launch tails.
-constexpr uint32_t HML_BATCH_CHUNK = 8;
+static uint32_t batch_chunk() {
+  static const uint32_t v = [] {
+    const char *e = getenv("HML_BATCH_CHUNK");  // tuning knob; default 8
+    const int n = e ? atoi(e) : 8;
+    return (uint32_t)std::min(std::max(n, 1), 32);
+  }();
+  return v;
+}
+#define HML_BATCH_CHUNK batch_chunk()
 
 static size_t hmult_ws_words(const Params &p, uint32_t L, uint32_t nb) {
   return (size_t)nb * ((size_t)p.N * 5 * L + std::max(ks_ws_words(p, L), rs_ws_words(p, L, 2)));
