@@ -38,42 +38,32 @@ static int upload(hml_ctx *ctx, const std::vector<T> &h, T **dev) {
   return HML_OK;
 }
 
-// A base conversion prepared for launch: destination limbs split into chunks that fit kernel-parameter space
-// (n_src * chunk <= BCONV_MAX_PAIRS), each with its matrix in 12-bit pieces and its destination LimbMap.
+// A base conversion prepared for launch: the matrix in 12-bit pieces, zero-padded, uploaded once; the destination LimbMap.
 // dst_pos[t] = limb slot (in the output buffer) of destination t.
-static void prepare_bconv(const BConvTable &bt, const std::vector<uint32_t> &dst_pos, hml::HostBConv &out) {
+static int prepare_bconv(hml_ctx *ctx, const BConvTable &bt, const std::vector<uint32_t> &dst_pos, hml::HostBConv &out) {
   const int ns = (int)bt.src.size(), nd = (int)bt.dst.size();
-  int chunk = BCONV_MAX_PAIRS / ns;
-  if (chunk >= nd) chunk = nd;
-  else chunk -= chunk % 7 ? chunk % 7 : 0;  // keep chunks a multiple of the tallest tile
+  const int nsp = bconv_pad_src(ns), ndp = bconv_pad_dst(nd);
   out.n_src = ns; out.n_dst = nd;
-  out.chunks.clear();
-  for (int first = 0; first < nd; first += chunk) {
-    hml::HostBConvChunk ch;
-    ch.first = first; ch.count = std::min(chunk, nd - first);
-    memset(&ch.mat, 0, sizeof(ch.mat));
-    memset(&ch.dst_lm, 0, sizeof(ch.dst_lm));
-    for (int t = 0; t < ch.count; ++t) {
-      ch.dst_lm.mod[t] = (uint16_t)bt.dst[first + t];
-      ch.dst_lm.pos[t] = (uint16_t)dst_pos[first + t];
-      for (int i = 0; i < ns; ++i) {
-        const u64 h = bt.hat[(size_t)i * nd + first + t];
-        double *d = &ch.mat.h[((size_t)i * ch.count + t) * 3];
-        d[0] = (double)(h & 0xFFF);
-        d[1] = (double)((h >> 12) & 0xFFF);
-        d[2] = (double)(h >> 24);
-      }
+  memset(&out.dst_lm, 0, sizeof(out.dst_lm));
+  std::vector<double> m((size_t)nsp * ndp * 3, 0.0);
+  for (int t = 0; t < nd; ++t) {
+    out.dst_lm.mod[t] = (uint16_t)bt.dst[t];
+    out.dst_lm.pos[t] = (uint16_t)dst_pos[t];
+    for (int i = 0; i < ns; ++i) {
+      const u64 h = bt.hat[(size_t)i * nd + t];
+      double *d = &m[((size_t)i * ndp + t) * 3];
+      d[0] = (double)(h & 0xFFF);
+      d[1] = (double)((h >> 12) & 0xFFF);
+      d[2] = (double)(h >> 24);
     }
-    out.chunks.push_back(ch);
   }
+  return upload(ctx, m, &out.d_mat);
 }
 
 static void run_bconv(hml_ctx *ctx, const hml::HostBConv &hb, const LimbMap &src_lm, BConvArgs a, cudaStream_t s) {
-  for (const auto &ch : hb.chunks) {
-    a.n_src = hb.n_src; a.n_dst = ch.count;
-    launch_bconv(ctx->mc, src_lm, ch.dst_lm, a, ch.mat, s);
-    ctx->exec.kernel_launches++;
-  }
+  a.n_src = hb.n_src; a.n_dst = hb.n_dst;
+  launch_bconv(ctx->mc, src_lm, hb.dst_lm, a, hb.d_mat, s);
+  ctx->exec.kernel_launches++;
   ctx->exec.bconv_limb_macs += (uint64_t)hb.n_src * hb.n_dst * a.n_batches;
 }
 
@@ -89,16 +79,21 @@ static int ctx_init_device(hml_ctx *ctx) {
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   const Params &p = ctx->p;
   const size_t N = p.N, nm = p.n_mod();
-  std::vector<double2> f(nm * N), iv(nm * N);
+  const bool two_pass = p.logN > NTT_SMALL_LOG;
+  std::vector<double> f(nm * N), iv(nm * N), fr(two_pass ? nm * N : 0), ir(two_pass ? nm * N : 0);
   std::vector<ModConst> mc(nm);
   std::vector<u64> tw;
   for (uint32_t i = 0; i < nm; ++i) {
     const u64 q = p.mod[i];
     const double qd = (double)q;
     p.twiddles(i, false, tw);
-    for (size_t k = 0; k < N; ++k) f[i * N + k] = make_double2((double)tw[k], (double)tw[k] / qd);
+    for (size_t k = 0; k < N; ++k) f[i * N + k] = (double)tw[k];
     p.twiddles(i, true, tw);
-    for (size_t k = 0; k < N; ++k) iv[i * N + k] = make_double2((double)tw[k], (double)tw[k] / qd);
+    for (size_t k = 0; k < N; ++k) iv[i * N + k] = (double)tw[k];
+    if (two_pass) {
+      ntt_permute_row_twiddles(&f[i * N], (int)p.logN, &fr[i * N]);
+      ntt_permute_row_twiddles(&iv[i * N], (int)p.logN, &ir[i * N]);
+    }
     mc[i].q = qd; mc[i].qinv = 1.0 / qd;
     mc[i].ninv = (double)p.n_inv[i]; mc[i].ninv_q = (double)p.n_inv[i] / qd;
     mc[i].qi = q; mc[i].pad = 0;
@@ -106,7 +101,10 @@ static int ctx_init_device(hml_ctx *ctx) {
   int rc;
   if ((rc = upload(ctx, f, &ctx->tw_fwd))) return rc;
   if ((rc = upload(ctx, iv, &ctx->tw_inv))) return rc;
+  if ((rc = upload(ctx, fr, &ctx->tw_fwd_rows))) return rc;
+  if ((rc = upload(ctx, ir, &ctx->tw_inv_rows))) return rc;
   if ((rc = upload(ctx, mc, &ctx->mc))) return rc;
+  ctx->tabs.fwd_rows = ctx->tw_fwd_rows; ctx->tabs.inv_rows = ctx->tw_inv_rows;
   ctx->tabs.fwd = ctx->tw_fwd; ctx->tabs.inv = ctx->tw_inv; ctx->tabs.mc = ctx->mc;
   return HML_OK;
 }
@@ -151,15 +149,20 @@ extern "C" int hml_ctx_create(const char *cfg_path, uint32_t max_level, uint32_t
 
 static void free_level(LevelConsts &lc) {
   cudaFree(lc.modup_scale); cudaFree(lc.moddown_scale); cudaFree(lc.pinv); cudaFree(lc.qlinv);
+  for (auto &u : lc.up) cudaFree(u.d_mat);
+  cudaFree(lc.down.d_mat);
 }
 
 extern "C" void hml_ctx_destroy(hml_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   for (auto &kv : ctx->levels) free_level(kv.second);
-  for (auto &kv : ctx->bconv_cache) cudaFree(kv.second.step1);
-  for (auto &kv : ctx->shard_plans) { cudaFree(kv.second.scale1); cudaFree(kv.second.scale2); cudaFree(kv.second.pinv); }
-  cudaFree(ctx->tw_fwd); cudaFree(ctx->tw_inv); cudaFree(ctx->mc); cudaFree(ctx->ws); cudaFree(ctx->stage);
+  for (auto &kv : ctx->bconv_cache) { cudaFree(kv.second.step1); cudaFree(kv.second.host.d_mat); }
+  for (auto &kv : ctx->shard_plans) {
+    cudaFree(kv.second.scale1); cudaFree(kv.second.scale2); cudaFree(kv.second.pinv); cudaFree(kv.second.down.d_mat);
+    for (auto &u : kv.second.up) cudaFree(u.d_mat);
+  }
+  cudaFree(ctx->tw_fwd); cudaFree(ctx->tw_inv); cudaFree(ctx->tw_fwd_rows); cudaFree(ctx->tw_inv_rows); cudaFree(ctx->mc); cudaFree(ctx->ws); cudaFree(ctx->stage);
   if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
   if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
   if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
@@ -265,7 +268,7 @@ static int get_level(hml_ctx *ctx, uint32_t L, LevelConsts **out) {
       up_scale[lo + i] = mk_cst(h_mulmod(p.n_inv[lo + i], bt.hat_inv[i], q), q);
     }
     lc.up.emplace_back();
-    prepare_bconv(bt, dst_pos, lc.up.back());
+    if ((rc = prepare_bconv(ctx, bt, dst_pos, lc.up.back()))) return rc;
   }
   if ((rc = upload(ctx, up_scale, &lc.modup_scale))) return rc;
   // ---- ModDown
@@ -286,7 +289,7 @@ static int get_level(hml_ctx *ctx, uint32_t L, LevelConsts **out) {
       for (uint32_t j = 0; j < A; ++j) P = h_mulmod(P, p.mod[p.max_level + j] % q, q);
       pinv[i] = mk_cst(h_invmod(P, q), q);
     }
-    prepare_bconv(bt, dst, lc.down);
+    if ((rc = prepare_bconv(ctx, bt, dst, lc.down))) return rc;
     if ((rc = upload(ctx, sc, &lc.moddown_scale))) return rc;
     if ((rc = upload(ctx, pinv, &lc.pinv))) return rc;
   }
@@ -325,7 +328,7 @@ static int ntt_api(hml_ctx *ctx, bool inverse, const uint64_t *in, uint64_t *out
     l.in_limb_stride = l.out_limb_stride = N; l.n_limbs = n; l.n_polys = 1; l.post_scale = nullptr;
     if (inverse) launch_ntt_inverse(ctx->tabs, ctx->p.logN, lm, l, (cudaStream_t)stream);
     else launch_ntt_forward(ctx->tabs, ctx->p.logN, lm, l, (cudaStream_t)stream);
-    ctx->exec.kernel_launches += ctx->p.logN <= 12 ? 1 : 2;
+    ctx->exec.kernel_launches += ctx->p.logN <= NTT_SMALL_LOG ? 1 : 2;
   }
   (inverse ? ctx->exec.intt_limbs : ctx->exec.ntt_limbs) += n_limbs;
   return check_launch(ctx, inverse ? "intt" : "ntt");
@@ -391,7 +394,7 @@ extern "C" int hml_bconv(hml_ctx *ctx, const uint64_t *in, const uint32_t *src_i
     if ((rc = upload(ctx, s1, &d.step1))) return rc;
     std::vector<uint32_t> ident(n_dst);
     for (uint32_t t = 0; t < n_dst; ++t) ident[t] = t;
-    prepare_bconv(bt, ident, d.host);
+    if ((rc = prepare_bconv(ctx, bt, ident, d.host))) return rc;
     it = ctx->bconv_cache.emplace(key, d).first;
   }
   LimbMap slm;
@@ -434,7 +437,7 @@ static int ks_run(hml_ctx *ctx, uint32_t L, uint32_t nb, BatchPtr d, const u64 *
   if (beta > 8) return fail(ctx, HML_ERR_UNSUPPORTED, "more than 8 key-switch digits (ceil(L/alpha) > 8)");
   // workspace, every buffer batch-major: yb [nb][L] | ext [nb][beta][E] | acc [nb][2][E] | vb [nb][2][L]  (limbs of N words)
   u64 *yb = ws, *ext = yb + (size_t)nb * L * N, *acc = ext + (size_t)nb * beta * E * N, *vb = acc + (size_t)nb * 2 * E * N;
-  const int logN = p.logN, npass = logN <= 12 ? 1 : 2;
+  const int logN = p.logN, npass = logN <= NTT_SMALL_LOG ? 1 : 2;
   // K1 + K2 (reference :63-135): INTT of the input, digit scaling folded into the N^-1 multiply
   {
     NttLaunch l{};
@@ -593,7 +596,7 @@ static int get_shard_plan(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t worl
     if (!dst.empty()) {
       BConvTable bt;
       make_bconv_table(p, src, dst, bt);
-      prepare_bconv(bt, dst_pos, sp.up.back());
+      if ((rc = prepare_bconv(ctx, bt, dst_pos, sp.up.back()))) return rc;
     }
   }
   {  // ModDown conversion: all P-limbs (read from gather buffer 2) -> owned Q-limbs
@@ -604,7 +607,7 @@ static int get_shard_plan(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t worl
     if (!dst.empty()) {
       BConvTable bt;
       make_bconv_table(p, src, dst, bt);
-      prepare_bconv(bt, dst_pos, sp.down);
+      if ((rc = prepare_bconv(ctx, bt, dst_pos, sp.down))) return rc;
     }
   }
   auto ins = ctx->shard_plans.emplace(key, sp);
@@ -657,7 +660,7 @@ extern "C" int hml_keyswitch_shard_begin(hml_ctx *ctx, uint32_t L, uint32_t rank
     l.in = (const u64 *)d_own; l.out = (u64 *)gather1 + (size_t)rank * sp->gq * N;
     l.in_limb_stride = l.out_limb_stride = N; l.n_limbs = nq; l.n_polys = 1; l.post_scale = sp->scale1;
     launch_ntt_inverse(ctx->tabs, ctx->p.logN, sp->q_lm, l, (cudaStream_t)stream);
-    ctx->exec.intt_limbs += nq; ctx->exec.kernel_launches += ctx->p.logN <= 12 ? 1 : 2;
+    ctx->exec.intt_limbs += nq; ctx->exec.kernel_launches += ctx->p.logN <= NTT_SMALL_LOG ? 1 : 2;
   }
   return check_launch(ctx, "keyswitch shard begin");
 }
@@ -674,12 +677,12 @@ extern "C" int hml_keyswitch_shard_mid(hml_ctx *ctx, uint32_t L, uint32_t rank, 
   const Params &p = ctx->p;
   const size_t N = p.N;
   const uint32_t nq = sp->own_q.size(), np = sp->own_p.size(), ne = nq + np, beta = sp->beta;
-  const int logN = p.logN, npass = logN <= 12 ? 1 : 2;
+  const int logN = p.logN, npass = logN <= NTT_SMALL_LOG ? 1 : 2;
   cudaStream_t s = (cudaStream_t)stream;
   u64 *ext = ctx->ws, *acc = ext + (size_t)beta * ne * N;
   if (ne == 0) return HML_OK;
   for (uint32_t j = 0; j < beta; ++j) {
-    if (sp->up[j].chunks.empty()) continue;
+    if (sp->up[j].empty()) continue;
     BConvArgs a{};
     a.in = (const u64 *)gather1; a.out = ext + (size_t)j * ne * N; a.step1 = nullptr; a.N = N; a.n_batches = 1;
     run_bconv(ctx, sp->up[j], sp->up_src[j], a, s);
@@ -726,7 +729,7 @@ extern "C" int hml_keyswitch_shard_end(hml_ctx *ctx, uint32_t L, uint32_t rank, 
   const Params &p = ctx->p;
   const size_t N = p.N;
   const uint32_t nq = sp->own_q.size(), np = sp->own_p.size(), ne = nq + np, beta = sp->beta;
-  const int logN = p.logN, npass = logN <= 12 ? 1 : 2;
+  const int logN = p.logN, npass = logN <= NTT_SMALL_LOG ? 1 : 2;
   cudaStream_t s = (cudaStream_t)stream;
   if (nq == 0) return HML_OK;
   u64 *ext = ctx->ws, *acc = ext + (size_t)beta * ne * N, *vb = acc + 2 * (size_t)ne * N;
@@ -765,7 +768,7 @@ static int rescale_run(hml_ctx *ctx, uint32_t L, const u64 *in, long long in_pol
   int rc = get_level(ctx, L, &lc);
   if (rc) return rc;
   const size_t N = p.N;
-  const int logN = p.logN, npass = logN <= 12 ? 1 : 2;
+  const int logN = p.logN, npass = logN <= NTT_SMALL_LOG ? 1 : 2;
   u64 *rb = ws, *rh = ws + (size_t)n_polys * N;  // rb [n_polys][N], rh [n_polys][L-1][N]
   {  // INTT of the dropped limb (reference :766-805)
     LimbMap lm; clear_map(lm);

@@ -14,14 +14,13 @@
 
 namespace hml {
 
-struct HostBConvChunk {
-  int first = 0, count = 0;   // destination limbs [first, first + count)
-  BConvMatrix mat;
-  LimbMap dst_lm;
-};
+// A base conversion prepared for launch: the 12-bit-split matrix in device memory (zero-padded to whole k-steps and
+// target blocks, see ewe.cuh) and the destination limb map.
 struct HostBConv {
   int n_src = 0, n_dst = 0;
-  std::vector<HostBConvChunk> chunks;
+  double *d_mat = nullptr;   // [bconv_pad_src(n_src)][bconv_pad_dst(n_dst)][3]
+  LimbMap dst_lm;
+  bool empty() const { return n_dst == 0; }
 };
 
 // Per-level constants of the key-switch / rescale pipeline (SURVEY.md Appendix A "Constant tables").
@@ -73,7 +72,7 @@ struct hml_ctx {
   hml::CfgFile cfg;
   bool has_cfg = false;
 
-  double2 *tw_fwd = nullptr, *tw_inv = nullptr;
+  double *tw_fwd = nullptr, *tw_inv = nullptr, *tw_fwd_rows = nullptr, *tw_inv_rows = nullptr;
   hml::ModConst *mc = nullptr;
   hml::NttTables tabs{};
 

@@ -1,4 +1,4 @@
-// See ewe.cuh.  All kernels are streaming (HBM-bound) except base conversion (FP64-pipe bound).
+// See ewe.cuh.  All kernels are streaming (HBM-bound) except base conversion (FP64 tensor-core path, pipe bound).
 #include "ewe.cuh"
 
 namespace hml {
@@ -184,127 +184,131 @@ void launch_automorph(int logN, int n_limbs, const u64 *in, u64 *out, u64 g, cud
 }
 
 // ------------------------------------------------------------------------------------------------ base conversion
-// One CTA = 256 coefficients (two per thread) x OT output limbs.  The inner loop is 3 DFMA per modular MAC
-// (12-bit-split matrix, exact double sums):
-//   * input words come through a 4-deep register ring (loads for sources i+1..i+4 in flight while source i is
-//     accumulated);
-//   * the matrix operand does not go through the LSU: the whole [n_src][n_dst][3] matrix travels in
-//     kernel-parameter space (constant bank, __grid_constant__, <= 30 KB), so each matrix word is a constant
-//     load feeding DFMA.  (A shared-memory broadcast costs one LSU wavefront per load and made an earlier
-//     version LSU-bound — profiles/README.md.)
-//   * the epilogue is branch-free with its moduli in shared memory, so the 2*OT dependent reduction chains
-//     interleave instead of running one after another behind a global load each.
-// OT is chosen by the launcher so that n_dst splits without padding (35 = 5x7, 45 = 9x5, 50 = 10x5).
-constexpr int BC_THREADS = 128;
-constexpr int BC_RING = 4;
+// out[t][m] = sum_i y_i[m] * H[i][t]  (mod q_t)  is a matrix product [coefficients x sources] x [sources x targets]
+// with exact integer entries.  It runs on the FP64 tensor-core path (DMMA m8n8k4): H is split into three 12-bit pieces
+// so that every product (36 + 12 bits) and every 16-term partial sum (<= 52 bits) is an exactly representable double,
+// whatever the accumulation order inside the MMA.  Measured on B200 (profiles/microbench/dmma_bench.cu): DMMA reaches
+// the FP64 pipe's full 18.5 T FMA/s with ONE instruction per 256 FMAs, and integer / load instructions issue in its
+// shadow, whereas a DFMA holds the issue port for two cycles per 32 FMAs — the earlier DFMA kernel spent 25% of its
+// issue slots on matrix-operand loads alone.
+//   CTA  = `tm` coefficients (256, or 64 when there are many sources) x all targets; the sources of the tile are
+//          staged once in shared memory as doubles, pitch tm + 4 (conflict-free fragment reads), zero rows as padding
+//   warp = one block of 8 targets: B fragments (sources x 8 targets x 3 pieces) live in registers for <= 16 sources
+//          (KS = number of 4-source k-steps), else they are re-read from the L1-resident matrix and the accumulators are
+//          folded mod q_t every 16 sources
+//   lane = coefficient lane/4 of each 8-coefficient m-tile, targets 2*(lane%4), +1 of the block: the three pieces of a
+//          target meet in one lane, so the epilogue (Horner over the pieces, 3 reductions) needs no exchange
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
 
-template <int OT, bool STEP1>
-__global__ void __launch_bounds__(BC_THREADS, 4) k_bconv(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BConvArgs a,
-                                                         const __grid_constant__ BConvMatrix mat) {
-  __shared__ double qs[OT], qinvs[OT];
-  __shared__ u64 qis[OT];
-  const int t0 = blockIdx.y * OT;
-  const int nt = min(OT, a.n_dst - t0);
-  if (threadIdx.x < OT) {
-    const ModConst m = mc[dst_lm.mod[min(t0 + (int)threadIdx.x, a.n_dst - 1)]];  // a padded tail repeats the last modulus
-    qs[threadIdx.x] = m.q; qinvs[threadIdx.x] = m.qinv; qis[threadIdx.x] = m.qi;
-  }
-  const int i2 = min(blockIdx.x * BC_THREADS + threadIdx.x, (unsigned)(a.N / 2 - 1));
-  const bool live = blockIdx.x * BC_THREADS + threadIdx.x < (unsigned)(a.N / 2);
-  const size_t n2 = a.N / 2;
-  const ulonglong2 *in = reinterpret_cast<const ulonglong2 *>(a.in + (size_t)blockIdx.z * a.in_batch_stride) + i2;
-  u64 *out = a.out + (size_t)blockIdx.z * a.out_batch_stride;
-  ulonglong2 ring[BC_RING];
-#pragma unroll
-  for (int k = 0; k < BC_RING; ++k) ring[k] = __ldg(in + (size_t)src_lm.pos[min(k, a.n_src - 1)] * n2);
-  __syncthreads();
-  double acc[OT][3][2];
-#pragma unroll
-  for (int o = 0; o < OT; ++o)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) acc[o][k][0] = acc[o][k][1] = 0.0;
-  for (int i0 = 0; i0 < a.n_src; i0 += BC_RING) {
-#pragma unroll
-    for (int k = 0; k < BC_RING; ++k) {
-      const int i = i0 + k;
+template <int KS, bool STEP1>
+__global__ void __launch_bounds__(512) k_bconv_mma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BConvArgs a,
+                                                   const double *__restrict__ mat, int n_src_pad, int n_dst_pad, int tm) {
+  extern __shared__ __align__(16) double ys[];  // [n_src_pad][tm + 4]
+  const int pitch = tm + 4;
+  const int lane = threadIdx.x & 31, tb = threadIdx.x >> 5;
+  const size_t m_base = (size_t)blockIdx.x * tm;
+  const u64 *in = a.in + (size_t)blockIdx.y * a.in_batch_stride;
+  u64 *out = a.out + (size_t)blockIdx.y * a.out_batch_stride;
+  {  // stage the tile's sources (step 1 applied here when requested), zero the padding rows
+    const int half = tm >> 1;
+    for (int e = threadIdx.x; e < n_src_pad * half; e += blockDim.x) {
+      const int i = e / half, m2 = e - i * half;
+      double y0 = 0.0, y1 = 0.0;
       if (i < a.n_src) {
-        double y0 = u64_to_f64(ring[k].x), y1 = u64_to_f64(ring[k].y);
-        ring[k] = __ldg(in + (size_t)src_lm.pos[min(i + BC_RING, a.n_src - 1)] * n2);
+        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(in + (size_t)src_lm.pos[i] * a.N + m_base) + m2);
+        y0 = u64_to_f64(v.x); y1 = u64_to_f64(v.y);
         if (STEP1) {
           const ModConst m = mc[src_lm.mod[i]];
           const double2 sc = a.step1[i];
           y0 = canonicalize(mulmod_const(y0, sc.x, sc.y, m.q), m.q);
           y1 = canonicalize(mulmod_const(y1, sc.x, sc.y, m.q), m.q);
         }
-        const int hb = (i * a.n_dst + t0) * 3;  // uniform: matrix row of source i, first output of this tile
+      }
+      *reinterpret_cast<double2 *>(&ys[i * pitch + 2 * m2]) = make_double2(y0, y1);
+    }
+  }
+  __syncthreads();
+  const int kq = lane & 3, rq = lane >> 2;
+  const int t0 = tb * 8 + 2 * kq, t1 = t0 + 1;
+  const bool live0 = t0 < a.n_dst, live1 = t1 < a.n_dst;
+  const ModConst m0 = mc[dst_lm.mod[live0 ? t0 : a.n_dst - 1]], m1 = mc[dst_lm.mod[live1 ? t1 : a.n_dst - 1]];
+  u64 *o0 = out + (size_t)dst_lm.pos[live0 ? t0 : a.n_dst - 1] * a.N + m_base + rq;
+  u64 *o1 = out + (size_t)dst_lm.pos[live1 ? t1 : a.n_dst - 1] * a.N + m_base + rq;
+  const double *bsrc = mat + ((size_t)kq * n_dst_pad + tb * 8 + rq) * 3;  // B[k = lane%4][n = lane/4], k-step stride 4 rows
+  const size_t brow = (size_t)4 * n_dst_pad * 3;
+  double bf[KS > 0 ? KS : 1][3];
+  if constexpr (KS > 0) {
 #pragma unroll
-        for (int o = 0; o < OT; ++o)
+    for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
-          for (int kk = 0; kk < 3; ++kk) {
-            const double hv = mat.h[hb + o * 3 + kk];  // the struct's padding keeps a partial last tile in bounds
-            acc[o][kk][0] = __fma_rn(y0, hv, acc[o][kk][0]);
-            acc[o][kk][1] = __fma_rn(y1, hv, acc[o][kk][1]);
+      for (int p = 0; p < 3; ++p) bf[ks][p] = __ldg(bsrc + ks * brow + p);
+  }
+  const double *yl = ys + kq * pitch + rq;  // A[row = lane/4][col = lane%4]
+  const int n_ks = n_src_pad >> 2;
+#pragma unroll 2
+  for (int mt = 0; mt < (tm >> 3); ++mt) {
+    double acc[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+    if constexpr (KS > 0) {
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const double af = yl[ks * 4 * pitch + mt * 8];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) dmma884(acc[p][0], acc[p][1], af, bf[ks][p]);
+      }
+    } else {
+      for (int ks = 0; ks < n_ks; ++ks) {
+        const double af = yl[ks * 4 * pitch + mt * 8];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) dmma884(acc[p][0], acc[p][1], af, __ldg(bsrc + ks * brow + p));
+        // each term is < 2^36 * 2^12: fold every 16 sources so the exact sums stay below 2^53
+        if ((ks & 3) == 3 && ks + 1 < n_ks) {
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {
+            acc[p][0] = reduce_signed(acc[p][0], m0.q, m0.qinv);
+            acc[p][1] = reduce_signed(acc[p][1], m1.q, m1.qinv);
           }
-        // each term is < 2^36 * 2^12; fold every 16 sources so the exact sums stay below 2^53
-        if ((i & 15) == 15 && i + 1 < a.n_src) {
-#pragma unroll
-          for (int o = 0; o < OT; ++o)
-#pragma unroll
-            for (int kk = 0; kk < 3; ++kk) {
-              acc[o][kk][0] = reduce_signed(acc[o][kk][0], qs[o], qinvs[o]);
-              acc[o][kk][1] = reduce_signed(acc[o][kk][1], qs[o], qinvs[o]);
-            }
         }
       }
     }
-  }
-  // branch-free epilogue: all 2*OT reduction chains are independent and interleave; only the store is predicated
-  u64 r[OT][2];
-#pragma unroll
-  for (int o = 0; o < OT; ++o) {
-    const double q = qs[o], qinv = qinvs[o];
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      // value = S2*2^24 + S1*2^12 + S0 (mod q), folded top-down; every intermediate is an exact integer < 2^53
-      double v = reduce_signed(acc[o][2][c], q, qinv);
-      v = reduce_signed(__fma_rn(v, 4096.0, acc[o][1][c]), q, qinv);
-      v = reduce_signed(__fma_rn(v, 4096.0, acc[o][0][c]), q, qinv);
-      r[o][c] = f64_to_canonical(v, qis[o]);
-    }
-  }
-  if (!live) return;
-#pragma unroll
-  for (int o = 0; o < OT; ++o) {
-    if (o < nt) {
-      st2(out, (size_t)dst_lm.pos[t0 + o] * n2 + i2, r[o][0], r[o][1]);
-    }
+    // value = S2*2^24 + S1*2^12 + S0 (mod q), folded top-down; every intermediate is an exact integer < 2^53
+    double v0 = reduce_signed(acc[2][0], m0.q, m0.qinv), v1 = reduce_signed(acc[2][1], m1.q, m1.qinv);
+    v0 = reduce_signed(__fma_rn(v0, 4096.0, acc[1][0]), m0.q, m0.qinv);
+    v1 = reduce_signed(__fma_rn(v1, 4096.0, acc[1][1]), m1.q, m1.qinv);
+    v0 = reduce_signed(__fma_rn(v0, 4096.0, acc[0][0]), m0.q, m0.qinv);
+    v1 = reduce_signed(__fma_rn(v1, 4096.0, acc[0][1]), m1.q, m1.qinv);
+    if (live0) o0[mt * 8] = f64_to_canonical(v0, m0.qi);
+    if (live1) o1[mt * 8] = f64_to_canonical(v1, m1.qi);
   }
 }
 
-int bconv_tile_height(int n_dst) {
-  // the tile height that wastes the fewest padded output limbs (ties -> the taller tile)
-  int best = 7, waste = 1 << 30;
-  for (int ot : {7, 6, 5}) {
-    const int w = (n_dst + ot - 1) / ot * ot - n_dst;
-    if (w < waste) { waste = w; best = ot; }
-  }
-  return best;
+template <int KS>
+static void launch_bconv_t(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const double *mat,
+                           int n_src_pad, int n_dst_pad, int tm, cudaStream_t s) {
+  const dim3 grid(a.N / tm, a.n_batches);
+  const int threads = 32 * (n_dst_pad / 8);
+  const size_t smem = (size_t)n_src_pad * (tm + 4) * sizeof(double);
+  static bool once = [] {
+    cudaFuncSetAttribute(k_bconv_mma<KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 68 * 8);
+    cudaFuncSetAttribute(k_bconv_mma<KS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 68 * 8);
+    return true;
+  }();
+  (void)once;
+  if (a.step1) k_bconv_mma<KS, true><<<grid, threads, smem, s>>>(mc, src_lm, dst_lm, a, mat, n_src_pad, n_dst_pad, tm);
+  else k_bconv_mma<KS, false><<<grid, threads, smem, s>>>(mc, src_lm, dst_lm, a, mat, n_src_pad, n_dst_pad, tm);
 }
 
-template <int OT>
-static void launch_bconv_t(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a,
-                           const BConvMatrix &mat, cudaStream_t s) {
-  const dim3 grid((a.N / 2 + BC_THREADS - 1) / BC_THREADS, (a.n_dst + OT - 1) / OT, a.n_batches);
-  if (a.step1) k_bconv<OT, true><<<grid, BC_THREADS, 0, s>>>(mc, src_lm, dst_lm, a, mat);
-  else k_bconv<OT, false><<<grid, BC_THREADS, 0, s>>>(mc, src_lm, dst_lm, a, mat);
-}
-
-void launch_bconv(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const BConvMatrix &mat,
-                  cudaStream_t s) {
-  switch (bconv_tile_height(a.n_dst)) {
-    case 7: launch_bconv_t<7>(mc, src_lm, dst_lm, a, mat, s); break;
-    case 6: launch_bconv_t<6>(mc, src_lm, dst_lm, a, mat, s); break;
-    default: launch_bconv_t<5>(mc, src_lm, dst_lm, a, mat, s); break;
+void launch_bconv(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const double *mat, cudaStream_t s) {
+  const int n_src_pad = bconv_pad_src(a.n_src), n_dst_pad = bconv_pad_dst(a.n_dst);
+  int tm = n_src_pad <= 16 ? 256 : 64;
+  while (tm > a.N) tm >>= 1;  // tiny rings (tests): N >= 8
+  switch (n_src_pad <= 16 ? n_src_pad / 4 : 0) {
+    case 1: launch_bconv_t<1>(mc, src_lm, dst_lm, a, mat, n_src_pad, n_dst_pad, tm, s); break;
+    case 2: launch_bconv_t<2>(mc, src_lm, dst_lm, a, mat, n_src_pad, n_dst_pad, tm, s); break;
+    case 3: launch_bconv_t<3>(mc, src_lm, dst_lm, a, mat, n_src_pad, n_dst_pad, tm, s); break;
+    case 4: launch_bconv_t<4>(mc, src_lm, dst_lm, a, mat, n_src_pad, n_dst_pad, tm, s); break;
+    default: launch_bconv_t<0>(mc, src_lm, dst_lm, a, mat, n_src_pad, n_dst_pad, tm, s); break;
   }
 }
 

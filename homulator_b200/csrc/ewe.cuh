@@ -50,23 +50,19 @@ void launch_automorph(int logN, int n_limbs, const u64 *in, u64 *out, u64 g, cud
 // Fast base conversion.  in [n_src][N] coefficient form.  If step1 != nullptr the per-source scaling
 // y_i = in_i * hat_inv_i mod s_i is applied inside (step1[i] = (hat_inv_i, RN(hat_inv_i / s_i)));
 // otherwise `in` must already hold y_i (the fused pipeline folds it into the preceding INTT).
-// The matrix (D/s_i mod t), split into three 12-bit pieces as doubles, is passed BY VALUE in kernel-parameter
-// space: h[(i * n_dst + t) * 3 + k].  One launch handles n_src * n_dst <= BCONV_MAX_PAIRS (callers chunk n_dst).
-constexpr int BCONV_MAX_PAIRS = 1200;
-struct BConvMatrix {
-  double h[(BCONV_MAX_PAIRS + 8) * 3];  // + one padded tile row so a partial last tile reads zeros
-};
+// The matrix (D/s_i mod t), split into three 12-bit pieces as doubles, lives in device memory, zero-padded:
+//   mat[(i * n_dst_pad + t) * 3 + k],  i < n_src_pad = bconv_pad_src(n_src),  t < n_dst_pad = bconv_pad_dst(n_dst)
 struct BConvArgs {
   const u64 *in;
   u64 *out;
-  long long in_batch_stride, out_batch_stride;  // grid.z batches (e.g. the two key-switch accumulators)
+  long long in_batch_stride, out_batch_stride;  // grid.y batches (e.g. the two key-switch accumulators)
   const double2 *step1;   // [n_src] or null
   int N, n_src, n_dst, n_batches;
 };
+inline int bconv_pad_src(int n_src) { return (n_src + 3) & ~3; }   // k-steps of 4 sources
+inline int bconv_pad_dst(int n_dst) { return (n_dst + 7) & ~7; }   // target blocks of 8 (one warp each); n_dst <= 128
 // Source limb i is read at in + src_lm.pos[i] * N (modulus src_lm.mod[i], used by step 1 only); output limb t is
-// written at out + dst_lm.pos[t] * N with modulus dst_lm.mod[t].
-int bconv_tile_height(int n_dst);
-void launch_bconv(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const BConvMatrix &mat,
-                  cudaStream_t s);
+// written at out + dst_lm.pos[t] * N with modulus dst_lm.mod[t].  N >= 8.
+void launch_bconv(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const double *mat, cudaStream_t s);
 
 }  // namespace hml

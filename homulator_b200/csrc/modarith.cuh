@@ -60,18 +60,20 @@ __device__ __forceinline__ double mulmod_var(double a, double b, double q, doubl
   return __dadd_rn(r, l);
 }
 
-// ---- Cooley-Tukey (forward) butterfly: (x, y) -> (x + y*w, x - y*w), growth +0.51q per stage
-__device__ __forceinline__ void ct_butterfly(double &x, double &y, double w, double wq, double q) {
-  double t = mulmod_const(y, w, wq, q);
+// ---- Cooley-Tukey (forward) butterfly: (x, y) -> (x + y*w, x - y*w), growth +0.51q per stage.  The twiddle is a
+// single double; the quotient estimate comes from h * (1/q) (mulmod_var), so tables and shared memory hold 8 bytes
+// per twiddle instead of 16.
+__device__ __forceinline__ void ct_butterfly(double &x, double &y, double w, double q, double qinv) {
+  double t = mulmod_var(y, w, q, qinv);
   double X = x;
   x = __dadd_rn(X, t);
   y = __dsub_rn(X, t);
 }
 // ---- Gentleman-Sande (inverse) butterfly: (x, y) -> (x + y, (x - y)*w); x doubles, y resets to <= 0.51q
-__device__ __forceinline__ void gs_butterfly(double &x, double &y, double w, double wq, double q) {
+__device__ __forceinline__ void gs_butterfly(double &x, double &y, double w, double q, double qinv) {
   double d = __dsub_rn(x, y);
   x = __dadd_rn(x, y);
-  y = mulmod_const(d, w, wq, q);
+  y = mulmod_var(d, w, q, qinv);
 }
 
 // per-modulus constants kept in device memory

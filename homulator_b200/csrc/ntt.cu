@@ -1,10 +1,13 @@
 // See ntt.cuh for the algorithm.  sm_100a only.
 #include "ntt.cuh"
 
+#include <cstring>
+
 namespace hml {
 
-// ---- asynchronous bulk copy (TMA engine, no tensor map) global -> shared, completion on an mbarrier
+// ---- asynchronous copies global -> shared
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+// bulk copy (TMA engine, no tensor map), completion on an mbarrier
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -30,424 +33,369 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
       "r"(parity)
       : "memory");
 }
+// 16-byte per-thread asynchronous copy (LDGSTS), L2 only
+__device__ __forceinline__ void cp_async16(unsigned smem_dst, const void *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
 
 // ------------------------------------------------------------------------------------------------
-// A "round" = S consecutive radix-2 stages (S <= 3) of a length-2^LOGR sub-NTT, starting at stage ST,
-// executed on 8 register-resident points per thread.  Thread unit u in [0, 2^LOGR / 8) owns 8/2^S
-// butterfly groups of 2^S points each; register r = (group gi, point kk).
+// The 16-point network.  Level T (0..3) pairs registers D = 8 >> T apart; the 2^T butterfly groups of the
+// level use w[0 .. 2^T).  Four levels = four radix-2 stages on 16 register-resident points; with the
+// registers holding points  base + stride * j  the levels are the stages of distance 8, 4, 2, 1 strides.
 // ------------------------------------------------------------------------------------------------
-template <int LOGR, int ST, int S>
-struct Round {
-  static constexpr int TL = (1 << LOGR) >> (ST + S);  // smallest butterfly distance in the round
-  static constexpr int G = 8 >> S;                    // groups per thread
-  __device__ static __forceinline__ int point(int u, int r) {
-    const int gi = r >> S, kk = r & ((1 << S) - 1);
-    const int g = u * G + gi;
-    const int hi = g / TL, lo = g % TL;
-    return hi * (TL << S) + kk * TL + lo;
-  }
-};
-
-// twiddle index of the butterfly whose lower point is p, at stage i of a sub-NTT whose twiddle block
-// starts at tw_base (1 for the column pass; R1 + row for the row pass): (tw_base << i) + p / (2t)
-// One stage of a round: JS = position in the 3-stage register pattern (distance 4 >> JS).
-template <int LOGR, int ST, int S, int JS, bool INV, bool TW_SMEM>
-__device__ __forceinline__ void round_stage(double (&a)[8], int u, const double2 *__restrict__ tw, unsigned tw_base, double q) {
-  using RD = Round<LOGR, ST, S>;
-  constexpr int h = 4 >> JS, i = ST + JS - (3 - S);
+template <int T>
+__device__ __forceinline__ void ct_level(double (&a)[16], const double (&w)[8], double q, double qinv) {
+  constexpr int D = 8 >> T;
 #pragma unroll
-  for (int sg = 0; sg < (1 << JS); ++sg) {
-    const int r0 = sg << (3 - JS);
-    const int p0 = RD::point(u, r0);
-    const unsigned ti = (tw_base << i) + (p0 >> (LOGR - i));
-    const double2 w = TW_SMEM ? tw[ti] : __ldg(&tw[ti]);
+  for (int g = 0; g < (1 << T); ++g)
 #pragma unroll
-    for (int o = 0; o < h; ++o) {
-      if constexpr (INV) gs_butterfly(a[r0 + o], a[r0 + o + h], w.x, w.y, q);
-      else ct_butterfly(a[r0 + o], a[r0 + o + h], w.x, w.y, q);
+    for (int o = 0; o < D; ++o) ct_butterfly(a[g * 2 * D + o], a[g * 2 * D + o + D], w[g], q, qinv);
+}
+template <int T>
+__device__ __forceinline__ void gs_level(double (&a)[16], const double (&w)[8], double q, double qinv) {
+  constexpr int D = 8 >> T;
+#pragma unroll
+  for (int g = 0; g < (1 << T); ++g)
+#pragma unroll
+    for (int o = 0; o < D; ++o) gs_butterfly(a[g * 2 * D + o], a[g * 2 * D + o + D], w[g], q, qinv);
+}
+// CNT contiguous twiddles from shared memory (16-byte aligned when CNT >= 2)
+template <int CNT>
+__device__ __forceinline__ void lds_run(double (&w)[8], const double *p) {
+  if constexpr (CNT == 1) {
+    w[0] = p[0];
+  } else {
+#pragma unroll
+    for (int k = 0; k < CNT / 2; ++k) {
+      const double2 v = reinterpret_cast<const double2 *>(p)[k];
+      w[2 * k] = v.x; w[2 * k + 1] = v.y;
     }
   }
 }
 
-template <int LOGR, int ST, int S, bool TW_SMEM = false>
-__device__ __forceinline__ void ct_round(double (&a)[8], int u, const double2 *__restrict__ tw, unsigned tw_base, double q) {
-  if constexpr (S >= 3) round_stage<LOGR, ST, S, 0, false, TW_SMEM>(a, u, tw, tw_base, q);
-  if constexpr (S >= 2) round_stage<LOGR, ST, S, 1, false, TW_SMEM>(a, u, tw, tw_base, q);
-  round_stage<LOGR, ST, S, 2, false, TW_SMEM>(a, u, tw, tw_base, q);
-}
-
-template <int LOGR, int ST, int S, bool TW_SMEM = false>
-__device__ __forceinline__ void gs_round(double (&a)[8], int u, const double2 *__restrict__ tw, unsigned tw_base, double q) {
-  round_stage<LOGR, ST, S, 2, true, TW_SMEM>(a, u, tw, tw_base, q);
-  if constexpr (S >= 2) round_stage<LOGR, ST, S, 1, true, TW_SMEM>(a, u, tw, tw_base, q);
-  if constexpr (S >= 3) round_stage<LOGR, ST, S, 0, true, TW_SMEM>(a, u, tw, tw_base, q);
-}
-
-// round split of a length-2^LOGR sub-NTT: S1 = 3, then S2, S3 (S3 may be 0)
-template <int LOGR> struct Split {
-  static constexpr int S1 = 3;
-  static constexpr int S2 = (LOGR <= 6) ? (LOGR - 3) : (LOGR - 3 + 1) / 2;
-  static constexpr int S3 = LOGR - 3 - S2;
+// ================================================================================ column passes
+// Tile = C adjacent columns x all R1 rows; thread (c, u) = (tid % C, tid / C), U = R1 / 16 row groups.
+//   round A: rows u + U*j   (shared-memory word tid + 256*j): stages 0..3
+//   round B: rows 16*u + j  : stages 4..LOGR1-1 (the last LOGR1-4 levels of the network)
+// Work item = (limb-poly-batch y, tile); a CTA walks items blockIdx.x, + gridDim.x, ... with the next item's tile and
+// its R1 twiddles already in flight (two stages of 32 KB + 2 KB).
+template <int LOGR1>
+struct ColCfg {
+  static constexpr int R1 = 1 << LOGR1, C = NTT_TILE / R1, SKIP = 8 - LOGR1, TILES = (1 << NTT_ROW_LOG) / C;
+  static constexpr int STAGE_BYTES = NTT_TILE * 8 + 2048 + 64;  // tile | R1 twiddles | ModConst (48 B) | post-scale (16 B)
 };
 
-struct LimbCtx {
+struct ColWork {
   const u64 *in;
   u64 *out;
-  const double2 *tw;
-  double q, qinv;
-  u64 qi;
-  int limb;
+  int mi, limb, tile;
 };
 
-__device__ __forceinline__ LimbCtx limb_ctx(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, bool inverse,
-                                            int limb, int poly, int batch = 0) {
-  LimbCtx c;
-  c.limb = limb;
-  const int mi = lm.mod[c.limb];
+template <int LOGR1>
+__device__ __forceinline__ bool col_decode(int wi, const LimbMap &lm, const NttLaunch &l, bool in_is_out, ColWork &w) {
+  using K = ColCfg<LOGR1>;
+  const int y = wi / K::TILES, tile = wi % K::TILES;
+  const int limb = y % l.n_limbs, poly = (y / l.n_limbs) % l.n_polys, batch = y / (l.n_limbs * l.n_polys);
+  if (poly == lm.skip[limb]) return false;
+  const long long slot = lm.pos[limb];
+  w.out = l.out + (long long)batch * l.out_batch_stride + (long long)poly * l.out_poly_stride + slot * l.out_limb_stride + tile * K::C;
+  w.in = in_is_out ? w.out
+                   : l.in + (long long)batch * l.in_batch_stride + (long long)poly * l.in_poly_stride + slot * l.in_limb_stride + tile * K::C;
+  w.mi = lm.mod[limb];
+  w.limb = limb;
+  w.tile = tile;
+  return true;
+}
+
+template <int LOGR1>
+__device__ __forceinline__ void col_issue(const ColWork &w, const double *tw_table, const ModConst *mc, const double2 *post_scale, int logN,
+                                          unsigned stage_smem) {
+  using K = ColCfg<LOGR1>;
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int qd = tid + 256 * k, row = qd / (K::C / 2), cc = qd % (K::C / 2);
+    cp_async16(stage_smem + qd * 16, w.in + (size_t)row * (1 << NTT_ROW_LOG) + 2 * cc);
+  }
+  if (tid < K::R1 / 2) cp_async16(stage_smem + NTT_TILE * 8 + tid * 16, tw_table + ((size_t)w.mi << logN) + 2 * tid);
+  // the per-modulus constants ride along, so the transform never waits on a dependent global load
+  else if (tid < K::R1 / 2 + 3) cp_async16(stage_smem + NTT_TILE * 8 + 2048 + (tid - K::R1 / 2) * 16, reinterpret_cast<const char *>(mc + w.mi) + (tid - K::R1 / 2) * 16);
+  else if (tid == K::R1 / 2 + 3 && post_scale) cp_async16(stage_smem + NTT_TILE * 8 + 2048 + 48, post_scale + w.limb);
+}
+
+template <int LOGR1>
+__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_fwd_cols(NttTables t, int logN, LimbMap lm, NttLaunch l, int total) {
+  using K = ColCfg<LOGR1>;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int tid = threadIdx.x, c = tid % K::C, u = tid / K::C;
+  const unsigned smem0 = smem_u32(smem);
+  ColWork cur, nxt;
+  int wi = blockIdx.x;
+  while (wi < total && !col_decode<LOGR1>(wi, lm, l, false, cur)) wi += gridDim.x;
+  if (wi < total) col_issue<LOGR1>(cur, t.fwd, t.mc, nullptr, logN, smem0);
+  cp_async_commit();
+  for (int it = 0; wi < total; ++it) {
+    int nwi = wi + gridDim.x;
+    while (nwi < total && !col_decode<LOGR1>(nwi, lm, l, false, nxt)) nwi += gridDim.x;
+    cp_async_wait<0>();
+    __syncthreads();  // tile `it` has landed for every thread; everybody is done with the other stage
+    if (nwi < total) col_issue<LOGR1>(nxt, t.fwd, t.mc, nullptr, logN, smem0 + ((it + 1) & 1) * K::STAGE_BYTES);
+    cp_async_commit();
+    double *data = reinterpret_cast<double *>(smem + (it & 1) * K::STAGE_BYTES);
+    const double *tw = data + NTT_TILE;
+    const ModConst &mc = *reinterpret_cast<const ModConst *>(tw + 256);
+    const double q = mc.q, qinv = mc.qinv;
+    double a[16], w[8];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = u64_to_f64(reinterpret_cast<const u64 *>(data)[tid + 256 * j]);
+    // A constant added to coefficient 0 appears unchanged in every evaluation slot: subtracting h = (q-1)/2 here makes
+    // the row pass's centred reduction land in [-h, h] = [0, q-1] - h, so its canonicalisation is one add (no sign fix).
+    if (cur.tile == 0 && tid == 0) a[0] -= (q - 1.0) * 0.5;
+    lds_run<1>(w, tw + 1); ct_level<0>(a, w, q, qinv);
+    lds_run<2>(w, tw + 2); ct_level<1>(a, w, q, qinv);
+    lds_run<4>(w, tw + 4); ct_level<2>(a, w, q, qinv);
+    lds_run<8>(w, tw + 8); ct_level<3>(a, w, q, qinv);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) data[tid + 256 * j] = a[j];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = data[(16 * u + j) * K::C + c];
+    if constexpr (K::SKIP <= 0) { lds_run<1>(w, tw + (1 << (LOGR1 - 4)) + u); ct_level<0>(a, w, q, qinv); }
+    if constexpr (K::SKIP <= 1) { lds_run<2>(w, tw + (1 << (LOGR1 - 3)) + 2 * u); ct_level<1>(a, w, q, qinv); }
+    if constexpr (K::SKIP <= 2) { lds_run<4>(w, tw + (1 << (LOGR1 - 2)) + 4 * u); ct_level<2>(a, w, q, qinv); }
+    lds_run<8>(w, tw + (1 << (LOGR1 - 1)) + 8 * u); ct_level<3>(a, w, q, qinv);
+    double *outd = reinterpret_cast<double *>(cur.out) + c;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) outd[(size_t)(16 * u + j) << NTT_ROW_LOG] = a[j];
+    wi = nwi; cur = nxt;
+  }
+}
+
+// inverse, second pass: raw doubles in `out` -> canonical words, post-scale folded into the N^-1 multiply
+template <int LOGR1>
+__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_inv_cols(NttTables t, int logN, LimbMap lm, NttLaunch l, int total) {
+  using K = ColCfg<LOGR1>;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int tid = threadIdx.x, c = tid % K::C, u = tid / K::C;
+  const unsigned smem0 = smem_u32(smem);
+  ColWork cur, nxt;
+  int wi = blockIdx.x;
+  while (wi < total && !col_decode<LOGR1>(wi, lm, l, true, cur)) wi += gridDim.x;
+  if (wi < total) col_issue<LOGR1>(cur, t.inv, t.mc, l.post_scale, logN, smem0);
+  cp_async_commit();
+  for (int it = 0; wi < total; ++it) {
+    int nwi = wi + gridDim.x;
+    while (nwi < total && !col_decode<LOGR1>(nwi, lm, l, true, nxt)) nwi += gridDim.x;
+    cp_async_wait<0>();
+    __syncthreads();
+    if (nwi < total) col_issue<LOGR1>(nxt, t.inv, t.mc, l.post_scale, logN, smem0 + ((it + 1) & 1) * K::STAGE_BYTES);
+    cp_async_commit();
+    double *data = reinterpret_cast<double *>(smem + (it & 1) * K::STAGE_BYTES);
+    const double *tw = data + NTT_TILE;
+    const ModConst &mc = *reinterpret_cast<const ModConst *>(tw + 256);
+    const double q = mc.q, qinv = mc.qinv;
+    double a[16], w[8];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = data[(16 * u + j) * K::C + c];
+    lds_run<8>(w, tw + (1 << (LOGR1 - 1)) + 8 * u); gs_level<3>(a, w, q, qinv);
+    if constexpr (K::SKIP <= 2) { lds_run<4>(w, tw + (1 << (LOGR1 - 2)) + 4 * u); gs_level<2>(a, w, q, qinv); }
+    if constexpr (K::SKIP <= 1) { lds_run<2>(w, tw + (1 << (LOGR1 - 3)) + 2 * u); gs_level<1>(a, w, q, qinv); }
+    if constexpr (K::SKIP <= 0) { lds_run<1>(w, tw + (1 << (LOGR1 - 4)) + u); gs_level<0>(a, w, q, qinv); }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) data[(16 * u + j) * K::C + c] = a[j];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = data[tid + 256 * j];
+    lds_run<8>(w, tw + 8); gs_level<3>(a, w, q, qinv);
+    lds_run<4>(w, tw + 4); gs_level<2>(a, w, q, qinv);
+    lds_run<2>(w, tw + 2); gs_level<1>(a, w, q, qinv);
+    lds_run<1>(w, tw + 1); gs_level<0>(a, w, q, qinv);
+    double2 sc;
+    if (l.post_scale) sc = *reinterpret_cast<const double2 *>(tw + 256 + 6);
+    else sc = make_double2(mc.ninv, mc.ninv_q);
+    const u64 qi = mc.qi;
+    u64 *outp = cur.out + tid % K::C;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      outp[(size_t)(u + (K::R1 / 16) * j) << NTT_ROW_LOG] = f64_to_canonical(mulmod_const(a[j], sc.x, sc.y, q), qi);
+    wi = nwi; cur = nxt;
+  }
+}
+
+// ================================================================================ row passes
+// A CTA owns 16 consecutive 256-point rows (32 KB contiguous) of one limb and walks the items (ciphertext, poly) that
+// share the limb's modulus; warp w owns rows 2w, 2w+1 (one per half-warp), so the whole pipeline is warp-local:
+// no block barrier after the twiddle blob has landed.  Thread (rr, l) = (2w + lane/16, lane%16):
+//   round A: points l + 16*j   (stages t = 128 .. 16),   round B: points 16*l + j   (stages t = 8 .. 1)
+// Shared-memory rows are stored with their 16-byte chunks XOR-swizzled inside each 128-byte line
+// (chunk c of line g at position c ^ (g & 7)): round A's 8-byte accesses, round B's per-thread 128-byte runs and the
+// coalesced 16-byte output reads are all conflict-free.
+constexpr int ROW_TILE_BYTES = NTT_TILE * 8;
+constexpr int ROW_SMEM_BYTES = 3 * ROW_TILE_BYTES;  // twiddle blob + two data stages
+
+struct RowAddr {
+  unsigned xa[8];  // round A: byte offset of point l + 16*j is xa[j & 7] + 128 * j
+  unsigned xb[8];  // round B: byte offset of the chunk holding points 16*l + 2k, 2k+1
+  unsigned xc[8];  // output:  byte offset of chunk (line 2k + l/8, chunk l%8)
+};
+__device__ __forceinline__ RowAddr row_addr(int lane, int warp) {
+  RowAddr r;
+  const int l = lane & 15, rr = 2 * warp + (lane >> 4);
+  const unsigned base = rr * 2048;
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    r.xa[m] = base + ((((l >> 1) ^ m) << 4) | ((l & 1) << 3));
+    r.xb[m] = base + l * 128 + ((m ^ (l & 7)) << 4);
+    const int g = 2 * m + (l >> 3);
+    r.xc[m] = base + g * 128 + (((l & 7) ^ (g & 7)) << 4);
+  }
+  return r;
+}
+
+// the warp's two rows (4 KB) of item `src_tile` (pointer to the CTA's first row): 8 chunks per lane
+__device__ __forceinline__ void row_issue(const u64 *src_tile, unsigned stage_smem, int lane, int warp) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int qd = lane + 32 * k, g = (qd >> 3) & 15, cpos = qd & 7;
+    const unsigned dst = stage_smem + (2 * warp + (qd >> 7)) * 2048 + g * 128 + ((cpos ^ (g & 7)) << 4);
+    cp_async16(dst, src_tile + (size_t)warp * 512 + 2 * qd);
+  }
+}
+
+struct RowItems {
+  int n_polys, n_items, skip, step;
+  __device__ __forceinline__ int next(int idx) const {
+    idx += step;
+    while (idx < n_items && (idx % n_polys) == skip) idx += step;
+    return idx;
+  }
+};
+
+template <bool INV>
+__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN, LimbMap lm, NttLaunch l) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long bar;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, limb = blockIdx.y;
+  const int mi = lm.mod[limb];
+  const double *blob = reinterpret_cast<const double *>(smem);
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, ROW_TILE_BYTES);
+    bulk_g2s(smem, (INV ? t.inv_rows : t.fwd_rows) + ((size_t)mi << logN) + (size_t)blockIdx.x * NTT_TILE, ROW_TILE_BYTES, &bar);
+  }
   const ModConst mc = t.mc[mi];
-  c.q = mc.q; c.qinv = mc.qinv; c.qi = mc.qi;
-  c.tw = (inverse ? t.inv : t.fwd) + ((size_t)mi << logN);
-  const long long slot = lm.pos[c.limb];
-  c.in = l.in + (long long)batch * l.in_batch_stride + (long long)poly * l.in_poly_stride + slot * l.in_limb_stride;
-  c.out = l.out + (long long)batch * l.out_batch_stride + (long long)poly * l.out_poly_stride + slot * l.out_limb_stride;
-  return c;
-}
-
-// ================================================================================ forward, columns
-template <int LOGR1>
-__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_fwd_cols(NttTables t, int logN, LimbMap lm, NttLaunch l) {
-  constexpr int R1 = 1 << LOGR1, C = NTT_TILE / R1, R2 = 1 << NTT_ROW_LOG;
-  using SP = Split<LOGR1>;
-  extern __shared__ __align__(16) double sm[];  // [R1][C] tile, then the R1 twiddles of the column pass
-  double2 *stw = reinterpret_cast<double2 *>(sm + NTT_TILE);
-  __shared__ __align__(8) unsigned long long bar;
-  const int limb = blockIdx.y % l.n_limbs, poly = (blockIdx.y / l.n_limbs) % l.n_polys, batch = blockIdx.y / (l.n_limbs * l.n_polys);
-  if (poly == lm.skip[limb]) return;
-  const LimbCtx lc = limb_ctx(t, logN, lm, l, false, limb, poly, batch);
-  if (threadIdx.x == 0) mbar_init(&bar, 1);
-  __syncthreads();
-  if (threadIdx.x == 0) {  // every column shares the same 2^LOGR1 twiddles: one 4 KB bulk copy
-    mbar_expect_tx(&bar, R1 * 16u);
-    bulk_g2s(stw, lc.tw, R1 * 16u, &bar);
-  }
-  const int c = threadIdx.x % C, u = threadIdx.x / C;
-  const int col = blockIdx.x * C + c;
-  double a[8];
-  {
-    using RD = Round<LOGR1, 0, SP::S1>;
+  const double q = mc.q, qinv = mc.qinv;
+  const double hb = 4503599627370496.0 + (q - 1.0) * 0.5;  // 2^52 + h
+  const RowAddr ad = row_addr(lane, warp);
+  const unsigned data0 = smem_u32(smem) + ROW_TILE_BYTES;
+  const long long slot = lm.pos[limb];
+  const size_t tile_off = (size_t)blockIdx.x * NTT_TILE;
+  // forward rows read the raw doubles pass 1 left in `out`; inverse rows read the canonical input words
+  auto src_of = [&](int idx) -> const u64 * {
+    const long long b = idx / l.n_polys, p = idx % l.n_polys;
+    return (INV ? l.in + b * l.in_batch_stride + p * l.in_poly_stride + slot * l.in_limb_stride
+                : l.out + b * l.out_batch_stride + p * l.out_poly_stride + slot * l.out_limb_stride) + tile_off;
+  };
+  auto dst_of = [&](int idx) -> u64 * {
+    const long long b = idx / l.n_polys, p = idx % l.n_polys;
+    return l.out + b * l.out_batch_stride + p * l.out_poly_stride + slot * l.out_limb_stride + tile_off;
+  };
+  RowItems items{l.n_polys, l.n_polys * l.n_batch, lm.skip[limb], (int)gridDim.z};
+  int cur = items.next((int)blockIdx.z - items.step);
+  int nxt = cur < items.n_items ? items.next(cur) : cur;
+  if (cur < items.n_items) row_issue(src_of(cur), data0, lane, warp);
+  cp_async_commit();
+  if (nxt < items.n_items) row_issue(src_of(nxt), data0 + ROW_TILE_BYTES, lane, warp);
+  cp_async_commit();
+  mbar_wait(&bar, 0);
+  const int l16 = lane & 15, rr = 2 * warp + (lane >> 4);
+  const double *tw_a = blob + rr * 16;
+  for (int k = 0; cur < items.n_items; ++k) {
+    const int nn = nxt < items.n_items ? items.next(nxt) : nxt;
+    cp_async_wait<1>();
+    __syncwarp();
+    unsigned char *data = smem + ROW_TILE_BYTES + (k & 1) * ROW_TILE_BYTES;
+    double a[16], w[8];
+    if constexpr (!INV) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) a[r] = u64_to_f64(__ldg(&lc.in[(size_t)RD::point(u, r) * R2 + col]));
-    mbar_wait(&bar, 0);
-    ct_round<LOGR1, 0, SP::S1, true>(a, u, stw, 1u, lc.q);
+      for (int j = 0; j < 16; ++j) a[j] = *reinterpret_cast<const double *>(data + ad.xa[j & 7] + 128 * j);
+      lds_run<1>(w, tw_a + 1); ct_level<0>(a, w, q, qinv);
+      lds_run<2>(w, tw_a + 2); ct_level<1>(a, w, q, qinv);
+      lds_run<4>(w, tw_a + 4); ct_level<2>(a, w, q, qinv);
+      lds_run<8>(w, tw_a + 8); ct_level<3>(a, w, q, qinv);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) sm[RD::point(u, r) * C + c] = a[r];
-  }
-  __syncthreads();
-  double *outd = reinterpret_cast<double *>(lc.out);
-  if constexpr (SP::S3 == 0) {
-    using RD = Round<LOGR1, SP::S1, SP::S2>;
+      for (int j = 0; j < 16; ++j) *reinterpret_cast<double *>(data + ad.xa[j & 7] + 128 * j) = a[j];
+      __syncwarp();
 #pragma unroll
-    for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(u, r) * C + c];
-    ct_round<LOGR1, SP::S1, SP::S2, true>(a, u, stw, 1u, lc.q);
+      for (int m = 0; m < 8; ++m) {
+        const double2 v = *reinterpret_cast<const double2 *>(data + ad.xb[m]);
+        a[2 * m] = v.x; a[2 * m + 1] = v.y;
+      }
+      w[0] = blob[256 + tid]; ct_level<0>(a, w, q, qinv);
+      lds_run<2>(w, blob + 512 + 2 * tid); ct_level<1>(a, w, q, qinv);
+      lds_run<2>(w, blob + 1024 + 2 * tid);
+      { const double2 v = *reinterpret_cast<const double2 *>(blob + 1536 + 2 * tid); w[2] = v.x; w[3] = v.y; }
+      ct_level<2>(a, w, q, qinv);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) outd[(size_t)RD::point(u, r) * R2 + col] = a[r];
-  } else {
-    {
-      using RD = Round<LOGR1, SP::S1, SP::S2>;
+      for (int m = 0; m < 4; ++m) {
+        const double2 v = *reinterpret_cast<const double2 *>(blob + 2048 + 512 * m + 2 * tid);
+        w[2 * m] = v.x; w[2 * m + 1] = v.y;
+      }
+      ct_level<3>(a, w, q, qinv);
+      // canonical words back through the swizzled tile so that the global stores are 16 bytes per lane, 256 B per half-warp
 #pragma unroll
-      for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(u, r) * C + c];
-      ct_round<LOGR1, SP::S1, SP::S2, true>(a, u, stw, 1u, lc.q);
+      for (int m = 0; m < 8; ++m) {
+        // values are (true - h) mod q (bias planted by the column pass): centred remainder + h is canonical
+        const u64 v0 = (u64)__double_as_longlong(reduce_signed(a[2 * m], q, qinv) + hb) & 0x000FFFFFFFFFFFFFull;
+        const u64 v1 = (u64)__double_as_longlong(reduce_signed(a[2 * m + 1], q, qinv) + hb) & 0x000FFFFFFFFFFFFFull;
+        *reinterpret_cast<ulonglong2 *>(data + ad.xb[m]) = make_ulonglong2(v0, v1);
+      }
+      __syncwarp();
+      u64 *outp = dst_of(cur) + (size_t)rr * 256 + (l16 >> 3) * 16 + (l16 & 7) * 2;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) sm[RD::point(u, r) * C + c] = a[r];
-    }
-    __syncthreads();
-    using RD = Round<LOGR1, SP::S1 + SP::S2, SP::S3>;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(u, r) * C + c];
-    ct_round<LOGR1, SP::S1 + SP::S2, SP::S3, true>(a, u, stw, 1u, lc.q);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) outd[(size_t)RD::point(u, r) * R2 + col] = a[r];
-  }
-}
-
-// ================================================================================ row passes: one warp per row
-// The last 8 forward stages (first 8 inverse stages) stay inside a contiguous 256-point row.  A warp owns a row:
-// lane l holds points kk*32 + l (kk = register index), so the three widest stages (t = 128, 64, 32) are
-// register-only and global accesses are 256-byte coalesced.  The five narrow stages (t = 16 .. 1) pair points in
-// different lanes; instead of shared memory each stage swaps HALF of every lane's registers with lane ^ t
-// (register bit 2 <-> lane bit b), after which each lane owns four complete butterflies (registers j, j+4).
-// The swaps are never undone: the logical point of (lane, register) is tracked in closed form
-//   stage b (= 4..0):  kk = (r & 3) | (lane bit 4) << 2,   lane-point bits: P_m = lane bit m-1 (m > b), P_b = r bit 2,
-//                      P_m = lane bit m (m < b)
-// and after the last stage registers (j, j+4) hold the adjacent points p, p+1 with
-//   p = ((j + 4*(lane>>4)) * 32 + 2*(lane & 15)),  i.e. 16-byte stores that tile two 256-byte segments per warp.
-// No shared memory, no block barrier.
-constexpr int ROW_WARPS = 8;  // rows per CTA
-
-__device__ __forceinline__ void swap_half(double (&a)[8], int b, bool upper) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const double send = upper ? a[j] : a[j + 4];
-    const double recv = __shfl_xor_sync(0xffffffffu, send, 1 << b);
-    if (upper) a[j] = recv; else a[j + 4] = recv;
-  }
-}
-
-// twiddle index of pair j at lane-stage b (NTT stage i = 7 - b): (tw_base << i) + kk * 2^(4-b) + ((lane & 15) >> b)
-__device__ __forceinline__ unsigned lane_stage_tw(unsigned tw_base, int b, int j, int lane) {
-  const int kk = j + ((lane >> 4) << 2);
-  return (tw_base << (7 - b)) + (kk << (4 - b)) + ((lane & 15) >> b);
-}
-
-// The twiddles of the CTA's ROW_WARPS consecutive rows form ONE contiguous table segment per stage
-// ((R1 + row0) << i .. (R1 + row0 + 8) << i), so eight bulk copies bring all of them (32 KB) into shared memory
-// while the warps are still waiting for their data rows; every poly of the limb then reuses them.
-// Three mbarriers, small segments first: stages 0-4 (4 KB) land almost immediately, stages 5-6 (12 KB) and
-// stage 7 (16 KB) are only awaited right before the butterflies that need them.
-constexpr int ROW_TW_ENTRIES = ROW_WARPS * 255;
-__device__ __forceinline__ int row_tw_off(int i) { return ROW_WARPS * ((1 << i) - 1); }
-__device__ __forceinline__ int row_tw_bar(int i) { return i <= 4 ? 0 : (i <= 6 ? 1 : 2); }
-
-__device__ __forceinline__ void stage_row_twiddles(double2 *stw, unsigned long long *bar, const double2 *tw, unsigned tw_base0) {
-  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); mbar_init(bar + 2, 1); }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(bar, (ROW_WARPS * 16u) * 31);
-    mbar_expect_tx(bar + 1, (ROW_WARPS * 16u) * 96);
-    mbar_expect_tx(bar + 2, (ROW_WARPS * 16u) * 128);
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      bulk_g2s(stw + row_tw_off(i), tw + ((size_t)tw_base0 << i), (ROW_WARPS * 16u) << i, bar + row_tw_bar(i));
-  }
-}
-
-// index inside the shared twiddle block: row-local w, lane-stage b (NTT stage i = 7 - b), butterfly pair j
-__device__ __forceinline__ int lane_stage_stw(int w, int b, int j, int lane) {
-  const int i = 7 - b, kk = j + ((lane >> 4) << 2);
-  return row_tw_off(i) + (w << i) + (kk << (4 - b)) + ((lane & 15) >> b);
-}
-
-// Polys that share the limb's modulus (the beta digits of ModUp, the two key-switch accumulators, the two
-// rescaled polys) are processed back to back by the same warp with the same shared twiddles.
-// PIPE: software-pipelined item loop (next item's row prefetched into registers; 3 CTAs/SM) for launches with
-// several items per limb; the plain variant keeps 4 CTAs/SM for single-item launches.
-template <bool PIPE>
-__global__ void __launch_bounds__(ROW_WARPS * 32, PIPE ? 3 : 4) ntt_fwd_rows(NttTables t, int logN, LimbMap lm, NttLaunch l) {
-  constexpr int LR = NTT_ROW_LOG, R2 = 1 << LR;
-  __shared__ __align__(16) double2 stw[ROW_TW_ENTRIES];
-  __shared__ __align__(8) unsigned long long bar[3];
-  const int limb = blockIdx.y;
-  const unsigned R1 = 1u << (logN - LR);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, row = blockIdx.x * ROW_WARPS + w;
-  stage_row_twiddles(stw, bar, t.fwd + ((size_t)lm.mod[limb] << logN), R1 + blockIdx.x * ROW_WARPS);
-  bool ready = false;
-  // items = (ciphertext b, poly p) pairs sharing this limb's modulus; the next item's row is in flight (registers)
-  // while the current one is transformed
-  const int skip = lm.skip[limb], n_items = l.n_polys * l.n_batch;
-  auto next_item = [&](int it) { ++it; while (it < n_items && (it % l.n_polys) == skip) ++it; return it; };
-  int item = next_item(-1);
-  double nx[PIPE ? 8 : 1];
-  if (PIPE && item < n_items) {
-    const LimbCtx lc0 = limb_ctx(t, logN, lm, l, false, limb, item % l.n_polys, item / l.n_polys);
-    const double *ind = reinterpret_cast<const double *>(lc0.out) + (size_t)row * R2;  // pass 1 left raw doubles in `out`
-#pragma unroll
-    for (int r = 0; r < 8; ++r) nx[PIPE ? r : 0] = ind[r * 32 + lane];
-  }
-  while (item < n_items) {
-    const LimbCtx lc = limb_ctx(t, logN, lm, l, false, limb, item % l.n_polys, item / l.n_polys);
-    double a[8];
-    if (PIPE) {
-#pragma unroll
-      for (int r = 0; r < 8; ++r) a[r] = nx[PIPE ? r : 0];
+      for (int m = 0; m < 8; ++m)
+        *reinterpret_cast<ulonglong2 *>(outp + 32 * m) = *reinterpret_cast<const ulonglong2 *>(data + ad.xc[m]);
     } else {
-      const double *ind = reinterpret_cast<const double *>(lc.out) + (size_t)row * R2;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) a[r] = ind[r * 32 + lane];
-    }
-    item = next_item(item);
-    if (PIPE && item < n_items) {
-      const LimbCtx ln = limb_ctx(t, logN, lm, l, false, limb, item % l.n_polys, item / l.n_polys);
-      const double *ind = reinterpret_cast<const double *>(ln.out) + (size_t)row * R2;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) nx[PIPE ? r : 0] = ind[r * 32 + lane];
-    }
-    if (!ready) mbar_wait(bar, 0);
-    {  // stages t = 128, 64, 32: register-only, twiddles broadcast from shared memory
-      const double2 w0 = stw[row_tw_off(0) + w];
-#pragma unroll
-      for (int o = 0; o < 4; ++o) ct_butterfly(a[o], a[o + 4], w0.x, w0.y, lc.q);
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const double2 w1 = stw[row_tw_off(1) + (w << 1) + g];
-#pragma unroll
-        for (int o = 0; o < 2; ++o) ct_butterfly(a[4 * g + o], a[4 * g + o + 2], w1.x, w1.y, lc.q);
+      for (int m = 0; m < 8; ++m) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(data + ad.xb[m]);
+        a[2 * m] = u64_to_f64(v.x); a[2 * m + 1] = u64_to_f64(v.y);
       }
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const double2 w2 = stw[row_tw_off(2) + (w << 2) + g];
-        ct_butterfly(a[2 * g], a[2 * g + 1], w2.x, w2.y, lc.q);
+      for (int m = 0; m < 4; ++m) {
+        const double2 v = *reinterpret_cast<const double2 *>(blob + 2048 + 512 * m + 2 * tid);
+        w[2 * m] = v.x; w[2 * m + 1] = v.y;
       }
+      gs_level<3>(a, w, q, qinv);
+      lds_run<2>(w, blob + 1024 + 2 * tid);
+      { const double2 v = *reinterpret_cast<const double2 *>(blob + 1536 + 2 * tid); w[2] = v.x; w[3] = v.y; }
+      gs_level<2>(a, w, q, qinv);
+      lds_run<2>(w, blob + 512 + 2 * tid); gs_level<1>(a, w, q, qinv);
+      w[0] = blob[256 + tid]; gs_level<0>(a, w, q, qinv);
+#pragma unroll
+      for (int m = 0; m < 8; ++m) *reinterpret_cast<double2 *>(data + ad.xb[m]) = make_double2(a[2 * m], a[2 * m + 1]);
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) a[j] = *reinterpret_cast<const double *>(data + ad.xa[j & 7] + 128 * j);
+      lds_run<8>(w, tw_a + 8); gs_level<3>(a, w, q, qinv);
+      lds_run<4>(w, tw_a + 4); gs_level<2>(a, w, q, qinv);
+      lds_run<2>(w, tw_a + 2); gs_level<1>(a, w, q, qinv);
+      lds_run<1>(w, tw_a + 1); gs_level<0>(a, w, q, qinv);
+      // the sums have grown to <= 2^8 q: bring them back to |v| <= q/2 before the column pass doubles them again
+      double *outd = reinterpret_cast<double *>(dst_of(cur)) + (size_t)rr * 256 + l16;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) outd[16 * j] = reduce_signed(a[j], q, qinv);
     }
-#pragma unroll
-    for (int b = 4; b >= 0; --b) {
-      if (!ready && b == 2) mbar_wait(bar + 1, 0);  // stages 5, 6
-      if (!ready && b == 0) mbar_wait(bar + 2, 0);  // stage 7
-      double2 tw4[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) tw4[j] = stw[lane_stage_stw(w, b, j, lane)];
-      swap_half(a, b, (lane >> b) & 1);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) ct_butterfly(a[j], a[j + 4], tw4[j].x, tw4[j].y, lc.q);
-    }
-    ready = true;
-    u64 *outp = lc.out + (size_t)row * R2 + (lane >> 4) * 128 + 2 * (lane & 15);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const u64 v0 = f64_to_canonical(reduce_signed(a[j], lc.q, lc.qinv), lc.qi);
-      const u64 v1 = f64_to_canonical(reduce_signed(a[j + 4], lc.q, lc.qinv), lc.qi);
-      *reinterpret_cast<ulonglong2 *>(outp + j * 32) = make_ulonglong2(v0, v1);
-    }
+    __syncwarp();  // every lane is done with this stage before it is refilled
+    if (nn < items.n_items) row_issue(src_of(nn), data0 + (k & 1) * ROW_TILE_BYTES, lane, warp);
+    cp_async_commit();
+    cur = nxt; nxt = nn;
   }
-  if (!ready) { mbar_wait(bar, 0); mbar_wait(bar + 1, 0); mbar_wait(bar + 2, 0); }  // never exit with a bulk copy in flight
-}
-
-template <bool PIPE>
-__global__ void __launch_bounds__(ROW_WARPS * 32, PIPE ? 3 : 4) ntt_inv_rows(NttTables t, int logN, LimbMap lm, NttLaunch l) {
-  constexpr int LR = NTT_ROW_LOG, R2 = 1 << LR;
-  __shared__ __align__(16) double2 stw[ROW_TW_ENTRIES];
-  __shared__ __align__(8) unsigned long long bar[3];
-  const int limb = blockIdx.y;
-  const unsigned R1 = 1u << (logN - LR);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, row = blockIdx.x * ROW_WARPS + w;
-  stage_row_twiddles(stw, bar, t.inv + ((size_t)lm.mod[limb] << logN), R1 + blockIdx.x * ROW_WARPS);
-  bool ready = false;
-  const int skip = lm.skip[limb], n_items = l.n_polys * l.n_batch;
-  auto next_item = [&](int it) { ++it; while (it < n_items && (it % l.n_polys) == skip) ++it; return it; };
-  int item = next_item(-1);
-  ulonglong2 nx[PIPE ? 4 : 1];
-  if (PIPE && item < n_items) {
-    const LimbCtx lc0 = limb_ctx(t, logN, lm, l, true, limb, item % l.n_polys, item / l.n_polys);
-    const u64 *inp = lc0.in + (size_t)row * R2 + (lane >> 4) * 128 + 2 * (lane & 15);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) nx[PIPE ? j : 0] = __ldg(reinterpret_cast<const ulonglong2 *>(inp + j * 32));
-  }
-  while (item < n_items) {
-    const LimbCtx lc = limb_ctx(t, logN, lm, l, true, limb, item % l.n_polys, item / l.n_polys);
-    double a[8];
-    if (PIPE) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        a[j] = u64_to_f64(nx[PIPE ? j : 0].x);
-        a[j + 4] = u64_to_f64(nx[PIPE ? j : 0].y);
-      }
-    } else {
-      const u64 *inp = lc.in + (size_t)row * R2 + (lane >> 4) * 128 + 2 * (lane & 15);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(inp + j * 32));
-        a[j] = u64_to_f64(v.x);
-        a[j + 4] = u64_to_f64(v.y);
-      }
-    }
-    item = next_item(item);
-    if (PIPE && item < n_items) {
-      const LimbCtx ln = limb_ctx(t, logN, lm, l, true, limb, item % l.n_polys, item / l.n_polys);
-      const u64 *inp = ln.in + (size_t)row * R2 + (lane >> 4) * 128 + 2 * (lane & 15);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) nx[PIPE ? j : 0] = __ldg(reinterpret_cast<const ulonglong2 *>(inp + j * 32));
-    }
-    if (!ready) { mbar_wait(bar + 2, 0); mbar_wait(bar + 1, 0); mbar_wait(bar, 0); ready = true; }  // the inverse starts with stage 7
-#pragma unroll
-    for (int b = 0; b <= 4; ++b) {
-      double2 tw4[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) tw4[j] = stw[lane_stage_stw(w, b, j, lane)];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) gs_butterfly(a[j], a[j + 4], tw4[j].x, tw4[j].y, lc.q);
-      swap_half(a, b, (lane >> b) & 1);
-    }
-    {  // stages t = 32, 64, 128
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const double2 w2 = stw[row_tw_off(2) + (w << 2) + g];
-        gs_butterfly(a[2 * g], a[2 * g + 1], w2.x, w2.y, lc.q);
-      }
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const double2 w1 = stw[row_tw_off(1) + (w << 1) + g];
-#pragma unroll
-        for (int o = 0; o < 2; ++o) gs_butterfly(a[4 * g + o], a[4 * g + o + 2], w1.x, w1.y, lc.q);
-      }
-      const double2 w0 = stw[row_tw_off(0) + w];
-#pragma unroll
-      for (int o = 0; o < 4; ++o) gs_butterfly(a[o], a[o + 4], w0.x, w0.y, lc.q);
-    }
-    double *outd = reinterpret_cast<double *>(lc.out) + (size_t)row * R2;
-    // the sums have grown to <= 2^8 q: bring them back to |v| <= q/2 before the column pass doubles them again
-#pragma unroll
-    for (int r = 0; r < 8; ++r) outd[r * 32 + lane] = reduce_signed(a[r], lc.q, lc.qinv);
-  }
-  if (!ready) { mbar_wait(bar, 0); mbar_wait(bar + 1, 0); mbar_wait(bar + 2, 0); }
-}
-
-// ================================================================================ inverse, columns (second)
-template <int LOGR1>
-__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_inv_cols(NttTables t, int logN, LimbMap lm, NttLaunch l) {
-  constexpr int R1 = 1 << LOGR1, C = NTT_TILE / R1, R2 = 1 << NTT_ROW_LOG;
-  using SP = Split<LOGR1>;
-  extern __shared__ __align__(16) double sm[];  // [R1][C] tile, then the R1 twiddles of the column pass
-  double2 *stw = reinterpret_cast<double2 *>(sm + NTT_TILE);
-  __shared__ __align__(8) unsigned long long bar;
-  const int limb = blockIdx.y % l.n_limbs, poly = (blockIdx.y / l.n_limbs) % l.n_polys, batch = blockIdx.y / (l.n_limbs * l.n_polys);
-  if (poly == lm.skip[limb]) return;
-  const LimbCtx lc = limb_ctx(t, logN, lm, l, true, limb, poly, batch);
-  if (threadIdx.x == 0) mbar_init(&bar, 1);
-  __syncthreads();
-  if (threadIdx.x == 0) {  // every column shares the same 2^LOGR1 twiddles: one 4 KB bulk copy
-    mbar_expect_tx(&bar, R1 * 16u);
-    bulk_g2s(stw, lc.tw, R1 * 16u, &bar);
-  }
-  const int c = threadIdx.x % C, u = threadIdx.x / C;
-  const int col = blockIdx.x * C + c;
-  const double *ind = reinterpret_cast<const double *>(lc.out);
-  double a[8];
-  if constexpr (SP::S3 != 0) {
-    {
-      using RD = Round<LOGR1, SP::S1 + SP::S2, SP::S3>;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) a[r] = ind[(size_t)RD::point(u, r) * R2 + col];
-      mbar_wait(&bar, 0);
-      gs_round<LOGR1, SP::S1 + SP::S2, SP::S3, true>(a, u, stw, 1u, lc.q);
-#pragma unroll
-      for (int r = 0; r < 8; ++r) sm[RD::point(u, r) * C + c] = a[r];
-    }
-    __syncthreads();
-    using RD = Round<LOGR1, SP::S1, SP::S2>;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(u, r) * C + c];
-    gs_round<LOGR1, SP::S1, SP::S2, true>(a, u, stw, 1u, lc.q);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) sm[RD::point(u, r) * C + c] = a[r];
-  } else {
-    using RD = Round<LOGR1, SP::S1, SP::S2>;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) a[r] = ind[(size_t)RD::point(u, r) * R2 + col];
-    mbar_wait(&bar, 0);
-    gs_round<LOGR1, SP::S1, SP::S2, true>(a, u, stw, 1u, lc.q);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) sm[RD::point(u, r) * C + c] = a[r];
-  }
-  __syncthreads();
-  using RD = Round<LOGR1, 0, SP::S1>;
-#pragma unroll
-  for (int r = 0; r < 8; ++r) a[r] = sm[RD::point(u, r) * C + c];
-  gs_round<LOGR1, 0, SP::S1, true>(a, u, stw, 1u, lc.q);
-  double2 sc;
-  if (l.post_scale) sc = l.post_scale[lc.limb];
-  else { const ModConst mc = t.mc[lm.mod[lc.limb]]; sc = make_double2(mc.ninv, mc.ninv_q); }
-#pragma unroll
-  for (int r = 0; r < 8; ++r)
-    lc.out[(size_t)RD::point(u, r) * R2 + col] = f64_to_canonical(mulmod_const(a[r], sc.x, sc.y, lc.q), lc.qi);
+  cp_async_wait<0>();
 }
 
 // ================================================================================ small N (<= 4096): one CTA per limb
@@ -455,87 +403,144 @@ __global__ void __launch_bounds__(256) ntt_small(NttTables t, int logN, LimbMap 
   extern __shared__ double sm[];
   const int limb = blockIdx.y % l.n_limbs, poly = (blockIdx.y / l.n_limbs) % l.n_polys, batch = blockIdx.y / (l.n_limbs * l.n_polys);
   if (poly == lm.skip[limb]) return;
-  const LimbCtx lc = limb_ctx(t, logN, lm, l, inverse != 0, limb, poly, batch);
+  const int mi = lm.mod[limb];
+  const ModConst mc = t.mc[mi];
+  const double q = mc.q, qinv = mc.qinv;
+  const double *tw = (inverse ? t.inv : t.fwd) + ((size_t)mi << logN);
+  const long long slot = lm.pos[limb];
+  const u64 *in = l.in + (long long)batch * l.in_batch_stride + (long long)poly * l.in_poly_stride + slot * l.in_limb_stride;
+  u64 *out = l.out + (long long)batch * l.out_batch_stride + (long long)poly * l.out_poly_stride + slot * l.out_limb_stride;
   const int N = 1 << logN, half = N >> 1;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) sm[i] = u64_to_f64(__ldg(&lc.in[i]));
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sm[i] = u64_to_f64(__ldg(&in[i]));
   __syncthreads();
   if (!inverse) {
     for (int s = 0; s < logN; ++s) {
       const int tt = N >> (s + 1);
       for (int b = threadIdx.x; b < half; b += blockDim.x) {
         const int grp = b / tt, j = b % tt, i0 = grp * 2 * tt + j;
-        const double2 w = __ldg(&lc.tw[(1 << s) + grp]);
+        const double w = __ldg(&tw[(1 << s) + grp]);
         double x = sm[i0], y = sm[i0 + tt];
-        ct_butterfly(x, y, w.x, w.y, lc.q);
+        ct_butterfly(x, y, w, q, qinv);
         sm[i0] = x; sm[i0 + tt] = y;
       }
       __syncthreads();
     }
-    for (int i = threadIdx.x; i < N; i += blockDim.x)
-      lc.out[i] = f64_to_canonical(reduce_signed(sm[i], lc.q, lc.qinv), lc.qi);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) out[i] = f64_to_canonical(reduce_signed(sm[i], q, qinv), mc.qi);
   } else {
     for (int s = logN - 1; s >= 0; --s) {
       const int tt = N >> (s + 1);
       for (int b = threadIdx.x; b < half; b += blockDim.x) {
         const int grp = b / tt, j = b % tt, i0 = grp * 2 * tt + j;
-        const double2 w = __ldg(&lc.tw[(1 << s) + grp]);
+        const double w = __ldg(&tw[(1 << s) + grp]);
         double x = sm[i0], y = sm[i0 + tt];
-        gs_butterfly(x, y, w.x, w.y, lc.q);
-        if (((logN - s) & 3) == 0) { x = reduce_signed(x, lc.q, lc.qinv); }  // bound the doubling every 4 stages
+        gs_butterfly(x, y, w, q, qinv);
+        if (((logN - s) & 3) == 0) { x = reduce_signed(x, q, qinv); }  // bound the doubling every 4 stages
         sm[i0] = x; sm[i0 + tt] = y;
       }
       __syncthreads();
     }
     double2 sc;
-    if (l.post_scale) sc = l.post_scale[lc.limb];
-    else { const ModConst mc = t.mc[lm.mod[lc.limb]]; sc = make_double2(mc.ninv, mc.ninv_q); }
-    for (int i = threadIdx.x; i < N; i += blockDim.x)
-      lc.out[i] = f64_to_canonical(mulmod_const(sm[i], sc.x, sc.y, lc.q), lc.qi);
+    if (l.post_scale) sc = l.post_scale[limb];
+    else sc = make_double2(mc.ninv, mc.ninv_q);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) out[i] = f64_to_canonical(mulmod_const(sm[i], sc.x, sc.y, q), mc.qi);
   }
 }
 
-// ================================================================================ host launchers
-template <int LOGR1>
-static void launch_fwd_t(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
-  constexpr int C = NTT_TILE >> LOGR1;
-  const dim3 g1((1 << NTT_ROW_LOG) / C, l.n_limbs * l.n_polys * l.n_batch), g2((1 << LOGR1) / ROW_WARPS, l.n_limbs);
-  ntt_fwd_cols<LOGR1><<<g1, NTT_THREADS, NTT_TILE * sizeof(double) + (16u << LOGR1), s>>>(t, logN, lm, l);
-  if (l.n_polys * l.n_batch >= 3) ntt_fwd_rows<true><<<g2, ROW_WARPS * 32, 0, s>>>(t, logN, lm, l);
-  else ntt_fwd_rows<false><<<g2, ROW_WARPS * 32, 0, s>>>(t, logN, lm, l);
+// ================================================================================ host side
+void ntt_permute_row_twiddles(const double *nat, int logN, double *out) {
+  const size_t N = (size_t)1 << logN, R1 = N >> NTT_ROW_LOG;
+  memset(out, 0, N * sizeof(double));
+  for (size_t r = 0; r < R1; ++r) {
+    double *blob = out + (r / 16) * NTT_TILE;
+    const size_t rr = r % 16, base = R1 + r;
+    for (int s = 0; s < 4; ++s)
+      for (size_t g = 0; g < ((size_t)1 << s); ++g) blob[rr * 16 + ((size_t)1 << s) + g] = nat[(base << s) + g];
+    for (size_t l = 0; l < 16; ++l) {
+      const size_t ts = rr * 16 + l;
+      blob[256 + ts] = nat[(base << 4) + l];
+      for (size_t x = 0; x < 2; ++x) blob[512 + ts * 2 + x] = nat[(base << 5) + 2 * l + x];
+      for (size_t k = 0; k < 2; ++k)
+        for (size_t x = 0; x < 2; ++x) blob[1024 + k * 512 + ts * 2 + x] = nat[(base << 6) + 4 * l + 2 * k + x];
+      for (size_t k = 0; k < 4; ++k)
+        for (size_t x = 0; x < 2; ++x) blob[2048 + k * 512 + ts * 2 + x] = nat[(base << 7) + 8 * l + 2 * k + x];
+    }
+  }
 }
+
+static int sm_count() {
+  static int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    return v;
+  }();
+  return n;
+}
+
+template <class KERNEL>
+static void allow_smem(KERNEL k, int bytes) {
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+// items of a row CTA: enough CTAs to fill the machine several times over, but at least ~6 items per twiddle blob
+static int row_split(int n_items, int ctas_xy) {
+  int z = (n_items + 7) / 8;
+  while (z > 1 && (long long)ctas_xy * z > 64ll * sm_count()) --z;
+  return z < 1 ? 1 : z;
+}
+
 template <int LOGR1>
-static void launch_inv_t(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
-  constexpr int C = NTT_TILE >> LOGR1;
-  const dim3 g1((1 << LOGR1) / ROW_WARPS, l.n_limbs), g2((1 << NTT_ROW_LOG) / C, l.n_limbs * l.n_polys * l.n_batch);
-  if (l.n_polys * l.n_batch >= 3) ntt_inv_rows<true><<<g1, ROW_WARPS * 32, 0, s>>>(t, logN, lm, l);
-  else ntt_inv_rows<false><<<g1, ROW_WARPS * 32, 0, s>>>(t, logN, lm, l);
-  ntt_inv_cols<LOGR1><<<g2, NTT_THREADS, NTT_TILE * sizeof(double) + (16u << LOGR1), s>>>(t, logN, lm, l);
+static void launch_cols_t(bool inverse, const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
+  using K = ColCfg<LOGR1>;
+  const int total = l.n_limbs * l.n_polys * l.n_batch * K::TILES;
+  const int grid = total < 2 * sm_count() ? total : 2 * sm_count();
+  static bool once = [] {
+    allow_smem(ntt_fwd_cols<LOGR1>, 2 * K::STAGE_BYTES);
+    allow_smem(ntt_inv_cols<LOGR1>, 2 * K::STAGE_BYTES);
+    return true;
+  }();
+  (void)once;
+  if (inverse) ntt_inv_cols<LOGR1><<<grid, NTT_THREADS, 2 * K::STAGE_BYTES, s>>>(t, logN, lm, l, total);
+  else ntt_fwd_cols<LOGR1><<<grid, NTT_THREADS, 2 * K::STAGE_BYTES, s>>>(t, logN, lm, l, total);
+}
+
+static void launch_cols(bool inverse, const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
+  switch (logN - NTT_ROW_LOG) {
+    case 5: launch_cols_t<5>(inverse, t, logN, lm, l, s); break;
+    case 6: launch_cols_t<6>(inverse, t, logN, lm, l, s); break;
+    case 7: launch_cols_t<7>(inverse, t, logN, lm, l, s); break;
+    case 8: launch_cols_t<8>(inverse, t, logN, lm, l, s); break;
+  }
+}
+
+static void launch_rows(bool inverse, const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
+  static bool once = [] {
+    allow_smem(ntt_rows<false>, ROW_SMEM_BYTES);
+    allow_smem(ntt_rows<true>, ROW_SMEM_BYTES);
+    return true;
+  }();
+  (void)once;
+  const int tiles = 1 << (logN - NTT_ROW_LOG - 4);
+  const dim3 grid(tiles, l.n_limbs, row_split(l.n_polys * l.n_batch, tiles * l.n_limbs));
+  if (inverse) ntt_rows<true><<<grid, NTT_THREADS, ROW_SMEM_BYTES, s>>>(t, logN, lm, l);
+  else ntt_rows<false><<<grid, NTT_THREADS, ROW_SMEM_BYTES, s>>>(t, logN, lm, l);
 }
 
 void launch_ntt_forward(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
-  if (logN <= 12) {
+  if (logN <= NTT_SMALL_LOG) {
     ntt_small<<<dim3(1, l.n_limbs * l.n_polys * l.n_batch), 256, sizeof(double) << logN, s>>>(t, logN, lm, l, 0);
     return;
   }
-  switch (logN - NTT_ROW_LOG) {
-    case 5: launch_fwd_t<5>(t, logN, lm, l, s); break;
-    case 6: launch_fwd_t<6>(t, logN, lm, l, s); break;
-    case 7: launch_fwd_t<7>(t, logN, lm, l, s); break;
-    case 8: launch_fwd_t<8>(t, logN, lm, l, s); break;
-  }
+  launch_cols(false, t, logN, lm, l, s);
+  launch_rows(false, t, logN, lm, l, s);
 }
 
 void launch_ntt_inverse(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
-  if (logN <= 12) {
+  if (logN <= NTT_SMALL_LOG) {
     ntt_small<<<dim3(1, l.n_limbs * l.n_polys * l.n_batch), 256, sizeof(double) << logN, s>>>(t, logN, lm, l, 1);
     return;
   }
-  switch (logN - NTT_ROW_LOG) {
-    case 5: launch_inv_t<5>(t, logN, lm, l, s); break;
-    case 6: launch_inv_t<6>(t, logN, lm, l, s); break;
-    case 7: launch_inv_t<7>(t, logN, lm, l, s); break;
-    case 8: launch_inv_t<8>(t, logN, lm, l, s); break;
-  }
+  launch_rows(true, t, logN, lm, l, s);
+  launch_cols(true, t, logN, lm, l, s);
 }
 
 }  // namespace hml

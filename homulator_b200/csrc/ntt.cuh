@@ -5,24 +5,27 @@
 // two-phase + transpose structure, :397-431) on real data.
 //
 // Algorithm: merged-psi Cooley-Tukey (forward, natural in -> bit-reversed out) / Gentleman-Sande
-// (inverse), split 4-step style into TWO passes so that every pass works on a 4096-element tile held in
-// registers + shared memory:
+// (inverse), split 4-step style into TWO passes over 4096-point tiles (256 threads x 16 points):
 //   forward  pass 1 "columns": the first log2(R1) stages couple elements R2 apart (R2 = 256, R1 = N/256);
 //            a CTA owns C = 4096/R1 adjacent columns (>= 128 B contiguous per row -> full-line accesses).
 //   forward  pass 2 "rows":    the last 8 stages stay inside contiguous 256-element rows; a CTA owns 16 rows.
 //   inverse  = the mirror image (rows first, then columns).
-// Inside a pass each thread keeps 8 points in registers and runs up to 3 radix-2 stages per "round";
-// rounds exchange data through shared memory laid out [point][column] (conflict-free: a warp always
-// touches whole rows; the row pass uses pitch C+1 for its transposing accesses).
+// Every thread keeps 16 points in registers and runs FOUR radix-2 stages per round (one 16-point network with
+// a 15-entry twiddle heap), so a pass needs a single exchange through shared memory.  Tiles reach shared
+// memory by asynchronous 16-byte copies (cp.async), double buffered: the next tile / item is in flight while
+// the current one is transformed.  Twiddles are single doubles (the quotient estimate uses 1/q, see
+// mulmod_var); the row pass reads them from a per-tile blob laid out for conflict-free vector loads
+// (ntt_permute_row_twiddles) that arrives by ONE bulk copy (TMA engine) per CTA.
 // The buffer between the passes holds raw signed-lazy doubles (no conversion / reduction cost).
 #pragma once
 #include "modarith.cuh"
 
 namespace hml {
 
-constexpr int NTT_TILE = 4096;     // elements per CTA
-constexpr int NTT_THREADS = 512;   // 8 elements per thread
+constexpr int NTT_TILE = 4096;     // elements per CTA tile
+constexpr int NTT_THREADS = 256;   // 16 elements per thread
 constexpr int NTT_ROW_LOG = 8;     // R2 = 256: contiguous row length handled by the row pass
+constexpr int NTT_SMALL_LOG = 12;  // N <= 4096: one CTA per limb, all stages in shared memory
 constexpr int NTT_MAX_LIMBS = 128; // limbs (x polys) per launch
 
 struct LimbMap {
@@ -32,12 +35,24 @@ struct LimbMap {
                                 // ModUp, where digit j's own limbs stay as they are
 };
 
-// Twiddle tables: per modulus, N entries of (w, RN(w/q)) as double2, index = bit-reversed exponent
+// Twiddle tables, one double per entry (w = psi^(+-bitrev)), per modulus N entries.
+//   fwd / inv          natural "heap" order: the butterflies of stage s, group g use entry (1 << s) + g
+//   fwd_rows/inv_rows  the same values permuted per 16-row tile for the row pass (null when N <= 4096)
 struct NttTables {
-  const double2 *fwd;      // [n_mod][N]
-  const double2 *inv;      // [n_mod][N]
-  const ModConst *mc;      // [n_mod]
+  const double *fwd, *inv;            // [n_mod][N]
+  const double *fwd_rows, *inv_rows;  // [n_mod][N / 4096][4096]
+  const ModConst *mc;                 // [n_mod]
 };
+
+// Host: permute one modulus' natural table (N entries) into the row-pass layout.  Per 16-row tile (rows r = 16 *
+// tile + rr, thread slot ts = rr * 16 + l) a 4096-entry blob:
+//   [   0 +  rr*16 + h ]            h = 1..15: heap of the row's first four stages (t = 128..16), h = (1 << s) + g
+//   [ 256 +  ts ]                   stage 4 (t = 8):  entry ((R1 + r) << 4) + l
+//   [ 512 +  ts*2 + x ]             stage 5 (t = 4):  entry ((R1 + r) << 5) + 2l + x
+//   [1024 + k*512 + ts*2 + x ]      stage 6 (t = 2):  entry ((R1 + r) << 6) + 4l + 2k + x,  k < 2
+//   [2048 + k*512 + ts*2 + x ]      stage 7 (t = 1):  entry ((R1 + r) << 7) + 8l + 2k + x,  k < 4
+// so that every 16-byte load instruction of a warp covers 512 contiguous bytes.
+void ntt_permute_row_twiddles(const double *nat, int logN, double *out);
 
 // ---- launch descriptors (host side, ntt.cu)
 struct NttLaunch {
