@@ -490,16 +490,30 @@ static int ks_run(hml_ctx *ctx, uint32_t L, uint32_t nb, BatchPtr d, const u64 *
     a.step1 = nullptr; a.N = N; a.n_batches = 2 * nb;
     run_bconv(ctx, lc->down, lc->p_lm, a, s);
   }
-  // K9 (reference :521-546, emitted with opcode INTT — delta D1): forward NTT of the converted limbs
+  // K9 (reference :521-546, emitted with opcode INTT — delta D1): forward NTT of the converted limbs, and
+  // K10 (reference :548-590) (+ the caller's addend: HMULT add :967-1005 / HROTATE add :1339-1357).
+  // Two-pass rings fuse K10 into the transform's row pass (NttFuse): v-hat never reaches HBM.
+  const bool fuse = npass == 2 && out0.stride == out1.stride && (!add0.ptr || !add1.ptr || add0.stride == add1.stride);
   {
     NttLaunch l{};
     l.in = vb; l.out = vb; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)L * N;
     l.n_limbs = L; l.n_polys = 2 * nb; l.n_batch = 1;
+    if (fuse) {
+      NttFuse &f = l.fuse;
+      f.x = acc; f.x_c_stride = (long long)E * N; f.x_b_stride = 2ll * E * N;
+      const BatchPtr zb = add0.ptr ? add0 : add1;  // component c reads zb.ptr + c * z_c_stride; only masked components are touched
+      f.z = zb.ptr; f.z_b_stride = zb.stride;
+      f.z_c_stride = (add0.ptr && add1.ptr) ? (long long)(add1.ptr - add0.ptr) : 0;
+      if (!add0.ptr && add1.ptr) f.z = add1.ptr;
+      f.z_mask = (add0.ptr ? 1u : 0u) | (add1.ptr ? 2u : 0u);
+      f.dst = out0.ptr; f.dst_c_stride = (long long)(out1.ptr - out0.ptr); f.dst_b_stride = out0.stride;
+      f.cst = lc->pinv; f.n_c = 2;
+    }
     launch_ntt_forward(ctx->tabs, logN, lc->q_lm, l, s);
     ctx->exec.ntt_limbs += 2ull * nb * L; ctx->exec.kernel_launches += npass;
+    if (fuse) ctx->exec.ewe_limbs += (uint64_t)nb * (2 * L + (add0.ptr ? L : 0) + (add1.ptr ? L : 0));
   }
-  // K10 (reference :548-590) (+ the caller's addend: HMULT add :967-1005 / HROTATE add :1339-1357)
-  for (int c = 0; c < 2; ++c) {
+  for (int c = 0; c < 2 && !fuse; ++c) {
     const BatchPtr add = c ? add1 : add0;
     const BatchOut out = c ? out1 : out0;
     SubMulArgs a{};
@@ -780,21 +794,29 @@ static int rescale_run(hml_ctx *ctx, uint32_t L, const u64 *in, long long in_pol
     launch_ntt_inverse(ctx->tabs, logN, lm, l, s);
     ctx->exec.intt_limbs += n_polys; ctx->exec.kernel_launches += npass;
   }
-  {  // NTT of that polynomial under each remaining modulus (reference :807-822 counts ONE; delta D2)
+  const bool fuse = npass == 2;
+  {  // NTT of that polynomial under each remaining modulus (reference :807-822 counts ONE; delta D2); on two-pass rings
+     // the sub + mul (reference :825-911) is the transform's fused epilogue
     NttLaunch l{};
     l.n_batch = 1;
     l.in = rb; l.out = rh; l.in_limb_stride = 0; l.out_limb_stride = N; l.in_poly_stride = N;
     l.out_poly_stride = (long long)(L - 1) * N; l.n_limbs = L - 1; l.n_polys = n_polys;
+    if (fuse) {
+      NttFuse &f = l.fuse;
+      f.x = in; f.x_c_stride = in_poly_stride; f.x_b_stride = 0; f.z = nullptr; f.z_mask = 0;
+      f.dst = out; f.dst_c_stride = out_poly_stride; f.dst_b_stride = 0; f.cst = lc->qlinv; f.n_c = (int)n_polys;
+    }
     launch_ntt_forward(ctx->tabs, logN, lc->q_lm, l, s);
     ctx->exec.ntt_limbs += (uint64_t)n_polys * (L - 1); ctx->exec.kernel_launches += npass;
   }
-  {  // sub + mul (reference :825-911), one fused pass
+  if (!fuse) {  // sub + mul (reference :825-911), one fused pass
     SubMulArgs a{};
     a.x = in; a.y = rh; a.z = nullptr; a.out = out; a.x_poly_stride = in_poly_stride; a.y_poly_stride = (long long)(L - 1) * N;
     a.out_poly_stride = out_poly_stride; a.cst = lc->qlinv; a.N = N; a.n_limbs = L - 1; a.n_polys = n_polys;
     launch_sub_mul_add(ctx->mc, lc->q_lm, a, s);
-    ctx->exec.ewe_limbs += 2ull * n_polys * (L - 1); ctx->exec.kernel_launches++;
+    ctx->exec.kernel_launches++;
   }
+  ctx->exec.ewe_limbs += 2ull * n_polys * (L - 1);
   return check_launch(ctx, "rescale");
 }
 

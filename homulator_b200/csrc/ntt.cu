@@ -1,6 +1,7 @@
 // See ntt.cuh for the algorithm.  sm_100a only.
 #include "ntt.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace hml {
@@ -77,15 +78,19 @@ __device__ __forceinline__ void lds_run(double (&w)[8], const double *p) {
 }
 
 // ================================================================================ column passes
-// Tile = C adjacent columns x all R1 rows; thread (c, u) = (tid % C, tid / C), U = R1 / 16 row groups.
-//   round A: rows u + U*j   (shared-memory word tid + 256*j): stages 0..3
+// Tile = C adjacent columns x all R1 rows = 16 * NT points for a CTA of NT threads (NT = 256: 32 KB tiles, two CTAs per
+// SM; NT = 128: 16 KB tiles, four CTAs per SM, i.e. four independent barrier domains);
+// thread (c, u) = (tid % C, tid / C), U = R1 / 16 row groups.
+//   round A: rows u + U*j   (shared-memory word tid + NT*j): stages 0..3
 //   round B: rows 16*u + j  : stages 4..LOGR1-1 (the last LOGR1-4 levels of the network)
-// Work item = (limb-poly-batch y, tile); a CTA walks items blockIdx.x, + gridDim.x, ... with the next item's tile and
-// its R1 twiddles already in flight (two stages of 32 KB + 2 KB).
-template <int LOGR1>
+// Work item = (limb-poly-batch y, tile); a CTA walks items blockIdx.x, + gridDim.x, ... with the next item's tile, its R1
+// twiddles and its modulus constants already in flight (two stages).
+template <int LOGR1, int NT>
 struct ColCfg {
-  static constexpr int R1 = 1 << LOGR1, C = NTT_TILE / R1, SKIP = 8 - LOGR1, TILES = (1 << NTT_ROW_LOG) / C;
-  static constexpr int STAGE_BYTES = NTT_TILE * 8 + 2048 + 64;  // tile | R1 twiddles | ModConst (48 B) | post-scale (16 B)
+  static constexpr int R1 = 1 << LOGR1, TILE = 16 * NT, C = TILE / R1, SKIP = 8 - LOGR1, TILES = (1 << NTT_ROW_LOG) / C;
+  static constexpr int STAGE_BYTES = TILE * 8 + 2048 + 64;  // tile | R1 twiddles | ModConst (48 B) | post-scale (16 B)
+  static constexpr int MIN_CTAS = NT == 256 ? 2 : 4;
+  static_assert(C >= 2 && C * (R1 / 16) == NT, "thread map");
 };
 
 struct ColWork {
@@ -94,9 +99,9 @@ struct ColWork {
   int mi, limb, tile;
 };
 
-template <int LOGR1>
+template <int LOGR1, int NT>
 __device__ __forceinline__ bool col_decode(int wi, const LimbMap &lm, const NttLaunch &l, bool in_is_out, ColWork &w) {
-  using K = ColCfg<LOGR1>;
+  using K = ColCfg<LOGR1, NT>;
   const int y = wi / K::TILES, tile = wi % K::TILES;
   const int limb = y % l.n_limbs, poly = (y / l.n_limbs) % l.n_polys, batch = y / (l.n_limbs * l.n_polys);
   if (poly == lm.skip[limb]) return false;
@@ -110,56 +115,59 @@ __device__ __forceinline__ bool col_decode(int wi, const LimbMap &lm, const NttL
   return true;
 }
 
-template <int LOGR1>
+template <int LOGR1, int NT>
 __device__ __forceinline__ void col_issue(const ColWork &w, const double *tw_table, const ModConst *mc, const double2 *post_scale, int logN,
                                           unsigned stage_smem) {
-  using K = ColCfg<LOGR1>;
+  using K = ColCfg<LOGR1, NT>;
   const int tid = threadIdx.x;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const int qd = tid + 256 * k, row = qd / (K::C / 2), cc = qd % (K::C / 2);
+    const int qd = tid + NT * k, row = qd / (K::C / 2), cc = qd % (K::C / 2);
     cp_async16(stage_smem + qd * 16, w.in + (size_t)row * (1 << NTT_ROW_LOG) + 2 * cc);
   }
-  if (tid < K::R1 / 2) cp_async16(stage_smem + NTT_TILE * 8 + tid * 16, tw_table + ((size_t)w.mi << logN) + 2 * tid);
-  // the per-modulus constants ride along, so the transform never waits on a dependent global load
-  else if (tid < K::R1 / 2 + 3) cp_async16(stage_smem + NTT_TILE * 8 + 2048 + (tid - K::R1 / 2) * 16, reinterpret_cast<const char *>(mc + w.mi) + (tid - K::R1 / 2) * 16);
-  else if (tid == K::R1 / 2 + 3 && post_scale) cp_async16(stage_smem + NTT_TILE * 8 + 2048 + 48, post_scale + w.limb);
+  // the R1 twiddles and the per-modulus constants ride along, so the transform never waits on a dependent global load
+  for (int x = tid; x < K::R1 / 2 + 4; x += NT) {
+    const int y = x - K::R1 / 2;
+    if (y < 0) cp_async16(stage_smem + K::TILE * 8 + x * 16, tw_table + ((size_t)w.mi << logN) + 2 * x);
+    else if (y < 3) cp_async16(stage_smem + K::TILE * 8 + 2048 + y * 16, reinterpret_cast<const char *>(mc + w.mi) + y * 16);
+    else if (post_scale) cp_async16(stage_smem + K::TILE * 8 + 2048 + 48, post_scale + w.limb);
+  }
 }
 
-template <int LOGR1>
-__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_fwd_cols(NttTables t, int logN, LimbMap lm, NttLaunch l, int total) {
-  using K = ColCfg<LOGR1>;
+template <int LOGR1, int NT>
+__global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_fwd_cols(NttTables t, int logN, LimbMap lm, NttLaunch l, int total) {
+  using K = ColCfg<LOGR1, NT>;
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, c = tid % K::C, u = tid / K::C;
   const unsigned smem0 = smem_u32(smem);
   ColWork cur, nxt;
   int wi = blockIdx.x;
-  while (wi < total && !col_decode<LOGR1>(wi, lm, l, false, cur)) wi += gridDim.x;
-  if (wi < total) col_issue<LOGR1>(cur, t.fwd, t.mc, nullptr, logN, smem0);
+  while (wi < total && !col_decode<LOGR1, NT>(wi, lm, l, false, cur)) wi += gridDim.x;
+  if (wi < total) col_issue<LOGR1, NT>(cur, t.fwd, t.mc, nullptr, logN, smem0);
   cp_async_commit();
   for (int it = 0; wi < total; ++it) {
     int nwi = wi + gridDim.x;
-    while (nwi < total && !col_decode<LOGR1>(nwi, lm, l, false, nxt)) nwi += gridDim.x;
+    while (nwi < total && !col_decode<LOGR1, NT>(nwi, lm, l, false, nxt)) nwi += gridDim.x;
     cp_async_wait<0>();
     __syncthreads();  // tile `it` has landed for every thread; everybody is done with the other stage
-    if (nwi < total) col_issue<LOGR1>(nxt, t.fwd, t.mc, nullptr, logN, smem0 + ((it + 1) & 1) * K::STAGE_BYTES);
+    if (nwi < total) col_issue<LOGR1, NT>(nxt, t.fwd, t.mc, nullptr, logN, smem0 + ((it + 1) & 1) * K::STAGE_BYTES);
     cp_async_commit();
     double *data = reinterpret_cast<double *>(smem + (it & 1) * K::STAGE_BYTES);
-    const double *tw = data + NTT_TILE;
+    const double *tw = data + K::TILE;
     const ModConst &mc = *reinterpret_cast<const ModConst *>(tw + 256);
     const double q = mc.q, qinv = mc.qinv;
     double a[16], w[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) a[j] = u64_to_f64(reinterpret_cast<const u64 *>(data)[tid + 256 * j]);
+    for (int j = 0; j < 16; ++j) a[j] = u64_to_f64(reinterpret_cast<const u64 *>(data)[tid + NT * j]);
     // A constant added to coefficient 0 appears unchanged in every evaluation slot: subtracting h = (q-1)/2 here makes
     // the row pass's centred reduction land in [-h, h] = [0, q-1] - h, so its canonicalisation is one add (no sign fix).
-    if (cur.tile == 0 && tid == 0) a[0] -= (q - 1.0) * 0.5;
+    if (cur.tile == 0 && tid == 0 && l.fuse.x == nullptr) a[0] -= (q - 1.0) * 0.5;
     lds_run<1>(w, tw + 1); ct_level<0>(a, w, q, qinv);
     lds_run<2>(w, tw + 2); ct_level<1>(a, w, q, qinv);
     lds_run<4>(w, tw + 4); ct_level<2>(a, w, q, qinv);
     lds_run<8>(w, tw + 8); ct_level<3>(a, w, q, qinv);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) data[tid + 256 * j] = a[j];
+    for (int j = 0; j < 16; ++j) data[tid + NT * j] = a[j];
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 16; ++j) a[j] = data[(16 * u + j) * K::C + c];
@@ -175,26 +183,26 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_fwd_cols(NttTables t, int 
 }
 
 // inverse, second pass: raw doubles in `out` -> canonical words, post-scale folded into the N^-1 multiply
-template <int LOGR1>
-__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_inv_cols(NttTables t, int logN, LimbMap lm, NttLaunch l, int total) {
-  using K = ColCfg<LOGR1>;
+template <int LOGR1, int NT>
+__global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_inv_cols(NttTables t, int logN, LimbMap lm, NttLaunch l, int total) {
+  using K = ColCfg<LOGR1, NT>;
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, c = tid % K::C, u = tid / K::C;
   const unsigned smem0 = smem_u32(smem);
   ColWork cur, nxt;
   int wi = blockIdx.x;
-  while (wi < total && !col_decode<LOGR1>(wi, lm, l, true, cur)) wi += gridDim.x;
-  if (wi < total) col_issue<LOGR1>(cur, t.inv, t.mc, l.post_scale, logN, smem0);
+  while (wi < total && !col_decode<LOGR1, NT>(wi, lm, l, true, cur)) wi += gridDim.x;
+  if (wi < total) col_issue<LOGR1, NT>(cur, t.inv, t.mc, l.post_scale, logN, smem0);
   cp_async_commit();
   for (int it = 0; wi < total; ++it) {
     int nwi = wi + gridDim.x;
-    while (nwi < total && !col_decode<LOGR1>(nwi, lm, l, true, nxt)) nwi += gridDim.x;
+    while (nwi < total && !col_decode<LOGR1, NT>(nwi, lm, l, true, nxt)) nwi += gridDim.x;
     cp_async_wait<0>();
     __syncthreads();
-    if (nwi < total) col_issue<LOGR1>(nxt, t.inv, t.mc, l.post_scale, logN, smem0 + ((it + 1) & 1) * K::STAGE_BYTES);
+    if (nwi < total) col_issue<LOGR1, NT>(nxt, t.inv, t.mc, l.post_scale, logN, smem0 + ((it + 1) & 1) * K::STAGE_BYTES);
     cp_async_commit();
     double *data = reinterpret_cast<double *>(smem + (it & 1) * K::STAGE_BYTES);
-    const double *tw = data + NTT_TILE;
+    const double *tw = data + K::TILE;
     const ModConst &mc = *reinterpret_cast<const ModConst *>(tw + 256);
     const double q = mc.q, qinv = mc.qinv;
     double a[16], w[8];
@@ -208,7 +216,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_inv_cols(NttTables t, int 
     for (int j = 0; j < 16; ++j) data[(16 * u + j) * K::C + c] = a[j];
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) a[j] = data[tid + 256 * j];
+    for (int j = 0; j < 16; ++j) a[j] = data[tid + NT * j];
     lds_run<8>(w, tw + 8); gs_level<3>(a, w, q, qinv);
     lds_run<4>(w, tw + 4); gs_level<2>(a, w, q, qinv);
     lds_run<2>(w, tw + 2); gs_level<1>(a, w, q, qinv);
@@ -274,7 +282,7 @@ struct RowItems {
   }
 };
 
-template <bool INV>
+template <bool INV, bool FUSE>
 __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN, LimbMap lm, NttLaunch l) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bar;
@@ -346,19 +354,63 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
         w[2 * m] = v.x; w[2 * m + 1] = v.y;
       }
       ct_level<3>(a, w, q, qinv);
-      // canonical words back through the swizzled tile so that the global stores are 16 bytes per lane, 256 B per half-warp
+      if constexpr (!FUSE) {
+        // canonical words back through the swizzled tile so that the global stores are 16 bytes per lane, 256 B per half-warp
 #pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        // values are (true - h) mod q (bias planted by the column pass): centred remainder + h is canonical
-        const u64 v0 = (u64)__double_as_longlong(reduce_signed(a[2 * m], q, qinv) + hb) & 0x000FFFFFFFFFFFFFull;
-        const u64 v1 = (u64)__double_as_longlong(reduce_signed(a[2 * m + 1], q, qinv) + hb) & 0x000FFFFFFFFFFFFFull;
-        *reinterpret_cast<ulonglong2 *>(data + ad.xb[m]) = make_ulonglong2(v0, v1);
+        for (int m = 0; m < 8; ++m) {
+          // values are (true - h) mod q (bias planted by the column pass): centred remainder + h is canonical
+          const u64 v0 = (u64)__double_as_longlong(reduce_signed(a[2 * m], q, qinv) + hb) & 0x000FFFFFFFFFFFFFull;
+          const u64 v1 = (u64)__double_as_longlong(reduce_signed(a[2 * m + 1], q, qinv) + hb) & 0x000FFFFFFFFFFFFFull;
+          *reinterpret_cast<ulonglong2 *>(data + ad.xb[m]) = make_ulonglong2(v0, v1);
+        }
+        __syncwarp();
+        u64 *outp = dst_of(cur) + (size_t)rr * 256 + (l16 >> 3) * 16 + (l16 & 7) * 2;
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+          *reinterpret_cast<ulonglong2 *>(outp + 32 * m) = *reinterpret_cast<const ulonglong2 *>(data + ad.xc[m]);
+      } else {
+        // fused epilogue: the raw lazy sums go through the swizzled tile, then every lane handles the 16-byte chunks it
+        // will store, so x, z and dst are all accessed 256 B per half-warp
+#pragma unroll
+        for (int m = 0; m < 8; ++m) *reinterpret_cast<double2 *>(data + ad.xb[m]) = make_double2(a[2 * m], a[2 * m + 1]);
+        __syncwarp();
+        const NttFuse &f = l.fuse;
+        const long long fb = cur / f.n_c, fc = cur % f.n_c;
+        const size_t off = (size_t)limb * ((size_t)1 << logN) + tile_off + (size_t)rr * 256 + (l16 >> 3) * 16 + (l16 & 7) * 2;
+        const u64 *xp = f.x + fc * f.x_c_stride + fb * f.x_b_stride + off;
+        const bool has_z = f.z != nullptr && ((f.z_mask >> fc) & 1u);
+        const u64 *zp = has_z ? f.z + fc * f.z_c_stride + fb * f.z_b_stride + off : nullptr;
+        u64 *dp = f.dst + fc * f.dst_c_stride + fb * f.dst_b_stride + off;
+        const double2 cst = f.cst[limb];
+        ulonglong2 xv[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) xv[m] = __ldg(reinterpret_cast<const ulonglong2 *>(xp + 32 * m));
+        if (has_z) {
+          ulonglong2 zv[8];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) zv[m] = __ldg(reinterpret_cast<const ulonglong2 *>(zp + 32 * m));
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            const double2 y = *reinterpret_cast<const double2 *>(data + ad.xc[m]);
+            // z - h rides on the integer -> double conversion: (2^52 | z) - (2^52 + h)
+            const double z0 = __longlong_as_double((long long)(zv[m].x | 0x4330000000000000ull)) - hb;
+            const double z1 = __longlong_as_double((long long)(zv[m].y | 0x4330000000000000ull)) - hb;
+            const double r0 = mulmod_const(u64_to_f64(xv[m].x) - y.x, cst.x, cst.y, q) + z0;
+            const double r1 = mulmod_const(u64_to_f64(xv[m].y) - y.y, cst.x, cst.y, q) + z1;
+            const u64 v0 = (u64)__double_as_longlong(reduce_signed(r0, q, qinv) + hb) & 0x000FFFFFFFFFFFFFull;
+            const u64 v1 = (u64)__double_as_longlong(reduce_signed(r1, q, qinv) + hb) & 0x000FFFFFFFFFFFFFull;
+            *reinterpret_cast<ulonglong2 *>(dp + 32 * m) = make_ulonglong2(v0, v1);
+          }
+        } else {
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            const double2 y = *reinterpret_cast<const double2 *>(data + ad.xc[m]);
+            const u64 v0 = f64_to_canonical(mulmod_const(u64_to_f64(xv[m].x) - y.x, cst.x, cst.y, q), mc.qi);
+            const u64 v1 = f64_to_canonical(mulmod_const(u64_to_f64(xv[m].y) - y.y, cst.x, cst.y, q), mc.qi);
+            *reinterpret_cast<ulonglong2 *>(dp + 32 * m) = make_ulonglong2(v0, v1);
+          }
+        }
       }
-      __syncwarp();
-      u64 *outp = dst_of(cur) + (size_t)rr * 256 + (l16 >> 3) * 16 + (l16 & 7) * 2;
-#pragma unroll
-      for (int m = 0; m < 8; ++m)
-        *reinterpret_cast<ulonglong2 *>(outp + 32 * m) = *reinterpret_cast<const ulonglong2 *>(data + ad.xc[m]);
     } else {
 #pragma unroll
       for (int m = 0; m < 8; ++m) {
@@ -488,41 +540,53 @@ static int row_split(int n_items, int ctas_xy) {
   return z < 1 ? 1 : z;
 }
 
-template <int LOGR1>
+template <int LOGR1, int NT>
 static void launch_cols_t(bool inverse, const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
-  using K = ColCfg<LOGR1>;
+  using K = ColCfg<LOGR1, NT>;
   const int total = l.n_limbs * l.n_polys * l.n_batch * K::TILES;
-  const int grid = total < 2 * sm_count() ? total : 2 * sm_count();
+  const int resident = K::MIN_CTAS * sm_count();
+  const int grid = total < resident ? total : resident;
   static bool once = [] {
-    allow_smem(ntt_fwd_cols<LOGR1>, 2 * K::STAGE_BYTES);
-    allow_smem(ntt_inv_cols<LOGR1>, 2 * K::STAGE_BYTES);
+    allow_smem(ntt_fwd_cols<LOGR1, NT>, 2 * K::STAGE_BYTES);
+    allow_smem(ntt_inv_cols<LOGR1, NT>, 2 * K::STAGE_BYTES);
     return true;
   }();
   (void)once;
-  if (inverse) ntt_inv_cols<LOGR1><<<grid, NTT_THREADS, 2 * K::STAGE_BYTES, s>>>(t, logN, lm, l, total);
-  else ntt_fwd_cols<LOGR1><<<grid, NTT_THREADS, 2 * K::STAGE_BYTES, s>>>(t, logN, lm, l, total);
+  if (inverse) ntt_inv_cols<LOGR1, NT><<<grid, NT, 2 * K::STAGE_BYTES, s>>>(t, logN, lm, l, total);
+  else ntt_fwd_cols<LOGR1, NT><<<grid, NT, 2 * K::STAGE_BYTES, s>>>(t, logN, lm, l, total);
+}
+
+static int col_threads() {
+  static const int v = [] {
+    const char *e = getenv("HML_COL_NT");  // tuning knob: 128 or 256 threads per column-pass CTA
+    return e && atoi(e) == 256 ? 256 : 128;
+  }();
+  return v;
 }
 
 static void launch_cols(bool inverse, const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
+  const bool big = col_threads() == 256;
   switch (logN - NTT_ROW_LOG) {
-    case 5: launch_cols_t<5>(inverse, t, logN, lm, l, s); break;
-    case 6: launch_cols_t<6>(inverse, t, logN, lm, l, s); break;
-    case 7: launch_cols_t<7>(inverse, t, logN, lm, l, s); break;
-    case 8: launch_cols_t<8>(inverse, t, logN, lm, l, s); break;
+    case 5: big ? launch_cols_t<5, 256>(inverse, t, logN, lm, l, s) : launch_cols_t<5, 128>(inverse, t, logN, lm, l, s); break;
+    case 6: big ? launch_cols_t<6, 256>(inverse, t, logN, lm, l, s) : launch_cols_t<6, 128>(inverse, t, logN, lm, l, s); break;
+    case 7: big ? launch_cols_t<7, 256>(inverse, t, logN, lm, l, s) : launch_cols_t<7, 128>(inverse, t, logN, lm, l, s); break;
+    case 8: big ? launch_cols_t<8, 256>(inverse, t, logN, lm, l, s) : launch_cols_t<8, 128>(inverse, t, logN, lm, l, s); break;
   }
 }
 
 static void launch_rows(bool inverse, const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
   static bool once = [] {
-    allow_smem(ntt_rows<false>, ROW_SMEM_BYTES);
-    allow_smem(ntt_rows<true>, ROW_SMEM_BYTES);
+    allow_smem(ntt_rows<false, false>, ROW_SMEM_BYTES);
+    allow_smem(ntt_rows<false, true>, ROW_SMEM_BYTES);
+    allow_smem(ntt_rows<true, false>, ROW_SMEM_BYTES);
     return true;
   }();
   (void)once;
   const int tiles = 1 << (logN - NTT_ROW_LOG - 4);
   const dim3 grid(tiles, l.n_limbs, row_split(l.n_polys * l.n_batch, tiles * l.n_limbs));
-  if (inverse) ntt_rows<true><<<grid, NTT_THREADS, ROW_SMEM_BYTES, s>>>(t, logN, lm, l);
-  else ntt_rows<false><<<grid, NTT_THREADS, ROW_SMEM_BYTES, s>>>(t, logN, lm, l);
+  if (inverse) ntt_rows<true, false><<<grid, NTT_THREADS, ROW_SMEM_BYTES, s>>>(t, logN, lm, l);
+  else if (l.fuse.x) ntt_rows<false, true><<<grid, NTT_THREADS, ROW_SMEM_BYTES, s>>>(t, logN, lm, l);
+  else ntt_rows<false, false><<<grid, NTT_THREADS, ROW_SMEM_BYTES, s>>>(t, logN, lm, l);
 }
 
 void launch_ntt_forward(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {

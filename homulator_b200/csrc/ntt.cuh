@@ -54,6 +54,20 @@ struct NttTables {
 // so that every 16-byte load instruction of a warp covers 512 contiguous bytes.
 void ntt_permute_row_twiddles(const double *nat, int logN, double *out);
 
+// Optional fused epilogue of a FORWARD transform (ModDownSub + add, reference src/Operation.cpp:548-590, :967-1005, and
+// Rescale sub + mul, :825-911): instead of storing y = NTT(in) the row pass writes
+//   dst = (x - y) * cst[limb] (+ z)   mod q, canonical
+// so the transform's output never round-trips HBM.  Items are (b, c) = (idx / n_c, idx % n_c) with idx the launch's
+// poly index (n_batch must be 1); every operand is addressed as base + c * c_stride + b * b_stride + limb * N.
+struct NttFuse {
+  const u64 *x, *z;             // x = null: no fusion;  z may be null
+  u64 *dst;
+  long long x_c_stride, x_b_stride, z_c_stride, z_b_stride, dst_c_stride, dst_b_stride;
+  const double2 *cst;           // [n_limbs] (c, RN(c/q))
+  int n_c;
+  unsigned z_mask;              // z is added for component c iff bit c is set
+};
+
 // ---- launch descriptors (host side, ntt.cu)
 struct NttLaunch {
   const u64 *in;        // [n_polys][n_limbs][N] (poly stride / limb stride in elements below)
@@ -65,6 +79,7 @@ struct NttLaunch {
   long long in_batch_stride, out_batch_stride;
   // inverse only: per-limb post-scale constant c (folded with N^-1 on the host): out = INTT(in) * c, canonical.
   const double2 *post_scale;  // [n_limbs] (c*ninv mod q, RN(that / q)) or nullptr for plain N^-1
+  NttFuse fuse;               // forward only
 };
 
 void launch_ntt_forward(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s);

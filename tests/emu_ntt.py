@@ -65,33 +65,34 @@ def gs_level(a, T, w, q):
 
 
 # ------------------------------------------------------------------------------------------------ column passes
-def col_tile(data, logN, tw, q, tile, inverse, post=1):
+def col_tile(data, logN, tw, q, tile, inverse, post=1, NT=256):
     """one work item of ntt_fwd_cols / ntt_inv_cols on the limb `data` (list of N ints), in place"""
     LOGR1 = logN - ROW_LOG
     R1 = 1 << LOGR1
-    C = TILE // R1
+    CT = 16 * NT  # points per column-pass tile
+    C = CT // R1
     SKIP = 8 - LOGR1
     col0 = tile * C
-    sm = [None] * TILE
+    sm = [None] * CT
     # col_issue: chunk qd = tid + 256k -> row qd / (C/2), column pair qd % (C/2); linear shared-memory layout
-    for tid in range(256):
+    for tid in range(NT):
         for k in range(8):
-            qd = tid + 256 * k
+            qd = tid + NT * k
             row, cc = qd // (C // 2), qd % (C // 2)
             for x in range(2):
                 sm[2 * qd + x] = data[row * 256 + col0 + 2 * cc + x]
     assert all(v is not None for v in sm)
     regs = {}
     if not inverse:
-        for tid in range(256):
-            a = [sm[tid + 256 * j] for j in range(16)]
+        for tid in range(NT):
+            a = [sm[tid + NT * j] for j in range(16)]
             for T in range(4):
                 ct_level(a, T, tw[(1 << T):(2 << T)], q)
             regs[tid] = a
-        for tid in range(256):
+        for tid in range(NT):
             for j in range(16):
-                sm[tid + 256 * j] = regs[tid][j]
-        for tid in range(256):
+                sm[tid + NT * j] = regs[tid][j]
+        for tid in range(NT):
             c, u = tid % C, tid // C
             a = [sm[(16 * u + j) * C + c] for j in range(16)]
             for T in range(max(SKIP, 0), 4):
@@ -100,20 +101,20 @@ def col_tile(data, logN, tw, q, tile, inverse, post=1):
             for j in range(16):
                 data[(16 * u + j) * 256 + col0 + c] = a[j]
     else:
-        for tid in range(256):
+        for tid in range(NT):
             c, u = tid % C, tid // C
             a = [sm[(16 * u + j) * C + c] for j in range(16)]
             for T in range(3, max(SKIP, 0) - 1, -1):
                 b = (1 << (LOGR1 - 4 + T)) + (u << T)
                 gs_level(a, T, tw[b:b + (1 << T)], q)
             regs[tid] = a
-        for tid in range(256):
+        for tid in range(NT):
             c, u = tid % C, tid // C
             for j in range(16):
                 sm[(16 * u + j) * C + c] = regs[tid][j]
-        for tid in range(256):
+        for tid in range(NT):
             c, u = tid % C, tid // C
-            a = [sm[tid + 256 * j] for j in range(16)]
+            a = [sm[tid + NT * j] for j in range(16)]
             for T in range(3, -1, -1):
                 gs_level(a, T, tw[(1 << T):(2 << T)], q)
             for j in range(16):
@@ -239,26 +240,26 @@ def row_tile(data, logN, blob_all, q, tile, inverse, check_banks=False):
                     data[base + rr * 256 + l16 + 16 * j] = a[j]
 
 
-def forward(x, psi, q, logN):
+def forward(x, psi, q, logN, NT=256):
     nat = natural_table(psi, q, logN)
     rows = permute_row_twiddles(nat, logN)
     d = list(x)
-    C = TILE >> (logN - ROW_LOG)
+    C = (16 * NT) >> (logN - ROW_LOG)
     for tile in range(256 // C):
-        col_tile(d, logN, nat, q, tile, False)
+        col_tile(d, logN, nat, q, tile, False, NT=NT)
     for tile in range((1 << logN) // TILE):
         row_tile(d, logN, rows, q, tile, False, check_banks=(tile == 0))
     return d
 
 
-def inverse(x, psi, q, logN):
+def inverse(x, psi, q, logN, NT=256):
     nat = natural_table(psi, q, logN, inverse=True)
     rows = permute_row_twiddles(nat, logN)
     d = list(x)
-    C = TILE >> (logN - ROW_LOG)
+    C = (16 * NT) >> (logN - ROW_LOG)
     for tile in range((1 << logN) // TILE):
         row_tile(d, logN, rows, q, tile, True, check_banks=(tile == 0))
     ninv = pow(1 << logN, -1, q)
     for tile in range(256 // C):
-        col_tile(d, logN, nat, q, tile, True, post=ninv)
+        col_tile(d, logN, nat, q, tile, True, post=ninv, NT=NT)
     return d
