@@ -11,7 +11,7 @@ in HBM (2*B*36.7 MB of input per GPU, far larger than L2, so no L2 flush is need
 independent ciphertexts sharded across ranks, no data-path collective ("scaling": "weak").
 
 The JSON line also carries: `e2e` (same metric through the host-buffer C-ABI call, H2D/D2H inside the timed
-region), `roofline` (the forward-NTT kernel pair timed alone with CUDA events), `cpu_baseline` (the scalar
+region), `roofline` (the forward-NTT kernel pair timed alone with CUDA events on the batched ModUp launch shape), `cpu_baseline` (the scalar
 oracle port timed on one host core on a bounded sample), `extra` (single-op latencies with L2 flushed,
 hrotate, NTT limbs/s, the reference's published-by-survey simulator figures).
 """
@@ -219,33 +219,46 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    # ---------------- roofline of the dominant kernel: forward NTT (column pass + row pass), timed alone
+    # ---------------- roofline of the dominant kernel pair: forward NTT (column pass + row pass), timed alone on the launch
+    # shape the batched step uses — the ModUp NTT of one chunk: 8 ciphertexts x 115 limbs in ONE launch pair
     peak, peak_src = measured_peaks()
     W_bytes = 8 * N_RING
-    n_limbs = 115  # the ModUp NTT launch of one key switch at (35, 15): the largest NTT launch of the step
+    n_limbs, n_b = 115, 8
     idx = [ctx.ext_mod_idx(L)[i % (L + ALPHA)] for i in range(n_limbs)]
-    bufs = [ctx.uniform(idx, 50 + i) for i in range(4)]  # 4 x 60 MB > L2: every launch reads from HBM
-    dst = ctx.empty(n_limbs, N_RING)
-    for i in range(4):
-        ctx.ntt(bufs[i], idx, out=dst)
+    bufs = [ctx.uniform(idx, 50 + i, lead=(n_b,)) for i in range(2)]  # 2 x 482 MB >> L2: every launch reads from HBM
+    dst = ctx.empty(n_b, n_limbs, N_RING)
+    for i in range(3):
+        ctx.ntt_batch(bufs[i % 2], idx, out=dst)
     torch.cuda.synchronize()
-    reps = 20
+    reps = 10
     e0.record()
     for i in range(reps):
-        ctx.ntt(bufs[i % 4], idx, out=dst)
+        ctx.ntt_batch(bufs[i % 2], idx, out=dst)
     e1.record()
     torch.cuda.synchronize()
     ntt_ms = e0.elapsed_time(e1) / reps
-    ntt_bytes = 2.0 * W_bytes * n_limbs
+    ntt_bytes = 2.0 * W_bytes * n_limbs * n_b
     ntt_gbs = ntt_bytes / (ntt_ms * 1e-3) / 1e9
-    ntt_limbs_per_s = n_limbs / (ntt_ms * 1e-3)
+    ntt_limbs_per_s = n_limbs * n_b / (ntt_ms * 1e-3)
+    # single-ciphertext launch (115 limbs), for the latency-mode figure
+    for i in range(3):
+        ctx.ntt(bufs[i % 2][0], idx, out=dst[0])
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(20):
+        ctx.ntt(bufs[i % 2][i % n_b], idx, out=dst[0])
+    e1.record()
+    torch.cuda.synchronize()
+    ntt1_us_per_limb = e0.elapsed_time(e1) / 20 * 1e3 / n_limbs
+    del bufs, dst
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ntt_traffic.json")))["dram_bytes_per_launch"]
     except Exception:
         pass
 
-    extra = {"ntt_limbs_per_s": ntt_limbs_per_s, "ntt_us_per_limb": ntt_ms * 1e3 / n_limbs, "e2e_matches_device_path": e2e_ok}
+    extra = {"ntt_limbs_per_s": ntt_limbs_per_s, "ntt_us_per_limb": ntt_ms * 1e3 / (n_limbs * n_b),
+             "ntt_us_per_limb_single_ciphertext_launch": ntt1_us_per_limb, "e2e_matches_device_path": e2e_ok}
     if not args.no_extra:
         flush = torch.empty(64 << 20, dtype=torch.int64, device="cuda")  # 512 MiB
 
@@ -299,7 +312,7 @@ def main():
                 "batch_per_gpu_per_step": Be},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
-        "roofline": {"bound": "hbm", "kernel": "ntt_fwd_cols + ntt_fwd_rows (forward NTT, 115 limbs)", "achieved": ntt_gbs,
+        "roofline": {"bound": "hbm", "kernel": "ntt_fwd_cols + ntt_rows (forward NTT pair, 8 ciphertexts x 115 limbs per launch)", "achieved": ntt_gbs,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ntt_gbs / peak, "traffic": traffic,
                      "algorithmic_bytes_per_launch": ntt_bytes},
         "cpu_baseline": cpu,

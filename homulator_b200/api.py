@@ -49,7 +49,7 @@ def lib_path():
 EXPORTS = [
     "hml_ctx_create", "hml_ctx_create_params", "hml_ctx_destroy", "hml_last_error", "hml_last_create_error",
     "hml_ring_degree", "hml_n_moduli", "hml_get_moduli", "hml_get_roots", "hml_dev_alloc", "hml_dev_free", "hml_h2d",
-    "hml_d2h", "hml_sync", "hml_ntt", "hml_intt", "hml_ewe", "hml_automorph", "hml_bconv", "hml_keyswitch", "hml_rescale",
+    "hml_d2h", "hml_sync", "hml_ntt", "hml_intt", "hml_ntt_batch", "hml_intt_batch", "hml_ewe", "hml_automorph", "hml_bconv", "hml_keyswitch", "hml_rescale",
     "hml_hmult", "hml_hrotate", "hml_hadd", "hml_pmult", "hml_padd", "hml_hmult_batch", "hml_hrotate_batch",
     "hml_hmult_host", "hml_hrotate_host", "hml_host_alloc_pinned", "hml_host_free_pinned", "hml_trace_counts",
     "hml_get_counts", "hml_exec_counts_get", "hml_exec_counts_reset", "hml_cli_main",
@@ -83,6 +83,8 @@ def load_library():
     L.hml_get_roots.argtypes = [vp, C.POINTER(u64), u32]
     L.hml_ntt.argtypes = [vp, vp, vp, C.POINTER(u32), u32, vp]
     L.hml_intt.argtypes = [vp, vp, vp, C.POINTER(u32), u32, vp]
+    L.hml_ntt_batch.argtypes = [vp, vp, vp, C.POINTER(u32), u32, u32, vp]
+    L.hml_intt_batch.argtypes = [vp, vp, vp, C.POINTER(u32), u32, u32, vp]
     L.hml_ewe.argtypes = [vp, vp, vp, vp, vp, i32, vp, C.POINTER(u32), u32, vp]
     L.hml_automorph.argtypes = [vp, vp, vp, u64, u32, vp]
     L.hml_bconv.argtypes = [vp, vp, C.POINTER(u32), u32, vp, C.POINTER(u32), u32, vp]
@@ -237,6 +239,16 @@ class Context:
 
     def intt(self, x, mod_idx, out=None):
         return self.ntt(x, mod_idx, out, inverse=True)
+
+    def ntt_batch(self, x, mod_idx, out=None, inverse=False):
+        """x [n_batch][len(mod_idx)][N]: one launch pair for the whole batch (hml_ntt_batch / hml_intt_batch)"""
+        out = self.empty(*x.shape) if out is None else out
+        n = len(mod_idx)
+        nb = x.numel() // (n * self.N)
+        assert x.numel() == nb * n * self.N
+        f = self.lib.hml_intt_batch if inverse else self.lib.hml_ntt_batch
+        self._chk(f(self.h, _ptr(x), _ptr(out), _u32arr(mod_idx), n, nb, self._stream()))
+        return out
 
     def ewe(self, x1, x2, x3, x4, mod_idx, subtract=False, out=None):
         ref = x1 if x1 is not None else x3

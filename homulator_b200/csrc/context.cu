@@ -340,6 +340,38 @@ extern "C" int hml_intt(hml_ctx *ctx, const uint64_t *in, uint64_t *out, const u
   return ntt_api(ctx, true, in, out, mod_idx, n, s);
 }
 
+static int ntt_batch_api(hml_ctx *ctx, bool inverse, const uint64_t *in, uint64_t *out, const uint32_t *mod_idx, uint32_t n_limbs,
+                         uint32_t n_batch, void *stream) {
+  if (!ctx || !in || !out || !mod_idx) return HML_ERR_INVALID;
+  if (n_limbs == 0 || n_batch == 0) return HML_OK;
+  if (n_limbs > NTT_MAX_LIMBS) return fail(ctx, HML_ERR_UNSUPPORTED, "more than 128 limbs per batched transform");
+  for (uint32_t i = 0; i < n_limbs; ++i)
+    if (mod_idx[i] >= ctx->p.n_mod()) return fail(ctx, HML_ERR_INVALID, "modulus index out of range");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t N = ctx->p.N;
+  LimbMap lm;
+  id_map(lm, mod_idx, n_limbs);
+  // the launch's linear work index must stay below 2^31 tiles: chunk the batch
+  const uint32_t per = std::max<uint32_t>(1, 16384 / n_limbs);
+  for (uint32_t b0 = 0; b0 < n_batch; b0 += per) {
+    NttLaunch l{};
+    l.in = (const u64 *)in + (size_t)b0 * n_limbs * N; l.out = (u64 *)out + (size_t)b0 * n_limbs * N;
+    l.in_limb_stride = l.out_limb_stride = N; l.n_limbs = n_limbs; l.n_polys = 1; l.post_scale = nullptr;
+    l.n_batch = std::min(per, n_batch - b0); l.in_batch_stride = l.out_batch_stride = (long long)n_limbs * N;
+    if (inverse) launch_ntt_inverse(ctx->tabs, ctx->p.logN, lm, l, (cudaStream_t)stream);
+    else launch_ntt_forward(ctx->tabs, ctx->p.logN, lm, l, (cudaStream_t)stream);
+    ctx->exec.kernel_launches += ctx->p.logN <= NTT_SMALL_LOG ? 1 : 2;
+  }
+  (inverse ? ctx->exec.intt_limbs : ctx->exec.ntt_limbs) += (uint64_t)n_limbs * n_batch;
+  return check_launch(ctx, inverse ? "intt batch" : "ntt batch");
+}
+extern "C" int hml_ntt_batch(hml_ctx *ctx, const uint64_t *in, uint64_t *out, const uint32_t *mod_idx, uint32_t n, uint32_t nb, void *s) {
+  return ntt_batch_api(ctx, false, in, out, mod_idx, n, nb, s);
+}
+extern "C" int hml_intt_batch(hml_ctx *ctx, const uint64_t *in, uint64_t *out, const uint32_t *mod_idx, uint32_t n, uint32_t nb, void *s) {
+  return ntt_batch_api(ctx, true, in, out, mod_idx, n, nb, s);
+}
+
 extern "C" int hml_ewe(hml_ctx *ctx, const uint64_t *x1, const uint64_t *x2, const uint64_t *x3, const uint64_t *x4,
                        int subtract, uint64_t *out, const uint32_t *mod_idx, uint32_t n_limbs, void *stream) {
   if (!ctx || !out || !mod_idx) return HML_ERR_INVALID;
@@ -830,13 +862,13 @@ extern "C" int hml_rescale(hml_ctx *ctx, uint32_t L, const uint64_t *in, uint64_
 }
 
 // ------------------------------------------------------------------------------------------------ top-level ops
-// Batched ops run HML_BATCH_CHUNK ciphertexts per kernel launch: per-CTA set-up (twiddle staging, conversion matrices,
+// Batched ops run HML_BATCH_CHUNK (default 16) ciphertexts per kernel launch: per-CTA set-up (twiddle staging, conversion matrices,
 // key words) is paid once per chunk instead of once per ciphertext and grids are large enough to hide launch tails.
 static uint32_t batch_chunk() {
   static const uint32_t v = [] {
-    const char *e = getenv("HML_BATCH_CHUNK");  // tuning knob; default 8
-    const int n = e ? atoi(e) : 8;
-    return (uint32_t)std::min(std::max(n, 1), 32);
+    const char *e = getenv("HML_BATCH_CHUNK");  // tuning knob; default 16
+    const int n = e ? atoi(e) : 16;
+    return (uint32_t)std::min(std::max(n, 1), 64);
   }();
   return v;
 }

@@ -1,6 +1,8 @@
 // See ewe.cuh.  All kernels are streaming (HBM-bound) except base conversion (FP64 tensor-core path, pipe bound).
 #include "ewe.cuh"
 
+#include <cstdlib>
+
 namespace hml {
 
 constexpr int EW_THREADS = 256;  // 2 coefficients per thread, 16-byte accesses
@@ -247,39 +249,51 @@ __global__ void __launch_bounds__(512) k_bconv_mma(const ModConst *__restrict__ 
   }
   const double *yl = ys + kq * pitch + rq;  // A[row = lane/4][col = lane%4]
   const int n_ks = n_src_pad >> 2;
-#pragma unroll 2
-  for (int mt = 0; mt < (tm >> 3); ++mt) {
-    double acc[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+  // two m-tiles (16 coefficients) per iteration: six independent accumulator chains keep the tensor pipe fed
+  for (int mt = 0; mt < (tm >> 3); mt += 2) {
+    double acc[2][3][2] = {{{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}}};
     if constexpr (KS > 0) {
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
-        const double af = yl[ks * 4 * pitch + mt * 8];
+        const double af0 = yl[ks * 4 * pitch + mt * 8], af1 = yl[ks * 4 * pitch + mt * 8 + 8];
 #pragma unroll
-        for (int p = 0; p < 3; ++p) dmma884(acc[p][0], acc[p][1], af, bf[ks][p]);
+        for (int p = 0; p < 3; ++p) {
+          dmma884(acc[0][p][0], acc[0][p][1], af0, bf[ks][p]);
+          dmma884(acc[1][p][0], acc[1][p][1], af1, bf[ks][p]);
+        }
       }
     } else {
       for (int ks = 0; ks < n_ks; ++ks) {
-        const double af = yl[ks * 4 * pitch + mt * 8];
+        const double af0 = yl[ks * 4 * pitch + mt * 8], af1 = yl[ks * 4 * pitch + mt * 8 + 8];
 #pragma unroll
-        for (int p = 0; p < 3; ++p) dmma884(acc[p][0], acc[p][1], af, __ldg(bsrc + ks * brow + p));
+        for (int p = 0; p < 3; ++p) {
+          const double b = __ldg(bsrc + ks * brow + p);
+          dmma884(acc[0][p][0], acc[0][p][1], af0, b);
+          dmma884(acc[1][p][0], acc[1][p][1], af1, b);
+        }
         // each term is < 2^36 * 2^12: fold every 16 sources so the exact sums stay below 2^53
         if ((ks & 3) == 3 && ks + 1 < n_ks) {
 #pragma unroll
-          for (int p = 0; p < 3; ++p) {
-            acc[p][0] = reduce_signed(acc[p][0], m0.q, m0.qinv);
-            acc[p][1] = reduce_signed(acc[p][1], m1.q, m1.qinv);
-          }
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+              acc[h][p][0] = reduce_signed(acc[h][p][0], m0.q, m0.qinv);
+              acc[h][p][1] = reduce_signed(acc[h][p][1], m1.q, m1.qinv);
+            }
         }
       }
     }
-    // value = S2*2^24 + S1*2^12 + S0 (mod q), folded top-down; every intermediate is an exact integer < 2^53
-    double v0 = reduce_signed(acc[2][0], m0.q, m0.qinv), v1 = reduce_signed(acc[2][1], m1.q, m1.qinv);
-    v0 = reduce_signed(__fma_rn(v0, 4096.0, acc[1][0]), m0.q, m0.qinv);
-    v1 = reduce_signed(__fma_rn(v1, 4096.0, acc[1][1]), m1.q, m1.qinv);
-    v0 = reduce_signed(__fma_rn(v0, 4096.0, acc[0][0]), m0.q, m0.qinv);
-    v1 = reduce_signed(__fma_rn(v1, 4096.0, acc[0][1]), m1.q, m1.qinv);
-    if (live0) o0[mt * 8] = f64_to_canonical(v0, m0.qi);
-    if (live1) o1[mt * 8] = f64_to_canonical(v1, m1.qi);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      // value = S2*2^24 + S1*2^12 + S0 (mod q), folded top-down; every intermediate is an exact integer < 2^53
+      double v0 = reduce_signed(acc[h][2][0], m0.q, m0.qinv), v1 = reduce_signed(acc[h][2][1], m1.q, m1.qinv);
+      v0 = reduce_signed(__fma_rn(v0, 4096.0, acc[h][1][0]), m0.q, m0.qinv);
+      v1 = reduce_signed(__fma_rn(v1, 4096.0, acc[h][1][1]), m1.q, m1.qinv);
+      v0 = reduce_signed(__fma_rn(v0, 4096.0, acc[h][0][0]), m0.q, m0.qinv);
+      v1 = reduce_signed(__fma_rn(v1, 4096.0, acc[h][0][1]), m1.q, m1.qinv);
+      if (live0) o0[(mt + h) * 8] = f64_to_canonical(v0, m0.qi);
+      if (live1) o1[(mt + h) * 8] = f64_to_canonical(v1, m1.qi);
+    }
   }
 }
 
@@ -301,8 +315,13 @@ static void launch_bconv_t(const ModConst *mc, const LimbMap &src_lm, const Limb
 
 void launch_bconv(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const double *mat, cudaStream_t s) {
   const int n_src_pad = bconv_pad_src(a.n_src), n_dst_pad = bconv_pad_dst(a.n_dst);
-  int tm = n_src_pad <= 16 ? 256 : 64;
-  while (tm > a.N) tm >>= 1;  // tiny rings (tests): N >= 8
+  static const int tm_big = [] {
+    const char *e = getenv("HML_BCONV_TM");  // tuning knob: coefficients per CTA (<= 16 sources)
+    const int v = e ? atoi(e) : 256;
+    return (v == 64 || v == 128 || v == 256) ? v : 256;
+  }();
+  int tm = n_src_pad <= 16 ? tm_big : 64;
+  while (tm > a.N) tm >>= 1;  // tiny rings (tests): N >= 16
   switch (n_src_pad <= 16 ? n_src_pad / 4 : 0) {
     case 1: launch_bconv_t<1>(mc, src_lm, dst_lm, a, mat, n_src_pad, n_dst_pad, tm, s); break;
     case 2: launch_bconv_t<2>(mc, src_lm, dst_lm, a, mat, n_src_pad, n_dst_pad, tm, s); break;

@@ -62,7 +62,7 @@ struct BConvArgs {
 inline int bconv_pad_src(int n_src) { return (n_src + 3) & ~3; }   // k-steps of 4 sources
 inline int bconv_pad_dst(int n_dst) { return (n_dst + 7) & ~7; }   // target blocks of 8 (one warp each); n_dst <= 128
 // Source limb i is read at in + src_lm.pos[i] * N (modulus src_lm.mod[i], used by step 1 only); output limb t is
-// written at out + dst_lm.pos[t] * N with modulus dst_lm.mod[t].  N >= 8.
+// written at out + dst_lm.pos[t] * N with modulus dst_lm.mod[t].  N >= 16.
 void launch_bconv(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const double *mat, cudaStream_t s);
 
 }  // namespace hml

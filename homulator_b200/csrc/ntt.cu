@@ -89,7 +89,7 @@ template <int LOGR1, int NT>
 struct ColCfg {
   static constexpr int R1 = 1 << LOGR1, TILE = 16 * NT, C = TILE / R1, SKIP = 8 - LOGR1, TILES = (1 << NTT_ROW_LOG) / C;
   static constexpr int STAGE_BYTES = TILE * 8 + 2048 + 64;  // tile | R1 twiddles | ModConst (48 B) | post-scale (16 B)
-  static constexpr int MIN_CTAS = NT == 256 ? 2 : 4;
+  static constexpr int MIN_CTAS = NT == 256 ? 3 : 6;
   static_assert(C >= 2 && C * (R1 / 16) == NT, "thread map");
 };
 
@@ -99,19 +99,39 @@ struct ColWork {
   int mi, limb, tile;
 };
 
+// Position of a work item in the (batch, poly, limb, tile) lattice.  A CTA starts at item blockIdx.x and advances by
+// gridDim.x items per step; both are decomposed once, so the per-tile cost is a few adds instead of divisions.
+struct ColPos {
+  int tile, limb, poly, batch;
+};
+__device__ __forceinline__ ColPos col_pos(int wi, int tiles, int n_limbs, int n_polys) {
+  ColPos p;
+  p.tile = wi % tiles; wi /= tiles;
+  p.limb = wi % n_limbs; wi /= n_limbs;
+  p.poly = wi % n_polys; p.batch = wi / n_polys;
+  return p;
+}
+__device__ __forceinline__ void col_advance(ColPos &p, const ColPos &st, int tiles, int n_limbs, int n_polys) {
+  p.tile += st.tile; int c = p.tile >= tiles; p.tile -= c ? tiles : 0;
+  p.limb += st.limb + c; c = p.limb >= n_limbs; p.limb -= c ? n_limbs : 0;
+  p.poly += st.poly + c; c = p.poly >= n_polys; p.poly -= c ? n_polys : 0;
+  p.batch += st.batch + c;
+}
+// next item of this CTA that is not skipped (digit-owned limbs of ModUp); false when the CTA has run out of work
 template <int LOGR1, int NT>
-__device__ __forceinline__ bool col_decode(int wi, const LimbMap &lm, const NttLaunch &l, bool in_is_out, ColWork &w) {
+__device__ __forceinline__ bool col_next(ColPos &p, const ColPos &st, bool first, const LimbMap &lm, const NttLaunch &l, bool in_is_out,
+                                         ColWork &w) {
   using K = ColCfg<LOGR1, NT>;
-  const int y = wi / K::TILES, tile = wi % K::TILES;
-  const int limb = y % l.n_limbs, poly = (y / l.n_limbs) % l.n_polys, batch = y / (l.n_limbs * l.n_polys);
-  if (poly == lm.skip[limb]) return false;
-  const long long slot = lm.pos[limb];
-  w.out = l.out + (long long)batch * l.out_batch_stride + (long long)poly * l.out_poly_stride + slot * l.out_limb_stride + tile * K::C;
+  if (!first) col_advance(p, st, K::TILES, l.n_limbs, l.n_polys);
+  while (p.batch < l.n_batch && p.poly == lm.skip[p.limb]) col_advance(p, st, K::TILES, l.n_limbs, l.n_polys);
+  if (p.batch >= l.n_batch) return false;
+  const long long slot = lm.pos[p.limb];
+  w.out = l.out + (long long)p.batch * l.out_batch_stride + (long long)p.poly * l.out_poly_stride + slot * l.out_limb_stride + p.tile * K::C;
   w.in = in_is_out ? w.out
-                   : l.in + (long long)batch * l.in_batch_stride + (long long)poly * l.in_poly_stride + slot * l.in_limb_stride + tile * K::C;
-  w.mi = lm.mod[limb];
-  w.limb = limb;
-  w.tile = tile;
+                   : l.in + (long long)p.batch * l.in_batch_stride + (long long)p.poly * l.in_poly_stride + slot * l.in_limb_stride + p.tile * K::C;
+  w.mi = lm.mod[p.limb];
+  w.limb = p.limb;
+  w.tile = p.tile;
   return true;
 }
 
@@ -141,16 +161,16 @@ __global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_fwd_col
   const int tid = threadIdx.x, c = tid % K::C, u = tid / K::C;
   const unsigned smem0 = smem_u32(smem);
   ColWork cur, nxt;
-  int wi = blockIdx.x;
-  while (wi < total && !col_decode<LOGR1, NT>(wi, lm, l, false, cur)) wi += gridDim.x;
-  if (wi < total) col_issue<LOGR1, NT>(cur, t.fwd, t.mc, nullptr, logN, smem0);
+  ColPos pos = col_pos(blockIdx.x < total ? blockIdx.x : 0, K::TILES, l.n_limbs, l.n_polys);
+  const ColPos step = col_pos(gridDim.x, K::TILES, l.n_limbs, l.n_polys);
+  bool have = blockIdx.x < total && col_next<LOGR1, NT>(pos, step, true, lm, l, false, cur);
+  if (have) col_issue<LOGR1, NT>(cur, t.fwd, t.mc, nullptr, logN, smem0);
   cp_async_commit();
-  for (int it = 0; wi < total; ++it) {
-    int nwi = wi + gridDim.x;
-    while (nwi < total && !col_decode<LOGR1, NT>(nwi, lm, l, false, nxt)) nwi += gridDim.x;
+  for (int it = 0; have; ++it) {
+    const bool have_next = col_next<LOGR1, NT>(pos, step, false, lm, l, false, nxt);
     cp_async_wait<0>();
     __syncthreads();  // tile `it` has landed for every thread; everybody is done with the other stage
-    if (nwi < total) col_issue<LOGR1, NT>(nxt, t.fwd, t.mc, nullptr, logN, smem0 + ((it + 1) & 1) * K::STAGE_BYTES);
+    if (have_next) col_issue<LOGR1, NT>(nxt, t.fwd, t.mc, nullptr, logN, smem0 + ((it + 1) & 1) * K::STAGE_BYTES);
     cp_async_commit();
     double *data = reinterpret_cast<double *>(smem + (it & 1) * K::STAGE_BYTES);
     const double *tw = data + K::TILE;
@@ -178,7 +198,7 @@ __global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_fwd_col
     double *outd = reinterpret_cast<double *>(cur.out) + c;
 #pragma unroll
     for (int j = 0; j < 16; ++j) outd[(size_t)(16 * u + j) << NTT_ROW_LOG] = a[j];
-    wi = nwi; cur = nxt;
+    have = have_next; cur = nxt;
   }
 }
 
@@ -190,16 +210,16 @@ __global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_inv_col
   const int tid = threadIdx.x, c = tid % K::C, u = tid / K::C;
   const unsigned smem0 = smem_u32(smem);
   ColWork cur, nxt;
-  int wi = blockIdx.x;
-  while (wi < total && !col_decode<LOGR1, NT>(wi, lm, l, true, cur)) wi += gridDim.x;
-  if (wi < total) col_issue<LOGR1, NT>(cur, t.inv, t.mc, l.post_scale, logN, smem0);
+  ColPos pos = col_pos(blockIdx.x < total ? blockIdx.x : 0, K::TILES, l.n_limbs, l.n_polys);
+  const ColPos step = col_pos(gridDim.x, K::TILES, l.n_limbs, l.n_polys);
+  bool have = blockIdx.x < total && col_next<LOGR1, NT>(pos, step, true, lm, l, true, cur);
+  if (have) col_issue<LOGR1, NT>(cur, t.inv, t.mc, l.post_scale, logN, smem0);
   cp_async_commit();
-  for (int it = 0; wi < total; ++it) {
-    int nwi = wi + gridDim.x;
-    while (nwi < total && !col_decode<LOGR1, NT>(nwi, lm, l, true, nxt)) nwi += gridDim.x;
+  for (int it = 0; have; ++it) {
+    const bool have_next = col_next<LOGR1, NT>(pos, step, false, lm, l, true, nxt);
     cp_async_wait<0>();
-    __syncthreads();
-    if (nwi < total) col_issue<LOGR1, NT>(nxt, t.inv, t.mc, l.post_scale, logN, smem0 + ((it + 1) & 1) * K::STAGE_BYTES);
+    __syncthreads();  // tile `it` has landed for every thread; everybody is done with the other stage
+    if (have_next) col_issue<LOGR1, NT>(nxt, t.inv, t.mc, l.post_scale, logN, smem0 + ((it + 1) & 1) * K::STAGE_BYTES);
     cp_async_commit();
     double *data = reinterpret_cast<double *>(smem + (it & 1) * K::STAGE_BYTES);
     const double *tw = data + K::TILE;
@@ -220,16 +240,20 @@ __global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_inv_col
     lds_run<8>(w, tw + 8); gs_level<3>(a, w, q, qinv);
     lds_run<4>(w, tw + 4); gs_level<2>(a, w, q, qinv);
     lds_run<2>(w, tw + 2); gs_level<1>(a, w, q, qinv);
-    lds_run<1>(w, tw + 1); gs_level<0>(a, w, q, qinv);
+    // last level (one twiddle w1 for the whole limb) with the post-scale c folded in: (x + y) * c and (x - y) * (w1 * c)
     double2 sc;
     if (l.post_scale) sc = *reinterpret_cast<const double2 *>(tw + 256 + 6);
     else sc = make_double2(mc.ninv, mc.ninv_q);
+    const double w1c = mulmod_var(tw[1], sc.x, q, qinv);
     const u64 qi = mc.qi;
     u64 *outp = cur.out + tid % K::C;
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-      outp[(size_t)(u + (K::R1 / 16) * j) << NTT_ROW_LOG] = f64_to_canonical(mulmod_const(a[j], sc.x, sc.y, q), qi);
-    wi = nwi; cur = nxt;
+    for (int j = 0; j < 8; ++j) {
+      const double sum = __dadd_rn(a[j], a[j + 8]), dif = __dsub_rn(a[j], a[j + 8]);
+      outp[(size_t)(u + (K::R1 / 16) * j) << NTT_ROW_LOG] = f64_to_canonical(mulmod_const(sum, sc.x, sc.y, q), qi);
+      outp[(size_t)(u + (K::R1 / 16) * (j + 8)) << NTT_ROW_LOG] = f64_to_canonical(mulmod_var(dif, w1c, q, qinv), qi);
+    }
+    have = have_next; cur = nxt;
   }
 }
 
@@ -244,22 +268,23 @@ __global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_inv_col
 constexpr int ROW_TILE_BYTES = NTT_TILE * 8;
 constexpr int ROW_SMEM_BYTES = 3 * ROW_TILE_BYTES;  // twiddle blob + two data stages
 
+// Byte offsets inside a stage, each family = one per-thread base XOR a compile-time constant (+ a constant):
+//   round A, point l + 16*j:                  (pa ^ ((j & 7) << 4)) + 128 * j
+//   round B, chunk of points 16*l + 2m, 2m+1:  pb ^ (m << 4)
+//   output chunk (line 2m + l/8, chunk l%8):  (pc ^ (((2*m) & 7) << 4)) + 256 * m
 struct RowAddr {
-  unsigned xa[8];  // round A: byte offset of point l + 16*j is xa[j & 7] + 128 * j
-  unsigned xb[8];  // round B: byte offset of the chunk holding points 16*l + 2k, 2k+1
-  unsigned xc[8];  // output:  byte offset of chunk (line 2k + l/8, chunk l%8)
+  unsigned pa, pb, pc;
+  __device__ __forceinline__ unsigned A(int j) const { return (pa ^ ((j & 7) << 4)) + 128 * j; }
+  __device__ __forceinline__ unsigned B(int m) const { return pb ^ (m << 4); }
+  __device__ __forceinline__ unsigned C(int m) const { return (pc ^ (((2 * m) & 7) << 4)) + 256 * m; }
 };
 __device__ __forceinline__ RowAddr row_addr(int lane, int warp) {
   RowAddr r;
   const int l = lane & 15, rr = 2 * warp + (lane >> 4);
   const unsigned base = rr * 2048;
-#pragma unroll
-  for (int m = 0; m < 8; ++m) {
-    r.xa[m] = base + ((((l >> 1) ^ m) << 4) | ((l & 1) << 3));
-    r.xb[m] = base + l * 128 + ((m ^ (l & 7)) << 4);
-    const int g = 2 * m + (l >> 3);
-    r.xc[m] = base + g * 128 + (((l & 7) ^ (g & 7)) << 4);
-  }
+  r.pa = base + ((l >> 1) << 4) + ((l & 1) << 3);
+  r.pb = base + l * 128 + ((l & 7) << 4);
+  r.pc = base + (l >> 3) * 128 + (((l & 7) ^ (l >> 3)) << 4);
   return r;
 }
 
@@ -273,12 +298,19 @@ __device__ __forceinline__ void row_issue(const u64 *src_tile, unsigned stage_sm
   }
 }
 
+// Items (ciphertext b, poly p) of one limb, walked with stride gridDim.z in the linear order b * n_polys + p.
+struct RowItem {
+  int b, p;
+};
 struct RowItems {
-  int n_polys, n_items, skip, step;
-  __device__ __forceinline__ int next(int idx) const {
-    idx += step;
-    while (idx < n_items && (idx % n_polys) == skip) idx += step;
-    return idx;
+  int n_polys, n_batch, skip, step;
+  __device__ __forceinline__ bool valid(const RowItem &i) const { return i.b < n_batch; }
+  __device__ __forceinline__ RowItem next(RowItem i) const {
+    do {
+      i.p += step;
+      while (i.p >= n_polys) { i.p -= n_polys; ++i.b; }
+    } while (i.b < n_batch && i.p == skip);
+    return i;
   }
 };
 
@@ -303,44 +335,42 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
   const long long slot = lm.pos[limb];
   const size_t tile_off = (size_t)blockIdx.x * NTT_TILE;
   // forward rows read the raw doubles pass 1 left in `out`; inverse rows read the canonical input words
-  auto src_of = [&](int idx) -> const u64 * {
-    const long long b = idx / l.n_polys, p = idx % l.n_polys;
-    return (INV ? l.in + b * l.in_batch_stride + p * l.in_poly_stride + slot * l.in_limb_stride
-                : l.out + b * l.out_batch_stride + p * l.out_poly_stride + slot * l.out_limb_stride) + tile_off;
+  auto src_of = [&](const RowItem &i) -> const u64 * {
+    return (INV ? l.in + (long long)i.b * l.in_batch_stride + (long long)i.p * l.in_poly_stride + slot * l.in_limb_stride
+                : l.out + (long long)i.b * l.out_batch_stride + (long long)i.p * l.out_poly_stride + slot * l.out_limb_stride) + tile_off;
   };
-  auto dst_of = [&](int idx) -> u64 * {
-    const long long b = idx / l.n_polys, p = idx % l.n_polys;
-    return l.out + b * l.out_batch_stride + p * l.out_poly_stride + slot * l.out_limb_stride + tile_off;
+  auto dst_of = [&](const RowItem &i) -> u64 * {
+    return l.out + (long long)i.b * l.out_batch_stride + (long long)i.p * l.out_poly_stride + slot * l.out_limb_stride + tile_off;
   };
-  RowItems items{l.n_polys, l.n_polys * l.n_batch, lm.skip[limb], (int)gridDim.z};
-  int cur = items.next((int)blockIdx.z - items.step);
-  int nxt = cur < items.n_items ? items.next(cur) : cur;
-  if (cur < items.n_items) row_issue(src_of(cur), data0, lane, warp);
+  const RowItems items{l.n_polys, l.n_batch, lm.skip[limb], (int)gridDim.z};
+  RowItem cur = items.next(RowItem{0, (int)blockIdx.z - (int)gridDim.z});
+  RowItem nxt = items.valid(cur) ? items.next(cur) : cur;
+  if (items.valid(cur)) row_issue(src_of(cur), data0, lane, warp);
   cp_async_commit();
-  if (nxt < items.n_items) row_issue(src_of(nxt), data0 + ROW_TILE_BYTES, lane, warp);
+  if (items.valid(nxt)) row_issue(src_of(nxt), data0 + ROW_TILE_BYTES, lane, warp);
   cp_async_commit();
   mbar_wait(&bar, 0);
   const int l16 = lane & 15, rr = 2 * warp + (lane >> 4);
   const double *tw_a = blob + rr * 16;
-  for (int k = 0; cur < items.n_items; ++k) {
-    const int nn = nxt < items.n_items ? items.next(nxt) : nxt;
+  for (int k = 0; items.valid(cur); ++k) {
+    const RowItem nn = items.valid(nxt) ? items.next(nxt) : nxt;
     cp_async_wait<1>();
     __syncwarp();
     unsigned char *data = smem + ROW_TILE_BYTES + (k & 1) * ROW_TILE_BYTES;
     double a[16], w[8];
     if constexpr (!INV) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) a[j] = *reinterpret_cast<const double *>(data + ad.xa[j & 7] + 128 * j);
+      for (int j = 0; j < 16; ++j) a[j] = *reinterpret_cast<const double *>(data + ad.A(j));
       lds_run<1>(w, tw_a + 1); ct_level<0>(a, w, q, qinv);
       lds_run<2>(w, tw_a + 2); ct_level<1>(a, w, q, qinv);
       lds_run<4>(w, tw_a + 4); ct_level<2>(a, w, q, qinv);
       lds_run<8>(w, tw_a + 8); ct_level<3>(a, w, q, qinv);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) *reinterpret_cast<double *>(data + ad.xa[j & 7] + 128 * j) = a[j];
+      for (int j = 0; j < 16; ++j) *reinterpret_cast<double *>(data + ad.A(j)) = a[j];
       __syncwarp();
 #pragma unroll
       for (int m = 0; m < 8; ++m) {
-        const double2 v = *reinterpret_cast<const double2 *>(data + ad.xb[m]);
+        const double2 v = *reinterpret_cast<const double2 *>(data + ad.B(m));
         a[2 * m] = v.x; a[2 * m + 1] = v.y;
       }
       w[0] = blob[256 + tid]; ct_level<0>(a, w, q, qinv);
@@ -361,21 +391,21 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
           // values are (true - h) mod q (bias planted by the column pass): centred remainder + h is canonical
           const u64 v0 = (u64)__double_as_longlong(reduce_signed(a[2 * m], q, qinv) + hb) & 0x000FFFFFFFFFFFFFull;
           const u64 v1 = (u64)__double_as_longlong(reduce_signed(a[2 * m + 1], q, qinv) + hb) & 0x000FFFFFFFFFFFFFull;
-          *reinterpret_cast<ulonglong2 *>(data + ad.xb[m]) = make_ulonglong2(v0, v1);
+          *reinterpret_cast<ulonglong2 *>(data + ad.B(m)) = make_ulonglong2(v0, v1);
         }
         __syncwarp();
         u64 *outp = dst_of(cur) + (size_t)rr * 256 + (l16 >> 3) * 16 + (l16 & 7) * 2;
 #pragma unroll
         for (int m = 0; m < 8; ++m)
-          *reinterpret_cast<ulonglong2 *>(outp + 32 * m) = *reinterpret_cast<const ulonglong2 *>(data + ad.xc[m]);
+          *reinterpret_cast<ulonglong2 *>(outp + 32 * m) = *reinterpret_cast<const ulonglong2 *>(data + ad.C(m));
       } else {
         // fused epilogue: the raw lazy sums go through the swizzled tile, then every lane handles the 16-byte chunks it
         // will store, so x, z and dst are all accessed 256 B per half-warp
 #pragma unroll
-        for (int m = 0; m < 8; ++m) *reinterpret_cast<double2 *>(data + ad.xb[m]) = make_double2(a[2 * m], a[2 * m + 1]);
+        for (int m = 0; m < 8; ++m) *reinterpret_cast<double2 *>(data + ad.B(m)) = make_double2(a[2 * m], a[2 * m + 1]);
         __syncwarp();
         const NttFuse &f = l.fuse;
-        const long long fb = cur / f.n_c, fc = cur % f.n_c;
+        const long long fb = cur.p / f.n_c, fc = cur.p % f.n_c;  // n_batch == 1 for fused launches
         const size_t off = (size_t)limb * ((size_t)1 << logN) + tile_off + (size_t)rr * 256 + (l16 >> 3) * 16 + (l16 & 7) * 2;
         const u64 *xp = f.x + fc * f.x_c_stride + fb * f.x_b_stride + off;
         const bool has_z = f.z != nullptr && ((f.z_mask >> fc) & 1u);
@@ -391,7 +421,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
           for (int m = 0; m < 8; ++m) zv[m] = __ldg(reinterpret_cast<const ulonglong2 *>(zp + 32 * m));
 #pragma unroll
           for (int m = 0; m < 8; ++m) {
-            const double2 y = *reinterpret_cast<const double2 *>(data + ad.xc[m]);
+            const double2 y = *reinterpret_cast<const double2 *>(data + ad.C(m));
             // z - h rides on the integer -> double conversion: (2^52 | z) - (2^52 + h)
             const double z0 = __longlong_as_double((long long)(zv[m].x | 0x4330000000000000ull)) - hb;
             const double z1 = __longlong_as_double((long long)(zv[m].y | 0x4330000000000000ull)) - hb;
@@ -404,7 +434,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
         } else {
 #pragma unroll
           for (int m = 0; m < 8; ++m) {
-            const double2 y = *reinterpret_cast<const double2 *>(data + ad.xc[m]);
+            const double2 y = *reinterpret_cast<const double2 *>(data + ad.C(m));
             const u64 v0 = f64_to_canonical(mulmod_const(u64_to_f64(xv[m].x) - y.x, cst.x, cst.y, q), mc.qi);
             const u64 v1 = f64_to_canonical(mulmod_const(u64_to_f64(xv[m].y) - y.y, cst.x, cst.y, q), mc.qi);
             *reinterpret_cast<ulonglong2 *>(dp + 32 * m) = make_ulonglong2(v0, v1);
@@ -414,7 +444,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
     } else {
 #pragma unroll
       for (int m = 0; m < 8; ++m) {
-        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(data + ad.xb[m]);
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(data + ad.B(m));
         a[2 * m] = u64_to_f64(v.x); a[2 * m + 1] = u64_to_f64(v.y);
       }
 #pragma unroll
@@ -429,10 +459,10 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
       lds_run<2>(w, blob + 512 + 2 * tid); gs_level<1>(a, w, q, qinv);
       w[0] = blob[256 + tid]; gs_level<0>(a, w, q, qinv);
 #pragma unroll
-      for (int m = 0; m < 8; ++m) *reinterpret_cast<double2 *>(data + ad.xb[m]) = make_double2(a[2 * m], a[2 * m + 1]);
+      for (int m = 0; m < 8; ++m) *reinterpret_cast<double2 *>(data + ad.B(m)) = make_double2(a[2 * m], a[2 * m + 1]);
       __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) a[j] = *reinterpret_cast<const double *>(data + ad.xa[j & 7] + 128 * j);
+      for (int j = 0; j < 16; ++j) a[j] = *reinterpret_cast<const double *>(data + ad.A(j));
       lds_run<8>(w, tw_a + 8); gs_level<3>(a, w, q, qinv);
       lds_run<4>(w, tw_a + 4); gs_level<2>(a, w, q, qinv);
       lds_run<2>(w, tw_a + 2); gs_level<1>(a, w, q, qinv);
@@ -443,7 +473,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
       for (int j = 0; j < 16; ++j) outd[16 * j] = reduce_signed(a[j], q, qinv);
     }
     __syncwarp();  // every lane is done with this stage before it is refilled
-    if (nn < items.n_items) row_issue(src_of(nn), data0 + (k & 1) * ROW_TILE_BYTES, lane, warp);
+    if (items.valid(nn)) row_issue(src_of(nn), data0 + (k & 1) * ROW_TILE_BYTES, lane, warp);
     cp_async_commit();
     cur = nxt; nxt = nn;
   }
@@ -533,9 +563,19 @@ static void allow_smem(KERNEL k, int bytes) {
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
-// items of a row CTA: enough CTAs to fill the machine several times over, but at least ~6 items per twiddle blob
+// items of a row CTA: short CTAs keep the tail of the launch small (a CTA is dispatched whenever a slot frees up, so the
+// launch ends about one CTA-time after the ideal), long CTAs amortise the 32 KB twiddle blob
+static int row_items_target() {
+  static const int v = [] {
+    const char *e = getenv("HML_ROW_ITEMS");  // tuning knob
+    const int n = e ? atoi(e) : 8;
+    return n < 1 ? 1 : n;
+  }();
+  return v;
+}
 static int row_split(int n_items, int ctas_xy) {
-  int z = (n_items + 7) / 8;
+  const int tgt = row_items_target();
+  int z = (n_items + tgt - 1) / tgt;
   while (z > 1 && (long long)ctas_xy * z > 64ll * sm_count()) --z;
   return z < 1 ? 1 : z;
 }

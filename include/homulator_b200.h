@@ -80,6 +80,13 @@ int hml_sync(hml_ctx *ctx, void *stream);
 /* replaces InsGen::GenNTT(ntt=true/false)  (reference src/InsGen.cpp:17-44).  in == out allowed. */
 int hml_ntt(hml_ctx *ctx, const uint64_t *in, uint64_t *out, const uint32_t *mod_idx, uint32_t n_limbs, void *stream);
 int hml_intt(hml_ctx *ctx, const uint64_t *in, uint64_t *out, const uint32_t *mod_idx, uint32_t n_limbs, void *stream);
+/* The same transforms for n_batch polynomials that share one limb list: in / out are [n_batch][n_limbs][N].  This is the
+ * shape the batched ops launch (reference batchCount, src/InsGen.cpp:12): one kernel pair for the whole batch, the per-limb
+ * twiddles staged once per CTA and reused by every polynomial.  n_limbs <= 128. */
+int hml_ntt_batch(hml_ctx *ctx, const uint64_t *in, uint64_t *out, const uint32_t *mod_idx, uint32_t n_limbs, uint32_t n_batch,
+                  void *stream);
+int hml_intt_batch(hml_ctx *ctx, const uint64_t *in, uint64_t *out, const uint32_t *mod_idx, uint32_t n_limbs, uint32_t n_batch,
+                   void *stream);
 
 /* replaces InsGen::GenEWE (reference src/InsGen.cpp:77-125): out = x1*x2 (+|-) x3*x4 mod m per limb.
  * NULL x2/x4: multiplier 1.  NULL x1/x3: that product is absent (the reference's "address 0",

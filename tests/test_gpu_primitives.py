@@ -78,6 +78,22 @@ def test_ntt_repeated_moduli_and_more_than_128_limbs():
         assert np.array_equal(got[k], o.ntt(idx[k], x[k]))
 
 
+@pytest.mark.parametrize("logN,nb", [(8, 3), (13, 5), (16, 9), (16, 1)])
+def test_ntt_batch_matches_oracle(logN, nb):
+    """hml_ntt_batch / hml_intt_batch: one launch pair for [n_batch][n_limbs][N], twiddles reused across the batch"""
+    N = 1 << logN
+    ctx, o = hml.Context(N=N, max_level=4, alpha=2), Oracle(N, 36, 4, 2)
+    idx = [5, 0, 3]
+    x = np.stack([np.stack([uniform_limbs([o.moduli[i]], N, 700 + 10 * b + i)[0] for i in idx]) for b in range(nb)])
+    want = np.stack([np.stack([o.ntt(i, x[b][r]) for r, i in enumerate(idx)]) for b in range(nb)])
+    got = to_host(ctx.ntt_batch(to_dev(x), idx))
+    assert np.array_equal(got, want)
+    assert np.array_equal(to_host(ctx.ntt_batch(to_dev(want), idx, inverse=True)), x)
+    d = to_dev(x)
+    ctx.ntt_batch(d, idx, out=d)  # in place
+    assert np.array_equal(to_host(d), want)
+
+
 @pytest.mark.parametrize("N", [16, 4096, 65536])
 def test_ewe_variants(N):
     ctx, o = hml.Context(N=N, max_level=4, alpha=2), Oracle(N, 36, 4, 2)
