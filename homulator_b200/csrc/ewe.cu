@@ -213,22 +213,29 @@ __global__ void __launch_bounds__(512) k_bconv_mma(const ModConst *__restrict__ 
   const size_t m_base = (size_t)blockIdx.x * tm;
   const u64 *in = a.in + (size_t)blockIdx.y * a.in_batch_stride;
   u64 *out = a.out + (size_t)blockIdx.y * a.out_batch_stride;
-  {  // stage the tile's sources (step 1 applied here when requested), zero the padding rows
-    const int half = tm >> 1;
-    for (int e = threadIdx.x; e < n_src_pad * half; e += blockDim.x) {
-      const int i = e / half, m2 = e - i * half;
-      double y0 = 0.0, y1 = 0.0;
-      if (i < a.n_src) {
-        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(in + (size_t)src_lm.pos[i] * a.N + m_base) + m2);
-        y0 = u64_to_f64(v.x); y1 = u64_to_f64(v.y);
-        if (STEP1) {
+  {  // stage the tile's sources (step 1 applied here when requested), zero the padding rows; four loads in flight per thread
+    const int half = tm >> 1, total = n_src_pad * half;
+    for (int e0 = threadIdx.x; e0 < total; e0 += 4 * blockDim.x) {
+      ulonglong2 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = e0 + k * blockDim.x, i = e / half, m2 = e - i * half;
+        v[k] = make_ulonglong2(0, 0);
+        if (e < total && i < a.n_src) v[k] = __ldg(reinterpret_cast<const ulonglong2 *>(in + (size_t)src_lm.pos[i] * a.N + m_base) + m2);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = e0 + k * blockDim.x, i = e / half, m2 = e - i * half;
+        if (e >= total) break;
+        double y0 = u64_to_f64(v[k].x), y1 = u64_to_f64(v[k].y);
+        if (STEP1 && i < a.n_src) {
           const ModConst m = mc[src_lm.mod[i]];
           const double2 sc = a.step1[i];
           y0 = canonicalize(mulmod_const(y0, sc.x, sc.y, m.q), m.q);
           y1 = canonicalize(mulmod_const(y1, sc.x, sc.y, m.q), m.q);
         }
+        *reinterpret_cast<double2 *>(&ys[i * pitch + 2 * m2]) = make_double2(y0, y1);
       }
-      *reinterpret_cast<double2 *>(&ys[i * pitch + 2 * m2]) = make_double2(y0, y1);
     }
   }
   __syncthreads();

@@ -358,6 +358,14 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
     __syncwarp();
     unsigned char *data = smem + ROW_TILE_BYTES + (k & 1) * ROW_TILE_BYTES;
     double a[16], w[8];
+    if constexpr (FUSE) {
+      // the epilogue's operands (this warp's two rows of x and z, 4 KB each) start their trip to L2 now
+      const NttFuse &f = l.fuse;
+      const long long fb = cur.p / f.n_c, fc = cur.p % f.n_c;
+      const size_t off = (size_t)limb * ((size_t)1 << logN) + tile_off + (size_t)warp * 512 + lane * 16;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(f.x + fc * f.x_c_stride + fb * f.x_b_stride + off));
+      if (f.z != nullptr && ((f.z_mask >> fc) & 1u)) asm volatile("prefetch.global.L2 [%0];" ::"l"(f.z + fc * f.z_c_stride + fb * f.z_b_stride + off));
+    }
     if constexpr (!INV) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) a[j] = *reinterpret_cast<const double *>(data + ad.A(j));

@@ -1,4 +1,7 @@
-"""Profiling driver for the batched path: hmult_batch over one chunk of 8 ciphertext pairs."""
+"""Profiling driver for the batched path: hmult_batch over one chunk of B (default 16) ciphertext pairs.
+
+    python profiles/prof_batch.py [n_warm] [n_prof] [B]
+"""
 import os
 import sys
 
@@ -9,7 +12,8 @@ import homulator_b200 as hml  # noqa: E402
 
 n_warm = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 n_prof = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-L, A, B = 35, 15, 8
+L, A = 35, 15
+B = int(sys.argv[3]) if len(sys.argv) > 3 else 16
 ctx = hml.Context(os.path.join(ROOT, "config", "config_4.cfg"), 45, A)
 q = list(range(L))
 evk = ctx.uniform(ctx.ext_mod_idx(L), 3, lead=(3, 2))
