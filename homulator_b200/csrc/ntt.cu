@@ -607,7 +607,7 @@ static void launch_cols_t(bool inverse, const NttTables &t, int logN, const Limb
 static int col_threads() {
   static const int v = [] {
     const char *e = getenv("HML_COL_NT");  // tuning knob: 128 or 256 threads per column-pass CTA
-    return e && atoi(e) == 256 ? 256 : 128;
+    return e && atoi(e) == 128 ? 128 : 256;
   }();
   return v;
 }
