@@ -150,7 +150,7 @@ extern "C" int hml_ctx_create(const char *cfg_path, uint32_t max_level, uint32_t
 static void free_level(LevelConsts &lc) {
   cudaFree(lc.modup_scale); cudaFree(lc.moddown_scale); cudaFree(lc.pinv); cudaFree(lc.qlinv);
   for (auto &u : lc.up) cudaFree(u.d_mat);
-  cudaFree(lc.down.d_mat);
+  cudaFree(lc.down.d_mat); cudaFree(lc.merged_rest.d_mat); cudaFree(lc.merged_last.d_mat);
 }
 
 extern "C" void hml_ctx_destroy(hml_ctx *ctx) {
@@ -292,6 +292,42 @@ static int get_level(hml_ctx *ctx, uint32_t L, LevelConsts **out) {
     if ((rc = prepare_bconv(ctx, bt, dst, lc.down))) return rc;
     if ((rc = upload(ctx, sc, &lc.moddown_scale))) return rc;
     if ((rc = upload(ctx, pinv, &lc.pinv))) return rc;
+  }
+  // ---- hmult: ModDown merged with Rescale (matrices with P^-1 folded in and a unit row for the extra source)
+  if (L >= 2) {
+    std::vector<uint32_t> src, dst;
+    for (uint32_t j = 0; j < A; ++j) src.push_back(p.max_level + j);
+    for (uint32_t i = 0; i < L; ++i) dst.push_back(i);
+    BConvTable bt;
+    make_bconv_table(p, src, dst, bt);
+    std::vector<u64> pinv_i(L);
+    for (uint32_t i = 0; i < L; ++i) {
+      const u64 q = p.mod[i];
+      u64 P = 1;
+      for (uint32_t j = 0; j < A; ++j) P = h_mulmod(P, p.mod[p.max_level + j] % q, q);
+      pinv_i[i] = h_invmod(P, q);
+    }
+    clear_map(lc.merged_src); clear_map(lc.last_lm);
+    for (uint32_t j = 0; j < A; ++j) { lc.merged_src.mod[j] = p.max_level + j; lc.merged_src.pos[j] = L + j; }
+    lc.merged_src.mod[A] = L - 1; lc.merged_src.pos[A] = E;  // the extra source lives in slot E of the accumulator
+    lc.last_lm.mod[0] = L - 1; lc.last_lm.pos[0] = 0;
+    BConvTable rest, last;
+    rest.src = src; rest.src.push_back(L - 1); last.src = rest.src;
+    for (uint32_t i = 0; i + 1 < L; ++i) rest.dst.push_back(i);
+    last.dst.push_back(L - 1);
+    const uint32_t nr = L - 1;
+    rest.hat.assign((size_t)(A + 1) * nr, 0); last.hat.assign(A + 1, 0);
+    for (uint32_t j = 0; j < A; ++j) {
+      for (uint32_t i = 0; i < nr; ++i) rest.hat[(size_t)j * nr + i] = h_mulmod(bt.hat[(size_t)j * L + i], pinv_i[i], p.mod[i]);
+      const u64 ql = p.mod[L - 1], t = h_mulmod(bt.hat[(size_t)j * L + L - 1], pinv_i[L - 1], ql);
+      last.hat[j] = t ? ql - t : 0;  // minus: r = slot_E - v * P^-1
+    }
+    for (uint32_t i = 0; i < nr; ++i) rest.hat[(size_t)A * nr + i] = 1;
+    last.hat[A] = 1;
+    std::vector<uint32_t> rest_pos(nr), last_pos(1, E);
+    for (uint32_t i = 0; i < nr; ++i) rest_pos[i] = i;
+    if ((rc = prepare_bconv(ctx, rest, rest_pos, lc.merged_rest))) return rc;
+    if ((rc = prepare_bconv(ctx, last, last_pos, lc.merged_last))) return rc;
   }
   // ---- Rescale
   {
@@ -455,20 +491,13 @@ struct BatchOut {
   long long stride;
 };
 
-// nb independent key switches sharing one key, one kernel launch per stage:
-// d[b] [L][N] -> out_c[b] = KS_c(d[b]) (+ add_c[b]).  `ws` must hold nb * ks_ws_words().
-static int ks_run(hml_ctx *ctx, uint32_t L, uint32_t nb, BatchPtr d, const u64 *evk, uint32_t evk_q_limbs, BatchOut out0,
-                  BatchOut out1, BatchPtr add0, BatchPtr add1, u64 *ws, cudaStream_t s) {
+// K1..K7: ModUp (INTT, base conversion, NTT), inner product with the key, INTT (+ step-1 scaling) of the P-limbs of both
+// accumulators.  Buffers: yb [nb][L] | ext [nb][beta][E] | acc [nb][2][AL] with AL >= E limbs per accumulator.
+static int ks_front(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d, const u64 *evk, uint32_t evk_q_limbs, u64 *yb,
+                    u64 *ext, u64 *acc, uint32_t AL, cudaStream_t s) {
   const Params &p = ctx->p;
-  if (evk_q_limbs < L || evk_q_limbs > p.max_level) return fail(ctx, HML_ERR_INVALID, "evk_q_limbs must be in [L, maxLevel]");
-  LevelConsts *lc;
-  int rc = get_level(ctx, L, &lc);
-  if (rc) return rc;
   const size_t N = p.N;
   const uint32_t A = p.alpha, E = L + A, beta = lc->beta;
-  if (beta > 8) return fail(ctx, HML_ERR_UNSUPPORTED, "more than 8 key-switch digits (ceil(L/alpha) > 8)");
-  // workspace, every buffer batch-major: yb [nb][L] | ext [nb][beta][E] | acc [nb][2][E] | vb [nb][2][L]  (limbs of N words)
-  u64 *yb = ws, *ext = yb + (size_t)nb * L * N, *acc = ext + (size_t)nb * beta * E * N, *vb = acc + (size_t)nb * 2 * E * N;
   const int logN = p.logN, npass = logN <= NTT_SMALL_LOG ? 1 : 2;
   // K1 + K2 (reference :63-135): INTT of the input, digit scaling folded into the N^-1 multiply
   {
@@ -502,19 +531,39 @@ static int ks_run(hml_ctx *ctx, uint32_t L, uint32_t nb, BatchPtr d, const u64 *
     for (uint32_t e = 0; e < E; ++e) ip.pos[e] = (uint16_t)(e < L ? e : evk_q_limbs + (e - L));
     InnerArgs a{};
     a.d = d.ptr; a.ext = ext; a.evk = evk; a.acc = acc; a.N = N; a.n_ext = E; a.beta = beta; a.evk_limbs = evk_q_limbs + A;
-    a.n_batch = nb; a.d_batch_stride = d.stride; a.ext_batch_stride = (long long)beta * E * N; a.acc_batch_stride = 2ll * E * N;
+    a.n_batch = nb; a.d_batch_stride = d.stride; a.ext_batch_stride = (long long)beta * E * N; a.acc_batch_stride = 2ll * AL * N;
+    a.acc_comp_stride = (long long)AL * N;
     launch_inner_product(ctx->mc, ip, a, s);
     ctx->exec.ewe_limbs += 2ull * nb * E * beta; ctx->exec.kernel_launches++;
   }
   // K6 + K7 (reference :417-487): INTT of the P-limbs of both accumulators, in place, BConv step 1 folded in
   {
     NttLaunch l{};
-    l.in = acc; l.out = acc; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)E * N;
-    l.n_limbs = A; l.n_polys = 2 * nb; l.post_scale = lc->moddown_scale;  // acc is [nb][2][E][N]: uniform poly stride
+    l.in = acc; l.out = acc; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)AL * N;
+    l.n_limbs = A; l.n_polys = 2 * nb; l.post_scale = lc->moddown_scale;  // acc is [nb][2][AL][N]: uniform poly stride
     l.n_batch = 1;
     launch_ntt_inverse(ctx->tabs, logN, lc->p_lm, l, s);
     ctx->exec.intt_limbs += 2ull * nb * A; ctx->exec.kernel_launches += npass;
   }
+  return HML_OK;
+}
+
+// nb independent key switches sharing one key, one kernel launch per stage:
+// d[b] [L][N] -> out_c[b] = KS_c(d[b]) (+ add_c[b]).  `ws` must hold nb * ks_ws_words().
+static int ks_run(hml_ctx *ctx, uint32_t L, uint32_t nb, BatchPtr d, const u64 *evk, uint32_t evk_q_limbs, BatchOut out0,
+                  BatchOut out1, BatchPtr add0, BatchPtr add1, u64 *ws, cudaStream_t s) {
+  const Params &p = ctx->p;
+  if (evk_q_limbs < L || evk_q_limbs > p.max_level) return fail(ctx, HML_ERR_INVALID, "evk_q_limbs must be in [L, maxLevel]");
+  LevelConsts *lc;
+  int rc = get_level(ctx, L, &lc);
+  if (rc) return rc;
+  const size_t N = p.N;
+  const uint32_t A = p.alpha, E = L + A, beta = lc->beta;
+  if (beta > 8) return fail(ctx, HML_ERR_UNSUPPORTED, "more than 8 key-switch digits (ceil(L/alpha) > 8)");
+  // workspace, every buffer batch-major: yb [nb][L] | ext [nb][beta][E] | acc [nb][2][E] | vb [nb][2][L]  (limbs of N words)
+  u64 *yb = ws, *ext = yb + (size_t)nb * L * N, *acc = ext + (size_t)nb * beta * E * N, *vb = acc + (size_t)nb * 2 * E * N;
+  const int logN = p.logN, npass = logN <= NTT_SMALL_LOG ? 1 : 2;
+  if ((rc = ks_front(ctx, lc, L, nb, d, evk, evk_q_limbs, yb, ext, acc, E, s))) return rc;
   // K8 (reference :489-519): P -> Q_L
   {
     BConvArgs a{};
@@ -879,17 +928,81 @@ static size_t hmult_ws_words(const Params &p, uint32_t L, uint32_t nb) {
 }
 
 // nb ciphertext pairs [nb][2][L][N] -> [nb][2][L-1][N]
+//
+// Two-pass rings merge ModDown with Rescale.  With u = d + acc_Q * P^-1 (evaluation form) and v = BConv(z; P -> Q)
+// (coefficient form), the textbook sequence is  c = u - NTT(v) * P^-1,  r = INTT(c[L-1]),
+// out[l] = (c[l] - NTT_l([r]_{q_l})) * q_{L-1}^-1.  Every step is exact arithmetic mod q_l and the NTT is linear, so
+//   r      = INTT_{L-1}(u[L-1]) - v[L-1] * P^-1                      (no forward transform of limb L-1 at all)
+//   out[l] = (u[l] - NTT_l(v_l * P^-1 + [r]_{q_l})) * q_{L-1}^-1      (ONE forward transform per output limb instead of two)
+// yields bit-identical residues with 2(L-1) forward transforms instead of 2L + 2(L-1).  v_l * P^-1 + [r]_{q_l} comes
+// straight out of the base conversion: P^-1 is folded into the matrix on the host and r rides in the otherwise padded
+// 16th source row with matrix entry 1 (exact: it only adds one term < 2^36 to the 16-term sums).
 static int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, const u64 *ct_b, const u64 *evk, uint32_t evk_q_limbs,
                      u64 *ct_out, cudaStream_t s) {
-  const size_t N = ctx->p.N, PL = N * L;
+  const Params &p = ctx->p;
+  const size_t N = p.N, PL = N * L;
   // d0 | d1 | d2 each [nb][L][N], cb [nb][2][L][N], then the key-switch / rescale workspace
-  u64 *d0 = ctx->ws, *d1 = d0 + nb * PL, *d2 = d1 + nb * PL, *cb = d2 + nb * PL, *rest = cb + 2 * nb * PL;
+  u64 *d0 = ctx->ws, *d1 = d0 + nb * PL, *d2 = d1 + nb * PL;
   launch_tensor3(ctx->mc, (int)N, (int)L, ct_a, ct_a + PL, ct_b, ct_b + PL, d0, d1, d2, (int)nb, (long long)(2 * PL), (long long)PL, s);  // reference :592-739
   ctx->exec.ewe_limbs += 3ull * nb * L; ctx->exec.kernel_launches++;
-  int rc = ks_run(ctx, L, nb, {d2, (long long)PL}, evk, evk_q_limbs, {cb, (long long)(2 * PL)}, {cb + PL, (long long)(2 * PL)}, {d0, (long long)PL},
-                  {d1, (long long)PL}, rest, s);
+  if (p.logN <= NTT_SMALL_LOG) {  // single-pass rings: the textbook sequence
+    u64 *cb = d2 + nb * PL, *rest = cb + 2 * nb * PL;
+    int rc = ks_run(ctx, L, nb, {d2, (long long)PL}, evk, evk_q_limbs, {cb, (long long)(2 * PL)}, {cb + PL, (long long)(2 * PL)}, {d0, (long long)PL},
+                    {d1, (long long)PL}, rest, s);
+    if (rc) return rc;
+    return rescale_run(ctx, L, cb, (long long)PL, 2 * nb, ct_out, (long long)(L - 1) * N, rest, s);
+  }
+  if (evk_q_limbs < L || evk_q_limbs > p.max_level) return fail(ctx, HML_ERR_INVALID, "evk_q_limbs must be in [L, maxLevel]");
+  LevelConsts *lc;
+  int rc = get_level(ctx, L, &lc);
   if (rc) return rc;
-  return rescale_run(ctx, L, cb, (long long)PL, 2 * nb, ct_out, (long long)(L - 1) * N, rest, s);
+  const uint32_t A = p.alpha, E = L + A, AL = E + 1, beta = lc->beta;
+  if (beta > 8) return fail(ctx, HML_ERR_UNSUPPORTED, "more than 8 key-switch digits (ceil(L/alpha) > 8)");
+  // yb [nb][L] | ext [nb][beta][E] | acc [nb][2][E+1] | wb [nb][2][L-1]; yb is free again after ModUp: ul [nb][2][N] reuses it
+  u64 *yb = d2 + nb * PL, *ext = yb + (size_t)nb * L * N, *acc = ext + (size_t)nb * beta * E * N, *wb = acc + (size_t)nb * 2 * AL * N;
+  u64 *ul = yb;
+  if ((rc = ks_front(ctx, lc, L, nb, {d2, (long long)PL}, evk, evk_q_limbs, yb, ext, acc, AL, s))) return rc;
+  const int logN = p.logN;
+  for (int c = 0; c < 2; ++c) {  // u[L-1] = d_c[L-1] + acc_c[L-1] * P^-1
+    SubMulArgs a{};
+    a.x = acc + ((size_t)c * AL + (L - 1)) * N; a.x_poly_stride = 2ll * AL * N;
+    a.y = nullptr;
+    a.z = (c ? d1 : d0) + (size_t)(L - 1) * N; a.z_poly_stride = (long long)PL;
+    a.out = ul + (size_t)c * N; a.out_poly_stride = 2ll * N;
+    a.cst = lc->pinv + (L - 1); a.N = N; a.n_limbs = 1; a.n_polys = nb;
+    launch_sub_mul_add(ctx->mc, lc->last_lm, a, s);
+    ctx->exec.ewe_limbs += 2ull * nb; ctx->exec.kernel_launches++;
+  }
+  {  // INTT_{L-1}(u[L-1]) -> slot E of each accumulator (reference Rescale INTT :766-805)
+    NttLaunch l{};
+    l.n_batch = 1;
+    l.in = ul; l.out = acc + (size_t)E * N; l.in_limb_stride = l.out_limb_stride = N;
+    l.in_poly_stride = N; l.out_poly_stride = (long long)AL * N; l.n_limbs = 1; l.n_polys = 2 * nb;
+    launch_ntt_inverse(ctx->tabs, logN, lc->last_lm, l, s);
+    ctx->exec.intt_limbs += 2ull * nb; ctx->exec.kernel_launches += 2;
+  }
+  {  // r = slot_E - v[L-1] * P^-1, in place; then w_l = v_l * P^-1 + [r]_{q_l}, l < L-1 (reference K8 :489-519)
+    BConvArgs a{};
+    a.in = acc; a.out = acc; a.in_batch_stride = a.out_batch_stride = (long long)AL * N;
+    a.step1 = nullptr; a.N = N; a.n_batches = 2 * nb;
+    run_bconv(ctx, lc->merged_last, lc->merged_src, a, s);
+    a.out = wb; a.out_batch_stride = (long long)(L - 1) * N;
+    run_bconv(ctx, lc->merged_rest, lc->merged_src, a, s);
+  }
+  {  // out[l] = ((acc[l] * P^-1 + d[l]) - NTT_l(w_l)) * q_{L-1}^-1  (K9, K10, HMULT add and Rescale in one transform)
+    NttLaunch l{};
+    l.in = wb; l.out = wb; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)(L - 1) * N;
+    l.n_limbs = L - 1; l.n_polys = 2 * nb; l.n_batch = 1;
+    NttFuse &f = l.fuse;
+    f.x = acc; f.x_c_stride = (long long)AL * N; f.x_b_stride = 2ll * AL * N;
+    f.z = d0; f.z_c_stride = (long long)(d1 - d0); f.z_b_stride = (long long)PL; f.z_mask = 3;
+    f.dst = ct_out; f.dst_c_stride = (long long)(L - 1) * N; f.dst_b_stride = 2ll * (L - 1) * N;
+    f.cst = lc->pinv; f.cst2 = lc->qlinv; f.n_c = 2;
+    launch_ntt_forward(ctx->tabs, logN, lc->q_lm, l, s);
+    ctx->exec.ntt_limbs += 2ull * nb * (L - 1); ctx->exec.kernel_launches += 2;
+    ctx->exec.ewe_limbs += 2ull * nb * 4 * (L - 1);
+  }
+  return check_launch(ctx, "hmult");
 }
 
 extern "C" int hml_hmult(hml_ctx *ctx, uint32_t L, const uint64_t *ct_a, const uint64_t *ct_b, const uint64_t *evk,

@@ -1,6 +1,7 @@
 // See ewe.cuh.  All kernels are streaming (HBM-bound) except base conversion (FP64 tensor-core path, pipe bound).
 #include "ewe.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace hml {
@@ -131,8 +132,9 @@ __global__ void __launch_bounds__(EW_THREADS) k_inner(const ModConst *__restrict
         s10 += mulmod_var(t0, k[j][1][0], m.q, m.qinv);
         s11 += mulmod_var(t1, k[j][1][1], m.q, m.qinv);
       }
-    st2(acc, ((size_t)0 * a.n_ext + e) * n2 + i2, finish(s00, m), finish(s01, m));
-    st2(acc, ((size_t)1 * a.n_ext + e) * n2 + i2, finish(s10, m), finish(s11, m));
+    const size_t comp2 = (a.acc_comp_stride ? (size_t)a.acc_comp_stride : (size_t)a.n_ext * a.N) / 2;
+    st2(acc, (size_t)e * n2 + i2, finish(s00, m), finish(s01, m));
+    st2(acc, comp2 + (size_t)e * n2 + i2, finish(s10, m), finish(s11, m));
   }
 }
 
@@ -153,7 +155,8 @@ __global__ void __launch_bounds__(EW_THREADS) k_sub_mul_add(const ModConst *__re
   const ModConst m = mc[lm.mod[limb]];
   const double2 c = a.cst[limb];
   const size_t o = (size_t)limb * (a.N / 2) + i2;
-  const ulonglong2 x = ld2(a.x + poly * a.x_poly_stride, o), y = ld2(a.y + poly * a.y_poly_stride, o);
+  const ulonglong2 x = ld2(a.x + poly * a.x_poly_stride, o);
+  const ulonglong2 y = a.y ? ld2(a.y + poly * a.y_poly_stride, o) : make_ulonglong2(0, 0);
   double r0 = mulmod_const(u64_to_f64(x.x) - u64_to_f64(y.x), c.x, c.y, m.q);
   double r1 = mulmod_const(u64_to_f64(x.y) - u64_to_f64(y.y), c.x, c.y, m.q);
   if (a.z) {
@@ -239,6 +242,7 @@ __global__ void __launch_bounds__(512) k_bconv_mma(const ModConst *__restrict__ 
     }
   }
   __syncthreads();
+  if (tb * 8 >= n_dst_pad) return;  // staging helpers of a launch with fewer than four target blocks
   const int kq = lane & 3, rq = lane >> 2;
   const int t0 = tb * 8 + 2 * kq, t1 = t0 + 1;
   const bool live0 = t0 < a.n_dst, live1 = t1 < a.n_dst;
@@ -308,7 +312,7 @@ template <int KS>
 static void launch_bconv_t(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const double *mat,
                            int n_src_pad, int n_dst_pad, int tm, cudaStream_t s) {
   const dim3 grid(a.N / tm, a.n_batches);
-  const int threads = 32 * (n_dst_pad / 8);
+  const int threads = std::max(128, 32 * (n_dst_pad / 8));  // at least four warps so that staging has loads in flight
   const size_t smem = (size_t)n_src_pad * (tm + 4) * sizeof(double);
   static bool once = [] {
     cudaFuncSetAttribute(k_bconv_mma<KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 68 * 8);

@@ -30,13 +30,14 @@ struct InnerArgs {
   int N, n_ext, beta, evk_limbs;   // beta <= 8
   int n_batch;                     // ciphertexts sharing the key: d / ext / acc advance by the strides below
   long long d_batch_stride, ext_batch_stride, acc_batch_stride;
+  long long acc_comp_stride;       // words between the two accumulators of a ciphertext (0 = n_ext * N)
 };
 void launch_inner_product(const ModConst *mc, const LimbMap &lm, const InnerArgs &a, cudaStream_t s);
 
 // out = (x - y) * c (+ z) per limb:  ModDownSub (+ HMULT add)  reference src/Operation.cpp:548-590, :967-1005
 // and Rescale sub+mul  reference src/Operation.cpp:825-911.  cst[limb] = (c, RN(c/q)).  n_polys via strides.
 struct SubMulArgs {
-  const u64 *x, *y, *z;   // z may be null
+  const u64 *x, *y, *z;   // y and z may be null (y = 0: out = x * c + z)
   u64 *out;
   long long x_poly_stride, y_poly_stride, z_poly_stride, out_poly_stride;
   const double2 *cst;     // [n_limbs]

@@ -423,7 +423,21 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
         ulonglong2 xv[8];
 #pragma unroll
         for (int m = 0; m < 8; ++m) xv[m] = __ldg(reinterpret_cast<const ulonglong2 *>(xp + 32 * m));
-        if (has_z) {
+        if (f.cst2 != nullptr) {  // ((x * c + z) - y) * c2: z is mandatory
+          const double2 cst2 = f.cst2[limb];
+          ulonglong2 zv[8];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) zv[m] = __ldg(reinterpret_cast<const ulonglong2 *>(zp + 32 * m));
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            const double2 y = *reinterpret_cast<const double2 *>(data + ad.C(m));
+            const double u0 = mulmod_const(u64_to_f64(xv[m].x), cst.x, cst.y, q) + u64_to_f64(zv[m].x) - y.x;
+            const double u1 = mulmod_const(u64_to_f64(xv[m].y), cst.x, cst.y, q) + u64_to_f64(zv[m].y) - y.y;
+            const u64 v0 = f64_to_canonical(mulmod_const(u0, cst2.x, cst2.y, q), mc.qi);
+            const u64 v1 = f64_to_canonical(mulmod_const(u1, cst2.x, cst2.y, q), mc.qi);
+            *reinterpret_cast<ulonglong2 *>(dp + 32 * m) = make_ulonglong2(v0, v1);
+          }
+        } else if (has_z) {
           ulonglong2 zv[8];
 #pragma unroll
           for (int m = 0; m < 8; ++m) zv[m] = __ldg(reinterpret_cast<const ulonglong2 *>(zp + 32 * m));

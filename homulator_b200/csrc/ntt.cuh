@@ -56,7 +56,8 @@ void ntt_permute_row_twiddles(const double *nat, int logN, double *out);
 
 // Optional fused epilogue of a FORWARD transform (ModDownSub + add, reference src/Operation.cpp:548-590, :967-1005, and
 // Rescale sub + mul, :825-911): instead of storing y = NTT(in) the row pass writes
-//   dst = (x - y) * cst[limb] (+ z)   mod q, canonical
+//   dst = (x - y) * cst[limb] (+ z)              mod q, canonical,      or, when cst2 is given (merged ModDown + Rescale
+//   dst = ((x * cst[limb] + z) - y) * cst2[limb]  mod q, canonical       of hmult, see context.cu),
 // so the transform's output never round-trips HBM.  Items are (b, c) = (idx / n_c, idx % n_c) with idx the launch's
 // poly index (n_batch must be 1); every operand is addressed as base + c * c_stride + b * b_stride + limb * N.
 struct NttFuse {
@@ -64,6 +65,7 @@ struct NttFuse {
   u64 *dst;
   long long x_c_stride, x_b_stride, z_c_stride, z_b_stride, dst_c_stride, dst_b_stride;
   const double2 *cst;           // [n_limbs] (c, RN(c/q))
+  const double2 *cst2;          // [n_limbs] or null
   int n_c;
   unsigned z_mask;              // z is added for component c iff bit c is set
 };
