@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "launch.h"
 #include "planner.h"
 
 using namespace hml;
@@ -911,12 +912,12 @@ extern "C" int hml_rescale(hml_ctx *ctx, uint32_t L, const uint64_t *in, uint64_
 }
 
 // ------------------------------------------------------------------------------------------------ top-level ops
-// Batched ops run HML_BATCH_CHUNK (default 16) ciphertexts per kernel launch: per-CTA set-up (twiddle staging, conversion matrices,
+// Batched ops run HML_BATCH_CHUNK (default 32) ciphertexts per kernel launch: per-CTA set-up (twiddle staging, conversion matrices,
 // key words) is paid once per chunk instead of once per ciphertext and grids are large enough to hide launch tails.
 static uint32_t batch_chunk() {
   static const uint32_t v = [] {
-    const char *e = getenv("HML_BATCH_CHUNK");  // tuning knob; default 16
-    const int n = e ? atoi(e) : 16;
+    const char *e = getenv("HML_BATCH_CHUNK");  // tuning knob; default 32
+    const int n = e ? atoi(e) : 32;
     return (uint32_t)std::min(std::max(n, 1), 64);
   }();
   return v;
@@ -939,6 +940,7 @@ static size_t hmult_ws_words(const Params &p, uint32_t L, uint32_t nb) {
 // 16th source row with matrix entry 1 (exact: it only adds one term < 2^36 to the 16-term sums).
 static int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, const u64 *ct_b, const u64 *evk, uint32_t evk_q_limbs,
                      u64 *ct_out, cudaStream_t s) {
+  const PdlScope pdl(nb <= 2);
   const Params &p = ctx->p;
   const size_t N = p.N, PL = N * L;
   // d0 | d1 | d2 each [nb][L][N], cb [nb][2][L][N], then the key-switch / rescale workspace
@@ -1020,6 +1022,7 @@ static size_t hrot_ws_words(const Params &p, uint32_t L, uint32_t nb) { return (
 // nb ciphertexts [nb][2][L][N] -> [nb][2][L][N]
 static int hrot_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct, const u64 *rk, uint32_t evk_q_limbs, u64 g, u64 *ct_out,
                     cudaStream_t s) {
+  const PdlScope pdl(nb <= 2);
   const size_t N = ctx->p.N, PL = N * L;
   u64 *sb = ctx->ws, *rest = sb + 2 * nb * PL;  // sb [nb][2][L][N]
   launch_automorph(ctx->p.logN, 2 * L * nb, ct, sb, g, s);  // reference :1302-1319

@@ -1,5 +1,6 @@
 // See ewe.cuh.  All kernels are streaming (HBM-bound) except base conversion (FP64 tensor-core path, pipe bound).
 #include "ewe.cuh"
+#include "launch.h"
 
 #include <algorithm>
 #include <cstdlib>
@@ -17,6 +18,8 @@ static inline dim3 ew_grid(int N, int ny, int nz = 1) { return dim3((N / 2 + EW_
 // ------------------------------------------------------------------------------------------------ generic EWE
 __global__ void __launch_bounds__(EW_THREADS) k_ewe(const ModConst *__restrict__ mc, LimbMap lm, int N, const u64 *x1,
                                                     const u64 *x2, const u64 *x3, const u64 *x4, int subtract, u64 *out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i2 = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i2 >= N / 2) return;
   const int limb = blockIdx.y;
@@ -47,13 +50,15 @@ __global__ void __launch_bounds__(EW_THREADS) k_ewe(const ModConst *__restrict__
 
 void launch_ewe(const ModConst *mc, const LimbMap &lm, int N, int n_limbs, const u64 *x1, const u64 *x2, const u64 *x3,
                 const u64 *x4, int subtract, u64 *out, cudaStream_t s) {
-  k_ewe<<<ew_grid(N, n_limbs), EW_THREADS, 0, s>>>(mc, lm, N, x1, x2, x3, x4, subtract, out);
+  launch_pdl(k_ewe, ew_grid(N, n_limbs), EW_THREADS, 0, s, mc, lm, N, x1, x2, x3, x4, subtract, out);
 }
 
 // ------------------------------------------------------------------------------------------------ tensor product
 __global__ void __launch_bounds__(EW_THREADS) k_tensor3(const ModConst *__restrict__ mc, int N, const u64 *a0, const u64 *a1,
                                                         const u64 *b0, const u64 *b1, u64 *d0, u64 *d1, u64 *d2,
                                                         long long in_stride, long long out_stride) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i2 = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i2 >= N / 2) return;
   const int limb = blockIdx.y;  // limbs 0..L-1 are moduli q_0..q_{L-1}
@@ -78,7 +83,7 @@ __global__ void __launch_bounds__(EW_THREADS) k_tensor3(const ModConst *__restri
 
 void launch_tensor3(const ModConst *mc, int N, int L, const u64 *a0, const u64 *a1, const u64 *b0, const u64 *b1, u64 *d0,
                     u64 *d1, u64 *d2, int n_batch, long long in_stride, long long out_stride, cudaStream_t s) {
-  k_tensor3<<<ew_grid(N, L, n_batch), EW_THREADS, 0, s>>>(mc, N, a0, a1, b0, b1, d0, d1, d2, in_stride, out_stride);
+  launch_pdl(k_tensor3, ew_grid(N, L, n_batch), EW_THREADS, 0, s, mc, N, a0, a1, b0, b1, d0, d1, d2, in_stride, out_stride);
 }
 
 // ------------------------------------------------------------------------------------------------ key-switch inner product
@@ -86,6 +91,8 @@ void launch_tensor3(const ModConst *mc, int N, int L, const u64 *a0, const u64 *
 // (the key is 60% of the traffic of an unbatched inner product).
 template <int IP_MAX_BETA>
 __global__ void __launch_bounds__(EW_THREADS) k_inner(const ModConst *__restrict__ mc, LimbMap lm, InnerArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i2 = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i2 >= a.N / 2) return;
   const int e = blockIdx.y;
@@ -140,15 +147,17 @@ __global__ void __launch_bounds__(EW_THREADS) k_inner(const ModConst *__restrict
 
 void launch_inner_product(const ModConst *mc, const LimbMap &lm, const InnerArgs &a, cudaStream_t s) {
   const dim3 g = ew_grid(a.N, a.n_ext);
-  if (a.beta <= 1) k_inner<1><<<g, EW_THREADS, 0, s>>>(mc, lm, a);
-  else if (a.beta <= 2) k_inner<2><<<g, EW_THREADS, 0, s>>>(mc, lm, a);
-  else if (a.beta <= 3) k_inner<3><<<g, EW_THREADS, 0, s>>>(mc, lm, a);
-  else if (a.beta <= 4) k_inner<4><<<g, EW_THREADS, 0, s>>>(mc, lm, a);
-  else k_inner<8><<<g, EW_THREADS, 0, s>>>(mc, lm, a);
+  if (a.beta <= 1) launch_pdl(k_inner<1>, g, EW_THREADS, 0, s, mc, lm, a);
+  else if (a.beta <= 2) launch_pdl(k_inner<2>, g, EW_THREADS, 0, s, mc, lm, a);
+  else if (a.beta <= 3) launch_pdl(k_inner<3>, g, EW_THREADS, 0, s, mc, lm, a);
+  else if (a.beta <= 4) launch_pdl(k_inner<4>, g, EW_THREADS, 0, s, mc, lm, a);
+  else launch_pdl(k_inner<8>, g, EW_THREADS, 0, s, mc, lm, a);
 }
 
 // ------------------------------------------------------------------------------------------------ (x - y) * c (+ z)
 __global__ void __launch_bounds__(EW_THREADS) k_sub_mul_add(const ModConst *__restrict__ mc, LimbMap lm, SubMulArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i2 = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i2 >= a.N / 2) return;
   const int limb = blockIdx.y, poly = blockIdx.z;
@@ -168,11 +177,13 @@ __global__ void __launch_bounds__(EW_THREADS) k_sub_mul_add(const ModConst *__re
 }
 
 void launch_sub_mul_add(const ModConst *mc, const LimbMap &lm, const SubMulArgs &a, cudaStream_t s) {
-  k_sub_mul_add<<<ew_grid(a.N, a.n_limbs, a.n_polys), EW_THREADS, 0, s>>>(mc, lm, a);
+  launch_pdl(k_sub_mul_add, ew_grid(a.N, a.n_limbs, a.n_polys), EW_THREADS, 0, s, mc, lm, a);
 }
 
 // ------------------------------------------------------------------------------------------------ automorphism
 __global__ void __launch_bounds__(EW_THREADS) k_automorph(int logN, const u64 *__restrict__ in, u64 *__restrict__ out, unsigned g) {
+  pdl_launch_dependents();
+  pdl_wait();
   const unsigned N = 1u << logN;
   const unsigned k = blockIdx.x * EW_THREADS + threadIdx.x;
   if (k >= N) return;
@@ -185,7 +196,7 @@ __global__ void __launch_bounds__(EW_THREADS) k_automorph(int logN, const u64 *_
 
 void launch_automorph(int logN, int n_limbs, const u64 *in, u64 *out, u64 g, cudaStream_t s) {
   const unsigned N = 1u << logN;
-  k_automorph<<<dim3((N + EW_THREADS - 1) / EW_THREADS, n_limbs), EW_THREADS, 0, s>>>(logN, in, out, (unsigned)(g & (2ull * N - 1)));
+  launch_pdl(k_automorph, dim3((N + EW_THREADS - 1) / EW_THREADS, n_limbs), EW_THREADS, 0, s, logN, in, out, (unsigned)(g & (2ull * N - 1)));
 }
 
 // ------------------------------------------------------------------------------------------------ base conversion
@@ -216,6 +227,25 @@ __global__ void __launch_bounds__(512) k_bconv_mma(const ModConst *__restrict__ 
   const size_t m_base = (size_t)blockIdx.x * tm;
   const u64 *in = a.in + (size_t)blockIdx.y * a.in_batch_stride;
   u64 *out = a.out + (size_t)blockIdx.y * a.out_batch_stride;
+  pdl_launch_dependents();
+  // matrix fragments and moduli are constant tables: fetched before the programmatic dependency is resolved
+  const bool mma_warp = tb * 8 < n_dst_pad;  // a launch with fewer than four target blocks has staging-only helper warps
+  const int kq = lane & 3, rq = lane >> 2;
+  const int t0 = tb * 8 + 2 * kq, t1 = t0 + 1;
+  const bool live0 = t0 < a.n_dst, live1 = t1 < a.n_dst;
+  const ModConst m0 = mc[dst_lm.mod[live0 ? t0 : a.n_dst - 1]], m1 = mc[dst_lm.mod[live1 ? t1 : a.n_dst - 1]];
+  u64 *o0 = out + (size_t)dst_lm.pos[live0 ? t0 : a.n_dst - 1] * a.N + m_base + rq;
+  u64 *o1 = out + (size_t)dst_lm.pos[live1 ? t1 : a.n_dst - 1] * a.N + m_base + rq;
+  const double *bsrc = mat + ((size_t)kq * n_dst_pad + tb * 8 + rq) * 3;  // B[k = lane%4][n = lane/4], k-step stride 4 rows
+  const size_t brow = (size_t)4 * n_dst_pad * 3;
+  double bf[KS > 0 ? KS : 1][3];
+  if constexpr (KS > 0) {
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int p = 0; p < 3; ++p) bf[ks][p] = mma_warp ? __ldg(bsrc + ks * brow + p) : 0.0;
+  }
+  pdl_wait();  // the sources are another kernel's output
   {  // stage the tile's sources (step 1 applied here when requested), zero the padding rows; four loads in flight per thread
     const int half = tm >> 1, total = n_src_pad * half;
     for (int e0 = threadIdx.x; e0 < total; e0 += 4 * blockDim.x) {
@@ -242,27 +272,16 @@ __global__ void __launch_bounds__(512) k_bconv_mma(const ModConst *__restrict__ 
     }
   }
   __syncthreads();
-  if (tb * 8 >= n_dst_pad) return;  // staging helpers of a launch with fewer than four target blocks
-  const int kq = lane & 3, rq = lane >> 2;
-  const int t0 = tb * 8 + 2 * kq, t1 = t0 + 1;
-  const bool live0 = t0 < a.n_dst, live1 = t1 < a.n_dst;
-  const ModConst m0 = mc[dst_lm.mod[live0 ? t0 : a.n_dst - 1]], m1 = mc[dst_lm.mod[live1 ? t1 : a.n_dst - 1]];
-  u64 *o0 = out + (size_t)dst_lm.pos[live0 ? t0 : a.n_dst - 1] * a.N + m_base + rq;
-  u64 *o1 = out + (size_t)dst_lm.pos[live1 ? t1 : a.n_dst - 1] * a.N + m_base + rq;
-  const double *bsrc = mat + ((size_t)kq * n_dst_pad + tb * 8 + rq) * 3;  // B[k = lane%4][n = lane/4], k-step stride 4 rows
-  const size_t brow = (size_t)4 * n_dst_pad * 3;
-  double bf[KS > 0 ? KS : 1][3];
-  if constexpr (KS > 0) {
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-      for (int p = 0; p < 3; ++p) bf[ks][p] = __ldg(bsrc + ks * brow + p);
-  }
+  if (!mma_warp) return;
+  const double nh0 = -(m0.q - 1.0) * 0.5, nh1 = -(m1.q - 1.0) * 0.5;
+  const double hb0 = 4503599627370496.0 - nh0, hb1 = 4503599627370496.0 - nh1;  // 2^52 + h
   const double *yl = ys + kq * pitch + rq;  // A[row = lane/4][col = lane%4]
   const int n_ks = n_src_pad >> 2;
   // two m-tiles (16 coefficients) per iteration: six independent accumulator chains keep the tensor pipe fed
   for (int mt = 0; mt < (tm >> 3); mt += 2) {
-    double acc[2][3][2] = {{{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}}};
+    // piece-0 accumulators start at -h, h = (q_t - 1) / 2: the final centred remainder is then (value - h) in [-h, h] and
+    // canonicalisation is one add of 2^52 + h (no sign fix-up)
+    double acc[2][3][2] = {{{nh0, nh1}, {0.0, 0.0}, {0.0, 0.0}}, {{nh0, nh1}, {0.0, 0.0}, {0.0, 0.0}}};
     if constexpr (KS > 0) {
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
@@ -302,8 +321,8 @@ __global__ void __launch_bounds__(512) k_bconv_mma(const ModConst *__restrict__ 
       v1 = reduce_signed(__fma_rn(v1, 4096.0, acc[h][1][1]), m1.q, m1.qinv);
       v0 = reduce_signed(__fma_rn(v0, 4096.0, acc[h][0][0]), m0.q, m0.qinv);
       v1 = reduce_signed(__fma_rn(v1, 4096.0, acc[h][0][1]), m1.q, m1.qinv);
-      if (live0) o0[(mt + h) * 8] = f64_to_canonical(v0, m0.qi);
-      if (live1) o1[(mt + h) * 8] = f64_to_canonical(v1, m1.qi);
+      if (live0) o0[(mt + h) * 8] = (u64)__double_as_longlong(v0 + hb0) & 0x000FFFFFFFFFFFFFull;
+      if (live1) o1[(mt + h) * 8] = (u64)__double_as_longlong(v1 + hb1) & 0x000FFFFFFFFFFFFFull;
     }
   }
 }
@@ -320,8 +339,8 @@ static void launch_bconv_t(const ModConst *mc, const LimbMap &src_lm, const Limb
     return true;
   }();
   (void)once;
-  if (a.step1) k_bconv_mma<KS, true><<<grid, threads, smem, s>>>(mc, src_lm, dst_lm, a, mat, n_src_pad, n_dst_pad, tm);
-  else k_bconv_mma<KS, false><<<grid, threads, smem, s>>>(mc, src_lm, dst_lm, a, mat, n_src_pad, n_dst_pad, tm);
+  if (a.step1) launch_pdl(k_bconv_mma<KS, true>, grid, threads, smem, s, mc, src_lm, dst_lm, a, mat, n_src_pad, n_dst_pad, tm);
+  else launch_pdl(k_bconv_mma<KS, false>, grid, threads, smem, s, mc, src_lm, dst_lm, a, mat, n_src_pad, n_dst_pad, tm);
 }
 
 void launch_bconv(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const double *mat, cudaStream_t s) {

@@ -1,0 +1,38 @@
+// Kernel launch helper: programmatic dependent launch (HML_PDL=0 turns it off everywhere), see modarith.cuh.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <utility>
+
+namespace hml {
+
+inline int pdl_enabled() {
+  static const int v = [] {
+    const char *e = getenv("HML_PDL");
+    return e && atoi(e) == 0 ? 0 : 1;
+  }();
+  return v;
+}
+
+// Measured on B200 (profiles/README.md): overlapping a kernel's start-up with its predecessor's tail takes 9 % off a single
+// hmult (18 short launches) but costs 5 % on 32-ciphertext chunks, so the composed ops switch it off for large batches.
+inline thread_local int g_pdl_scope = 1;
+struct PdlScope {
+  int saved;
+  explicit PdlScope(bool on) : saved(g_pdl_scope) { g_pdl_scope = on ? 1 : 0; }
+  ~PdlScope() { g_pdl_scope = saved; }
+};
+
+template <class... KArgs, class... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() && g_pdl_scope;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+}  // namespace hml

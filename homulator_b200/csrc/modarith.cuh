@@ -76,6 +76,13 @@ __device__ __forceinline__ void gs_butterfly(double &x, double &y, double w, dou
   y = mulmod_var(d, w, q, qinv);
 }
 
+// ---- programmatic dependent launch (PDL): every kernel of the library is launched with the programmatic-serialisation
+// attribute (launch.h), so its CTAs may be scheduled while the previous kernel of the stream drains.  A kernel may touch
+// read-only tables (twiddles, moduli, matrices) right away; it must call pdl_wait() before the first access (read OR
+// write) to any buffer another kernel may produce or still be reading.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // per-modulus constants kept in device memory
 struct ModConst {
   double q;       // modulus as double

@@ -1,5 +1,6 @@
 // See ntt.cuh for the algorithm.  sm_100a only.
 #include "ntt.cuh"
+#include "launch.h"
 
 #include <cstdlib>
 #include <cstring>
@@ -163,6 +164,8 @@ __global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_fwd_col
   ColWork cur, nxt;
   ColPos pos = col_pos(blockIdx.x < total ? blockIdx.x : 0, K::TILES, l.n_limbs, l.n_polys);
   const ColPos step = col_pos(gridDim.x, K::TILES, l.n_limbs, l.n_polys);
+  pdl_launch_dependents();
+  pdl_wait();
   bool have = blockIdx.x < total && col_next<LOGR1, NT>(pos, step, true, lm, l, false, cur);
   if (have) col_issue<LOGR1, NT>(cur, t.fwd, t.mc, nullptr, logN, smem0);
   cp_async_commit();
@@ -212,6 +215,8 @@ __global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_inv_col
   ColWork cur, nxt;
   ColPos pos = col_pos(blockIdx.x < total ? blockIdx.x : 0, K::TILES, l.n_limbs, l.n_polys);
   const ColPos step = col_pos(gridDim.x, K::TILES, l.n_limbs, l.n_polys);
+  pdl_launch_dependents();
+  pdl_wait();
   bool have = blockIdx.x < total && col_next<LOGR1, NT>(pos, step, true, lm, l, true, cur);
   if (have) col_issue<LOGR1, NT>(cur, t.inv, t.mc, l.post_scale, logN, smem0);
   cp_async_commit();
@@ -345,6 +350,8 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
   const RowItems items{l.n_polys, l.n_batch, lm.skip[limb], (int)gridDim.z};
   RowItem cur = items.next(RowItem{0, (int)blockIdx.z - (int)gridDim.z});
   RowItem nxt = items.valid(cur) ? items.next(cur) : cur;
+  pdl_launch_dependents();
+  pdl_wait();  // the twiddle blob (a constant table) is already in flight; the data is another kernel's output
   if (items.valid(cur)) row_issue(src_of(cur), data0, lane, warp);
   cp_async_commit();
   if (items.valid(nxt)) row_issue(src_of(nxt), data0 + ROW_TILE_BYTES, lane, warp);
@@ -505,6 +512,8 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
 // ================================================================================ small N (<= 4096): one CTA per limb
 __global__ void __launch_bounds__(256) ntt_small(NttTables t, int logN, LimbMap lm, NttLaunch l, int inverse) {
   extern __shared__ double sm[];
+  pdl_launch_dependents();
+  pdl_wait();
   const int limb = blockIdx.y % l.n_limbs, poly = (blockIdx.y / l.n_limbs) % l.n_polys, batch = blockIdx.y / (l.n_limbs * l.n_polys);
   if (poly == lm.skip[limb]) return;
   const int mi = lm.mod[limb];
@@ -614,8 +623,8 @@ static void launch_cols_t(bool inverse, const NttTables &t, int logN, const Limb
     return true;
   }();
   (void)once;
-  if (inverse) ntt_inv_cols<LOGR1, NT><<<grid, NT, 2 * K::STAGE_BYTES, s>>>(t, logN, lm, l, total);
-  else ntt_fwd_cols<LOGR1, NT><<<grid, NT, 2 * K::STAGE_BYTES, s>>>(t, logN, lm, l, total);
+  if (inverse) launch_pdl(ntt_inv_cols<LOGR1, NT>, grid, NT, 2 * K::STAGE_BYTES, s, t, logN, lm, l, total);
+  else launch_pdl(ntt_fwd_cols<LOGR1, NT>, grid, NT, 2 * K::STAGE_BYTES, s, t, logN, lm, l, total);
 }
 
 static int col_threads() {
@@ -646,14 +655,14 @@ static void launch_rows(bool inverse, const NttTables &t, int logN, const LimbMa
   (void)once;
   const int tiles = 1 << (logN - NTT_ROW_LOG - 4);
   const dim3 grid(tiles, l.n_limbs, row_split(l.n_polys * l.n_batch, tiles * l.n_limbs));
-  if (inverse) ntt_rows<true, false><<<grid, NTT_THREADS, ROW_SMEM_BYTES, s>>>(t, logN, lm, l);
-  else if (l.fuse.x) ntt_rows<false, true><<<grid, NTT_THREADS, ROW_SMEM_BYTES, s>>>(t, logN, lm, l);
-  else ntt_rows<false, false><<<grid, NTT_THREADS, ROW_SMEM_BYTES, s>>>(t, logN, lm, l);
+  if (inverse) launch_pdl(ntt_rows<true, false>, grid, NTT_THREADS, ROW_SMEM_BYTES, s, t, logN, lm, l);
+  else if (l.fuse.x) launch_pdl(ntt_rows<false, true>, grid, NTT_THREADS, ROW_SMEM_BYTES, s, t, logN, lm, l);
+  else launch_pdl(ntt_rows<false, false>, grid, NTT_THREADS, ROW_SMEM_BYTES, s, t, logN, lm, l);
 }
 
 void launch_ntt_forward(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
   if (logN <= NTT_SMALL_LOG) {
-    ntt_small<<<dim3(1, l.n_limbs * l.n_polys * l.n_batch), 256, sizeof(double) << logN, s>>>(t, logN, lm, l, 0);
+    launch_pdl(ntt_small, dim3(1, l.n_limbs * l.n_polys * l.n_batch), 256, sizeof(double) << logN, s, t, logN, lm, l, 0);
     return;
   }
   launch_cols(false, t, logN, lm, l, s);
@@ -662,7 +671,7 @@ void launch_ntt_forward(const NttTables &t, int logN, const LimbMap &lm, const N
 
 void launch_ntt_inverse(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
   if (logN <= NTT_SMALL_LOG) {
-    ntt_small<<<dim3(1, l.n_limbs * l.n_polys * l.n_batch), 256, sizeof(double) << logN, s>>>(t, logN, lm, l, 1);
+    launch_pdl(ntt_small, dim3(1, l.n_limbs * l.n_polys * l.n_batch), 256, sizeof(double) << logN, s, t, logN, lm, l, 1);
     return;
   }
   launch_rows(true, t, logN, lm, l, s);
