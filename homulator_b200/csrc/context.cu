@@ -167,6 +167,9 @@ extern "C" void hml_ctx_destroy(hml_ctx *ctx) {
   if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
   if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
   if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+  if (ctx->s_lane) cudaStreamDestroy(ctx->s_lane);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   delete ctx;
 }
 
@@ -939,12 +942,12 @@ static size_t hmult_ws_words(const Params &p, uint32_t L, uint32_t nb) {
 // straight out of the base conversion: P^-1 is folded into the matrix on the host and r rides in the otherwise padded
 // 16th source row with matrix entry 1 (exact: it only adds one term < 2^36 to the 16-term sums).
 static int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, const u64 *ct_b, const u64 *evk, uint32_t evk_q_limbs,
-                     u64 *ct_out, cudaStream_t s) {
+                     u64 *ct_out, u64 *ws, cudaStream_t s) {
   const PdlScope pdl(nb <= 2);
   const Params &p = ctx->p;
   const size_t N = p.N, PL = N * L;
   // d0 | d1 | d2 each [nb][L][N], cb [nb][2][L][N], then the key-switch / rescale workspace
-  u64 *d0 = ctx->ws, *d1 = d0 + nb * PL, *d2 = d1 + nb * PL;
+  u64 *d0 = ws, *d1 = d0 + nb * PL, *d2 = d1 + nb * PL;
   launch_tensor3(ctx->mc, (int)N, (int)L, ct_a, ct_a + PL, ct_b, ct_b + PL, d0, d1, d2, (int)nb, (long long)(2 * PL), (long long)PL, s);  // reference :592-739
   ctx->exec.ewe_limbs += 3ull * nb * L; ctx->exec.kernel_launches++;
   if (p.logN <= NTT_SMALL_LOG) {  // single-pass rings: the textbook sequence
@@ -1014,17 +1017,17 @@ extern "C" int hml_hmult(hml_ctx *ctx, uint32_t L, const uint64_t *ct_a, const u
   if (!ct_a || !ct_b || !evk || !ct_out) return fail(ctx, HML_ERR_INVALID, "null buffer");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   if ((rc = ensure_ws(ctx, hmult_ws_words(ctx->p, L, 1)))) return rc;
-  return hmult_run(ctx, L, 1, (const u64 *)ct_a, (const u64 *)ct_b, (const u64 *)evk, evk_q_limbs, (u64 *)ct_out, (cudaStream_t)stream);
+  return hmult_run(ctx, L, 1, (const u64 *)ct_a, (const u64 *)ct_b, (const u64 *)evk, evk_q_limbs, (u64 *)ct_out, ctx->ws, (cudaStream_t)stream);
 }
 
 static size_t hrot_ws_words(const Params &p, uint32_t L, uint32_t nb) { return (size_t)nb * ((size_t)p.N * 2 * L + ks_ws_words(p, L)); }
 
 // nb ciphertexts [nb][2][L][N] -> [nb][2][L][N]
 static int hrot_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct, const u64 *rk, uint32_t evk_q_limbs, u64 g, u64 *ct_out,
-                    cudaStream_t s) {
+                    u64 *ws, cudaStream_t s) {
   const PdlScope pdl(nb <= 2);
   const size_t N = ctx->p.N, PL = N * L;
-  u64 *sb = ctx->ws, *rest = sb + 2 * nb * PL;  // sb [nb][2][L][N]
+  u64 *sb = ws, *rest = sb + 2 * nb * PL;  // sb [nb][2][L][N]
   launch_automorph(ctx->p.logN, 2 * L * nb, ct, sb, g, s);  // reference :1302-1319
   ctx->exec.automorph_limbs += 2ull * nb * L; ctx->exec.kernel_launches++;
   // reference :1326-1357 key-switches AUTOOutput(0) and adds AUTOOutput(1) (naming only, delta D4):
@@ -1041,7 +1044,7 @@ extern "C" int hml_hrotate(hml_ctx *ctx, uint32_t L, const uint64_t *ct, const u
   if (!(galois_elt & 1)) return fail(ctx, HML_ERR_INVALID, "galois element must be odd");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   if ((rc = ensure_ws(ctx, hrot_ws_words(ctx->p, L, 1)))) return rc;
-  return hrot_run(ctx, L, 1, (const u64 *)ct, (const u64 *)rotkey, evk_q_limbs, galois_elt, (u64 *)ct_out, (cudaStream_t)stream);
+  return hrot_run(ctx, L, 1, (const u64 *)ct, (const u64 *)rotkey, evk_q_limbs, galois_elt, (u64 *)ct_out, ctx->ws, (cudaStream_t)stream);
 }
 
 static int ew_ct_op(hml_ctx *ctx, uint32_t L, const uint64_t *a, const uint64_t *b, bool b_is_pt, bool mul, uint64_t *out, void *stream) {
@@ -1071,21 +1074,60 @@ extern "C" int hml_padd(hml_ctx *ctx, uint32_t L, const uint64_t *ct, const uint
 }
 
 // ------------------------------------------------------------------------------------------------ batched
+// Optionally (HML_BATCH_LANES=2) chunks alternate between two lanes — the caller's stream + an internal one, each with its
+// own workspace half, fork / join with events — so that the HBM-bound element-wise kernels of one chunk may overlap the
+// FP64-bound transforms of the other.  Measured on B200: two lanes of 16 = one lane of 32 (209.9 vs 209.7 us per hmult;
+// every kernel already fills the machine, only launch tails overlap), so one lane is the default.
+static uint32_t batch_lanes() {
+  static const uint32_t v = [] {
+    const char *e = getenv("HML_BATCH_LANES");  // tuning knob: 1 or 2
+    return (uint32_t)(e && atoi(e) == 2 ? 2 : 1);
+  }();
+  return v;
+}
+
+template <class RunChunk>
+static int run_batch_lanes(hml_ctx *ctx, uint32_t n, size_t ws_per_ct, cudaStream_t user, RunChunk run) {
+  const uint32_t lanes = n > 1 ? batch_lanes() : 1;
+  // chunks no larger than HML_BATCH_CHUNK, and at least `lanes` of them when the batch allows it
+  uint32_t chunk = std::min<uint32_t>(HML_BATCH_CHUNK, (n + lanes - 1) / lanes);
+  int rc = ensure_ws(ctx, (size_t)lanes * chunk * ws_per_ct);
+  if (rc) return rc;
+  const bool two = lanes == 2 && n > chunk;
+  if (two) {
+    if (!ctx->s_lane) {
+      CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_lane, cudaStreamNonBlocking));
+      CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+      CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_fork, user));
+    CU_TRY(ctx, cudaStreamWaitEvent(ctx->s_lane, ctx->ev_fork, 0));
+  }
+  uint32_t k = 0;
+  for (uint32_t i = 0; i < n; i += chunk, ++k) {
+    const uint32_t nb = std::min(chunk, n - i);
+    const bool side = two && (k & 1);
+    if ((rc = run(i, nb, ctx->ws + (side ? (size_t)chunk * ws_per_ct : 0), side ? ctx->s_lane : user))) break;
+  }
+  if (two) {
+    cudaEventRecord(ctx->ev_join, ctx->s_lane);
+    cudaStreamWaitEvent(user, ctx->ev_join, 0);
+  }
+  return rc;
+}
+
 extern "C" int hml_hmult_batch(hml_ctx *ctx, uint32_t L, uint32_t n, const uint64_t *ct_a, const uint64_t *ct_b,
                                const uint64_t *evk, uint32_t evk_q_limbs, uint64_t *ct_out, void *stream) {
   int rc = check_level(ctx, L, 2);
   if (rc) return rc;
   if (!ct_a || !ct_b || !evk || !ct_out) return fail(ctx, HML_ERR_INVALID, "null buffer");
+  if (n == 0) return HML_OK;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  if ((rc = ensure_ws(ctx, hmult_ws_words(ctx->p, L, std::min(n, HML_BATCH_CHUNK))))) return rc;
   const size_t N = ctx->p.N, in_w = 2 * N * L, out_w = 2 * N * (L - 1);
-  for (uint32_t i = 0; i < n; i += HML_BATCH_CHUNK) {
-    const uint32_t nb = std::min(HML_BATCH_CHUNK, n - i);
-    if ((rc = hmult_run(ctx, L, nb, (const u64 *)ct_a + i * in_w, (const u64 *)ct_b + i * in_w, (const u64 *)evk, evk_q_limbs,
-                        (u64 *)ct_out + i * out_w, (cudaStream_t)stream)))
-      return rc;
-  }
-  return HML_OK;
+  return run_batch_lanes(ctx, n, hmult_ws_words(ctx->p, L, 1), (cudaStream_t)stream, [&](uint32_t i, uint32_t nb, u64 *ws, cudaStream_t s) {
+    return hmult_run(ctx, L, nb, (const u64 *)ct_a + i * in_w, (const u64 *)ct_b + i * in_w, (const u64 *)evk, evk_q_limbs,
+                     (u64 *)ct_out + i * out_w, ws, s);
+  });
 }
 
 extern "C" int hml_hrotate_batch(hml_ctx *ctx, uint32_t L, uint32_t n, const uint64_t *ct, const uint64_t *rotkey,
@@ -1094,16 +1136,12 @@ extern "C" int hml_hrotate_batch(hml_ctx *ctx, uint32_t L, uint32_t n, const uin
   if (rc) return rc;
   if (!ct || !rotkey || !ct_out) return fail(ctx, HML_ERR_INVALID, "null buffer");
   if (!(galois_elt & 1)) return fail(ctx, HML_ERR_INVALID, "galois element must be odd");
+  if (n == 0) return HML_OK;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  if ((rc = ensure_ws(ctx, hrot_ws_words(ctx->p, L, std::min(n, HML_BATCH_CHUNK))))) return rc;
   const size_t w = 2 * (size_t)ctx->p.N * L;
-  for (uint32_t i = 0; i < n; i += HML_BATCH_CHUNK) {
-    const uint32_t nb = std::min(HML_BATCH_CHUNK, n - i);
-    if ((rc = hrot_run(ctx, L, nb, (const u64 *)ct + i * w, (const u64 *)rotkey, evk_q_limbs, galois_elt, (u64 *)ct_out + i * w,
-                       (cudaStream_t)stream)))
-      return rc;
-  }
-  return HML_OK;
+  return run_batch_lanes(ctx, n, hrot_ws_words(ctx->p, L, 1), (cudaStream_t)stream, [&](uint32_t i, uint32_t nb, u64 *ws, cudaStream_t s) {
+    return hrot_run(ctx, L, nb, (const u64 *)ct + i * w, (const u64 *)rotkey, evk_q_limbs, galois_elt, (u64 *)ct_out + i * w, ws, s);
+  });
 }
 
 // ------------------------------------------------------------------------------------------------ host-buffer API
@@ -1146,8 +1184,8 @@ static int host_pipeline(hml_ctx *ctx, bool is_mult, uint32_t L, uint32_t n, con
     cudaEventRecord(ev_in[k], ctx->s_in);
     cudaStreamWaitEvent(ctx->s_comp, ev_in[k], 0);
     if (i >= 2) cudaStreamWaitEvent(ctx->s_comp, ev_out[k], 0);  // slot output free once item i-2 has been copied out
-    rc = is_mult ? hmult_run(ctx, L, 1, sa, sb, (const u64 *)key_dev, evk_q_limbs, so, ctx->s_comp)
-                 : hrot_run(ctx, L, 1, sa, (const u64 *)key_dev, evk_q_limbs, g, so, ctx->s_comp);
+    rc = is_mult ? hmult_run(ctx, L, 1, sa, sb, (const u64 *)key_dev, evk_q_limbs, so, ctx->ws, ctx->s_comp)
+                 : hrot_run(ctx, L, 1, sa, (const u64 *)key_dev, evk_q_limbs, g, so, ctx->ws, ctx->s_comp);
     cudaEventRecord(ev_comp[k], ctx->s_comp);
     cudaStreamWaitEvent(ctx->s_out, ev_comp[k], 0);
     cudaMemcpyAsync(out_host + i * out_w, so, out_w * 8, cudaMemcpyDeviceToHost, ctx->s_out);

@@ -92,6 +92,10 @@ struct hml_ctx {
 
   // host-buffer API: staging buffers + streams
   cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+  // batched ops: a second lane (stream + workspace half) so that the HBM-bound kernels of one chunk overlap the
+  // FP64-bound kernels of the other
+  cudaStream_t s_lane = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   hml::u64 *stage = nullptr;
   size_t stage_words = 0;
 };

@@ -5,7 +5,7 @@ L, A = 35, 15
 ctx = hml.Context(os.path.join(os.getcwd(), "config", "config_4.cfg"), 45, A)
 q = list(range(L))
 evk = ctx.uniform(ctx.ext_mod_idx(L), 3, lead=(3, 2))
-B = 32
+B = int(os.environ.get("B", "32"))
 a = ctx.uniform(q, 1, lead=(B, 2)); b = ctx.uniform(q, 2, lead=(B, 2))
 out = ctx.empty(B, 2, L - 1, ctx.N)
 def timeit(fn, reps=5):
