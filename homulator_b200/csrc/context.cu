@@ -151,7 +151,7 @@ extern "C" int hml_ctx_create(const char *cfg_path, uint32_t max_level, uint32_t
 static void free_level(LevelConsts &lc) {
   cudaFree(lc.modup_scale); cudaFree(lc.moddown_scale); cudaFree(lc.pinv); cudaFree(lc.qlinv);
   for (auto &u : lc.up) cudaFree(u.d_mat);
-  cudaFree(lc.down.d_mat); cudaFree(lc.merged_rest.d_mat); cudaFree(lc.merged_last.d_mat);
+  cudaFree(lc.down.d_mat); cudaFree(lc.merged_rest.d_mat); cudaFree(lc.merged_fold);
 }
 
 extern "C" void hml_ctx_destroy(hml_ctx *ctx) {
@@ -315,23 +315,23 @@ static int get_level(hml_ctx *ctx, uint32_t L, LevelConsts **out) {
     for (uint32_t j = 0; j < A; ++j) { lc.merged_src.mod[j] = p.max_level + j; lc.merged_src.pos[j] = L + j; }
     lc.merged_src.mod[A] = L - 1; lc.merged_src.pos[A] = E;  // the extra source lives in slot E of the accumulator
     lc.last_lm.mod[0] = L - 1; lc.last_lm.pos[0] = 0;
-    BConvTable rest, last;
-    rest.src = src; rest.src.push_back(L - 1); last.src = rest.src;
+    BConvTable rest;
+    rest.src = src; rest.src.push_back(L - 1);
     for (uint32_t i = 0; i + 1 < L; ++i) rest.dst.push_back(i);
-    last.dst.push_back(L - 1);
     const uint32_t nr = L - 1;
-    rest.hat.assign((size_t)(A + 1) * nr, 0); last.hat.assign(A + 1, 0);
+    rest.hat.assign((size_t)(A + 1) * nr, 0);
+    std::vector<double> fold(3 * (size_t)A);
     for (uint32_t j = 0; j < A; ++j) {
       for (uint32_t i = 0; i < nr; ++i) rest.hat[(size_t)j * nr + i] = h_mulmod(bt.hat[(size_t)j * L + i], pinv_i[i], p.mod[i]);
       const u64 ql = p.mod[L - 1], t = h_mulmod(bt.hat[(size_t)j * L + L - 1], pinv_i[L - 1], ql);
-      last.hat[j] = t ? ql - t : 0;  // minus: r = slot_E - v * P^-1
+      const u64 neg = t ? ql - t : 0;  // minus: r = slot_E - v[L-1] * P^-1
+      fold[3 * j] = (double)(neg & 0xFFF); fold[3 * j + 1] = (double)((neg >> 12) & 0xFFF); fold[3 * j + 2] = (double)(neg >> 24);
     }
     for (uint32_t i = 0; i < nr; ++i) rest.hat[(size_t)A * nr + i] = 1;
-    last.hat[A] = 1;
-    std::vector<uint32_t> rest_pos(nr), last_pos(1, E);
+    std::vector<uint32_t> rest_pos(nr);
     for (uint32_t i = 0; i < nr; ++i) rest_pos[i] = i;
     if ((rc = prepare_bconv(ctx, rest, rest_pos, lc.merged_rest))) return rc;
-    if ((rc = prepare_bconv(ctx, last, last_pos, lc.merged_last))) return rc;
+    if ((rc = upload(ctx, fold, &lc.merged_fold))) return rc;
   }
   // ---- Rescale
   {
@@ -939,8 +939,9 @@ static size_t hmult_ws_words(const Params &p, uint32_t L, uint32_t nb) {
 //   r      = INTT_{L-1}(u[L-1]) - v[L-1] * P^-1                      (no forward transform of limb L-1 at all)
 //   out[l] = (u[l] - NTT_l(v_l * P^-1 + [r]_{q_l})) * q_{L-1}^-1      (ONE forward transform per output limb instead of two)
 // yields bit-identical residues with 2(L-1) forward transforms instead of 2L + 2(L-1).  v_l * P^-1 + [r]_{q_l} comes
-// straight out of the base conversion: P^-1 is folded into the matrix on the host and r rides in the otherwise padded
-// 16th source row with matrix entry 1 (exact: it only adds one term < 2^36 to the 16-term sums).
+// straight out of the base conversion: P^-1 is folded into the matrix on the host, r is computed by the conversion kernel on
+// its staged tile (a 15-term dot product per coefficient) and rides in the otherwise padded 16th source row with matrix
+// entry 1 (exact: it only adds one term < 2^36 to the 16-term sums).
 static int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, const u64 *ct_b, const u64 *evk, uint32_t evk_q_limbs,
                      u64 *ct_out, u64 *ws, cudaStream_t s) {
   const PdlScope pdl(nb <= 2);
@@ -986,12 +987,10 @@ static int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, con
     launch_ntt_inverse(ctx->tabs, logN, lc->last_lm, l, s);
     ctx->exec.intt_limbs += 2ull * nb; ctx->exec.kernel_launches += 2;
   }
-  {  // r = slot_E - v[L-1] * P^-1, in place; then w_l = v_l * P^-1 + [r]_{q_l}, l < L-1 (reference K8 :489-519)
+  {  // w_l = v_l * P^-1 + [r]_{q_l}, l < L-1, with r = slot_E - v[L-1] * P^-1 folded on the staged tile (reference K8 :489-519)
     BConvArgs a{};
-    a.in = acc; a.out = acc; a.in_batch_stride = a.out_batch_stride = (long long)AL * N;
-    a.step1 = nullptr; a.N = N; a.n_batches = 2 * nb;
-    run_bconv(ctx, lc->merged_last, lc->merged_src, a, s);
-    a.out = wb; a.out_batch_stride = (long long)(L - 1) * N;
+    a.in = acc; a.in_batch_stride = (long long)AL * N; a.out = wb; a.out_batch_stride = (long long)(L - 1) * N;
+    a.step1 = nullptr; a.N = N; a.n_batches = 2 * nb; a.fold = lc->merged_fold; a.fold_mod = (int)(L - 1);
     run_bconv(ctx, lc->merged_rest, lc->merged_src, a, s);
   }
   {  // out[l] = ((acc[l] * P^-1 + d[l]) - NTT_l(w_l)) * q_{L-1}^-1  (K9, K10, HMULT add and Rescale in one transform)

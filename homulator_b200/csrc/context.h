@@ -39,9 +39,11 @@ struct LevelConsts {
   // Rescale: q_{L-1}^-1 mod q_l
   double2 *qlinv = nullptr;                  // [L-1]
   // hmult only (L >= 2): ModDown merged with Rescale by linearity of the NTT (context.cu, hmult_run).  Sources = the alpha
-  // P-limbs of an accumulator (slots L + j) plus one extra coefficient-form limb in slot E; `merged_last` produces
-  // r = slot_E - v[L-1] * P^-1 (mod q_{L-1}) in place, `merged_rest` produces w_l = v_l * P^-1 + [r]_{q_l} for l < L-1.
-  HostBConv merged_last, merged_rest;
+  // P-limbs of an accumulator (slots L + j) plus one extra coefficient-form limb in slot E holding INTT(u[L-1]).  The
+  // conversion first folds r = slot_E - v[L-1] * P^-1 (mod q_{L-1}) on its staged tile (`merged_fold`: the constants
+  // -(P/p_j mod q_{L-1}) * P^-1 in 12-bit pieces), then produces w_l = v_l * P^-1 + [r]_{q_l} for l < L-1 (`merged_rest`).
+  HostBConv merged_rest;
+  double *merged_fold = nullptr;             // [alpha][3]
   LimbMap merged_src, last_lm;
   LimbMap q_lm;                              // limbs 0..L-1 -> moduli q_0..q_{L-1}, pos = limb
   LimbMap p_lm;                              // limbs 0..alpha-1 -> moduli p_j, pos = L + j (inside an [E][N] buffer)

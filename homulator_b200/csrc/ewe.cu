@@ -272,6 +272,24 @@ __global__ void __launch_bounds__(512) k_bconv_mma(const ModConst *__restrict__ 
     }
   }
   __syncthreads();
+  if (a.fold) {  // uniform branch: every thread of the CTA takes it
+    const ModConst mf = mc[a.fold_mod];
+    const int last = a.n_src - 1;
+    for (int m = threadIdx.x; m < tm; m += blockDim.x) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;  // <= 15 terms of < 2^48 each: exact
+      for (int i = 0; i < last; ++i) {
+        const double y = ys[i * pitch + m];
+        s0 = __fma_rn(y, __ldg(a.fold + 3 * i), s0);
+        s1 = __fma_rn(y, __ldg(a.fold + 3 * i + 1), s1);
+        s2 = __fma_rn(y, __ldg(a.fold + 3 * i + 2), s2);
+      }
+      double v = reduce_signed(s2, mf.q, mf.qinv);
+      v = reduce_signed(__fma_rn(v, 4096.0, s1), mf.q, mf.qinv);
+      v = reduce_signed(__fma_rn(v, 4096.0, s0 + ys[last * pitch + m]), mf.q, mf.qinv);
+      ys[last * pitch + m] = canonicalize(v, mf.q);
+    }
+    __syncthreads();
+  }
   if (!mma_warp) return;
   const double nh0 = -(m0.q - 1.0) * 0.5, nh1 = -(m1.q - 1.0) * 0.5;
   const double hb0 = 4503599627370496.0 - nh0, hb1 = 4503599627370496.0 - nh1;  // 2^52 + h

@@ -59,6 +59,11 @@ struct BConvArgs {
   long long in_batch_stride, out_batch_stride;  // grid.y batches (e.g. the two key-switch accumulators)
   const double2 *step1;   // [n_src] or null
   int N, n_src, n_dst, n_batches;
+  // optional pre-pass on the staged tile (hmult's merged ModDown + Rescale, context.cu): the LAST source row is replaced by
+  //   row_last + sum_{i < n_src-1} y_i * fold_i   mod q_{fold_mod}   (canonical)
+  // before the conversion; fold = [n_src-1][3] 12-bit pieces of the per-source constants, or null
+  const double *fold;
+  int fold_mod;
 };
 inline int bconv_pad_src(int n_src) { return (n_src + 3) & ~3; }   // k-steps of 4 sources
 inline int bconv_pad_dst(int n_dst) { return (n_dst + 7) & ~7; }   // target blocks of 8 (one warp each); n_dst <= 128

@@ -90,12 +90,12 @@ def test_hmult_north_star_bit_exact(north_star):
     assert np.array_equal(got, want)
     # executed-vs-trace bookkeeping: D3 elides 35 NTTs; ModDown is merged with Rescale by linearity of the
     # NTT: the 70 ModDown NTTs and the 68 Rescale NTTs become 68 transforms; the base conversion gains the
-    # rescale remainder as a 16th source: 1275 (ModUp) + 2 * 16 * (34 + 1)
+    # rescale remainder as a 16th source: 1275 (ModUp) + 2 * 16 * 34
     ctx.exec_counts(reset=True)
     ctx.hmult(35, to_dev(a), to_dev(b), to_dev(evk))
     ex = ctx.exec_counts()
     assert ex["ntt_limbs"] == 115 + 68 and ex["intt_limbs"] == 35 + 30 + 2
-    assert ex["bconv_limb_macs"] == 1275 + 2 * 16 * 35
+    assert ex["bconv_limb_macs"] == 1275 + 2 * 16 * 34
     tr = ctx.counts("hmult", 35)
     assert (tr["NTT"] + tr["INTT"]) // 256 == 289
 
