@@ -192,9 +192,51 @@ def test_op_sequence_replay_matches_oracle():
     assert np.array_equal(to_host(env["z"]), h["z"])
 
 
-@pytest.mark.parametrize("n", [1, 8, 11])
+@pytest.mark.parametrize("N,ML,A,L", [(65536, 24, 6, 24), (65536, 26, 9, 26), (65536, 26, 9, 11), (16384, 12, 4, 9)])
+def test_parameter_sets_B_C_two_pass_rings(N, ML, A, L):
+    """the reference's other parameter sets (alpha 6 / beta 4, alpha 9 / beta 3) plus shapes with
+    L % alpha != 0 and alpha % 4 == 0, on two-pass rings: hmult takes the merged ModDown + Rescale path with 7, 10 and 5
+    conversion sources (padding to 8, 12, 8), hrotate the textbook one."""
+    Oracle.set_threads(0)
+    ctx, o = hml.Context(N=N, max_level=ML, alpha=A), Oracle(N, 36, ML, A)
+    (a, b), evk = make_case(o, L, L, 1300 + L)
+    got = to_host(ctx.hmult(L, to_dev(a), to_dev(b), to_dev(evk)))
+    assert np.array_equal(got, o.hmult(L, a, b, evk, L))
+    got = to_host(ctx.hrotate(L, to_dev(a), to_dev(evk), 5))
+    assert np.array_equal(got, o.hrotate(L, a, evk, L, 5))
+    Oracle.set_threads(1)
+
+
+def test_batch_lanes_and_small_chunks_in_a_subprocess():
+    """HML_BATCH_CHUNK / HML_BATCH_LANES are read once per process: run a 7-ciphertext batch with chunks of 2 on two lanes
+    (two streams, two workspace halves) in a child process and compare with single calls."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import torch, homulator_b200 as hml\n"
+        "ctx = hml.Context(N=8192, max_level=6, alpha=2)\n"
+        "L, n = 5, 7\n"
+        "q = list(range(L))\n"
+        "evk = ctx.uniform(ctx.ext_mod_idx(L), 3, lead=(3, 2))\n"
+        "a = ctx.uniform(q, 1, lead=(n, 2)); b = ctx.uniform(q, 2, lead=(n, 2))\n"
+        "for rep in range(3):\n"
+        "    got = ctx.hmult_batch(L, a, b, evk)\n"
+        "    rot = ctx.hrotate_batch(L, a, evk, 5)\n"
+        "torch.cuda.synchronize()\n"
+        "assert torch.equal(got, torch.stack([ctx.hmult(L, a[i], b[i], evk) for i in range(n)]))\n"
+        "assert torch.equal(rot, torch.stack([ctx.hrotate(L, a[i], evk, 5) for i in range(n)]))\n"
+        "print('lanes ok')\n" % root)
+    env = dict(os.environ, HML_BATCH_CHUNK="2", HML_BATCH_LANES="2")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "lanes ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("n", [1, 8, 35])
 def test_batch_chunking_small(n):
-    """hml_*_batch runs 8 ciphertexts per launch: cover a partial chunk, one full chunk and a full + partial chunk."""
+    """hml_*_batch runs up to 32 ciphertexts per launch: cover a partial chunk and a full + partial chunk."""
     N, ML, A, L = 2048, 7, 3, 7
     ctx, o = hml.Context(N=N, max_level=ML, alpha=A), Oracle(N, 36, ML, A)
     (a, b), evk = make_case(o, L, L, 1200)
