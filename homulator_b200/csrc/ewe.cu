@@ -351,12 +351,11 @@ static void launch_bconv_t(const ModConst *mc, const LimbMap &src_lm, const Limb
   const dim3 grid(a.N / tm, a.n_batches);
   const int threads = std::max(128, 32 * (n_dst_pad / 8));  // at least four warps so that staging has loads in flight
   const size_t smem = (size_t)n_src_pad * (tm + 4) * sizeof(double);
-  static bool once = [] {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(k_bconv_mma<KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 68 * 8);
     cudaFuncSetAttribute(k_bconv_mma<KS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 68 * 8);
-    return true;
-  }();
-  (void)once;
+  }
   if (a.step1) launch_pdl(k_bconv_mma<KS, true>, grid, threads, smem, s, mc, src_lm, dst_lm, a, mat, n_src_pad, n_dst_pad, tm);
   else launch_pdl(k_bconv_mma<KS, false>, grid, threads, smem, s, mc, src_lm, dst_lm, a, mat, n_src_pad, n_dst_pad, tm);
 }

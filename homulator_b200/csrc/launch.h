@@ -24,6 +24,20 @@ struct PdlScope {
   ~PdlScope() { g_pdl_scope = saved; }
 };
 
+// cudaFuncSetAttribute is per device: true exactly once per (call site, device), so a process that drives several GPUs
+// opts every one of them into the large dynamic shared-memory carve-out
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return true;
+    const bool f = !done[dev];
+    done[dev] = true;
+    return f;
+  }
+};
+
 template <class... KArgs, class... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
   cudaLaunchConfig_t cfg = {};

@@ -617,12 +617,11 @@ static void launch_cols_t(bool inverse, const NttTables &t, int logN, const Limb
   const int total = l.n_limbs * l.n_polys * l.n_batch * K::TILES;
   const int resident = K::MIN_CTAS * sm_count();
   const int grid = total < resident ? total : resident;
-  static bool once = [] {
+  static PerDeviceOnce once;
+  if (once.first()) {
     allow_smem(ntt_fwd_cols<LOGR1, NT>, 2 * K::STAGE_BYTES);
     allow_smem(ntt_inv_cols<LOGR1, NT>, 2 * K::STAGE_BYTES);
-    return true;
-  }();
-  (void)once;
+  }
   if (inverse) launch_pdl(ntt_inv_cols<LOGR1, NT>, grid, NT, 2 * K::STAGE_BYTES, s, t, logN, lm, l, total);
   else launch_pdl(ntt_fwd_cols<LOGR1, NT>, grid, NT, 2 * K::STAGE_BYTES, s, t, logN, lm, l, total);
 }
@@ -646,13 +645,12 @@ static void launch_cols(bool inverse, const NttTables &t, int logN, const LimbMa
 }
 
 static void launch_rows(bool inverse, const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
-  static bool once = [] {
+  static PerDeviceOnce once;
+  if (once.first()) {
     allow_smem(ntt_rows<false, false>, ROW_SMEM_BYTES);
     allow_smem(ntt_rows<false, true>, ROW_SMEM_BYTES);
     allow_smem(ntt_rows<true, false>, ROW_SMEM_BYTES);
-    return true;
-  }();
-  (void)once;
+  }
   const int tiles = 1 << (logN - NTT_ROW_LOG - 4);
   const dim3 grid(tiles, l.n_limbs, row_split(l.n_polys * l.n_batch, tiles * l.n_limbs));
   if (inverse) launch_pdl(ntt_rows<true, false>, grid, NTT_THREADS, ROW_SMEM_BYTES, s, t, logN, lm, l);
