@@ -517,6 +517,7 @@ static int ks_front(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, Batc
     BConvArgs a{};
     a.in = yb + (size_t)lo * N; a.out = ext + (size_t)j * E * N; a.step1 = nullptr;
     a.N = N; a.n_batches = nb; a.in_batch_stride = (long long)L * N; a.out_batch_stride = (long long)beta * E * N;
+    a.out_f64 = npass == 2;  // hand-off to the forward NTT as doubles
     run_bconv(ctx, lc->up[j], lc->q_lm, a, s);
   }
   // K4 (reference :190-292): NTT of the converted limbs.  The digit's own limbs are the untouched input
@@ -526,6 +527,7 @@ static int ks_front(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, Batc
     l.in = ext; l.out = ext; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)E * N;
     l.n_limbs = E; l.n_polys = beta;  // digit j skips the limbs it owns (LimbMap::skip)
     l.n_batch = nb; l.in_batch_stride = l.out_batch_stride = (long long)beta * E * N;
+    l.in_f64 = npass == 2;
     launch_ntt_forward(ctx->tabs, logN, lc->ext_lm, l, s);
     ctx->exec.ntt_limbs += (uint64_t)nb * ((uint64_t)beta * E - L); ctx->exec.kernel_launches += npass;
   }
@@ -572,7 +574,7 @@ static int ks_run(hml_ctx *ctx, uint32_t L, uint32_t nb, BatchPtr d, const u64 *
   {
     BConvArgs a{};
     a.in = acc; a.out = vb; a.in_batch_stride = (long long)E * N; a.out_batch_stride = (long long)L * N;  // p_lm.pos = L + j
-    a.step1 = nullptr; a.N = N; a.n_batches = 2 * nb;
+    a.step1 = nullptr; a.N = N; a.n_batches = 2 * nb; a.out_f64 = npass == 2;
     run_bconv(ctx, lc->down, lc->p_lm, a, s);
   }
   // K9 (reference :521-546, emitted with opcode INTT — delta D1): forward NTT of the converted limbs, and
@@ -582,7 +584,7 @@ static int ks_run(hml_ctx *ctx, uint32_t L, uint32_t nb, BatchPtr d, const u64 *
   {
     NttLaunch l{};
     l.in = vb; l.out = vb; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)L * N;
-    l.n_limbs = L; l.n_polys = 2 * nb; l.n_batch = 1;
+    l.n_limbs = L; l.n_polys = 2 * nb; l.n_batch = 1; l.in_f64 = npass == 2;
     if (fuse) {
       NttFuse &f = l.fuse;
       f.x = acc; f.x_c_stride = (long long)E * N; f.x_b_stride = 2ll * E * N;
@@ -990,13 +992,13 @@ static int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, con
   {  // w_l = v_l * P^-1 + [r]_{q_l}, l < L-1, with r = slot_E - v[L-1] * P^-1 folded on the staged tile (reference K8 :489-519)
     BConvArgs a{};
     a.in = acc; a.in_batch_stride = (long long)AL * N; a.out = wb; a.out_batch_stride = (long long)(L - 1) * N;
-    a.step1 = nullptr; a.N = N; a.n_batches = 2 * nb; a.fold = lc->merged_fold; a.fold_mod = (int)(L - 1);
+    a.step1 = nullptr; a.N = N; a.n_batches = 2 * nb; a.fold = lc->merged_fold; a.fold_mod = (int)(L - 1); a.out_f64 = 1;
     run_bconv(ctx, lc->merged_rest, lc->merged_src, a, s);
   }
   {  // out[l] = ((acc[l] * P^-1 + d[l]) - NTT_l(w_l)) * q_{L-1}^-1  (K9, K10, HMULT add and Rescale in one transform)
     NttLaunch l{};
     l.in = wb; l.out = wb; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)(L - 1) * N;
-    l.n_limbs = L - 1; l.n_polys = 2 * nb; l.n_batch = 1;
+    l.n_limbs = L - 1; l.n_polys = 2 * nb; l.n_batch = 1; l.in_f64 = 1;
     NttFuse &f = l.fuse;
     f.x = acc; f.x_c_stride = (long long)AL * N; f.x_b_stride = 2ll * AL * N;
     f.z = d0; f.z_c_stride = (long long)(d1 - d0); f.z_b_stride = (long long)PL; f.z_mask = 3;

@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(512) k_bconv_mma(const ModConst *__restrict__ 
     __syncthreads();
   }
   if (!mma_warp) return;
-  const double nh0 = -(m0.q - 1.0) * 0.5, nh1 = -(m1.q - 1.0) * 0.5;
+  const double nh0 = a.out_f64 ? 0.0 : -(m0.q - 1.0) * 0.5, nh1 = a.out_f64 ? 0.0 : -(m1.q - 1.0) * 0.5;
   const double hb0 = 4503599627370496.0 - nh0, hb1 = 4503599627370496.0 - nh1;  // 2^52 + h
   const double *yl = ys + kq * pitch + rq;  // A[row = lane/4][col = lane%4]
   const int n_ks = n_src_pad >> 2;
@@ -339,8 +339,13 @@ __global__ void __launch_bounds__(512) k_bconv_mma(const ModConst *__restrict__ 
       v1 = reduce_signed(__fma_rn(v1, 4096.0, acc[h][1][1]), m1.q, m1.qinv);
       v0 = reduce_signed(__fma_rn(v0, 4096.0, acc[h][0][0]), m0.q, m0.qinv);
       v1 = reduce_signed(__fma_rn(v1, 4096.0, acc[h][0][1]), m1.q, m1.qinv);
-      if (live0) o0[(mt + h) * 8] = (u64)__double_as_longlong(v0 + hb0) & 0x000FFFFFFFFFFFFFull;
-      if (live1) o1[(mt + h) * 8] = (u64)__double_as_longlong(v1 + hb1) & 0x000FFFFFFFFFFFFFull;
+      if (a.out_f64) {  // uniform
+        if (live0) reinterpret_cast<double *>(o0)[(mt + h) * 8] = v0;
+        if (live1) reinterpret_cast<double *>(o1)[(mt + h) * 8] = v1;
+      } else {
+        if (live0) o0[(mt + h) * 8] = (u64)__double_as_longlong(v0 + hb0) & 0x000FFFFFFFFFFFFFull;
+        if (live1) o1[(mt + h) * 8] = (u64)__double_as_longlong(v1 + hb1) & 0x000FFFFFFFFFFFFFull;
+      }
     }
   }
 }

@@ -64,6 +64,9 @@ struct BConvArgs {
   // before the conversion; fold = [n_src-1][3] 12-bit pieces of the per-source constants, or null
   const double *fold;
   int fold_mod;
+  // 1: store the centred remainder as a double (|v| <= q/2) instead of the canonical word — the hand-off format to a
+  // forward NTT launched with NttLaunch::in_f64 (saves the canonicalisation here and the integer -> double conversion there)
+  int out_f64;
 };
 inline int bconv_pad_src(int n_src) { return (n_src + 3) & ~3; }   // k-steps of 4 sources
 inline int bconv_pad_dst(int n_dst) { return (n_dst + 7) & ~7; }   // target blocks of 8 (one warp each); n_dst <= 128

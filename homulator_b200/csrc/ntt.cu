@@ -155,7 +155,7 @@ __device__ __forceinline__ void col_issue(const ColWork &w, const double *tw_tab
   }
 }
 
-template <int LOGR1, int NT>
+template <int LOGR1, int NT, bool IN_F64>
 __global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_fwd_cols(NttTables t, int logN, LimbMap lm, NttLaunch l, int total) {
   using K = ColCfg<LOGR1, NT>;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_fwd_col
     const double q = mc.q, qinv = mc.qinv;
     double a[16], w[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) a[j] = u64_to_f64(reinterpret_cast<const u64 *>(data)[tid + NT * j]);
+    for (int j = 0; j < 16; ++j) a[j] = IN_F64 ? data[tid + NT * j] : u64_to_f64(reinterpret_cast<const u64 *>(data)[tid + NT * j]);
     // A constant added to coefficient 0 appears unchanged in every evaluation slot: subtracting h = (q-1)/2 here makes
     // the row pass's centred reduction land in [-h, h] = [0, q-1] - h, so its canonicalisation is one add (no sign fix).
     if (cur.tile == 0 && tid == 0 && l.fuse.x == nullptr) a[0] -= (q - 1.0) * 0.5;
@@ -619,11 +619,13 @@ static void launch_cols_t(bool inverse, const NttTables &t, int logN, const Limb
   const int grid = total < resident ? total : resident;
   static PerDeviceOnce once;
   if (once.first()) {
-    allow_smem(ntt_fwd_cols<LOGR1, NT>, 2 * K::STAGE_BYTES);
+    allow_smem(ntt_fwd_cols<LOGR1, NT, false>, 2 * K::STAGE_BYTES);
+    allow_smem(ntt_fwd_cols<LOGR1, NT, true>, 2 * K::STAGE_BYTES);
     allow_smem(ntt_inv_cols<LOGR1, NT>, 2 * K::STAGE_BYTES);
   }
   if (inverse) launch_pdl(ntt_inv_cols<LOGR1, NT>, grid, NT, 2 * K::STAGE_BYTES, s, t, logN, lm, l, total);
-  else launch_pdl(ntt_fwd_cols<LOGR1, NT>, grid, NT, 2 * K::STAGE_BYTES, s, t, logN, lm, l, total);
+  else if (l.in_f64) launch_pdl(ntt_fwd_cols<LOGR1, NT, true>, grid, NT, 2 * K::STAGE_BYTES, s, t, logN, lm, l, total);
+  else launch_pdl(ntt_fwd_cols<LOGR1, NT, false>, grid, NT, 2 * K::STAGE_BYTES, s, t, logN, lm, l, total);
 }
 
 static int col_threads() {

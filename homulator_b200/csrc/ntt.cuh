@@ -82,6 +82,7 @@ struct NttLaunch {
   // inverse only: per-limb post-scale constant c (folded with N^-1 on the host): out = INTT(in) * c, canonical.
   const double2 *post_scale;  // [n_limbs] (c*ninv mod q, RN(that / q)) or nullptr for plain N^-1
   NttFuse fuse;               // forward only
+  int in_f64;                 // forward only, two-pass rings: `in` holds signed doubles |v| <= q (BConvArgs::out_f64)
 };
 
 void launch_ntt_forward(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s);
