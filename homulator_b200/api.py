@@ -52,7 +52,7 @@ EXPORTS = [
     "hml_d2h", "hml_sync", "hml_ntt", "hml_intt", "hml_ntt_batch", "hml_intt_batch", "hml_ewe", "hml_automorph", "hml_bconv", "hml_keyswitch", "hml_rescale",
     "hml_hmult", "hml_hrotate", "hml_hadd", "hml_pmult", "hml_padd", "hml_hmult_batch", "hml_hrotate_batch",
     "hml_hmult_host", "hml_hrotate_host", "hml_host_alloc_pinned", "hml_host_free_pinned", "hml_trace_counts",
-    "hml_get_counts", "hml_exec_counts_get", "hml_exec_counts_reset", "hml_cli_main",
+    "hml_get_counts", "hml_buffer_plan", "hml_exec_counts_get", "hml_exec_counts_reset", "hml_cli_main",
     "hml_shard_layout", "hml_keyswitch_shard_begin", "hml_keyswitch_shard_mid", "hml_keyswitch_shard_end",
 ]
 
@@ -102,6 +102,7 @@ def load_library():
     L.hml_host_free_pinned.argtypes = [vp, vp]
     L.hml_trace_counts.argtypes = [C.c_char_p, u32, u32, u32, u32, u32, u32, u32, C.POINTER(_Counts)]
     L.hml_get_counts.argtypes = [vp, C.c_char_p, u32, C.POINTER(_Counts)]
+    L.hml_buffer_plan.argtypes = [vp, C.c_char_p, u32, C.c_char_p, u64]
     L.hml_exec_counts_get.argtypes = [vp, C.POINTER(_ExecCounts)]
     L.hml_exec_counts_reset.argtypes = [vp]
     L.hml_cli_main.argtypes = [i32, C.POINTER(C.c_char_p)]
@@ -351,6 +352,12 @@ class Context:
         if rc:
             raise HmlError(rc, self.lib.hml_last_create_error().decode())
         return _counts_to_dict(c)
+
+    def buffer_plan(self, op, L):
+        """the op's device workspace as `Malloc <name> from A to B` lines (reference include/Addr.h:29-48)"""
+        buf = C.create_string_buffer(8192)
+        self._chk(self.lib.hml_buffer_plan(self.h, op.encode(), L, buf, len(buf)))
+        return buf.value.decode()
 
     def exec_counts(self, reset=False):
         e = _ExecCounts()

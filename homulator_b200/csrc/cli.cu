@@ -140,6 +140,10 @@ extern "C" int hml_cli_main(int argc, char **argv) {
     if (op == "pmult") return hml_pmult(ctx, L, a, b, out, nullptr);
     return hml_padd(ctx, L, a, b, out, nullptr);
   };
+  {  // buffer plan, like the reference's `Malloc <name> from A to B` lines (reference include/Addr.h:46-47)
+    std::vector<char> plan(8192);
+    if (hml_buffer_plan(ctx, op.c_str(), L, plan.data(), plan.size()) == HML_OK) fputs(plan.data(), stdout);
+  }
   std::string OP = op;
   std::transform(OP.begin(), OP.end(), OP.begin(), ::toupper);
   printf("\n\nWelcome! Start executing %s on %s (%d SMs)!\n\n", OP.c_str(), prop.name, prop.multiProcessorCount);

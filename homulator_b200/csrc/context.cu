@@ -1253,6 +1253,50 @@ extern "C" int hml_get_counts(const hml_ctx *ctx, const char *op, uint32_t L, hm
   return hml_trace_counts(op, p.N, p.batch_size, p.max_level, L, p.alpha, p.bconv_high, p.bconv_width, out);
 }
 
+extern "C" int hml_buffer_plan(const hml_ctx *ctx, const char *op, uint32_t L, char *out, uint64_t cap) {
+  if (!ctx || !op || !out || cap == 0) return HML_ERR_INVALID;
+  const Params &p = ctx->p;
+  if (L < 1 || L > p.max_level) return HML_ERR_INVALID;
+  const std::string o(op);
+  const uint32_t A = p.alpha, E = L + A, beta = p.beta(L), bs = std::max<uint32_t>(1, p.batch_size);
+  const bool merged = o == "hmult" && p.logN > NTT_SMALL_LOG;
+  std::string text;
+  uint64_t limb = 0;  // running limb index inside the workspace
+  auto add = [&](const std::string &name, uint64_t n_limbs) {
+    char line[160];
+    snprintf(line, sizeof(line), "Malloc %s from %llu to %llu\n", name.c_str(), (unsigned long long)(limb * bs),
+             (unsigned long long)((limb + (n_limbs ? n_limbs - 1 : 0)) * bs));
+    text += line;
+    limb += n_limbs;
+  };
+  auto keyswitch = [&](uint32_t acc_limbs, bool with_vb) {
+    add("ModUpINTTOut", L);  // K1 + K2 (digit scaling folded in)
+    for (uint32_t j = 0; j < beta; ++j) add("BConvOut_(" + std::to_string(j) + ") = NTTOut_beta(" + std::to_string(j) + ")", E);
+    for (int k = 0; k < 2; ++k) add("InnerProduceOut_Key" + std::to_string(k) + (acc_limbs > E ? " (+ Rescale INTT slot)" : ""), acc_limbs);
+    if (with_vb) for (int k = 0; k < 2; ++k) add("ModdownBConvOut_Key" + std::to_string(k) + " = NTTOut_ModDown_Key" + std::to_string(k), L);
+  };
+  if (o == "hmult") {
+    if (L < 2) return HML_ERR_INVALID;
+    add("TensorD0Out", L); add("TensorD1Out", L); add("TensorD2Out", L);
+    if (merged) {
+      keyswitch(E + 1, false);
+      for (int k = 0; k < 2; ++k) add("ModdownBConvOut_Key" + std::to_string(k) + " (merged with Rescale)", L - 1);
+    } else {
+      for (int k = 0; k < 2; ++k) add("HMULTHaddOutput" + std::to_string(k), L);
+      keyswitch(E, true);
+    }
+  } else if (o == "hrotate") {
+    add("AUTOOutput(0)", L); add("AUTOOutput(1)", L);
+    keyswitch(E, true);
+  } else if (o == "hadd" || o == "pmult" || o == "padd") {
+    text = "(no intermediates: one element-wise pass per component)\n";
+  } else {
+    return HML_ERR_OP;
+  }
+  snprintf(out, (size_t)cap, "%s", text.c_str());
+  return HML_OK;
+}
+
 extern "C" int hml_exec_counts_get(const hml_ctx *ctx, hml_exec_counts *out) {
   if (!ctx || !out) return HML_ERR_INVALID;
   *out = ctx->exec;

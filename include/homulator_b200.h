@@ -202,6 +202,12 @@ typedef struct {
   uint64_t ntt_limbs, intt_limbs, ewe_limbs, bconv_limb_macs, automorph_limbs;
   uint64_t kernel_launches;
 } hml_exec_counts;
+/* Buffer plan of one op at level L (reference AddrManage::MallocMem, include/Addr.h:29-48, which prints one
+ * `Malloc <name> from A to B` line per intermediate): the device workspace this library carves up for the op, one line per
+ * buffer with the reference's buffer names and address unit (limb stride = batchSize addresses; A and B are the base
+ * addresses of the first and last limb).  Writes a NUL-terminated string of at most cap bytes; returns HML_OK. */
+int hml_buffer_plan(const hml_ctx *ctx, const char *op, uint32_t L, char *out, uint64_t cap);
+
 int hml_exec_counts_get(const hml_ctx *ctx, hml_exec_counts *out);
 int hml_exec_counts_reset(hml_ctx *ctx);
 

@@ -261,3 +261,21 @@ def test_invalid_key_layout_is_rejected():
         ctx.hmult(4, x, x, evk, evk_q_limbs=3)   # fewer Q-limbs in the key than the level needs
     with pytest.raises(hml.HmlError):
         ctx.hmult(4, x, x, evk, evk_q_limbs=7)   # more than maxLevel
+
+
+def test_buffer_plan_follows_reference_names(north_star):
+    """reference AddrManage::MallocMem (include/Addr.h:29-48) prints one `Malloc <name> from A to B` line per intermediate,
+    addresses in units of batchSize per limb; hml_buffer_plan does the same for the device workspace"""
+    ctx, *_ = north_star
+    plan = ctx.buffer_plan("hmult", 35).splitlines()
+    assert plan[0] == "Malloc TensorD0Out from 0 to %d" % (34 * 256)
+    assert plan[1] == "Malloc TensorD1Out from %d to %d" % (35 * 256, 69 * 256)
+    assert any(l.startswith("Malloc ModUpINTTOut from") for l in plan)
+    assert sum(l.startswith("Malloc BConvOut_(") for l in plan) == 3          # beta = 3 digits of 50 limbs
+    assert sum(l.startswith("Malloc InnerProduceOut_Key") for l in plan) == 2
+    last = int(plan[-1].split()[-1]) // 256 + 1                                # limbs used by the plan
+    assert last == 3 * 35 + 35 + 3 * 50 + 2 * 51 + 2 * 34
+    rot = ctx.buffer_plan("hrotate", 35)
+    assert rot.startswith("Malloc AUTOOutput(0) from 0 to") and "NTTOut_ModDown_Key1" in rot
+    with pytest.raises(hml.HmlError):
+        ctx.buffer_plan("nonsense", 35)
