@@ -527,7 +527,7 @@ static int ks_front(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, Batc
     l.in = ext; l.out = ext; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)E * N;
     l.n_limbs = E; l.n_polys = beta;  // digit j skips the limbs it owns (LimbMap::skip)
     l.n_batch = nb; l.in_batch_stride = l.out_batch_stride = (long long)beta * E * N;
-    l.in_f64 = npass == 2;
+    l.in_f64 = l.out_f64 = npass == 2;  // doubles in from the conversion, raw lazy doubles out to the inner product
     launch_ntt_forward(ctx->tabs, logN, lc->ext_lm, l, s);
     ctx->exec.ntt_limbs += (uint64_t)nb * ((uint64_t)beta * E - L); ctx->exec.kernel_launches += npass;
   }
@@ -538,7 +538,7 @@ static int ks_front(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, Batc
     InnerArgs a{};
     a.d = d.ptr; a.ext = ext; a.evk = evk; a.acc = acc; a.N = N; a.n_ext = E; a.beta = beta; a.evk_limbs = evk_q_limbs + A;
     a.n_batch = nb; a.d_batch_stride = d.stride; a.ext_batch_stride = (long long)beta * E * N; a.acc_batch_stride = 2ll * AL * N;
-    a.acc_comp_stride = (long long)AL * N;
+    a.acc_comp_stride = (long long)AL * N; a.ext_f64 = npass == 2;
     launch_inner_product(ctx->mc, ip, a, s);
     ctx->exec.ewe_limbs += 2ull * nb * E * beta; ctx->exec.kernel_launches++;
   }

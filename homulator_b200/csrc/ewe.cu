@@ -133,7 +133,10 @@ __global__ void __launch_bounds__(EW_THREADS) k_inner(const ModConst *__restrict
 #pragma unroll
     for (int j = 0; j < IP_MAX_BETA; ++j)
       if (j < a.beta) {
-        const double t0 = u64_to_f64(t[j].x), t1 = u64_to_f64(t[j].y);
+        // converted digits may arrive as raw lazy doubles straight from the transform (own-digit limbs are always words)
+        const bool f64 = a.ext_f64 && j != own;
+        const double t0 = f64 ? __longlong_as_double((long long)t[j].x) : u64_to_f64(t[j].x);
+        const double t1 = f64 ? __longlong_as_double((long long)t[j].y) : u64_to_f64(t[j].y);
         s00 += mulmod_var(t0, k[j][0][0], m.q, m.qinv);
         s01 += mulmod_var(t1, k[j][0][1], m.q, m.qinv);
         s10 += mulmod_var(t0, k[j][1][0], m.q, m.qinv);

@@ -31,6 +31,7 @@ struct InnerArgs {
   int n_batch;                     // ciphertexts sharing the key: d / ext / acc advance by the strides below
   long long d_batch_stride, ext_batch_stride, acc_batch_stride;
   long long acc_comp_stride;       // words between the two accumulators of a ciphertext (0 = n_ext * N)
+  int ext_f64;                     // 1: `ext` holds the forward NTT's raw signed doubles (NttLaunch::out_f64), |v| < 2^41
 };
 void launch_inner_product(const ModConst *mc, const LimbMap &lm, const InnerArgs &a, cudaStream_t s);
 

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_fwd_col
     for (int j = 0; j < 16; ++j) a[j] = IN_F64 ? data[tid + NT * j] : u64_to_f64(reinterpret_cast<const u64 *>(data)[tid + NT * j]);
     // A constant added to coefficient 0 appears unchanged in every evaluation slot: subtracting h = (q-1)/2 here makes
     // the row pass's centred reduction land in [-h, h] = [0, q-1] - h, so its canonicalisation is one add (no sign fix).
-    if (cur.tile == 0 && tid == 0 && l.fuse.x == nullptr) a[0] -= (q - 1.0) * 0.5;
+    if (cur.tile == 0 && tid == 0 && l.fuse.x == nullptr && !l.out_f64) a[0] -= (q - 1.0) * 0.5;
     lds_run<1>(w, tw + 1); ct_level<0>(a, w, q, qinv);
     lds_run<2>(w, tw + 2); ct_level<1>(a, w, q, qinv);
     lds_run<4>(w, tw + 4); ct_level<2>(a, w, q, qinv);
@@ -401,12 +401,17 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
       ct_level<3>(a, w, q, qinv);
       if constexpr (!FUSE) {
         // canonical words back through the swizzled tile so that the global stores are 16 bytes per lane, 256 B per half-warp
+        if (l.out_f64) {  // uniform: the consumer takes the lazy sums as they are
+#pragma unroll
+          for (int m = 0; m < 8; ++m) *reinterpret_cast<double2 *>(data + ad.B(m)) = make_double2(a[2 * m], a[2 * m + 1]);
+        } else {
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
           // values are (true - h) mod q (bias planted by the column pass): centred remainder + h is canonical
           const u64 v0 = (u64)__double_as_longlong(reduce_signed(a[2 * m], q, qinv) + hb) & 0x000FFFFFFFFFFFFFull;
           const u64 v1 = (u64)__double_as_longlong(reduce_signed(a[2 * m + 1], q, qinv) + hb) & 0x000FFFFFFFFFFFFFull;
           *reinterpret_cast<ulonglong2 *>(data + ad.B(m)) = make_ulonglong2(v0, v1);
+        }
         }
         __syncwarp();
         u64 *outp = dst_of(cur) + (size_t)rr * 256 + (l16 >> 3) * 16 + (l16 & 7) * 2;
