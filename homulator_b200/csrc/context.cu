@@ -1056,12 +1056,16 @@ static int ew_ct_op(hml_ctx *ctx, uint32_t L, const uint64_t *a, const uint64_t 
   LevelConsts *lc;
   if ((rc = get_level(ctx, L, &lc))) return rc;
   const size_t N = ctx->p.N, PL = N * L;
-  for (int k = 0; k < 2; ++k) {
-    const u64 *x = (const u64 *)a + k * PL, *y = (const u64 *)b + (b_is_pt ? 0 : k * PL);
-    if (mul) launch_ewe(ctx->mc, lc->q_lm, (int)N, (int)L, x, y, nullptr, nullptr, 0, (u64 *)out + k * PL, (cudaStream_t)stream);
-    else launch_ewe(ctx->mc, lc->q_lm, (int)N, (int)L, x, nullptr, y, nullptr, 0, (u64 *)out + k * PL, (cudaStream_t)stream);
-    ctx->exec.ewe_limbs += L; ctx->exec.kernel_launches++;
+  // both components in one launch; a plaintext operand is repeated (stride 0)
+  const long long ct = (long long)PL, pt = b_is_pt ? 0 : (long long)PL;
+  if (mul) {
+    const long long cs[5] = {ct, pt, 0, 0, ct};
+    launch_ewe(ctx->mc, lc->q_lm, (int)N, (int)L, (const u64 *)a, (const u64 *)b, nullptr, nullptr, 0, (u64 *)out, (cudaStream_t)stream, 2, cs);
+  } else {
+    const long long cs[5] = {ct, 0, pt, 0, ct};
+    launch_ewe(ctx->mc, lc->q_lm, (int)N, (int)L, (const u64 *)a, nullptr, (const u64 *)b, nullptr, 0, (u64 *)out, (cudaStream_t)stream, 2, cs);
   }
+  ctx->exec.ewe_limbs += 2ull * L; ctx->exec.kernel_launches++;
   return check_launch(ctx, "ewe op");
 }
 extern "C" int hml_hadd(hml_ctx *ctx, uint32_t L, const uint64_t *a, const uint64_t *b, uint64_t *out, void *s) {

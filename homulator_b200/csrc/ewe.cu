@@ -16,8 +16,13 @@ __device__ __forceinline__ u64 finish(double v, const ModConst &m) { return f64_
 static inline dim3 ew_grid(int N, int ny, int nz = 1) { return dim3((N / 2 + EW_THREADS - 1) / EW_THREADS, ny, nz); }
 
 // ------------------------------------------------------------------------------------------------ generic EWE
+// grid.z = component of a ciphertext op: operand k advances by cs[k] words per component (0 repeats a plaintext), out by cs[4]
+struct EweStrides {
+  long long cs[5];
+};
 __global__ void __launch_bounds__(EW_THREADS) k_ewe(const ModConst *__restrict__ mc, LimbMap lm, int N, const u64 *x1,
-                                                    const u64 *x2, const u64 *x3, const u64 *x4, int subtract, u64 *out) {
+                                                    const u64 *x2, const u64 *x3, const u64 *x4, int subtract, u64 *out,
+                                                    EweStrides st) {
   pdl_launch_dependents();
   pdl_wait();
   const int i2 = blockIdx.x * EW_THREADS + threadIdx.x;
@@ -25,6 +30,12 @@ __global__ void __launch_bounds__(EW_THREADS) k_ewe(const ModConst *__restrict__
   const int limb = blockIdx.y;
   const ModConst m = mc[lm.mod[limb]];
   const size_t o = (size_t)limb * (N / 2) + i2;
+  const long long z = blockIdx.z;
+  if (x1) x1 += z * st.cs[0];
+  if (x2) x2 += z * st.cs[1];
+  if (x3) x3 += z * st.cs[2];
+  if (x4) x4 += z * st.cs[3];
+  out += z * st.cs[4];
   double p0 = 0, p1 = 0, s0 = 0, s1 = 0;
   if (x1) {
     ulonglong2 a = ld2(x1, o);
@@ -49,8 +60,10 @@ __global__ void __launch_bounds__(EW_THREADS) k_ewe(const ModConst *__restrict__
 }
 
 void launch_ewe(const ModConst *mc, const LimbMap &lm, int N, int n_limbs, const u64 *x1, const u64 *x2, const u64 *x3,
-                const u64 *x4, int subtract, u64 *out, cudaStream_t s) {
-  launch_pdl(k_ewe, ew_grid(N, n_limbs), EW_THREADS, 0, s, mc, lm, N, x1, x2, x3, x4, subtract, out);
+                const u64 *x4, int subtract, u64 *out, cudaStream_t s, int n_comp, const long long *comp_strides) {
+  EweStrides st{};
+  if (comp_strides) for (int k = 0; k < 5; ++k) st.cs[k] = comp_strides[k];
+  launch_pdl(k_ewe, ew_grid(N, n_limbs, n_comp), EW_THREADS, 0, s, mc, lm, N, x1, x2, x3, x4, subtract, out, st);
 }
 
 // ------------------------------------------------------------------------------------------------ tensor product

@@ -10,9 +10,11 @@
 
 namespace hml {
 
-// out = x1*x2 (+|-) x3*x4 per limb; null operands as in hml_ewe().  All [n_limbs][N].
+// out = x1*x2 (+|-) x3*x4 per limb; null operands as in hml_ewe().  All [n_limbs][N].  n_comp > 1 runs the components
+// of a ciphertext op in one launch: operand k advances by comp_strides[k] words per component (x1, x2, x3, x4, out;
+// 0 repeats a plaintext).
 void launch_ewe(const ModConst *mc, const LimbMap &lm, int N, int n_limbs, const u64 *x1, const u64 *x2, const u64 *x3,
-                const u64 *x4, int subtract, u64 *out, cudaStream_t s);
+                const u64 *x4, int subtract, u64 *out, cudaStream_t s, int n_comp = 1, const long long *comp_strides = nullptr);
 
 // TensorCompute (reference src/Operation.cpp:592-739): d0 = a0*b0, d1 = a0*b1 + a1*b0, d2 = a1*b1; limbs 0..L-1
 // n_batch ciphertext pairs: inputs advance by in_stride words per pair, outputs by out_stride.

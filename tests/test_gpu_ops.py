@@ -279,3 +279,15 @@ def test_buffer_plan_follows_reference_names(north_star):
     assert rot.startswith("Malloc AUTOOutput(0) from 0 to") and "NTTOut_ModDown_Key1" in rot
     with pytest.raises(hml.HmlError):
         ctx.buffer_plan("nonsense", 35)
+
+
+def test_parameter_set_sweep_module(tmp_path):
+    """python -m homulator_b200.sweep walks the reference's benchmark matrix (script/para*/micro24_*.sh): a thinned set-A
+    sweep must log one file per (op, level) under the reference's outLogs layout and summarise them"""
+    from homulator_b200 import sweep
+    rows = sweep.run(["A"], ["hmult", "padd"], 13, 1, str(tmp_path / "outLogs"), str(tmp_path / "sweep.md"))
+    assert [(r["op"], r["L"]) for r in rows] == [("hmult", 28), ("hmult", 15), ("hmult", 2), ("padd", 28), ("padd", 15), ("padd", 2)]
+    assert all(r["us_median"] > 0 and r["N"] == 32768 for r in rows)
+    assert rows[0]["trace_total"] == 390656  # SURVEY.md 8a golden: config_4_N15 hmult 28 28 28
+    assert (tmp_path / "outLogs" / "paraA" / "gpu" / "hmult" / "28_28" / "hmult_28_28_15.log").exists()
+    assert "## Set A" in (tmp_path / "sweep.md").read_text()
