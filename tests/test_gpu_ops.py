@@ -291,3 +291,23 @@ def test_parameter_set_sweep_module(tmp_path):
     assert rows[0]["trace_total"] == 390656  # SURVEY.md 8a golden: config_4_N15 hmult 28 28 28
     assert (tmp_path / "outLogs" / "paraA" / "gpu" / "hmult" / "28_28" / "hmult_28_28_15.log").exists()
     assert "## Set A" in (tmp_path / "sweep.md").read_text()
+
+
+def test_repeatability_stress(north_star):
+    """The kernels synchronise with warp-level barriers, cp.async groups, mbarriers and programmatic dependent launch;
+    a missing ordering would show up as run-to-run differences.  Repeat single and batched ops back to back (no host
+    synchronisation in between) and demand bit-identical results."""
+    ctx, o, a, b, evk = north_star
+    L, n = 35, 5
+    A = torch.stack([to_dev(a if i % 2 == 0 else b) for i in range(n)])
+    B = torch.stack([to_dev(b if i % 3 == 0 else a) for i in range(n)])
+    K = to_dev(evk)
+    ref_m, ref_r = ctx.hmult_batch(L, A, B, K), ctx.hrotate_batch(L, A, K, 5)
+    ref_1 = ctx.hmult(L, A[1], B[1], K)
+    assert torch.equal(ref_m[1], ref_1)
+    outs = []
+    for _ in range(8):
+        outs.append((ctx.hmult_batch(L, A, B, K), ctx.hrotate_batch(L, A, K, 5), ctx.hmult(L, A[1], B[1], K)))
+    torch.cuda.synchronize()
+    for m, r, s1 in outs:
+        assert torch.equal(m, ref_m) and torch.equal(r, ref_r) and torch.equal(s1, ref_1)
