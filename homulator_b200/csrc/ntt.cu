@@ -158,7 +158,7 @@ __device__ __forceinline__ void col_issue(const ColWork &w, const double *tw_tab
 template <int LOGR1, int NT, bool IN_F64>
 __global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_fwd_cols(NttTables t, int logN, LimbMap lm, NttLaunch l, int total) {
   using K = ColCfg<LOGR1, NT>;
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, c = tid % K::C, u = tid / K::C;
   const unsigned smem0 = smem_u32(smem);
   ColWork cur, nxt;
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_fwd_col
 template <int LOGR1, int NT>
 __global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_inv_cols(NttTables t, int logN, LimbMap lm, NttLaunch l, int total) {
   using K = ColCfg<LOGR1, NT>;
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, c = tid % K::C, u = tid / K::C;
   const unsigned smem0 = smem_u32(smem);
   ColWork cur, nxt;
