@@ -946,7 +946,6 @@ static size_t hmult_ws_words(const Params &p, uint32_t L, uint32_t nb) {
 // entry 1 (exact: it only adds one term < 2^36 to the 16-term sums).
 static int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, const u64 *ct_b, const u64 *evk, uint32_t evk_q_limbs,
                      u64 *ct_out, u64 *ws, cudaStream_t s) {
-  const PdlScope pdl(nb <= 2);
   const Params &p = ctx->p;
   const size_t N = p.N, PL = N * L;
   // d0 | d1 | d2 each [nb][L][N], cb [nb][2][L][N], then the key-switch / rescale workspace
@@ -1026,7 +1025,6 @@ static size_t hrot_ws_words(const Params &p, uint32_t L, uint32_t nb) { return (
 // nb ciphertexts [nb][2][L][N] -> [nb][2][L][N]
 static int hrot_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct, const u64 *rk, uint32_t evk_q_limbs, u64 g, u64 *ct_out,
                     u64 *ws, cudaStream_t s) {
-  const PdlScope pdl(nb <= 2);
   const size_t N = ctx->p.N, PL = N * L;
   u64 *sb = ws, *rest = sb + 2 * nb * PL;  // sb [nb][2][L][N]
   launch_automorph(ctx->p.logN, 2 * L * nb, ct, sb, g, s);  // reference :1302-1319

@@ -23,7 +23,6 @@ struct EweStrides {
 __global__ void __launch_bounds__(EW_THREADS) k_ewe(const ModConst *__restrict__ mc, LimbMap lm, int N, const u64 *x1,
                                                     const u64 *x2, const u64 *x3, const u64 *x4, int subtract, u64 *out,
                                                     EweStrides st) {
-  pdl_launch_dependents();
   pdl_wait();
   const int i2 = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i2 >= N / 2) return;
@@ -70,7 +69,6 @@ void launch_ewe(const ModConst *mc, const LimbMap &lm, int N, int n_limbs, const
 __global__ void __launch_bounds__(EW_THREADS) k_tensor3(const ModConst *__restrict__ mc, int N, const u64 *a0, const u64 *a1,
                                                         const u64 *b0, const u64 *b1, u64 *d0, u64 *d1, u64 *d2,
                                                         long long in_stride, long long out_stride) {
-  pdl_launch_dependents();
   pdl_wait();
   const int i2 = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i2 >= N / 2) return;
@@ -104,7 +102,6 @@ void launch_tensor3(const ModConst *mc, int N, int L, const u64 *a0, const u64 *
 // (the key is 60% of the traffic of an unbatched inner product).
 template <int IP_MAX_BETA>
 __global__ void __launch_bounds__(EW_THREADS) k_inner(const ModConst *__restrict__ mc, LimbMap lm, InnerArgs a) {
-  pdl_launch_dependents();
   pdl_wait();
   const int i2 = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i2 >= a.N / 2) return;
@@ -172,7 +169,6 @@ void launch_inner_product(const ModConst *mc, const LimbMap &lm, const InnerArgs
 
 // ------------------------------------------------------------------------------------------------ (x - y) * c (+ z)
 __global__ void __launch_bounds__(EW_THREADS) k_sub_mul_add(const ModConst *__restrict__ mc, LimbMap lm, SubMulArgs a) {
-  pdl_launch_dependents();
   pdl_wait();
   const int i2 = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i2 >= a.N / 2) return;
@@ -198,7 +194,6 @@ void launch_sub_mul_add(const ModConst *mc, const LimbMap &lm, const SubMulArgs 
 
 // ------------------------------------------------------------------------------------------------ automorphism
 __global__ void __launch_bounds__(EW_THREADS) k_automorph(int logN, const u64 *__restrict__ in, u64 *__restrict__ out, unsigned g) {
-  pdl_launch_dependents();
   pdl_wait();
   const unsigned N = 1u << logN;
   const unsigned k = blockIdx.x * EW_THREADS + threadIdx.x;
@@ -243,7 +238,6 @@ __global__ void __launch_bounds__(512) k_bconv_mma(const ModConst *__restrict__ 
   const size_t m_base = (size_t)blockIdx.x * tm;
   const u64 *in = a.in + (size_t)blockIdx.y * a.in_batch_stride;
   u64 *out = a.out + (size_t)blockIdx.y * a.out_batch_stride;
-  pdl_launch_dependents();
   // matrix fragments and moduli are constant tables: fetched before the programmatic dependency is resolved
   const bool mma_warp = tb * 8 < n_dst_pad;  // a launch with fewer than four target blocks has staging-only helper warps
   const int kq = lane & 3, rq = lane >> 2;

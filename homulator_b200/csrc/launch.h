@@ -15,15 +15,6 @@ inline int pdl_enabled() {
   return v;
 }
 
-// Measured on B200 (profiles/README.md): overlapping a kernel's start-up with its predecessor's tail takes 9 % off a single
-// hmult (18 short launches) but costs 5 % on 32-ciphertext chunks, so the composed ops switch it off for large batches.
-inline thread_local int g_pdl_scope = 1;
-struct PdlScope {
-  int saved;
-  explicit PdlScope(bool on) : saved(g_pdl_scope) { g_pdl_scope = on ? 1 : 0; }
-  ~PdlScope() { g_pdl_scope = saved; }
-};
-
 // cudaFuncSetAttribute is per device: true exactly once per (call site, device), so a process that drives several GPUs
 // opts every one of them into the large dynamic shared-memory carve-out
 struct PerDeviceOnce {
@@ -44,7 +35,7 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() && g_pdl_scope;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled();
   cfg.attrs = attr; cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }

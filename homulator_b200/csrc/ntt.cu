@@ -164,7 +164,6 @@ __global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_fwd_col
   ColWork cur, nxt;
   ColPos pos = col_pos(blockIdx.x < total ? blockIdx.x : 0, K::TILES, l.n_limbs, l.n_polys);
   const ColPos step = col_pos(gridDim.x, K::TILES, l.n_limbs, l.n_polys);
-  pdl_launch_dependents();
   pdl_wait();
   bool have = blockIdx.x < total && col_next<LOGR1, NT>(pos, step, true, lm, l, false, cur);
   if (have) col_issue<LOGR1, NT>(cur, t.fwd, t.mc, nullptr, logN, smem0);
@@ -215,7 +214,6 @@ __global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_inv_col
   ColWork cur, nxt;
   ColPos pos = col_pos(blockIdx.x < total ? blockIdx.x : 0, K::TILES, l.n_limbs, l.n_polys);
   const ColPos step = col_pos(gridDim.x, K::TILES, l.n_limbs, l.n_polys);
-  pdl_launch_dependents();
   pdl_wait();
   bool have = blockIdx.x < total && col_next<LOGR1, NT>(pos, step, true, lm, l, true, cur);
   if (have) col_issue<LOGR1, NT>(cur, t.inv, t.mc, l.post_scale, logN, smem0);
@@ -350,7 +348,6 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
   const RowItems items{l.n_polys, l.n_batch, lm.skip[limb], (int)gridDim.z};
   RowItem cur = items.next(RowItem{0, (int)blockIdx.z - (int)gridDim.z});
   RowItem nxt = items.valid(cur) ? items.next(cur) : cur;
-  pdl_launch_dependents();
   pdl_wait();  // the twiddle blob (a constant table) is already in flight; the data is another kernel's output
   if (items.valid(cur)) row_issue(src_of(cur), data0, lane, warp);
   cp_async_commit();
@@ -517,7 +514,6 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
 // ================================================================================ small N (<= 4096): one CTA per limb
 __global__ void __launch_bounds__(256) ntt_small(NttTables t, int logN, LimbMap lm, NttLaunch l, int inverse) {
   extern __shared__ double sm[];
-  pdl_launch_dependents();
   pdl_wait();
   const int limb = blockIdx.y % l.n_limbs, poly = (blockIdx.y / l.n_limbs) % l.n_polys, batch = blockIdx.y / (l.n_limbs * l.n_polys);
   if (poly == lm.skip[limb]) return;
