@@ -311,3 +311,13 @@ def test_repeatability_stress(north_star):
     torch.cuda.synchronize()
     for m, r, s1 in outs:
         assert torch.equal(m, ref_m) and torch.equal(r, ref_r) and torch.equal(s1, ref_1)
+
+
+def test_hmult_is_commutative_bitwise(north_star):
+    """d0 = a0 b0, d1 = a0 b1 + a1 b0, d2 = a1 b1 are symmetric in (a, b) and everything after the tensor product is a
+    function of (d0, d1, d2): hmult(a, b) and hmult(b, a) must agree bit for bit, single and batched."""
+    ctx, o, a, b, evk = north_star
+    A, B, K = to_dev(a), to_dev(b), to_dev(evk)
+    assert torch.equal(ctx.hmult(35, A, B, K), ctx.hmult(35, B, A, K))
+    AB, BA = torch.stack([A, B, A]), torch.stack([B, A, A])
+    assert torch.equal(ctx.hmult_batch(35, AB, BA, K), ctx.hmult_batch(35, BA, AB, K))

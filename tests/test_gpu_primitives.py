@@ -156,3 +156,24 @@ def test_errors_are_reported_not_raised_across_the_abi(big):
         ctx.hmult(1, x, x, x)  # L < 2
     with pytest.raises(hml.HmlError):
         ctx.hmult(46, x, x, x)  # L > maxLevel
+
+
+def test_full_size_properties_without_the_oracle(big):
+    """Size-independent properties at N = 2^16 over all 60 moduli: linearity of the transform, the convolution theorem on
+    a monomial (multiplying by X^s is a negacyclic shift), and the batched launch shape against the single-limb one."""
+    ctx, o = big
+    N, idx = 65536, list(range(60))
+    q = torch.tensor(o.moduli, dtype=torch.int64, device="cuda").view(60, 1)
+    a, b = ctx.uniform(idx, 11), ctx.uniform(idx, 12)
+    fa, fb = ctx.ntt(a, idx), ctx.ntt(b, idx)
+    assert torch.equal(ctx.ntt((a + b) % q, idx), (fa + fb) % q)                      # linearity, exact mod q
+    s = 12345
+    mono = torch.zeros(60, N, dtype=torch.int64, device="cuda")
+    mono[:, s] = 1
+    prod = ctx.intt(ctx.ewe(ctx.ntt(mono, idx), fb, None, None, idx), idx)              # X^s * b in Z_q[X]/(X^N + 1)
+    want = torch.cat([(q - b[:, N - s:]) % q, b[:, :N - s]], dim=1)
+    assert torch.equal(prod, want)
+    batch = torch.stack([a, b, (a + b) % q])
+    fbatch = ctx.ntt_batch(batch[:, :50].contiguous(), idx[:50])
+    assert torch.equal(fbatch[0], fa[:50]) and torch.equal(fbatch[1], fb[:50])
+    assert torch.equal(ctx.ntt_batch(fbatch, idx[:50], inverse=True), batch[:, :50])
