@@ -220,12 +220,12 @@ def main():
         return 0
 
     # ---------------- roofline of the dominant kernel pair: forward NTT (column pass + row pass), timed alone on the launch
-    # shape the batched step uses — the ModUp NTT of one chunk: 8 ciphertexts x 115 limbs in ONE launch pair
+    # shape the batched step uses — the ModUp NTT of one chunk: 32 ciphertexts x 115 limbs in ONE launch pair
     peak, peak_src = measured_peaks()
     W_bytes = 8 * N_RING
-    n_limbs, n_b = 115, 8
+    n_limbs, n_b = 115, 32
     idx = [ctx.ext_mod_idx(L)[i % (L + ALPHA)] for i in range(n_limbs)]
-    bufs = [ctx.uniform(idx, 50 + i, lead=(n_b,)) for i in range(2)]  # 2 x 482 MB >> L2: every launch reads from HBM
+    bufs = [ctx.uniform(idx, 50 + i, lead=(n_b,)) for i in range(2)]  # 2 x 1.9 GB >> L2: every launch reads from HBM
     dst = ctx.empty(n_b, n_limbs, N_RING)
     for i in range(3):
         ctx.ntt_batch(bufs[i % 2], idx, out=dst)
@@ -312,7 +312,7 @@ def main():
                 "batch_per_gpu_per_step": Be},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
-        "roofline": {"bound": "hbm", "kernel": "ntt_fwd_cols + ntt_rows (forward NTT pair, 8 ciphertexts x 115 limbs per launch)", "achieved": ntt_gbs,
+        "roofline": {"bound": "hbm", "kernel": "ntt_fwd_cols + ntt_rows (forward NTT pair, 32 ciphertexts x 115 limbs per launch)", "achieved": ntt_gbs,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ntt_gbs / peak, "traffic": traffic,
                      "algorithmic_bytes_per_launch": ntt_bytes},
         "cpu_baseline": cpu,

@@ -56,10 +56,10 @@ if op == "time":
     print("hrotate %.1f us" % timeit(lambda: ctx.hrotate(L, a, evk, 5)))
     d = ctx.uniform(q, 9)
     print("keyswitch %.1f us" % timeit(lambda: ctx.keyswitch(L, d, evk)))
-elif op == "ntt":  # the launch shape bench.py's roofline times: 8 ciphertexts x 115 limbs per launch pair
+elif op == "ntt":  # the launch shape bench.py's roofline times: 32 ciphertexts x 115 limbs per launch pair
     idx = [ctx.ext_mod_idx(L)[i % 50] for i in range(115)]
-    x = ctx.uniform(idx, 5, lead=(8,))
-    y = ctx.empty(8, 115, ctx.N)
+    x = ctx.uniform(idx, 5, lead=(32,))
+    y = ctx.empty(32, 115, ctx.N)
     for _ in range(n_warm + n_prof):
         ctx.ntt_batch(x, idx, out=y)
         ctx.ntt_batch(x, idx, out=y, inverse=True)
