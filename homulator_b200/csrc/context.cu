@@ -539,6 +539,7 @@ static int ks_front(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, Batc
     a.d = d.ptr; a.ext = ext; a.evk = evk; a.acc = acc; a.N = N; a.n_ext = E; a.beta = beta; a.evk_limbs = evk_q_limbs + A;
     a.n_batch = nb; a.d_batch_stride = d.stride; a.ext_batch_stride = (long long)beta * E * N; a.acc_batch_stride = 2ll * AL * N;
     a.acc_comp_stride = (long long)AL * N; a.ext_f64 = npass == 2;
+    a.acc_pack_limbs = npass == 2 ? (int)L : 0;  // Q-limb accumulators only feed element-wise epilogues: packed (5 B / coefficient)
     launch_inner_product(ctx->mc, ip, a, s);
     ctx->exec.ewe_limbs += 2ull * nb * E * beta; ctx->exec.kernel_launches++;
   }
@@ -587,7 +588,7 @@ static int ks_run(hml_ctx *ctx, uint32_t L, uint32_t nb, BatchPtr d, const u64 *
     l.n_limbs = L; l.n_polys = 2 * nb; l.n_batch = 1; l.in_f64 = npass == 2;
     if (fuse) {
       NttFuse &f = l.fuse;
-      f.x = acc; f.x_c_stride = (long long)E * N; f.x_b_stride = 2ll * E * N;
+      f.x = acc; f.x_c_stride = (long long)E * N; f.x_b_stride = 2ll * E * N; f.x_packed = 1;
       const BatchPtr zb = add0.ptr ? add0 : add1;  // component c reads zb.ptr + c * z_c_stride; only masked components are touched
       f.z = zb.ptr; f.z_b_stride = zb.stride;
       f.z_c_stride = (add0.ptr && add1.ptr) ? (long long)(add1.ptr - add0.ptr) : 0;
@@ -608,7 +609,7 @@ static int ks_run(hml_ctx *ctx, uint32_t L, uint32_t nb, BatchPtr d, const u64 *
     a.y = vb + (size_t)c * L * N; a.y_poly_stride = 2ll * L * N;
     a.z = add.ptr; a.z_poly_stride = add.stride;
     a.out = out.ptr; a.out_poly_stride = out.stride;
-    a.cst = lc->pinv; a.N = N; a.n_limbs = L; a.n_polys = nb;
+    a.cst = lc->pinv; a.N = N; a.n_limbs = L; a.n_polys = nb; a.x_packed = npass == 2;
     launch_sub_mul_add(ctx->mc, lc->q_lm, a, s);
     ctx->exec.ewe_limbs += (uint64_t)nb * (L + (a.z ? L : 0)); ctx->exec.kernel_launches++;
   }
@@ -950,9 +951,10 @@ static int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, con
   const size_t N = p.N, PL = N * L;
   // d0 | d1 | d2 each [nb][L][N], cb [nb][2][L][N], then the key-switch / rescale workspace
   u64 *d0 = ws, *d1 = d0 + nb * PL, *d2 = d1 + nb * PL;
-  launch_tensor3(ctx->mc, (int)N, (int)L, ct_a, ct_a + PL, ct_b, ct_b + PL, d0, d1, d2, (int)nb, (long long)(2 * PL), (long long)PL, s);  // reference :592-739
+  const int merged = p.logN > NTT_SMALL_LOG;  // d0 / d1 then only feed element-wise epilogues: stored packed
+  launch_tensor3(ctx->mc, (int)N, (int)L, ct_a, ct_a + PL, ct_b, ct_b + PL, d0, d1, d2, (int)nb, (long long)(2 * PL), (long long)PL, s, merged);  // reference :592-739
   ctx->exec.ewe_limbs += 3ull * nb * L; ctx->exec.kernel_launches++;
-  if (p.logN <= NTT_SMALL_LOG) {  // single-pass rings: the textbook sequence
+  if (!merged) {  // single-pass rings: the textbook sequence
     u64 *cb = d2 + nb * PL, *rest = cb + 2 * nb * PL;
     int rc = ks_run(ctx, L, nb, {d2, (long long)PL}, evk, evk_q_limbs, {cb, (long long)(2 * PL)}, {cb + PL, (long long)(2 * PL)}, {d0, (long long)PL},
                     {d1, (long long)PL}, rest, s);
@@ -976,7 +978,7 @@ static int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, con
     a.y = nullptr;
     a.z = (c ? d1 : d0) + (size_t)(L - 1) * N; a.z_poly_stride = (long long)PL;
     a.out = ul + (size_t)c * N; a.out_poly_stride = 2ll * N;
-    a.cst = lc->pinv + (L - 1); a.N = N; a.n_limbs = 1; a.n_polys = nb;
+    a.cst = lc->pinv + (L - 1); a.N = N; a.n_limbs = 1; a.n_polys = nb; a.x_packed = a.z_packed = 1;
     launch_sub_mul_add(ctx->mc, lc->last_lm, a, s);
     ctx->exec.ewe_limbs += 2ull * nb; ctx->exec.kernel_launches++;
   }
@@ -1002,7 +1004,7 @@ static int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, con
     f.x = acc; f.x_c_stride = (long long)AL * N; f.x_b_stride = 2ll * AL * N;
     f.z = d0; f.z_c_stride = (long long)(d1 - d0); f.z_b_stride = (long long)PL; f.z_mask = 3;
     f.dst = ct_out; f.dst_c_stride = (long long)(L - 1) * N; f.dst_b_stride = 2ll * (L - 1) * N;
-    f.cst = lc->pinv; f.cst2 = lc->qlinv; f.n_c = 2;
+    f.cst = lc->pinv; f.cst2 = lc->qlinv; f.n_c = 2; f.x_packed = f.z_packed = 1;
     launch_ntt_forward(ctx->tabs, logN, lc->q_lm, l, s);
     ctx->exec.ntt_limbs += 2ull * nb * (L - 1); ctx->exec.kernel_launches += 2;
     ctx->exec.ewe_limbs += 2ull * nb * 4 * (L - 1);

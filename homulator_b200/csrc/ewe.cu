@@ -68,7 +68,7 @@ void launch_ewe(const ModConst *mc, const LimbMap &lm, int N, int n_limbs, const
 // ------------------------------------------------------------------------------------------------ tensor product
 __global__ void __launch_bounds__(EW_THREADS) k_tensor3(const ModConst *__restrict__ mc, int N, const u64 *a0, const u64 *a1,
                                                         const u64 *b0, const u64 *b1, u64 *d0, u64 *d1, u64 *d2,
-                                                        long long in_stride, long long out_stride) {
+                                                        long long in_stride, long long out_stride, int pack01) {
   pdl_wait();
   const int i2 = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i2 >= N / 2) return;
@@ -87,14 +87,19 @@ __global__ void __launch_bounds__(EW_THREADS) k_tensor3(const ModConst *__restri
     r1[k] = finish(mulmod_var(x0, y1, m.q, m.qinv) + mulmod_var(x1, y0, m.q, m.qinv), m);
     r2[k] = f64_to_canonical(mulmod_var(x1, y1, m.q, m.qinv), m.qi);
   }
-  st2(d0, o, r0[0], r0[1]);
-  st2(d1, o, r1[0], r1[1]);
+  if (pack01) {
+    st_packed2(d0 + (size_t)limb * N, N, i2, r0[0], r0[1]);
+    st_packed2(d1 + (size_t)limb * N, N, i2, r1[0], r1[1]);
+  } else {
+    st2(d0, o, r0[0], r0[1]);
+    st2(d1, o, r1[0], r1[1]);
+  }
   st2(d2, o, r2[0], r2[1]);
 }
 
 void launch_tensor3(const ModConst *mc, int N, int L, const u64 *a0, const u64 *a1, const u64 *b0, const u64 *b1, u64 *d0,
-                    u64 *d1, u64 *d2, int n_batch, long long in_stride, long long out_stride, cudaStream_t s) {
-  launch_pdl(k_tensor3, ew_grid(N, L, n_batch), EW_THREADS, 0, s, mc, N, a0, a1, b0, b1, d0, d1, d2, in_stride, out_stride);
+                    u64 *d1, u64 *d2, int n_batch, long long in_stride, long long out_stride, cudaStream_t s, int pack01) {
+  launch_pdl(k_tensor3, ew_grid(N, L, n_batch), EW_THREADS, 0, s, mc, N, a0, a1, b0, b1, d0, d1, d2, in_stride, out_stride, pack01);
 }
 
 // ------------------------------------------------------------------------------------------------ key-switch inner product
@@ -153,8 +158,13 @@ __global__ void __launch_bounds__(EW_THREADS) k_inner(const ModConst *__restrict
         s11 += mulmod_var(t1, k[j][1][1], m.q, m.qinv);
       }
     const size_t comp2 = (a.acc_comp_stride ? (size_t)a.acc_comp_stride : (size_t)a.n_ext * a.N) / 2;
-    st2(acc, (size_t)e * n2 + i2, finish(s00, m), finish(s01, m));
-    st2(acc, comp2 + (size_t)e * n2 + i2, finish(s10, m), finish(s11, m));
+    if (e < a.acc_pack_limbs) {  // uniform per CTA
+      st_packed2(acc + (size_t)e * a.N, a.N, i2, finish(s00, m), finish(s01, m));
+      st_packed2(acc + 2 * comp2 + (size_t)e * a.N, a.N, i2, finish(s10, m), finish(s11, m));
+    } else {
+      st2(acc, (size_t)e * n2 + i2, finish(s00, m), finish(s01, m));
+      st2(acc, comp2 + (size_t)e * n2 + i2, finish(s10, m), finish(s11, m));
+    }
   }
 }
 
@@ -176,12 +186,12 @@ __global__ void __launch_bounds__(EW_THREADS) k_sub_mul_add(const ModConst *__re
   const ModConst m = mc[lm.mod[limb]];
   const double2 c = a.cst[limb];
   const size_t o = (size_t)limb * (a.N / 2) + i2;
-  const ulonglong2 x = ld2(a.x + poly * a.x_poly_stride, o);
+  const ulonglong2 x = a.x_packed ? ld_packed2(a.x + poly * a.x_poly_stride + (size_t)limb * a.N, a.N, i2) : ld2(a.x + poly * a.x_poly_stride, o);
   const ulonglong2 y = a.y ? ld2(a.y + poly * a.y_poly_stride, o) : make_ulonglong2(0, 0);
   double r0 = mulmod_const(u64_to_f64(x.x) - u64_to_f64(y.x), c.x, c.y, m.q);
   double r1 = mulmod_const(u64_to_f64(x.y) - u64_to_f64(y.y), c.x, c.y, m.q);
   if (a.z) {
-    const ulonglong2 z = ld2(a.z + poly * a.z_poly_stride, o);
+    const ulonglong2 z = a.z_packed ? ld_packed2(a.z + poly * a.z_poly_stride + (size_t)limb * a.N, a.N, i2) : ld2(a.z + poly * a.z_poly_stride, o);
     r0 += u64_to_f64(z.x);
     r1 += u64_to_f64(z.y);
   }

@@ -18,8 +18,9 @@ void launch_ewe(const ModConst *mc, const LimbMap &lm, int N, int n_limbs, const
 
 // TensorCompute (reference src/Operation.cpp:592-739): d0 = a0*b0, d1 = a0*b1 + a1*b0, d2 = a1*b1; limbs 0..L-1
 // n_batch ciphertext pairs: inputs advance by in_stride words per pair, outputs by out_stride.
+// pack01: d0 and d1 are stored as packed limbs (modarith.cuh), d2 always as words.
 void launch_tensor3(const ModConst *mc, int N, int L, const u64 *a0, const u64 *a1, const u64 *b0, const u64 *b1,
-                    u64 *d0, u64 *d1, u64 *d2, int n_batch, long long in_stride, long long out_stride, cudaStream_t s);
+                    u64 *d0, u64 *d1, u64 *d2, int n_batch, long long in_stride, long long out_stride, cudaStream_t s, int pack01 = 0);
 
 // Key-switch inner product (reference src/Operation.cpp:294-414, emitted as MULT) over n_ext extended limbs:
 //   acc[c][e] = sum_j t_j[e] * evk[j][c][lm.pos[e]],   modulus lm.mod[e]
@@ -34,6 +35,7 @@ struct InnerArgs {
   long long d_batch_stride, ext_batch_stride, acc_batch_stride;
   long long acc_comp_stride;       // words between the two accumulators of a ciphertext (0 = n_ext * N)
   int ext_f64;                     // 1: `ext` holds the forward NTT's raw signed doubles (NttLaunch::out_f64), |v| < 2^41
+  int acc_pack_limbs;              // the accumulators of extended limbs e < acc_pack_limbs are stored as packed limbs
 };
 void launch_inner_product(const ModConst *mc, const LimbMap &lm, const InnerArgs &a, cudaStream_t s);
 
@@ -45,6 +47,7 @@ struct SubMulArgs {
   long long x_poly_stride, y_poly_stride, z_poly_stride, out_poly_stride;
   const double2 *cst;     // [n_limbs]
   int N, n_limbs, n_polys;
+  int x_packed, z_packed; // x / z hold packed limbs (modarith.cuh)
 };
 void launch_sub_mul_add(const ModConst *mc, const LimbMap &lm, const SubMulArgs &a, cudaStream_t s);
 

@@ -85,6 +85,21 @@ __device__ __forceinline__ void gs_butterfly(double &x, double &y, double w, dou
 // only the tail and wins everywhere (single hmult 347 -> 297 us, batched 194.7 -> 193.5 us).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// ---- packed limbs.  A residue has at most 36 significant bits, but the ABI word has 64: HBM-bound kernels that hand a limb
+// to another kernel of the same op store it "packed" inside the limb's own 8N-byte slot — a plane of N 32-bit low words at
+// the start of the slot, a plane of N bytes (bits 32..39) at byte offset 4N — 5 bytes per coefficient instead of 8.  The
+// slot geometry (strides, offsets) is unchanged, only 5/8 of it is touched.  i2 = index of a coefficient pair.
+__device__ __forceinline__ void st_packed2(u64 *limb_slot, size_t N, size_t i2, u64 a, u64 b) {
+  reinterpret_cast<uint2 *>(limb_slot)[i2] = make_uint2((unsigned)a, (unsigned)b);
+  reinterpret_cast<unsigned short *>(reinterpret_cast<unsigned char *>(limb_slot) + 4 * N)[i2] =
+      (unsigned short)((unsigned)(a >> 32) | ((unsigned)(b >> 32) << 8));
+}
+__device__ __forceinline__ ulonglong2 ld_packed2(const u64 *limb_slot, size_t N, size_t i2) {
+  const uint2 lo = __ldg(reinterpret_cast<const uint2 *>(limb_slot) + i2);
+  const unsigned hi = __ldg(reinterpret_cast<const unsigned short *>(reinterpret_cast<const unsigned char *>(limb_slot) + 4 * N) + i2);
+  return make_ulonglong2(((u64)(hi & 0xFFu) << 32) | lo.x, ((u64)(hi >> 8) << 32) | lo.y);
+}
+
 // per-modulus constants kept in device memory
 struct ModConst {
   double q;       // modulus as double

@@ -363,12 +363,20 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
     unsigned char *data = smem + ROW_TILE_BYTES + (k & 1) * ROW_TILE_BYTES;
     double a[16], w[8];
     if constexpr (FUSE) {
-      // the epilogue's operands (this warp's two rows of x and z, 4 KB each) start their trip to L2 now
+      // the epilogue's operands (this warp's two rows = 512 coefficients of x and z) start their trip to L2 now
       const NttFuse &f = l.fuse;
       const long long fb = cur.p / f.n_c, fc = cur.p % f.n_c;
-      const size_t off = (size_t)limb * ((size_t)1 << logN) + tile_off + (size_t)warp * 512 + lane * 16;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(f.x + fc * f.x_c_stride + fb * f.x_b_stride + off));
-      if (f.z != nullptr && ((f.z_mask >> fc) & 1u)) asm volatile("prefetch.global.L2 [%0];" ::"l"(f.z + fc * f.z_c_stride + fb * f.z_b_stride + off));
+      const size_t nn = (size_t)1 << logN, c0 = tile_off + (size_t)warp * 512;  // first coefficient of the warp's rows
+      auto prefetch = [&](const u64 *slot, int packed) {
+        const unsigned char *b = reinterpret_cast<const unsigned char *>(slot);
+        const unsigned char *p = nullptr;
+        if (!packed) p = b + c0 * 8 + lane * 128;                       // 4 KB of words
+        else if (lane < 16) p = b + c0 * 4 + lane * 128;                 // 2 KB of low words
+        else if (lane < 20) p = b + 4 * nn + c0 + (lane - 16) * 128;     // 512 high bytes
+        if (p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+      };
+      prefetch(f.x + fc * f.x_c_stride + fb * f.x_b_stride + (size_t)limb * nn, f.x_packed);
+      if (f.z != nullptr && ((f.z_mask >> fc) & 1u)) prefetch(f.z + fc * f.z_c_stride + fb * f.z_b_stride + (size_t)limb * nn, f.z_packed);
     }
     if constexpr (!INV) {
 #pragma unroll
@@ -423,20 +431,24 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
         __syncwarp();
         const NttFuse &f = l.fuse;
         const long long fb = cur.p / f.n_c, fc = cur.p % f.n_c;  // n_batch == 1 for fused launches
-        const size_t off = (size_t)limb * ((size_t)1 << logN) + tile_off + (size_t)rr * 256 + (l16 >> 3) * 16 + (l16 & 7) * 2;
-        const u64 *xp = f.x + fc * f.x_c_stride + fb * f.x_b_stride + off;
+        const size_t nn = (size_t)1 << logN;
+        const size_t ci = tile_off + (size_t)rr * 256 + (l16 >> 3) * 16 + (l16 & 7) * 2;  // first coefficient of this lane's chunk m = 0
+        const u64 *xs = f.x + fc * f.x_c_stride + fb * f.x_b_stride + (size_t)limb * nn;  // limb slots
         const bool has_z = f.z != nullptr && ((f.z_mask >> fc) & 1u);
-        const u64 *zp = has_z ? f.z + fc * f.z_c_stride + fb * f.z_b_stride + off : nullptr;
-        u64 *dp = f.dst + fc * f.dst_c_stride + fb * f.dst_b_stride + off;
+        const u64 *zs = has_z ? f.z + fc * f.z_c_stride + fb * f.z_b_stride + (size_t)limb * nn : nullptr;
+        u64 *dp = f.dst + fc * f.dst_c_stride + fb * f.dst_b_stride + (size_t)limb * nn + ci;
         const double2 cst = f.cst[limb];
+        auto load_chunk = [&](const u64 *slot, int packed, int m) -> ulonglong2 {
+          return packed ? ld_packed2(slot, nn, (ci >> 1) + 16 * m) : __ldg(reinterpret_cast<const ulonglong2 *>(slot + ci + 32 * m));
+        };
         ulonglong2 xv[8];
 #pragma unroll
-        for (int m = 0; m < 8; ++m) xv[m] = __ldg(reinterpret_cast<const ulonglong2 *>(xp + 32 * m));
+        for (int m = 0; m < 8; ++m) xv[m] = load_chunk(xs, f.x_packed, m);
         if (f.cst2 != nullptr) {  // ((x * c + z) - y) * c2: z is mandatory
           const double2 cst2 = f.cst2[limb];
           ulonglong2 zv[8];
 #pragma unroll
-          for (int m = 0; m < 8; ++m) zv[m] = __ldg(reinterpret_cast<const ulonglong2 *>(zp + 32 * m));
+          for (int m = 0; m < 8; ++m) zv[m] = load_chunk(zs, f.z_packed, m);
 #pragma unroll
           for (int m = 0; m < 8; ++m) {
             const double2 y = *reinterpret_cast<const double2 *>(data + ad.C(m));
@@ -449,7 +461,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
         } else if (has_z) {
           ulonglong2 zv[8];
 #pragma unroll
-          for (int m = 0; m < 8; ++m) zv[m] = __ldg(reinterpret_cast<const ulonglong2 *>(zp + 32 * m));
+          for (int m = 0; m < 8; ++m) zv[m] = load_chunk(zs, f.z_packed, m);
 #pragma unroll
           for (int m = 0; m < 8; ++m) {
             const double2 y = *reinterpret_cast<const double2 *>(data + ad.C(m));

@@ -68,6 +68,7 @@ struct NttFuse {
   const double2 *cst2;          // [n_limbs] or null
   int n_c;
   unsigned z_mask;              // z is added for component c iff bit c is set
+  int x_packed, z_packed;       // x / z hold packed limbs (modarith.cuh: 5 bytes per coefficient inside the 8N-byte slot)
 };
 
 // ---- launch descriptors (host side, ntt.cu)
