@@ -41,7 +41,10 @@ static int upload(hml_ctx *ctx, const std::vector<T> &h, T **dev) {
 
 // A base conversion prepared for launch: the matrix in 12-bit pieces, zero-padded, uploaded once; the destination LimbMap.
 // dst_pos[t] = limb slot (in the output buffer) of destination t.
-static int prepare_bconv(hml_ctx *ctx, const BConvTable &bt, const std::vector<uint32_t> &dst_pos, hml::HostBConv &out) {
+// fold_c (optional): the constants of BConvArgs::fold as integers, modulus index fold_mod; the tcgen05 image then carries the
+// fold as a virtual target (bconv_umma.cu) while the DMMA kernel keeps using the caller's 12-bit pieces.
+static int prepare_bconv(hml_ctx *ctx, const BConvTable &bt, const std::vector<uint32_t> &dst_pos, hml::HostBConv &out,
+                         const std::vector<u64> *fold_c = nullptr, uint32_t fold_mod = 0) {
   const int ns = (int)bt.src.size(), nd = (int)bt.dst.size();
   const int nsp = bconv_pad_src(ns), ndp = bconv_pad_dst(nd);
   out.n_src = ns; out.n_dst = nd;
@@ -58,12 +61,24 @@ static int prepare_bconv(hml_ctx *ctx, const BConvTable &bt, const std::vector<u
       d[2] = (double)(h >> 24);
     }
   }
+  {
+    std::vector<u64> dq(nd);
+    for (int t = 0; t < nd; ++t) dq[t] = ctx->p.mod[bt.dst[t]];
+    std::vector<uint8_t> img;
+    BConvImage im;
+    if (bconv_image_build(bt.hat.data(), ns, nd, dq.data(), fold_c ? fold_c->data() : nullptr, fold_c ? ctx->p.mod[fold_mod] : 0, img, im)) {
+      int rc = upload(ctx, img, &out.d_img);
+      if (rc) return rc;
+      im.img = out.d_img;
+      out.im = im;
+    }
+  }
   return upload(ctx, m, &out.d_mat);
 }
 
 static void run_bconv(hml_ctx *ctx, const hml::HostBConv &hb, const LimbMap &src_lm, BConvArgs a, cudaStream_t s) {
   a.n_src = hb.n_src; a.n_dst = hb.n_dst;
-  launch_bconv(ctx->mc, src_lm, hb.dst_lm, a, hb.d_mat, s);
+  launch_bconv(ctx->mc, src_lm, hb.dst_lm, a, hb.d_mat, s, &hb.im);
   ctx->exec.kernel_launches++;
   ctx->exec.bconv_limb_macs += (uint64_t)hb.n_src * hb.n_dst * a.n_batches;
 }
@@ -150,18 +165,19 @@ extern "C" int hml_ctx_create(const char *cfg_path, uint32_t max_level, uint32_t
 
 static void free_level(LevelConsts &lc) {
   cudaFree(lc.modup_scale); cudaFree(lc.moddown_scale); cudaFree(lc.pinv); cudaFree(lc.qlinv);
-  for (auto &u : lc.up) cudaFree(u.d_mat);
+  for (auto &u : lc.up) { cudaFree(u.d_mat); cudaFree(u.d_img); }
   cudaFree(lc.down.d_mat); cudaFree(lc.merged_rest.d_mat); cudaFree(lc.merged_fold);
+  cudaFree(lc.down.d_img); cudaFree(lc.merged_rest.d_img);
 }
 
 extern "C" void hml_ctx_destroy(hml_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   for (auto &kv : ctx->levels) free_level(kv.second);
-  for (auto &kv : ctx->bconv_cache) { cudaFree(kv.second.step1); cudaFree(kv.second.host.d_mat); }
+  for (auto &kv : ctx->bconv_cache) { cudaFree(kv.second.step1); cudaFree(kv.second.host.d_mat); cudaFree(kv.second.host.d_img); }
   for (auto &kv : ctx->shard_plans) {
-    cudaFree(kv.second.scale1); cudaFree(kv.second.scale2); cudaFree(kv.second.pinv); cudaFree(kv.second.down.d_mat);
-    for (auto &u : kv.second.up) cudaFree(u.d_mat);
+    cudaFree(kv.second.scale1); cudaFree(kv.second.scale2); cudaFree(kv.second.pinv); cudaFree(kv.second.down.d_mat); cudaFree(kv.second.down.d_img);
+    for (auto &u : kv.second.up) { cudaFree(u.d_mat); cudaFree(u.d_img); }
   }
   cudaFree(ctx->tw_fwd); cudaFree(ctx->tw_inv); cudaFree(ctx->tw_fwd_rows); cudaFree(ctx->tw_inv_rows); cudaFree(ctx->mc); cudaFree(ctx->ws); cudaFree(ctx->stage);
   if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
@@ -321,16 +337,18 @@ static int get_level(hml_ctx *ctx, uint32_t L, LevelConsts **out) {
     const uint32_t nr = L - 1;
     rest.hat.assign((size_t)(A + 1) * nr, 0);
     std::vector<double> fold(3 * (size_t)A);
+    std::vector<u64> fold_c(A);
     for (uint32_t j = 0; j < A; ++j) {
       for (uint32_t i = 0; i < nr; ++i) rest.hat[(size_t)j * nr + i] = h_mulmod(bt.hat[(size_t)j * L + i], pinv_i[i], p.mod[i]);
       const u64 ql = p.mod[L - 1], t = h_mulmod(bt.hat[(size_t)j * L + L - 1], pinv_i[L - 1], ql);
       const u64 neg = t ? ql - t : 0;  // minus: r = slot_E - v[L-1] * P^-1
+      fold_c[j] = neg;
       fold[3 * j] = (double)(neg & 0xFFF); fold[3 * j + 1] = (double)((neg >> 12) & 0xFFF); fold[3 * j + 2] = (double)(neg >> 24);
     }
     for (uint32_t i = 0; i < nr; ++i) rest.hat[(size_t)A * nr + i] = 1;
     std::vector<uint32_t> rest_pos(nr);
     for (uint32_t i = 0; i < nr; ++i) rest_pos[i] = i;
-    if ((rc = prepare_bconv(ctx, rest, rest_pos, lc.merged_rest))) return rc;
+    if ((rc = prepare_bconv(ctx, rest, rest_pos, lc.merged_rest, &fold_c, L - 1))) return rc;
     if ((rc = upload(ctx, fold, &lc.merged_fold))) return rc;
   }
   // ---- Rescale

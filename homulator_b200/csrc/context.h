@@ -19,6 +19,8 @@ namespace hml {
 struct HostBConv {
   int n_src = 0, n_dst = 0;
   double *d_mat = nullptr;   // [bconv_pad_src(n_src)][bconv_pad_dst(n_dst)][3]
+  uint8_t *d_img = nullptr;  // the same matrix as the tcgen05 kernel's int8 operand image (null: shape not eligible)
+  BConvImage im;
   LimbMap dst_lm;
   bool empty() const { return n_dst == 0; }
 };

@@ -385,7 +385,20 @@ static void launch_bconv_t(const ModConst *mc, const LimbMap &src_lm, const Limb
   else launch_pdl(k_bconv_mma<KS, false>, grid, threads, smem, s, mc, src_lm, dst_lm, a, mat, n_src_pad, n_dst_pad, tm);
 }
 
-void launch_bconv(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const double *mat, cudaStream_t s) {
+int bconv_umma_enabled() {
+  static const int v = [] {
+    const char *e = getenv("HML_BCONV_UMMA");
+    return e && atoi(e) == 0 ? 0 : 1;
+  }();
+  return v;
+}
+
+void launch_bconv(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const double *mat, cudaStream_t s,
+                  const BConvImage *im) {
+  if (im && im->img && a.N >= 128 && a.N % 128 == 0 && (a.fold != nullptr) == (im->fold != 0) && bconv_umma_enabled()) {
+    launch_bconv_umma(mc, src_lm, dst_lm, a, *im, s);
+    return;
+  }
   const int n_src_pad = bconv_pad_src(a.n_src), n_dst_pad = bconv_pad_dst(a.n_dst);
   static const int tm_env = [] {
     const char *e = getenv("HML_BCONV_TM");  // tuning knob: coefficients per CTA (<= 16 sources); 0 = adaptive

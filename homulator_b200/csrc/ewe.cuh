@@ -5,6 +5,8 @@
 //   AUTO         InsGen::GenAUTO  reference src/InsGen.cpp:46-71    (unit AUTOU, src/Components.cpp:173-266)
 //   BCONV_STEP2  InsGen::GenBCONV reference src/InsGen.cpp:263-313  (unit BCONVU, src/Components.cpp:268-362)
 #pragma once
+#include <vector>
+
 #include "modarith.cuh"
 #include "ntt.cuh"
 
@@ -74,10 +76,25 @@ struct BConvArgs {
   // forward NTT launched with NttLaunch::in_f64 (saves the canonicalisation here and the integer -> double conversion there)
   int out_f64;
 };
+// int8 operand image of a conversion matrix for the tcgen05 path (bconv_umma.cu): img == null -> the DMMA kernel runs
+struct BConvImage {
+  const uint8_t *img = nullptr;   // device, K * NP bytes in the kernel's shared-memory layout
+  int K = 0, NP = 0, ND = 0, n16 = 0, fold = 0;
+};
+// host: eligibility (n_src <= 48, 5 * pad8(n_dst + fold) <= 256) and image construction; see bconv_umma.cu
+bool bconv_image_shape(int n_src, int n_dst, int fold, BConvImage &im);
+bool bconv_image_build(const u64 *hat, int n_src, int n_dst, const u64 *dst_q, const u64 *fold, u64 fold_q, std::vector<uint8_t> &img,
+                       BConvImage &im);
+void launch_bconv_umma(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const BConvImage &im, cudaStream_t s);
+// HML_BCONV_UMMA=0 keeps every conversion on the DMMA kernel
+int bconv_umma_enabled();
 inline int bconv_pad_src(int n_src) { return (n_src + 3) & ~3; }   // k-steps of 4 sources
 inline int bconv_pad_dst(int n_dst) { return (n_dst + 7) & ~7; }   // target blocks of 8 (one warp each); n_dst <= 128
 // Source limb i is read at in + src_lm.pos[i] * N (modulus src_lm.mod[i], used by step 1 only); output limb t is
 // written at out + dst_lm.pos[t] * N with modulus dst_lm.mod[t].  N >= 16.
-void launch_bconv(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const double *mat, cudaStream_t s);
+// `im` (optional): the same matrix as an int8 operand image; when it is usable for this launch (N a multiple of 128,
+// image built with / without the fold as the launch asks) the conversion runs on tcgen05 (bconv_umma.cu) instead.
+void launch_bconv(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const double *mat, cudaStream_t s,
+                  const BConvImage *im = nullptr);
 
 }  // namespace hml
