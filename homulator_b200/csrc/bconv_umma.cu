@@ -16,8 +16,9 @@
 // integer-split BConv beats CUDA cores in ncu" — measured numbers in profiles/README.md.
 //
 // Kernel shape (one persistent CTA per SM, 512 threads, no warp specialisation, one __syncthreads per tile):
-//   tile    128 coefficients (UMMA M = 128: TMEM lane = coefficient) x all targets (UMMA N = NP <= 256 s32 columns,
-//           column = byte level b * ND + target) x K = 80 bytes per 16 sources, padded to a multiple of 32
+//   tile    128 coefficients (UMMA M = 128: TMEM lane = coefficient) x all targets (UMMA N = NP <= 256 s32 columns: byte
+//           levels 0 and 4 of target t in columns 2t, 2t + 1, levels 1..3 in columns (b + 1) * ND + t) x K = 80 bytes per
+//           16 sources, padded to a multiple of 32
 //   A       [K/16][128 rows][16 B] in shared memory = the canonical K-major no-swizzle UMMA layout (core matrix = 8 rows x
 //           16 B contiguous; SBO = 128 B between 8-row groups, LBO = 2048 B between 16-byte K chunks).  K order: chunk
 //           (i/16)*5 + a holds byte a of sources 16*(i/16) .. +15, so a thread that holds four consecutive sources of one
@@ -25,8 +26,8 @@
 //   B       the host-built image, same layout with NP rows, copied once per CTA
 //   D       two TMEM buffers of 256 columns: the MMA of tile n+1 runs while tile n's accumulators are drained
 //   loop    pack(n+1) -> sync -> [thread 0: MMA(n+1), commit] -> global loads(n+2) in flight -> wait MMA(n) ->
-//           epilogue(n): tcgen05.ld 4 targets x 5 levels, shift-add on the integer pipe, one FP64 reduction, 256-byte
-//           coalesced stores per warp and target
+//           epilogue(n): tcgen05.ld of 4 targets x 5 levels per trip, shift-add on the integer pipe, one FP64 reduction,
+//           256-byte coalesced stores per warp and target; the target pairs are dealt evenly to the 4 warps of a lane quarter
 // The optional fold of hmult's merged ModDown + Rescale (context.cu) is one more (virtual) target: its remainder r is
 // computed first by every warp for its rows and added to every real target's sum before the reduction.
 #include <algorithm>
@@ -42,6 +43,9 @@ namespace hml {
 static inline u64 h_mulmod64(u64 a, u64 b, u64 q) { return (u64)((unsigned __int128)a * b % q); }
 
 static inline int umma_k_index(int i, int a) { return ((i >> 4) * 5 + a) * 16 + (i & 15); }
+// accumulator column of (byte level b, target t): levels 0 and 4 are interleaved (columns 2t, 2t + 1) so that one TMEM load
+// hands the epilogue the register pair (low word, top bits) it assembles the 64-bit sum in; levels 1..3 follow, ND apart
+static inline int umma_n_index(int b, int t, int ND) { return b == 0 ? 2 * t : b == 4 ? 2 * t + 1 : (b + 1) * ND + t; }
 
 bool bconv_image_shape(int n_src, int n_dst, int fold, BConvImage &im) {
   im = BConvImage{};
@@ -76,7 +80,7 @@ bool bconv_image_build(const u64 *hat, int n_src, int n_dst, const u64 *dst_q, c
         const u64 ha = h_mulmod64(h, (1ull << (8 * a)) % q, q);
         const int k = umma_k_index(i, a);
         for (int b = 0; b < 5; ++b) {
-          const int n = b * im.ND + t;
+          const int n = umma_n_index(b, t, im.ND);
           img[(size_t)(k >> 4) * im.NP * 16 + (size_t)n * 16 + (k & 15)] = (uint8_t)(ha >> (8 * b));
         }
       }
@@ -95,10 +99,10 @@ extern "C" int hml_dbg_bconv_umma_model(const uint64_t *hat, int n_src, int n_ds
   std::vector<uint8_t> arow(im.K);
   std::vector<int32_t> T(im.NP);
   auto value = [&](int t) {  // exact integer sum_b 2^(8b) T_b[t] as the epilogue forms it
-    u64 acc = ((u64)(0x43300000u + (uint32_t)T[4 * im.ND + t]) << 32) | (uint32_t)T[t];
-    acc += (u64)(uint32_t)T[1 * im.ND + t] << 8;
-    acc += (u64)(uint32_t)T[2 * im.ND + t] << 16;
-    acc += (u64)(uint32_t)T[3 * im.ND + t] << 24;
+    u64 acc = ((u64)(0x43300000u + (uint32_t)T[umma_n_index(4, t, im.ND)]) << 32) | (uint32_t)T[umma_n_index(0, t, im.ND)];
+    acc += (u64)(uint32_t)T[umma_n_index(1, t, im.ND)] << 8;
+    acc += (u64)(uint32_t)T[umma_n_index(2, t, im.ND)] << 16;
+    acc += (u64)(uint32_t)T[umma_n_index(3, t, im.ND)] << 24;
     double d;
     memcpy(&d, &acc, 8);
     return d - 4503599627370496.0;
@@ -178,15 +182,6 @@ __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
   return v;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// the loaded registers are operands of the wait, so that no use of them can be scheduled above it
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[5][4]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(v[0][0]), "+r"(v[0][1]), "+r"(v[0][2]), "+r"(v[0][3]), "+r"(v[1][0]), "+r"(v[1][1]), "+r"(v[1][2]), "+r"(v[1][3]),
-                 "+r"(v[2][0]), "+r"(v[2][1]), "+r"(v[2][2]), "+r"(v[2][3]), "+r"(v[3][0]), "+r"(v[3][1]), "+r"(v[3][2]), "+r"(v[3][3]),
-                 "+r"(v[4][0]), "+r"(v[4][1]), "+r"(v[4][2]), "+r"(v[4][3])
-               :
-               : "memory");
-}
 __device__ __forceinline__ void tmem_ld_wait(uint32_t (&f)[5]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(f[0]), "+r"(f[1]), "+r"(f[2]), "+r"(f[3]), "+r"(f[4]) : : "memory");
 }
@@ -195,41 +190,91 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // sum_b 2^(8b) T_b as an exact double (< 2^52): the 64-bit integer is assembled directly inside the mantissa of 2^52
-__device__ __forceinline__ double level_sum(uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, uint32_t t4) {
-  u64 acc = ((u64)(0x43300000u + t4) << 32) | t0;
-  acc += (u64)t1 * 256u;
-  acc += (u64)t2 * 65536u;
-  acc += (u64)t3 * 16777216u;
+// The multipliers arrive as kernel parameters (LevelMul) the compiler cannot see through, otherwise ptxas expands the wide
+// multiply-adds by 2^8 / 2^16 / 2^24 into nine shift / carry instructions; (t0, t4) come out of one TMEM load as an aligned
+// register pair, so the 64-bit accumulator is formed in place.
+struct LevelMul {
+  uint32_t m8, m16, m24;  // 2^8, 2^16, 2^24, passed as kernel parameters
+};
+__device__ __forceinline__ double level_sum(const LevelMul &lm, uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, uint32_t t4) {
+  u64 acc;
+  asm("{\n\t.reg .b32 h;\n\tadd.u32 h, %2, 0x43300000;\n\tmov.b64 %0, {%1, h};\n\t}" : "=l"(acc) : "r"(t0), "r"(t4));
+  asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(t1), "r"(lm.m8));
+  asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(t2), "r"(lm.m16));
+  asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(t3), "r"(lm.m24));
   return __longlong_as_double((long long)acc) - 4503599627370496.0;
 }
 
 constexpr int UMMA_THREADS = 512;
 constexpr int UMMA_TM = 128;
 
-template <int N16>
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+// accumulators of four consecutive targets: e = (level 0, level 4) pairs, l[b - 1] = levels 1..3
+struct Quad {
+  uint32_t e[8];
+  uint32_t l[3][4];
+};
+// the loaded registers are operands of the wait, so that no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(Quad &q) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(q.e[0]), "+r"(q.e[1]), "+r"(q.e[2]), "+r"(q.e[3]), "+r"(q.e[4]), "+r"(q.e[5]), "+r"(q.e[6]), "+r"(q.e[7]),
+                 "+r"(q.l[0][0]), "+r"(q.l[0][1]), "+r"(q.l[0][2]), "+r"(q.l[0][3]), "+r"(q.l[1][0]), "+r"(q.l[1][1]), "+r"(q.l[1][2]),
+                 "+r"(q.l[1][3]), "+r"(q.l[2][0]), "+r"(q.l[2][1]), "+r"(q.l[2][2]), "+r"(q.l[2][3])
+               :
+               : "memory");
+}
+// the store is an asm statement so that the reduction above it is computed unconditionally (four interleaved dependency
+// chains per trip) instead of being sunk into a per-target branch
+__device__ __forceinline__ void st_if(void *p, u64 bits, bool on) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.global.b64 [%0], %1;\n\t}" ::"l"(p), "l"(bits), "r"((uint32_t)on) : "memory");
+}
+
+// tile -> (batch, 128-coefficient block) without a division per tile: the walk advances by gridDim.x tiles
+struct TileWalk {
+  int batch, m;
+  __device__ __forceinline__ void init(int tile, int tpb) { batch = tile / tpb; m = tile - batch * tpb; }
+  __device__ __forceinline__ void step(int by, int tpb) {
+    m += by;
+    while (m >= tpb) { m -= tpb; ++batch; }
+  }
+};
+
+// N16 = 16-source slabs; W = targets reduced per epilogue trip (3 or 4, whichever wastes fewer masked slots)
+template <int N16, bool FOLD, bool F64, int W>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
 k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BConvArgs a, const uint8_t *__restrict__ img, int K, int NP,
-             int ND, int has_fold, int tiles_per_batch, int n_tiles) {
+             int ND, int tiles_per_batch, int n_tiles, LevelMul lmul) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t a_bytes = (uint32_t)UMMA_TM * K;
   unsigned char *As = smem;                                  // two buffers
   unsigned char *Bs = smem + 2 * a_bytes;                    // NP * K
-  double2 *tq = reinterpret_cast<double2 *>(Bs + (size_t)NP * K);   // [ND] (q, 1/q) per target
-  uint64_t *bars = reinterpret_cast<uint64_t *>(tq + ND);    // two mbarriers
+  double2 *tq = reinterpret_cast<double2 *>(Bs + (size_t)NP * K);   // [ND + 4] (q, 1/q) per target (a trip may run 3 past the last)
+  long long *toff = reinterpret_cast<long long *>(tq + ND + 4);  // [ND + 4] byte offset of the target's limb in the output
+  uint64_t *bars = reinterpret_cast<uint64_t *>(toff + ND + 4);  // two mbarriers
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2);
+  // raw source words on their way from HBM: STAGES tiles of [N16 * 4][512 threads] words, every thread owns its slots
+  constexpr int STAGES = N16 <= 2 ? 3 : 2;
+  constexpr uint32_t stage_bytes = N16 * 4 * UMMA_THREADS * 8;
+  unsigned char *St = reinterpret_cast<unsigned char *>(bars + 4);
 
   // ---- constant set-up (before the programmatic dependency is resolved)
   for (uint32_t e = tid; e < 2 * a_bytes / 16; e += UMMA_THREADS) reinterpret_cast<uint4 *>(As)[e] = make_uint4(0, 0, 0, 0);
+  for (uint32_t e = tid; e < STAGES * stage_bytes / 16; e += UMMA_THREADS) reinterpret_cast<uint4 *>(St)[e] = make_uint4(0, 0, 0, 0);
   for (uint32_t e = tid; e < (uint32_t)NP * K / 16; e += UMMA_THREADS) reinterpret_cast<uint4 *>(Bs)[e] = __ldg(reinterpret_cast<const uint4 *>(img) + e);
-  const int ntv = a.n_dst + has_fold;
-  for (int t = tid; t < ND; t += UMMA_THREADS) {
+  const int ntv = a.n_dst + (FOLD ? 1 : 0);
+  for (int t = tid; t < ND + 4; t += UMMA_THREADS) {
     double2 c = make_double2(1.0, 1.0);
     if (t < ntv) {
       const ModConst m = mc[t < a.n_dst ? dst_lm.mod[t] : a.fold_mod];
       c = make_double2(m.q, m.qinv);
     }
     tq[t] = c;
+    toff[t] = t < a.n_dst ? (long long)dst_lm.pos[t] * a.N * 8 : 0;
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(tmem_slot)) : "memory");
@@ -250,40 +295,55 @@ k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BC
 
   // loader role: coefficient row lr, source group g (sources 16 s + 4 g .. + 3 of every 16-source slab s)
   const int g = tid & 3, lr = tid >> 2;
-  // epilogue role: TMEM lanes 32 (warp % 4) .. + 31 = coefficient rows, target blocks sub, sub + 4, ...
+  long long soff[N16][4];  // word offset of each of the thread's sources inside a batch; -1: beyond n_src (zero row)
+#pragma unroll
+  for (int s = 0; s < N16; ++s)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = s * 16 + g * 4 + k;
+      soff[s][k] = i < a.n_src ? (long long)src_lm.pos[i] * a.N + lr : -1;
+    }
+  // epilogue role: TMEM lanes 32 (warp % 4) .. + 31 = coefficient rows; the targets are dealt evenly to the four warps of a
+  // lane quarter as contiguous ranges, walked W targets per trip
   const int row = ((warp & 3) << 5) | lane, sub = warp >> 2;
   const uint32_t t_lane = (uint32_t)((warp & 3) << 5) << 16;
+  const int cb = a.n_dst >> 2, cr = a.n_dst & 3;
+  const int t_first = sub * cb + min(sub, cr);
+  const int t_end = t_first + cb + (sub < cr ? 1 : 0);
 
-  u64 y[N16][4];
-  auto load_tile = [&](int tile) {
-    const int batch = tile / tiles_per_batch;
-    const u64 *in = a.in + (size_t)batch * a.in_batch_stride + (size_t)(tile - batch * tiles_per_batch) * UMMA_TM + lr;
-#pragma unroll
-    for (int s = 0; s < N16; ++s)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int i = s * 16 + g * 4 + k;
-        y[s][k] = i < a.n_src ? __ldg(in + (size_t)src_lm.pos[i] * a.N) : 0ull;
-      }
-    if (a.step1) {  // uniform: per-source scaling inside the conversion (primitive entry point)
+  auto load_tile = [&](const TileWalk &w, int stage, bool on) {  // asynchronous: global -> the thread's staging slots
+    if (on) {
+      const u64 *in = a.in + (size_t)w.batch * a.in_batch_stride + (size_t)w.m * UMMA_TM;
+      const uint32_t dst = smem_addr(St + (size_t)stage * stage_bytes) + tid * 8;
 #pragma unroll
       for (int s = 0; s < N16; ++s)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (soff[s][k] >= 0)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (s * 4 + k) * UMMA_THREADS * 8), "l"(in + soff[s][k]) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");  // one group per tile slot, empty or not: the wait counts stay uniform
+  };
+  auto pack_tile = [&](int stage, unsigned char *Ab) {
+    const u64 *src = reinterpret_cast<const u64 *>(St + (size_t)stage * stage_bytes) + tid;
+#pragma unroll
+    for (int s = 0; s < N16; ++s) {
+      u64 y[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) y[k] = src[(s * 4 + k) * UMMA_THREADS];
+      if (a.step1) {  // uniform: per-source scaling inside the conversion (primitive entry point)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int i = s * 16 + g * 4 + k;
           if (i < a.n_src) {
             const ModConst m = mc[src_lm.mod[i]];
             const double2 sc = a.step1[i];
-            y[s][k] = f64_to_canonical(mulmod_const(u64_to_f64(y[s][k]), sc.x, sc.y, m.q), m.qi);
+            y[k] = f64_to_canonical(mulmod_const(u64_to_f64(y[k]), sc.x, sc.y, m.q), m.qi);
           }
         }
-    }
-  };
-  auto pack_tile = [&](unsigned char *Ab) {
-#pragma unroll
-    for (int s = 0; s < N16; ++s) {
-      const uint32_t l0 = (uint32_t)y[s][0], l1 = (uint32_t)y[s][1], l2 = (uint32_t)y[s][2], l3 = (uint32_t)y[s][3];
-      const uint32_t h0 = (uint32_t)(y[s][0] >> 32), h1 = (uint32_t)(y[s][1] >> 32), h2 = (uint32_t)(y[s][2] >> 32), h3 = (uint32_t)(y[s][3] >> 32);
+      }
+      const uint32_t l0 = (uint32_t)y[0], l1 = (uint32_t)y[1], l2 = (uint32_t)y[2], l3 = (uint32_t)y[3];
+      const uint32_t h0 = (uint32_t)(y[0] >> 32), h1 = (uint32_t)(y[1] >> 32), h2 = (uint32_t)(y[2] >> 32), h3 = (uint32_t)(y[3] >> 32);
       uint32_t *dst = reinterpret_cast<uint32_t *>(Ab + ((size_t)(s * 5) * UMMA_TM + lr) * 16 + 4 * g);
       dst[0 * UMMA_TM * 4] = __byte_perm(__byte_perm(l0, l1, 0x0040), __byte_perm(l2, l3, 0x0040), 0x5410);
       dst[1 * UMMA_TM * 4] = __byte_perm(__byte_perm(l0, l1, 0x0051), __byte_perm(l2, l3, 0x0051), 0x5410);
@@ -300,65 +360,66 @@ k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BC
               ks > 0);
     umma_commit(bar0 + 8u * buf);
   };
-  auto epilogue = [&](int tile, int buf) {
-    const int batch = tile / tiles_per_batch;
-    u64 *out = a.out + (size_t)batch * a.out_batch_stride + (size_t)(tile - batch * tiles_per_batch) * UMMA_TM + row;
+  auto epilogue = [&](const TileWalk &w, int buf) {
+    unsigned char *out = reinterpret_cast<unsigned char *>(a.out + (size_t)w.batch * a.out_batch_stride + (size_t)w.m * UMMA_TM + row);
     const uint32_t tb = tmem_base + t_lane + (uint32_t)buf * 256u;
     double rf = 0.0;
-    if (has_fold) {  // uniform
+    if (FOLD) {
       uint32_t f[5];
+      f[0] = tmem_ld1(tb + 2 * a.n_dst);
+      f[4] = tmem_ld1(tb + 2 * a.n_dst + 1);
 #pragma unroll
-      for (int b = 0; b < 5; ++b) f[b] = tmem_ld1(tb + b * ND + a.n_dst);
+      for (int b = 1; b < 4; ++b) f[b] = tmem_ld1(tb + (b + 1) * ND + a.n_dst);
       tmem_ld_wait(f);
       const double2 c = tq[a.n_dst];
-      rf = canonicalize(reduce_signed(level_sum(f[0], f[1], f[2], f[3], f[4]), c.x, c.y), c.x);
+      rf = canonicalize(reduce_signed(level_sum(lmul, f[0], f[1], f[2], f[3], f[4]), c.x, c.y), c.x);
     }
-    const int n_blk = (a.n_dst + 3) >> 2;
-    uint32_t v[2][5][4];
-    if (sub < n_blk) {
+    auto fetch = [&](int t, Quad &q) {
+      tmem_ld8(tb + 2 * t, q.e);
 #pragma unroll
-      for (int b = 0; b < 5; ++b) tmem_ld4(tb + b * ND + 4 * sub, v[0][b]);
-    }
+      for (int b = 0; b < 3; ++b) tmem_ld4(tb + (b + 2) * ND + t, q.l[b]);
+    };
+    auto reduce4 = [&](int t, Quad &q) {
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        const double2 c = tq[t + j];
+        unsigned char *o = out + toff[t + j];
+        double s = level_sum(lmul, q.e[2 * j], q.l[0][j], q.l[1][j], q.l[2][j], q.e[2 * j + 1]);
+        if (FOLD) s += rf;
+        const double r = reduce_signed(s, c.x, c.y);
+        st_if(o, F64 ? (u64)__double_as_longlong(r) : f64_to_canonical(r, (u64)c.x), t + j < t_end);
+      }
+    };
+    Quad qa, qb;
+    if (t_first < t_end) fetch(t_first, qa);
 #pragma unroll 1
-    for (int blk = sub; blk < n_blk; blk += 8) {  // two blocks per trip: the second block's accumulators load while the first is reduced
-      tmem_ld_wait(v[0]);
-      const bool more1 = blk + 4 < n_blk;
-      if (more1) {
-#pragma unroll
-        for (int b = 0; b < 5; ++b) tmem_ld4(tb + b * ND + 4 * (blk + 4), v[1][b]);
-      }
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int bl = blk + 4 * h;
-        if (h == 1) {
-          if (!more1) break;
-          tmem_ld_wait(v[1]);
-          if (bl + 4 < n_blk) {
-#pragma unroll
-            for (int b = 0; b < 5; ++b) tmem_ld4(tb + b * ND + 4 * (bl + 4), v[0][b]);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int t = 4 * bl + j;
-          if (t < a.n_dst) {
-            const double2 c = tq[t];
-            const double r = reduce_signed(level_sum(v[h][0][j], v[h][1][j], v[h][2][j], v[h][3][j], v[h][4][j]) + rf, c.x, c.y);
-            u64 *o = out + (size_t)dst_lm.pos[t] * a.N;
-            if (a.out_f64) *reinterpret_cast<double *>(o) = r;
-            else *o = f64_to_canonical(r, (u64)c.x);
-          }
-        }
-      }
+    for (int t = t_first; t < t_end; t += 2 * W) {  // the next trip's accumulators are on their way from TMEM while this one is reduced
+      tmem_ld_wait(qa);
+      const bool more = t + W < t_end;
+      if (more) fetch(t + W, qb);
+      reduce4(t, qa);
+      if (!more) break;
+      tmem_ld_wait(qb);
+      if (t + 2 * W < t_end) fetch(t + 2 * W, qa);
+      reduce4(t + W, qb);
     }
     tmem_ld_wait();
   };
 
-  const int n_my = blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int n_my = (int)blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int stride = (int)gridDim.x;
   pdl_wait();  // the sources are another kernel's output; the outputs may still be read by one
   if (n_my > 0) {
-    load_tile(blockIdx.x);
-    pack_tile(As);
+    TileWalk wl, we;  // the loader runs STAGES tiles ahead of the epilogue
+    wl.init(blockIdx.x, tiles_per_batch);
+    we = wl;
+#pragma unroll
+    for (int d = 0; d < STAGES; ++d) {
+      load_tile(wl, d, d < n_my);
+      wl.step(stride, tiles_per_batch);
+    }
+    asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+    pack_tile(0, As);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -366,55 +427,80 @@ k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BC
       tc_fence_after();
       issue_mma(0);
     }
-    if (n_my > 1) load_tile(blockIdx.x + gridDim.x);
+    int st_next = STAGES > 1 ? 1 : 0, st_load = 0;  // stage of tile it + 1 / stage the next load refills (= the one tile `it` was in)
     for (int it = 0; it < n_my; ++it) {
       const int buf = it & 1;
       const bool next = it + 1 < n_my;
       if (next) {
-        pack_tile(As + (size_t)(buf ^ 1) * a_bytes);
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
+        pack_tile(st_next, As + (size_t)(buf ^ 1) * a_bytes);
         fence_async_smem();
       }
       tc_fence_before();
       __syncthreads();
-      if (next) {
-        if (tid == 0) {
-          tc_fence_after();
-          issue_mma(buf ^ 1);
-        }
-        if (it + 2 < n_my) load_tile(blockIdx.x + (it + 2) * gridDim.x);
+      if (next && tid == 0) {
+        tc_fence_after();
+        issue_mma(buf ^ 1);
       }
+      load_tile(wl, st_load, it + STAGES < n_my);
+      wl.step(stride, tiles_per_batch);
+      st_next = st_next + 1 == STAGES ? 0 : st_next + 1;
+      st_load = st_load + 1 == STAGES ? 0 : st_load + 1;
       mbar_wait(bar0 + 8u * buf, (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
-      epilogue(blockIdx.x + it * gridDim.x, buf);
+      epilogue(we, buf);
+      we.step(stride, tiles_per_batch);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
-template <int N16>
+template <int N16, bool FOLD, bool F64, int W>
 static void launch_umma_t(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const BConvImage &im, cudaStream_t s) {
   const int tiles_per_batch = a.N / UMMA_TM, n_tiles = tiles_per_batch * a.n_batches;
+  constexpr int STAGES = N16 <= 2 ? 3 : 2;
   // at least half of the SM's shared memory: ONE CTA per SM (a second one would only sit in tcgen05.alloc until the first ends)
-  const size_t smem = std::max<size_t>((size_t)2 * UMMA_TM * im.K + (size_t)im.NP * im.K + (size_t)im.ND * sizeof(double2) + 32, 116 * 1024);
+  const size_t need = (size_t)2 * UMMA_TM * im.K + (size_t)im.NP * im.K + (size_t)(im.ND + 4) * 24 + 32 + (size_t)STAGES * N16 * 4 * UMMA_THREADS * 8;
+  const size_t smem = std::max<size_t>(need, 116 * 1024);
   static PerDeviceOnce once;
   static int n_sm[64];
   int dev = 0;
   cudaGetDevice(&dev);
   if (once.first()) {
-    cudaFuncSetAttribute(k_bconv_umma<N16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * UMMA_TM * 256 + 256 * 256 + 64 * 16 + 32);  // 132 KB
+    cudaFuncSetAttribute(k_bconv_umma<N16, FOLD, F64, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaDeviceGetAttribute(&n_sm[dev & 63], cudaDevAttrMultiProcessorCount, dev);
   }
   const int grid = std::min(n_tiles, std::max(1, n_sm[dev & 63]));
-  launch_pdl(k_bconv_umma<N16>, dim3(grid), dim3(UMMA_THREADS), smem, s, mc, src_lm, dst_lm, a, im.img, im.K, im.NP, im.ND, im.fold, tiles_per_batch, n_tiles);
+  launch_pdl(k_bconv_umma<N16, FOLD, F64, W>, dim3(grid), dim3(UMMA_THREADS), smem, s, mc, src_lm, dst_lm, a, im.img, im.K, im.NP, im.ND, tiles_per_batch, n_tiles,
+             LevelMul{256u, 65536u, 16777216u});
+}
+
+template <int N16, bool FOLD, bool F64>
+static void launch_umma_w(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const BConvImage &im, cudaStream_t s) {
+  const int c = (a.n_dst + 3) / 4;  // targets per epilogue warp; trips of 3 or 4, whichever leaves fewer masked slots
+  if (((c + 2) / 3) * 3 < ((c + 3) / 4) * 4) launch_umma_t<N16, FOLD, F64, 3>(mc, src_lm, dst_lm, a, im, s);
+  else launch_umma_t<N16, FOLD, F64, 4>(mc, src_lm, dst_lm, a, im, s);
+}
+
+template <int N16>
+static void launch_umma_n(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const BConvImage &im, cudaStream_t s) {
+  if (im.fold) {
+    if (a.out_f64) launch_umma_w<N16, true, true>(mc, src_lm, dst_lm, a, im, s);
+    else launch_umma_w<N16, true, false>(mc, src_lm, dst_lm, a, im, s);
+  } else {
+    if (a.out_f64) launch_umma_w<N16, false, true>(mc, src_lm, dst_lm, a, im, s);
+    else launch_umma_w<N16, false, false>(mc, src_lm, dst_lm, a, im, s);
+  }
 }
 
 void launch_bconv_umma(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const BConvImage &im, cudaStream_t s) {
   switch (im.n16) {
-    case 1: launch_umma_t<1>(mc, src_lm, dst_lm, a, im, s); break;
-    case 2: launch_umma_t<2>(mc, src_lm, dst_lm, a, im, s); break;
-    default: launch_umma_t<3>(mc, src_lm, dst_lm, a, im, s); break;
+    case 1: launch_umma_n<1>(mc, src_lm, dst_lm, a, im, s); break;
+    case 2: launch_umma_n<2>(mc, src_lm, dst_lm, a, im, s); break;
+    default: launch_umma_n<3>(mc, src_lm, dst_lm, a, im, s); break;
   }
 }
 
