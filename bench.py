@@ -251,6 +251,22 @@ def main():
     torch.cuda.synchronize()
     ntt1_us_per_limb = e0.elapsed_time(e1) / 20 * 1e3 / n_limbs
     del bufs, dst
+    # base conversion on the tensor cores (tcgen05 kind::i8), batched ModDown shape: 64 polynomials x (15 P-limbs -> 35 Q-limbs)
+    # in one launch through hml_bconv_batch (that entry point also applies step 1 and stores canonical words)
+    src_p, dst_q, n_bc = list(range(MAX_LEVEL, MAX_LEVEL + ALPHA)), list(range(L)), 64
+    xb = [ctx.uniform(src_p, 70 + i, lead=(n_bc,)) for i in range(2)]
+    ob = ctx.empty(n_bc, L, N_RING)
+    for i in range(3):
+        ctx.bconv_batch(xb[i % 2], src_p, dst_q, out=ob)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(reps):
+        ctx.bconv_batch(xb[i % 2], src_p, dst_q, out=ob)
+    e1.record()
+    torch.cuda.synchronize()
+    bconv_ms = e0.elapsed_time(e1) / reps
+    bconv_bytes = float(ALPHA + L) * W_bytes * n_bc
+    del xb, ob
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ntt_traffic.json")))["dram_bytes_per_launch"]
@@ -258,7 +274,11 @@ def main():
         pass
 
     extra = {"ntt_limbs_per_s": ntt_limbs_per_s, "ntt_us_per_limb": ntt_ms * 1e3 / (n_limbs * n_b),
-             "ntt_us_per_limb_single_ciphertext_launch": ntt1_us_per_limb, "e2e_matches_device_path": e2e_ok}
+             "ntt_us_per_limb_single_ciphertext_launch": ntt1_us_per_limb, "e2e_matches_device_path": e2e_ok,
+             "bconv_tcgen05": {"kernel": "k_bconv_umma (tcgen05.mma kind::i8, 64 polynomials x 15 -> 35 limbs per launch)",
+                               "us_per_launch": bconv_ms * 1e3, "algorithmic_bytes_per_launch": bconv_bytes,
+                               "achieved_gbs": bconv_bytes / (bconv_ms * 1e-3) / 1e9, "hbm_frac": bconv_bytes / (bconv_ms * 1e-3) / 1e9 / peak,
+                               "limb_macs_per_s": ALPHA * L * n_bc / (bconv_ms * 1e-3)}}
     if not args.no_extra:
         flush = torch.empty(64 << 20, dtype=torch.int64, device="cuda")  # 512 MiB
 

@@ -49,7 +49,7 @@ def lib_path():
 EXPORTS = [
     "hml_ctx_create", "hml_ctx_create_params", "hml_ctx_destroy", "hml_last_error", "hml_last_create_error",
     "hml_ring_degree", "hml_n_moduli", "hml_get_moduli", "hml_get_roots", "hml_dev_alloc", "hml_dev_free", "hml_h2d",
-    "hml_d2h", "hml_sync", "hml_ntt", "hml_intt", "hml_ntt_batch", "hml_intt_batch", "hml_ewe", "hml_automorph", "hml_bconv", "hml_keyswitch", "hml_rescale",
+    "hml_d2h", "hml_sync", "hml_ntt", "hml_intt", "hml_ntt_batch", "hml_intt_batch", "hml_ewe", "hml_automorph", "hml_bconv", "hml_bconv_batch", "hml_keyswitch", "hml_rescale",
     "hml_hmult", "hml_hrotate", "hml_hadd", "hml_pmult", "hml_padd", "hml_hmult_batch", "hml_hrotate_batch",
     "hml_hmult_host", "hml_hrotate_host", "hml_host_alloc_pinned", "hml_host_free_pinned", "hml_trace_counts",
     "hml_get_counts", "hml_buffer_plan", "hml_exec_counts_get", "hml_exec_counts_reset", "hml_cli_main",
@@ -88,6 +88,7 @@ def load_library():
     L.hml_ewe.argtypes = [vp, vp, vp, vp, vp, i32, vp, C.POINTER(u32), u32, vp]
     L.hml_automorph.argtypes = [vp, vp, vp, u64, u32, vp]
     L.hml_bconv.argtypes = [vp, vp, C.POINTER(u32), u32, vp, C.POINTER(u32), u32, vp]
+    L.hml_bconv_batch.argtypes = [vp, vp, C.POINTER(u32), u32, vp, C.POINTER(u32), u32, u32, vp]
     L.hml_keyswitch.argtypes = [vp, u32, vp, vp, u32, vp, vp, vp]
     L.hml_rescale.argtypes = [vp, u32, vp, vp, vp]
     L.hml_hmult.argtypes = [vp, u32, vp, vp, vp, u32, vp, vp]
@@ -267,6 +268,14 @@ class Context:
         out = self.empty(len(dst_idx), self.N) if out is None else out
         self._chk(self.lib.hml_bconv(self.h, _ptr(x), _u32arr(src_idx), len(src_idx), _ptr(out), _u32arr(dst_idx),
                                      len(dst_idx), self._stream()))
+        return out
+
+    def bconv_batch(self, x, src_idx, dst_idx, out=None):
+        """x [n_batch][n_src][N] -> [n_batch][n_dst][N] in one launch."""
+        nb = x.shape[0]
+        out = self.empty(nb, len(dst_idx), self.N) if out is None else out
+        self._chk(self.lib.hml_bconv_batch(self.h, _ptr(x), _u32arr(src_idx), len(src_idx), _ptr(out), _u32arr(dst_idx),
+                                           len(dst_idx), nb, self._stream()))
         return out
 
     # ---- sub-operations and operations

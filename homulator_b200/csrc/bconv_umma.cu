@@ -249,7 +249,8 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
 k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BConvArgs a, const uint8_t *__restrict__ img, int K, int NP,
              int ND, int tiles_per_batch, int n_tiles, LevelMul lmul) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the shuffle tells the compiler that `warp` is warp-uniform: TMEM addresses and target indices then live in uniform registers
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const uint32_t a_bytes = (uint32_t)UMMA_TM * K;
   unsigned char *As = smem;                                  // two buffers
   unsigned char *Bs = smem + 2 * a_bytes;                    // NP * K

@@ -463,9 +463,9 @@ extern "C" int hml_automorph(hml_ctx *ctx, const uint64_t *in, uint64_t *out, ui
   return check_launch(ctx, "automorph");
 }
 
-extern "C" int hml_bconv(hml_ctx *ctx, const uint64_t *in, const uint32_t *src_idx, uint32_t n_src, uint64_t *out,
-                         const uint32_t *dst_idx, uint32_t n_dst, void *stream) {
-  if (!ctx || !in || !out || !src_idx || !dst_idx || !n_src || !n_dst) return HML_ERR_INVALID;
+extern "C" int hml_bconv_batch(hml_ctx *ctx, const uint64_t *in, const uint32_t *src_idx, uint32_t n_src, uint64_t *out,
+                               const uint32_t *dst_idx, uint32_t n_dst, uint32_t n_batch, void *stream) {
+  if (!ctx || !in || !out || !src_idx || !dst_idx || !n_src || !n_dst || !n_batch) return HML_ERR_INVALID;
   if (n_src > NTT_MAX_LIMBS || n_dst > NTT_MAX_LIMBS) return fail(ctx, HML_ERR_UNSUPPORTED, "more than 128 limbs in one conversion");
   for (uint32_t i = 0; i < n_src; ++i) if (src_idx[i] >= ctx->p.n_mod()) return fail(ctx, HML_ERR_INVALID, "modulus index out of range");
   for (uint32_t i = 0; i < n_dst; ++i) if (dst_idx[i] >= ctx->p.n_mod()) return fail(ctx, HML_ERR_INVALID, "modulus index out of range");
@@ -491,10 +491,16 @@ extern "C" int hml_bconv(hml_ctx *ctx, const uint64_t *in, const uint32_t *src_i
   id_map(slm, src_idx, n_src);
   BConvArgs a{};
   a.in = (const u64 *)in; a.out = (u64 *)out; a.step1 = it->second.step1;
-  a.N = ctx->p.N; a.n_batches = 1;
+  a.N = ctx->p.N; a.n_batches = (int)n_batch;
+  a.in_batch_stride = (long long)n_src * ctx->p.N; a.out_batch_stride = (long long)n_dst * ctx->p.N;
   run_bconv(ctx, it->second.host, slm, a, (cudaStream_t)stream);
-  ctx->exec.ewe_limbs += n_src;  // step 1
+  ctx->exec.ewe_limbs += (uint64_t)n_src * n_batch;  // step 1
   return check_launch(ctx, "bconv");
+}
+
+extern "C" int hml_bconv(hml_ctx *ctx, const uint64_t *in, const uint32_t *src_idx, uint32_t n_src, uint64_t *out,
+                         const uint32_t *dst_idx, uint32_t n_dst, void *stream) {
+  return hml_bconv_batch(ctx, in, src_idx, n_src, out, dst_idx, n_dst, 1, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ key switch

@@ -103,6 +103,12 @@ int hml_automorph(hml_ctx *ctx, const uint64_t *in, uint64_t *out, uint64_t galo
  * out [n_dst][N]: out_m = sum_i [in_i * (D/s_i)^-1]_{s_i} * [D/s_i]_m mod m, no overflow correction. */
 int hml_bconv(hml_ctx *ctx, const uint64_t *in, const uint32_t *src_idx, uint32_t n_src, uint64_t *out,
               const uint32_t *dst_idx, uint32_t n_dst, void *stream);
+/* The same conversion for n_batch independent polynomials: in [n_batch][n_src][N], out [n_batch][n_dst][N], ONE launch (the
+ * shape the batched ops use).  Conversions with <= 48 sources and <= 48 targets on rings with N >= 128 run on the 5th-gen
+ * tensor cores (tcgen05.mma kind::i8, accumulators in TMEM; homulator_b200/csrc/bconv_umma.cu), the rest on the FP64
+ * tensor-core path; HML_BCONV_UMMA=0 forces the latter. */
+int hml_bconv_batch(hml_ctx *ctx, const uint64_t *in, const uint32_t *src_idx, uint32_t n_src, uint64_t *out,
+                    const uint32_t *dst_idx, uint32_t n_dst, uint32_t n_batch, void *stream);
 
 /* ------------------------------------------------------------------ sub-operations */
 /* replaces KeySwitch::KeySwitch (reference src/Operation.cpp:9-54, stages :63-590).

@@ -145,6 +145,61 @@ def test_bconv(N, ml, al, src, dst):
         assert np.array_equal(got[t], o.bconv(src, dst[t], x)), dst[t]
 
 
+@pytest.mark.parametrize("N,ml,al,src,dst,nb", [
+    (128, 50, 48, list(range(50, 98)), list(range(48)), 3),            # 48 -> 48: the largest shape of the tcgen05 kernel, one tile per batch
+    (256, 20, 10, list(range(17)), list(range(17, 30)), 5),            # two 16-source slabs, ragged targets
+    (1024, 12, 5, [0, 2, 4, 6, 8], list(range(9, 17)), 7),             # strided sources, more batches than SMs-per-tile
+    (512, 60, 20, list(range(33)), list(range(33, 80)), 2),            # three slabs, 47 targets
+    (256, 70, 20, list(range(10)), list(range(10, 70)), 2),            # 60 targets: above the tcgen05 limit -> FP64 tensor-core kernel
+    (65536, 45, 15, list(range(45, 60)), list(range(35)), 3),          # ModDown shape, 1536 tiles on 148 persistent CTAs
+])
+def test_bconv_batch(N, ml, al, src, dst, nb):
+    """hml_bconv_batch against the oracle: every batch, every target on the small rings (tail tiles, padding targets and
+    sources, the 2- and 3-slab kernels), sampled targets at N = 2^16."""
+    ctx, o = hml.Context(N=N, max_level=ml, alpha=al), Oracle(N, 36, ml, al)
+    x = np.stack([np.stack([uniform_limbs([o.moduli[i]], N, 900 + 31 * b + i)[0] for i in src]) for b in range(nb)])
+    x[0, 0, :2] = o.moduli[src[0]] - 1
+    x[nb - 1, :, N - 1] = [o.moduli[i] - 1 for i in src]
+    got = to_host(ctx.bconv_batch(to_dev(x), src, dst))
+    assert got.shape == (nb, len(dst), N)
+    check = range(len(dst)) if N <= 4096 else (0, 17, len(dst) - 1)
+    for b in range(nb):
+        for t in check:
+            assert np.array_equal(got[b, t], o.bconv(src, dst[t], x[b])), (b, dst[t])
+
+
+def test_bconv_tensor_core_kernels_agree_in_a_subprocess():
+    """HML_BCONV_UMMA is read once per process: the same batched conversions and one hmult on the FP64 tensor-core kernel
+    (child process, HML_BCONV_UMMA=0) must be bit-identical to the tcgen05 kernel's results here."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    body = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import torch, homulator_b200 as hml\n"
+        "ctx = hml.Context(N=8192, max_level=12, alpha=4)\n"
+        "L = 11\n"
+        "src, dst = list(range(12, 16)), list(range(L))\n"
+        "x = ctx.uniform(src, 5, lead=(6,))\n"
+        "y = ctx.bconv_batch(x, src, dst)\n"
+        "evk = ctx.uniform(ctx.ext_mod_idx(L), 3, lead=(ctx.beta(L), 2))\n"
+        "a = ctx.uniform(list(range(L)), 1, lead=(3, 2)); b = ctx.uniform(list(range(L)), 2, lead=(3, 2))\n"
+        "h = ctx.hmult_batch(L, a, b, evk); r = ctx.hrotate_batch(L, a, evk, 5)\n"
+        "torch.save([y.cpu(), h.cpu(), r.cpu()], sys.argv[1])\n" % root)
+    outs = []
+    with tempfile.TemporaryDirectory() as d:
+        for flag in ("1", "0"):
+            path = os.path.join(d, "o%s.pt" % flag)
+            r = subprocess.run([sys.executable, "-c", body, path], env=dict(os.environ, HML_BCONV_UMMA=flag), capture_output=True,
+                               text=True, timeout=600)
+            assert r.returncode == 0, r.stdout + r.stderr
+            outs.append(torch.load(path))
+    for u, v in zip(*outs):
+        assert torch.equal(u, v)
+
+
 def test_errors_are_reported_not_raised_across_the_abi(big):
     ctx, _ = big
     x = ctx.empty(1, 65536)
