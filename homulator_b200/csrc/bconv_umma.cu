@@ -243,17 +243,23 @@ struct TileWalk {
   }
 };
 
-// N16 = 16-source slabs; W = targets reduced per epilogue trip (3 or 4, whichever wastes fewer masked slots)
-template <int N16, bool FOLD, bool F64, int W>
-__global__ void __launch_bounds__(UMMA_THREADS, 1)
+// N16 = 16-source slabs; W = targets reduced per epilogue trip (3 or 4, whichever wastes fewer masked slots); NT = threads:
+//   NT = 512  one CTA per SM, two TMEM buffers (512 columns): the MMA of tile n+1 overlaps the epilogue of tile n
+//   NT = 256  two CTAs per SM, one TMEM buffer each (256 columns): a CTA runs pack -> MMA -> epilogue strictly in turn and
+//             the OTHER CTA of the SM fills its barrier / MMA waits (16-source conversions only: shared memory)
+template <int N16, bool FOLD, bool F64, int W, int NT>
+__global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
 k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BConvArgs a, const uint8_t *__restrict__ img, int K, int NP,
              int ND, int tiles_per_batch, int n_tiles, LevelMul lmul) {
   extern __shared__ __align__(128) unsigned char smem[];
   // the shuffle tells the compiler that `warp` is warp-uniform: TMEM addresses and target indices then live in uniform registers
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  constexpr int NBUF = NT == 512 ? 2 : 1;    // TMEM accumulator buffers = A operand buffers
+  constexpr int IPT = UMMA_THREADS / NT;     // (coefficient, source group) items per thread and slab
+  constexpr int NSUB = NT / 128;             // epilogue warps per TMEM lane quarter
   const uint32_t a_bytes = (uint32_t)UMMA_TM * K;
-  unsigned char *As = smem;                                  // two buffers
-  unsigned char *Bs = smem + 2 * a_bytes;                    // NP * K
+  unsigned char *As = smem;                                  // NBUF buffers
+  unsigned char *Bs = smem + NBUF * a_bytes;                 // NP * K
   double2 *tq = reinterpret_cast<double2 *>(Bs + (size_t)NP * K);   // [ND + 4] (q, 1/q) per target (a trip may run 3 past the last)
   long long *toff = reinterpret_cast<long long *>(tq + ND + 4);  // [ND + 4] byte offset of the target's limb in the output
   uint64_t *bars = reinterpret_cast<uint64_t *>(toff + ND + 4);  // two mbarriers
@@ -264,11 +270,11 @@ k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BC
   unsigned char *St = reinterpret_cast<unsigned char *>(bars + 4);
 
   // ---- constant set-up (before the programmatic dependency is resolved)
-  for (uint32_t e = tid; e < 2 * a_bytes / 16; e += UMMA_THREADS) reinterpret_cast<uint4 *>(As)[e] = make_uint4(0, 0, 0, 0);
-  for (uint32_t e = tid; e < STAGES * stage_bytes / 16; e += UMMA_THREADS) reinterpret_cast<uint4 *>(St)[e] = make_uint4(0, 0, 0, 0);
-  for (uint32_t e = tid; e < (uint32_t)NP * K / 16; e += UMMA_THREADS) reinterpret_cast<uint4 *>(Bs)[e] = __ldg(reinterpret_cast<const uint4 *>(img) + e);
+  for (uint32_t e = tid; e < NBUF * a_bytes / 16; e += NT) reinterpret_cast<uint4 *>(As)[e] = make_uint4(0, 0, 0, 0);
+  for (uint32_t e = tid; e < STAGES * stage_bytes / 16; e += NT) reinterpret_cast<uint4 *>(St)[e] = make_uint4(0, 0, 0, 0);
+  for (uint32_t e = tid; e < (uint32_t)NP * K / 16; e += NT) reinterpret_cast<uint4 *>(Bs)[e] = __ldg(reinterpret_cast<const uint4 *>(img) + e);
   const int ntv = a.n_dst + (FOLD ? 1 : 0);
-  for (int t = tid; t < ND + 4; t += UMMA_THREADS) {
+  for (int t = tid; t < ND + 4; t += NT) {
     double2 c = make_double2(1.0, 1.0);
     if (t < ntv) {
       const ModConst m = mc[t < a.n_dst ? dst_lm.mod[t] : a.fold_mod];
@@ -278,7 +284,7 @@ k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BC
     toff[t] = t < a.n_dst ? (long long)dst_lm.pos[t] * a.N * 8 : 0;
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(tmem_slot)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "n"(256 * NBUF) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 32) {
@@ -294,7 +300,8 @@ k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BC
   const uint32_t idesc = 0x20u | ((uint32_t)(NP >> 3) << 17) | (8u << 24);   // D = s32, A = B = u8, K-major, N = NP, M = 128
   const uint32_t bar0 = smem_addr(&bars[0]);
 
-  // loader role: coefficient row lr, source group g (sources 16 s + 4 g .. + 3 of every 16-source slab s)
+  // loader role: coefficient row lr (+ NT/4 for the thread's second item when NT = 256), source group g (sources
+  // 16 s + 4 g .. + 3 of every 16-source slab s)
   const int g = tid & 3, lr = tid >> 2;
   long long soff[N16][4];  // word offset of each of the thread's sources inside a batch; -1: beyond n_src (zero row)
 #pragma unroll
@@ -308,7 +315,7 @@ k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BC
   // lane quarter as contiguous ranges, walked W targets per trip
   const int row = ((warp & 3) << 5) | lane, sub = warp >> 2;
   const uint32_t t_lane = (uint32_t)((warp & 3) << 5) << 16;
-  const int cb = a.n_dst >> 2, cr = a.n_dst & 3;
+  const int cb = a.n_dst / NSUB, cr = a.n_dst % NSUB;
   const int t_first = sub * cb + min(sub, cr);
   const int t_end = t_first + cb + (sub < cr ? 1 : 0);
 
@@ -320,38 +327,45 @@ k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BC
       for (int s = 0; s < N16; ++s)
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (soff[s][k] >= 0)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (s * 4 + k) * UMMA_THREADS * 8), "l"(in + soff[s][k]) : "memory");
+          if (soff[s][k] >= 0) {
+#pragma unroll
+            for (int h = 0; h < IPT; ++h)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + ((s * 4 + k) * UMMA_THREADS + h * NT) * 8),
+                           "l"(in + soff[s][k] + h * (NT / 4))
+                           : "memory");
+          }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");  // one group per tile slot, empty or not: the wait counts stay uniform
   };
   auto pack_tile = [&](int stage, unsigned char *Ab) {
     const u64 *src = reinterpret_cast<const u64 *>(St + (size_t)stage * stage_bytes) + tid;
 #pragma unroll
-    for (int s = 0; s < N16; ++s) {
-      u64 y[4];
+    for (int h = 0; h < IPT; ++h)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) y[k] = src[(s * 4 + k) * UMMA_THREADS];
-      if (a.step1) {  // uniform: per-source scaling inside the conversion (primitive entry point)
+      for (int s = 0; s < N16; ++s) {
+        u64 y[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int i = s * 16 + g * 4 + k;
-          if (i < a.n_src) {
-            const ModConst m = mc[src_lm.mod[i]];
-            const double2 sc = a.step1[i];
-            y[k] = f64_to_canonical(mulmod_const(u64_to_f64(y[k]), sc.x, sc.y, m.q), m.qi);
+        for (int k = 0; k < 4; ++k) y[k] = src[(s * 4 + k) * UMMA_THREADS + h * NT];
+        if (a.step1) {  // uniform: per-source scaling inside the conversion (primitive entry point)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = s * 16 + g * 4 + k;
+            if (i < a.n_src) {
+              const ModConst m = mc[src_lm.mod[i]];
+              const double2 sc = a.step1[i];
+              y[k] = f64_to_canonical(mulmod_const(u64_to_f64(y[k]), sc.x, sc.y, m.q), m.qi);
+            }
           }
         }
+        const uint32_t l0 = (uint32_t)y[0], l1 = (uint32_t)y[1], l2 = (uint32_t)y[2], l3 = (uint32_t)y[3];
+        const uint32_t h0 = (uint32_t)(y[0] >> 32), h1 = (uint32_t)(y[1] >> 32), h2 = (uint32_t)(y[2] >> 32), h3 = (uint32_t)(y[3] >> 32);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(Ab + ((size_t)(s * 5) * UMMA_TM + lr + h * (NT / 4)) * 16 + 4 * g);
+        dst[0 * UMMA_TM * 4] = __byte_perm(__byte_perm(l0, l1, 0x0040), __byte_perm(l2, l3, 0x0040), 0x5410);
+        dst[1 * UMMA_TM * 4] = __byte_perm(__byte_perm(l0, l1, 0x0051), __byte_perm(l2, l3, 0x0051), 0x5410);
+        dst[2 * UMMA_TM * 4] = __byte_perm(__byte_perm(l0, l1, 0x0062), __byte_perm(l2, l3, 0x0062), 0x5410);
+        dst[3 * UMMA_TM * 4] = __byte_perm(__byte_perm(l0, l1, 0x0073), __byte_perm(l2, l3, 0x0073), 0x5410);
+        dst[4 * UMMA_TM * 4] = __byte_perm(__byte_perm(h0, h1, 0x0040), __byte_perm(h2, h3, 0x0040), 0x5410);
       }
-      const uint32_t l0 = (uint32_t)y[0], l1 = (uint32_t)y[1], l2 = (uint32_t)y[2], l3 = (uint32_t)y[3];
-      const uint32_t h0 = (uint32_t)(y[0] >> 32), h1 = (uint32_t)(y[1] >> 32), h2 = (uint32_t)(y[2] >> 32), h3 = (uint32_t)(y[3] >> 32);
-      uint32_t *dst = reinterpret_cast<uint32_t *>(Ab + ((size_t)(s * 5) * UMMA_TM + lr) * 16 + 4 * g);
-      dst[0 * UMMA_TM * 4] = __byte_perm(__byte_perm(l0, l1, 0x0040), __byte_perm(l2, l3, 0x0040), 0x5410);
-      dst[1 * UMMA_TM * 4] = __byte_perm(__byte_perm(l0, l1, 0x0051), __byte_perm(l2, l3, 0x0051), 0x5410);
-      dst[2 * UMMA_TM * 4] = __byte_perm(__byte_perm(l0, l1, 0x0062), __byte_perm(l2, l3, 0x0062), 0x5410);
-      dst[3 * UMMA_TM * 4] = __byte_perm(__byte_perm(l0, l1, 0x0073), __byte_perm(l2, l3, 0x0073), 0x5410);
-      dst[4 * UMMA_TM * 4] = __byte_perm(__byte_perm(h0, h1, 0x0040), __byte_perm(h2, h3, 0x0040), 0x5410);
-    }
   };
   auto issue_mma = [&](int buf) {  // one thread
     const uint32_t a_addr = smem_addr(As + (size_t)buf * a_bytes), b_addr = smem_addr(Bs);
@@ -419,71 +433,111 @@ k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BC
       load_tile(wl, d, d < n_my);
       wl.step(stride, tiles_per_batch);
     }
-    asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
-    pack_tile(0, As);
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_mma(0);
-    }
-    int st_next = STAGES > 1 ? 1 : 0, st_load = 0;  // stage of tile it + 1 / stage the next load refills (= the one tile `it` was in)
-    for (int it = 0; it < n_my; ++it) {
-      const int buf = it & 1;
-      const bool next = it + 1 < n_my;
-      if (next) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
-        pack_tile(st_next, As + (size_t)(buf ^ 1) * a_bytes);
-        fence_async_smem();
-      }
+    if (NBUF == 2) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+      pack_tile(0, As);
+      fence_async_smem();
       tc_fence_before();
       __syncthreads();
-      if (next && tid == 0) {
+      if (tid == 0) {
         tc_fence_after();
-        issue_mma(buf ^ 1);
+        issue_mma(0);
       }
-      load_tile(wl, st_load, it + STAGES < n_my);
-      wl.step(stride, tiles_per_batch);
-      st_next = st_next + 1 == STAGES ? 0 : st_next + 1;
-      st_load = st_load + 1 == STAGES ? 0 : st_load + 1;
-      mbar_wait(bar0 + 8u * buf, (uint32_t)(it >> 1) & 1u);
-      tc_fence_after();
-      epilogue(we, buf);
-      we.step(stride, tiles_per_batch);
+      int st_next = STAGES > 1 ? 1 : 0, st_load = 0;  // stage of tile it + 1 / stage the next load refills (= the one tile `it` was in)
+      for (int it = 0; it < n_my; ++it) {
+        const int buf = it & 1;
+        const bool next = it + 1 < n_my;
+        if (next) {
+          asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
+          pack_tile(st_next, As + (size_t)(buf ^ 1) * a_bytes);
+          fence_async_smem();
+        }
+        tc_fence_before();
+        __syncthreads();
+        if (next && tid == 0) {
+          tc_fence_after();
+          issue_mma(buf ^ 1);
+        }
+        load_tile(wl, st_load, it + STAGES < n_my);
+        wl.step(stride, tiles_per_batch);
+        st_next = st_next + 1 == STAGES ? 0 : st_next + 1;
+        st_load = st_load + 1 == STAGES ? 0 : st_load + 1;
+        mbar_wait(bar0 + 8u * buf, (uint32_t)(it >> 1) & 1u);
+        tc_fence_after();
+        epilogue(we, buf);
+        we.step(stride, tiles_per_batch);
+      }
+    } else {  // one accumulator buffer: pack -> MMA -> epilogue in turn; the co-resident CTA fills the waits
+      int st = 0;
+      for (int it = 0; it < n_my; ++it) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+        pack_tile(st, As);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();  // also: every warp has drained the accumulators of tile it - 1
+        if (tid == 0) {
+          tc_fence_after();
+          issue_mma(0);
+        }
+        load_tile(wl, st, it + STAGES < n_my);
+        wl.step(stride, tiles_per_batch);
+        st = st + 1 == STAGES ? 0 : st + 1;
+        mbar_wait(bar0, (uint32_t)it & 1u);
+        tc_fence_after();
+        epilogue(we, 0);
+        we.step(stride, tiles_per_batch);
+      }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256 * NBUF) : "memory");
 }
 
-template <int N16, bool FOLD, bool F64, int W>
+// HML_UMMA_CTAS = 1 | 2: CTAs per SM for 16-source conversions (tuning knob, see the kernel's NT parameter)
+static int umma_ctas_per_sm() {
+  static const int v = [] {
+    const char *e = getenv("HML_UMMA_CTAS");
+    return e && atoi(e) == 1 ? 1 : 2;
+  }();
+  return v;
+}
+
+template <int N16, bool FOLD, bool F64, int W, int NT>
 static void launch_umma_t(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const BConvImage &im, cudaStream_t s) {
   const int tiles_per_batch = a.N / UMMA_TM, n_tiles = tiles_per_batch * a.n_batches;
   constexpr int STAGES = N16 <= 2 ? 3 : 2;
-  // at least half of the SM's shared memory: ONE CTA per SM (a second one would only sit in tcgen05.alloc until the first ends)
-  const size_t need = (size_t)2 * UMMA_TM * im.K + (size_t)im.NP * im.K + (size_t)(im.ND + 4) * 24 + 32 + (size_t)STAGES * N16 * 4 * UMMA_THREADS * 8;
-  const size_t smem = std::max<size_t>(need, 116 * 1024);
+  constexpr int NBUF = NT == 512 ? 2 : 1;
+  const size_t need = (size_t)NBUF * UMMA_TM * im.K + (size_t)im.NP * im.K + (size_t)(im.ND + 4) * 24 + 32 + (size_t)STAGES * N16 * 4 * UMMA_THREADS * 8;
+  // NT = 512: at least half of the SM's shared memory, so that exactly ONE CTA is resident per SM (a second one would only
+  // sit in tcgen05.alloc until the first ends); NT = 256: two fit (<= 113 KB each), a third does not
+  const size_t smem = NT == 512 ? std::max<size_t>(need, 116 * 1024) : std::max<size_t>(need, 80 * 1024);
   static PerDeviceOnce once;
   static int n_sm[64];
   int dev = 0;
   cudaGetDevice(&dev);
   if (once.first()) {
-    cudaFuncSetAttribute(k_bconv_umma<N16, FOLD, F64, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(k_bconv_umma<N16, FOLD, F64, W, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, NT == 512 ? 227 * 1024 : 113 * 1024);
     cudaDeviceGetAttribute(&n_sm[dev & 63], cudaDevAttrMultiProcessorCount, dev);
   }
-  const int grid = std::min(n_tiles, std::max(1, n_sm[dev & 63]));
-  launch_pdl(k_bconv_umma<N16, FOLD, F64, W>, dim3(grid), dim3(UMMA_THREADS), smem, s, mc, src_lm, dst_lm, a, im.img, im.K, im.NP, im.ND, tiles_per_batch, n_tiles,
+  const int grid = std::min(n_tiles, (NT == 512 ? 1 : 2) * std::max(1, n_sm[dev & 63]));
+  launch_pdl(k_bconv_umma<N16, FOLD, F64, W, NT>, dim3(grid), dim3(NT), smem, s, mc, src_lm, dst_lm, a, im.img, im.K, im.NP, im.ND, tiles_per_batch, n_tiles,
              LevelMul{256u, 65536u, 16777216u});
 }
 
 template <int N16, bool FOLD, bool F64>
 static void launch_umma_w(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const BConvImage &im, cudaStream_t s) {
-  const int c = (a.n_dst + 3) / 4;  // targets per epilogue warp; trips of 3 or 4, whichever leaves fewer masked slots
-  if (((c + 2) / 3) * 3 < ((c + 3) / 4) * 4) launch_umma_t<N16, FOLD, F64, 3>(mc, src_lm, dst_lm, a, im, s);
-  else launch_umma_t<N16, FOLD, F64, 4>(mc, src_lm, dst_lm, a, im, s);
+  // targets per epilogue warp; trips of 3 or 4, whichever leaves fewer masked slots
+  if (N16 == 1 && umma_ctas_per_sm() == 2) {
+    const int c = (a.n_dst + 1) / 2;
+    if (((c + 2) / 3) * 3 < ((c + 3) / 4) * 4) launch_umma_t<1, FOLD, F64, 3, 256>(mc, src_lm, dst_lm, a, im, s);
+    else launch_umma_t<1, FOLD, F64, 4, 256>(mc, src_lm, dst_lm, a, im, s);
+    return;
+  }
+  const int c = (a.n_dst + 3) / 4;
+  if (((c + 2) / 3) * 3 < ((c + 3) / 4) * 4) launch_umma_t<N16, FOLD, F64, 3, 512>(mc, src_lm, dst_lm, a, im, s);
+  else launch_umma_t<N16, FOLD, F64, 4, 512>(mc, src_lm, dst_lm, a, im, s);
 }
 
 template <int N16>
