@@ -96,7 +96,7 @@ def cpu_port_sample(n_ops, threads):
     return dt / n_ops * 1e6, used
 
 
-def run_reference(args):
+def run_reference(args, real_stdout):
     """Reference arm.  The reference itself (a cycle simulator) computes no ciphertext values and its own run of this
     config takes hours, so the CPU implementation of the path timed here is the scalar oracle
     port with all host threads; each step is ONE hmult (bounded sample of the workload)."""
@@ -126,11 +126,26 @@ def run_reference(args):
         "e2e": {"value": us, "unit": "us", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "extra": sim,
     }
-    print(json.dumps(line))
+    _emit(real_stdout, line)
     return 0
 
 
+def _claim_stdout():
+    """Everything libraries print to stdout while the bench runs (e.g. NCCL's version banner) goes to stderr; the JSON line is
+    written to the real stdout, which therefore holds exactly one line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def _emit(real_stdout, line):
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -142,7 +157,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, real_stdout)
 
     import torch
     import torch.distributed as dist
@@ -338,7 +353,7 @@ def main():
         "cpu_baseline": cpu,
         "extra": extra,
     }
-    print(json.dumps(line))
+    _emit(real_stdout, line)
     if world > 1:
         dist.destroy_process_group()
     return 0
