@@ -117,6 +117,25 @@ def run_reference(args, real_stdout):
             sim["homulator_insgen_seconds"] = json.loads(line)["insgen_seconds"]
         except Exception:
             pass
+    # Homulator's own host wall-clock: the unmodified reference CLI (oracle/_ref/Homulator.run) simulating THIS op and config
+    # on one host core for a bounded time; the full run takes hours, so the sample reports how far
+    # the cycle simulator got and the cycles it simulates per second of host time.
+    cli = os.path.join(ROOT, "oracle", "_ref", "Homulator.run")
+    if os.path.exists(cli) and not args.no_extra:
+        try:
+            budget = 20
+            t0 = time.perf_counter()
+            r = subprocess.run(["timeout", str(budget), "stdbuf", "-oL", cli, CFG, "hmult", str(MAX_LEVEL), str(LEVEL), str(ALPHA)],
+                               capture_output=True, text=True, timeout=budget + 30)
+            dt = time.perf_counter() - t0
+            cyc = [int(l.split()[2]) for l in r.stdout.splitlines() if l.startswith("FHE-Sim running")]
+            done = [int(l.split()[3]) for l in r.stdout.splitlines() if l.startswith("We have executed") and "instructions!" in l]
+            sim["homulator_cli_sample"] = {
+                "command": "Homulator.run config_4.cfg hmult 45 35 15", "host_seconds": dt, "cores": 1,
+                "simulated_cycles_reached": cyc[-1] if cyc else 0, "instructions_completed": done[-1] if done else 0,
+                "instructions_total": 7381760, "status": "DNF(budget)" if r.returncode == 124 else "exit %d" % r.returncode}
+        except Exception as e:  # reported baseline only
+            sim["homulator_cli_sample"] = {"error": str(e)[:120]}
     line = {
         "impl": "reference", "metric": METRIC, "value": us, "unit": "us", "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": us / 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,

@@ -269,36 +269,7 @@ k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BC
   constexpr uint32_t stage_bytes = N16 * 4 * UMMA_THREADS * 8;
   unsigned char *St = reinterpret_cast<unsigned char *>(bars + 4);
 
-  // ---- constant set-up (before the programmatic dependency is resolved)
-  for (uint32_t e = tid; e < NBUF * a_bytes / 16; e += NT) reinterpret_cast<uint4 *>(As)[e] = make_uint4(0, 0, 0, 0);
-  for (uint32_t e = tid; e < STAGES * stage_bytes / 16; e += NT) reinterpret_cast<uint4 *>(St)[e] = make_uint4(0, 0, 0, 0);
-  for (uint32_t e = tid; e < (uint32_t)NP * K / 16; e += NT) reinterpret_cast<uint4 *>(Bs)[e] = __ldg(reinterpret_cast<const uint4 *>(img) + e);
-  const int ntv = a.n_dst + (FOLD ? 1 : 0);
-  for (int t = tid; t < ND + 4; t += NT) {
-    double2 c = make_double2(1.0, 1.0);
-    if (t < ntv) {
-      const ModConst m = mc[t < a.n_dst ? dst_lm.mod[t] : a.fold_mod];
-      c = make_double2(m.q, m.qinv);
-    }
-    tq[t] = c;
-    toff[t] = t < a.n_dst ? (long long)dst_lm.pos[t] * a.N * 8 : 0;
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "n"(256 * NBUF) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (tid == 32) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bars[0])));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bars[1])));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  fence_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t idesc = 0x20u | ((uint32_t)(NP >> 3) << 17) | (8u << 24);   // D = s32, A = B = u8, K-major, N = NP, M = 128
-  const uint32_t bar0 = smem_addr(&bars[0]);
+  uint32_t tmem_base = 0, idesc = 0, bar0 = 0;  // set after the set-up below; the role lambdas capture them by reference
 
   // loader role: coefficient row lr (+ NT/4 for the thread's second item when NT = 256), source group g (sources
   // 16 s + 4 g .. + 3 of every 16-source slab s)
@@ -310,6 +281,12 @@ k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BC
     for (int k = 0; k < 4; ++k) {
       const int i = s * 16 + g * 4 + k;
       soff[s][k] = i < a.n_src ? (long long)src_lm.pos[i] * a.N + lr : -1;
+      if (soff[s][k] < 0) {  // padding sources: their staging slots are never written by a copy, they stay zero
+#pragma unroll
+        for (int d = 0; d < STAGES; ++d)
+#pragma unroll
+          for (int h = 0; h < IPT; ++h) reinterpret_cast<u64 *>(St + (size_t)d * stage_bytes)[(s * 4 + k) * UMMA_THREADS + tid + h * NT] = 0;
+      }
     }
   // epilogue role: TMEM lanes 32 (warp % 4) .. + 31 = coefficient rows; the targets are dealt evenly to the four warps of a
   // lane quarter as contiguous ranges, walked W targets per trip
@@ -433,6 +410,41 @@ k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BC
       load_tile(wl, d, d < n_my);
       wl.step(stride, tiles_per_batch);
     }
+    // ---- constant set-up, while the first tiles are on their way: matrix image, per-target table, TMEM, barriers
+    for (uint32_t e = tid; e < (uint32_t)NP * K / 16; e += NT) reinterpret_cast<uint4 *>(Bs)[e] = __ldg(reinterpret_cast<const uint4 *>(img) + e);
+    {  // K padding of the A operand (chunks past 5 per slab): written once, never touched by the packer
+      const uint32_t used = (uint32_t)N16 * 5 * UMMA_TM * 16, pad = a_bytes - used;
+      for (uint32_t e = tid; e < NBUF * pad / 16; e += NT) {
+        const uint32_t b = e / (pad / 16), o = e - b * (pad / 16);
+        reinterpret_cast<uint4 *>(As + (size_t)b * a_bytes + used)[o] = make_uint4(0, 0, 0, 0);
+      }
+    }
+    const int ntv = a.n_dst + (FOLD ? 1 : 0);
+    for (int t = tid; t < ND + 4; t += NT) {
+      double2 c = make_double2(1.0, 1.0);
+      if (t < ntv) {
+        const ModConst m = mc[t < a.n_dst ? dst_lm.mod[t] : a.fold_mod];
+        c = make_double2(m.q, m.qinv);
+      }
+      tq[t] = c;
+      toff[t] = t < a.n_dst ? (long long)dst_lm.pos[t] * a.N * 8 : 0;
+    }
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "n"(256 * NBUF) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bars[0])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bars[1])));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    tmem_base = *tmem_slot;
+    idesc = 0x20u | ((uint32_t)(NP >> 3) << 17) | (8u << 24);   // D = s32, A = B = u8, K-major, N = NP, M = 128
+    bar0 = smem_addr(&bars[0]);
     if (NBUF == 2) {
       asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
       pack_tile(0, As);
@@ -489,10 +501,10 @@ k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BC
       }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256 * NBUF) : "memory");
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256 * NBUF) : "memory");
 }
 
 // HML_UMMA_CTAS = 1 | 2: CTAs per SM for 16-source conversions (tuning knob, see the kernel's NT parameter)
