@@ -54,6 +54,8 @@ EXPORTS = [
     "hml_hmult_host", "hml_hrotate_host", "hml_host_alloc_pinned", "hml_host_free_pinned", "hml_trace_counts",
     "hml_get_counts", "hml_buffer_plan", "hml_exec_counts_get", "hml_exec_counts_reset", "hml_cli_main",
     "hml_shard_layout", "hml_keyswitch_shard_begin", "hml_keyswitch_shard_mid", "hml_keyswitch_shard_end",
+    "hml_keyswitch_shard_mid_p2p", "hml_keyswitch_shard_end_p2p", "hml_shard_signal", "hml_shard_wait",
+    "hml_ipc_export", "hml_ipc_import", "hml_ipc_close",
 ]
 
 
@@ -111,6 +113,17 @@ def load_library():
     L.hml_keyswitch_shard_begin.argtypes = [vp, u32, u32, u32, vp, vp, vp]
     L.hml_keyswitch_shard_mid.argtypes = [vp, u32, u32, u32, vp, vp, vp, vp, vp]
     L.hml_keyswitch_shard_end.argtypes = [vp, u32, u32, u32, vp, vp, vp, vp]
+    L.hml_keyswitch_shard_mid_p2p.argtypes = [vp, u32, u32, u32, vp, C.POINTER(vp), vp, vp, vp]
+    L.hml_keyswitch_shard_end_p2p.argtypes = [vp, u32, u32, u32, C.POINTER(vp), vp, vp, vp]
+    L.hml_shard_signal.argtypes = [vp, vp, u32, u64, u32, vp]
+    L.hml_shard_wait.argtypes = [vp, vp, u32, u64, u32, vp]
+    L.hml_ipc_export.argtypes = [vp, vp, C.c_char_p]
+    L.hml_ipc_import.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    L.hml_ipc_close.argtypes = [vp, vp]
+    L.hml_dev_alloc.argtypes = [vp, u64, C.POINTER(vp)]
+    L.hml_dev_free.argtypes = [vp, vp]
+    L.hml_h2d.argtypes = [vp, vp, vp, u64, vp]
+    L.hml_sync.argtypes = [vp, vp]
     _LIB = L
     return L
 
@@ -355,6 +368,44 @@ class Context:
         self._chk(self.lib.hml_keyswitch_shard_end(self.h, L, rank, world, _ptr(g2), _ptr(o0), _ptr(o1), st))
         return o0[:nq], o1[:nq]
 
+    # ---- peer-direct limb-sharded key switch (no collective; NVLink loads inside the base conversion)
+    def dev_alloc(self, n_words, zero=True):
+        """Plain cudaMalloc through the ABI (shareable with cudaIpc, unlike a slice of torch's caching allocator)."""
+        p = C.c_void_p()
+        self._chk(self.lib.hml_dev_alloc(self.h, n_words, C.byref(p)))
+        if zero:
+            import numpy as np
+            z = np.zeros(n_words, dtype=np.uint64)
+            self._chk(self.lib.hml_h2d(self.h, p.value, z.ctypes.data, n_words, None))
+            self._chk(self.lib.hml_sync(self.h, None))
+        return p.value
+
+    def ipc_export(self, ptr):
+        buf = C.create_string_buffer(64)
+        self._chk(self.lib.hml_ipc_export(self.h, ptr, buf))
+        return bytes(buf.raw)
+
+    def ipc_import(self, handle):
+        p = C.c_void_p()
+        self._chk(self.lib.hml_ipc_import(self.h, handle, C.byref(p)))
+        return p.value
+
+    def shard_p2p_setup(self, L, rank, world, exchange):
+        """Allocate this rank's gather buffers + flag block and map every peer's.  `exchange(obj)` must return the list of all
+        ranks' objects (torch.distributed.all_gather_object); with world == 1 or for emulated ranks pass the pointers in directly
+        through ShardP2P(...)."""
+        lay = shard_layout(L, self.alpha, rank, world)
+        n1, n2 = world * lay["gather1_slots"] * self.N, world * 2 * lay["gather2_slots"] * self.N
+        g1, g2, fl = self.dev_alloc(n1), self.dev_alloc(n2), self.dev_alloc(2 * world)
+        handles = exchange((self.ipc_export(g1), self.ipc_export(g2), self.ipc_export(fl)))
+        p1, p2, pf = [], [], []
+        for r, (h1, h2, hf) in enumerate(handles):
+            if r == rank:
+                p1.append(g1); p2.append(g2); pf.append(fl)
+            else:
+                p1.append(self.ipc_import(h1)); p2.append(self.ipc_import(h2)); pf.append(self.ipc_import(hf))
+        return ShardP2P(self, L, rank, world, p1, p2, pf)
+
     def counts(self, op, L):
         c = _Counts()
         rc = self.lib.hml_get_counts(self.h, op.encode(), L, C.byref(c))
@@ -388,6 +439,50 @@ class Context:
         for i, mi in enumerate(mod_idx):
             out[:, i].random_(0, self.moduli[mi], generator=g)
         return out.view(*lead, len(mod_idx), self.N)
+
+
+class ShardP2P:
+    """State of the peer-direct limb-sharded key switch on one rank: pointers to every rank's gather buffers / flag block
+    (own allocation at index `rank`, peer mappings elsewhere) and the epoch counter."""
+
+    def __init__(self, ctx, L, rank, world, peers1, peers2, peer_flags):
+        import torch
+        self.ctx, self.L, self.rank, self.world = ctx, L, rank, world
+        self.p1 = (C.c_void_p * world)(*peers1)
+        self.p2 = (C.c_void_p * world)(*peers2)
+        self.flags_own = peer_flags[rank]
+        self.pf_dev = torch.tensor(list(peer_flags), dtype=torch.int64, device="cuda")  # device array of the peers' flag blocks
+        self.g1_own, self.g2_own = peers1[rank], peers2[rank]
+        self.epoch = 0
+        self.lay = shard_layout(L, ctx.alpha, rank, world)
+
+    # the three phases, separately callable so that ranks emulated on one stream can be interleaved
+    def begin(self, d_own):
+        c = self.ctx
+        self.epoch += 1
+        c._chk(c.lib.hml_keyswitch_shard_begin(c.h, self.L, self.rank, self.world, _ptr(d_own), self.g1_own, c._stream()))
+        c._chk(c.lib.hml_shard_signal(c.h, self.pf_dev.data_ptr(), self.rank, self.epoch, self.world, c._stream()))
+
+    def mid(self, d_own, evk_own):
+        c = self.ctx
+        c._chk(c.lib.hml_shard_wait(c.h, self.flags_own, 0, self.epoch, self.world, c._stream()))
+        if evk_own is not None:  # a rank that owns no limb still takes part in the flag protocol
+            c._chk(c.lib.hml_keyswitch_shard_mid_p2p(c.h, self.L, self.rank, self.world, _ptr(d_own), self.p1, _ptr(evk_own), self.g2_own,
+                                                     c._stream()))
+        c._chk(c.lib.hml_shard_signal(c.h, self.pf_dev.data_ptr(), self.world + self.rank, self.epoch, self.world, c._stream()))
+
+    def end(self):
+        c = self.ctx
+        nq = len(self.lay["own_q"])
+        o0, o1 = c.empty(max(nq, 1), c.N), c.empty(max(nq, 1), c.N)
+        c._chk(c.lib.hml_shard_wait(c.h, self.flags_own, self.world, self.epoch, self.world, c._stream()))
+        c._chk(c.lib.hml_keyswitch_shard_end_p2p(c.h, self.L, self.rank, self.world, self.p2, _ptr(o0), _ptr(o1), c._stream()))
+        return o0[:nq], o1[:nq]
+
+    def keyswitch(self, d_own, evk_own):
+        self.begin(d_own)
+        self.mid(d_own, evk_own)
+        return self.end()
 
 
 class _Op:

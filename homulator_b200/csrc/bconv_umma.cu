@@ -274,14 +274,16 @@ k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BC
   // loader role: coefficient row lr (+ NT/4 for the thread's second item when NT = 256), source group g (sources
   // 16 s + 4 g .. + 3 of every 16-source slab s)
   const int g = tid & 3, lr = tid >> 2;
-  long long soff[N16][4];  // word offset of each of the thread's sources inside a batch; -1: beyond n_src (zero row)
+  long long soff[N16][4];  // word offset of each of the thread's sources inside a batch (may be negative: a peer's buffer)
+  unsigned live[N16] = {};  // bit k: source 16 s + 4 g + k exists (the others are zero rows)
 #pragma unroll
   for (int s = 0; s < N16; ++s)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int i = s * 16 + g * 4 + k;
-      soff[s][k] = i < a.n_src ? (long long)src_lm.pos[i] * a.N + lr : -1;
-      if (soff[s][k] < 0) {  // padding sources: their staging slots are never written by a copy, they stay zero
+      soff[s][k] = i < a.n_src ? (a.src_off ? __ldg(a.src_off + i) : (long long)src_lm.pos[i] * a.N) + lr : -1;
+      live[s] |= (i < a.n_src ? 1u : 0u) << k;
+      if (i >= a.n_src) {  // padding sources: their staging slots are never written by a copy, they stay zero
 #pragma unroll
         for (int d = 0; d < STAGES; ++d)
 #pragma unroll
@@ -304,7 +306,7 @@ k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BC
       for (int s = 0; s < N16; ++s)
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (soff[s][k] >= 0) {
+          if ((live[s] >> k) & 1u) {
 #pragma unroll
             for (int h = 0; h < IPT; ++h)
               asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + ((s * 4 + k) * UMMA_THREADS + h * NT) * 8),

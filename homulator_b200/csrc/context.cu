@@ -177,6 +177,8 @@ extern "C" void hml_ctx_destroy(hml_ctx *ctx) {
   for (auto &kv : ctx->bconv_cache) { cudaFree(kv.second.step1); cudaFree(kv.second.host.d_mat); cudaFree(kv.second.host.d_img); }
   for (auto &kv : ctx->shard_plans) {
     cudaFree(kv.second.scale1); cudaFree(kv.second.scale2); cudaFree(kv.second.pinv); cudaFree(kv.second.down.d_mat); cudaFree(kv.second.down.d_img);
+    cudaFree(kv.second.d_off2);
+    for (auto *o : kv.second.d_off1) cudaFree(o);
     for (auto &u : kv.second.up) { cudaFree(u.d_mat); cudaFree(u.d_img); }
   }
   cudaFree(ctx->tw_fwd); cudaFree(ctx->tw_inv); cudaFree(ctx->tw_fwd_rows); cudaFree(ctx->tw_inv_rows); cudaFree(ctx->mc); cudaFree(ctx->ws); cudaFree(ctx->stage);
@@ -791,28 +793,14 @@ extern "C" int hml_keyswitch_shard_begin(hml_ctx *ctx, uint32_t L, uint32_t rank
   return check_launch(ctx, "keyswitch shard begin");
 }
 
-extern "C" int hml_keyswitch_shard_mid(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, const uint64_t *d_own,
-                                       const uint64_t *gather1, const uint64_t *evk_own, uint64_t *gather2, void *stream) {
-  int rc = shard_check(ctx, L, rank, world);
-  if (rc) return rc;
-  if (!d_own || !gather1 || !evk_own || !gather2) return fail(ctx, HML_ERR_INVALID, "null buffer");
-  CU_TRY(ctx, cudaSetDevice(ctx->device));
-  ShardPlan *sp;
-  if ((rc = get_shard_plan(ctx, L, rank, world, &sp))) return rc;
-  if ((rc = ensure_ws(ctx, shard_ws_words(ctx->p, *sp)))) return rc;
+// everything of the middle phase after the ModUp conversions: NTT of the extended digits, inner product with the owned key
+// slices, INTT (+ scaling) of the owned P-limbs, copied into this rank's slot of gather buffer 2
+static int shard_mid_tail(hml_ctx *ctx, ShardPlan *sp, uint32_t rank, const u64 *d_own, const u64 *evk_own, u64 *gather2, cudaStream_t s) {
   const Params &p = ctx->p;
   const size_t N = p.N;
   const uint32_t nq = sp->own_q.size(), np = sp->own_p.size(), ne = nq + np, beta = sp->beta;
   const int logN = p.logN, npass = logN <= NTT_SMALL_LOG ? 1 : 2;
-  cudaStream_t s = (cudaStream_t)stream;
   u64 *ext = ctx->ws, *acc = ext + (size_t)beta * ne * N;
-  if (ne == 0) return HML_OK;
-  for (uint32_t j = 0; j < beta; ++j) {
-    if (sp->up[j].empty()) continue;
-    BConvArgs a{};
-    a.in = (const u64 *)gather1; a.out = ext + (size_t)j * ne * N; a.step1 = nullptr; a.N = N; a.n_batches = 1;
-    run_bconv(ctx, sp->up[j], sp->up_src[j], a, s);
-  }
   {
     NttLaunch l{};
     l.n_batch = 1;
@@ -823,7 +811,7 @@ extern "C" int hml_keyswitch_shard_mid(hml_ctx *ctx, uint32_t L, uint32_t rank, 
   }
   {
     InnerArgs a{};
-    a.d = (const u64 *)d_own; a.ext = ext; a.evk = (const u64 *)evk_own; a.acc = acc; a.N = N; a.n_ext = ne; a.beta = beta;
+    a.d = d_own; a.ext = ext; a.evk = evk_own; a.acc = acc; a.N = N; a.n_ext = ne; a.beta = beta;
     a.evk_limbs = ne; a.n_batch = 1;
     launch_inner_product(ctx->mc, sp->e_lm, a, s);
     ctx->exec.ewe_limbs += 2ull * ne * beta; ctx->exec.kernel_launches++;
@@ -837,32 +825,49 @@ extern "C" int hml_keyswitch_shard_mid(hml_ctx *ctx, uint32_t L, uint32_t rank, 
     ctx->exec.intt_limbs += 2 * np; ctx->exec.kernel_launches += npass;
     // this rank's contribution to gather buffer 2: [2][gp][N] at slot `rank`
     for (int c = 0; c < 2; ++c)
-      CU_TRY(ctx, cudaMemcpyAsync((u64 *)gather2 + ((size_t)rank * 2 + c) * sp->gp * N, acc + ((size_t)c * ne + nq) * N,
+      CU_TRY(ctx, cudaMemcpyAsync(gather2 + ((size_t)rank * 2 + c) * sp->gp * N, acc + ((size_t)c * ne + nq) * N,
                                   (size_t)np * N * 8, cudaMemcpyDeviceToDevice, s));
   }
   return check_launch(ctx, "keyswitch shard mid");
 }
 
-extern "C" int hml_keyswitch_shard_end(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, const uint64_t *gather2,
-                                       uint64_t *out0_own, uint64_t *out1_own, void *stream) {
+extern "C" int hml_keyswitch_shard_mid(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, const uint64_t *d_own,
+                                       const uint64_t *gather1, const uint64_t *evk_own, uint64_t *gather2, void *stream) {
   int rc = shard_check(ctx, L, rank, world);
   if (rc) return rc;
-  if (!gather2 || !out0_own || !out1_own) return fail(ctx, HML_ERR_INVALID, "null buffer");
+  if (!d_own || !gather1 || !evk_own || !gather2) return fail(ctx, HML_ERR_INVALID, "null buffer");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   ShardPlan *sp;
   if ((rc = get_shard_plan(ctx, L, rank, world, &sp))) return rc;
+  if ((rc = ensure_ws(ctx, shard_ws_words(ctx->p, *sp)))) return rc;
+  const size_t N = ctx->p.N;
+  const uint32_t ne = sp->own_q.size() + sp->own_p.size(), beta = sp->beta;
+  cudaStream_t s = (cudaStream_t)stream;
+  u64 *ext = ctx->ws;
+  if (ne == 0) return HML_OK;
+  for (uint32_t j = 0; j < beta; ++j) {
+    if (sp->up[j].empty()) continue;
+    BConvArgs a{};
+    a.in = (const u64 *)gather1; a.out = ext + (size_t)j * ne * N; a.step1 = nullptr; a.N = N; a.n_batches = 1;
+    run_bconv(ctx, sp->up[j], sp->up_src[j], a, s);
+  }
+  return shard_mid_tail(ctx, sp, rank, (const u64 *)d_own, (const u64 *)evk_own, (u64 *)gather2, s);
+}
+
+// last phase: BConv P -> owned Q-limbs (sources in `gather2`, or at src_off relative to it), NTT, (acc - v) * P^-1
+static int shard_end_run(hml_ctx *ctx, ShardPlan *sp, const u64 *gather2, const long long *src_off, u64 *out0_own, u64 *out1_own, cudaStream_t s) {
+  int rc;
   if ((rc = ensure_ws(ctx, shard_ws_words(ctx->p, *sp)))) return rc;
   const Params &p = ctx->p;
   const size_t N = p.N;
   const uint32_t nq = sp->own_q.size(), np = sp->own_p.size(), ne = nq + np, beta = sp->beta;
   const int logN = p.logN, npass = logN <= NTT_SMALL_LOG ? 1 : 2;
-  cudaStream_t s = (cudaStream_t)stream;
   if (nq == 0) return HML_OK;
   u64 *ext = ctx->ws, *acc = ext + (size_t)beta * ne * N, *vb = acc + 2 * (size_t)ne * N;
   {
     BConvArgs a{};
-    a.in = (const u64 *)gather2; a.out = vb; a.in_batch_stride = (long long)sp->gp * N; a.out_batch_stride = (long long)nq * N;
-    a.step1 = nullptr; a.N = N; a.n_batches = 2;
+    a.in = gather2; a.out = vb; a.in_batch_stride = (long long)sp->gp * N; a.out_batch_stride = (long long)nq * N;
+    a.step1 = nullptr; a.N = N; a.n_batches = 2; a.src_off = src_off;
     run_bconv(ctx, sp->down, sp->down_src, a, s);
   }
   {
@@ -875,12 +880,166 @@ extern "C" int hml_keyswitch_shard_end(hml_ctx *ctx, uint32_t L, uint32_t rank, 
   }
   for (int c = 0; c < 2; ++c) {
     SubMulArgs a{};
-    a.x = acc + (size_t)c * ne * N; a.y = vb + (size_t)c * nq * N; a.z = nullptr; a.out = (u64 *)(c ? out1_own : out0_own);
+    a.x = acc + (size_t)c * ne * N; a.y = vb + (size_t)c * nq * N; a.z = nullptr; a.out = c ? out1_own : out0_own;
     a.cst = sp->pinv; a.N = N; a.n_limbs = nq; a.n_polys = 1;
     launch_sub_mul_add(ctx->mc, sp->q_lm, a, s);
     ctx->exec.ewe_limbs += nq; ctx->exec.kernel_launches++;
   }
   return check_launch(ctx, "keyswitch shard end");
+}
+
+extern "C" int hml_keyswitch_shard_end(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, const uint64_t *gather2,
+                                       uint64_t *out0_own, uint64_t *out1_own, void *stream) {
+  int rc = shard_check(ctx, L, rank, world);
+  if (rc) return rc;
+  if (!gather2 || !out0_own || !out1_own) return fail(ctx, HML_ERR_INVALID, "null buffer");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  ShardPlan *sp;
+  if ((rc = get_shard_plan(ctx, L, rank, world, &sp))) return rc;
+  return shard_end_run(ctx, sp, (const u64 *)gather2, nullptr, (u64 *)out0_own, (u64 *)out1_own, (cudaStream_t)stream);
+}
+
+// ---- peer-direct variant: no collective.  Every rank keeps its contribution in its OWN gather buffer; the base
+// conversions of the other ranks read the source limbs straight out of the owners' memory over NVLink (per-source offsets,
+// BConvArgs::src_off) while they compute: the all-gather is fused into the consumer's tile loop (cp.async ring of the tcgen05
+// kernel, two tiles ahead) instead of being a separate NCCL step.  Ordering between GPUs: monotonically increasing epoch
+// counters in a per-rank flag block ([0, world): "gather buffer 1 of rank r is ready", [world, 2 world): buffer 2), written
+// into every peer by hml_shard_signal after the producing kernels, polled by hml_shard_wait before the consuming conversion.
+// Write-after-read safety needs no extra flags: a rank passes wait(ready2, t) only after every peer has finished its ModUp
+// reads of epoch t, and wait(ready1, t + 1) only after every peer has finished the ModDown reads of epoch t.
+__global__ void k_shard_signal(unsigned long long *const *peer_flags, int slot, unsigned long long epoch, int world) {
+  const int p = threadIdx.x;
+  if (p >= world) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flags[p] + slot), "l"(epoch) : "memory");
+}
+__global__ void k_shard_wait(const unsigned long long *flags, int base, unsigned long long epoch, int world) {
+  const int r = threadIdx.x;
+  if (r >= world) return;
+  const long long t0 = clock64();
+  unsigned long long v;
+  do {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + base + r) : "memory");
+    if (v < epoch && clock64() - t0 > (4ll << 30)) __trap();  // ~2 s: a peer that never signals must not hang the device
+  } while (v < epoch);
+}
+
+extern "C" int hml_shard_signal(hml_ctx *ctx, uint64_t *const *peer_flags_dev, uint32_t slot, uint64_t epoch, uint32_t world, void *stream) {
+  if (!ctx || !peer_flags_dev || world == 0 || world > 64) return HML_ERR_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  // a plain launch (no programmatic dependent launch): it starts after the producing kernels have completed and flushed
+  k_shard_signal<<<1, 64, 0, (cudaStream_t)stream>>>((unsigned long long *const *)peer_flags_dev, (int)slot, epoch, (int)world);
+  ctx->exec.kernel_launches++;
+  return check_launch(ctx, "shard signal");
+}
+extern "C" int hml_shard_wait(hml_ctx *ctx, const uint64_t *flags, uint32_t base, uint64_t epoch, uint32_t world, void *stream) {
+  if (!ctx || !flags || world == 0 || world > 64) return HML_ERR_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  k_shard_wait<<<1, 64, 0, (cudaStream_t)stream>>>((const unsigned long long *)flags, (int)base, epoch, (int)world);
+  ctx->exec.kernel_launches++;
+  return check_launch(ctx, "shard wait");
+}
+
+extern "C" int hml_ipc_export(hml_ctx *ctx, const uint64_t *dev_ptr, unsigned char handle[64]) {
+  if (!ctx || !dev_ptr || !handle) return HML_ERR_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  CU_TRY(ctx, cudaIpcGetMemHandle(&h, (void *)dev_ptr));
+  memcpy(handle, &h, 64);
+  return HML_OK;
+}
+extern "C" int hml_ipc_import(hml_ctx *ctx, const unsigned char handle[64], uint64_t **out) {
+  if (!ctx || !handle || !out) return HML_ERR_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CU_TRY(ctx, cudaIpcOpenMemHandle((void **)out, h, cudaIpcMemLazyEnablePeerAccess));
+  return HML_OK;
+}
+extern "C" int hml_ipc_close(hml_ctx *ctx, uint64_t *ptr) {
+  if (!ctx || !ptr) return HML_ERR_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaIpcCloseMemHandle(ptr));
+  return HML_OK;
+}
+
+// (re)build the per-source offset tables for the given peer buffers
+static int shard_peer_offsets(hml_ctx *ctx, ShardPlan *sp, const uint64_t *const *peers, bool second) {
+  const Params &p = ctx->p;
+  const uint32_t world = sp->world, rank = sp->rank, A = p.alpha, L = sp->L;
+  std::vector<const void *> sig(peers, peers + world);
+  std::vector<const void *> &cur = second ? sp->peers2_sig : sp->peers1_sig;
+  if (cur == sig) return HML_OK;
+  const long long N = p.N;
+  auto rel = [&](uint32_t owner) { return (long long)(peers[owner] - peers[rank]); };  // words
+  int rc;
+  if (!second) {
+    for (auto *o : sp->d_off1) cudaFree(o);
+    sp->d_off1.clear();
+    for (uint32_t j = 0; j < sp->beta; ++j) {
+      const uint32_t lo = j * A, aj = p.digit_size(L, j);
+      std::vector<long long> off(aj);
+      for (uint32_t i = 0; i < aj; ++i) off[i] = rel((lo + i) % world) + (long long)sp->up_src[j].pos[i] * N;
+      long long *d = nullptr;
+      if ((rc = upload(ctx, off, &d))) return rc;
+      sp->d_off1.push_back(d);
+    }
+  } else {
+    cudaFree(sp->d_off2); sp->d_off2 = nullptr;
+    std::vector<long long> off(A);
+    for (uint32_t j = 0; j < A; ++j) off[j] = rel((L + j) % world) + (long long)sp->down_src.pos[j] * N;
+    if ((rc = upload(ctx, off, &sp->d_off2))) return rc;
+  }
+  cur = sig;
+  return HML_OK;
+}
+
+static int shard_p2p_check(hml_ctx *ctx, const HostBConv &hb) {
+  if (hb.empty()) return HML_OK;
+  if (!hb.im.img || ctx->p.N < 128 || !bconv_umma_enabled())
+    return fail(ctx, HML_ERR_UNSUPPORTED, "peer-direct key switch needs the tcgen05 base conversion (N >= 128, <= 48 x 48 limbs)");
+  return HML_OK;
+}
+
+extern "C" int hml_keyswitch_shard_mid_p2p(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, const uint64_t *d_own,
+                                           const uint64_t *const *peers1, const uint64_t *evk_own, uint64_t *gather2_own, void *stream) {
+  int rc = shard_check(ctx, L, rank, world);
+  if (rc) return rc;
+  if (!d_own || !peers1 || !evk_own || !gather2_own) return fail(ctx, HML_ERR_INVALID, "null buffer");
+  for (uint32_t r = 0; r < world; ++r) if (!peers1[r]) return fail(ctx, HML_ERR_INVALID, "null peer buffer");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  ShardPlan *sp;
+  if ((rc = get_shard_plan(ctx, L, rank, world, &sp))) return rc;
+  for (auto &u : sp->up) if ((rc = shard_p2p_check(ctx, u))) return rc;
+  if ((rc = shard_peer_offsets(ctx, sp, peers1, false))) return rc;
+  if ((rc = ensure_ws(ctx, shard_ws_words(ctx->p, *sp)))) return rc;
+  const size_t N = ctx->p.N;
+  const uint32_t ne = sp->own_q.size() + sp->own_p.size(), beta = sp->beta;
+  if (ne == 0) return HML_OK;
+  u64 *ext = ctx->ws;
+  for (uint32_t j = 0; j < beta; ++j) {
+    if (sp->up[j].empty()) continue;
+    BConvArgs a{};
+    a.in = (const u64 *)peers1[rank]; a.out = ext + (size_t)j * ne * N; a.step1 = nullptr; a.N = N; a.n_batches = 1;
+    a.src_off = sp->d_off1[j];
+    run_bconv(ctx, sp->up[j], sp->up_src[j], a, (cudaStream_t)stream);
+  }
+  return shard_mid_tail(ctx, sp, rank, (const u64 *)d_own, (const u64 *)evk_own, (u64 *)gather2_own, (cudaStream_t)stream);
+}
+
+extern "C" int hml_keyswitch_shard_end_p2p(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, const uint64_t *const *peers2,
+                                           uint64_t *out0_own, uint64_t *out1_own, void *stream) {
+  int rc = shard_check(ctx, L, rank, world);
+  if (rc) return rc;
+  if (!peers2 || !out0_own || !out1_own) return fail(ctx, HML_ERR_INVALID, "null buffer");
+  for (uint32_t r = 0; r < world; ++r) if (!peers2[r]) return fail(ctx, HML_ERR_INVALID, "null peer buffer");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  ShardPlan *sp;
+  if ((rc = get_shard_plan(ctx, L, rank, world, &sp))) return rc;
+  if ((rc = shard_p2p_check(ctx, sp->down))) return rc;
+  if ((rc = shard_peer_offsets(ctx, sp, peers2, true))) return rc;
+  return shard_end_run(ctx, sp, (const u64 *)peers2[rank], sp->d_off2, (u64 *)out0_own, (u64 *)out1_own, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------ rescale

@@ -65,6 +65,11 @@ struct ShardPlan {
   // rank r's owned P-limbs are the extended limbs e = L + j with e % world == r; its first such e sits at slot
   // floor(e / world) counted over ALL its limbs, so subtract the number of Q-limbs it owns
   static uint32_t first_p_slot(uint32_t r, uint32_t L, uint32_t world) { return L > r ? (L - r + world - 1) / world : 0; }
+  // peer-direct mode (hml_keyswitch_shard_*_p2p): per-source word offsets into the OWNERS' gather buffers, relative to this
+  // rank's own buffer, rebuilt whenever the peer pointers change
+  std::vector<long long *> d_off1;         // [beta] device arrays [a_j]
+  long long *d_off2 = nullptr;             // device array [alpha]
+  std::vector<const void *> peers1_sig, peers2_sig;
 };
 
 struct DevBConv {  // cached tables of an arbitrary (src, dst) conversion for the primitive entry point

@@ -75,6 +75,9 @@ struct BConvArgs {
   // 1: store the centred remainder as a double (|v| <= q/2) instead of the canonical word — the hand-off format to a
   // forward NTT launched with NttLaunch::in_f64 (saves the canonicalisation here and the integer -> double conversion there)
   int out_f64;
+  // optional (tcgen05 kernel only): word offset of every source limb relative to `in`, replacing src_lm.pos[i] * N.  The
+  // limb-sharded key switch points these at the PEER GPUs' buffers (NVLink loads inside the conversion, no all-gather).
+  const long long *src_off;   // device array [n_src] or null
 };
 // int8 operand image of a conversion matrix for the tcgen05 path (bconv_umma.cu): img == null -> the DMMA kernel runs
 struct BConvImage {

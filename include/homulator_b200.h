@@ -146,6 +146,29 @@ int hml_keyswitch_shard_mid(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t wo
 int hml_keyswitch_shard_end(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, const uint64_t *gather2,
                             uint64_t *out0_own, uint64_t *out1_own, void *stream);
 
+/* Peer-direct variant of the same three phases: NO collective.  Every rank keeps its contribution in its own gather
+ * buffers; the base conversions of the other ranks read the source limbs straight out of the owners' memory over NVLink
+ * while they compute (the all-gather is fused into the consumer kernel's tile loop, homulator_b200/csrc/bconv_umma.cu).
+ *   peers1[r] / peers2[r]   rank r's gather buffer 1 / 2 as a pointer valid on THIS device: the rank's own allocation for
+ *                           r == rank, a cudaIpcOpenMemHandle / peer-enabled mapping otherwise (HOST arrays of `world` pointers)
+ *   flags                   per rank 2 * world zero-initialised words: [r] = epoch up to which rank r's buffer 1 is ready,
+ *                           [world + r] = the same for buffer 2
+ * Sequence per key switch (epoch = 1, 2, ... per call): shard_begin(own buffer 1) -> shard_signal(slot rank) ->
+ * shard_wait(base 0) -> shard_mid_p2p -> shard_signal(slot world + rank) -> shard_wait(base world) -> shard_end_p2p.
+ * hml_shard_signal writes `epoch` into flags[slot] of EVERY peer (peer_flags_dev = DEVICE array of `world` pointers);
+ * hml_shard_wait spins on the device until flags[base + r] >= epoch for all r (traps after ~2 s).  hml_ipc_export / import
+ * wrap cudaIpcGetMemHandle / cudaIpcOpenMemHandle for buffers obtained from hml_dev_alloc, so a host without the CUDA
+ * runtime can exchange them between the per-GPU processes. */
+int hml_keyswitch_shard_mid_p2p(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, const uint64_t *d_own,
+                                const uint64_t *const *peers1, const uint64_t *evk_own, uint64_t *gather2_own, void *stream);
+int hml_keyswitch_shard_end_p2p(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, const uint64_t *const *peers2,
+                                uint64_t *out0_own, uint64_t *out1_own, void *stream);
+int hml_shard_signal(hml_ctx *ctx, uint64_t *const *peer_flags_dev, uint32_t slot, uint64_t epoch, uint32_t world, void *stream);
+int hml_shard_wait(hml_ctx *ctx, const uint64_t *flags, uint32_t base, uint64_t epoch, uint32_t world, void *stream);
+int hml_ipc_export(hml_ctx *ctx, const uint64_t *dev_ptr, unsigned char handle[64]);
+int hml_ipc_import(hml_ctx *ctx, const unsigned char handle[64], uint64_t **out);
+int hml_ipc_close(hml_ctx *ctx, uint64_t *ptr);
+
 /* ------------------------------------------------------------------ operations (reference include/Operation.h) */
 /* HMULT (reference src/Operation.cpp:913-1023): tensor + keyswitch(relinearise) + add + rescale x2.
  * ct_a, ct_b [2][L][N]; ct_out [2][L-1][N].  Requires L >= 2 (the reference segfaults at L=1). */

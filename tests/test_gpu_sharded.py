@@ -75,6 +75,60 @@ def test_sharded_keyswitch_emulated_ranks(N, ML, L, A, world):
     assert np.array_equal(one0, want0) and np.array_equal(one1, want1)
 
 
+def sharded_keyswitch_p2p_emulated(ctxs, L, d, evk, world, reps=2):
+    """Peer-direct variant with the ranks emulated on one GPU and one stream: every rank's conversions read the other ranks'
+    gather buffers through per-source offsets, ordered by the epoch flags (signals are enqueued before the waits that need
+    them).  Runs `reps` key switches back to back (buffer reuse across epochs)."""
+    A, N = ctxs[0].alpha, ctxs[0].N
+    lays = [hml.shard_layout(L, A, r, world) for r in range(world)]
+    g1 = [c.dev_alloc(world * lays[r]["gather1_slots"] * N) for r, c in enumerate(ctxs)]
+    g2 = [c.dev_alloc(world * 2 * lays[r]["gather2_slots"] * N) for r, c in enumerate(ctxs)]
+    fl = [c.dev_alloc(2 * world) for c in ctxs]
+    sh = [hml.ShardP2P(c, L, r, world, g1, g2, fl) for r, c in enumerate(ctxs)]
+    d_own, evk_own = [], []
+    for r, lay in enumerate(lays):
+        own_e = lay["own_q"] + [L + j for j in lay["own_p"]]
+        d_own.append(to_dev(d[lay["own_q"]] if lay["own_q"] else np.zeros((1, N), dtype=np.uint64)))
+        evk_own.append(to_dev(evk[:, :, own_e]) if own_e else None)
+    for _ in range(reps):
+        for r in range(world):
+            sh[r].begin(d_own[r])
+        for r in range(world):
+            sh[r].mid(d_own[r], evk_own[r])
+        outs = [sh[r].end() for r in range(world)]
+    out0, out1 = np.zeros((L, N), dtype=np.uint64), np.zeros((L, N), dtype=np.uint64)
+    for r in range(world):
+        if lays[r]["own_q"]:
+            out0[lays[r]["own_q"]] = to_host(outs[r][0])
+            out1[lays[r]["own_q"]] = to_host(outs[r][1])
+    return out0, out1
+
+
+@pytest.mark.parametrize("N,ML,L,A,world", [(256, 7, 7, 3, 2), (256, 7, 7, 3, 3), (1024, 6, 5, 2, 4), (8192, 9, 8, 3, 2),
+                                             (65536, 45, 35, 15, 4)])
+def test_sharded_keyswitch_peer_direct_emulated_ranks(N, ML, L, A, world):
+    o = Oracle(N, 36, ML, A)
+    Oracle.set_threads(0)
+    beta = -(-L // A)
+    d = uniform_limbs(o.moduli[:L], N, 2100 + L)
+    evk = uniform_limbs(o.moduli[:L] + o.moduli[ML:], N, 2101, lead=(beta, 2))
+    want0, want1 = o.keyswitch(L, d, evk, L)
+    Oracle.set_threads(1)
+    ctxs = [hml.Context(N=N, max_level=ML, alpha=A) for _ in range(world)]
+    got0, got1 = sharded_keyswitch_p2p_emulated(ctxs, L, d, evk, world)
+    assert np.array_equal(got0, want0) and np.array_equal(got1, want1)
+
+
+def test_peer_direct_needs_the_tcgen05_conversion():
+    ctx = hml.Context(N=64, max_level=5, alpha=3)  # N < 128: the FP64 tensor-core kernel has no per-source offsets
+    g1, g2, fl = ctx.dev_alloc(2 * 1 * 64), ctx.dev_alloc(2 * 2 * 2 * 64), ctx.dev_alloc(4)
+    sh = hml.ShardP2P(ctx, 2, 0, 2, [g1, g1], [g2, g2], [fl, fl])
+    d = ctx.uniform([0], 1)
+    evk = ctx.uniform([0, 1, 2], 2, lead=(1, 2))
+    with pytest.raises(hml.HmlError):
+        ctx._chk(ctx.lib.hml_keyswitch_shard_mid_p2p(ctx.h, 2, 0, 2, d.data_ptr(), sh.p1, evk.data_ptr(), g2, None))
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
 def test_sharded_keyswitch_nccl():
     n = min(torch.cuda.device_count(), 4)
@@ -83,3 +137,13 @@ def test_sharded_keyswitch_nccl():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "SHARDED_KS_OK" in r.stdout
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
+def test_sharded_keyswitch_peer_direct_over_nvlink():
+    n = min(torch.cuda.device_count(), 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "mp_sharded_keyswitch_p2p.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "SHARDED_P2P_OK" in r.stdout
