@@ -54,7 +54,7 @@ EXPORTS = [
     "hml_hmult_host", "hml_hrotate_host", "hml_host_alloc_pinned", "hml_host_free_pinned", "hml_trace_counts",
     "hml_get_counts", "hml_buffer_plan", "hml_exec_counts_get", "hml_exec_counts_reset", "hml_cli_main",
     "hml_shard_layout", "hml_keyswitch_shard_begin", "hml_keyswitch_shard_mid", "hml_keyswitch_shard_end",
-    "hml_keyswitch_shard_mid_p2p", "hml_keyswitch_shard_end_p2p", "hml_shard_signal", "hml_shard_wait",
+    "hml_keyswitch_shard_mid_p2p", "hml_keyswitch_shard_end_p2p", "hml_shard_signal", "hml_shard_wait", "hml_shard_sync",
     "hml_ipc_export", "hml_ipc_import", "hml_ipc_close",
 ]
 
@@ -117,6 +117,7 @@ def load_library():
     L.hml_keyswitch_shard_end_p2p.argtypes = [vp, u32, u32, u32, C.POINTER(vp), vp, vp, vp]
     L.hml_shard_signal.argtypes = [vp, vp, u32, u64, u32, vp]
     L.hml_shard_wait.argtypes = [vp, vp, u32, u64, u32, vp]
+    L.hml_shard_sync.argtypes = [vp, vp, u32, vp, u32, u64, u32, vp]
     L.hml_ipc_export.argtypes = [vp, vp, C.c_char_p]
     L.hml_ipc_import.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.hml_ipc_close.argtypes = [vp, vp]
@@ -480,9 +481,18 @@ class ShardP2P:
         return o0[:nq], o1[:nq]
 
     def keyswitch(self, d_own, evk_own):
-        self.begin(d_own)
-        self.mid(d_own, evk_own)
-        return self.end()
+        """One rank per GPU: the whole key switch, signal + wait fused into one launch per exchange."""
+        c, st = self.ctx, self.ctx._stream()
+        self.epoch += 1
+        nq = len(self.lay["own_q"])
+        o0, o1 = c.empty(max(nq, 1), c.N), c.empty(max(nq, 1), c.N)
+        c._chk(c.lib.hml_keyswitch_shard_begin(c.h, self.L, self.rank, self.world, _ptr(d_own), self.g1_own, st))
+        c._chk(c.lib.hml_shard_sync(c.h, self.pf_dev.data_ptr(), self.rank, self.flags_own, 0, self.epoch, self.world, st))
+        if evk_own is not None:
+            c._chk(c.lib.hml_keyswitch_shard_mid_p2p(c.h, self.L, self.rank, self.world, _ptr(d_own), self.p1, _ptr(evk_own), self.g2_own, st))
+        c._chk(c.lib.hml_shard_sync(c.h, self.pf_dev.data_ptr(), self.world + self.rank, self.flags_own, self.world, self.epoch, self.world, st))
+        c._chk(c.lib.hml_keyswitch_shard_end_p2p(c.h, self.L, self.rank, self.world, self.p2, _ptr(o0), _ptr(o1), st))
+        return o0[:nq], o1[:nq]
 
 
 class _Op:

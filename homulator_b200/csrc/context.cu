@@ -819,14 +819,13 @@ static int shard_mid_tail(hml_ctx *ctx, ShardPlan *sp, uint32_t rank, const u64 
   if (np) {
     NttLaunch l{};
     l.n_batch = 1;
-    l.in = acc; l.out = acc; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)ne * N;
+    // straight into this rank's contribution to gather buffer 2, [2][gp][N] at slot `rank`: limb k of p_lm sits at position
+    // nq + k of an accumulator, so the output base is shifted back by nq limbs (never dereferenced below the slot)
+    l.in = acc; l.in_limb_stride = N; l.in_poly_stride = (long long)ne * N;
+    l.out = gather2 + (size_t)rank * 2 * sp->gp * N - (size_t)nq * N; l.out_limb_stride = N; l.out_poly_stride = (long long)sp->gp * N;
     l.n_limbs = np; l.n_polys = 2; l.post_scale = sp->scale2;
     launch_ntt_inverse(ctx->tabs, logN, sp->p_lm, l, s);
     ctx->exec.intt_limbs += 2 * np; ctx->exec.kernel_launches += npass;
-    // this rank's contribution to gather buffer 2: [2][gp][N] at slot `rank`
-    for (int c = 0; c < 2; ++c)
-      CU_TRY(ctx, cudaMemcpyAsync(gather2 + ((size_t)rank * 2 + c) * sp->gp * N, acc + ((size_t)c * ne + nq) * N,
-                                  (size_t)np * N * 8, cudaMemcpyDeviceToDevice, s));
   }
   return check_launch(ctx, "keyswitch shard mid");
 }
@@ -922,6 +921,31 @@ __global__ void k_shard_wait(const unsigned long long *flags, int base, unsigned
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + base + r) : "memory");
     if (v < epoch && clock64() - t0 > (4ll << 30)) __trap();  // ~2 s: a peer that never signals must not hang the device
   } while (v < epoch);
+}
+
+// signal + wait in one launch (one rank per GPU; ranks emulated on ONE stream must use the two separate calls, because a
+// rank's wait would otherwise sit in front of the signals it is waiting for)
+__global__ void k_shard_sync(unsigned long long *const *peer_flags, int slot, const unsigned long long *flags, int base,
+                             unsigned long long epoch, int world) {
+  const int r = threadIdx.x;
+  if (r >= world) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flags[r] + slot), "l"(epoch) : "memory");
+  const long long t0 = clock64();
+  unsigned long long v;
+  do {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + base + r) : "memory");
+    if (v < epoch && clock64() - t0 > (4ll << 30)) __trap();
+  } while (v < epoch);
+}
+extern "C" int hml_shard_sync(hml_ctx *ctx, uint64_t *const *peer_flags_dev, uint32_t slot, const uint64_t *flags, uint32_t base,
+                              uint64_t epoch, uint32_t world, void *stream) {
+  if (!ctx || !peer_flags_dev || !flags || world == 0 || world > 64) return HML_ERR_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  k_shard_sync<<<1, 64, 0, (cudaStream_t)stream>>>((unsigned long long *const *)peer_flags_dev, (int)slot, (const unsigned long long *)flags,
+                                                   (int)base, epoch, (int)world);
+  ctx->exec.kernel_launches++;
+  return check_launch(ctx, "shard sync");
 }
 
 extern "C" int hml_shard_signal(hml_ctx *ctx, uint64_t *const *peer_flags_dev, uint32_t slot, uint64_t epoch, uint32_t world, void *stream) {

@@ -165,6 +165,9 @@ int hml_keyswitch_shard_end_p2p(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_
                                 uint64_t *out0_own, uint64_t *out1_own, void *stream);
 int hml_shard_signal(hml_ctx *ctx, uint64_t *const *peer_flags_dev, uint32_t slot, uint64_t epoch, uint32_t world, void *stream);
 int hml_shard_wait(hml_ctx *ctx, const uint64_t *flags, uint32_t base, uint64_t epoch, uint32_t world, void *stream);
+/* signal followed by wait in ONE launch (one rank per GPU only: ranks emulated on a single stream need the separate calls) */
+int hml_shard_sync(hml_ctx *ctx, uint64_t *const *peer_flags_dev, uint32_t slot, const uint64_t *flags, uint32_t base,
+                   uint64_t epoch, uint32_t world, void *stream);
 int hml_ipc_export(hml_ctx *ctx, const uint64_t *dev_ptr, unsigned char handle[64]);
 int hml_ipc_import(hml_ctx *ctx, const unsigned char handle[64], uint64_t **out);
 int hml_ipc_close(hml_ctx *ctx, uint64_t *ptr);
