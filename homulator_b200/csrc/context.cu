@@ -877,12 +877,13 @@ static int shard_end_run(hml_ctx *ctx, ShardPlan *sp, const u64 *gather2, const 
     launch_ntt_forward(ctx->tabs, logN, sp->q_lm, l, s);
     ctx->exec.ntt_limbs += 2 * nq; ctx->exec.kernel_launches += npass;
   }
-  for (int c = 0; c < 2; ++c) {
+  {  // both outputs in one launch: the "poly" stride of the output is simply the distance between the two buffers
     SubMulArgs a{};
-    a.x = acc + (size_t)c * ne * N; a.y = vb + (size_t)c * nq * N; a.z = nullptr; a.out = c ? out1_own : out0_own;
-    a.cst = sp->pinv; a.N = N; a.n_limbs = nq; a.n_polys = 1;
+    a.x = acc; a.x_poly_stride = (long long)ne * N; a.y = vb; a.y_poly_stride = (long long)nq * N; a.z = nullptr;
+    a.out = out0_own; a.out_poly_stride = (long long)(out1_own - out0_own);
+    a.cst = sp->pinv; a.N = N; a.n_limbs = nq; a.n_polys = 2;
     launch_sub_mul_add(ctx->mc, sp->q_lm, a, s);
-    ctx->exec.ewe_limbs += nq; ctx->exec.kernel_launches++;
+    ctx->exec.ewe_limbs += 2 * nq; ctx->exec.kernel_launches++;
   }
   return check_launch(ctx, "keyswitch shard end");
 }
