@@ -55,7 +55,7 @@ EXPORTS = [
     "hml_get_counts", "hml_buffer_plan", "hml_exec_counts_get", "hml_exec_counts_reset", "hml_cli_main",
     "hml_shard_layout", "hml_keyswitch_shard_begin", "hml_keyswitch_shard_mid", "hml_keyswitch_shard_end",
     "hml_keyswitch_shard_mid_p2p", "hml_keyswitch_shard_end_p2p", "hml_shard_signal", "hml_shard_wait", "hml_shard_sync",
-    "hml_ipc_export", "hml_ipc_import", "hml_ipc_close",
+    "hml_ipc_export", "hml_ipc_import", "hml_ipc_close", "hml_rescale_shard_begin", "hml_rescale_shard_end",
 ]
 
 
@@ -118,6 +118,8 @@ def load_library():
     L.hml_shard_signal.argtypes = [vp, vp, u32, u64, u32, vp]
     L.hml_shard_wait.argtypes = [vp, vp, u32, u64, u32, vp]
     L.hml_shard_sync.argtypes = [vp, vp, u32, vp, u32, u64, u32, vp]
+    L.hml_rescale_shard_begin.argtypes = [vp, u32, u32, u32, vp, vp, vp]
+    L.hml_rescale_shard_end.argtypes = [vp, u32, u32, u32, vp, vp, vp, vp]
     L.hml_ipc_export.argtypes = [vp, vp, C.c_char_p]
     L.hml_ipc_import.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.hml_ipc_close.argtypes = [vp, vp]
@@ -397,15 +399,15 @@ class Context:
         through ShardP2P(...)."""
         lay = shard_layout(L, self.alpha, rank, world)
         n1, n2 = world * lay["gather1_slots"] * self.N, world * 2 * lay["gather2_slots"] * self.N
-        g1, g2, fl = self.dev_alloc(n1), self.dev_alloc(n2), self.dev_alloc(2 * world)
-        handles = exchange((self.ipc_export(g1), self.ipc_export(g2), self.ipc_export(fl)))
-        p1, p2, pf = [], [], []
-        for r, (h1, h2, hf) in enumerate(handles):
+        g1, g2, fl, rb = self.dev_alloc(n1), self.dev_alloc(n2), self.dev_alloc(3 * world), self.dev_alloc(2 * self.N)
+        handles = exchange((self.ipc_export(g1), self.ipc_export(g2), self.ipc_export(fl), self.ipc_export(rb)))
+        p1, p2, pf, pr = [], [], [], []
+        for r, (h1, h2, hf, hr) in enumerate(handles):
             if r == rank:
-                p1.append(g1); p2.append(g2); pf.append(fl)
+                p1.append(g1); p2.append(g2); pf.append(fl); pr.append(rb)
             else:
-                p1.append(self.ipc_import(h1)); p2.append(self.ipc_import(h2)); pf.append(self.ipc_import(hf))
-        return ShardP2P(self, L, rank, world, p1, p2, pf)
+                p1.append(self.ipc_import(h1)); p2.append(self.ipc_import(h2)); pf.append(self.ipc_import(hf)); pr.append(self.ipc_import(hr))
+        return ShardP2P(self, L, rank, world, p1, p2, pf, pr)
 
     def counts(self, op, L):
         c = _Counts()
@@ -443,10 +445,15 @@ class Context:
 
 
 class ShardP2P:
-    """State of the peer-direct limb-sharded key switch on one rank: pointers to every rank's gather buffers / flag block
-    (own allocation at index `rank`, peer mappings elsewhere) and the epoch counter."""
+    """State of the peer-direct limb-sharded ops on one rank: pointers to every rank's gather buffers, rescale buffer and flag
+    block (own allocation at index `rank`, peer mappings elsewhere) and the epoch counters.  A sharded ciphertext is a tensor
+    [2][nq][N] holding this rank's Q-limbs (ascending limb index, limb i lives on rank i % world).
 
-    def __init__(self, ctx, L, rank, world, peers1, peers2, peer_flags):
+    Phase methods (begin / mid / end, rescale_begin / rescale_end) use separate signal and wait launches so that ranks emulated
+    on ONE stream can be interleaved phase by phase; keyswitch / hrotate / hmult are the one-rank-per-GPU compositions with
+    signal + wait fused into one launch per exchange."""
+
+    def __init__(self, ctx, L, rank, world, peers1, peers2, peer_flags, peers_r=None):
         import torch
         self.ctx, self.L, self.rank, self.world = ctx, L, rank, world
         self.p1 = (C.c_void_p * world)(*peers1)
@@ -454,10 +461,15 @@ class ShardP2P:
         self.flags_own = peer_flags[rank]
         self.pf_dev = torch.tensor(list(peer_flags), dtype=torch.int64, device="cuda")  # device array of the peers' flag blocks
         self.g1_own, self.g2_own = peers1[rank], peers2[rank]
-        self.epoch = 0
+        self.pr = list(peers_r) if peers_r is not None else None
+        self.epoch = 0      # key-switch exchanges
+        self.epoch_r = 0    # rescale exchanges
         self.lay = shard_layout(L, ctx.alpha, rank, world)
+        self.own = list(self.lay["own_q"])
+        self.nq = len(self.own)
+        self.nk = self.nq - (1 if (L - 1) % world == rank else 0)   # owned limbs that survive a rescale
 
-    # the three phases, separately callable so that ranks emulated on one stream can be interleaved
+    # ---- key switch
     def begin(self, d_own):
         c = self.ctx
         self.epoch += 1
@@ -472,27 +484,99 @@ class ShardP2P:
                                                      c._stream()))
         c._chk(c.lib.hml_shard_signal(c.h, self.pf_dev.data_ptr(), self.world + self.rank, self.epoch, self.world, c._stream()))
 
-    def end(self):
+    def _outs(self, o0, o1):
         c = self.ctx
-        nq = len(self.lay["own_q"])
-        o0, o1 = c.empty(max(nq, 1), c.N), c.empty(max(nq, 1), c.N)
+        return (c.empty(max(self.nq, 1), c.N) if o0 is None else o0), (c.empty(max(self.nq, 1), c.N) if o1 is None else o1)
+
+    def end(self, o0=None, o1=None):
+        c = self.ctx
+        o0, o1 = self._outs(o0, o1)
         c._chk(c.lib.hml_shard_wait(c.h, self.flags_own, self.world, self.epoch, self.world, c._stream()))
         c._chk(c.lib.hml_keyswitch_shard_end_p2p(c.h, self.L, self.rank, self.world, self.p2, _ptr(o0), _ptr(o1), c._stream()))
-        return o0[:nq], o1[:nq]
+        return o0[:self.nq], o1[:self.nq]
 
-    def keyswitch(self, d_own, evk_own):
+    def keyswitch(self, d_own, evk_own, o0=None, o1=None):
         """One rank per GPU: the whole key switch, signal + wait fused into one launch per exchange."""
         c, st = self.ctx, self.ctx._stream()
         self.epoch += 1
-        nq = len(self.lay["own_q"])
-        o0, o1 = c.empty(max(nq, 1), c.N), c.empty(max(nq, 1), c.N)
+        o0, o1 = self._outs(o0, o1)
         c._chk(c.lib.hml_keyswitch_shard_begin(c.h, self.L, self.rank, self.world, _ptr(d_own), self.g1_own, st))
         c._chk(c.lib.hml_shard_sync(c.h, self.pf_dev.data_ptr(), self.rank, self.flags_own, 0, self.epoch, self.world, st))
         if evk_own is not None:
             c._chk(c.lib.hml_keyswitch_shard_mid_p2p(c.h, self.L, self.rank, self.world, _ptr(d_own), self.p1, _ptr(evk_own), self.g2_own, st))
         c._chk(c.lib.hml_shard_sync(c.h, self.pf_dev.data_ptr(), self.world + self.rank, self.flags_own, self.world, self.epoch, self.world, st))
         c._chk(c.lib.hml_keyswitch_shard_end_p2p(c.h, self.L, self.rank, self.world, self.p2, _ptr(o0), _ptr(o1), st))
-        return o0[:nq], o1[:nq]
+        return o0[:self.nq], o1[:self.nq]
+
+    # ---- limb-local pieces of the ops (element-wise kernels over the owned limbs)
+    def _ew(self, x1, x2, x3, x4, comps, out=None):
+        return self.ctx.ewe(x1, x2, x3, x4, self.own * comps, out=out)
+
+    def hadd(self, a, b):
+        return self._ew(a.view(-1, self.ctx.N), None, b.view(-1, self.ctx.N), None, 2).view(2, self.nq, self.ctx.N)
+
+    def pmult(self, ct, pt2):
+        """pt2 = the plaintext's owned limbs repeated for both components, [2][nq][N]."""
+        return self._ew(ct.view(-1, self.ctx.N), pt2.view(-1, self.ctx.N), None, None, 2).view(2, self.nq, self.ctx.N)
+
+    def padd(self, ct, pt2):
+        return self._ew(ct.view(-1, self.ctx.N), None, pt2.view(-1, self.ctx.N), None, 2).view(2, self.nq, self.ctx.N)
+
+    def hrotate_pre(self, ct, g):
+        return self.ctx.automorph(ct.view(-1, self.ctx.N), g).view(2, self.nq, self.ctx.N)
+
+    def hrotate_post(self, sig, k0, out):
+        self._ew(sig[0], None, k0, None, 1, out=out[0])   # out[1] was written by the key switch itself
+        return out
+
+    def hmult_pre(self, a, b):
+        d0 = self._ew(a[0], b[0], None, None, 1)
+        d1 = self._ew(a[0], b[1], a[1], b[0], 1)
+        d2 = self._ew(a[1], b[1], None, None, 1)
+        return d0, d1, d2
+
+    def hmult_post(self, d0, d1, k0, k1):
+        c = self.ctx.empty(2, self.nq, self.ctx.N)
+        self._ew(d0, None, k0, None, 1, out=c[0])
+        self._ew(d1, None, k1, None, 1, out=c[1])
+        return c
+
+    # ---- rescale
+    def rescale_begin(self, x):
+        c = self.ctx
+        self.epoch_r += 1
+        c._chk(c.lib.hml_rescale_shard_begin(c.h, self.L, self.rank, self.world, _ptr(x), self.pr[self.rank], c._stream()))
+        c._chk(c.lib.hml_shard_signal(c.h, self.pf_dev.data_ptr(), 2 * self.world + self.rank, self.epoch_r, self.world, c._stream()))
+
+    def rescale_end(self, x):
+        c = self.ctx
+        out = c.empty(2, max(self.nk, 1), c.N)
+        c._chk(c.lib.hml_shard_wait(c.h, self.flags_own, 2 * self.world, self.epoch_r, self.world, c._stream()))
+        c._chk(c.lib.hml_rescale_shard_end(c.h, self.L, self.rank, self.world, _ptr(x), self.pr[(self.L - 1) % self.world], _ptr(out),
+                                           c._stream()))
+        return out[:, :self.nk]
+
+    def rescale(self, x):
+        c, st = self.ctx, self.ctx._stream()
+        self.epoch_r += 1
+        out = c.empty(2, max(self.nk, 1), c.N)
+        c._chk(c.lib.hml_rescale_shard_begin(c.h, self.L, self.rank, self.world, _ptr(x), self.pr[self.rank], st))
+        c._chk(c.lib.hml_shard_sync(c.h, self.pf_dev.data_ptr(), 2 * self.world + self.rank, self.flags_own, 2 * self.world, self.epoch_r,
+                                    self.world, st))
+        c._chk(c.lib.hml_rescale_shard_end(c.h, self.L, self.rank, self.world, _ptr(x), self.pr[(self.L - 1) % self.world], _ptr(out), st))
+        return out[:, :self.nk]
+
+    # ---- whole ops, one rank per GPU
+    def hrotate(self, ct, rk_own, g):
+        sig = self.hrotate_pre(ct, g)
+        out = self.ctx.empty(2, self.nq, self.ctx.N)
+        k0, _ = self.keyswitch(sig[1], rk_own, o1=out[1])
+        return self.hrotate_post(sig, k0, out)
+
+    def hmult(self, a, b, evk_own):
+        d0, d1, d2 = self.hmult_pre(a, b)
+        k0, k1 = self.keyswitch(d2, evk_own)
+        return self.rescale(self.hmult_post(d0, d1, k0, k1))
 
 
 class _Op:

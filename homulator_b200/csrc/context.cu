@@ -177,7 +177,7 @@ extern "C" void hml_ctx_destroy(hml_ctx *ctx) {
   for (auto &kv : ctx->bconv_cache) { cudaFree(kv.second.step1); cudaFree(kv.second.host.d_mat); cudaFree(kv.second.host.d_img); }
   for (auto &kv : ctx->shard_plans) {
     cudaFree(kv.second.scale1); cudaFree(kv.second.scale2); cudaFree(kv.second.pinv); cudaFree(kv.second.down.d_mat); cudaFree(kv.second.down.d_img);
-    cudaFree(kv.second.d_off2);
+    cudaFree(kv.second.d_off2); cudaFree(kv.second.qlinv_own);
     for (auto *o : kv.second.d_off1) cudaFree(o);
     for (auto &u : kv.second.up) { cudaFree(u.d_mat); cudaFree(u.d_img); }
   }
@@ -708,6 +708,14 @@ static int get_shard_plan(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t worl
   if ((rc = upload(ctx, s1, &sp.scale1))) return rc;
   if ((rc = upload(ctx, s2, &sp.scale2))) return rc;
   if ((rc = upload(ctx, pinv, &sp.pinv))) return rc;
+  if (L >= 2) {
+    std::vector<double2> ql;
+    for (uint32_t k = 0; k < nq; ++k) {
+      const uint32_t i = sp.own_q[k];
+      if (i + 1 < L) ql.push_back(mk_cst(h_invmod(p.mod[L - 1] % p.mod[i], p.mod[i]), p.mod[i]));
+    }
+    if ((rc = upload(ctx, ql, &sp.qlinv_own))) return rc;
+  }
   // ModUp conversions: digit j (all its limbs, read from gather buffer 1) -> owned extended limbs outside the digit
   for (uint32_t j = 0; j < beta; ++j) {
     const uint32_t lo = j * A, aj = p.digit_size(L, j);
@@ -1123,6 +1131,82 @@ extern "C" int hml_rescale(hml_ctx *ctx, uint32_t L, const uint64_t *in, uint64_
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   if ((rc = ensure_ws(ctx, rs_ws_words(ctx->p, L, 1)))) return rc;
   return rescale_run(ctx, L, (const u64 *)in, 0, 1, (u64 *)out, 0, ctx->ws, (cudaStream_t)stream);
+}
+
+// Sharded rescale (reference Rescale, src/Operation.cpp:741-911, on limb-sharded polynomials): the rank that owns limb L-1
+// turns it to coefficient form (begin); after one flag exchange every rank transforms that polynomial under its own
+// remaining moduli — reading it from the owner's buffer, over NVLink when the owner is a peer — and applies sub + mul (end).
+//   x_own   [2][nq][N]   the two polynomials, this rank's Q-limbs at level L (ascending limb index)
+//   r_own   [2][N]       this rank's peer-visible buffer; written only by the owner of limb L-1
+//   r_src   [2][N]       the OWNER's buffer (own allocation or peer mapping)
+//   out_own [2][nq'][N]  nq' = owned limbs below L-1
+extern "C" int hml_rescale_shard_begin(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, const uint64_t *x_own, uint64_t *r_own,
+                                       void *stream) {
+  int rc = shard_check(ctx, L, rank, world);
+  if (rc) return rc;
+  if (L < 2) return fail(ctx, HML_ERR_INVALID, "rescale needs L >= 2");
+  if (!x_own || !r_own) return fail(ctx, HML_ERR_INVALID, "null buffer");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if ((L - 1) % world != rank) return HML_OK;  // not the owner of the dropped limb
+  ShardPlan *sp;
+  if ((rc = get_shard_plan(ctx, L, rank, world, &sp))) return rc;
+  const size_t N = ctx->p.N;
+  const uint32_t nq = sp->own_q.size();
+  LimbMap lm; clear_map(lm);
+  lm.mod[0] = L - 1; lm.pos[0] = nq - 1;  // the dropped limb is the last one this rank owns
+  NttLaunch l{};
+  l.n_batch = 1;
+  l.in = (const u64 *)x_own; l.in_limb_stride = N; l.in_poly_stride = (long long)nq * N;
+  l.out = (u64 *)r_own - (size_t)(nq - 1) * N; l.out_limb_stride = N; l.out_poly_stride = N;  // position nq-1 lands on r_own
+  l.n_limbs = 1; l.n_polys = 2;
+  launch_ntt_inverse(ctx->tabs, ctx->p.logN, lm, l, (cudaStream_t)stream);
+  ctx->exec.intt_limbs += 2; ctx->exec.kernel_launches += ctx->p.logN <= NTT_SMALL_LOG ? 1 : 2;
+  return check_launch(ctx, "rescale shard begin");
+}
+
+extern "C" int hml_rescale_shard_end(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, const uint64_t *x_own, const uint64_t *r_src,
+                                     uint64_t *out_own, void *stream) {
+  int rc = shard_check(ctx, L, rank, world);
+  if (rc) return rc;
+  if (L < 2) return fail(ctx, HML_ERR_INVALID, "rescale needs L >= 2");
+  if (!x_own || !r_src || !out_own) return fail(ctx, HML_ERR_INVALID, "null buffer");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  ShardPlan *sp;
+  if ((rc = get_shard_plan(ctx, L, rank, world, &sp))) return rc;
+  const Params &p = ctx->p;
+  const size_t N = p.N;
+  const uint32_t nq = sp->own_q.size();
+  const uint32_t nk = nq - ((L - 1) % world == rank ? 1 : 0);  // owned limbs that survive
+  if (nk == 0) return HML_OK;
+  if ((rc = ensure_ws(ctx, std::max(shard_ws_words(p, *sp), (size_t)2 * nk * N)))) return rc;
+  const int logN = p.logN, npass = logN <= NTT_SMALL_LOG ? 1 : 2;
+  cudaStream_t s = (cudaStream_t)stream;
+  LimbMap lm; clear_map(lm);
+  for (uint32_t k = 0; k < nk; ++k) { lm.mod[k] = sp->own_q[k]; lm.pos[k] = k; }
+  u64 *rh = ctx->ws;  // [2][nk][N]
+  const bool fuse = npass == 2;
+  {
+    NttLaunch l{};
+    l.n_batch = 1;
+    l.in = (const u64 *)r_src; l.in_limb_stride = 0; l.in_poly_stride = N;
+    l.out = rh; l.out_limb_stride = N; l.out_poly_stride = (long long)nk * N; l.n_limbs = nk; l.n_polys = 2;
+    if (fuse) {
+      NttFuse &f = l.fuse;
+      f.x = (const u64 *)x_own; f.x_c_stride = (long long)nq * N; f.x_b_stride = 0; f.z = nullptr; f.z_mask = 0;
+      f.dst = (u64 *)out_own; f.dst_c_stride = (long long)nk * N; f.dst_b_stride = 0; f.cst = sp->qlinv_own; f.n_c = 2;
+    }
+    launch_ntt_forward(ctx->tabs, logN, lm, l, s);
+    ctx->exec.ntt_limbs += 2ull * nk; ctx->exec.kernel_launches += npass;
+  }
+  if (!fuse) {
+    SubMulArgs a{};
+    a.x = (const u64 *)x_own; a.y = rh; a.z = nullptr; a.out = (u64 *)out_own; a.x_poly_stride = (long long)nq * N;
+    a.y_poly_stride = (long long)nk * N; a.out_poly_stride = (long long)nk * N; a.cst = sp->qlinv_own; a.N = N; a.n_limbs = nk; a.n_polys = 2;
+    launch_sub_mul_add(ctx->mc, lm, a, s);
+    ctx->exec.kernel_launches++;
+  }
+  ctx->exec.ewe_limbs += 4ull * nk;
+  return check_launch(ctx, "rescale shard end");
 }
 
 // ------------------------------------------------------------------------------------------------ top-level ops

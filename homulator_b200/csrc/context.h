@@ -70,6 +70,8 @@ struct ShardPlan {
   std::vector<long long *> d_off1;         // [beta] device arrays [a_j]
   long long *d_off2 = nullptr;             // device array [alpha]
   std::vector<const void *> peers1_sig, peers2_sig;
+  // sharded rescale (hml_rescale_shard_*): q_{L-1}^-1 mod q_l for the owned limbs l < L - 1
+  double2 *qlinv_own = nullptr;
 };
 
 struct DevBConv {  // cached tables of an arbitrary (src, dst) conversion for the primitive entry point

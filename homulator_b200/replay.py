@@ -65,3 +65,27 @@ def replay(ctx, L, trace, x, plaintexts, rot_keys, evk):
         else:
             raise ValueError("unknown op in trace: %r" % (kind,))
     return env
+
+
+def replay_sharded(sh, trace, x_own, plaintexts2, rot_keys_own, evk_own):
+    """The same trace on limb-sharded operands, one rank per GPU (homulator_b200.api.ShardP2P, peer-direct exchanges over
+    NVLink).  x_own: this rank's limbs of the input [2][nq][N]; plaintexts2: idx -> [2][nq][N] (owned limbs, repeated for
+    both components); rot_keys_own / evk_own: this rank's key slices [beta][2][n_own_ext][N].  The trace must end with its
+    only hmult (every op runs at the level `sh` was built for)."""
+    N2 = 2 * sh.ctx.N
+    env = {"x": x_own}
+    for op in trace:
+        kind, dst = op[0], op[1]
+        if kind == "hrotate":
+            env[dst] = sh.hrotate(env[op[2]], rot_keys_own[op[3]], pow(5, op[3], N2))
+        elif kind == "pmult":
+            env[dst] = sh.pmult(env[op[2]], plaintexts2[op[3]])
+        elif kind == "padd":
+            env[dst] = sh.padd(env[op[2]], plaintexts2[op[3]])
+        elif kind == "hadd":
+            env[dst] = sh.hadd(env[op[2]], env[op[3]])
+        elif kind == "hmult":
+            env[dst] = sh.hmult(env[op[2]], env[op[3]], evk_own)
+        else:
+            raise ValueError("unknown op in trace: %r" % (kind,))
+    return env

@@ -151,8 +151,8 @@ int hml_keyswitch_shard_end(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t wo
  * while they compute (the all-gather is fused into the consumer kernel's tile loop, homulator_b200/csrc/bconv_umma.cu).
  *   peers1[r] / peers2[r]   rank r's gather buffer 1 / 2 as a pointer valid on THIS device: the rank's own allocation for
  *                           r == rank, a cudaIpcOpenMemHandle / peer-enabled mapping otherwise (HOST arrays of `world` pointers)
- *   flags                   per rank 2 * world zero-initialised words: [r] = epoch up to which rank r's buffer 1 is ready,
- *                           [world + r] = the same for buffer 2
+ *   flags                   per rank 3 * world zero-initialised words: [r] = epoch up to which rank r's buffer 1 is ready,
+ *                           [world + r] = the same for buffer 2, [2 world + r] = the sharded rescale's exchange
  * Sequence per key switch (epoch = 1, 2, ... per call): shard_begin(own buffer 1) -> shard_signal(slot rank) ->
  * shard_wait(base 0) -> shard_mid_p2p -> shard_signal(slot world + rank) -> shard_wait(base world) -> shard_end_p2p.
  * hml_shard_signal writes `epoch` into flags[slot] of EVERY peer (peer_flags_dev = DEVICE array of `world` pointers);
@@ -168,6 +168,13 @@ int hml_shard_wait(hml_ctx *ctx, const uint64_t *flags, uint32_t base, uint64_t 
 /* signal followed by wait in ONE launch (one rank per GPU only: ranks emulated on a single stream need the separate calls) */
 int hml_shard_sync(hml_ctx *ctx, uint64_t *const *peer_flags_dev, uint32_t slot, const uint64_t *flags, uint32_t base,
                    uint64_t epoch, uint32_t world, void *stream);
+/* Sharded rescale of a limb-sharded ciphertext (reference Rescale, src/Operation.cpp:741-911): x_own [2][nq][N] = the two
+ * polynomials' owned Q-limbs at level L (ascending); the owner of limb L-1 writes its coefficient form to r_own [2][N]
+ * (begin); after one flag exchange (third slot group of the flag block, base 2 * world) every rank reads r_src = the OWNER's
+ * buffer (own or peer mapping) and produces out_own [2][nq'][N], nq' = owned limbs below L-1 (end). */
+int hml_rescale_shard_begin(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, const uint64_t *x_own, uint64_t *r_own, void *stream);
+int hml_rescale_shard_end(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, const uint64_t *x_own, const uint64_t *r_src,
+                          uint64_t *out_own, void *stream);
 int hml_ipc_export(hml_ctx *ctx, const uint64_t *dev_ptr, unsigned char handle[64]);
 int hml_ipc_import(hml_ctx *ctx, const unsigned char handle[64], uint64_t **out);
 int hml_ipc_close(hml_ctx *ctx, uint64_t *ptr);

@@ -119,6 +119,73 @@ def test_sharded_keyswitch_peer_direct_emulated_ranks(N, ML, L, A, world):
     assert np.array_equal(got0, want0) and np.array_equal(got1, want1)
 
 
+def _emulated_shards(ctxs, L, world):
+    N = ctxs[0].N
+    lays = [hml.shard_layout(L, ctxs[0].alpha, r, world) for r in range(world)]
+    g1 = [c.dev_alloc(world * lays[r]["gather1_slots"] * N) for r, c in enumerate(ctxs)]
+    g2 = [c.dev_alloc(world * 2 * lays[r]["gather2_slots"] * N) for r, c in enumerate(ctxs)]
+    fl = [c.dev_alloc(3 * world) for c in ctxs]
+    rb = [c.dev_alloc(2 * N) for c in ctxs]
+    return [hml.ShardP2P(c, L, r, world, g1, g2, fl, rb) for r, c in enumerate(ctxs)], lays
+
+
+@pytest.mark.parametrize("N,ML,L,A,world", [(256, 7, 7, 3, 2), (1024, 6, 5, 2, 3), (8192, 9, 8, 3, 4), (8192, 9, 9, 3, 2)])
+def test_sharded_hrotate_and_hmult_peer_direct_emulated_ranks(N, ML, L, A, world):
+    """Whole ops on limb-sharded ciphertexts (automorphism / tensor product / additions limb-local, key switch and rescale with
+    peer-direct exchanges), ranks emulated phase by phase on one stream, against the oracle's unsharded hrotate and hmult."""
+    o = Oracle(N, 36, ML, A)
+    Oracle.set_threads(0)
+    beta = -(-L // A)
+    a = uniform_limbs(o.moduli[:L], N, 2200, lead=(2,))
+    b = uniform_limbs(o.moduli[:L], N, 2201, lead=(2,))
+    evk = uniform_limbs(o.moduli[:L] + o.moduli[ML:], N, 2202, lead=(beta, 2))
+    g = 25
+    want_rot = o.hrotate(L, a, evk, L, g)
+    want_mul = o.hmult(L, a, b, evk, L)
+    Oracle.set_threads(1)
+    ctxs = [hml.Context(N=N, max_level=ML, alpha=A) for _ in range(world)]
+    shs, lays = _emulated_shards(ctxs, L, world)
+    R = range(world)
+    own = [lays[r]["own_q"] for r in R]
+    a_own = [to_dev(a[:, own[r]]) for r in R]
+    b_own = [to_dev(b[:, own[r]]) for r in R]
+    evk_own = [to_dev(evk[:, :, own[r] + [L + j for j in lays[r]["own_p"]]]) for r in R]
+    # hrotate, twice (epochs)
+    for _ in range(2):
+        sig = [shs[r].hrotate_pre(a_own[r], g) for r in R]
+        outs = [ctxs[r].empty(2, shs[r].nq, N) for r in R]
+        for r in R:
+            shs[r].begin(sig[r][1])
+        for r in R:
+            shs[r].mid(sig[r][1], evk_own[r])
+        for r in R:
+            k0, _ = shs[r].end(o1=outs[r][1])
+            shs[r].hrotate_post(sig[r], k0, outs[r])
+    got = np.zeros((2, L, N), dtype=np.uint64)
+    for r in R:
+        got[:, own[r]] = to_host(outs[r])
+    assert np.array_equal(got, want_rot)
+    # hmult
+    pre = [shs[r].hmult_pre(a_own[r], b_own[r]) for r in R]
+    for r in R:
+        shs[r].begin(pre[r][2])
+    for r in R:
+        shs[r].mid(pre[r][2], evk_own[r])
+    cs = []
+    for r in R:
+        k0, k1 = shs[r].end()
+        cs.append(shs[r].hmult_post(pre[r][0], pre[r][1], k0, k1))
+    for r in R:
+        shs[r].rescale_begin(cs[r])
+    res = [shs[r].rescale_end(cs[r]) for r in R]
+    got = np.zeros((2, L - 1, N), dtype=np.uint64)
+    for r in R:
+        keep = [i for i in own[r] if i < L - 1]
+        if keep:
+            got[:, keep] = to_host(res[r].contiguous())
+    assert np.array_equal(got, want_mul)
+
+
 def test_peer_direct_needs_the_tcgen05_conversion():
     ctx = hml.Context(N=64, max_level=5, alpha=3)  # N < 128: the FP64 tensor-core kernel has no per-source offsets
     g1, g2, fl = ctx.dev_alloc(2 * 1 * 64), ctx.dev_alloc(2 * 2 * 2 * 64), ctx.dev_alloc(4)
@@ -147,3 +214,13 @@ def test_sharded_keyswitch_peer_direct_over_nvlink():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "SHARDED_P2P_OK" in r.stdout
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
+def test_sharded_op_sequence_over_nvlink():
+    n = min(torch.cuda.device_count(), 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", "29539", os.path.join(ROOT, "tests", "mp_sharded_replay.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "SHARDED_REPLAY_OK" in r.stdout
