@@ -407,7 +407,10 @@ class Context:
                 p1.append(g1); p2.append(g2); pf.append(fl); pr.append(rb)
             else:
                 p1.append(self.ipc_import(h1)); p2.append(self.ipc_import(h2)); pf.append(self.ipc_import(hf)); pr.append(self.ipc_import(hr))
-        return ShardP2P(self, L, rank, world, p1, p2, pf, pr)
+        sh = ShardP2P(self, L, rank, world, p1, p2, pf, pr)
+        sh._own_ptrs = [g1, g2, fl, rb]
+        sh._peer_ptrs = [p for lst in (p1, p2, pf, pr) for r, p in enumerate(lst) if r != rank]
+        return sh
 
     def counts(self, op, L):
         c = _Counts()
@@ -468,6 +471,16 @@ class ShardP2P:
         self.own = list(self.lay["own_q"])
         self.nq = len(self.own)
         self.nk = self.nq - (1 if (L - 1) % world == rank else 0)   # owned limbs that survive a rescale
+
+    def close(self):
+        """Unmap the peers' buffers and free this rank's (only for objects made by Context.shard_p2p_setup)."""
+        c = self.ctx
+        c._chk(c.lib.hml_sync(c.h, None))
+        for p in getattr(self, "_peer_ptrs", []):
+            c._chk(c.lib.hml_ipc_close(c.h, p))
+        for p in getattr(self, "_own_ptrs", []):
+            c._chk(c.lib.hml_dev_free(c.h, p))
+        self._peer_ptrs, self._own_ptrs = [], []
 
     # ---- key switch
     def begin(self, d_own):

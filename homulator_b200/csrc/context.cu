@@ -1264,15 +1264,26 @@ static int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, con
   u64 *ul = yb;
   if ((rc = ks_front(ctx, lc, L, nb, {d2, (long long)PL}, evk, evk_q_limbs, yb, ext, acc, AL, s))) return rc;
   const int logN = p.logN;
-  for (int c = 0; c < 2; ++c) {  // u[L-1] = d_c[L-1] + acc_c[L-1] * P^-1
+  if (nb == 1) {  // u[L-1] = d_c[L-1] + acc_c[L-1] * P^-1: one ciphertext -> both components in ONE launch (the poly index is c)
     SubMulArgs a{};
-    a.x = acc + ((size_t)c * AL + (L - 1)) * N; a.x_poly_stride = 2ll * AL * N;
+    a.x = acc + (size_t)(L - 1) * N; a.x_poly_stride = (long long)AL * N;
     a.y = nullptr;
-    a.z = (c ? d1 : d0) + (size_t)(L - 1) * N; a.z_poly_stride = (long long)PL;
-    a.out = ul + (size_t)c * N; a.out_poly_stride = 2ll * N;
-    a.cst = lc->pinv + (L - 1); a.N = N; a.n_limbs = 1; a.n_polys = nb; a.x_packed = a.z_packed = 1;
+    a.z = d0 + (size_t)(L - 1) * N; a.z_poly_stride = (long long)(d1 - d0);
+    a.out = ul; a.out_poly_stride = (long long)N;
+    a.cst = lc->pinv + (L - 1); a.N = N; a.n_limbs = 1; a.n_polys = 2; a.x_packed = a.z_packed = 1;
     launch_sub_mul_add(ctx->mc, lc->last_lm, a, s);
-    ctx->exec.ewe_limbs += 2ull * nb; ctx->exec.kernel_launches++;
+    ctx->exec.ewe_limbs += 4; ctx->exec.kernel_launches++;
+  } else {
+    for (int c = 0; c < 2; ++c) {
+      SubMulArgs a{};
+      a.x = acc + ((size_t)c * AL + (L - 1)) * N; a.x_poly_stride = 2ll * AL * N;
+      a.y = nullptr;
+      a.z = (c ? d1 : d0) + (size_t)(L - 1) * N; a.z_poly_stride = (long long)PL;
+      a.out = ul + (size_t)c * N; a.out_poly_stride = 2ll * N;
+      a.cst = lc->pinv + (L - 1); a.N = N; a.n_limbs = 1; a.n_polys = nb; a.x_packed = a.z_packed = 1;
+      launch_sub_mul_add(ctx->mc, lc->last_lm, a, s);
+      ctx->exec.ewe_limbs += 2ull * nb; ctx->exec.kernel_launches++;
+    }
   }
   {  // INTT_{L-1}(u[L-1]) -> slot E of each accumulator (reference Rescale INTT :766-805)
     NttLaunch l{};

@@ -77,6 +77,9 @@ def main():
         print("sharded keyswitch world=%d: peer-direct %.1f us, NCCL all-gather %.1f us, single GPU %.1f us" % (world, t_p2p, t_nccl, t_one))
         print("SHARDED_P2P_OK" if int(flag) == 1 else "SHARDED_P2P_MISMATCH")
     dist.barrier()
+    torch.cuda.synchronize()
+    sh.close()
+    dist.barrier()
     dist.destroy_process_group()
     return 0 if int(flag) == 1 else 1
 

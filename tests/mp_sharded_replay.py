@@ -75,6 +75,9 @@ def main():
         print("op sequence %s world=%d: limb-sharded peer-direct %.1f us, one GPU %.1f us" % (trace_counts(tr), world, t_sh, t_one))
         print("SHARDED_REPLAY_OK" if int(flag) == 1 else "SHARDED_REPLAY_MISMATCH")
     dist.barrier()
+    torch.cuda.synchronize()
+    sh.close()
+    dist.barrier()
     dist.destroy_process_group()
     return 0 if int(flag) == 1 else 1
 
