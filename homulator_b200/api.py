@@ -399,7 +399,7 @@ class Context:
         through ShardP2P(...)."""
         lay = shard_layout(L, self.alpha, rank, world)
         n1, n2 = world * lay["gather1_slots"] * self.N, world * 2 * lay["gather2_slots"] * self.N
-        g1, g2, fl, rb = self.dev_alloc(n1), self.dev_alloc(n2), self.dev_alloc(3 * world), self.dev_alloc(2 * self.N)
+        g1, g2, fl, rb = self.dev_alloc(n1), self.dev_alloc(n2), self.dev_alloc(3 * world + 8), self.dev_alloc(2 * self.N)
         handles = exchange((self.ipc_export(g1), self.ipc_export(g2), self.ipc_export(fl), self.ipc_export(rb)))
         p1, p2, pf, pr = [], [], [], []
         for r, (h1, h2, hf, hr) in enumerate(handles):
@@ -467,6 +467,10 @@ class ShardP2P:
         self.pr = list(peers_r) if peers_r is not None else None
         self.epoch = 0      # key-switch exchanges
         self.epoch_r = 0    # rescale exchanges
+        # True: the fused-sync compositions (keyswitch / rescale / hrotate / hmult) take their epochs from device-side counters
+        # (hml_shard_sync with epoch 0), so a CUDA graph captured around them can be replayed.  Do not mix with the phase
+        # methods on the same object.
+        self.device_epochs = False
         self.lay = shard_layout(L, ctx.alpha, rank, world)
         self.own = list(self.lay["own_q"])
         self.nq = len(self.own)
@@ -512,12 +516,13 @@ class ShardP2P:
         """One rank per GPU: the whole key switch, signal + wait fused into one launch per exchange."""
         c, st = self.ctx, self.ctx._stream()
         self.epoch += 1
+        ep = 0 if self.device_epochs else self.epoch
         o0, o1 = self._outs(o0, o1)
         c._chk(c.lib.hml_keyswitch_shard_begin(c.h, self.L, self.rank, self.world, _ptr(d_own), self.g1_own, st))
-        c._chk(c.lib.hml_shard_sync(c.h, self.pf_dev.data_ptr(), self.rank, self.flags_own, 0, self.epoch, self.world, st))
+        c._chk(c.lib.hml_shard_sync(c.h, self.pf_dev.data_ptr(), self.rank, self.flags_own, 0, ep, self.world, st))
         if evk_own is not None:
             c._chk(c.lib.hml_keyswitch_shard_mid_p2p(c.h, self.L, self.rank, self.world, _ptr(d_own), self.p1, _ptr(evk_own), self.g2_own, st))
-        c._chk(c.lib.hml_shard_sync(c.h, self.pf_dev.data_ptr(), self.world + self.rank, self.flags_own, self.world, self.epoch, self.world, st))
+        c._chk(c.lib.hml_shard_sync(c.h, self.pf_dev.data_ptr(), self.world + self.rank, self.flags_own, self.world, ep, self.world, st))
         c._chk(c.lib.hml_keyswitch_shard_end_p2p(c.h, self.L, self.rank, self.world, self.p2, _ptr(o0), _ptr(o1), st))
         return o0[:self.nq], o1[:self.nq]
 
@@ -574,8 +579,8 @@ class ShardP2P:
         self.epoch_r += 1
         out = c.empty(2, max(self.nk, 1), c.N)
         c._chk(c.lib.hml_rescale_shard_begin(c.h, self.L, self.rank, self.world, _ptr(x), self.pr[self.rank], st))
-        c._chk(c.lib.hml_shard_sync(c.h, self.pf_dev.data_ptr(), 2 * self.world + self.rank, self.flags_own, 2 * self.world, self.epoch_r,
-                                    self.world, st))
+        c._chk(c.lib.hml_shard_sync(c.h, self.pf_dev.data_ptr(), 2 * self.world + self.rank, self.flags_own, 2 * self.world,
+                                    0 if self.device_epochs else self.epoch_r, self.world, st))
         c._chk(c.lib.hml_rescale_shard_end(c.h, self.L, self.rank, self.world, _ptr(x), self.pr[(self.L - 1) % self.world], _ptr(out), st))
         return out[:, :self.nk]
 

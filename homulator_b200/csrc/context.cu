@@ -934,24 +934,34 @@ __global__ void k_shard_wait(const unsigned long long *flags, int base, unsigned
 
 // signal + wait in one launch (one rank per GPU; ranks emulated on ONE stream must use the two separate calls, because a
 // rank's wait would otherwise sit in front of the signals it is waiting for)
-__global__ void k_shard_sync(unsigned long long *const *peer_flags, int slot, const unsigned long long *flags, int base,
+// epoch == 0: the epoch is this rank's own counter for the exchange group (word 3 * world + base / world of its flag block),
+// read and advanced here — no host-side state, so a captured CUDA graph of a whole op sequence can be replayed.
+__global__ void k_shard_sync(unsigned long long *const *peer_flags, int slot, unsigned long long *flags, int base,
                              unsigned long long epoch, int world) {
+  __shared__ unsigned long long e_sh;
   const int r = threadIdx.x;
-  if (r >= world) return;
-  __threadfence_system();
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flags[r] + slot), "l"(epoch) : "memory");
-  const long long t0 = clock64();
-  unsigned long long v;
-  do {
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + base + r) : "memory");
-    if (v < epoch && clock64() - t0 > (4ll << 30)) __trap();
-  } while (v < epoch);
+  unsigned long long *ctr = flags + 3 * world + base / world;
+  if (r == 0) e_sh = epoch ? epoch : *ctr + 1;
+  __syncthreads();
+  const unsigned long long e = e_sh;
+  if (r < world) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flags[r] + slot), "l"(e) : "memory");
+    const long long t0 = clock64();
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + base + r) : "memory");
+      if (v < e && clock64() - t0 > (4ll << 30)) __trap();
+    } while (v < e);
+  }
+  __syncthreads();
+  if (r == 0 && !epoch) *ctr = e;
 }
-extern "C" int hml_shard_sync(hml_ctx *ctx, uint64_t *const *peer_flags_dev, uint32_t slot, const uint64_t *flags, uint32_t base,
+extern "C" int hml_shard_sync(hml_ctx *ctx, uint64_t *const *peer_flags_dev, uint32_t slot, uint64_t *flags, uint32_t base,
                               uint64_t epoch, uint32_t world, void *stream) {
   if (!ctx || !peer_flags_dev || !flags || world == 0 || world > 64) return HML_ERR_INVALID;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  k_shard_sync<<<1, 64, 0, (cudaStream_t)stream>>>((unsigned long long *const *)peer_flags_dev, (int)slot, (const unsigned long long *)flags,
+  k_shard_sync<<<1, 64, 0, (cudaStream_t)stream>>>((unsigned long long *const *)peer_flags_dev, (int)slot, (unsigned long long *)flags,
                                                    (int)base, epoch, (int)world);
   ctx->exec.kernel_launches++;
   return check_launch(ctx, "shard sync");

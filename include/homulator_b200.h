@@ -165,8 +165,10 @@ int hml_keyswitch_shard_end_p2p(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_
                                 uint64_t *out0_own, uint64_t *out1_own, void *stream);
 int hml_shard_signal(hml_ctx *ctx, uint64_t *const *peer_flags_dev, uint32_t slot, uint64_t epoch, uint32_t world, void *stream);
 int hml_shard_wait(hml_ctx *ctx, const uint64_t *flags, uint32_t base, uint64_t epoch, uint32_t world, void *stream);
-/* signal followed by wait in ONE launch (one rank per GPU only: ranks emulated on a single stream need the separate calls) */
-int hml_shard_sync(hml_ctx *ctx, uint64_t *const *peer_flags_dev, uint32_t slot, const uint64_t *flags, uint32_t base,
+/* signal followed by wait in ONE launch (one rank per GPU only: ranks emulated on a single stream need the separate calls).
+ * epoch == 0: use and advance this rank's device-side counter of the exchange group (word 3 * world + base / world of its
+ * flag block, which then needs 3 * world + 3 words) — no host state, so a captured CUDA graph of a whole op sequence replays. */
+int hml_shard_sync(hml_ctx *ctx, uint64_t *const *peer_flags_dev, uint32_t slot, uint64_t *flags, uint32_t base,
                    uint64_t epoch, uint32_t world, void *stream);
 /* Sharded rescale of a limb-sharded ciphertext (reference Rescale, src/Operation.cpp:741-911): x_own [2][nq][N] = the two
  * polynomials' owned Q-limbs at level L (ascending); the owner of limb L-1 writes its coefficient form to r_own [2][N]
