@@ -486,6 +486,17 @@ class ShardP2P:
             c._chk(c.lib.hml_dev_free(c.h, p))
         self._peer_ptrs, self._own_ptrs = [], []
 
+    def reset_flags(self):
+        """Zero this rank's flag block and epochs (every rank must be idle and must do the same before the next exchange)."""
+        import numpy as np
+        c = self.ctx
+        n = 3 * self.world + 8
+        c._chk(c.lib.hml_sync(c.h, None))
+        z = np.zeros(n, dtype=np.uint64)
+        c._chk(c.lib.hml_h2d(c.h, self.flags_own, z.ctypes.data, n, None))
+        c._chk(c.lib.hml_sync(c.h, None))
+        self.epoch = self.epoch_r = 0
+
     # ---- key switch
     def begin(self, d_own):
         c = self.ctx

@@ -186,6 +186,15 @@ def test_sharded_hrotate_and_hmult_peer_direct_emulated_ranks(N, ML, L, A, world
     assert np.array_equal(got, want_mul)
 
 
+def test_fused_exchange_with_device_side_epochs_on_two_streams():
+    """The one-launch signal + wait (hml_shard_sync) with device-side epoch counters — the form the multi-GPU path and its CUDA
+    graph use — on ONE GPU: two emulated ranks, each on its own stream, so that a rank's spin-wait runs while the other rank's
+    kernels make progress.  Three key switches and one hmult back to back, against the oracle (tests/sp_fused_exchange.py,
+    in a child process: a spin-wait that times out traps and would take this process's CUDA context with it)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "sp_fused_exchange.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "FUSED_EXCHANGE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_peer_direct_needs_the_tcgen05_conversion():
     ctx = hml.Context(N=64, max_level=5, alpha=3)  # N < 128: the FP64 tensor-core kernel has no per-source offsets
     g1, g2, fl = ctx.dev_alloc(2 * 1 * 64), ctx.dev_alloc(2 * 2 * 2 * 64), ctx.dev_alloc(4)
