@@ -164,6 +164,70 @@ def _emit(real_stdout, line):
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
+def limb_sharded(ctx, rank, world, L, evk, dist, torch):
+    """SURVEY.md 8e mode 2 / BASELINE.json configs[4] on all ranks: one ciphertext's key switch and the baby-step/giant-step op
+    sequence with the limbs sharded over the GPUs (limb i on rank i % world).  Device events, max over ranks."""
+    import homulator_b200 as hml
+    from homulator_b200.replay import bsgs_trace, replay, replay_sharded
+    q = list(range(L))
+    d = ctx.uniform(q, 900)
+    x = ctx.uniform(q, 901, lead=(2,))
+    lay = hml.shard_layout(L, ALPHA, rank, world)
+    own = lay["own_q"]
+    own_e = own + [L + j for j in lay["own_p"]]
+    oi, oe = torch.tensor(own, device="cuda"), torch.tensor(own_e, device="cuda")
+    d_own, evk_own, x_own = d[oi].contiguous(), evk[:, :, oe].contiguous(), x[:, oi].contiguous()
+
+    def exchange(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    def timeit(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e3 / reps], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    sh = ctx.shard_p2p_setup(L, rank, world, exchange)
+    dist.barrier()
+    ref0, ref1 = ctx.keyswitch(L, d, evk)
+    o0, o1 = sh.keyswitch(d_own, evk_own)
+    ok = bool(torch.equal(o0, ref0[oi]) and torch.equal(o1, ref1[oi]))
+    res = {"keyswitch_peer_direct_us": timeit(lambda: sh.keyswitch(d_own, evk_own), 20),
+           "keyswitch_nccl_allgather_us": timeit(lambda: ctx.keyswitch_sharded(
+               L, d_own, evk_own, rank, world, lambda buf: dist.all_gather_into_tensor(buf, buf[rank].clone())), 20),
+           "keyswitch_one_gpu_us": timeit(lambda: ctx.keyswitch(L, d, evk), 20)}
+    tr = bsgs_trace(4, 4)
+    pts = {i: ctx.uniform(q, 920 + i) for i in range(16)}
+    pts2 = {i: torch.stack([p[oi], p[oi]]).contiguous() for i, p in pts.items()}
+    keys = {r: evk for r in sorted({op[3] for op in tr if op[0] == "hrotate"})}
+    keys_own = {r: evk_own for r in keys}
+    ref = replay(ctx, L, tr, x, pts, keys, evk)["z"]
+    got = replay_sharded(sh, tr, x_own, pts2, keys_own, evk_own)["z"]
+    keep = torch.tensor([i for i in own if i < L - 1], device="cuda")
+    ok = ok and bool(torch.equal(got.contiguous(), ref[:, keep]))
+    res["sequence_peer_direct_us"] = timeit(lambda: replay_sharded(sh, tr, x_own, pts2, keys_own, evk_own), 5)
+    res["sequence_one_gpu_us"] = timeit(lambda: replay(ctx, L, tr, x, pts, keys, evk), 5)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    res["bit_identical_to_one_gpu"] = bool(int(flag) == 1)
+    dist.barrier()
+    torch.cuda.synchronize()
+    sh.close()
+    dist.barrier()
+    return res
+
+
 def main():
     real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -175,6 +239,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--sharded", action="store_true",
+                    help="with --gpus N > 1: also time ONE ciphertext's key switch and the op sequence limb-sharded over the N GPUs "
+                         "(peer-direct NVLink exchanges vs NCCL all-gathers vs one GPU) -> extra.limb_sharded")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args, real_stdout)
@@ -248,6 +315,8 @@ def main():
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_us = float(e2e_ms.item()) * 1e3 / (K * Be * world)
     e2e_ok = bool(torch.equal(oh.cuda(), out[:Be]))
+
+    sharded = limb_sharded(ctx, rank, world, L, evk, dist, torch) if (args.sharded and world > 1) else None
 
     if rank != 0:
         if world > 1:
@@ -351,6 +420,8 @@ def main():
         seq = lat(lambda: replay(ctx, L, tr, ct_a[0], pts, keys, evk), iters=5)
         extra["bsgs_sequence"] = {"ops": trace_counts(tr), "us": seq}
 
+    if sharded is not None:
+        extra["limb_sharded"] = sharded
     cpu = None
     if not args.no_cpu_baseline:
         v, used = cpu_port_sample(3, 1)
