@@ -15,7 +15,10 @@
 // single reduction mod q_t on the FP64 pipe.  SURVEY.md / BASELINE.json north_star: "tensor cores are used only if an
 // integer-split BConv beats CUDA cores in ncu" — measured numbers in profiles/README.md.
 //
-// Kernel shape (one persistent CTA per SM, 512 threads, no warp specialisation, one __syncthreads per tile):
+// Kernel shape (persistent CTAs, no warp specialisation, one __syncthreads per tile).  Two variants (template NT):
+//   NT=256  conversions with <= 16 sources: TWO CTAs per SM, one TMEM accumulator buffer (256 columns) each; a CTA runs
+//           pack -> MMA -> epilogue strictly in turn and the co-resident CTA fills its barrier and MMA waits
+//   NT=512  more sources (shared memory allows one CTA): two TMEM buffers, the MMA of tile n+1 runs while tile n is drained
 //   tile    128 coefficients (UMMA M = 128: TMEM lane = coefficient) x all targets (UMMA N = NP <= 256 s32 columns: byte
 //           levels 0 and 4 of target t in columns 2t, 2t + 1, levels 1..3 in columns (b + 1) * ND + t) x K = 80 bytes per
 //           16 sources, padded to a multiple of 32
@@ -24,10 +27,11 @@
 //           (i/16)*5 + a holds byte a of sources 16*(i/16) .. +15, so a thread that holds four consecutive sources of one
 //           coefficient emits one 32-bit word per byte position (3 PRMT) and a warp's 32 words are conflict-free
 //   B       the host-built image, same layout with NP rows, copied once per CTA
-//   D       two TMEM buffers of 256 columns: the MMA of tile n+1 runs while tile n's accumulators are drained
-//   loop    pack(n+1) -> sync -> [thread 0: MMA(n+1), commit] -> global loads(n+2) in flight -> wait MMA(n) ->
-//           epilogue(n): tcgen05.ld of 4 targets x 5 levels per trip, shift-add on the integer pipe, one FP64 reduction,
-//           256-byte coalesced stores per warp and target; the target pairs are dealt evenly to the 4 warps of a lane quarter
+//   loads   cp.async (8 B) into a ring of per-thread staging slots, issued STAGES tiles ahead; with BConvArgs::src_off the
+//           sources may live in ANOTHER GPU's memory (limb-sharded key switch: the all-gather is this ring, over NVLink)
+//   epilog  tcgen05.ld of 4 targets x 5 levels per trip (the next trip's load in flight), shift-add on the integer pipe, one
+//           FP64 reduction, predicated-asm store (256 B coalesced per warp and target); the targets are dealt evenly to the
+//           warps of a TMEM lane quarter as contiguous ranges, 3 or 4 per trip
 // The optional fold of hmult's merged ModDown + Rescale (context.cu) is one more (virtual) target: its remainder r is
 // computed first by every warp for its rows and added to every real target's sum before the reduction.
 #include <algorithm>
