@@ -111,7 +111,7 @@ def run_reference(args, real_stdout):
     us, used = cpu_port_sample(steps, threads)
     sim = {}
     run = os.path.join(ROOT, "oracle", "_ref", "count.run")
-    if os.path.exists(run):  # the reference's own instruction generation for this op (the part our planner replaces)
+    if os.path.exists(run) and not args.no_extra:  # the reference's own instruction generation for this op (the part our planner replaces)
         try:
             line = subprocess.run([run, CFG, "hmult", str(MAX_LEVEL), str(LEVEL), str(ALPHA)], capture_output=True, text=True,
                                   timeout=120).stdout.strip().splitlines()[-1]

@@ -94,3 +94,26 @@ def test_cli_usage_and_unknown_op(capfd):
     assert "Error operation requirement, please double confirm!" in out
     assert "Configuration details are as follow:" in out and "elementBitWidth" in out
     assert run(["Homulator.run", "/nonexistent.cfg", "hmult", "45", "35", "15"]) == 2
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py --impl reference (the CPU arm the driver times beside the GPU arm): stdout is ONE JSON line with the contract's
+    keys; under a multi-rank launch only rank 0 works and prints."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--no-extra"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-1000:]
+    lines = [x for x in r.stdout.splitlines() if x.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "us" and d["higher_is_better"] is False and d["value"] > 0
+    for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
