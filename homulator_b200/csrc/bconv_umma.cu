@@ -406,6 +406,11 @@ k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BC
 
   const int n_my = (int)blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int stride = (int)gridDim.x;
+  // the matrix image (a constant table) starts its trip before the programmatic dependency is resolved: asynchronous 16-byte
+  // copies, the OLDEST copy group of every thread, so every later wait_group covers it
+  for (uint32_t e = tid; e < (uint32_t)NP * K / 16; e += NT)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(Bs + (size_t)e * 16)), "l"(img + (size_t)e * 16) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
   pdl_wait();  // the sources are another kernel's output; the outputs may still be read by one
   if (n_my > 0) {
     TileWalk wl, we;  // the loader runs STAGES tiles ahead of the epilogue
@@ -416,8 +421,7 @@ k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BC
       load_tile(wl, d, d < n_my);
       wl.step(stride, tiles_per_batch);
     }
-    // ---- constant set-up, while the first tiles are on their way: matrix image, per-target table, TMEM, barriers
-    for (uint32_t e = tid; e < (uint32_t)NP * K / 16; e += NT) reinterpret_cast<uint4 *>(Bs)[e] = __ldg(reinterpret_cast<const uint4 *>(img) + e);
+    // ---- constant set-up, while the matrix image and the first tiles are on their way: per-target table, TMEM, barriers
     {  // K padding of the A operand (chunks past 5 per slab): written once, never touched by the packer
       const uint32_t used = (uint32_t)N16 * 5 * UMMA_TM * 16, pad = a_bytes - used;
       for (uint32_t e = tid; e < NBUF * pad / 16; e += NT) {
@@ -444,6 +448,7 @@ k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BC
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bars[1])));
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    asm volatile("cp.async.wait_group %0;" ::"n"(STAGES) : "memory");  // the image has landed (the tile groups may still fly)
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
