@@ -235,7 +235,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32, help="hmult per GPU per step")
-    ap.add_argument("--e2e-batch", type=int, default=16, help="hmult per GPU per step on the host-buffer path")
+    ap.add_argument("--e2e-batch", type=int, default=32, help="hmult per GPU per step on the host-buffer path")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
