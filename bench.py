@@ -30,7 +30,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 CFG = os.path.join(ROOT, "config", "config_4.cfg")
 N_RING, MAX_LEVEL, LEVEL, ALPHA = 65536, 45, 35, 15
 METRIC = "hmult_us_N65536_l35_alpha15"
-HMULT_SIM_CYCLES = None  # the reference's own hmult 45 35 15 run (multi-hour) had not finished when this was written
+HMULT_SIM_CYCLES = 221716  # the reference's own `Homulator.run config_4.cfg hmult 45 35 15` (353 host minutes on one core)
 WORKLOAD = "hmult config_4.cfg maxLevel=45 currentLevel=35 alpha=15 (BASELINE.json configs[0]/[3])"
 
 
@@ -408,7 +408,7 @@ def main():
             "hmult_hbm_frac_unfused_bytes": aw_m * W_bytes / (hm * 1e-6) / 1e9 / peak,
             "hrotate_hbm_frac_unfused_bytes": aw_r * W_bytes / (hr * 1e-6) / 1e9 / peak,
             "hmult_batched_hbm_frac_unfused_bytes": aw_m * W_bytes / (us_per_op * 1e-6) / 1e9 / peak,
-            "homulator_simulated_cycles": {"hrotate_45_35_15": 203651, "hrotate_host_minutes_1core": 235.9,
+            "homulator_simulated_cycles": {"hrotate_45_35_15": 203651, "hrotate_host_minutes_1core": 235.9, "hmult_host_minutes_1core": 353.4,
                                            "hmult_45_35_15": HMULT_SIM_CYCLES, "note": "unmodified reference CLI, g++ -O2, build container; "
                                            "cycles are machine-independent (BASELINE.md section 2); 1 cycle = 1 ns at an assumed 1 GHz"},
         })
