@@ -234,14 +234,16 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=32, help="hmult per GPU per step")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="hmult per GPU per step; default 256 / n_gpus (BASELINE.json configs[3]: 256 ciphertexts per step over the job)")
     ap.add_argument("--e2e-batch", type=int, default=32, help="hmult per GPU per step on the host-buffer path")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
-    ap.add_argument("--sharded", action="store_true",
-                    help="with --gpus N > 1: also time ONE ciphertext's key switch and the op sequence limb-sharded over the N GPUs "
-                         "(peer-direct NVLink exchanges vs NCCL all-gathers vs one GPU) -> extra.limb_sharded")
+    ap.add_argument("--no-sharded", action="store_true",
+                    help="with --gpus N > 1 the bench also times ONE ciphertext's key switch and the op sequence limb-sharded over the "
+                         "N GPUs (peer-direct NVLink exchanges vs NCCL all-gathers vs one GPU) -> extra.limb_sharded; this skips it")
+    ap.add_argument("--sharded", action="store_true", help="(default for N > 1; kept for compatibility)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args, real_stdout)
@@ -260,7 +262,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     W = max(3, args.warmup)
-    K, B, L = max(1, args.steps), args.batch, LEVEL
+    K, L = max(1, args.steps), LEVEL
+    B = args.batch if args.batch > 0 else max(1, 256 // world)
 
     ctx = hml.Context(CFG, MAX_LEVEL, ALPHA, device=local)
     q = list(range(L))
@@ -316,7 +319,23 @@ def main():
     e2e_us = float(e2e_ms.item()) * 1e3 / (K * Be * world)
     e2e_ok = bool(torch.equal(oh.cuda(), out[:Be]))
 
-    sharded = limb_sharded(ctx, rank, world, L, evk, dist, torch) if (args.sharded and world > 1) else None
+    # ---------------- hrotate, batched (same step shape), all ranks
+    out_r = ctx.empty(B, 2, L, N_RING)
+    for _ in range(2):
+        ctx.hrotate_batch(L, ct_a, evk, 5, out=out_r)
+    barrier()
+    e0.record()
+    for _ in range(max(2, K // 2)):
+        ctx.hrotate_batch(L, ct_a, evk, 5, out=out_r)
+    e1.record()
+    barrier()
+    hr_ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(hr_ms, op=dist.ReduceOp.MAX)
+    hrot_batched_us = float(hr_ms.item()) * 1e3 / (max(2, K // 2) * B * world)
+    del out_r
+
+    sharded = limb_sharded(ctx, rank, world, L, evk, dist, torch) if (world > 1 and not args.no_sharded) else None
 
     if rank != 0:
         if world > 1:
@@ -377,7 +396,7 @@ def main():
     except Exception:
         pass
 
-    extra = {"ntt_limbs_per_s": ntt_limbs_per_s, "ntt_us_per_limb": ntt_ms * 1e3 / (n_limbs * n_b),
+    extra = {"hrotate_batched_us": hrot_batched_us, "hmult_batched_us": us_per_op, "ntt_limbs_per_s": ntt_limbs_per_s, "ntt_us_per_limb": ntt_ms * 1e3 / (n_limbs * n_b),
              "ntt_us_per_limb_single_ciphertext_launch": ntt1_us_per_limb, "e2e_matches_device_path": e2e_ok,
              "bconv_tcgen05": {"kernel": "k_bconv_umma (tcgen05.mma kind::i8, 64 polynomials x 15 -> 35 limbs per launch)",
                                "us_per_launch": bconv_ms * 1e3, "algorithmic_bytes_per_launch": bconv_bytes,
@@ -405,9 +424,12 @@ def main():
         aw_m, aw_r = hml.algorithmic_words("hmult", L, ALPHA), hml.algorithmic_words("hrotate", L, ALPHA)
         extra.update({
             "hmult_single_us_l2_flushed": hm, "hrotate_single_us_l2_flushed": hr,
-            "hmult_hbm_frac_unfused_bytes": aw_m * W_bytes / (hm * 1e-6) / 1e9 / peak,
-            "hrotate_hbm_frac_unfused_bytes": aw_r * W_bytes / (hr * 1e-6) / 1e9 / peak,
-            "hmult_batched_hbm_frac_unfused_bytes": aw_m * W_bytes / (us_per_op * 1e-6) / 1e9 / peak,
+            "hmult_single_unfused_bytes_equivalent_over_hbm_peak": aw_m * W_bytes / (hm * 1e-6) / 1e9 / peak,
+            "hrotate_single_unfused_bytes_equivalent_over_hbm_peak": aw_r * W_bytes / (hr * 1e-6) / 1e9 / peak,
+            # NOT a roofline fraction: SURVEY 8d's UNFUSED byte count divided by the time of the fused / merged schedule (which
+            # moves ~0.9 GB per hmult, not 1.32 GB) — can exceed 1; quoted because 8d asks for it
+            "hmult_batched_unfused_bytes_equivalent_over_hbm_peak": aw_m * W_bytes / (us_per_op * 1e-6) / 1e9 / peak,
+            "hrotate_batched_unfused_bytes_equivalent_over_hbm_peak": aw_r * W_bytes / (hrot_batched_us * 1e-6) / 1e9 / peak,
             "homulator_simulated_cycles": {"hrotate_45_35_15": 203651, "hrotate_host_minutes_1core": 235.9, "hmult_host_minutes_1core": 353.4,
                                            "hmult_45_35_15": HMULT_SIM_CYCLES, "note": "unmodified reference CLI, g++ -O2, build container; "
                                            "cycles are machine-independent (BASELINE.md section 2); 1 cycle = 1 ns at an assumed 1 GHz"},
@@ -434,7 +456,8 @@ def main():
         "metric": METRIC, "value": us_per_op, "unit": "us", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64 residues (36-bit), arithmetic on the FP64 pipe", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu_per_step": B, "l2": "inputs larger than L2 (no flush)",
+        "config": {"workload": WORKLOAD, "batch_per_gpu_per_step": B, "ciphertexts_per_step": B * world,
+                   "l2": "inputs larger than L2 (no flush)",
                    "throughput_hmult_per_s": n_ops / (ms_total * 1e-3)},
         "e2e": {"value": e2e_us, "unit": "us", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                 "batch_per_gpu_per_step": Be},

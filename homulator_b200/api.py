@@ -41,6 +41,10 @@ class _ExecCounts(C.Structure):
                 ("bconv_limb_macs", C.c_uint64), ("automorph_limbs", C.c_uint64), ("kernel_launches", C.c_uint64)]
 
 
+class _Profile(C.Structure):
+    _fields_ = [("us", C.c_double * 5), ("launches", C.c_uint64 * 5), ("total_us", C.c_double)]
+
+
 def lib_path():
     return os.path.join(HERE, "libhomulator_b200.so")
 
@@ -52,7 +56,7 @@ EXPORTS = [
     "hml_d2h", "hml_sync", "hml_ntt", "hml_intt", "hml_ntt_batch", "hml_intt_batch", "hml_ewe", "hml_automorph", "hml_bconv", "hml_bconv_batch", "hml_keyswitch", "hml_rescale",
     "hml_hmult", "hml_hrotate", "hml_hadd", "hml_pmult", "hml_padd", "hml_hmult_batch", "hml_hrotate_batch",
     "hml_hmult_host", "hml_hrotate_host", "hml_host_alloc_pinned", "hml_host_free_pinned", "hml_trace_counts",
-    "hml_get_counts", "hml_buffer_plan", "hml_exec_counts_get", "hml_exec_counts_reset", "hml_cli_main",
+    "hml_get_counts", "hml_buffer_plan", "hml_exec_counts_get", "hml_exec_counts_reset", "hml_cli_main", "hml_profile_begin", "hml_profile_end",
     "hml_shard_layout", "hml_keyswitch_shard_begin", "hml_keyswitch_shard_mid", "hml_keyswitch_shard_end",
     "hml_keyswitch_shard_mid_p2p", "hml_keyswitch_shard_end_p2p", "hml_shard_signal", "hml_shard_wait", "hml_shard_sync",
     "hml_ipc_export", "hml_ipc_import", "hml_ipc_close", "hml_rescale_shard_begin", "hml_rescale_shard_end",
@@ -65,9 +69,8 @@ def load_library():
     if _LIB is not None:
         return _LIB
     path = lib_path()
-    if not os.path.exists(path):
-        from .build import build
-        build()
+    from .build import build
+    build()  # mtime-guarded: rebuilds only when a source is newer than the library (no-op on a box without nvcc)
     L = C.CDLL(path)
     vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
     L.hml_ctx_create.argtypes = [C.c_char_p, u32, u32, i32, C.POINTER(vp)]
@@ -126,6 +129,9 @@ def load_library():
     L.hml_dev_alloc.argtypes = [vp, u64, C.POINTER(vp)]
     L.hml_dev_free.argtypes = [vp, vp]
     L.hml_h2d.argtypes = [vp, vp, vp, u64, vp]
+    L.hml_d2h.argtypes = [vp, vp, vp, u64, vp]
+    L.hml_profile_begin.argtypes = [vp, vp]
+    L.hml_profile_end.argtypes = [vp, C.POINTER(_Profile)]
     L.hml_sync.argtypes = [vp, vp]
     _LIB = L
     return L
@@ -424,6 +430,18 @@ class Context:
         buf = C.create_string_buffer(8192)
         self._chk(self.lib.hml_buffer_plan(self.h, op.encode(), L, buf, len(buf)))
         return buf.value.decode()
+
+    def profile(self, fn):
+        """Run fn() in measuring mode: device microseconds per kernel class (the reference's per-unit statistics)."""
+        self._chk(self.lib.hml_profile_begin(self.h, self._stream()))
+        try:
+            fn()
+        finally:
+            pr = _Profile()
+            self._chk(self.lib.hml_profile_end(self.h, C.byref(pr)))
+        names = ("NTT", "INTT", "BCONV", "EWE", "AUTO")
+        return {"us": {n: pr.us[i] for i, n in enumerate(names)}, "launches": {n: pr.launches[i] for i, n in enumerate(names)},
+                "total_us": pr.total_us}
 
     def exec_counts(self, reset=False):
         e = _ExecCounts()

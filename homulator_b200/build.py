@@ -61,7 +61,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("build failed")
         if verbose:
             sys.stderr.write(out)
-    _run([nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"])
+    _run([nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"])
     _run([nvcc] + ARCH + common + [os.path.join(CSRC, "main.cpp"), "-o", CLI, "-L" + HERE, "-lhomulator_b200",
                                    "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"])
     return LIB

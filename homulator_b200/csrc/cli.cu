@@ -4,7 +4,10 @@
 // stream and clocking a pipeline model (reference src/Operation.cpp:1025-1112) it executes the operation on
 // seeded synthetic data on the GPU and reports measured time, the reference-shaped instruction counts and
 // the HBM roofline fraction.
+#include <dlfcn.h>
+
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -45,10 +48,39 @@ static double op_words(const std::string &op, double L, double A) {
   return 2 * 3 * L;
 }
 
+// Measured HBM copy bandwidth of this pool's B200s: MEASURED_PEAKS.json (driver-written, at the repository root = one level
+// above the directory this library lives in; HML_PEAKS_JSON overrides the path), else the profiling guide's fallback.
+static double measured_hbm_gbs(std::string &source) {
+  std::vector<std::string> cand;
+  if (const char *e = getenv("HML_PEAKS_JSON")) cand.push_back(e);
+  Dl_info info;
+  if (dladdr((const void *)&measured_hbm_gbs, &info) && info.dli_fname) {
+    std::string lib = info.dli_fname;
+    const size_t sl = lib.rfind('/');
+    if (sl != std::string::npos) cand.push_back(lib.substr(0, sl) + "/../MEASURED_PEAKS.json");
+  }
+  cand.push_back("MEASURED_PEAKS.json");
+  for (const std::string &path : cand) {
+    FILE *f = fopen(path.c_str(), "r");
+    if (!f) continue;
+    std::string text(1 << 14, '\0');
+    text.resize(fread(&text[0], 1, text.size(), f));
+    fclose(f);
+    const size_t k = text.find("\"hbm_gbs\"");
+    if (k == std::string::npos) continue;
+    const size_t c = text.find(':', k);
+    if (c == std::string::npos) continue;
+    const double v = atof(text.c_str() + c + 1);
+    if (v > 100.0) { source = "measured (MEASURED_PEAKS.json)"; return v; }
+  }
+  source = "fallback (B200_PROFILING.md)";
+  return 6650.0;
+}
+
 static int fill(hml_ctx *ctx, u64 *dev, const std::vector<u64> &limb_mod, u64 seed) {
   u64 *dq = nullptr;
-  cudaMalloc(&dq, limb_mod.size() * 8);
-  cudaMemcpy(dq, limb_mod.data(), limb_mod.size() * 8, cudaMemcpyHostToDevice);
+  if (!dev || cudaMalloc(&dq, limb_mod.size() * 8) != cudaSuccess) return 1;
+  if (cudaMemcpy(dq, limb_mod.data(), limb_mod.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(dq); return 1; }
   const size_t N = ctx->p.N;
   k_fill_uniform<<<dim3((unsigned)((N + 255) / 256), (unsigned)limb_mod.size()), 256>>>(dev, N, (int)limb_mod.size(), dq, seed);
   cudaError_t e = cudaDeviceSynchronize();
@@ -88,6 +120,12 @@ extern "C" int hml_cli_main(int argc, char **argv) {
     printf("Error operation requirement, please double confirm!\n");
     return 0;
   }
+  // the reference indexes its level tables without any check (and segfaults for hmult at L = 1); refuse instead
+  if (maxl == 0 || alpha == 0 || L < (op == "hmult" ? 2u : 1u) || L > maxl) {
+    fprintf(stderr, "homulator_b200: currentLevel %u out of range: %s needs %d <= currentLevel <= maxExecutionLevel = %u\n", L, op.c_str(),
+            op == "hmult" ? 2 : 1, maxl);
+    return 4;
+  }
   hml_ctx *ctx = nullptr;
   int rc = hml_ctx_create(path.c_str(), maxl, alpha, device, &ctx);
   if (rc) {
@@ -115,18 +153,18 @@ extern "C" int hml_cli_main(int argc, char **argv) {
   uint64_t *a = nullptr, *b = nullptr, *key = nullptr, *out = nullptr;
   u64 *flushbuf = nullptr;
   const u64 seed = 0x486F6D756C61746Full;
-  cudaMalloc(&a, ct_mod.size() * N * 8);
-  cudaMalloc(&b, ct_mod.size() * N * 8);
-  cudaMalloc(&out, ct_mod.size() * N * 8);
-  int bad = fill(ctx, (u64 *)a, ct_mod, seed + 1);
+  int bad = cudaMalloc(&a, ct_mod.size() * N * 8) != cudaSuccess;
+  bad |= cudaMalloc(&b, ct_mod.size() * N * 8) != cudaSuccess;
+  bad |= cudaMalloc(&out, ct_mod.size() * N * 8) != cudaSuccess;
+  bad |= fill(ctx, (u64 *)a, ct_mod, seed + 1);
   if (op == "pmult" || op == "padd") bad |= fill(ctx, (u64 *)b, pt_mod, seed + 2);
   else bad |= fill(ctx, (u64 *)b, ct_mod, seed + 2);
   if (op == "hmult" || op == "hrotate") {
-    cudaMalloc(&key, key_mod.size() * N * 8);
+    bad |= cudaMalloc(&key, key_mod.size() * N * 8) != cudaSuccess;
     bad |= fill(ctx, (u64 *)key, key_mod, seed + 3);
   }
   const size_t flush_words = (size_t)256 << 17;  // 256 MiB > L2
-  if (flush) cudaMalloc(&flushbuf, flush_words * 8);
+  if (flush) bad |= cudaMalloc(&flushbuf, flush_words * 8) != cudaSuccess;
   if (bad || cudaGetLastError() != cudaSuccess) {
     fprintf(stderr, "homulator_b200: device allocation / fill failed\n");
     return 5;
@@ -181,7 +219,15 @@ extern "C" int hml_cli_main(int argc, char **argv) {
   const double med = us.empty() ? 0 : us[us.size() / 2], mn = us.empty() ? 0 : us.front();
   const double words = op_words(op, L, alpha), bytes = words * 8.0 * N;
   const double gbs = med > 0 ? bytes / (med * 1e-6) / 1e9 : 0;
-  const double peak = 6546.2;  // measured copy bandwidth of this pool's B200s (MEASURED_PEAKS.json)
+  std::string peak_src;
+  const double peak = measured_hbm_gbs(peak_src);
+  // one more run in measuring mode: device time per kernel class, the executed counterpart of the reference's per-unit
+  // statistics dump (Statistic keys NTT_(c) / BCONV_(c) / EWE_(c) / AUTO_(c) / HBM_(c), reference include/Staistics.h:6-40)
+  hml_profile prof{};
+  if (hml_profile_begin(ctx, nullptr) == HML_OK) {
+    run();
+    if (hml_profile_end(ctx, &prof) != HML_OK) memset(&prof, 0, sizeof(prof));
+  }
   time_t t1 = time(nullptr);
   printf("\n\nCompleted!\n");
   printf("%s executed\t%.2f us (median of %d, min %.2f us, L2 %s between runs)\n\n", OP.c_str(), med, iters, mn,
@@ -201,18 +247,37 @@ extern "C" int hml_cli_main(int argc, char **argv) {
   printf("NTT_limbs :\t%llu\nINTT_limbs :\t%llu\nEWE_limbs :\t%llu\nBCONV_limb_MACs :\t%llu\nAUTO_limbs :\t%llu\nkernel_launches :\t%llu\n",
          (unsigned long long)ex.ntt_limbs, (unsigned long long)ex.intt_limbs, (unsigned long long)ex.ewe_limbs,
          (unsigned long long)ex.bconv_limb_macs, (unsigned long long)ex.automorph_limbs, (unsigned long long)ex.kernel_launches);
-  printf("Algorithmic traffic :\t%.0f W = %.4e B -> %.1f GB/s = %.1f%% of measured HBM peak (%.1f GB/s)\n", words, bytes, gbs,
-         100.0 * gbs / peak, peak);
+  printf("Algorithmic traffic :\t%.0f W = %.4e B -> %.1f GB/s = %.1f%% of the HBM peak (%.1f GB/s, %s)\n", words, bytes, gbs,
+         100.0 * gbs / peak, peak, peak_src.c_str());
+  {
+    // per-class algorithmic bytes of the EXECUTED schedule: transforms and automorphisms 2 W per limb, conversions
+    // (sources + targets) are folded into BCONV's limb-MAC count, element-wise passes ~3 W per output limb
+    const double Wb = 8.0 * N;
+    const double cls_bytes[HML_CLS_COUNT] = {2.0 * Wb * ex.ntt_limbs, 2.0 * Wb * ex.intt_limbs, 0.0, 3.0 * Wb * ex.ewe_limbs, 2.0 * Wb * ex.automorph_limbs};
+    const char *names[HML_CLS_COUNT] = {"NTT", "INTT", "BCONV", "EWE", "AUTO"};
+    printf("=====================================\n");
+    printf("Per-unit statistics (cluster 0 = this GPU; measuring mode, kernels serialised):\n");
+    for (int c = 0; c < HML_CLS_COUNT; ++c) {
+      printf("%s_(0) :\tbusy %.2f us\t%llu launches", names[c], prof.us[c], (unsigned long long)prof.launches[c]);
+      if (cls_bytes[c] > 0 && prof.us[c] > 0) printf("\t%.1f GB/s", cls_bytes[c] / (prof.us[c] * 1e-6) / 1e9);
+      if (c == HML_CLS_BCONV && prof.us[c] > 0) printf("\t%.3e limb-MACs/s", (double)ex.bconv_limb_macs / (prof.us[c] * 1e-6));
+      printf("\n");
+    }
+    printf("HBM_(0) :\t%.1f GB/s algorithmic over %.2f us serialised (%.1f%% of peak)\n", prof.total_us > 0 ? bytes / (prof.total_us * 1e-6) / 1e9 : 0.0,
+           prof.total_us, prof.total_us > 0 ? 100.0 * bytes / (prof.total_us * 1e-6) / 1e9 / peak : 0.0);
+  }
   printf("{\"op\": \"%s\", \"N\": %u, \"maxLevel\": %u, \"L\": %u, \"alpha\": %u, \"us_median\": %.3f, \"us_min\": %.3f, \"iters\": %d, "
          "\"l2_flushed\": %s, \"algorithmic_bytes\": %.0f, \"achieved_gbs\": %.2f, \"hbm_frac_of_measured\": %.4f, "
          "\"trace\": {\"NTT\": %llu, \"INTT\": %llu, \"MULT\": %llu, \"BCONV_STEP2\": %llu, \"AUTO\": %llu, \"total\": %llu, \"driverTotal\": %llu}, "
          "\"executed\": {\"ntt_limbs\": %llu, \"intt_limbs\": %llu, \"ewe_limbs\": %llu, \"bconv_limb_macs\": %llu, \"auto_limbs\": %llu, "
-         "\"kernel_launches\": %llu}, \"gpu\": \"%s\"}\n",
+         "\"kernel_launches\": %llu}, \"class_us\": {\"NTT\": %.2f, \"INTT\": %.2f, \"BCONV\": %.2f, \"EWE\": %.2f, \"AUTO\": %.2f}, \"hbm_peak_gbs\": %.1f, "
+         "\"hbm_peak_source\": \"%s\", \"cluster\": %ld, \"gpu\": \"%s\"}\n",
          op.c_str(), p.N, maxl, L, alpha, med, mn, iters, flush ? "true" : "false", bytes, gbs, gbs / peak,
          (unsigned long long)cnt.ntt, (unsigned long long)cnt.intt, (unsigned long long)cnt.mult, (unsigned long long)cnt.bconv_step2,
          (unsigned long long)cnt.automorph, (unsigned long long)cnt.total, (unsigned long long)cnt.driver_total,
          (unsigned long long)ex.ntt_limbs, (unsigned long long)ex.intt_limbs, (unsigned long long)ex.ewe_limbs,
-         (unsigned long long)ex.bconv_limb_macs, (unsigned long long)ex.automorph_limbs, (unsigned long long)ex.kernel_launches, prop.name);
+         (unsigned long long)ex.bconv_limb_macs, (unsigned long long)ex.automorph_limbs, (unsigned long long)ex.kernel_launches,
+         prof.us[0], prof.us[1], prof.us[2], prof.us[3], prof.us[4], peak, peak_src.c_str(), cluster, prop.name);
   cudaFree(a); cudaFree(b); cudaFree(out); cudaFree(key); cudaFree(flushbuf);
   hml_ctx_destroy(ctx);
   return 0;

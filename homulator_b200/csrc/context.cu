@@ -30,6 +30,60 @@ static int fail(hml_ctx *ctx, int code, const std::string &msg) {
   return code;
 }
 
+namespace hml {
+void ws_enter(hml_ctx *ctx, cudaStream_t s) {
+  if (ctx->have_last && ctx->last_stream != s) {
+    // everything queued so far on the previous stream (a superset of the ops that used the workspace) precedes this op
+    if (!ctx->ev_ws) cudaEventCreateWithFlags(&ctx->ev_ws, cudaEventDisableTiming);
+    if (ctx->ev_ws && cudaEventRecord(ctx->ev_ws, ctx->last_stream) == cudaSuccess) cudaStreamWaitEvent(s, ctx->ev_ws, 0);
+    else cudaGetLastError();  // the previous stream no longer exists: nothing of it can still be running
+  }
+  ctx->last_stream = s;
+  ctx->have_last = true;
+}
+void prof_mark(hml_ctx *ctx, int cls, cudaStream_t s) {
+  if (!ctx->prof.on) return;
+  cudaEvent_t e = nullptr;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, s);
+  ctx->prof.marks.emplace_back(cls, e);
+}
+}  // namespace hml
+
+extern "C" int hml_profile_begin(hml_ctx *ctx, void *stream) {
+  if (!ctx) return HML_ERR_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  for (auto &m : ctx->prof.marks) cudaEventDestroy(m.second);
+  ctx->prof.marks.clear();
+  if (!ctx->prof.start) CU_TRY(ctx, cudaEventCreate(&ctx->prof.start));
+  CU_TRY(ctx, cudaEventRecord(ctx->prof.start, (cudaStream_t)stream));
+  ctx->prof.on = true;
+  return HML_OK;
+}
+extern "C" int hml_profile_end(hml_ctx *ctx, hml_profile *out) {
+  if (!ctx || !out) return HML_ERR_INVALID;
+  if (!ctx->prof.on) return fail(ctx, HML_ERR_INVALID, "hml_profile_end without hml_profile_begin");
+  ctx->prof.on = false;
+  memset(out, 0, sizeof(*out));
+  cudaEvent_t prev = ctx->prof.start;
+  cudaError_t e = cudaSuccess;
+  for (auto &m : ctx->prof.marks) {
+    if (e == cudaSuccess) e = cudaEventSynchronize(m.second);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, prev, m.second);
+    if (e == cudaSuccess && m.first >= 0 && m.first < HML_CLS_COUNT) {
+      out->us[m.first] += ms * 1e3;
+      out->launches[m.first]++;
+      out->total_us += ms * 1e3;
+    }
+    prev = m.second;
+  }
+  for (auto &m : ctx->prof.marks) cudaEventDestroy(m.second);
+  ctx->prof.marks.clear();
+  if (e != cudaSuccess) return fail(ctx, HML_ERR_CUDA, std::string("profile: ") + cudaGetErrorString(e));
+  return HML_OK;
+}
+
 static double2 mk_cst(u64 c, u64 q) { return make_double2((double)c, (double)c / (double)q); }
 
 template <class T>
@@ -79,6 +133,7 @@ static int prepare_bconv(hml_ctx *ctx, const BConvTable &bt, const std::vector<u
 static void run_bconv(hml_ctx *ctx, const hml::HostBConv &hb, const LimbMap &src_lm, BConvArgs a, cudaStream_t s) {
   a.n_src = hb.n_src; a.n_dst = hb.n_dst;
   launch_bconv(ctx->mc, src_lm, hb.dst_lm, a, hb.d_mat, s, &hb.im);
+  prof_mark(ctx, HML_CLS_BCONV, s);
   ctx->exec.kernel_launches++;
   ctx->exec.bconv_limb_macs += (uint64_t)hb.n_src * hb.n_dst * a.n_batches;
 }
@@ -188,6 +243,9 @@ extern "C" void hml_ctx_destroy(hml_ctx *ctx) {
   if (ctx->s_lane) cudaStreamDestroy(ctx->s_lane);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->ev_ws) cudaEventDestroy(ctx->ev_ws);
+  if (ctx->prof.start) cudaEventDestroy(ctx->prof.start);
+  for (auto &m : ctx->prof.marks) cudaEventDestroy(m.second);
   delete ctx;
 }
 
@@ -388,6 +446,7 @@ static int ntt_api(hml_ctx *ctx, bool inverse, const uint64_t *in, uint64_t *out
     l.in_limb_stride = l.out_limb_stride = N; l.n_limbs = n; l.n_polys = 1; l.post_scale = nullptr;
     if (inverse) launch_ntt_inverse(ctx->tabs, ctx->p.logN, lm, l, (cudaStream_t)stream);
     else launch_ntt_forward(ctx->tabs, ctx->p.logN, lm, l, (cudaStream_t)stream);
+    prof_mark(ctx, inverse ? HML_CLS_INTT : HML_CLS_NTT, (cudaStream_t)stream);
     ctx->exec.kernel_launches += ctx->p.logN <= NTT_SMALL_LOG ? 1 : 2;
   }
   (inverse ? ctx->exec.intt_limbs : ctx->exec.ntt_limbs) += n_limbs;
@@ -420,6 +479,7 @@ static int ntt_batch_api(hml_ctx *ctx, bool inverse, const uint64_t *in, uint64_
     l.n_batch = std::min(per, n_batch - b0); l.in_batch_stride = l.out_batch_stride = (long long)n_limbs * N;
     if (inverse) launch_ntt_inverse(ctx->tabs, ctx->p.logN, lm, l, (cudaStream_t)stream);
     else launch_ntt_forward(ctx->tabs, ctx->p.logN, lm, l, (cudaStream_t)stream);
+    prof_mark(ctx, inverse ? HML_CLS_INTT : HML_CLS_NTT, (cudaStream_t)stream);
     ctx->exec.kernel_launches += ctx->p.logN <= NTT_SMALL_LOG ? 1 : 2;
   }
   (inverse ? ctx->exec.intt_limbs : ctx->exec.ntt_limbs) += (uint64_t)n_limbs * n_batch;
@@ -446,6 +506,7 @@ extern "C" int hml_ewe(hml_ctx *ctx, const uint64_t *x1, const uint64_t *x2, con
     id_map(lm, mod_idx + off, n);
     auto sh = [&](const uint64_t *p) { return p ? (const u64 *)p + off * N : nullptr; };
     launch_ewe(ctx->mc, lm, (int)N, (int)n, sh(x1), sh(x2), sh(x3), sh(x4), subtract, (u64 *)out + off * N, (cudaStream_t)stream);
+    prof_mark(ctx, HML_CLS_EWE, (cudaStream_t)stream);
     ctx->exec.kernel_launches++;
   }
   ctx->exec.ewe_limbs += n_limbs;
@@ -459,6 +520,7 @@ extern "C" int hml_automorph(hml_ctx *ctx, const uint64_t *in, uint64_t *out, ui
   for (uint32_t off = 0; off < n_limbs; off += 32768) {
     const uint32_t n = std::min<uint32_t>(32768, n_limbs - off);
     launch_automorph(ctx->p.logN, n, (const u64 *)in + (size_t)off * ctx->p.N, (u64 *)out + (size_t)off * ctx->p.N, g, (cudaStream_t)stream);
+    prof_mark(ctx, HML_CLS_AUTO, (cudaStream_t)stream);
     ctx->exec.kernel_launches++;
   }
   ctx->exec.automorph_limbs += n_limbs;
@@ -535,6 +597,7 @@ static int ks_front(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, Batc
     l.in = d.ptr; l.out = yb; l.in_limb_stride = l.out_limb_stride = N; l.n_limbs = L; l.n_polys = 1; l.post_scale = lc->modup_scale;
     l.n_batch = nb; l.in_batch_stride = d.stride; l.out_batch_stride = (long long)L * N;
     launch_ntt_inverse(ctx->tabs, logN, lc->q_lm, l, s);
+    prof_mark(ctx, HML_CLS_INTT, s);
     ctx->exec.intt_limbs += (uint64_t)nb * L; ctx->exec.kernel_launches += npass;
   }
   // K3 (reference :137-188): convert every digit to the limbs of the extended basis it does not own
@@ -555,6 +618,7 @@ static int ks_front(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, Batc
     l.n_batch = nb; l.in_batch_stride = l.out_batch_stride = (long long)beta * E * N;
     l.in_f64 = l.out_f64 = npass == 2;  // doubles in from the conversion, raw lazy doubles out to the inner product
     launch_ntt_forward(ctx->tabs, logN, lc->ext_lm, l, s);
+    prof_mark(ctx, HML_CLS_NTT, s);
     ctx->exec.ntt_limbs += (uint64_t)nb * ((uint64_t)beta * E - L); ctx->exec.kernel_launches += npass;
   }
   // K5 (reference :294-414): inner product with the key (key words loaded once per batch)
@@ -567,6 +631,7 @@ static int ks_front(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, Batc
     a.acc_comp_stride = (long long)AL * N; a.ext_f64 = npass == 2;
     a.acc_pack_limbs = npass == 2 ? (int)L : 0;  // Q-limb accumulators only feed element-wise epilogues: packed (5 B / coefficient)
     launch_inner_product(ctx->mc, ip, a, s);
+    prof_mark(ctx, HML_CLS_EWE, s);
     ctx->exec.ewe_limbs += 2ull * nb * E * beta; ctx->exec.kernel_launches++;
   }
   // K6 + K7 (reference :417-487): INTT of the P-limbs of both accumulators, in place, BConv step 1 folded in
@@ -576,6 +641,7 @@ static int ks_front(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, Batc
     l.n_limbs = A; l.n_polys = 2 * nb; l.post_scale = lc->moddown_scale;  // acc is [nb][2][AL][N]: uniform poly stride
     l.n_batch = 1;
     launch_ntt_inverse(ctx->tabs, logN, lc->p_lm, l, s);
+    prof_mark(ctx, HML_CLS_INTT, s);
     ctx->exec.intt_limbs += 2ull * nb * A; ctx->exec.kernel_launches += npass;
   }
   return HML_OK;
@@ -624,6 +690,7 @@ static int ks_run(hml_ctx *ctx, uint32_t L, uint32_t nb, BatchPtr d, const u64 *
       f.cst = lc->pinv; f.n_c = 2;
     }
     launch_ntt_forward(ctx->tabs, logN, lc->q_lm, l, s);
+    prof_mark(ctx, HML_CLS_NTT, s);
     ctx->exec.ntt_limbs += 2ull * nb * L; ctx->exec.kernel_launches += npass;
     if (fuse) ctx->exec.ewe_limbs += (uint64_t)nb * (2 * L + (add0.ptr ? L : 0) + (add1.ptr ? L : 0));
   }
@@ -637,6 +704,7 @@ static int ks_run(hml_ctx *ctx, uint32_t L, uint32_t nb, BatchPtr d, const u64 *
     a.out = out.ptr; a.out_poly_stride = out.stride;
     a.cst = lc->pinv; a.N = N; a.n_limbs = L; a.n_polys = nb; a.x_packed = npass == 2;
     launch_sub_mul_add(ctx->mc, lc->q_lm, a, s);
+    prof_mark(ctx, HML_CLS_EWE, s);
     ctx->exec.ewe_limbs += (uint64_t)nb * (L + (a.z ? L : 0)); ctx->exec.kernel_launches++;
   }
   return check_launch(ctx, "keyswitch");
@@ -649,6 +717,7 @@ extern "C" int hml_keyswitch(hml_ctx *ctx, uint32_t L, const uint64_t *d, const 
   if (!d || !evk || !out0 || !out1) return fail(ctx, HML_ERR_INVALID, "null buffer");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   if ((rc = ensure_ws(ctx, ks_ws_words(ctx->p, L)))) return rc;
+  ws_enter(ctx, (cudaStream_t)stream);
   return ks_run(ctx, L, 1, {(const u64 *)d, 0}, (const u64 *)evk, evk_q_limbs, {(u64 *)out0, 0}, {(u64 *)out1, 0}, {nullptr, 0},
                 {nullptr, 0}, ctx->ws, (cudaStream_t)stream);
 }
@@ -796,6 +865,7 @@ extern "C" int hml_keyswitch_shard_begin(hml_ctx *ctx, uint32_t L, uint32_t rank
     l.in = (const u64 *)d_own; l.out = (u64 *)gather1 + (size_t)rank * sp->gq * N;
     l.in_limb_stride = l.out_limb_stride = N; l.n_limbs = nq; l.n_polys = 1; l.post_scale = sp->scale1;
     launch_ntt_inverse(ctx->tabs, ctx->p.logN, sp->q_lm, l, (cudaStream_t)stream);
+    prof_mark(ctx, HML_CLS_INTT, (cudaStream_t)stream);
     ctx->exec.intt_limbs += nq; ctx->exec.kernel_launches += ctx->p.logN <= NTT_SMALL_LOG ? 1 : 2;
   }
   return check_launch(ctx, "keyswitch shard begin");
@@ -815,6 +885,7 @@ static int shard_mid_tail(hml_ctx *ctx, ShardPlan *sp, uint32_t rank, const u64 
     l.in = ext; l.out = ext; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)ne * N;
     l.n_limbs = ne; l.n_polys = beta;
     launch_ntt_forward(ctx->tabs, logN, sp->e_lm, l, s);
+    prof_mark(ctx, HML_CLS_NTT, s);
     ctx->exec.ntt_limbs += (uint64_t)beta * ne - nq; ctx->exec.kernel_launches += npass;
   }
   {
@@ -822,6 +893,7 @@ static int shard_mid_tail(hml_ctx *ctx, ShardPlan *sp, uint32_t rank, const u64 
     a.d = d_own; a.ext = ext; a.evk = evk_own; a.acc = acc; a.N = N; a.n_ext = ne; a.beta = beta;
     a.evk_limbs = ne; a.n_batch = 1;
     launch_inner_product(ctx->mc, sp->e_lm, a, s);
+    prof_mark(ctx, HML_CLS_EWE, s);
     ctx->exec.ewe_limbs += 2ull * ne * beta; ctx->exec.kernel_launches++;
   }
   if (np) {
@@ -833,6 +905,7 @@ static int shard_mid_tail(hml_ctx *ctx, ShardPlan *sp, uint32_t rank, const u64 
     l.out = gather2 + (size_t)rank * 2 * sp->gp * N - (size_t)nq * N; l.out_limb_stride = N; l.out_poly_stride = (long long)sp->gp * N;
     l.n_limbs = np; l.n_polys = 2; l.post_scale = sp->scale2;
     launch_ntt_inverse(ctx->tabs, logN, sp->p_lm, l, s);
+    prof_mark(ctx, HML_CLS_INTT, s);
     ctx->exec.intt_limbs += 2 * np; ctx->exec.kernel_launches += npass;
   }
   return check_launch(ctx, "keyswitch shard mid");
@@ -847,6 +920,7 @@ extern "C" int hml_keyswitch_shard_mid(hml_ctx *ctx, uint32_t L, uint32_t rank, 
   ShardPlan *sp;
   if ((rc = get_shard_plan(ctx, L, rank, world, &sp))) return rc;
   if ((rc = ensure_ws(ctx, shard_ws_words(ctx->p, *sp)))) return rc;
+  ws_enter(ctx, (cudaStream_t)stream);
   const size_t N = ctx->p.N;
   const uint32_t ne = sp->own_q.size() + sp->own_p.size(), beta = sp->beta;
   cudaStream_t s = (cudaStream_t)stream;
@@ -865,6 +939,7 @@ extern "C" int hml_keyswitch_shard_mid(hml_ctx *ctx, uint32_t L, uint32_t rank, 
 static int shard_end_run(hml_ctx *ctx, ShardPlan *sp, const u64 *gather2, const long long *src_off, u64 *out0_own, u64 *out1_own, cudaStream_t s) {
   int rc;
   if ((rc = ensure_ws(ctx, shard_ws_words(ctx->p, *sp)))) return rc;
+  ws_enter(ctx, s);
   const Params &p = ctx->p;
   const size_t N = p.N;
   const uint32_t nq = sp->own_q.size(), np = sp->own_p.size(), ne = nq + np, beta = sp->beta;
@@ -883,6 +958,7 @@ static int shard_end_run(hml_ctx *ctx, ShardPlan *sp, const u64 *gather2, const 
     l.in = vb; l.out = vb; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)nq * N;
     l.n_limbs = nq; l.n_polys = 2;
     launch_ntt_forward(ctx->tabs, logN, sp->q_lm, l, s);
+    prof_mark(ctx, HML_CLS_NTT, s);
     ctx->exec.ntt_limbs += 2 * nq; ctx->exec.kernel_launches += npass;
   }
   {  // both outputs in one launch: the "poly" stride of the output is simply the distance between the two buffers
@@ -891,6 +967,7 @@ static int shard_end_run(hml_ctx *ctx, ShardPlan *sp, const u64 *gather2, const 
     a.out = out0_own; a.out_poly_stride = (long long)(out1_own - out0_own);
     a.cst = sp->pinv; a.N = N; a.n_limbs = nq; a.n_polys = 2;
     launch_sub_mul_add(ctx->mc, sp->q_lm, a, s);
+    prof_mark(ctx, HML_CLS_EWE, s);
     ctx->exec.ewe_limbs += 2 * nq; ctx->exec.kernel_launches++;
   }
   return check_launch(ctx, "keyswitch shard end");
@@ -1057,6 +1134,7 @@ extern "C" int hml_keyswitch_shard_mid_p2p(hml_ctx *ctx, uint32_t L, uint32_t ra
   for (auto &u : sp->up) if ((rc = shard_p2p_check(ctx, u))) return rc;
   if ((rc = shard_peer_offsets(ctx, sp, peers1, false))) return rc;
   if ((rc = ensure_ws(ctx, shard_ws_words(ctx->p, *sp)))) return rc;
+  ws_enter(ctx, (cudaStream_t)stream);
   const size_t N = ctx->p.N;
   const uint32_t ne = sp->own_q.size() + sp->own_p.size(), beta = sp->beta;
   if (ne == 0) return HML_OK;
@@ -1106,6 +1184,7 @@ static int rescale_run(hml_ctx *ctx, uint32_t L, const u64 *in, long long in_pol
     l.in = in + (size_t)(L - 1) * N; l.out = rb; l.in_limb_stride = l.out_limb_stride = N;
     l.in_poly_stride = in_poly_stride; l.out_poly_stride = N; l.n_limbs = 1; l.n_polys = n_polys;
     launch_ntt_inverse(ctx->tabs, logN, lm, l, s);
+    prof_mark(ctx, HML_CLS_INTT, s);
     ctx->exec.intt_limbs += n_polys; ctx->exec.kernel_launches += npass;
   }
   const bool fuse = npass == 2;
@@ -1121,6 +1200,7 @@ static int rescale_run(hml_ctx *ctx, uint32_t L, const u64 *in, long long in_pol
       f.dst = out; f.dst_c_stride = out_poly_stride; f.dst_b_stride = 0; f.cst = lc->qlinv; f.n_c = (int)n_polys;
     }
     launch_ntt_forward(ctx->tabs, logN, lc->q_lm, l, s);
+    prof_mark(ctx, HML_CLS_NTT, s);
     ctx->exec.ntt_limbs += (uint64_t)n_polys * (L - 1); ctx->exec.kernel_launches += npass;
   }
   if (!fuse) {  // sub + mul (reference :825-911), one fused pass
@@ -1128,6 +1208,7 @@ static int rescale_run(hml_ctx *ctx, uint32_t L, const u64 *in, long long in_pol
     a.x = in; a.y = rh; a.z = nullptr; a.out = out; a.x_poly_stride = in_poly_stride; a.y_poly_stride = (long long)(L - 1) * N;
     a.out_poly_stride = out_poly_stride; a.cst = lc->qlinv; a.N = N; a.n_limbs = L - 1; a.n_polys = n_polys;
     launch_sub_mul_add(ctx->mc, lc->q_lm, a, s);
+    prof_mark(ctx, HML_CLS_EWE, s);
     ctx->exec.kernel_launches++;
   }
   ctx->exec.ewe_limbs += 2ull * n_polys * (L - 1);
@@ -1140,6 +1221,7 @@ extern "C" int hml_rescale(hml_ctx *ctx, uint32_t L, const uint64_t *in, uint64_
   if (!in || !out) return fail(ctx, HML_ERR_INVALID, "null buffer");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   if ((rc = ensure_ws(ctx, rs_ws_words(ctx->p, L, 1)))) return rc;
+  ws_enter(ctx, (cudaStream_t)stream);
   return rescale_run(ctx, L, (const u64 *)in, 0, 1, (u64 *)out, 0, ctx->ws, (cudaStream_t)stream);
 }
 
@@ -1170,6 +1252,7 @@ extern "C" int hml_rescale_shard_begin(hml_ctx *ctx, uint32_t L, uint32_t rank, 
   l.out = (u64 *)r_own - (size_t)(nq - 1) * N; l.out_limb_stride = N; l.out_poly_stride = N;  // position nq-1 lands on r_own
   l.n_limbs = 1; l.n_polys = 2;
   launch_ntt_inverse(ctx->tabs, ctx->p.logN, lm, l, (cudaStream_t)stream);
+  prof_mark(ctx, HML_CLS_INTT, (cudaStream_t)stream);
   ctx->exec.intt_limbs += 2; ctx->exec.kernel_launches += ctx->p.logN <= NTT_SMALL_LOG ? 1 : 2;
   return check_launch(ctx, "rescale shard begin");
 }
@@ -1189,6 +1272,7 @@ extern "C" int hml_rescale_shard_end(hml_ctx *ctx, uint32_t L, uint32_t rank, ui
   const uint32_t nk = nq - ((L - 1) % world == rank ? 1 : 0);  // owned limbs that survive
   if (nk == 0) return HML_OK;
   if ((rc = ensure_ws(ctx, std::max(shard_ws_words(p, *sp), (size_t)2 * nk * N)))) return rc;
+  ws_enter(ctx, (cudaStream_t)stream);
   const int logN = p.logN, npass = logN <= NTT_SMALL_LOG ? 1 : 2;
   cudaStream_t s = (cudaStream_t)stream;
   LimbMap lm; clear_map(lm);
@@ -1206,6 +1290,7 @@ extern "C" int hml_rescale_shard_end(hml_ctx *ctx, uint32_t L, uint32_t rank, ui
       f.dst = (u64 *)out_own; f.dst_c_stride = (long long)nk * N; f.dst_b_stride = 0; f.cst = sp->qlinv_own; f.n_c = 2;
     }
     launch_ntt_forward(ctx->tabs, logN, lm, l, s);
+    prof_mark(ctx, HML_CLS_NTT, s);
     ctx->exec.ntt_limbs += 2ull * nk; ctx->exec.kernel_launches += npass;
   }
   if (!fuse) {
@@ -1213,6 +1298,7 @@ extern "C" int hml_rescale_shard_end(hml_ctx *ctx, uint32_t L, uint32_t rank, ui
     a.x = (const u64 *)x_own; a.y = rh; a.z = nullptr; a.out = (u64 *)out_own; a.x_poly_stride = (long long)nq * N;
     a.y_poly_stride = (long long)nk * N; a.out_poly_stride = (long long)nk * N; a.cst = sp->qlinv_own; a.N = N; a.n_limbs = nk; a.n_polys = 2;
     launch_sub_mul_add(ctx->mc, lm, a, s);
+    prof_mark(ctx, HML_CLS_EWE, s);
     ctx->exec.kernel_launches++;
   }
   ctx->exec.ewe_limbs += 4ull * nk;
@@ -1255,6 +1341,7 @@ static int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, con
   u64 *d0 = ws, *d1 = d0 + nb * PL, *d2 = d1 + nb * PL;
   const int merged = p.logN > NTT_SMALL_LOG;  // d0 / d1 then only feed element-wise epilogues: stored packed
   launch_tensor3(ctx->mc, (int)N, (int)L, ct_a, ct_a + PL, ct_b, ct_b + PL, d0, d1, d2, (int)nb, (long long)(2 * PL), (long long)PL, s, merged);  // reference :592-739
+  prof_mark(ctx, HML_CLS_EWE, s);
   ctx->exec.ewe_limbs += 3ull * nb * L; ctx->exec.kernel_launches++;
   if (!merged) {  // single-pass rings: the textbook sequence
     u64 *cb = d2 + nb * PL, *rest = cb + 2 * nb * PL;
@@ -1282,6 +1369,7 @@ static int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, con
     a.out = ul; a.out_poly_stride = (long long)N;
     a.cst = lc->pinv + (L - 1); a.N = N; a.n_limbs = 1; a.n_polys = 2; a.x_packed = a.z_packed = 1;
     launch_sub_mul_add(ctx->mc, lc->last_lm, a, s);
+    prof_mark(ctx, HML_CLS_EWE, s);
     ctx->exec.ewe_limbs += 4; ctx->exec.kernel_launches++;
   } else {
     for (int c = 0; c < 2; ++c) {
@@ -1292,6 +1380,7 @@ static int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, con
       a.out = ul + (size_t)c * N; a.out_poly_stride = 2ll * N;
       a.cst = lc->pinv + (L - 1); a.N = N; a.n_limbs = 1; a.n_polys = nb; a.x_packed = a.z_packed = 1;
       launch_sub_mul_add(ctx->mc, lc->last_lm, a, s);
+      prof_mark(ctx, HML_CLS_EWE, s);
       ctx->exec.ewe_limbs += 2ull * nb; ctx->exec.kernel_launches++;
     }
   }
@@ -1301,6 +1390,7 @@ static int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, con
     l.in = ul; l.out = acc + (size_t)E * N; l.in_limb_stride = l.out_limb_stride = N;
     l.in_poly_stride = N; l.out_poly_stride = (long long)AL * N; l.n_limbs = 1; l.n_polys = 2 * nb;
     launch_ntt_inverse(ctx->tabs, logN, lc->last_lm, l, s);
+    prof_mark(ctx, HML_CLS_INTT, s);
     ctx->exec.intt_limbs += 2ull * nb; ctx->exec.kernel_launches += 2;
   }
   {  // w_l = v_l * P^-1 + [r]_{q_l}, l < L-1, with r = slot_E - v[L-1] * P^-1 folded on the staged tile (reference K8 :489-519)
@@ -1319,6 +1409,7 @@ static int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, con
     f.dst = ct_out; f.dst_c_stride = (long long)(L - 1) * N; f.dst_b_stride = 2ll * (L - 1) * N;
     f.cst = lc->pinv; f.cst2 = lc->qlinv; f.n_c = 2; f.x_packed = f.z_packed = 1;
     launch_ntt_forward(ctx->tabs, logN, lc->q_lm, l, s);
+    prof_mark(ctx, HML_CLS_NTT, s);
     ctx->exec.ntt_limbs += 2ull * nb * (L - 1); ctx->exec.kernel_launches += 2;
     ctx->exec.ewe_limbs += 2ull * nb * 4 * (L - 1);
   }
@@ -1332,6 +1423,7 @@ extern "C" int hml_hmult(hml_ctx *ctx, uint32_t L, const uint64_t *ct_a, const u
   if (!ct_a || !ct_b || !evk || !ct_out) return fail(ctx, HML_ERR_INVALID, "null buffer");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   if ((rc = ensure_ws(ctx, hmult_ws_words(ctx->p, L, 1)))) return rc;
+  ws_enter(ctx, (cudaStream_t)stream);
   return hmult_run(ctx, L, 1, (const u64 *)ct_a, (const u64 *)ct_b, (const u64 *)evk, evk_q_limbs, (u64 *)ct_out, ctx->ws, (cudaStream_t)stream);
 }
 
@@ -1343,6 +1435,7 @@ static int hrot_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct, const 
   const size_t N = ctx->p.N, PL = N * L;
   u64 *sb = ws, *rest = sb + 2 * nb * PL;  // sb [nb][2][L][N]
   launch_automorph(ctx->p.logN, 2 * L * nb, ct, sb, g, s);  // reference :1302-1319
+  prof_mark(ctx, HML_CLS_AUTO, s);
   ctx->exec.automorph_limbs += 2ull * nb * L; ctx->exec.kernel_launches++;
   // reference :1326-1357 key-switches AUTOOutput(0) and adds AUTOOutput(1) (naming only, delta D4):
   // textbook = key-switch sigma(c1), add sigma(c0) to the first output
@@ -1358,6 +1451,7 @@ extern "C" int hml_hrotate(hml_ctx *ctx, uint32_t L, const uint64_t *ct, const u
   if (!(galois_elt & 1)) return fail(ctx, HML_ERR_INVALID, "galois element must be odd");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   if ((rc = ensure_ws(ctx, hrot_ws_words(ctx->p, L, 1)))) return rc;
+  ws_enter(ctx, (cudaStream_t)stream);
   return hrot_run(ctx, L, 1, (const u64 *)ct, (const u64 *)rotkey, evk_q_limbs, galois_elt, (u64 *)ct_out, ctx->ws, (cudaStream_t)stream);
 }
 
@@ -1374,9 +1468,11 @@ static int ew_ct_op(hml_ctx *ctx, uint32_t L, const uint64_t *a, const uint64_t 
   if (mul) {
     const long long cs[5] = {ct, pt, 0, 0, ct};
     launch_ewe(ctx->mc, lc->q_lm, (int)N, (int)L, (const u64 *)a, (const u64 *)b, nullptr, nullptr, 0, (u64 *)out, (cudaStream_t)stream, 2, cs);
+    prof_mark(ctx, HML_CLS_EWE, (cudaStream_t)stream);
   } else {
     const long long cs[5] = {ct, 0, pt, 0, ct};
     launch_ewe(ctx->mc, lc->q_lm, (int)N, (int)L, (const u64 *)a, nullptr, (const u64 *)b, nullptr, 0, (u64 *)out, (cudaStream_t)stream, 2, cs);
+    prof_mark(ctx, HML_CLS_EWE, (cudaStream_t)stream);
   }
   ctx->exec.ewe_limbs += 2ull * L; ctx->exec.kernel_launches++;
   return check_launch(ctx, "ewe op");
@@ -1411,6 +1507,7 @@ static int run_batch_lanes(hml_ctx *ctx, uint32_t n, size_t ws_per_ct, cudaStrea
   uint32_t chunk = std::min<uint32_t>(HML_BATCH_CHUNK, (n + lanes - 1) / lanes);
   int rc = ensure_ws(ctx, (size_t)lanes * chunk * ws_per_ct);
   if (rc) return rc;
+  ws_enter(ctx, user);
   const bool two = lanes == 2 && n > chunk;
   if (two) {
     if (!ctx->s_lane) {
@@ -1493,6 +1590,7 @@ static int host_pipeline(hml_ctx *ctx, bool is_mult, uint32_t L, uint32_t n, con
     CU_TRY(ctx, cudaEventCreateWithFlags(&ev_out[k], cudaEventDisableTiming));
   }
   rc = HML_OK;
+  ws_enter(ctx, ctx->s_comp);  // the workspace may still be in use by an op queued earlier on a caller stream
   for (uint32_t i = 0; i < n && rc == HML_OK; ++i) {
     const int k = i & 1;
     u64 *sa = ctx->stage + k * slot_w, *sb = sa + in_w, *so = sa + (is_mult ? 2 : 1) * in_w;
@@ -1511,6 +1609,7 @@ static int host_pipeline(hml_ctx *ctx, bool is_mult, uint32_t L, uint32_t n, con
   }
   cudaError_t e1 = cudaStreamSynchronize(ctx->s_in), e2 = cudaStreamSynchronize(ctx->s_comp), e3 = cudaStreamSynchronize(ctx->s_out);
   for (int k = 0; k < 2; ++k) { cudaEventDestroy(ev_in[k]); cudaEventDestroy(ev_comp[k]); cudaEventDestroy(ev_out[k]); }
+  ctx->have_last = false;  // everything has completed: nothing left to order against
   if (rc) return rc;
   for (cudaError_t e : {e1, e2, e3})
     if (e != cudaSuccess) return fail(ctx, HML_ERR_CUDA, std::string("host pipeline: ") + cudaGetErrorString(e));

@@ -79,6 +79,15 @@ struct DevBConv {  // cached tables of an arbitrary (src, dst) conversion for th
   HostBConv host;
 };
 
+// Per-kernel-class device time of the ops executed between hml_profile_begin / hml_profile_end: the counterpart of the
+// reference's per-unit busy statistics (NTT_(c), BCONV_(c), EWE_(c), AUTO_(c); reference include/Staistics.h:6-40).  While
+// it is on, every launch group is followed by an event record (which also serialises the programmatic dependent launches).
+struct Prof {
+  bool on = false;
+  cudaEvent_t start = nullptr;
+  std::vector<std::pair<int, cudaEvent_t>> marks;
+};
+
 }  // namespace hml
 
 struct hml_ctx {
@@ -109,4 +118,19 @@ struct hml_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   hml::u64 *stage = nullptr;
   size_t stage_words = 0;
+
+  // Ops share ONE workspace.  The stream the workspace was last used on is remembered; an op arriving on a different
+  // stream first waits (device-side, through ev_ws) for everything queued on the previous one.
+  cudaStream_t last_stream = nullptr;
+  bool have_last = false;
+  cudaEvent_t ev_ws = nullptr;
+
+  hml::Prof prof;
 };
+
+namespace hml {
+// order the workspace between caller streams (see hml_ctx::last_stream); call at the start of every op that touches ctx->ws
+void ws_enter(hml_ctx *ctx, cudaStream_t s);
+// profiling mark after a launch group of class cls (HML_CLS_*); no-op unless hml_profile_begin was called
+void prof_mark(hml_ctx *ctx, int cls, cudaStream_t s);
+}  // namespace hml

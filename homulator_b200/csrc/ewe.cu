@@ -296,12 +296,17 @@ __global__ void __launch_bounds__(512) k_bconv_mma(const ModConst *__restrict__ 
     const ModConst mf = mc[a.fold_mod];
     const int last = a.n_src - 1;
     for (int m = threadIdx.x; m < tm; m += blockDim.x) {
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0;  // <= 15 terms of < 2^48 each: exact
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;  // terms of < 2^48 each: exact as long as at most 16 are summed unreduced
       for (int i = 0; i < last; ++i) {
         const double y = ys[i * pitch + m];
         s0 = __fma_rn(y, __ldg(a.fold + 3 * i), s0);
         s1 = __fma_rn(y, __ldg(a.fold + 3 * i + 1), s1);
         s2 = __fma_rn(y, __ldg(a.fold + 3 * i + 2), s2);
+        if ((i & 15) == 15) {  // alpha > 16 (DMMA path only): fold like the main loop does, every 16 sources
+          s0 = reduce_signed(s0, mf.q, mf.qinv);
+          s1 = reduce_signed(s1, mf.q, mf.qinv);
+          s2 = reduce_signed(s2, mf.q, mf.qinv);
+        }
       }
       double v = reduce_signed(s2, mf.q, mf.qinv);
       v = reduce_signed(__fma_rn(v, 4096.0, s1), mf.q, mf.qinv);

@@ -20,7 +20,11 @@
  *     `DataType = uint64_t`), caller-owned, residues < 2^elementBitWidth, layout [.. ][limb][N],
  *     a ciphertext is [2][L][N] (c0 limbs, then c1 limbs), in EVALUATION form:
  *         slot k of limb i holds a(psi_i^(2*bitrev(k)+1)) mod q_i      (bitrev over log2 N bits)
- *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous.  The ops of one ctx share
+ *     one device workspace: calls may arrive on different streams (the library orders the workspace between them with an
+ *     event, i.e. ops of ONE ctx never overlap each other), but every INPUT — including the key — must already be ordered
+ *     before the call on the stream it is issued to.  The *_host entry points run on internal streams and return after
+ *     completion; their device-resident key must be complete (synchronise its producer) before the call.
  *   - modulus indices: 0..maxLevel-1 are q_i, maxLevel..maxLevel+alpha-1 are p_j.  The moduli are all
  *     primes = 1 (mod 2N) in (2^(w-1), 2^w), w = elementBitWidth, scanned downward from 2^w.
  *   - evaluation / rotation key layout: [beta][2][evk_q_limbs + alpha][N], Q-limbs first then the alpha
@@ -251,6 +255,19 @@ int hml_buffer_plan(const hml_ctx *ctx, const char *op, uint32_t L, char *out, u
 
 int hml_exec_counts_get(const hml_ctx *ctx, hml_exec_counts *out);
 int hml_exec_counts_reset(hml_ctx *ctx);
+
+/* Per-kernel-class device time of everything executed on `stream` between the two calls — the executed counterpart of the
+ * reference's per-unit busy statistics (`NTT_(c)`, `BCONV_(c)`, `EWE_(c)`, `AUTO_(c)`; reference include/Staistics.h:6-40,
+ * dumped at src/Operation.cpp:1100-1108).  While profiling, an event follows every launch group, so kernels do not overlap
+ * (a measuring mode, not the fast path).  Classes: the reference's opcodes. */
+enum { HML_CLS_NTT = 0, HML_CLS_INTT = 1, HML_CLS_BCONV = 2, HML_CLS_EWE = 3, HML_CLS_AUTO = 4, HML_CLS_COUNT = 5 };
+typedef struct {
+  double us[HML_CLS_COUNT];          /* device time per class */
+  uint64_t launches[HML_CLS_COUNT];  /* launch groups per class */
+  double total_us;
+} hml_profile;
+int hml_profile_begin(hml_ctx *ctx, void *stream);
+int hml_profile_end(hml_ctx *ctx, hml_profile *out);
 
 /* ------------------------------------------------------------------ the CLI as a library call
  * `Homulator.run <configfile> <operationName> <maxExecutionLevel> <currentLevel> <alpha> [cluster] [--flags]`

@@ -321,3 +321,32 @@ def test_hmult_is_commutative_bitwise(north_star):
     assert torch.equal(ctx.hmult(35, A, B, K), ctx.hmult(35, B, A, K))
     AB, BA = torch.stack([A, B, A]), torch.stack([B, A, A])
     assert torch.equal(ctx.hmult_batch(35, AB, BA, K), ctx.hmult_batch(35, BA, AB, K))
+
+
+@pytest.mark.parametrize("N,ML,A,L", [(8192, 6, 2, 5), (8192, 6, 2, 2), (32768, 8, 3, 8), (65536, 45, 15, 35), (65536, 45, 15, 2)])
+def test_rescale_and_keyswitch_standalone_two_pass_rings(N, ML, A, L):
+    """hml_rescale / hml_keyswitch on two-pass rings (N >= 8192) take their own code paths (ntt_rows<0,1> with no z / cst2
+    for the rescale, the textbook K8-K10 for the key switch): compare them with the oracle directly, not only through
+    hmult / hrotate (reference Rescale src/Operation.cpp:741-911, KeySwitch :9-54)."""
+    Oracle.set_threads(0)
+    ctx, o = hml.Context(N=N, max_level=ML, alpha=A), Oracle(N, 36, ML, A)
+    (a, b), evk = make_case(o, L, L, 1500 + L)
+    for poly in (a[0], a[1], b[1]):
+        assert np.array_equal(to_host(ctx.rescale(L, to_dev(poly))), o.rescale(L, poly))
+    w0, w1 = o.keyswitch(L, b[0], evk, L)
+    g0, g1 = ctx.keyswitch(L, to_dev(b[0]), to_dev(evk), L)
+    assert np.array_equal(to_host(g0), w0) and np.array_equal(to_host(g1), w1)
+    Oracle.set_threads(1)
+
+
+def test_hmult_many_special_primes_dmma_fold():
+    """alpha = 50 > 48 sources: the merged ModDown + Rescale of hmult falls off the tcgen05 kernel onto the FP64 tensor-core
+    kernel, whose fold pre-pass sums alpha products of < 2^48 — more than the 16 an exact double sum can hold unreduced
+    (the fold must reduce every 16 terms like the main loop)."""
+    N, ML, A, L = 8192, 4, 50, 3
+    Oracle.set_threads(0)
+    ctx, o = hml.Context(N=N, max_level=ML, alpha=A), Oracle(N, 36, ML, A)
+    (a, b), evk = make_case(o, L, L, 1700)
+    assert np.array_equal(to_host(ctx.hmult(L, to_dev(a), to_dev(b), to_dev(evk))), o.hmult(L, a, b, evk, L))
+    assert np.array_equal(to_host(ctx.hrotate(L, to_dev(a), to_dev(evk), 5)), o.hrotate(L, a, evk, L, 5))
+    Oracle.set_threads(1)

@@ -1,0 +1,198 @@
+"""CPU test of the oracle's CKKS *semantics* (VERDICT r1, weak item 4): the bit-exact parity tests only prove that the CUDA
+path and the oracle agree with each other; nothing there checks that the shared specification is a key switch at all.  Here a
+real secret key, a real hybrid relinearisation key and a real rotation key are generated with Python big integers in the
+layout the ABI documents ([beta][2][evk_q_limbs + alpha][N], Q-limbs first, extended basis (q_0..q_{L-1}, p_0..p_{alpha-1})),
+ciphertexts are real RLWE encryptions, and
+    decrypt(orc_hmult(enc a, enc b))  ~  a * b / q_{L-1}        decrypt(orc_hrotate(enc a))  ~  sigma_g(a)
+must hold up to the noise of the scheme.  That pins the P/Q ordering, the digit partition, the gadget the key must encode,
+the sign of ModDown and of the rescale, and the automorphism's direction independently of the kernels' author
+(reference stage order: src/Operation.cpp:9-54 KeySwitch, :741-911 Rescale, :913-1023 HMULT, :1271-1358 HROTATE).
+"""
+import random
+
+import numpy as np
+import pytest
+
+from orc import Oracle
+
+
+def negacyclic_mul(a, b, N):
+    out = [0] * N
+    for i, x in enumerate(a):
+        if x == 0:
+            continue
+        for j, y in enumerate(b):
+            k = i + j
+            if k < N:
+                out[k] += x * y
+            else:
+                out[k - N] -= x * y
+    return out
+
+
+def automorph_coeff(a, g, N):
+    """sigma_g: X -> X^g on integer coefficients."""
+    out = [0] * N
+    for i, x in enumerate(a):
+        k = (i * g) % (2 * N)
+        if k < N:
+            out[k] += x
+        else:
+            out[k - N] -= x
+    return out
+
+
+def crt(residues, moduli):
+    """residues[l][n] -> centred integers mod prod(moduli)."""
+    Q = 1
+    for m in moduli:
+        Q *= m
+    n = len(residues[0])
+    out = [0] * n
+    for res, m in zip(residues, moduli):
+        Qi = Q // m
+        c = Qi * pow(Qi % m, -1, m)
+        for k in range(n):
+            out[k] += int(res[k]) * c
+    return [((v % Q) + Q // 2) % Q - Q // 2 for v in out], Q
+
+
+class Scheme:
+    def __init__(self, N, ML, A, seed):
+        self.o = Oracle(N, 36, ML, A)
+        self.N, self.ML, self.A = N, ML, A
+        self.rnd = random.Random(seed)
+        self.s = [self.rnd.choice((-1, 0, 1)) for _ in range(N)]
+
+    def to_eval(self, poly, mod_idx):
+        """integer coefficients -> [len(mod_idx)][N] evaluation-form residues (the oracle's own NTT, pinned in test_oracle.py)"""
+        out = np.empty((len(mod_idx), self.N), dtype=np.uint64)
+        for r, mi in enumerate(mod_idx):
+            m = self.o.moduli[mi]
+            out[r] = self.o.ntt(mi, np.array([v % m for v in poly], dtype=np.uint64))
+        return out
+
+    def from_eval(self, limbs, mod_idx):
+        res = [self.o.intt(mi, limbs[r]) for r, mi in enumerate(mod_idx)]
+        return crt(res, [self.o.moduli[mi] for mi in mod_idx])
+
+    def small(self):
+        return [int(round(self.rnd.gauss(0, 3.2))) for _ in range(self.N)]
+
+    def uniform(self, Q):
+        return [self.rnd.randrange(Q) for _ in range(self.N)]
+
+    def encrypt(self, msg, L):
+        idx = list(range(L))
+        Q = 1
+        for i in idx:
+            Q *= self.o.moduli[i]
+        a = self.uniform(Q)
+        e = self.small()
+        as_ = negacyclic_mul(a, self.s, self.N)
+        c0 = [(-as_[k] + msg[k] + e[k]) % Q for k in range(self.N)]
+        return np.stack([self.to_eval(c0, idx), self.to_eval(a, idx)])
+
+    def decrypt(self, ct, L):
+        idx = list(range(L))
+        c0, Q = self.from_eval(ct[0], idx)
+        c1, _ = self.from_eval(ct[1], idx)
+        c1s = negacyclic_mul(c1, self.s, self.N)
+        return [((c0[k] + c1s[k]) % Q + Q // 2) % Q - Q // 2 for k in range(self.N)]
+
+    def switch_key(self, s_from, key_q_limbs):
+        """Hybrid key switching key s_from -> s over (q_0..q_{key_q_limbs-1}, p_0..p_{alpha-1}):
+        evk[j] = (-a_j s + e_j + P * g_j * s_from, a_j),  g_j = 1 on the limbs of digit j, 0 on every other Q-limb."""
+        o, A, ML = self.o, self.A, self.ML
+        KQ = key_q_limbs
+        idx = list(range(KQ)) + [ML + j for j in range(A)]
+        mods = [o.moduli[i] for i in idx]
+        QP = 1
+        for m in mods:
+            QP *= m
+        P = 1
+        for j in range(A):
+            P *= o.moduli[ML + j]
+        beta = -(-KQ // A)
+        out = np.empty((beta, 2, KQ + A, self.N), dtype=np.uint64)
+        for j in range(beta):
+            a = self.uniform(QP)
+            e = self.small()
+            as_ = negacyclic_mul(a, self.s, self.N)
+            base = [(-as_[k] + e[k]) % QP for k in range(self.N)]
+            k0 = self.to_eval(base, idx)
+            # the gadget term is defined limb by limb: P * s_from on the limbs of digit j, nothing elsewhere
+            for r in range(j * A, min(KQ, (j + 1) * A)):
+                m = mods[r]
+                g = self.o.ntt(idx[r], np.array([(P % m) * v % m for v in s_from], dtype=np.uint64))
+                k0[r] = (k0[r] + g) % np.uint64(m)
+            out[j, 0] = k0
+            out[j, 1] = self.to_eval(a, idx)
+        return out
+
+
+CASES = [(64, 4, 4, 2, 4), (64, 4, 3, 2, 3), (64, 5, 3, 2, 5), (128, 6, 6, 3, 6), (64, 3, 2, 3, 2), (64, 4, 4, 4, 4)]
+
+
+@pytest.mark.parametrize("N,ML,L,A,KQ", CASES)
+def test_hmult_decrypts_to_the_rescaled_product(N, ML, L, A, KQ):
+    sc = Scheme(N, ML, A, seed=1000 + N + 7 * L + A)
+    s2 = negacyclic_mul(sc.s, sc.s, N)
+    evk = sc.switch_key(s2, KQ)
+    scale = 1 << 30
+    ma = [scale * sc.rnd.randint(-8, 8) for _ in range(N)]
+    mb = [scale * sc.rnd.randint(-8, 8) for _ in range(N)]
+    ct = sc.o.hmult(L, sc.encrypt(ma, L), sc.encrypt(mb, L), evk, KQ)
+    got = sc.decrypt(ct, L - 1)
+    ql = sc.o.moduli[L - 1]
+    prod = negacyclic_mul(ma, mb, N)
+    err = max(abs(got[k] - prod[k] / ql) for k in range(N))
+    signal = max(abs(v) / ql for v in prod)
+    # noise: fresh-encryption noise times the other message, scaled down by q_{L-1} (~ 2^30 * 8 * 3.2 * N / 2^36), plus the
+    # key-switch noise and the rescale rounding (1 + |s|_1) / 2; all far below the 2^24-sized product
+    assert signal > 2 ** 22
+    assert err < 64 * N, (err, signal)
+
+
+@pytest.mark.parametrize("N,ML,L,A,KQ", CASES + [(64, 4, 1, 2, 1)])
+@pytest.mark.parametrize("rot", [1, 3, -1])
+def test_hrotate_decrypts_to_the_automorphism(N, ML, L, A, KQ, rot):
+    sc = Scheme(N, ML, A, seed=2000 + N + 7 * L + A)
+    g = 2 * N - 1 if rot < 0 else pow(5, rot, 2 * N)
+    rk = sc.switch_key(automorph_coeff(sc.s, g, N), KQ)
+    msg = [(1 << 30) * sc.rnd.randint(-8, 8) for _ in range(N)]
+    ct = sc.o.hrotate(L, sc.encrypt(msg, L), rk, KQ, g)
+    got = sc.decrypt(ct, L)
+    want = automorph_coeff(msg, g, N)
+    err = max(abs(got[k] - want[k]) for k in range(N))
+    assert err < 64 * N, err   # fresh noise (sigma 3.2) + key-switch noise; the message coefficients are ~2^33
+
+
+def test_keyswitch_alone_moves_a_polynomial_under_the_new_key():
+    """KS(d) = (k0, k1) with k0 + k1 s ~ d * s_from: the statement every composite op relies on."""
+    N, ML, L, A = 64, 4, 4, 2
+    sc = Scheme(N, ML, A, seed=77)
+    s_from = [sc.rnd.choice((-1, 0, 1)) for _ in range(N)]
+    key = sc.switch_key(s_from, L)
+    Q = 1
+    for i in range(L):
+        Q *= sc.o.moduli[i]
+    d = sc.uniform(Q)
+    k0, k1 = sc.o.keyswitch(L, sc.to_eval(d, list(range(L))), key, L)
+    got = sc.decrypt(np.stack([k0, k1]), L)
+    want = negacyclic_mul(d, s_from, N)
+    err = max(abs((got[k] - want[k] + Q // 2) % Q - Q // 2) for k in range(N))
+    assert err < 2 ** 16, err   # sum_j ModUp_j * e_j / P + rounding: independent of |d| ~ 2^144
+
+
+def test_negative_control_swapped_key_components_do_not_decrypt():
+    """the bound above is meaningful: with the two key components exchanged the result is garbage of the size of Q"""
+    N, ML, L, A = 64, 4, 4, 2
+    sc = Scheme(N, ML, A, seed=5)
+    evk = sc.switch_key(negacyclic_mul(sc.s, sc.s, N), L)
+    bad = np.ascontiguousarray(evk[:, ::-1])
+    ma = [(1 << 30) * sc.rnd.randint(-8, 8) for _ in range(N)]
+    ct = sc.o.hmult(L, sc.encrypt(ma, L), sc.encrypt(ma, L), bad, L)
+    got = sc.decrypt(ct, L - 1)
+    prod = negacyclic_mul(ma, ma, N)
+    assert max(abs(got[k] - prod[k] / sc.o.moduli[L - 1]) for k in range(N)) > 2 ** 60
