@@ -165,18 +165,14 @@ def _emit(real_stdout, line):
 
 
 def limb_sharded(ctx, rank, world, L, evk, dist, torch):
-    """SURVEY.md 8e mode 2 / BASELINE.json configs[4] on all ranks: one ciphertext's key switch and the baby-step/giant-step op
-    sequence with the limbs sharded over the GPUs (limb i on rank i % world).  Device events, max over ranks."""
+    """SURVEY.md 8e mode 2 / BASELINE.json configs[4] on all ranks: one ciphertext's key switch and the rotation-heavy op
+    sequence with the limbs sharded over the GPUs (limb i on rank i % world), every sharded op ONE C-ABI call
+    (hml_keyswitch_sharded, hml_replay_* over an hml_shard).  Device events, max over ranks."""
     import homulator_b200 as hml
-    from homulator_b200.replay import bsgs_trace, replay, replay_sharded
+    from homulator_b200.replay import bsgs_trace, shard_operands, trace_counts
     q = list(range(L))
     d = ctx.uniform(q, 900)
     x = ctx.uniform(q, 901, lead=(2,))
-    lay = hml.shard_layout(L, ALPHA, rank, world)
-    own = lay["own_q"]
-    own_e = own + [L + j for j in lay["own_p"]]
-    oi, oe = torch.tensor(own, device="cuda"), torch.tensor(own_e, device="cuda")
-    d_own, evk_own, x_own = d[oi].contiguous(), evk[:, :, oe].contiguous(), x[:, oi].contiguous()
 
     def exchange(obj):
         out = [None] * world
@@ -198,31 +194,53 @@ def limb_sharded(ctx, rank, world, L, evk, dist, torch):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
-    sh = ctx.shard_p2p_setup(L, rank, world, exchange)
+    sh = hml.Shard.ipc(ctx, L, rank, world, exchange)
+    sh.prepare(L)
+    oi = torch.tensor(sh.own_q(L), device="cuda", dtype=torch.long)
+    oe = torch.tensor(sh.own_ext(L), device="cuda", dtype=torch.long)
+    d_own, evk_own = d[oi].contiguous(), evk[:, :, oe].contiguous()
     dist.barrier()
     ref0, ref1 = ctx.keyswitch(L, d, evk)
-    o0, o1 = sh.keyswitch(d_own, evk_own)
-    ok = bool(torch.equal(o0, ref0[oi]) and torch.equal(o1, ref1[oi]))
-    res = {"keyswitch_peer_direct_us": timeit(lambda: sh.keyswitch(d_own, evk_own), 20),
+    o0, o1 = ctx.empty(max(len(oi), 1), N_RING), ctx.empty(max(len(oi), 1), N_RING)
+    sh.keyswitch(L, d_own, evk_own, o0, o1)
+    ok = bool(torch.equal(o0[:len(oi)], ref0[oi]) and torch.equal(o1[:len(oi)], ref1[oi]))
+    t0 = time.perf_counter()
+    for _ in range(20):
+        sh.keyswitch(L, d_own, evk_own, o0, o1)
+    host_us = (time.perf_counter() - t0) / 20 * 1e6
+    torch.cuda.synchronize()
+    res = {"keyswitch_peer_direct_us": timeit(lambda: sh.keyswitch(L, d_own, evk_own, o0, o1), 20),
+           "keyswitch_host_enqueue_us": host_us,
            "keyswitch_nccl_allgather_us": timeit(lambda: ctx.keyswitch_sharded(
                L, d_own, evk_own, rank, world, lambda buf: dist.all_gather_into_tensor(buf, buf[rank].clone())), 20),
            "keyswitch_one_gpu_us": timeit(lambda: ctx.keyswitch(L, d, evk), 20)}
     tr = bsgs_trace(4, 4)
     pts = {i: ctx.uniform(q, 920 + i) for i in range(16)}
-    pts2 = {i: torch.stack([p[oi], p[oi]]).contiguous() for i, p in pts.items()}
     keys = {r: evk for r in sorted({op[3] for op in tr if op[0] == "hrotate"})}
-    keys_own = {r: evk_own for r in keys}
-    ref = replay(ctx, L, tr, x, pts, keys, evk)["z"]
-    got = replay_sharded(sh, tr, x_own, pts2, keys_own, evk_own)["z"]
-    keep = torch.tensor([i for i in own if i < L - 1], device="cuda")
-    ok = ok and bool(torch.equal(got.contiguous(), ref[:, keep]))
-    res["sequence_peer_direct_us"] = timeit(lambda: replay_sharded(sh, tr, x_own, pts2, keys_own, evk_own), 5)
-    res["sequence_one_gpu_us"] = timeit(lambda: replay(ctx, L, tr, x, pts, keys, evk), 5)
+    x_own, pts_own, keys_own, _ = shard_operands(sh, L, x, pts, keys, evk)
+    one = hml.Replay(ctx, L, tr).bind(x, pts, keys, evk)
+    ref = one.run().result("z").clone()
+    keep = torch.tensor([i for i in sh.own_q(L) if i < L - 1], device="cuda", dtype=torch.long)
+    res["sequence_ops"] = trace_counts(tr)
+    for name, graph in (("sequence_peer_direct_us", False), ("sequence_peer_direct_graph_us", True)):
+        rp = hml.Replay(ctx, L, tr, shard=sh, graph=graph).bind(x_own, pts_own, keys_own, evk_own)
+        got = rp.run().result("z")
+        torch.cuda.synchronize()
+        ok = ok and bool(torch.equal(got.contiguous(), ref[:, keep]))
+        res[name] = timeit(rp.run, 5)
+        dist.barrier()
+        rp.close()
+    res["sequence_one_gpu_us"] = timeit(one.run, 5)
+    try:
+        sh.check()
+    except hml.HmlError:
+        ok = False
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     res["bit_identical_to_one_gpu"] = bool(int(flag) == 1)
     dist.barrier()
     torch.cuda.synchronize()
+    one.close()
     sh.close()
     dist.barrier()
     return res
@@ -434,13 +452,23 @@ def main():
                                            "hmult_45_35_15": HMULT_SIM_CYCLES, "note": "unmodified reference CLI, g++ -O2, build container; "
                                            "cycles are machine-independent (BASELINE.md section 2); 1 cycle = 1 ns at an assumed 1 GHz"},
         })
-        # BASELINE.json configs[4]: synthetic rotation-heavy op sequence (baby-step/giant-step), replayed op by op
-        from homulator_b200.replay import bsgs_trace, replay, trace_counts
-        tr = bsgs_trace(4, 4)
+        # BASELINE.json configs[4]: synthetic rotation-heavy op sequences through hml_replay_*: the baby-step/giant-step trace
+        # (6 rotations) and the 16-rotation sum SURVEY.md 8d suggests; plain launches, one CUDA graph, hoisted rotations
+        from homulator_b200.replay import bsgs_trace, rotsum_trace, trace_counts
         pts = {i: ct_b[1][0] for i in range(16)}
-        keys = {r: evk for r in (1, 2, 3, 4, 8, 12)}
-        seq = lat(lambda: replay(ctx, L, tr, ct_a[0], pts, keys, evk), iters=5)
-        extra["bsgs_sequence"] = {"ops": trace_counts(tr), "us": seq}
+        seqs = {}
+        for name, tr in (("bsgs_4x4", bsgs_trace(4, 4)), ("rotsum_16", rotsum_trace(16))):
+            keys = {r: evk for r in sorted({op[3] for op in tr if op[0] == "hrotate"})}
+            row = {"ops": trace_counts(tr)}
+            for mode, kw in (("launches_us", {}), ("graph_us", {"graph": True}), ("hoisted_graph_us", {"graph": True, "hoist": True})):
+                rp = hml.Replay(ctx, L, tr, **kw).bind(ct_a[0], pts, keys, evk)
+                rp.run()
+                rp.run()
+                row[mode] = lat(rp.run, iters=5)
+                rp.close()
+            seqs[name] = row
+        extra["op_sequences"] = seqs
+        extra["bsgs_sequence"] = {"ops": seqs["bsgs_4x4"]["ops"], "us": seqs["bsgs_4x4"]["launches_us"]}
 
     if sharded is not None:
         extra["limb_sharded"] = sharded

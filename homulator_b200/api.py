@@ -41,6 +41,10 @@ class _ExecCounts(C.Structure):
                 ("bconv_limb_macs", C.c_uint64), ("automorph_limbs", C.c_uint64), ("kernel_launches", C.c_uint64)]
 
 
+class _TraceOp(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("dst", C.c_uint32), ("a", C.c_uint32), ("b", C.c_uint32)]
+
+
 class _Profile(C.Structure):
     _fields_ = [("us", C.c_double * 5), ("launches", C.c_uint64 * 5), ("total_us", C.c_double)]
 
@@ -60,6 +64,10 @@ EXPORTS = [
     "hml_shard_layout", "hml_keyswitch_shard_begin", "hml_keyswitch_shard_mid", "hml_keyswitch_shard_end",
     "hml_keyswitch_shard_mid_p2p", "hml_keyswitch_shard_end_p2p", "hml_shard_signal", "hml_shard_wait", "hml_shard_sync",
     "hml_ipc_export", "hml_ipc_import", "hml_ipc_close", "hml_rescale_shard_begin", "hml_rescale_shard_end",
+    "hml_shard_status", "hml_shard_create", "hml_shard_destroy", "hml_shard_handles", "hml_shard_connect_ipc",
+    "hml_shard_connect_local", "hml_shard_prepare", "hml_shard_check", "hml_shard_own_limbs", "hml_keyswitch_sharded",
+    "hml_hrotate_sharded", "hml_hmult_sharded", "hml_rescale_sharded", "hml_ew_sharded", "hml_group_op", "hml_hrotate_hoisted",
+    "hml_replay_create", "hml_replay_bind", "hml_replay_run", "hml_replay_slot", "hml_replay_destroy",
 ]
 
 
@@ -126,6 +134,28 @@ def load_library():
     L.hml_ipc_export.argtypes = [vp, vp, C.c_char_p]
     L.hml_ipc_import.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.hml_ipc_close.argtypes = [vp, vp]
+    L.hml_shard_status.argtypes = [vp, vp, u32, vp]
+    L.hml_shard_create.argtypes = [vp, u32, u32, u32, C.POINTER(vp)]
+    L.hml_shard_destroy.argtypes = [vp]
+    L.hml_shard_handles.argtypes = [vp, C.c_char_p]
+    L.hml_shard_connect_ipc.argtypes = [vp, C.c_char_p]
+    L.hml_shard_connect_local.argtypes = [C.POINTER(vp), u32]
+    L.hml_shard_prepare.argtypes = [vp, u32]
+    L.hml_shard_check.argtypes = [vp, vp]
+    L.hml_shard_own_limbs.argtypes = [vp, u32, C.POINTER(u32), C.POINTER(u32)]
+    L.hml_keyswitch_sharded.argtypes = [vp, u32, vp, vp, vp, vp, vp]
+    L.hml_hrotate_sharded.argtypes = [vp, u32, vp, vp, u64, vp, vp]
+    L.hml_hmult_sharded.argtypes = [vp, u32, vp, vp, vp, vp, vp]
+    L.hml_rescale_sharded.argtypes = [vp, u32, vp, vp, vp]
+    L.hml_ew_sharded.argtypes = [vp, u32, i32, vp, vp, vp, vp]
+    L.hml_group_op.argtypes = [C.POINTER(vp), u32, i32, u32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), u64,
+                               C.POINTER(vp)]
+    L.hml_hrotate_hoisted.argtypes = [vp, u32, vp, u32, C.POINTER(vp), u32, C.POINTER(u64), C.POINTER(vp), vp]
+    L.hml_replay_create.argtypes = [vp, vp, u32, C.POINTER(_TraceOp), u32, u32, C.POINTER(vp)]
+    L.hml_replay_bind.argtypes = [vp, vp, C.POINTER(vp), u32, C.POINTER(u32), C.POINTER(vp), u32, vp, u32]
+    L.hml_replay_run.argtypes = [vp, vp]
+    L.hml_replay_slot.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u32)]
+    L.hml_replay_destroy.argtypes = [vp]
     L.hml_dev_alloc.argtypes = [vp, u64, C.POINTER(vp)]
     L.hml_dev_free.argtypes = [vp, vp]
     L.hml_h2d.argtypes = [vp, vp, vp, u64, vp]
@@ -321,6 +351,16 @@ class Context:
         self._chk(self.lib.hml_hrotate(self.h, L, _ptr(ct), _ptr(rotkey), evk_q_limbs or L, galois_elt, _ptr(out), self._stream()))
         return out
 
+    def hrotate_hoisted(self, L, ct, rotkeys, galois_elts, evk_q_limbs=None, outs=None):
+        """Rotations of ONE ciphertext sharing one ModUp (hml_hrotate_hoisted); returns the list of outputs."""
+        n = len(galois_elts)
+        outs = [self.empty(2, L, self.N) for _ in range(n)] if outs is None else outs
+        keys = (C.c_void_p * n)(*[_ptr(k) for k in rotkeys])
+        po = (C.c_void_p * n)(*[_ptr(o) for o in outs])
+        gs = (C.c_uint64 * n)(*[int(g) for g in galois_elts])
+        self._chk(self.lib.hml_hrotate_hoisted(self.h, L, _ptr(ct), n, keys, evk_q_limbs or L, gs, po, self._stream()))
+        return outs
+
     def hadd(self, L, a, b, out=None):
         out = self.empty(2, L, self.N) if out is None else out
         self._chk(self.lib.hml_hadd(self.h, L, _ptr(a), _ptr(b), _ptr(out), self._stream()))
@@ -399,25 +439,6 @@ class Context:
         self._chk(self.lib.hml_ipc_import(self.h, handle, C.byref(p)))
         return p.value
 
-    def shard_p2p_setup(self, L, rank, world, exchange):
-        """Allocate this rank's gather buffers + flag block and map every peer's.  `exchange(obj)` must return the list of all
-        ranks' objects (torch.distributed.all_gather_object); with world == 1 or for emulated ranks pass the pointers in directly
-        through ShardP2P(...)."""
-        lay = shard_layout(L, self.alpha, rank, world)
-        n1, n2 = world * lay["gather1_slots"] * self.N, world * 2 * lay["gather2_slots"] * self.N
-        g1, g2, fl, rb = self.dev_alloc(n1), self.dev_alloc(n2), self.dev_alloc(3 * world + 8), self.dev_alloc(2 * self.N)
-        handles = exchange((self.ipc_export(g1), self.ipc_export(g2), self.ipc_export(fl), self.ipc_export(rb)))
-        p1, p2, pf, pr = [], [], [], []
-        for r, (h1, h2, hf, hr) in enumerate(handles):
-            if r == rank:
-                p1.append(g1); p2.append(g2); pf.append(fl); pr.append(rb)
-            else:
-                p1.append(self.ipc_import(h1)); p2.append(self.ipc_import(h2)); pf.append(self.ipc_import(hf)); pr.append(self.ipc_import(hr))
-        sh = ShardP2P(self, L, rank, world, p1, p2, pf, pr)
-        sh._own_ptrs = [g1, g2, fl, rb]
-        sh._peer_ptrs = [p for lst in (p1, p2, pf, pr) for r, p in enumerate(lst) if r != rank]
-        return sh
-
     def counts(self, op, L):
         c = _Counts()
         rc = self.lib.hml_get_counts(self.h, op.encode(), L, C.byref(c))
@@ -465,165 +486,190 @@ class Context:
         return out.view(*lead, len(mod_idx), self.N)
 
 
-class ShardP2P:
-    """State of the peer-direct limb-sharded ops on one rank: pointers to every rank's gather buffers, rescale buffer and flag
-    block (own allocation at index `rank`, peer mappings elsewhere) and the epoch counters.  A sharded ciphertext is a tensor
-    [2][nq][N] holding this rank's Q-limbs (ascending limb index, limb i lives on rank i % world).
+class Shard:
+    """One rank's view of a limb-shard group (hml_shard, homulator_b200/csrc/shard.cu): every sharded op is ONE C-ABI call.
+    Build with Shard.ipc(ctx, max_L, rank, world, exchange) (one process per GPU) or Shard.local_group(ctxs, max_L)
+    (one process driving all ranks; emulation on a single GPU when the ctxs share a device)."""
 
-    Phase methods (begin / mid / end, rescale_begin / rescale_end) use separate signal and wait launches so that ranks emulated
-    on ONE stream can be interleaved phase by phase; keyswitch / hrotate / hmult are the one-rank-per-GPU compositions with
-    signal + wait fused into one launch per exchange."""
+    def __init__(self, ctx, max_L, rank, world):
+        self.ctx, self.max_L, self.rank, self.world = ctx, max_L, rank, world
+        self.h = C.c_void_p()
+        ctx._chk(ctx.lib.hml_shard_create(ctx.h, max_L, rank, world, C.byref(self.h)))
 
-    def __init__(self, ctx, L, rank, world, peers1, peers2, peer_flags, peers_r=None):
-        import torch
-        self.ctx, self.L, self.rank, self.world = ctx, L, rank, world
-        self.p1 = (C.c_void_p * world)(*peers1)
-        self.p2 = (C.c_void_p * world)(*peers2)
-        self.flags_own = peer_flags[rank]
-        self.pf_dev = torch.tensor(list(peer_flags), dtype=torch.int64, device="cuda")  # device array of the peers' flag blocks
-        self.g1_own, self.g2_own = peers1[rank], peers2[rank]
-        self.pr = list(peers_r) if peers_r is not None else None
-        self.epoch = 0      # key-switch exchanges
-        self.epoch_r = 0    # rescale exchanges
-        # True: the fused-sync compositions (keyswitch / rescale / hrotate / hmult) take their epochs from device-side counters
-        # (hml_shard_sync with epoch 0), so a CUDA graph captured around them can be replayed.  Do not mix with the phase
-        # methods on the same object.
-        self.device_epochs = False
-        self.lay = shard_layout(L, ctx.alpha, rank, world)
-        self.own = list(self.lay["own_q"])
-        self.nq = len(self.own)
-        self.nk = self.nq - (1 if (L - 1) % world == rank else 0)   # owned limbs that survive a rescale
+    @classmethod
+    def ipc(cls, ctx, max_L, rank, world, exchange):
+        """`exchange(obj)` returns the list of every rank's obj (torch.distributed.all_gather_object)."""
+        sh = cls(ctx, max_L, rank, world)
+        buf = C.create_string_buffer(256)
+        ctx._chk(ctx.lib.hml_shard_handles(sh.h, buf))
+        allh = exchange(bytes(buf.raw))
+        if world > 1:
+            ctx._chk(ctx.lib.hml_shard_connect_ipc(sh.h, b"".join(allh)))
+        return sh
+
+    @classmethod
+    def local_group(cls, ctxs, max_L):
+        world = len(ctxs)
+        group = [cls(c, max_L, r, world) for r, c in enumerate(ctxs)]
+        if world > 1:
+            arr = (C.c_void_p * world)(*[g.h for g in group])
+            ctxs[0]._chk(ctxs[0].lib.hml_shard_connect_local(arr, world))
+        return group
 
     def close(self):
-        """Unmap the peers' buffers and free this rank's (only for objects made by Context.shard_p2p_setup)."""
+        if self.h:
+            self.ctx.lib.hml_shard_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def own(self, L):
+        a, b = C.c_uint32(), C.c_uint32()
+        self.ctx._chk(self.ctx.lib.hml_shard_own_limbs(self.h, L, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def own_q(self, L):
+        return list(range(self.rank, L, self.world))
+
+    def own_ext(self, L):
+        return [e for e in range(L + self.ctx.alpha) if e % self.world == self.rank]
+
+    def prepare(self, L):
+        self.ctx._chk(self.ctx.lib.hml_shard_prepare(self.h, L))
+
+    def check(self):
+        self.ctx._chk(self.ctx.lib.hml_shard_check(self.h, self.ctx._stream()))
+
+    def keyswitch(self, L, d_own, evk_own, o0=None, o1=None):
         c = self.ctx
-        c._chk(c.lib.hml_sync(c.h, None))
-        for p in getattr(self, "_peer_ptrs", []):
-            c._chk(c.lib.hml_ipc_close(c.h, p))
-        for p in getattr(self, "_own_ptrs", []):
-            c._chk(c.lib.hml_dev_free(c.h, p))
-        self._peer_ptrs, self._own_ptrs = [], []
+        nq, _ = self.own(L)
+        o0 = c.empty(max(nq, 1), c.N) if o0 is None else o0
+        o1 = c.empty(max(nq, 1), c.N) if o1 is None else o1
+        c._chk(c.lib.hml_keyswitch_sharded(self.h, L, _ptr(d_own), _ptr(evk_own), _ptr(o0), _ptr(o1), c._stream()))
+        return o0[:nq], o1[:nq]
 
-    def reset_flags(self):
-        """Zero this rank's flag block and epochs (every rank must be idle and must do the same before the next exchange)."""
-        import numpy as np
+    def hrotate(self, L, ct_own, rk_own, g, out=None):
         c = self.ctx
-        n = 3 * self.world + 8
-        c._chk(c.lib.hml_sync(c.h, None))
-        z = np.zeros(n, dtype=np.uint64)
-        c._chk(c.lib.hml_h2d(c.h, self.flags_own, z.ctypes.data, n, None))
-        c._chk(c.lib.hml_sync(c.h, None))
-        self.epoch = self.epoch_r = 0
-
-    # ---- key switch
-    def begin(self, d_own):
-        c = self.ctx
-        self.epoch += 1
-        c._chk(c.lib.hml_keyswitch_shard_begin(c.h, self.L, self.rank, self.world, _ptr(d_own), self.g1_own, c._stream()))
-        c._chk(c.lib.hml_shard_signal(c.h, self.pf_dev.data_ptr(), self.rank, self.epoch, self.world, c._stream()))
-
-    def mid(self, d_own, evk_own):
-        c = self.ctx
-        c._chk(c.lib.hml_shard_wait(c.h, self.flags_own, 0, self.epoch, self.world, c._stream()))
-        if evk_own is not None:  # a rank that owns no limb still takes part in the flag protocol
-            c._chk(c.lib.hml_keyswitch_shard_mid_p2p(c.h, self.L, self.rank, self.world, _ptr(d_own), self.p1, _ptr(evk_own), self.g2_own,
-                                                     c._stream()))
-        c._chk(c.lib.hml_shard_signal(c.h, self.pf_dev.data_ptr(), self.world + self.rank, self.epoch, self.world, c._stream()))
-
-    def _outs(self, o0, o1):
-        c = self.ctx
-        return (c.empty(max(self.nq, 1), c.N) if o0 is None else o0), (c.empty(max(self.nq, 1), c.N) if o1 is None else o1)
-
-    def end(self, o0=None, o1=None):
-        c = self.ctx
-        o0, o1 = self._outs(o0, o1)
-        c._chk(c.lib.hml_shard_wait(c.h, self.flags_own, self.world, self.epoch, self.world, c._stream()))
-        c._chk(c.lib.hml_keyswitch_shard_end_p2p(c.h, self.L, self.rank, self.world, self.p2, _ptr(o0), _ptr(o1), c._stream()))
-        return o0[:self.nq], o1[:self.nq]
-
-    def keyswitch(self, d_own, evk_own, o0=None, o1=None):
-        """One rank per GPU: the whole key switch, signal + wait fused into one launch per exchange."""
-        c, st = self.ctx, self.ctx._stream()
-        self.epoch += 1
-        ep = 0 if self.device_epochs else self.epoch
-        o0, o1 = self._outs(o0, o1)
-        c._chk(c.lib.hml_keyswitch_shard_begin(c.h, self.L, self.rank, self.world, _ptr(d_own), self.g1_own, st))
-        c._chk(c.lib.hml_shard_sync(c.h, self.pf_dev.data_ptr(), self.rank, self.flags_own, 0, ep, self.world, st))
-        if evk_own is not None:
-            c._chk(c.lib.hml_keyswitch_shard_mid_p2p(c.h, self.L, self.rank, self.world, _ptr(d_own), self.p1, _ptr(evk_own), self.g2_own, st))
-        c._chk(c.lib.hml_shard_sync(c.h, self.pf_dev.data_ptr(), self.world + self.rank, self.flags_own, self.world, ep, self.world, st))
-        c._chk(c.lib.hml_keyswitch_shard_end_p2p(c.h, self.L, self.rank, self.world, self.p2, _ptr(o0), _ptr(o1), st))
-        return o0[:self.nq], o1[:self.nq]
-
-    # ---- limb-local pieces of the ops (element-wise kernels over the owned limbs)
-    def _ew(self, x1, x2, x3, x4, comps, out=None):
-        return self.ctx.ewe(x1, x2, x3, x4, self.own * comps, out=out)
-
-    def hadd(self, a, b):
-        return self._ew(a.view(-1, self.ctx.N), None, b.view(-1, self.ctx.N), None, 2).view(2, self.nq, self.ctx.N)
-
-    def pmult(self, ct, pt2):
-        """pt2 = the plaintext's owned limbs repeated for both components, [2][nq][N]."""
-        return self._ew(ct.view(-1, self.ctx.N), pt2.view(-1, self.ctx.N), None, None, 2).view(2, self.nq, self.ctx.N)
-
-    def padd(self, ct, pt2):
-        return self._ew(ct.view(-1, self.ctx.N), None, pt2.view(-1, self.ctx.N), None, 2).view(2, self.nq, self.ctx.N)
-
-    def hrotate_pre(self, ct, g):
-        return self.ctx.automorph(ct.view(-1, self.ctx.N), g).view(2, self.nq, self.ctx.N)
-
-    def hrotate_post(self, sig, k0, out):
-        self._ew(sig[0], None, k0, None, 1, out=out[0])   # out[1] was written by the key switch itself
+        nq, _ = self.own(L)
+        out = c.empty(2, max(nq, 1), c.N) if out is None else out
+        c._chk(c.lib.hml_hrotate_sharded(self.h, L, _ptr(ct_own), _ptr(rk_own), g, _ptr(out), c._stream()))
         return out
 
-    def hmult_pre(self, a, b):
-        d0 = self._ew(a[0], b[0], None, None, 1)
-        d1 = self._ew(a[0], b[1], a[1], b[0], 1)
-        d2 = self._ew(a[1], b[1], None, None, 1)
-        return d0, d1, d2
-
-    def hmult_post(self, d0, d1, k0, k1):
-        c = self.ctx.empty(2, self.nq, self.ctx.N)
-        self._ew(d0, None, k0, None, 1, out=c[0])
-        self._ew(d1, None, k1, None, 1, out=c[1])
-        return c
-
-    # ---- rescale
-    def rescale_begin(self, x):
+    def hmult(self, L, a_own, b_own, evk_own, out=None):
         c = self.ctx
-        self.epoch_r += 1
-        c._chk(c.lib.hml_rescale_shard_begin(c.h, self.L, self.rank, self.world, _ptr(x), self.pr[self.rank], c._stream()))
-        c._chk(c.lib.hml_shard_signal(c.h, self.pf_dev.data_ptr(), 2 * self.world + self.rank, self.epoch_r, self.world, c._stream()))
+        _, nk = self.own(L)
+        out = c.empty(2, max(nk, 1), c.N) if out is None else out
+        c._chk(c.lib.hml_hmult_sharded(self.h, L, _ptr(a_own), _ptr(b_own), _ptr(evk_own), _ptr(out), c._stream()))
+        return out
 
-    def rescale_end(self, x):
+    def rescale(self, L, x_own, out=None):
         c = self.ctx
-        out = c.empty(2, max(self.nk, 1), c.N)
-        c._chk(c.lib.hml_shard_wait(c.h, self.flags_own, 2 * self.world, self.epoch_r, self.world, c._stream()))
-        c._chk(c.lib.hml_rescale_shard_end(c.h, self.L, self.rank, self.world, _ptr(x), self.pr[(self.L - 1) % self.world], _ptr(out),
-                                           c._stream()))
-        return out[:, :self.nk]
+        _, nk = self.own(L)
+        out = c.empty(2, max(nk, 1), c.N) if out is None else out
+        c._chk(c.lib.hml_rescale_sharded(self.h, L, _ptr(x_own), _ptr(out), c._stream()))
+        return out
 
-    def rescale(self, x):
-        c, st = self.ctx, self.ctx._stream()
-        self.epoch_r += 1
-        out = c.empty(2, max(self.nk, 1), c.N)
-        c._chk(c.lib.hml_rescale_shard_begin(c.h, self.L, self.rank, self.world, _ptr(x), self.pr[self.rank], st))
-        c._chk(c.lib.hml_shard_sync(c.h, self.pf_dev.data_ptr(), 2 * self.world + self.rank, self.flags_own, 2 * self.world,
-                                    0 if self.device_epochs else self.epoch_r, self.world, st))
-        c._chk(c.lib.hml_rescale_shard_end(c.h, self.L, self.rank, self.world, _ptr(x), self.pr[(self.L - 1) % self.world], _ptr(out), st))
-        return out[:, :self.nk]
+    def ew(self, L, kind, a_own, b_own, out=None):
+        c = self.ctx
+        out = c.empty(*a_own.shape) if out is None else out
+        c._chk(c.lib.hml_ew_sharded(self.h, L, {"hadd": 0, "pmult": 1, "padd": 2}[kind], _ptr(a_own), _ptr(b_own), _ptr(out), c._stream()))
+        return out
 
-    # ---- whole ops, one rank per GPU
-    def hrotate(self, ct, rk_own, g):
-        sig = self.hrotate_pre(ct, g)
-        out = self.ctx.empty(2, self.nq, self.ctx.N)
-        k0, _ = self.keyswitch(sig[1], rk_own, o1=out[1])
-        return self.hrotate_post(sig, k0, out)
 
-    def hmult(self, a, b, evk_own):
-        d0, d1, d2 = self.hmult_pre(a, b)
-        k0, k1 = self.keyswitch(d2, evk_own)
-        return self.rescale(self.hmult_post(d0, d1, k0, k1))
+def group_op(group, kind, L, a, b=None, key=None, out0=None, out1=None, galois_elt=0, streams=None):
+    """hml_group_op: all ranks of a local group, one host thread.  kind in keyswitch / hrotate / hmult / rescale; every
+    operand is a list indexed by rank (None entries allowed for ranks that own nothing)."""
+    import torch
+    world = len(group)
+    ctx = group[0].ctx
+
+    def arr(lst):
+        if lst is None:
+            return None
+        return (C.c_void_p * world)(*[(_ptr(t) if t is not None else None) for t in lst])
+
+    if streams is None:
+        st = torch.cuda.current_stream(ctx.device).cuda_stream
+        streams = [st] * world
+    gh = (C.c_void_p * world)(*[g.h for g in group])
+    sa = (C.c_void_p * world)(*streams)
+    rc = ctx.lib.hml_group_op(gh, world, {"keyswitch": 0, "hrotate": 1, "hmult": 2, "rescale": 3}[kind], L, arr(a), arr(b), arr(key),
+                              arr(out0), arr(out1), galois_elt, sa)
+    if rc:
+        msgs = [g.ctx.lib.hml_last_error(g.ctx.h).decode() for g in group]
+        raise HmlError(rc, next((m for m in msgs if m), "group op failed"))
+
+
+class Replay:
+    """hml_replay: a trace of (kind, dst, a, b) tuples over named ciphertexts, run through the C ABI (optionally as one CUDA
+    graph, optionally with hoisted rotations, optionally limb-sharded).  `trace` uses the tuple format of
+    homulator_b200.replay; names are mapped to slots here ("x" = slot 0 = the input)."""
+    KINDS = {"hrotate": 0, "pmult": 1, "hadd": 2, "padd": 3, "hmult": 4}
+
+    def __init__(self, ctx, L, trace, shard=None, graph=False, hoist=False):
+        self.ctx, self.L, self.shard = ctx, L, shard
+        self.names = {"x": 0}
+        ops = []
+        for op in trace:
+            kind, dst, a, b = op
+            if a not in self.names:
+                raise ValueError("trace reads %r before it is written" % (a,))
+            if kind in ("hadd", "hmult"):
+                if b not in self.names:
+                    raise ValueError("trace reads %r before it is written" % (b,))
+                bb = self.names[b]
+            else:
+                bb = int(b)
+            if dst not in self.names:
+                self.names[dst] = len(self.names)
+            ops.append((self.KINDS[kind], self.names[dst], self.names[a], bb))
+        arr = (_TraceOp * len(ops))(*[_TraceOp(*o) for o in ops])
+        self.h = C.c_void_p()
+        flags = (1 if graph else 0) | (2 if hoist else 0)
+        ctx._chk(ctx.lib.hml_replay_create(ctx.h, shard.h if shard is not None else None, L, arr, len(ops), flags, C.byref(self.h)))
+        self._keep = None
+
+    def bind(self, x, plaintexts, rot_keys, evk, evk_q_limbs=None):
+        """plaintexts: dict / list idx -> tensor; rot_keys: dict rotation amount -> key tensor."""
+        c = self.ctx
+        n_pt = (max(plaintexts.keys()) + 1) if isinstance(plaintexts, dict) and plaintexts else len(plaintexts or [])
+        get = (lambda i: plaintexts.get(i)) if isinstance(plaintexts, dict) else (lambda i: plaintexts[i])
+        pts = (C.c_void_p * max(n_pt, 1))(*[(_ptr(get(i)) if get(i) is not None else None) for i in range(n_pt)])
+        rots = sorted(rot_keys.keys())
+        ra = (C.c_uint32 * max(len(rots), 1))(*rots)
+        ka = (C.c_void_p * max(len(rots), 1))(*[_ptr(rot_keys[r]) for r in rots])
+        self._keep = (x, plaintexts, rot_keys, evk)
+        c._chk(c.lib.hml_replay_bind(self.h, _ptr(x), pts, n_pt, ra, ka, len(rots), _ptr(evk), evk_q_limbs or self.L))
+        return self
+
+    def run(self):
+        self.ctx._chk(self.ctx.lib.hml_replay_run(self.h, self.ctx._stream()))
+        return self
+
+    def result(self, name):
+        """Device tensor view [2][n_limbs][N] of a named ciphertext (owned by the replay object; valid until close())."""
+        import torch
+        p, n = C.c_void_p(), C.c_uint32()
+        self.ctx._chk(self.ctx.lib.hml_replay_slot(self.h, self.names[name], C.byref(p), C.byref(n)))
+        return _tensor_view(p.value, (2, n.value, self.ctx.N), self.ctx.device, self)
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.hml_replay_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class _DevArray:
+    """__cuda_array_interface__ holder so torch can view library-owned device memory without copying."""
+
+    def __init__(self, ptr, shape, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<i8", "data": (ptr, False), "version": 3, "strides": None}
+
+
+def _tensor_view(ptr, shape, device, owner):
+    import torch
+    if 0 in shape:
+        return torch.empty(*shape, dtype=torch.int64, device=device)
+    return torch.as_tensor(_DevArray(ptr, shape, owner), device=device)
 
 
 class _Op:

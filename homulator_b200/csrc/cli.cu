@@ -91,12 +91,12 @@ static int fill(hml_ctx *ctx, u64 *dev, const std::vector<u64> &limb_mod, u64 se
 extern "C" int hml_cli_main(int argc, char **argv) {
   if (argc < 6) {
     fprintf(stderr, "Usage: %s <configfile> <operationName> <maxExecutionLevel> <currentLevel> <alpha> [cluster]"
-                    " [--iters K] [--warmup W] [--rot R] [--device D] [--no-flush]\n", argv[0]);
+                    " [--iters K] [--warmup W] [--rot R] [--device D] [--no-flush] [--verify]\n", argv[0]);
     return 1;
   }
   const std::string path = argv[1], op = argv[2];
   const uint32_t maxl = (uint32_t)std::atoi(argv[3]), L = (uint32_t)std::atoi(argv[4]), alpha = (uint32_t)std::atoi(argv[5]);
-  int iters = 20, warmup = 3, rot = 1, device = 0, flush = 1, argi = 6;
+  int iters = 20, warmup = 3, rot = 1, device = 0, flush = 1, verify = 0, argi = 6;
   long cluster = -1;
   if (argi < argc && argv[argi][0] != '-') cluster = std::atol(argv[argi++]);  // accepted like the reference (bench_micro24.cpp:23-25)
   for (; argi < argc; ++argi) {
@@ -107,6 +107,7 @@ extern "C" int hml_cli_main(int argc, char **argv) {
     else if (f == "--rot") val(rot);
     else if (f == "--device") val(device);
     else if (f == "--no-flush") flush = 0;
+    else if (f == "--verify") verify = 1;
   }
   CfgFile cfg;
   std::string err;
@@ -266,18 +267,113 @@ extern "C" int hml_cli_main(int argc, char **argv) {
     printf("HBM_(0) :\t%.1f GB/s algorithmic over %.2f us serialised (%.1f%% of peak)\n", prof.total_us > 0 ? bytes / (prof.total_us * 1e-6) / 1e9 : 0.0,
            prof.total_us, prof.total_us > 0 ? 100.0 * bytes / (prof.total_us * 1e-6) / 1e9 / peak : 0.0);
   }
+  // ---- [cluster] (reference bench_micro24.cpp:23-25 overrides the number of compute clusters, to which the reference maps
+  // limb l as l % cluster, include/Driver.h:158,:178): here the cluster count is the limb-shard world.  With cluster >= 2 and
+  // that many (or fewer: clipped) visible GPUs, hmult / hrotate run once more limb-sharded over the GPUs, one rank per device,
+  // all driven from this process (hml_group_op), and the time is reported next to the one-GPU figure.
+  int n_dev = 0;
+  cudaGetDeviceCount(&n_dev);
+  const int gpus = (cluster >= 2 && (op == "hmult" || op == "hrotate")) ? (int)std::min<long>(cluster, n_dev) : 1;
+  double sharded_us = 0.0;
+  int sharded_ok = -1;
+  if (gpus >= 2) {
+    const uint32_t W = (uint32_t)gpus, Lout = op == "hmult" ? L - 1 : L;
+    std::vector<hml_ctx *> cx(W, nullptr);
+    std::vector<hml_shard *> sh(W, nullptr);
+    std::vector<uint64_t *> a_own(W, nullptr), b_own(W, nullptr), key_own(W, nullptr), out_own(W, nullptr);
+    std::vector<cudaStream_t> st(W, nullptr);
+    int src = 0;
+    for (uint32_t r = 0; r < W && !src; ++r) {
+      src = hml_ctx_create(path.c_str(), maxl, alpha, (device + (int)r) % n_dev, &cx[r]);
+      if (!src) src = hml_shard_create(cx[r], L, r, W, &sh[r]);
+    }
+    if (!src) src = hml_shard_connect_local(sh.data(), W);
+    for (uint32_t r = 0; r < W && !src; ++r) {
+      src = hml_shard_prepare(sh[r], L);
+      cudaSetDevice(cx[r]->device);
+      cudaStreamCreateWithFlags(&st[r], cudaStreamNonBlocking);
+      // this rank's limbs of the operands: ciphertexts [2][nq][N], key [beta][2][n_own_ext][N]
+      std::vector<uint32_t> oq, oe;
+      for (uint32_t i = r; i < L; i += W) oq.push_back(i);
+      for (uint32_t e = r; e < E; e += W) oe.push_back(e);
+      const size_t nq = oq.size(), ne = oe.size();
+      cudaMalloc(&a_own[r], std::max<size_t>(1, 2 * nq) * N * 8);
+      cudaMalloc(&b_own[r], std::max<size_t>(1, 2 * nq) * N * 8);
+      cudaMalloc(&out_own[r], std::max<size_t>(1, 2 * nq) * N * 8);
+      cudaMalloc(&key_own[r], std::max<size_t>(1, 2 * beta * ne) * N * 8);
+      for (int c = 0; c < 2; ++c)
+        for (size_t k = 0; k < nq; ++k) {
+          cudaMemcpy(a_own[r] + (c * nq + k) * N, a + ((size_t)c * L + oq[k]) * N, N * 8, cudaMemcpyDefault);
+          cudaMemcpy(b_own[r] + (c * nq + k) * N, b + ((size_t)c * L + oq[k]) * N, N * 8, cudaMemcpyDefault);
+        }
+      for (uint32_t jc = 0; jc < 2 * beta; ++jc)
+        for (size_t k = 0; k < ne; ++k) cudaMemcpy(key_own[r] + (jc * ne + k) * N, key + ((size_t)jc * E + oe[k]) * N, N * 8, cudaMemcpyDefault);
+      if (cudaDeviceSynchronize() != cudaSuccess) src = HML_ERR_CUDA;
+    }
+    const int kind = op == "hmult" ? 2 : 1;
+    auto run_sharded = [&]() -> int {
+      return hml_group_op(sh.data(), W, kind, L, (const uint64_t *const *)a_own.data(), (const uint64_t *const *)b_own.data(),
+                          (const uint64_t *const *)key_own.data(), out_own.data(), nullptr, g, (void *const *)st.data());
+    };
+    auto sync_all = [&]() { for (uint32_t r = 0; r < W; ++r) { cudaSetDevice(cx[r]->device); cudaStreamSynchronize(st[r]); } };
+    for (int i = 0; i < warmup + 1 && !src; ++i) src = run_sharded();
+    sync_all();
+    if (!src) {
+      std::vector<double> ts;
+      for (int i = 0; i < iters && !src; ++i) {
+        const double t_0 = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e6 + t.tv_nsec * 1e-3; }();
+        src = run_sharded();
+        sync_all();
+        const double t_1 = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e6 + t.tv_nsec * 1e-3; }();
+        ts.push_back(t_1 - t_0);
+      }
+      std::sort(ts.begin(), ts.end());
+      if (!ts.empty()) sharded_us = ts[ts.size() / 2];
+    }
+    for (uint32_t r = 0; r < W && !src; ++r) src = hml_shard_check(sh[r], st[r]);
+    if (!src && verify) {  // the sharded result must equal the one-GPU result limb by limb
+      cudaSetDevice(device);
+      run();
+      cudaDeviceSynchronize();
+      std::vector<uint64_t> h1(N), h2(N);
+      sharded_ok = 1;
+      for (uint32_t r = 0; r < W && sharded_ok == 1; ++r) {
+        std::vector<uint32_t> keep;
+        for (uint32_t i = r; i < Lout; i += W) keep.push_back(i);
+        for (int c = 0; c < 2 && sharded_ok == 1; ++c)
+          for (size_t k = 0; k < keep.size(); ++k) {
+            cudaMemcpy(h1.data(), out + ((size_t)c * Lout + keep[k]) * N, N * 8, cudaMemcpyDefault);
+            cudaMemcpy(h2.data(), out_own[r] + (c * keep.size() + k) * N, N * 8, cudaMemcpyDefault);
+            if (memcmp(h1.data(), h2.data(), N * 8) != 0) { sharded_ok = 0; break; }
+          }
+      }
+    }
+    if (src) fprintf(stderr, "homulator_b200: limb-sharded run over %d GPUs failed: %s\n", gpus, cx[0] ? hml_last_error(cx[0]) : hml_last_create_error());
+    else printf("%s limb-sharded over %d GPUs (cluster = %ld)\t%.2f us (median of %d, host clock around all ranks)%s\n\n", OP.c_str(), gpus, cluster,
+                sharded_us, iters, sharded_ok == 1 ? ", result identical to the one-GPU run" : sharded_ok == 0 ? ", RESULT DIFFERS from the one-GPU run" : "");
+    for (uint32_t r = 0; r < W; ++r) {
+      if (cx[r]) cudaSetDevice(cx[r]->device);
+      cudaFree(a_own[r]); cudaFree(b_own[r]); cudaFree(key_own[r]); cudaFree(out_own[r]);
+      if (st[r]) cudaStreamDestroy(st[r]);
+      hml_shard_destroy(sh[r]);
+      hml_ctx_destroy(cx[r]);
+    }
+    cudaSetDevice(device);
+    if (src || sharded_ok == 0) { hml_ctx_destroy(ctx); return 7; }
+  }
   printf("{\"op\": \"%s\", \"N\": %u, \"maxLevel\": %u, \"L\": %u, \"alpha\": %u, \"us_median\": %.3f, \"us_min\": %.3f, \"iters\": %d, "
          "\"l2_flushed\": %s, \"algorithmic_bytes\": %.0f, \"achieved_gbs\": %.2f, \"hbm_frac_of_measured\": %.4f, "
          "\"trace\": {\"NTT\": %llu, \"INTT\": %llu, \"MULT\": %llu, \"BCONV_STEP2\": %llu, \"AUTO\": %llu, \"total\": %llu, \"driverTotal\": %llu}, "
          "\"executed\": {\"ntt_limbs\": %llu, \"intt_limbs\": %llu, \"ewe_limbs\": %llu, \"bconv_limb_macs\": %llu, \"auto_limbs\": %llu, "
          "\"kernel_launches\": %llu}, \"class_us\": {\"NTT\": %.2f, \"INTT\": %.2f, \"BCONV\": %.2f, \"EWE\": %.2f, \"AUTO\": %.2f}, \"hbm_peak_gbs\": %.1f, "
-         "\"hbm_peak_source\": \"%s\", \"cluster\": %ld, \"gpu\": \"%s\"}\n",
+         "\"hbm_peak_source\": \"%s\", \"cluster\": %ld, \"gpus_used\": %d, \"sharded_us_median\": %.3f, \"sharded_matches_one_gpu\": %s, \"gpu\": \"%s\"}\n",
          op.c_str(), p.N, maxl, L, alpha, med, mn, iters, flush ? "true" : "false", bytes, gbs, gbs / peak,
          (unsigned long long)cnt.ntt, (unsigned long long)cnt.intt, (unsigned long long)cnt.mult, (unsigned long long)cnt.bconv_step2,
          (unsigned long long)cnt.automorph, (unsigned long long)cnt.total, (unsigned long long)cnt.driver_total,
          (unsigned long long)ex.ntt_limbs, (unsigned long long)ex.intt_limbs, (unsigned long long)ex.ewe_limbs,
          (unsigned long long)ex.bconv_limb_macs, (unsigned long long)ex.automorph_limbs, (unsigned long long)ex.kernel_launches,
-         prof.us[0], prof.us[1], prof.us[2], prof.us[3], prof.us[4], peak, peak_src.c_str(), cluster, prop.name);
+         prof.us[0], prof.us[1], prof.us[2], prof.us[3], prof.us[4], peak, peak_src.c_str(), cluster, gpus, sharded_us,
+         sharded_ok == 1 ? "true" : sharded_ok == 0 ? "false" : "null", prop.name);
   cudaFree(a); cudaFree(b); cudaFree(out); cudaFree(key); cudaFree(flushbuf);
   hml_ctx_destroy(ctx);
   return 0;

@@ -10,6 +10,7 @@
 #include <cstring>
 
 #include "launch.h"
+#include "ops.h"
 #include "planner.h"
 
 using namespace hml;
@@ -25,7 +26,7 @@ static thread_local std::string g_create_err;
     }                                                                                              \
   } while (0)
 
-static int fail(hml_ctx *ctx, int code, const std::string &msg) {
+int fail(hml_ctx *ctx, int code, const std::string &msg) {
   ctx->err = msg;
   return code;
 }
@@ -287,7 +288,7 @@ extern "C" int hml_host_alloc_pinned(hml_ctx *ctx, uint64_t n_words, uint64_t **
 }
 extern "C" int hml_host_free_pinned(hml_ctx *ctx, uint64_t *ptr) { CU_TRY(ctx, cudaFreeHost(ptr)); return HML_OK; }
 
-static int ensure_ws(hml_ctx *ctx, size_t words) {
+int ensure_ws(hml_ctx *ctx, size_t words) {
   if (ctx->ws_words >= words) return HML_OK;
   // growing the workspace must not race with work already queued on it
   CU_TRY(ctx, cudaDeviceSynchronize());
@@ -298,24 +299,24 @@ static int ensure_ws(hml_ctx *ctx, size_t words) {
   return HML_OK;
 }
 
-static int check_launch(hml_ctx *ctx, const char *what) {
+int check_launch(hml_ctx *ctx, const char *what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { ctx->err = std::string(what) + ": " + cudaGetErrorString(e); return HML_ERR_CUDA; }
   return HML_OK;
 }
 
-static void clear_map(LimbMap &lm) {
+void clear_map(LimbMap &lm) {
   memset(&lm, 0, sizeof(lm));
   memset(lm.skip, 0xFF, sizeof(lm.skip));
 }
 
-static void id_map(LimbMap &lm, const uint32_t *mod_idx, uint32_t n) {
+void id_map(LimbMap &lm, const uint32_t *mod_idx, uint32_t n) {
   clear_map(lm);
   for (uint32_t i = 0; i < n; ++i) { lm.mod[i] = (uint16_t)mod_idx[i]; lm.pos[i] = (uint16_t)i; }
 }
 
 // ------------------------------------------------------------------------------------------------ per-level constants
-static int get_level(hml_ctx *ctx, uint32_t L, LevelConsts **out) {
+int get_level(hml_ctx *ctx, uint32_t L, LevelConsts **out) {
   auto it = ctx->levels.find(L);
   if (it != ctx->levels.end()) { *out = &it->second; return HML_OK; }
   const Params &p = ctx->p;
@@ -422,7 +423,7 @@ static int get_level(hml_ctx *ctx, uint32_t L, LevelConsts **out) {
   return HML_OK;
 }
 
-static int check_level(hml_ctx *ctx, uint32_t L, uint32_t min_level) {
+int check_level(hml_ctx *ctx, uint32_t L, uint32_t min_level) {
   if (!ctx) return HML_ERR_INVALID;
   if (L < min_level || L > ctx->p.max_level) return fail(ctx, HML_ERR_INVALID, "currentLevel out of range");
   return HML_OK;
@@ -568,25 +569,14 @@ extern "C" int hml_bconv(hml_ctx *ctx, const uint64_t *in, const uint32_t *src_i
 }
 
 // ------------------------------------------------------------------------------------------------ key switch
-static size_t ks_ws_words(const Params &p, uint32_t L) {
+size_t ks_ws_words(const Params &p, uint32_t L) {
   const size_t N = p.N, E = L + p.alpha;
   return N * (L + (size_t)p.beta(L) * E + 2 * E + 2 * (size_t)L);
 }
 
-// Strided view of `nb` independent polynomials / ciphertext halves: item b lives at ptr + b * stride (words).
-struct BatchPtr {
-  const u64 *ptr;
-  long long stride;
-};
-struct BatchOut {
-  u64 *ptr;
-  long long stride;
-};
 
-// K1..K7: ModUp (INTT, base conversion, NTT), inner product with the key, INTT (+ step-1 scaling) of the P-limbs of both
-// accumulators.  Buffers: yb [nb][L] | ext [nb][beta][E] | acc [nb][2][AL] with AL >= E limbs per accumulator.
-static int ks_front(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d, const u64 *evk, uint32_t evk_q_limbs, u64 *yb,
-                    u64 *ext, u64 *acc, uint32_t AL, cudaStream_t s) {
+// K1..K4: ModUp (INTT + digit scaling, base conversion, NTT of the converted limbs).  Buffers: yb [nb][L] | ext [nb][beta][E].
+int ks_modup(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d, u64 *yb, u64 *ext, cudaStream_t s) {
   const Params &p = ctx->p;
   const size_t N = p.N;
   const uint32_t A = p.alpha, E = L + A, beta = lc->beta;
@@ -621,6 +611,17 @@ static int ks_front(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, Batc
     prof_mark(ctx, HML_CLS_NTT, s);
     ctx->exec.ntt_limbs += (uint64_t)nb * ((uint64_t)beta * E - L); ctx->exec.kernel_launches += npass;
   }
+  return HML_OK;
+}
+
+// K5..K7: inner product with the key, INTT (+ step-1 scaling) of the P-limbs of both accumulators.  acc [nb][2][AL], AL >= E.
+// galois != 0: the digits are read through the automorphism X -> X^galois (hoisted rotation, see InnerArgs::galois).
+int ks_inner(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d, const u64 *evk, uint32_t evk_q_limbs, const u64 *ext, u64 *acc,
+             uint32_t AL, u64 galois, cudaStream_t s) {
+  const Params &p = ctx->p;
+  const size_t N = p.N;
+  const uint32_t A = p.alpha, E = L + A, beta = lc->beta;
+  const int logN = p.logN, npass = logN <= NTT_SMALL_LOG ? 1 : 2;
   // K5 (reference :294-414): inner product with the key (key words loaded once per batch)
   {
     LimbMap ip = lc->ext_lm;  // pos = limb index inside the key (Q-limbs first, then P-limbs after evk_q_limbs)
@@ -630,6 +631,8 @@ static int ks_front(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, Batc
     a.n_batch = nb; a.d_batch_stride = d.stride; a.ext_batch_stride = (long long)beta * E * N; a.acc_batch_stride = 2ll * AL * N;
     a.acc_comp_stride = (long long)AL * N; a.ext_f64 = npass == 2;
     a.acc_pack_limbs = npass == 2 ? (int)L : 0;  // Q-limb accumulators only feed element-wise epilogues: packed (5 B / coefficient)
+    a.galois = (unsigned)(galois & (2ull * N - 1)); a.logN = logN;
+    if (a.galois == 1) a.galois = 0;
     launch_inner_product(ctx->mc, ip, a, s);
     prof_mark(ctx, HML_CLS_EWE, s);
     ctx->exec.ewe_limbs += 2ull * nb * E * beta; ctx->exec.kernel_launches++;
@@ -647,22 +650,21 @@ static int ks_front(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, Batc
   return HML_OK;
 }
 
-// nb independent key switches sharing one key, one kernel launch per stage:
-// d[b] [L][N] -> out_c[b] = KS_c(d[b]) (+ add_c[b]).  `ws` must hold nb * ks_ws_words().
-static int ks_run(hml_ctx *ctx, uint32_t L, uint32_t nb, BatchPtr d, const u64 *evk, uint32_t evk_q_limbs, BatchOut out0,
-                  BatchOut out1, BatchPtr add0, BatchPtr add1, u64 *ws, cudaStream_t s) {
-  const Params &p = ctx->p;
-  if (evk_q_limbs < L || evk_q_limbs > p.max_level) return fail(ctx, HML_ERR_INVALID, "evk_q_limbs must be in [L, maxLevel]");
-  LevelConsts *lc;
-  int rc = get_level(ctx, L, &lc);
+// K1..K7.  Buffers: yb [nb][L] | ext [nb][beta][E] | acc [nb][2][AL] with AL >= E limbs per accumulator.
+int ks_front(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d, const u64 *evk, uint32_t evk_q_limbs, u64 *yb,
+             u64 *ext, u64 *acc, uint32_t AL, cudaStream_t s) {
+  int rc = ks_modup(ctx, lc, L, nb, d, yb, ext, s);
   if (rc) return rc;
+  return ks_inner(ctx, lc, L, nb, d, evk, evk_q_limbs, ext, acc, AL, 0, s);
+}
+
+// K8..K10 (+ the caller's addends): ModDown of nb accumulator pairs acc [nb][2][E] -> out_c[b] = (acc_c - NTT(BConv(acc_c; P -> Q))) * P^-1 (+ add_c[b])
+int ks_tail(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, u64 *acc, u64 *vb, BatchOut out0, BatchOut out1, BatchPtr add0, BatchPtr add1,
+            cudaStream_t s) {
+  const Params &p = ctx->p;
   const size_t N = p.N;
-  const uint32_t A = p.alpha, E = L + A, beta = lc->beta;
-  if (beta > 8) return fail(ctx, HML_ERR_UNSUPPORTED, "more than 8 key-switch digits (ceil(L/alpha) > 8)");
-  // workspace, every buffer batch-major: yb [nb][L] | ext [nb][beta][E] | acc [nb][2][E] | vb [nb][2][L]  (limbs of N words)
-  u64 *yb = ws, *ext = yb + (size_t)nb * L * N, *acc = ext + (size_t)nb * beta * E * N, *vb = acc + (size_t)nb * 2 * E * N;
+  const uint32_t A = p.alpha, E = L + A;
   const int logN = p.logN, npass = logN <= NTT_SMALL_LOG ? 1 : 2;
-  if ((rc = ks_front(ctx, lc, L, nb, d, evk, evk_q_limbs, yb, ext, acc, E, s))) return rc;
   // K8 (reference :489-519): P -> Q_L
   {
     BConvArgs a{};
@@ -710,6 +712,24 @@ static int ks_run(hml_ctx *ctx, uint32_t L, uint32_t nb, BatchPtr d, const u64 *
   return check_launch(ctx, "keyswitch");
 }
 
+// nb independent key switches sharing one key, one kernel launch per stage:
+// d[b] [L][N] -> out_c[b] = KS_c(d[b]) (+ add_c[b]).  `ws` must hold nb * ks_ws_words().
+int ks_run(hml_ctx *ctx, uint32_t L, uint32_t nb, BatchPtr d, const u64 *evk, uint32_t evk_q_limbs, BatchOut out0,
+           BatchOut out1, BatchPtr add0, BatchPtr add1, u64 *ws, cudaStream_t s) {
+  const Params &p = ctx->p;
+  if (evk_q_limbs < L || evk_q_limbs > p.max_level) return fail(ctx, HML_ERR_INVALID, "evk_q_limbs must be in [L, maxLevel]");
+  LevelConsts *lc;
+  int rc = get_level(ctx, L, &lc);
+  if (rc) return rc;
+  const size_t N = p.N;
+  const uint32_t A = p.alpha, E = L + A, beta = lc->beta;
+  if (beta > 8) return fail(ctx, HML_ERR_UNSUPPORTED, "more than 8 key-switch digits (ceil(L/alpha) > 8)");
+  // workspace, every buffer batch-major: yb [nb][L] | ext [nb][beta][E] | acc [nb][2][E] | vb [nb][2][L]  (limbs of N words)
+  u64 *yb = ws, *ext = yb + (size_t)nb * L * N, *acc = ext + (size_t)nb * beta * E * N, *vb = acc + (size_t)nb * 2 * E * N;
+  if ((rc = ks_front(ctx, lc, L, nb, d, evk, evk_q_limbs, yb, ext, acc, E, s))) return rc;
+  return ks_tail(ctx, lc, L, nb, acc, vb, out0, out1, add0, add1, s);
+}
+
 extern "C" int hml_keyswitch(hml_ctx *ctx, uint32_t L, const uint64_t *d, const uint64_t *evk, uint32_t evk_q_limbs,
                              uint64_t *out0, uint64_t *out1, void *stream) {
   int rc = check_level(ctx, L, 1);
@@ -736,7 +756,7 @@ extern "C" int hml_keyswitch(hml_ctx *ctx, uint32_t L, const uint64_t *d, const 
 //   end:    BConv P -> owned Q-limbs, NTT, (acc - v) * P^-1 for the owned Q-limbs
 // The collective itself is issued by the caller (NCCL all-gather on the same stream; homulator_b200/api.py uses
 // torch.distributed) so the library stays free of a communicator dependency.
-static int get_shard_plan(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, ShardPlan **out) {
+int get_shard_plan(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, ShardPlan **out) {
   const uint64_t key = ((uint64_t)L << 32) | ((uint64_t)world << 16) | rank;
   auto it = ctx->shard_plans.find(key);
   if (it != ctx->shard_plans.end()) { *out = &it->second; return HML_OK; }
@@ -820,12 +840,12 @@ static int get_shard_plan(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t worl
   return HML_OK;
 }
 
-static size_t shard_ws_words(const Params &p, const ShardPlan &sp) {
+size_t shard_ws_words(const Params &p, const ShardPlan &sp) {
   const size_t ne = sp.own_q.size() + sp.own_p.size(), nq = sp.own_q.size();
   return (size_t)p.N * ((size_t)sp.beta * ne + 2 * ne + 2 * nq);
 }
 
-static int shard_check(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world) {
+int shard_check(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world) {
   int rc = check_level(ctx, L, 1);
   if (rc) return rc;
   if (world == 0 || rank >= world || world > 64) return fail(ctx, HML_ERR_INVALID, "bad rank / world");
@@ -936,7 +956,8 @@ extern "C" int hml_keyswitch_shard_mid(hml_ctx *ctx, uint32_t L, uint32_t rank, 
 }
 
 // last phase: BConv P -> owned Q-limbs (sources in `gather2`, or at src_off relative to it), NTT, (acc - v) * P^-1
-static int shard_end_run(hml_ctx *ctx, ShardPlan *sp, const u64 *gather2, const long long *src_off, u64 *out0_own, u64 *out1_own, cudaStream_t s) {
+static int shard_end_run(hml_ctx *ctx, ShardPlan *sp, const u64 *gather2, const long long *src_off, u64 *out0_own, u64 *out1_own, cudaStream_t s,
+                         const u64 *add0_own = nullptr, const u64 *add1_own = nullptr) {
   int rc;
   if ((rc = ensure_ws(ctx, shard_ws_words(ctx->p, *sp)))) return rc;
   ws_enter(ctx, s);
@@ -966,6 +987,11 @@ static int shard_end_run(hml_ctx *ctx, ShardPlan *sp, const u64 *gather2, const 
     a.x = acc; a.x_poly_stride = (long long)ne * N; a.y = vb; a.y_poly_stride = (long long)nq * N; a.z = nullptr;
     a.out = out0_own; a.out_poly_stride = (long long)(out1_own - out0_own);
     a.cst = sp->pinv; a.N = N; a.n_limbs = nq; a.n_polys = 2;
+    if (add0_own || add1_own) {  // the caller's addends (HROTATE add: component 0 only; HMULT add: both), owned limbs [nq][N]
+      a.z = add0_own ? add0_own : add1_own;
+      a.z_poly_stride = (add0_own && add1_own) ? (long long)(add1_own - add0_own) : 0;
+      a.z_mask = (add0_own ? 1u : 0u) | (add1_own ? 2u : 0u);  // a single addend is read with stride 0
+    }
     launch_sub_mul_add(ctx->mc, sp->q_lm, a, s);
     prof_mark(ctx, HML_CLS_EWE, s);
     ctx->exec.ewe_limbs += 2 * nq; ctx->exec.kernel_launches++;
@@ -998,15 +1024,40 @@ __global__ void k_shard_signal(unsigned long long *const *peer_flags, int slot, 
   __threadfence_system();
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flags[p] + slot), "l"(epoch) : "memory");
 }
-__global__ void k_shard_wait(const unsigned long long *flags, int base, unsigned long long epoch, int world) {
+// Spin-waits poll with a wall-clock limit (globaltimer, default 20 s, HML_SHARD_TIMEOUT_MS): a peer that is merely slow
+// (first-call planning, allocation, a debugger) must not be mistaken for a dead one, and a dead one must not kill the CUDA
+// context: on time-out the kernel sets the status word (word 3 * world + 4 of the rank's flag block) and returns; the host
+// turns it into HML_ERR_CUDA (hml_shard_status / the hml_shard ops).
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void spin_until(const unsigned long long *flag, unsigned long long epoch, unsigned long long *status,
+                                           unsigned long long timeout_ns) {
+  const unsigned long long t0 = globaltimer_ns();
+  unsigned long long v;
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    if (v >= epoch) return;
+    if (globaltimer_ns() - t0 > timeout_ns) {
+      atomicExch(status, 1ull);
+      return;
+    }
+  }
+}
+static unsigned long long shard_timeout_ns() {
+  static const unsigned long long v = [] {
+    const char *e = getenv("HML_SHARD_TIMEOUT_MS");
+    const long long ms = e ? atoll(e) : 20000;
+    return (unsigned long long)(ms > 0 ? ms : 20000) * 1000000ull;
+  }();
+  return v;
+}
+__global__ void k_shard_wait(const unsigned long long *flags, int base, unsigned long long epoch, int world, unsigned long long timeout_ns) {
   const int r = threadIdx.x;
   if (r >= world) return;
-  const long long t0 = clock64();
-  unsigned long long v;
-  do {
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + base + r) : "memory");
-    if (v < epoch && clock64() - t0 > (4ll << 30)) __trap();  // ~2 s: a peer that never signals must not hang the device
-  } while (v < epoch);
+  spin_until(flags + base + r, epoch, const_cast<unsigned long long *>(flags) + 3 * world + 4, timeout_ns);
 }
 
 // signal + wait in one launch (one rank per GPU; ranks emulated on ONE stream must use the two separate calls, because a
@@ -1014,7 +1065,7 @@ __global__ void k_shard_wait(const unsigned long long *flags, int base, unsigned
 // epoch == 0: the epoch is this rank's own counter for the exchange group (word 3 * world + base / world of its flag block),
 // read and advanced here — no host-side state, so a captured CUDA graph of a whole op sequence can be replayed.
 __global__ void k_shard_sync(unsigned long long *const *peer_flags, int slot, unsigned long long *flags, int base,
-                             unsigned long long epoch, int world) {
+                             unsigned long long epoch, int world, unsigned long long timeout_ns) {
   __shared__ unsigned long long e_sh;
   const int r = threadIdx.x;
   unsigned long long *ctr = flags + 3 * world + base / world;
@@ -1024,12 +1075,7 @@ __global__ void k_shard_sync(unsigned long long *const *peer_flags, int slot, un
   if (r < world) {
     __threadfence_system();
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flags[r] + slot), "l"(e) : "memory");
-    const long long t0 = clock64();
-    unsigned long long v;
-    do {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + base + r) : "memory");
-      if (v < e && clock64() - t0 > (4ll << 30)) __trap();
-    } while (v < e);
+    spin_until(flags + base + r, e, flags + 3 * world + 4, timeout_ns);
   }
   __syncthreads();
   if (r == 0 && !epoch) *ctr = e;
@@ -1039,7 +1085,7 @@ extern "C" int hml_shard_sync(hml_ctx *ctx, uint64_t *const *peer_flags_dev, uin
   if (!ctx || !peer_flags_dev || !flags || world == 0 || world > 64) return HML_ERR_INVALID;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   k_shard_sync<<<1, 64, 0, (cudaStream_t)stream>>>((unsigned long long *const *)peer_flags_dev, (int)slot, (unsigned long long *)flags,
-                                                   (int)base, epoch, (int)world);
+                                                   (int)base, epoch, (int)world, shard_timeout_ns());
   ctx->exec.kernel_launches++;
   return check_launch(ctx, "shard sync");
 }
@@ -1055,9 +1101,19 @@ extern "C" int hml_shard_signal(hml_ctx *ctx, uint64_t *const *peer_flags_dev, u
 extern "C" int hml_shard_wait(hml_ctx *ctx, const uint64_t *flags, uint32_t base, uint64_t epoch, uint32_t world, void *stream) {
   if (!ctx || !flags || world == 0 || world > 64) return HML_ERR_INVALID;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  k_shard_wait<<<1, 64, 0, (cudaStream_t)stream>>>((const unsigned long long *)flags, (int)base, epoch, (int)world);
+  k_shard_wait<<<1, 64, 0, (cudaStream_t)stream>>>((const unsigned long long *)flags, (int)base, epoch, (int)world, shard_timeout_ns());
   ctx->exec.kernel_launches++;
   return check_launch(ctx, "shard wait");
+}
+
+extern "C" int hml_shard_status(hml_ctx *ctx, const uint64_t *flags, uint32_t world, void *stream) {
+  if (!ctx || !flags || world == 0 || world > 64) return HML_ERR_INVALID;
+  HML_CU_TRY(ctx, cudaSetDevice(ctx->device));
+  unsigned long long st = 0;
+  HML_CU_TRY(ctx, cudaMemcpyAsync(&st, flags + 3 * world + 4, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  HML_CU_TRY(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+  if (st) return fail(ctx, HML_ERR_CUDA, "limb-sharded exchange timed out waiting for a peer (HML_SHARD_TIMEOUT_MS); results of this rank are invalid");
+  return HML_OK;
 }
 
 extern "C" int hml_ipc_export(hml_ctx *ctx, const uint64_t *dev_ptr, unsigned char handle[64]) {
@@ -1163,11 +1219,39 @@ extern "C" int hml_keyswitch_shard_end_p2p(hml_ctx *ctx, uint32_t L, uint32_t ra
   return shard_end_run(ctx, sp, (const u64 *)peers2[rank], sp->d_off2, (u64 *)out0_own, (u64 *)out1_own, (cudaStream_t)stream);
 }
 
+int shard_end_p2p_add(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, const uint64_t *const *peers2, uint64_t *out0_own,
+                      uint64_t *out1_own, const uint64_t *add0_own, const uint64_t *add1_own, cudaStream_t s) {
+  int rc = shard_check(ctx, L, rank, world);
+  if (rc) return rc;
+  HML_CU_TRY(ctx, cudaSetDevice(ctx->device));
+  ShardPlan *sp;
+  if ((rc = get_shard_plan(ctx, L, rank, world, &sp))) return rc;
+  if ((rc = shard_p2p_check(ctx, sp->down))) return rc;
+  if ((rc = shard_peer_offsets(ctx, sp, peers2, true))) return rc;
+  return shard_end_run(ctx, sp, (const u64 *)peers2[rank], sp->d_off2, (u64 *)out0_own, (u64 *)out1_own, s, (const u64 *)add0_own, (const u64 *)add1_own);
+}
+
+// everything a sharded op at level L needs that costs host time or synchronises the device (plans, conversion images, offset
+// tables, workspace): done ahead of the first exchange so that no rank sits in a spin-wait while a peer is still preparing
+int shard_prepare(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, const uint64_t *const *peers1, const uint64_t *const *peers2) {
+  int rc = shard_check(ctx, L, rank, world);
+  if (rc) return rc;
+  HML_CU_TRY(ctx, cudaSetDevice(ctx->device));
+  ShardPlan *sp;
+  if ((rc = get_shard_plan(ctx, L, rank, world, &sp))) return rc;
+  for (auto &u : sp->up) if ((rc = shard_p2p_check(ctx, u))) return rc;
+  if ((rc = shard_p2p_check(ctx, sp->down))) return rc;
+  if ((rc = shard_peer_offsets(ctx, sp, peers1, false))) return rc;
+  if ((rc = shard_peer_offsets(ctx, sp, peers2, true))) return rc;
+  const uint32_t nq = sp->own_q.size();
+  return ensure_ws(ctx, std::max(shard_ws_words(ctx->p, *sp), (size_t)2 * nq * ctx->p.N));
+}
+
 // ------------------------------------------------------------------------------------------------ rescale
-static size_t rs_ws_words(const Params &p, uint32_t L, uint32_t n_polys) { return (size_t)p.N * n_polys * L; }
+size_t rs_ws_words(const Params &p, uint32_t L, uint32_t n_polys) { return (size_t)p.N * n_polys * L; }
 
 // in: n_polys polys of L limbs (uniform stride in_poly_stride) -> out: n_polys polys of L-1 limbs
-static int rescale_run(hml_ctx *ctx, uint32_t L, const u64 *in, long long in_poly_stride, uint32_t n_polys, u64 *out,
+int rescale_run(hml_ctx *ctx, uint32_t L, const u64 *in, long long in_poly_stride, uint32_t n_polys, u64 *out,
                        long long out_poly_stride, u64 *ws, cudaStream_t s) {
   const Params &p = ctx->p;
   LevelConsts *lc;
@@ -1318,7 +1402,7 @@ static uint32_t batch_chunk() {
 }
 #define HML_BATCH_CHUNK batch_chunk()
 
-static size_t hmult_ws_words(const Params &p, uint32_t L, uint32_t nb) {
+size_t hmult_ws_words(const Params &p, uint32_t L, uint32_t nb) {
   return (size_t)nb * ((size_t)p.N * 5 * L + std::max(ks_ws_words(p, L), rs_ws_words(p, L, 2)));
 }
 
@@ -1333,7 +1417,7 @@ static size_t hmult_ws_words(const Params &p, uint32_t L, uint32_t nb) {
 // straight out of the base conversion: P^-1 is folded into the matrix on the host, r is computed by the conversion kernel on
 // its staged tile (a 15-term dot product per coefficient) and rides in the otherwise padded 16th source row with matrix
 // entry 1 (exact: it only adds one term < 2^36 to the 16-term sums).
-static int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, const u64 *ct_b, const u64 *evk, uint32_t evk_q_limbs,
+int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, const u64 *ct_b, const u64 *evk, uint32_t evk_q_limbs,
                      u64 *ct_out, u64 *ws, cudaStream_t s) {
   const Params &p = ctx->p;
   const size_t N = p.N, PL = N * L;
@@ -1427,10 +1511,10 @@ extern "C" int hml_hmult(hml_ctx *ctx, uint32_t L, const uint64_t *ct_a, const u
   return hmult_run(ctx, L, 1, (const u64 *)ct_a, (const u64 *)ct_b, (const u64 *)evk, evk_q_limbs, (u64 *)ct_out, ctx->ws, (cudaStream_t)stream);
 }
 
-static size_t hrot_ws_words(const Params &p, uint32_t L, uint32_t nb) { return (size_t)nb * ((size_t)p.N * 2 * L + ks_ws_words(p, L)); }
+size_t hrot_ws_words(const Params &p, uint32_t L, uint32_t nb) { return (size_t)nb * ((size_t)p.N * 2 * L + ks_ws_words(p, L)); }
 
 // nb ciphertexts [nb][2][L][N] -> [nb][2][L][N]
-static int hrot_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct, const u64 *rk, uint32_t evk_q_limbs, u64 g, u64 *ct_out,
+int hrot_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct, const u64 *rk, uint32_t evk_q_limbs, u64 g, u64 *ct_out,
                     u64 *ws, cudaStream_t s) {
   const size_t N = ctx->p.N, PL = N * L;
   u64 *sb = ws, *rest = sb + 2 * nb * PL;  // sb [nb][2][L][N]
@@ -1453,6 +1537,54 @@ extern "C" int hml_hrotate(hml_ctx *ctx, uint32_t L, const uint64_t *ct, const u
   if ((rc = ensure_ws(ctx, hrot_ws_words(ctx->p, L, 1)))) return rc;
   ws_enter(ctx, (cudaStream_t)stream);
   return hrot_run(ctx, L, 1, (const u64 *)ct, (const u64 *)rotkey, evk_q_limbs, galois_elt, (u64 *)ct_out, ctx->ws, (cudaStream_t)stream);
+}
+
+// Hoisted rotations: n_rot rotations of ONE ciphertext share one ModUp.  With t_j = NTT(ModUp_j(INTT(c1)))
+// the extended digits of c1 (K1..K4, computed once),
+//   out_r = (sigma_r(c0) + ks0, ks1),   (ks0, ks1) = ModDown( sum_j sigma_r(t_j) * rk_r[j] )
+// sigma_r is applied to the digits while the inner product loads them, so the rotated digits never exist in memory.  This is
+// NOT bit-identical to hml_hrotate: the approximate base conversion is not equivariant under the automorphism
+// (ModUp(sigma(c1)) and sigma(ModUp(c1)) differ by multiples of the digit's modulus product), both are valid key-switch
+// inputs; the oracle defines this op separately (oracle/oracle.c orc_hrotate_hoisted).  Reference: the rotation it replaces is
+// src/Operation.cpp:1271-1358 run n_rot times; the reference itself cannot chain or share work between ops (:636,:675,:714).
+int hrot_hoisted_run(hml_ctx *ctx, uint32_t L, const u64 *ct, uint32_t n_rot, const uint64_t *const *rotkeys, uint32_t evk_q_limbs,
+                     const uint64_t *galois, uint64_t *const *outs, u64 *ws, cudaStream_t s) {
+  const Params &p = ctx->p;
+  if (evk_q_limbs < L || evk_q_limbs > p.max_level) return fail(ctx, HML_ERR_INVALID, "evk_q_limbs must be in [L, maxLevel]");
+  LevelConsts *lc;
+  int rc = get_level(ctx, L, &lc);
+  if (rc) return rc;
+  const size_t N = p.N, PL = N * L;
+  const uint32_t A = p.alpha, E = L + A, beta = lc->beta;
+  if (beta > 8) return fail(ctx, HML_ERR_UNSUPPORTED, "more than 8 key-switch digits (ceil(L/alpha) > 8)");
+  u64 *sb = ws, *yb = sb + 2 * PL, *ext = yb + PL, *acc = ext + (size_t)beta * E * N, *vb = acc + 2 * (size_t)E * N;
+  const BatchPtr c1{ct + PL, 0};
+  if ((rc = ks_modup(ctx, lc, L, 1, c1, yb, ext, s))) return rc;
+  for (uint32_t r = 0; r < n_rot; ++r) {
+    launch_automorph(p.logN, L, ct, sb, galois[r], s);  // sigma_r(c0): the addend of the ModDown epilogue
+    prof_mark(ctx, HML_CLS_AUTO, s);
+    ctx->exec.automorph_limbs += L; ctx->exec.kernel_launches++;
+    if ((rc = ks_inner(ctx, lc, L, 1, c1, (const u64 *)rotkeys[r], evk_q_limbs, ext, acc, E, galois[r], s))) return rc;
+    u64 *o = (u64 *)outs[r];
+    if ((rc = ks_tail(ctx, lc, L, 1, acc, vb, {o, 0}, {o + PL, 0}, {sb, 0}, {nullptr, 0}, s))) return rc;
+  }
+  return check_launch(ctx, "hrotate hoisted");
+}
+
+extern "C" int hml_hrotate_hoisted(hml_ctx *ctx, uint32_t L, const uint64_t *ct, uint32_t n_rot, const uint64_t *const *rotkeys,
+                                   uint32_t evk_q_limbs, const uint64_t *galois_elts, uint64_t *const *ct_outs, void *stream) {
+  int rc = check_level(ctx, L, 1);
+  if (rc) return rc;
+  if (!ct || !rotkeys || !galois_elts || !ct_outs) return fail(ctx, HML_ERR_INVALID, "null buffer");
+  for (uint32_t r = 0; r < n_rot; ++r) {
+    if (!rotkeys[r] || !ct_outs[r] || ct_outs[r] == ct) return fail(ctx, HML_ERR_INVALID, "null key / output, or an output aliasing the input");
+    if (!(galois_elts[r] & 1)) return fail(ctx, HML_ERR_INVALID, "galois element must be odd");
+  }
+  if (n_rot == 0) return HML_OK;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if ((rc = ensure_ws(ctx, hrot_ws_words(ctx->p, L, 1)))) return rc;
+  ws_enter(ctx, (cudaStream_t)stream);
+  return hrot_hoisted_run(ctx, L, (const u64 *)ct, n_rot, rotkeys, evk_q_limbs, galois_elts, ct_outs, ctx->ws, (cudaStream_t)stream);
 }
 
 static int ew_ct_op(hml_ctx *ctx, uint32_t L, const uint64_t *a, const uint64_t *b, bool b_is_pt, bool mul, uint64_t *out, void *stream) {

@@ -120,10 +120,22 @@ __global__ void __launch_bounds__(EW_THREADS) k_inner(const ModConst *__restrict
     return j == own ? a.d + (size_t)b * a.d_batch_stride + (size_t)e * a.N
                     : a.ext + (size_t)b * a.ext_batch_stride + ((size_t)j * a.n_ext + e) * a.N;
   };
+  // source slots of this thread's two coefficients under the automorphism (identity when galois == 0)
+  unsigned s0 = 2u * i2, s1 = 2u * i2 + 1u;
+  if (a.galois) {
+    const unsigned sh = 32 - a.logN, m2n = (2u << a.logN) - 1u;
+    s0 = __brev((((a.galois * (2u * (__brev(s0) >> sh) + 1u)) & m2n) - 1u) >> 1) >> sh;
+    s1 = __brev((((a.galois * (2u * (__brev(s1) >> sh) + 1u)) & m2n) - 1u) >> 1) >> sh;
+  }
+  auto ld_digit = [&](int b, int j) -> ulonglong2 {
+    const u64 *p = digit_ptr(b, j);
+    if (!a.galois) return ld2(p, i2);
+    return make_ulonglong2(__ldg(p + s0), __ldg(p + s1));
+  };
   ulonglong2 tn[IP_MAX_BETA];
 #pragma unroll
   for (int j = 0; j < IP_MAX_BETA; ++j)
-    if (j < a.beta) tn[j] = ld2(digit_ptr(0, j), i2);
+    if (j < a.beta) tn[j] = ld_digit(0, j);
   double k[IP_MAX_BETA][2][2];  // [digit][component][coefficient]
 #pragma unroll
   for (int j = 0; j < IP_MAX_BETA; ++j)
@@ -142,7 +154,7 @@ __global__ void __launch_bounds__(EW_THREADS) k_inner(const ModConst *__restrict
     if (b + 1 < a.n_batch) {
 #pragma unroll
       for (int j = 0; j < IP_MAX_BETA; ++j)
-        if (j < a.beta) tn[j] = ld2(digit_ptr(b + 1, j), i2);
+        if (j < a.beta) tn[j] = ld_digit(b + 1, j);
     }
     double s00 = 0, s01 = 0, s10 = 0, s11 = 0;  // [component][coefficient]
 #pragma unroll
@@ -190,7 +202,7 @@ __global__ void __launch_bounds__(EW_THREADS) k_sub_mul_add(const ModConst *__re
   const ulonglong2 y = a.y ? ld2(a.y + poly * a.y_poly_stride, o) : make_ulonglong2(0, 0);
   double r0 = mulmod_const(u64_to_f64(x.x) - u64_to_f64(y.x), c.x, c.y, m.q);
   double r1 = mulmod_const(u64_to_f64(x.y) - u64_to_f64(y.y), c.x, c.y, m.q);
-  if (a.z) {
+  if (a.z && (a.z_mask == 0 || ((a.z_mask >> poly) & 1u))) {
     const ulonglong2 z = a.z_packed ? ld_packed2(a.z + poly * a.z_poly_stride + (size_t)limb * a.N, a.N, i2) : ld2(a.z + poly * a.z_poly_stride, o);
     r0 += u64_to_f64(z.x);
     r1 += u64_to_f64(z.y);

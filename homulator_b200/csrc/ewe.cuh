@@ -38,6 +38,11 @@ struct InnerArgs {
   long long acc_comp_stride;       // words between the two accumulators of a ciphertext (0 = n_ext * N)
   int ext_f64;                     // 1: `ext` holds the forward NTT's raw signed doubles (NttLaunch::out_f64), |v| < 2^41
   int acc_pack_limbs;              // the accumulators of extended limbs e < acc_pack_limbs are stored as packed limbs
+  // hoisted rotations: galois != 0 applies the automorphism X -> X^galois to every digit ON LOAD (t_j[k] is read at the
+  // slot k' the automorphism kernel would have fetched, 2*brv(k')+1 = galois*(2*brv(k)+1) mod 2N), so one ModUp serves many
+  // rotations and the rotated digits never exist in memory.  The key is read in place.
+  unsigned galois;
+  int logN;
 };
 void launch_inner_product(const ModConst *mc, const LimbMap &lm, const InnerArgs &a, cudaStream_t s);
 
@@ -50,6 +55,7 @@ struct SubMulArgs {
   const double2 *cst;     // [n_limbs]
   int N, n_limbs, n_polys;
   int x_packed, z_packed; // x / z hold packed limbs (modarith.cuh)
+  unsigned z_mask;        // 0: z is added for every poly; else only for the polys whose bit is set (poly < 32)
 };
 void launch_sub_mul_add(const ModConst *mc, const LimbMap &lm, const SubMulArgs &a, cudaStream_t s);
 

@@ -181,9 +181,53 @@ int hml_shard_sync(hml_ctx *ctx, uint64_t *const *peer_flags_dev, uint32_t slot,
 int hml_rescale_shard_begin(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, const uint64_t *x_own, uint64_t *r_own, void *stream);
 int hml_rescale_shard_end(hml_ctx *ctx, uint32_t L, uint32_t rank, uint32_t world, const uint64_t *x_own, const uint64_t *r_src,
                           uint64_t *out_own, void *stream);
+/* hml_shard_wait / hml_shard_sync never trap: a wait that exceeds HML_SHARD_TIMEOUT_MS (default 20000) sets the status word
+ * (word 3 * world + 4 of the rank's flag block, which therefore needs 3 * world + 8 words) and returns; hml_shard_status
+ * synchronises `stream` and reports it as HML_ERR_CUDA. */
+int hml_shard_status(hml_ctx *ctx, const uint64_t *flags, uint32_t world, void *stream);
 int hml_ipc_export(hml_ctx *ctx, const uint64_t *dev_ptr, unsigned char handle[64]);
 int hml_ipc_import(hml_ctx *ctx, const unsigned char handle[64], uint64_t **out);
 int hml_ipc_close(hml_ctx *ctx, uint64_t *ptr);
+
+/* ------------------------------------------------------------------ limb-sharded OPERATIONS (one call per op and rank)
+ * An hml_shard is one rank's view of a limb-shard group: its peer-visible buffers (two gather buffers sized for levels up to
+ * max_L, a rescale buffer, a flag block), the mappings of every peer's, and the scratch of the composite ops.  The whole op —
+ * limb-local phases, the exchanges between them (one launch each: release this rank's epoch to every peer, acquire-spin on
+ * theirs; epochs live in device memory, so a captured CUDA graph replays), the base conversions reading the peers' limbs
+ * over NVLink — is composed inside the library (homulator_b200/csrc/shard.cu); this replaces the reference's limb -> cluster
+ * mapping and NoC (reference include/Driver.h:155-246, include/mem.h:612-621).
+ * Group set-up, (a) one process per GPU: hml_shard_create -> hml_shard_handles (4 cudaIpc handles) -> exchange them by any
+ * means -> hml_shard_connect_ipc(all ranks' handles, [world][4][64] bytes); (b) one process driving several devices (one ctx
+ * per device): hml_shard_create for every rank -> hml_shard_connect_local(group).  hml_shard_prepare(L) builds every table
+ * and sizes the workspace for level L ahead of the first exchange (call it on all ranks before a barrier).
+ * Sharded layouts: a polynomial = this rank's Q-limbs [nq][N] (limb i on rank i % world, ascending), a ciphertext [2][nq][N],
+ * a key [beta][2][n_own_ext][N] (owned Q-limbs, then owned P-limbs); hmult / rescale outputs hold the owned limbs below L-1.
+ * Every rank of the group must issue the same sequence of sharded calls. */
+typedef struct hml_shard hml_shard;
+int hml_shard_create(hml_ctx *ctx, uint32_t max_L, uint32_t rank, uint32_t world, hml_shard **out);
+int hml_shard_destroy(hml_shard *sh);
+int hml_shard_handles(hml_shard *sh, unsigned char *out_4x64);
+int hml_shard_connect_ipc(hml_shard *sh, const unsigned char *handles_world_4x64);
+int hml_shard_connect_local(hml_shard *const *group, uint32_t world);
+int hml_shard_prepare(hml_shard *sh, uint32_t L);
+int hml_shard_check(hml_shard *sh, void *stream);   /* synchronises; HML_ERR_CUDA if an exchange of this rank timed out */
+int hml_shard_own_limbs(const hml_shard *sh, uint32_t L, uint32_t *n_own_q, uint32_t *n_own_q_after_rescale);
+/* KeySwitch / HROTATE / HMULT / Rescale on sharded operands (reference src/Operation.cpp:9-54, :1271-1358, :913-1023, :741-911) */
+int hml_keyswitch_sharded(hml_shard *sh, uint32_t L, const uint64_t *d_own, const uint64_t *evk_own, uint64_t *out0_own,
+                          uint64_t *out1_own, void *stream);
+int hml_hrotate_sharded(hml_shard *sh, uint32_t L, const uint64_t *ct_own, const uint64_t *rotkey_own, uint64_t galois_elt,
+                        uint64_t *out_own, void *stream);
+int hml_hmult_sharded(hml_shard *sh, uint32_t L, const uint64_t *a_own, const uint64_t *b_own, const uint64_t *evk_own,
+                      uint64_t *out_own, void *stream);
+int hml_rescale_sharded(hml_shard *sh, uint32_t L, const uint64_t *x_own, uint64_t *out_own, void *stream);
+/* HADD (kind 0, b = ciphertext), PMULT (1), PADD (2) (b = plaintext [nq][N]) on the owned limbs: no exchange */
+int hml_ew_sharded(hml_shard *sh, uint32_t L, int kind, const uint64_t *a_own, const uint64_t *b_own, uint64_t *out_own, void *stream);
+/* All ranks of a group driven by ONE host thread, phase by phase (the CLI's [cluster] argument; tests on a one-GPU box).
+ * op_kind: 0 keyswitch (a = d_own, out0, out1), 1 hrotate (a = ct_own, out0), 2 hmult (a, b, out0), 3 rescale (a, out0); every
+ * array is indexed by rank.  Ranks that share a device must share one stream: they are ordered by that stream and exchange
+ * with separate signal / wait launches, so no kernel ever spins on a flag a not-yet-launched kernel has to write. */
+int hml_group_op(hml_shard *const *group, uint32_t world, int op_kind, uint32_t L, const uint64_t *const *a, const uint64_t *const *b,
+                 const uint64_t *const *key, uint64_t *const *out0, uint64_t *const *out1, uint64_t galois_elt, void *const *streams);
 
 /* ------------------------------------------------------------------ operations (reference include/Operation.h) */
 /* HMULT (reference src/Operation.cpp:913-1023): tensor + keyswitch(relinearise) + add + rescale x2.
@@ -195,6 +239,13 @@ int hml_hmult(hml_ctx *ctx, uint32_t L, const uint64_t *ct_a, const uint64_t *ct
  * ct [2][L][N] -> ct_out [2][L][N] = (sigma(c0) + ks0, ks1), ks = KeySwitch(sigma(c1)). */
 int hml_hrotate(hml_ctx *ctx, uint32_t L, const uint64_t *ct, const uint64_t *rotkey, uint32_t evk_q_limbs,
                 uint64_t galois_elt, uint64_t *ct_out, void *stream);
+/* Hoisted rotations: n_rot rotations of ONE ciphertext share one ModUp of c1; the automorphism is
+ * applied to the extended digits as the inner product loads them.  out_r = (sigma_r(c0) + ks0, ks1).  A different function
+ * from hml_hrotate bit for bit (the approximate base conversion is not equivariant under the automorphism) and an equally
+ * valid rotation; pinned by its own oracle definition (oracle/oracle.c orc_hrotate_hoisted).  rotkeys / galois_elts /
+ * ct_outs are HOST arrays of n_rot entries; no output may alias the input. */
+int hml_hrotate_hoisted(hml_ctx *ctx, uint32_t L, const uint64_t *ct, uint32_t n_rot, const uint64_t *const *rotkeys,
+                        uint32_t evk_q_limbs, const uint64_t *galois_elts, uint64_t *const *ct_outs, void *stream);
 /* HADD / PMULT / PADD (reference src/Operation.cpp:1114-1176, :1453-1523, :1618-1680).  pt is [L][N].
  * PADD adds the plaintext to BOTH components, as the reference's trace does (:1650-1672). */
 int hml_hadd(hml_ctx *ctx, uint32_t L, const uint64_t *ct_a, const uint64_t *ct_b, uint64_t *ct_out, void *stream);
@@ -217,6 +268,29 @@ int hml_hrotate_host(hml_ctx *ctx, uint32_t L, uint32_t n, const uint64_t *ct_ho
                      uint32_t evk_q_limbs, uint64_t galois_elt, uint64_t *ct_out_host);
 int hml_host_alloc_pinned(hml_ctx *ctx, uint64_t n_words, uint64_t **out);
 int hml_host_free_pinned(hml_ctx *ctx, uint64_t *ptr);
+
+/* ------------------------------------------------------------------ op-sequence replay (BASELINE.json configs[4])
+ * The reference runs one operation per process and cannot chain them (reference src/Operation.cpp:636,675,714).  A trace is
+ * a list of the CLI's five operations (reference bench_test/bench_micro24.cpp:29-48) over numbered ciphertext slots at ONE
+ * level L: slot 0 is the bound input, every other slot is allocated by the replay object; an hmult result (one level lower)
+ * is final — it cannot be read by a later op of the trace.  In-place ops (dst == a) are allowed except for hmult.
+ *   HROTATE dst = rotate(a, 5^b)   (needs the key bound for rotation amount b)      PMULT / PADD dst = a (*|+) plaintext[b]
+ *   HADD    dst = a + slot b                                                     HMULT dst = rescale(relin(a * slot b))
+ * flags: HML_REPLAY_GRAPH — the whole sequence is captured once into a CUDA graph (after a warm-up run) and every run is one
+ * graph launch; HML_REPLAY_HOIST — consecutive rotations of one source share a ModUp (hml_hrotate_hoisted; sh == NULL only).
+ * With sh != NULL the trace runs limb-sharded: every pointer is the rank's owned-limb slice (see the sharded layouts above). */
+enum { HML_OP_HROTATE = 0, HML_OP_PMULT = 1, HML_OP_HADD = 2, HML_OP_PADD = 3, HML_OP_HMULT = 4 };
+enum { HML_REPLAY_GRAPH = 1, HML_REPLAY_HOIST = 2 };
+typedef struct { uint32_t kind, dst, a, b; } hml_trace_op;
+typedef struct hml_replay hml_replay;
+int hml_replay_create(hml_ctx *ctx, hml_shard *sh, uint32_t L, const hml_trace_op *ops, uint32_t n_ops, uint32_t flags,
+                      hml_replay **out);
+int hml_replay_bind(hml_replay *rp, const uint64_t *x, const uint64_t *const *plaintexts, uint32_t n_plaintexts,
+                    const uint32_t *rot_amounts, const uint64_t *const *rot_keys, uint32_t n_rot_keys, const uint64_t *evk,
+                    uint32_t evk_q_limbs);
+int hml_replay_run(hml_replay *rp, void *stream);
+int hml_replay_slot(hml_replay *rp, uint32_t slot, uint64_t **ptr, uint32_t *n_limbs);   /* n_limbs per polynomial */
+int hml_replay_destroy(hml_replay *rp);
 
 /* ------------------------------------------------------------------ the count contract
  * Instruction counts of the reference's InsGen trace for one op (what `new OP(...)` generates,

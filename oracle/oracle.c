@@ -295,17 +295,15 @@ void orc_bconv(const orc_params *p, const uint32_t *src, uint32_t n_src, uint32_
 }
 
 /* ---------------------------------------------------------------- key switch (K1..K10) */
-void orc_keyswitch(const orc_params *p, uint32_t L, const uint64_t *d, const uint64_t *evk, uint32_t evk_q_limbs,
-                   uint64_t *out0, uint64_t *out1) {
-  const uint32_t N = p->N, A = p->alpha, E = L + A, beta = (L + A - 1) / A;
-  const size_t W = N;
-  const uint32_t evk_limbs = evk_q_limbs + A;
-  /* extended basis E = (q_0..q_{L-1}, p_0..p_{A-1}): modulus index of extended limb e */
 #define EXT_MOD(e) ((e) < L ? (e) : p->max_level + ((e) - L))
 #define EVK_LIMB(e) ((e) < L ? (e) : evk_q_limbs + ((e) - L))
+
+/* K1..K4: the beta extended digits of d, evaluation form: t [beta][L + alpha][N].  Digit j keeps the residues of its own
+ * limbs and is base-converted (K2 + K3) to every other modulus of E = (q_0..q_{L-1}, p_0..p_{alpha-1}). */
+void orc_modup(const orc_params *p, uint32_t L, const uint64_t *d, uint64_t *t) {
+  const uint32_t N = p->N, A = p->alpha, E = L + A, beta = (L + A - 1) / A;
+  const size_t W = N;
   uint64_t *dc = (uint64_t *)malloc(8 * W * L);             /* K1: coefficient form of d */
-  uint64_t *acc = (uint64_t *)calloc(2 * W * E, 8);         /* K5 accumulators [2][E][N] */
-  uint64_t *t = (uint64_t *)malloc(8 * W * E);              /* one extended digit [E][N] */
   memcpy(dc, d, 8 * W * L);
 #pragma omp parallel for num_threads(g_threads) schedule(dynamic)
   for (uint32_t i = 0; i < L; i++) intt_any(p, i, dc + i * W); /* K1 */
@@ -313,20 +311,34 @@ void orc_keyswitch(const orc_params *p, uint32_t L, const uint64_t *d, const uin
     const uint32_t lo = j * A, aj = (L - lo < A) ? (L - lo) : A;
     uint32_t src[64 * 8];
     for (uint32_t i = 0; i < aj; i++) src[i] = lo + i;
-    /* K2+K3: convert the digit to every modulus of E outside the digit; K3 keeps own residues */
+    uint64_t *tj = t + (size_t)j * E * W;
 #pragma omp parallel for num_threads(g_threads) schedule(dynamic)
     for (uint32_t e = 0; e < E; e++) {
-      if (e >= lo && e < lo + aj) memcpy(t + e * W, dc + e * W, 8 * W);
-      else orc_bconv(p, src, aj, EXT_MOD(e), dc + (size_t)lo * W, t + e * W);
-      ntt_any(p, EXT_MOD(e), t + e * W); /* K4 */
-      /* K5: acc_c[e] += t_hat ⊙ evk[j][c][e] */
-      const uint64_t m = p->mod[EXT_MOD(e)];
-      for (uint32_t c = 0; c < 2; c++) {
-        const uint64_t *k = evk + (((size_t)j * 2 + c) * evk_limbs + EVK_LIMB(e)) * W;
-        uint64_t *a = acc + ((size_t)c * E + e) * W;
-        for (uint32_t n = 0; n < N; n++) a[n] = addmod(a[n], mulmod(t[e * W + n], k[n] % m, m), m);
-      }
+      if (e >= lo && e < lo + aj) memcpy(tj + e * W, dc + e * W, 8 * W);
+      else orc_bconv(p, src, aj, EXT_MOD(e), dc + (size_t)lo * W, tj + e * W);
+      ntt_any(p, EXT_MOD(e), tj + e * W); /* K4 */
     }
+  }
+  free(dc);
+}
+
+/* K5..K10 from given extended digits t [beta][E][N] (evaluation form) */
+void orc_keyswitch_digits(const orc_params *p, uint32_t L, const uint64_t *t, const uint64_t *evk, uint32_t evk_q_limbs,
+                          uint64_t *out0, uint64_t *out1) {
+  const uint32_t N = p->N, A = p->alpha, E = L + A, beta = (L + A - 1) / A;
+  const size_t W = N;
+  const uint32_t evk_limbs = evk_q_limbs + A;
+  uint64_t *acc = (uint64_t *)calloc(2 * W * E, 8);         /* K5 accumulators [2][E][N] */
+#pragma omp parallel for num_threads(g_threads) schedule(dynamic)
+  for (uint32_t e = 0; e < E; e++) {
+    const uint64_t m = p->mod[EXT_MOD(e)];
+    for (uint32_t j = 0; j < beta; j++)
+      for (uint32_t c = 0; c < 2; c++) {   /* K5: acc_c[e] += t_j[e] * evk[j][c][e] */
+        const uint64_t *k = evk + (((size_t)j * 2 + c) * evk_limbs + EVK_LIMB(e)) * W;
+        const uint64_t *tj = t + ((size_t)j * E + e) * W;
+        uint64_t *a = acc + ((size_t)c * E + e) * W;
+        for (uint32_t n = 0; n < N; n++) a[n] = addmod(a[n], mulmod(tj[n], k[n] % m, m), m);
+      }
   }
   /* ModDown, per accumulator c */
   uint32_t psrc[64 * 8];
@@ -351,10 +363,41 @@ void orc_keyswitch(const orc_params *p, uint32_t L, const uint64_t *d, const uin
     }
     free(u);
   }
-  free(dc); free(acc); free(t);
+  free(acc);
+}
+
+void orc_keyswitch(const orc_params *p, uint32_t L, const uint64_t *d, const uint64_t *evk, uint32_t evk_q_limbs,
+                   uint64_t *out0, uint64_t *out1) {
+  const uint32_t A = p->alpha, E = L + A, beta = (L + A - 1) / A;
+  uint64_t *t = (uint64_t *)malloc(8 * (size_t)p->N * E * beta);
+  orc_modup(p, L, d, t);
+  orc_keyswitch_digits(p, L, t, evk, evk_q_limbs, out0, out1);
+  free(t);
+}
+
+/* Hoisted rotations: n_rot rotations of one ciphertext share ONE ModUp of c1 (its own definition, NOT bit-identical to
+ * orc_hrotate: the approximate base conversion does not commute with the automorphism limb by limb).  With
+ * t = ModUp(c1) (K1..K4):   out_r = (sigma_r(c0) + ks0, ks1),  (ks0, ks1) = K5..K10( sigma_r(t), rotkeys[r] ),
+ * sigma_r applied to every limb of every extended digit in evaluation form.  Replaces n_rot runs of the reference's
+ * HROTATE (src/Operation.cpp:1271-1358), which cannot share work between operations (:636,:675,:714). */
+void orc_hrotate_hoisted(const orc_params *p, uint32_t L, const uint64_t *ct, uint32_t n_rot, const uint64_t *const *rotkeys,
+                         uint32_t evk_q_limbs, const uint64_t *galois, uint64_t *const *ct_outs) {
+  const uint32_t A = p->alpha, E = L + A, beta = (L + A - 1) / A;
+  const size_t W = p->N, PL = W * L;
+  uint64_t *t = (uint64_t *)malloc(8 * W * E * beta), *ts = (uint64_t *)malloc(8 * W * E * beta);
+  uint64_t *s0 = (uint64_t *)malloc(8 * PL);
+  orc_modup(p, L, ct + PL, t);
+  for (uint32_t r = 0; r < n_rot; r++) {
+    for (size_t k = 0; k < (size_t)beta * E; k++) orc_automorph_eval(p, galois[r], t + k * W, ts + k * W);
+    for (uint32_t l = 0; l < L; l++) orc_automorph_eval(p, galois[r], ct + l * W, s0 + l * W);
+    uint64_t *out = ct_outs[r];
+    orc_keyswitch_digits(p, L, ts, rotkeys[r], evk_q_limbs, out, out + PL);
+    for (uint32_t l = 0; l < L; l++) orc_ewe(p, l, out + l * W, NULL, s0 + l * W, NULL, 0, out + l * W);
+  }
+  free(t); free(ts); free(s0);
+}
 #undef EXT_MOD
 #undef EVK_LIMB
-}
 
 /* ---------------------------------------------------------------- rescale */
 void orc_rescale(const orc_params *p, uint32_t L, const uint64_t *in, uint64_t *out) {

@@ -81,6 +81,19 @@ void orc_bconv(const orc_params *p, const uint32_t *src_idx, uint32_t n_src, uin
 void orc_keyswitch(const orc_params *p, uint32_t L, const uint64_t *d, const uint64_t *evk,
                    uint32_t evk_q_limbs, uint64_t *out0, uint64_t *out1);
 
+/* The two halves of the key switch, exposed because the hoisted rotation is defined on them:
+ * orc_modup = K1..K4: t [beta][L+alpha][N], the extended digits of d in evaluation form;
+ * orc_keyswitch_digits = K5..K10 from given digits.  orc_keyswitch(d) == orc_keyswitch_digits(orc_modup(d)). */
+void orc_modup(const orc_params *p, uint32_t L, const uint64_t *d, uint64_t *t);
+void orc_keyswitch_digits(const orc_params *p, uint32_t L, const uint64_t *t, const uint64_t *evk, uint32_t evk_q_limbs,
+                          uint64_t *out0, uint64_t *out1);
+/* Hoisted rotations: n_rot rotations of ONE ciphertext share one ModUp of c1; the automorphism is
+ * applied to the extended digits.  Own definition — NOT bit-identical to orc_hrotate (approximate base conversion is not
+ * equivariant under the automorphism), equally valid: tests/test_oracle_semantics.py decrypts both.
+ * rotkeys / galois / ct_outs: n_rot entries; ct_outs[r] is [2][L][N]. */
+void orc_hrotate_hoisted(const orc_params *p, uint32_t L, const uint64_t *ct, uint32_t n_rot, const uint64_t *const *rotkeys,
+                         uint32_t evk_q_limbs, const uint64_t *galois, uint64_t *const *ct_outs);
+
 /* Rescale one polynomial: in [L][N] -> out [L-1][N]; non-negative reduction of the dropped limb. */
 void orc_rescale(const orc_params *p, uint32_t L, const uint64_t *in, uint64_t *out);
 

@@ -1,6 +1,7 @@
 """torchrun worker: peer-direct limb-sharded key switch, one rank per GPU, NO collective on the data path — the base
-conversions read the other GPUs' buffers over NVLink (cudaIpc mappings), ordered by epoch flags in peer memory.  Checked
-against the unsharded GPU path; timed against the NCCL variant and the single-GPU key switch.
+conversions read the other GPUs' buffers over NVLink (cudaIpc mappings), ordered by epoch flags in peer memory.  One C-ABI
+call per key switch (hml_keyswitch_sharded).  Checked against the unsharded GPU path; timed against the NCCL variant and the
+single-GPU key switch.
 Run as: python -m torch.distributed.run --nproc-per-node G --master-addr 127.0.0.1 tests/mp_sharded_keyswitch_p2p.py"""
 import os
 import sys
@@ -26,28 +27,27 @@ def main():
     o = Oracle(N, 36, ML, A)
     d = uniform_limbs(o.moduli[:L], N, 3000)
     evk = uniform_limbs(o.moduli[:L] + o.moduli[ML:], N, 3001, lead=(3, 2))
-    lay = hml.shard_layout(L, A, rank, world)
-    own_e = lay["own_q"] + [L + j for j in lay["own_p"]]
 
     def dev(x):
         return torch.from_numpy(np.ascontiguousarray(x).view(np.int64)).cuda()
-
-    d_own, evk_own = dev(d[lay["own_q"]]), dev(evk[:, :, own_e])
 
     def exchange(obj):
         out = [None] * world
         dist.all_gather_object(out, obj)
         return out
 
-    sh = ctx.shard_p2p_setup(L, rank, world, exchange)
+    sh = hml.Shard.ipc(ctx, L, rank, world, exchange)
+    sh.prepare(L)
+    d_own, evk_own = dev(d[sh.own_q(L)]), dev(evk[:, :, sh.own_ext(L)])
     dist.barrier()
     ref0, ref1 = ctx.keyswitch(L, dev(d), dev(evk))
-    idx = torch.tensor(lay["own_q"], device="cuda")
+    idx = torch.tensor(sh.own_q(L), device="cuda")
     ok = True
     for _ in range(3):  # buffer reuse across epochs
-        o0, o1 = sh.keyswitch(d_own, evk_own)
+        o0, o1 = sh.keyswitch(L, d_own, evk_own)
         torch.cuda.synchronize()
         ok = ok and torch.equal(o0, ref0[idx]) and torch.equal(o1, ref1[idx])
+    sh.check()
 
     def timeit(fn, reps=20):
         for _ in range(3):
@@ -67,7 +67,8 @@ def main():
     def all_gather(buf):
         dist.all_gather_into_tensor(buf, buf[rank].clone())
 
-    t_p2p = timeit(lambda: sh.keyswitch(d_own, evk_own))
+    o0b, o1b = ctx.empty(len(sh.own_q(L)), N), ctx.empty(len(sh.own_q(L)), N)
+    t_p2p = timeit(lambda: sh.keyswitch(L, d_own, evk_own, o0b, o1b))
     t_nccl = timeit(lambda: ctx.keyswitch_sharded(L, d_own, evk_own, rank, world, all_gather))
     dd, ee = dev(d), dev(evk)
     t_one = timeit(lambda: ctx.keyswitch(L, dd, ee))

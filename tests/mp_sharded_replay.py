@@ -1,6 +1,7 @@
-"""torchrun worker: BASELINE.json configs[4] — the synthetic baby-step/giant-step op sequence (homulator_b200/replay.py)
-replayed on LIMB-SHARDED operands, one rank per GPU, every key switch and the rescale exchanging over NVLink without a
-collective.  Checked against the single-GPU replay of the same trace; timed against it.
+"""torchrun worker: BASELINE.json configs[4] — the synthetic rotation-heavy op sequences (homulator_b200/replay.py) replayed
+on LIMB-SHARDED operands, one rank per GPU, through the C ABI only (hml_replay_* over an hml_shard): every key switch and
+rescale exchanges over NVLink without a collective; plain launches and ONE CUDA graph per rank.  Checked against the
+single-GPU replay of the same trace; timed against it.
 Run as: python -m torch.distributed.run --nproc-per-node G --master-addr 127.0.0.1 tests/mp_sharded_replay.py"""
 import os
 import sys
@@ -13,7 +14,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 import homulator_b200 as hml  # noqa: E402
-from homulator_b200.replay import bsgs_trace, replay, replay_sharded, trace_counts  # noqa: E402
+from homulator_b200.replay import bsgs_trace, shard_operands, trace_counts  # noqa: E402
 
 
 def main():
@@ -30,27 +31,19 @@ def main():
     rots = sorted({op[3] for op in tr if op[0] == "hrotate"})
     keys = {r: ctx.uniform(ctx.ext_mod_idx(L), 100 + r, lead=(3, 2)) for r in rots}
     pts = {i: ctx.uniform(q, 200 + i) for i in range(16)}
-    lay = hml.shard_layout(L, A, rank, world)
-    own = lay["own_q"]
-    own_e = own + [L + j for j in lay["own_p"]]
-    oi, oe = torch.tensor(own, device="cuda"), torch.tensor(own_e, device="cuda")
-    x_own = x[:, oi].contiguous()
-    evk_own = evk[:, :, oe].contiguous()
-    keys_own = {r: k[:, :, oe].contiguous() for r, k in keys.items()}
-    pts2 = {i: torch.stack([p[oi], p[oi]]).contiguous() for i, p in pts.items()}
 
     def exchange(obj):
         out = [None] * world
         dist.all_gather_object(out, obj)
         return out
 
-    sh = ctx.shard_p2p_setup(L, rank, world, exchange)
+    sh = hml.Shard.ipc(ctx, L, rank, world, exchange)
+    sh.prepare(L)
+    x_own, pts_own, keys_own, evk_own = shard_operands(sh, L, x, pts, keys, evk)
     dist.barrier()
-    ref = replay(ctx, L, tr, x, pts, keys, evk)["z"]
-    got = replay_sharded(sh, tr, x_own, pts2, keys_own, evk_own)["z"]
-    torch.cuda.synchronize()
-    keep = torch.tensor([i for i in own if i < L - 1], device="cuda")
-    ok = torch.equal(got.contiguous(), ref[:, keep])
+    one = hml.Replay(ctx, L, tr).bind(x, pts, keys, evk)
+    ref = one.run().result("z").clone()
+    keep = torch.tensor([i for i in sh.own_q(L) if i < L - 1], device="cuda", dtype=torch.long)
 
     def timeit(fn, reps=5):
         for _ in range(2):
@@ -67,40 +60,30 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
-    t_sh = timeit(lambda: replay_sharded(sh, tr, x_own, pts2, keys_own, evk_own))
-    t_one = timeit(lambda: replay(ctx, L, tr, x, pts, keys, evk))
-    # the same sharded sequence as ONE CUDA graph per rank: epochs come from device-side counters, so the graph replays;
-    # the host enqueue cost (about 100 us per key switch through Python) no longer bounds the ranks' small kernels
-    t_graph, ok_graph = float("nan"), True
-    if os.environ.get("HML_SHARDED_GRAPH", "1") != "0":
+    ok = True
+    times = {}
+    for name, graph in (("launches", False), ("graph", True)):
+        rp = hml.Replay(ctx, L, tr, shard=sh, graph=graph).bind(x_own, pts_own, keys_own, evk_own)
+        got = rp.run().result("z")
+        torch.cuda.synchronize()
+        ok = ok and torch.equal(got.contiguous(), ref[:, keep])
+        times[name] = timeit(rp.run)
+        got = rp.result("z")
+        torch.cuda.synchronize()
+        ok = ok and torch.equal(got.contiguous(), ref[:, keep])
         dist.barrier()
-        torch.cuda.synchronize()
-        sh2 = ctx.shard_p2p_setup(L, rank, world, exchange)
-        sh2.device_epochs = True
-        side = torch.cuda.Stream()
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                z = replay_sharded(sh2, tr, x_own, pts2, keys_own, evk_own)["z"]
-        torch.cuda.synchronize()
-        dist.barrier()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            zg = replay_sharded(sh2, tr, x_own, pts2, keys_own, evk_own)["z"]
-        torch.cuda.synchronize()
-        dist.barrier()
-        g.replay()
-        torch.cuda.synchronize()
-        ok_graph = torch.equal(zg.contiguous(), ref[:, keep])
-        t_graph = timeit(lambda: g.replay())
-        ok = ok and ok_graph
+        rp.close()
+    sh.check()
+    t_one = timeit(one.run)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("op sequence %s world=%d: limb-sharded peer-direct %.1f us (as one CUDA graph per rank %.1f us), one GPU %.1f us"
-              % (trace_counts(tr), world, t_sh, t_graph, t_one))
+              % (trace_counts(tr), world, times["launches"], times["graph"], t_one))
         print("SHARDED_REPLAY_OK" if int(flag) == 1 else "SHARDED_REPLAY_MISMATCH")
     dist.barrier()
     torch.cuda.synchronize()
+    one.close()
     sh.close()
     dist.barrier()
     dist.destroy_process_group()

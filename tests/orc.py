@@ -52,6 +52,10 @@ def lib():
         L.orc_bconv.argtypes = [C.c_void_p, _u32p, C.c_uint32, C.c_uint32, _u64p, _u64p]
         L.orc_keyswitch.argtypes = [C.c_void_p, C.c_uint32, _u64p, _u64p, C.c_uint32, _u64p, _u64p]
         L.orc_rescale.argtypes = [C.c_void_p, C.c_uint32, _u64p, _u64p]
+        L.orc_modup.argtypes = [C.c_void_p, C.c_uint32, _u64p, _u64p]
+        L.orc_keyswitch_digits.argtypes = [C.c_void_p, C.c_uint32, _u64p, _u64p, C.c_uint32, _u64p, _u64p]
+        L.orc_hrotate_hoisted.argtypes = [C.c_void_p, C.c_uint32, _u64p, C.c_uint32, C.POINTER(_u64p), C.c_uint32, _u64p,
+                                          C.POINTER(_u64p)]
         L.orc_hmult.argtypes = [C.c_void_p, C.c_uint32, _u64p, _u64p, _u64p, C.c_uint32, _u64p]
         L.orc_hrotate.argtypes = [C.c_void_p, C.c_uint32, _u64p, _u64p, C.c_uint32, C.c_uint64, _u64p]
         for f in ("orc_hadd", "orc_pmult", "orc_padd"):
@@ -165,6 +169,22 @@ class Oracle:
         out = np.empty((2, L, self.N), dtype=np.uint64)
         lib().orc_hrotate(self.h, L, _p(ct), _p(rk), evk_q_limbs, g, _p(out))
         return out
+
+    def hrotate_hoisted(self, L, ct, rks, evk_q_limbs, gs):
+        """rotations gs (galois elements) of ONE ciphertext sharing one ModUp; returns a list of [2][L][N] arrays"""
+        n = len(gs)
+        outs = [np.empty((2, L, self.N), dtype=np.uint64) for _ in range(n)]
+        keys = (_u64p * n)(*[_p(k) for k in rks])
+        po = (_u64p * n)(*[_p(o) for o in outs])
+        g = np.asarray(gs, dtype=np.uint64)
+        lib().orc_hrotate_hoisted(self.h, L, _p(ct), n, keys, evk_q_limbs, _p(g), po)
+        return outs
+
+    def modup(self, L, d):
+        beta = -(-L // self.alpha)
+        t = np.empty((beta, L + self.alpha, self.N), dtype=np.uint64)
+        lib().orc_modup(self.h, L, _p(d), _p(t))
+        return t
 
     def hadd(self, L, a, b):
         out = np.empty((2, L, self.N), dtype=np.uint64)

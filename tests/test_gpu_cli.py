@@ -28,11 +28,11 @@ def test_cli_runs_every_op_at_the_north_star_config(op):
     r = run_cli(CFG, op, 45, 35, 15, "--iters", 3, "--warmup", 1)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     out = r.stdout
-    assert out.startswith("N") or "N " in out.splitlines()[0] or "=" in out.splitlines()[0]  # config dump comes first
+    assert out.startswith("Configuration details are as follow:")  # the reference's config dump comes first (src/Config.cpp:40-51)
     assert "Welcome! Start executing %s" % op.upper() in out and "Completed!" in out
     line = json.loads(out.strip().splitlines()[-1])
     assert line["op"] == op and line["N"] == 65536 and line["L"] == 35 and line["us_median"] > 0
-    gold = GOLD[("config_4", op, 45, 35, 15)]
+    gold = GOLD[("config_4.cfg", op, 45, 35, 15)]
     for opc in ("NTT", "INTT", "MULT", "BCONV_STEP2", "AUTO"):
         assert line["trace"][opc] == gold["by_opcode"].get(opc, 0), opc
     assert line["trace"]["total"] == gold["total"] and line["trace"]["driverTotal"] == gold["driverTotal"]
@@ -53,7 +53,7 @@ def test_cli_accepts_the_cluster_argument_and_rejects_bad_levels():
     r = run_cli(CFG, "hmult", 45, 2, 15, 1, "--iters", 2, "--warmup", 1)   # positional [cluster] like the reference
     assert r.returncode == 0, r.stderr
     line = json.loads(r.stdout.strip().splitlines()[-1])
-    assert line["trace"]["total"] == GOLD[("config_4", "hmult", 45, 2, 15)]["total"]
+    assert line["trace"]["total"] == GOLD[("config_4.cfg", "hmult", 45, 2, 15)]["total"]
     assert line["cluster"] == 1
     for bad in (0, 46, 99):
         r = run_cli(CFG, "hrotate", 45, bad, 15)

@@ -163,33 +163,97 @@ def test_op_objects_mirror_reference_constructor(north_star):
     assert rot.counts["AUTO"] == 17920 and rot.counts["total"] == 780800
 
 
-def test_op_sequence_replay_matches_oracle():
-    """BASELINE.json configs[4]: synthetic rotation-heavy (baby-step/giant-step) sequence replayed as real kernels."""
-    from homulator_b200.replay import bsgs_trace, replay, trace_counts
-    N, ML, A, L = 2048, 6, 2, 5
-    ctx, o = hml.Context(N=N, max_level=ML, alpha=A), Oracle(N, 36, ML, A)
-    beta = -(-L // A)
-    trace = bsgs_trace(2, 2)
-    assert trace_counts(trace)["hmult"] == 1 and trace_counts(trace)["hrotate"] == 2
-    x = uniform_limbs(o.moduli[:L], N, 1, lead=(2,))
-    pts = {i: uniform_limbs(o.moduli[:L], N, 100 + i) for i in range(4)}
-    keys = {r: uniform_limbs(o.moduli[:L] + o.moduli[ML:], N, 200 + r, lead=(beta, 2)) for r in (1, 2)}
-    evk = uniform_limbs(o.moduli[:L] + o.moduli[ML:], N, 300, lead=(beta, 2))
-    env = replay(ctx, L, trace, to_dev(x), {k: to_dev(v) for k, v in pts.items()}, {k: to_dev(v) for k, v in keys.items()},
-                 to_dev(evk))
-    # the same trace on the oracle
+def _oracle_replay(o, L, trace, x, pts, keys, evk, hoist=False):
+    """the same trace on the oracle; hoist=True groups consecutive rotations of one source exactly as hml_replay does"""
+    N = o.N
     h = {"x": x}
-    for op in trace:
+    i = 0
+    while i < len(trace):
+        op = trace[i]
         if op[0] == "hrotate":
+            j = i
+            if hoist:
+                while j < len(trace) and trace[j][0] == "hrotate" and trace[j][2] == op[2] and trace[j][1] != op[2] \
+                        and trace[j][1] not in [t[1] for t in trace[i:j]]:
+                    j += 1
+            if j - i >= 2:
+                outs = o.hrotate_hoisted(L, h[op[2]], [keys[t[3]] for t in trace[i:j]], L, [pow(5, t[3], 2 * N) for t in trace[i:j]])
+                for t, out in zip(trace[i:j], outs):
+                    h[t[1]] = out
+                i = j
+                continue
             h[op[1]] = o.hrotate(L, h[op[2]], keys[op[3]], L, pow(5, op[3], 2 * N))
         elif op[0] == "pmult":
             h[op[1]] = o.pmult(L, h[op[2]], pts[op[3]])
+        elif op[0] == "padd":
+            h[op[1]] = o.padd(L, h[op[2]], pts[op[3]])
         elif op[0] == "hadd":
             h[op[1]] = o.hadd(L, h[op[2]], h[op[3]])
         elif op[0] == "hmult":
             h[op[1]] = o.hmult(L, h[op[2]], h[op[3]], evk, L)
-    assert np.array_equal(to_host(env["y"]), h["y"])
-    assert np.array_equal(to_host(env["z"]), h["z"])
+        i += 1
+    return h
+
+
+@pytest.mark.parametrize("N,ML,A,L,shape", [(2048, 6, 2, 5, "bsgs"), (8192, 6, 2, 5, "bsgs"), (8192, 7, 3, 7, "rotsum")])
+def test_op_sequence_replay_matches_oracle(N, ML, A, L, shape):
+    """BASELINE.json configs[4]: synthetic rotation-heavy sequences replayed through hml_replay_* — plain launches, one CUDA
+    graph (run twice: the graph must replay), and with hoisted rotations against the oracle's own hoisted definition."""
+    from homulator_b200.replay import bsgs_trace, rotsum_trace, trace_counts
+    ctx, o = hml.Context(N=N, max_level=ML, alpha=A), Oracle(N, 36, ML, A)
+    Oracle.set_threads(0)
+    beta = -(-L // A)
+    trace = bsgs_trace(3, 2) if shape == "bsgs" else rotsum_trace(5)
+    cnt = trace_counts(trace)
+    assert cnt["hmult"] == 1 and cnt["hrotate"] == (3 if shape == "bsgs" else 5)
+    rots = sorted({op[3] for op in trace if op[0] == "hrotate"})
+    x = uniform_limbs(o.moduli[:L], N, 1, lead=(2,))
+    pts = {i: uniform_limbs(o.moduli[:L], N, 100 + i) for i in range(6)}
+    keys = {r: uniform_limbs(o.moduli[:L] + o.moduli[ML:], N, 200 + r, lead=(beta, 2)) for r in rots}
+    evk = uniform_limbs(o.moduli[:L] + o.moduli[ML:], N, 300, lead=(beta, 2))
+    dx, dp, dk, de = to_dev(x), {k: to_dev(v) for k, v in pts.items()}, {k: to_dev(v) for k, v in keys.items()}, to_dev(evk)
+    want = _oracle_replay(o, L, trace, x, pts, keys, evk)
+    want_h = _oracle_replay(o, L, trace, x, pts, keys, evk, hoist=True)
+    assert not np.array_equal(want["z"], want_h["z"])   # hoisting is a different (equally valid) function bit for bit
+    for graph in (False, True):
+        for hoist in (False, True):
+            rp = hml.Replay(ctx, L, trace, graph=graph, hoist=hoist).bind(dx, dp, dk, de)
+            for _ in range(3 if graph else 1):
+                rp.run()
+            w = want_h if hoist else want
+            assert np.array_equal(to_host(rp.result("y")), w["y"]), (graph, hoist)
+            assert np.array_equal(to_host(rp.result("z")), w["z"]), (graph, hoist)
+            rp.close()
+    Oracle.set_threads(1)
+
+
+def test_replay_rejects_malformed_traces():
+    ctx = hml.Context(N=1024, max_level=4, alpha=2)
+    for bad in ([("hadd", "y", "nope", "x")], [("hmult", "z", "x", "x"), ("hadd", "w", "z", "x")], [("hmult", "x2", "x", "x"), ("pmult", "x2", "x", 0)]):
+        with pytest.raises((hml.HmlError, ValueError)):
+            hml.Replay(ctx, 3, bad)
+    rp = hml.Replay(ctx, 3, [("hrotate", "a", "x", 1)])
+    x = ctx.uniform([0, 1, 2], 1, lead=(2,))
+    with pytest.raises(hml.HmlError):
+        rp.bind(x, {}, {}, None)       # rotation 1 has no key
+    with pytest.raises(hml.HmlError):
+        rp.run()                       # not bound
+    rp.close()
+
+
+def test_hoisted_rotations_north_star(north_star):
+    """hml_hrotate_hoisted at BASELINE.json's config: 4 rotations of one ciphertext sharing one ModUp, bit-exact against the
+    oracle's hoisted definition (and different from the textbook rotation, which stays pinned by its own test)."""
+    ctx, o, a, b, evk = north_star
+    L, N = 35, 65536
+    gs = [pow(5, r, 2 * N) for r in (1, 2, 7)] + [2 * N - 1]
+    rks = [evk, uniform_limbs(o.moduli[:L] + o.moduli[45:], N, 811, lead=(3, 2)), evk, evk]
+    want = o.hrotate_hoisted(L, a, rks, L, gs)
+    dk = [to_dev(k) for k in rks]
+    got = ctx.hrotate_hoisted(L, to_dev(a), dk, gs)
+    for w, g in zip(want, got):
+        assert np.array_equal(to_host(g), w)
+    assert not np.array_equal(want[0], o.hrotate(L, a, evk, L, gs[0]))
 
 
 @pytest.mark.parametrize("N,ML,A,L", [(65536, 24, 6, 24), (65536, 26, 9, 26), (65536, 26, 9, 11), (16384, 12, 4, 9)])

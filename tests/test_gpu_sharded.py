@@ -75,134 +75,97 @@ def test_sharded_keyswitch_emulated_ranks(N, ML, L, A, world):
     assert np.array_equal(one0, want0) and np.array_equal(one1, want1)
 
 
-def sharded_keyswitch_p2p_emulated(ctxs, L, d, evk, world, reps=2):
-    """Peer-direct variant with the ranks emulated on one GPU and one stream: every rank's conversions read the other ranks'
-    gather buffers through per-source offsets, ordered by the epoch flags (signals are enqueued before the waits that need
-    them).  Runs `reps` key switches back to back (buffer reuse across epochs)."""
-    A, N = ctxs[0].alpha, ctxs[0].N
-    lays = [hml.shard_layout(L, A, r, world) for r in range(world)]
-    g1 = [c.dev_alloc(world * lays[r]["gather1_slots"] * N) for r, c in enumerate(ctxs)]
-    g2 = [c.dev_alloc(world * 2 * lays[r]["gather2_slots"] * N) for r, c in enumerate(ctxs)]
-    fl = [c.dev_alloc(2 * world) for c in ctxs]
-    sh = [hml.ShardP2P(c, L, r, world, g1, g2, fl) for r, c in enumerate(ctxs)]
-    d_own, evk_own = [], []
-    for r, lay in enumerate(lays):
-        own_e = lay["own_q"] + [L + j for j in lay["own_p"]]
-        d_own.append(to_dev(d[lay["own_q"]] if lay["own_q"] else np.zeros((1, N), dtype=np.uint64)))
-        evk_own.append(to_dev(evk[:, :, own_e]) if own_e else None)
-    for _ in range(reps):
-        for r in range(world):
-            sh[r].begin(d_own[r])
-        for r in range(world):
-            sh[r].mid(d_own[r], evk_own[r])
-        outs = [sh[r].end() for r in range(world)]
-    out0, out1 = np.zeros((L, N), dtype=np.uint64), np.zeros((L, N), dtype=np.uint64)
-    for r in range(world):
-        if lays[r]["own_q"]:
-            out0[lays[r]["own_q"]] = to_host(outs[r][0])
-            out1[lays[r]["own_q"]] = to_host(outs[r][1])
-    return out0, out1
+def _split(o, L, world, a, evk):
+    """owned-limb slices of a ciphertext-like array [.., L, N] and of a key [beta][2][E][N] for every rank"""
+    A = o.alpha
+    own = [list(range(r, L, world)) for r in range(world)]
+    own_e = [[e for e in range(L + A) if e % world == r] for r in range(world)]
+    a_own = [to_dev(a[..., own[r], :]) if own[r] else None for r in range(world)]
+    evk_own = [to_dev(evk[:, :, own_e[r]]) if own_e[r] else None for r in range(world)]
+    return own, a_own, evk_own
 
 
-@pytest.mark.parametrize("N,ML,L,A,world", [(256, 7, 7, 3, 2), (256, 7, 7, 3, 3), (1024, 6, 5, 2, 4), (8192, 9, 8, 3, 2),
+@pytest.mark.parametrize("N,ML,L,A,world", [(256, 7, 7, 3, 2), (256, 7, 7, 3, 3), (1024, 6, 5, 2, 4), (8192, 9, 8, 3, 2), (8192, 9, 9, 3, 8),
                                              (65536, 45, 35, 15, 4)])
-def test_sharded_keyswitch_peer_direct_emulated_ranks(N, ML, L, A, world):
+def test_sharded_ops_through_the_c_abi_emulated_ranks(N, ML, L, A, world):
+    """hml_group_op: keyswitch, hrotate, hmult and rescale on limb-sharded operands, every op ONE C-ABI call that composes the
+    limb-local phases and the exchanges inside the library (homulator_b200/csrc/shard.cu).  The ranks share this GPU and one
+    stream (signals are enqueued before the waits that need them, so nothing ever spins); the base conversions read the other
+    ranks' gather buffers through per-source offsets exactly as they do over NVLink.  Against the oracle's unsharded ops;
+    every op runs twice (buffer reuse across epochs)."""
     o = Oracle(N, 36, ML, A)
     Oracle.set_threads(0)
     beta = -(-L // A)
-    d = uniform_limbs(o.moduli[:L], N, 2100 + L)
-    evk = uniform_limbs(o.moduli[:L] + o.moduli[ML:], N, 2101, lead=(beta, 2))
-    want0, want1 = o.keyswitch(L, d, evk, L)
-    Oracle.set_threads(1)
-    ctxs = [hml.Context(N=N, max_level=ML, alpha=A) for _ in range(world)]
-    got0, got1 = sharded_keyswitch_p2p_emulated(ctxs, L, d, evk, world)
-    assert np.array_equal(got0, want0) and np.array_equal(got1, want1)
-
-
-def _emulated_shards(ctxs, L, world):
-    N = ctxs[0].N
-    lays = [hml.shard_layout(L, ctxs[0].alpha, r, world) for r in range(world)]
-    g1 = [c.dev_alloc(world * lays[r]["gather1_slots"] * N) for r, c in enumerate(ctxs)]
-    g2 = [c.dev_alloc(world * 2 * lays[r]["gather2_slots"] * N) for r, c in enumerate(ctxs)]
-    fl = [c.dev_alloc(3 * world) for c in ctxs]
-    rb = [c.dev_alloc(2 * N) for c in ctxs]
-    return [hml.ShardP2P(c, L, r, world, g1, g2, fl, rb) for r, c in enumerate(ctxs)], lays
-
-
-@pytest.mark.parametrize("N,ML,L,A,world", [(256, 7, 7, 3, 2), (1024, 6, 5, 2, 3), (8192, 9, 8, 3, 4), (8192, 9, 9, 3, 2)])
-def test_sharded_hrotate_and_hmult_peer_direct_emulated_ranks(N, ML, L, A, world):
-    """Whole ops on limb-sharded ciphertexts (automorphism / tensor product / additions limb-local, key switch and rescale with
-    peer-direct exchanges), ranks emulated phase by phase on one stream, against the oracle's unsharded hrotate and hmult."""
-    o = Oracle(N, 36, ML, A)
-    Oracle.set_threads(0)
-    beta = -(-L // A)
-    a = uniform_limbs(o.moduli[:L], N, 2200, lead=(2,))
-    b = uniform_limbs(o.moduli[:L], N, 2201, lead=(2,))
+    a = uniform_limbs(o.moduli[:L], N, 2200 + L, lead=(2,))
+    b = uniform_limbs(o.moduli[:L], N, 2201 + L, lead=(2,))
     evk = uniform_limbs(o.moduli[:L] + o.moduli[ML:], N, 2202, lead=(beta, 2))
     g = 25
+    want_ks = o.keyswitch(L, a[1], evk, L)
     want_rot = o.hrotate(L, a, evk, L, g)
     want_mul = o.hmult(L, a, b, evk, L)
+    want_rs = np.stack([o.rescale(L, b[0]), o.rescale(L, b[1])])
     Oracle.set_threads(1)
     ctxs = [hml.Context(N=N, max_level=ML, alpha=A) for _ in range(world)]
-    shs, lays = _emulated_shards(ctxs, L, world)
+    group = hml.Shard.local_group(ctxs, L)
+    for sh in group:
+        sh.prepare(L)
     R = range(world)
-    own = [lays[r]["own_q"] for r in R]
-    a_own = [to_dev(a[:, own[r]]) for r in R]
-    b_own = [to_dev(b[:, own[r]]) for r in R]
-    evk_own = [to_dev(evk[:, :, own[r] + [L + j for j in lays[r]["own_p"]]]) for r in R]
-    # hrotate, twice (epochs)
+    own, a_own, evk_own = _split(o, L, world, a, evk)
+    _, b_own, _ = _split(o, L, world, b, evk)
+    nq = [len(own[r]) for r in R]
+    keep = [[i for i in own[r] if i < L - 1] for r in R]
+
+    def empty(r, *shape):
+        return ctxs[r].empty(*shape)
+
+    def assemble(outs, idx, shape):
+        got = np.zeros(shape, dtype=np.uint64)
+        for r in R:
+            if idx[r]:
+                got[..., idx[r], :] = to_host(outs[r])[..., :len(idx[r]), :]
+        return got
+
     for _ in range(2):
-        sig = [shs[r].hrotate_pre(a_own[r], g) for r in R]
-        outs = [ctxs[r].empty(2, shs[r].nq, N) for r in R]
-        for r in R:
-            shs[r].begin(sig[r][1])
-        for r in R:
-            shs[r].mid(sig[r][1], evk_own[r])
-        for r in R:
-            k0, _ = shs[r].end(o1=outs[r][1])
-            shs[r].hrotate_post(sig[r], k0, outs[r])
-    got = np.zeros((2, L, N), dtype=np.uint64)
-    for r in R:
-        got[:, own[r]] = to_host(outs[r])
-    assert np.array_equal(got, want_rot)
-    # hmult
-    pre = [shs[r].hmult_pre(a_own[r], b_own[r]) for r in R]
-    for r in R:
-        shs[r].begin(pre[r][2])
-    for r in R:
-        shs[r].mid(pre[r][2], evk_own[r])
-    cs = []
-    for r in R:
-        k0, k1 = shs[r].end()
-        cs.append(shs[r].hmult_post(pre[r][0], pre[r][1], k0, k1))
-    for r in R:
-        shs[r].rescale_begin(cs[r])
-    res = [shs[r].rescale_end(cs[r]) for r in R]
-    got = np.zeros((2, L - 1, N), dtype=np.uint64)
-    for r in R:
-        keep = [i for i in own[r] if i < L - 1]
-        if keep:
-            got[:, keep] = to_host(res[r].contiguous())
-    assert np.array_equal(got, want_mul)
-
-
-def test_fused_exchange_with_device_side_epochs_on_two_streams():
-    """The one-launch signal + wait (hml_shard_sync) with device-side epoch counters — the form the multi-GPU path and its CUDA
-    graph use — on ONE GPU: two emulated ranks, each on its own stream, so that a rank's spin-wait runs while the other rank's
-    kernels make progress.  Three key switches and one hmult back to back, against the oracle (tests/sp_fused_exchange.py,
-    in a child process: a spin-wait that times out traps and would take this process's CUDA context with it)."""
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "sp_fused_exchange.py")], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "FUSED_EXCHANGE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+        o0 = [empty(r, max(nq[r], 1), N) for r in R]
+        o1 = [empty(r, max(nq[r], 1), N) for r in R]
+        d_own = [x[1].contiguous() if x is not None else None for x in a_own]
+        hml.group_op(group, "keyswitch", L, d_own, key=evk_own, out0=o0, out1=o1)
+        assert np.array_equal(assemble(o0, own, (L, N)), want_ks[0]) and np.array_equal(assemble(o1, own, (L, N)), want_ks[1])
+        rot = [empty(r, 2, max(nq[r], 1), N) for r in R]
+        hml.group_op(group, "hrotate", L, a_own, key=evk_own, out0=rot, galois_elt=g)
+        assert np.array_equal(assemble(rot, own, (2, L, N)), want_rot)
+        mul = [empty(r, 2, max(len(keep[r]), 1), N) for r in R]
+        hml.group_op(group, "hmult", L, a_own, b=b_own, key=evk_own, out0=mul)
+        assert np.array_equal(assemble(mul, keep, (2, L - 1, N)), want_mul)
+        for _ in range(2):  # rescale straight after a rescale: the rescale buffer is reused (write-after-read ordering)
+            rs = [empty(r, 2, max(len(keep[r]), 1), N) for r in R]
+            hml.group_op(group, "rescale", L, b_own, out0=rs)
+            assert np.array_equal(assemble(rs, keep, (2, L - 1, N)), want_rs)
+    for sh in group:
+        sh.check()
+        sh.close()
 
 
 def test_peer_direct_needs_the_tcgen05_conversion():
-    ctx = hml.Context(N=64, max_level=5, alpha=3)  # N < 128: the FP64 tensor-core kernel has no per-source offsets
-    g1, g2, fl = ctx.dev_alloc(2 * 1 * 64), ctx.dev_alloc(2 * 2 * 2 * 64), ctx.dev_alloc(4)
-    sh = hml.ShardP2P(ctx, 2, 0, 2, [g1, g1], [g2, g2], [fl, fl])
-    d = ctx.uniform([0], 1)
-    evk = ctx.uniform([0, 1, 2], 2, lead=(1, 2))
+    ctxs = [hml.Context(N=64, max_level=5, alpha=3) for _ in range(2)]  # N < 128: the FP64 tensor-core kernel has no per-source offsets
+    group = hml.Shard.local_group(ctxs, 2)
     with pytest.raises(hml.HmlError):
-        ctx._chk(ctx.lib.hml_keyswitch_shard_mid_p2p(ctx.h, 2, 0, 2, d.data_ptr(), sh.p1, evk.data_ptr(), g2, None))
+        group[0].prepare(2)
+    for sh in group:
+        sh.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
+def test_local_group_across_devices():
+    """one process driving one rank per DEVICE (hml_shard_connect_local: peer access, fused one-launch exchanges) — the mode the
+    CLI's [cluster] argument uses"""
+    n = min(torch.cuda.device_count(), 4)
+    r = subprocess.run([os.path.join(ROOT, "homulator_b200", "Homulator.run"), os.path.join(ROOT, "config", "config_4.cfg"), "hmult", "45", "35", "15",
+                        str(n), "--iters", "3", "--warmup", "1", "--verify"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    import json
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["cluster"] == n and line["gpus_used"] == n and line["sharded_matches_one_gpu"] is True
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")

@@ -196,3 +196,39 @@ def test_negative_control_swapped_key_components_do_not_decrypt():
     got = sc.decrypt(ct, L - 1)
     prod = negacyclic_mul(ma, ma, N)
     assert max(abs(got[k] - prod[k] / sc.o.moduli[L - 1]) for k in range(N)) > 2 ** 60
+
+
+@pytest.mark.parametrize("N,ML,L,A,KQ", [(64, 4, 4, 2, 4), (64, 5, 3, 2, 5), (128, 6, 6, 3, 6)])
+def test_hoisted_rotations_decrypt_to_the_automorphisms(N, ML, L, A, KQ):
+    """orc_hrotate_hoisted (one ModUp shared by all rotations, the automorphism applied to the extended digits) is a
+    different function from orc_hrotate bit for bit, and an equally valid rotation: every output decrypts to sigma_g(m)."""
+    sc = Scheme(N, ML, A, seed=3000 + N + L)
+    gs = [pow(5, r, 2 * N) for r in (1, 2, 5)] + [2 * N - 1]
+    rks = [sc.switch_key(automorph_coeff(sc.s, g, N), KQ) for g in gs]
+    msg = [(1 << 30) * sc.rnd.randint(-8, 8) for _ in range(N)]
+    ct = sc.encrypt(msg, L)
+    outs = sc.o.hrotate_hoisted(L, ct, rks, KQ, gs)
+    differs = 0
+    for g, rk, out in zip(gs, rks, outs):
+        got = sc.decrypt(out, L)
+        want = automorph_coeff(msg, g, N)
+        assert max(abs(got[k] - want[k]) for k in range(N)) < 64 * N
+        differs += int(not np.array_equal(out, sc.o.hrotate(L, ct, rk, KQ, g)))
+    assert differs > 0   # not the textbook function: that is why it has its own oracle definition
+
+
+def test_keyswitch_equals_its_two_halves():
+    N, ML, L, A = 64, 5, 5, 2
+    sc = Scheme(N, ML, A, seed=11)
+    key = sc.switch_key(sc.s, L)
+    d = sc.to_eval(sc.uniform(1 << 100), list(range(L)))
+    t = sc.o.modup(L, d)
+    assert t.shape == (3, L + A, N)
+    for j in range(3):   # a digit keeps its own limbs untouched
+        for i in range(j * A, min(L, (j + 1) * A)):
+            assert np.array_equal(t[j, i], d[i])
+    k0, k1 = sc.o.keyswitch(L, d, key, L)
+    o0, o1 = np.empty_like(k0), np.empty_like(k1)
+    from orc import lib, _p
+    lib().orc_keyswitch_digits(sc.o.h, L, _p(t), _p(key), L, _p(o0), _p(o1))
+    assert np.array_equal(o0, k0) and np.array_equal(o1, k1)
