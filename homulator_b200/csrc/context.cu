@@ -68,10 +68,15 @@ extern "C" int hml_profile_end(hml_ctx *ctx, hml_profile *out) {
   memset(out, 0, sizeof(*out));
   cudaEvent_t prev = ctx->prof.start;
   cudaError_t e = cudaSuccess;
+  static const bool dump = getenv("HML_PROFILE_DUMP") != nullptr;  // per-launch-group times on stderr (tuning aid)
+  static const char *cls_name[HML_CLS_COUNT] = {"NTT", "INTT", "BCONV", "EWE", "AUTO"};
+  int idx = 0;
   for (auto &m : ctx->prof.marks) {
     if (e == cudaSuccess) e = cudaEventSynchronize(m.second);
     float ms = 0.f;
     if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, prev, m.second);
+    if (dump && e == cudaSuccess) fprintf(stderr, "[hml profile] %2d %-5s %8.2f us\n", idx, m.first >= 0 && m.first < HML_CLS_COUNT ? cls_name[m.first] : "?", ms * 1e3);
+    ++idx;
     if (e == cudaSuccess && m.first >= 0 && m.first < HML_CLS_COUNT) {
       out->us[m.first] += ms * 1e3;
       out->launches[m.first]++;

@@ -46,7 +46,7 @@ def test_cli_runs_every_op_at_the_north_star_config(op):
     if op in ("hadd", "pmult", "padd"):
         assert ex["ewe_limbs"] == 70
     # the per-kernel-class report (reference Statistic dump, include/Staistics.h:6-40)
-    assert "NTT_(c)" in out and "HBM_(c)" in out
+    assert "NTT_(0) :" in out and "BCONV_(0) :" in out and "HBM_(0) :" in out
 
 
 def test_cli_accepts_the_cluster_argument_and_rejects_bad_levels():
