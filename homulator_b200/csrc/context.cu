@@ -31,6 +31,9 @@ int fail(hml_ctx *ctx, int code, const std::string &msg) {
   return code;
 }
 
+// the transform tables as seen from stream s: the batch path's second lane has its own queue counters (ntt_fused.cu)
+static const NttTables &tabs_for(hml_ctx *ctx, cudaStream_t s) { return (ctx->s_lane && s == ctx->s_lane) ? ctx->tabs_lane : ctx->tabs; }
+
 namespace hml {
 void ws_enter(hml_ctx *ctx, cudaStream_t s) {
   if (ctx->have_last && ctx->last_stream != s) {
@@ -183,6 +186,17 @@ static int ctx_init_device(hml_ctx *ctx) {
   if ((rc = upload(ctx, mc, &ctx->mc))) return rc;
   ctx->tabs.fwd_rows = ctx->tw_fwd_rows; ctx->tabs.inv_rows = ctx->tw_inv_rows;
   ctx->tabs.fwd = ctx->tw_fwd; ctx->tabs.inv = ctx->tw_inv; ctx->tabs.mc = ctx->mc;
+  if (two_pass) {  // queue + dependency counters of the single-launch transform, one block per stream lane
+    const size_t words = ntt_fused_ctrl_words();
+    CU_TRY(ctx, cudaMalloc((void **)&ctx->ntt_ctrl, 2 * words * sizeof(unsigned)));
+    CU_TRY(ctx, cudaMemset(ctx->ntt_ctrl, 0, 2 * words * sizeof(unsigned)));
+    ctx->tabs.fused_ctrl = ctx->ntt_ctrl;
+    ctx->tabs_lane = ctx->tabs;
+    ctx->tabs_lane.fused_ctrl = ctx->ntt_ctrl + words;
+  } else {
+    ctx->tabs.fused_ctrl = nullptr;
+    ctx->tabs_lane = ctx->tabs;
+  }
   return HML_OK;
 }
 
@@ -242,7 +256,7 @@ extern "C" void hml_ctx_destroy(hml_ctx *ctx) {
     for (auto *o : kv.second.d_off1) cudaFree(o);
     for (auto &u : kv.second.up) { cudaFree(u.d_mat); cudaFree(u.d_img); }
   }
-  cudaFree(ctx->tw_fwd); cudaFree(ctx->tw_inv); cudaFree(ctx->tw_fwd_rows); cudaFree(ctx->tw_inv_rows); cudaFree(ctx->mc); cudaFree(ctx->ws); cudaFree(ctx->stage);
+  cudaFree(ctx->tw_fwd); cudaFree(ctx->tw_inv); cudaFree(ctx->tw_fwd_rows); cudaFree(ctx->tw_inv_rows); cudaFree(ctx->mc); cudaFree(ctx->ws); cudaFree(ctx->stage); cudaFree(ctx->ntt_ctrl);
   if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
   if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
   if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
@@ -442,6 +456,7 @@ static int ntt_api(hml_ctx *ctx, bool inverse, const uint64_t *in, uint64_t *out
   for (uint32_t i = 0; i < n_limbs; ++i)
     if (mod_idx[i] >= ctx->p.n_mod()) return fail(ctx, HML_ERR_INVALID, "modulus index out of range");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
+  ws_enter(ctx, (cudaStream_t)stream);  // the transform's queue counters are per ctx, like the workspace
   for (uint32_t off = 0; off < n_limbs; off += NTT_MAX_LIMBS) {
     const uint32_t n = std::min<uint32_t>(NTT_MAX_LIMBS, n_limbs - off);
     LimbMap lm;
@@ -450,8 +465,8 @@ static int ntt_api(hml_ctx *ctx, bool inverse, const uint64_t *in, uint64_t *out
     l.n_batch = 1;
     l.in = (const u64 *)in + off * N; l.out = (u64 *)out + off * N;
     l.in_limb_stride = l.out_limb_stride = N; l.n_limbs = n; l.n_polys = 1; l.post_scale = nullptr;
-    if (inverse) launch_ntt_inverse(ctx->tabs, ctx->p.logN, lm, l, (cudaStream_t)stream);
-    else launch_ntt_forward(ctx->tabs, ctx->p.logN, lm, l, (cudaStream_t)stream);
+    if (inverse) launch_ntt_inverse(tabs_for(ctx, (cudaStream_t)stream), ctx->p.logN, lm, l, (cudaStream_t)stream);
+    else launch_ntt_forward(tabs_for(ctx, (cudaStream_t)stream), ctx->p.logN, lm, l, (cudaStream_t)stream);
     prof_mark(ctx, inverse ? HML_CLS_INTT : HML_CLS_NTT, (cudaStream_t)stream);
     ctx->exec.kernel_launches += ctx->p.logN <= NTT_SMALL_LOG ? 1 : 2;
   }
@@ -473,6 +488,7 @@ static int ntt_batch_api(hml_ctx *ctx, bool inverse, const uint64_t *in, uint64_
   for (uint32_t i = 0; i < n_limbs; ++i)
     if (mod_idx[i] >= ctx->p.n_mod()) return fail(ctx, HML_ERR_INVALID, "modulus index out of range");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
+  ws_enter(ctx, (cudaStream_t)stream);
   const size_t N = ctx->p.N;
   LimbMap lm;
   id_map(lm, mod_idx, n_limbs);
@@ -483,8 +499,8 @@ static int ntt_batch_api(hml_ctx *ctx, bool inverse, const uint64_t *in, uint64_
     l.in = (const u64 *)in + (size_t)b0 * n_limbs * N; l.out = (u64 *)out + (size_t)b0 * n_limbs * N;
     l.in_limb_stride = l.out_limb_stride = N; l.n_limbs = n_limbs; l.n_polys = 1; l.post_scale = nullptr;
     l.n_batch = std::min(per, n_batch - b0); l.in_batch_stride = l.out_batch_stride = (long long)n_limbs * N;
-    if (inverse) launch_ntt_inverse(ctx->tabs, ctx->p.logN, lm, l, (cudaStream_t)stream);
-    else launch_ntt_forward(ctx->tabs, ctx->p.logN, lm, l, (cudaStream_t)stream);
+    if (inverse) launch_ntt_inverse(tabs_for(ctx, (cudaStream_t)stream), ctx->p.logN, lm, l, (cudaStream_t)stream);
+    else launch_ntt_forward(tabs_for(ctx, (cudaStream_t)stream), ctx->p.logN, lm, l, (cudaStream_t)stream);
     prof_mark(ctx, inverse ? HML_CLS_INTT : HML_CLS_NTT, (cudaStream_t)stream);
     ctx->exec.kernel_launches += ctx->p.logN <= NTT_SMALL_LOG ? 1 : 2;
   }
@@ -591,7 +607,7 @@ int ks_modup(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d,
     NttLaunch l{};
     l.in = d.ptr; l.out = yb; l.in_limb_stride = l.out_limb_stride = N; l.n_limbs = L; l.n_polys = 1; l.post_scale = lc->modup_scale;
     l.n_batch = nb; l.in_batch_stride = d.stride; l.out_batch_stride = (long long)L * N;
-    launch_ntt_inverse(ctx->tabs, logN, lc->q_lm, l, s);
+    launch_ntt_inverse(tabs_for(ctx, s), logN, lc->q_lm, l, s);
     prof_mark(ctx, HML_CLS_INTT, s);
     ctx->exec.intt_limbs += (uint64_t)nb * L; ctx->exec.kernel_launches += npass;
   }
@@ -612,7 +628,7 @@ int ks_modup(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d,
     l.n_limbs = E; l.n_polys = beta;  // digit j skips the limbs it owns (LimbMap::skip)
     l.n_batch = nb; l.in_batch_stride = l.out_batch_stride = (long long)beta * E * N;
     l.in_f64 = l.out_f64 = npass == 2;  // doubles in from the conversion, raw lazy doubles out to the inner product
-    launch_ntt_forward(ctx->tabs, logN, lc->ext_lm, l, s);
+    launch_ntt_forward(tabs_for(ctx, s), logN, lc->ext_lm, l, s);
     prof_mark(ctx, HML_CLS_NTT, s);
     ctx->exec.ntt_limbs += (uint64_t)nb * ((uint64_t)beta * E - L); ctx->exec.kernel_launches += npass;
   }
@@ -648,7 +664,7 @@ int ks_inner(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d,
     l.in = acc; l.out = acc; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)AL * N;
     l.n_limbs = A; l.n_polys = 2 * nb; l.post_scale = lc->moddown_scale;  // acc is [nb][2][AL][N]: uniform poly stride
     l.n_batch = 1;
-    launch_ntt_inverse(ctx->tabs, logN, lc->p_lm, l, s);
+    launch_ntt_inverse(tabs_for(ctx, s), logN, lc->p_lm, l, s);
     prof_mark(ctx, HML_CLS_INTT, s);
     ctx->exec.intt_limbs += 2ull * nb * A; ctx->exec.kernel_launches += npass;
   }
@@ -696,7 +712,7 @@ int ks_tail(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, u64 *acc, u6
       f.dst = out0.ptr; f.dst_c_stride = (long long)(out1.ptr - out0.ptr); f.dst_b_stride = out0.stride;
       f.cst = lc->pinv; f.n_c = 2;
     }
-    launch_ntt_forward(ctx->tabs, logN, lc->q_lm, l, s);
+    launch_ntt_forward(tabs_for(ctx, s), logN, lc->q_lm, l, s);
     prof_mark(ctx, HML_CLS_NTT, s);
     ctx->exec.ntt_limbs += 2ull * nb * L; ctx->exec.kernel_launches += npass;
     if (fuse) ctx->exec.ewe_limbs += (uint64_t)nb * (2 * L + (add0.ptr ? L : 0) + (add1.ptr ? L : 0));
@@ -882,6 +898,7 @@ extern "C" int hml_keyswitch_shard_begin(hml_ctx *ctx, uint32_t L, uint32_t rank
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   ShardPlan *sp;
   if ((rc = get_shard_plan(ctx, L, rank, world, &sp))) return rc;
+  ws_enter(ctx, (cudaStream_t)stream);
   const size_t N = ctx->p.N;
   const uint32_t nq = sp->own_q.size();
   if (nq) {
@@ -889,7 +906,7 @@ extern "C" int hml_keyswitch_shard_begin(hml_ctx *ctx, uint32_t L, uint32_t rank
     l.n_batch = 1;
     l.in = (const u64 *)d_own; l.out = (u64 *)gather1 + (size_t)rank * sp->gq * N;
     l.in_limb_stride = l.out_limb_stride = N; l.n_limbs = nq; l.n_polys = 1; l.post_scale = sp->scale1;
-    launch_ntt_inverse(ctx->tabs, ctx->p.logN, sp->q_lm, l, (cudaStream_t)stream);
+    launch_ntt_inverse(tabs_for(ctx, (cudaStream_t)stream), ctx->p.logN, sp->q_lm, l, (cudaStream_t)stream);
     prof_mark(ctx, HML_CLS_INTT, (cudaStream_t)stream);
     ctx->exec.intt_limbs += nq; ctx->exec.kernel_launches += ctx->p.logN <= NTT_SMALL_LOG ? 1 : 2;
   }
@@ -909,7 +926,7 @@ static int shard_mid_tail(hml_ctx *ctx, ShardPlan *sp, uint32_t rank, const u64 
     l.n_batch = 1;
     l.in = ext; l.out = ext; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)ne * N;
     l.n_limbs = ne; l.n_polys = beta;
-    launch_ntt_forward(ctx->tabs, logN, sp->e_lm, l, s);
+    launch_ntt_forward(tabs_for(ctx, s), logN, sp->e_lm, l, s);
     prof_mark(ctx, HML_CLS_NTT, s);
     ctx->exec.ntt_limbs += (uint64_t)beta * ne - nq; ctx->exec.kernel_launches += npass;
   }
@@ -929,7 +946,7 @@ static int shard_mid_tail(hml_ctx *ctx, ShardPlan *sp, uint32_t rank, const u64 
     l.in = acc; l.in_limb_stride = N; l.in_poly_stride = (long long)ne * N;
     l.out = gather2 + (size_t)rank * 2 * sp->gp * N - (size_t)nq * N; l.out_limb_stride = N; l.out_poly_stride = (long long)sp->gp * N;
     l.n_limbs = np; l.n_polys = 2; l.post_scale = sp->scale2;
-    launch_ntt_inverse(ctx->tabs, logN, sp->p_lm, l, s);
+    launch_ntt_inverse(tabs_for(ctx, s), logN, sp->p_lm, l, s);
     prof_mark(ctx, HML_CLS_INTT, s);
     ctx->exec.intt_limbs += 2 * np; ctx->exec.kernel_launches += npass;
   }
@@ -983,7 +1000,7 @@ static int shard_end_run(hml_ctx *ctx, ShardPlan *sp, const u64 *gather2, const 
     l.n_batch = 1;
     l.in = vb; l.out = vb; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)nq * N;
     l.n_limbs = nq; l.n_polys = 2;
-    launch_ntt_forward(ctx->tabs, logN, sp->q_lm, l, s);
+    launch_ntt_forward(tabs_for(ctx, s), logN, sp->q_lm, l, s);
     prof_mark(ctx, HML_CLS_NTT, s);
     ctx->exec.ntt_limbs += 2 * nq; ctx->exec.kernel_launches += npass;
   }
@@ -1272,7 +1289,7 @@ int rescale_run(hml_ctx *ctx, uint32_t L, const u64 *in, long long in_poly_strid
     l.n_batch = 1;
     l.in = in + (size_t)(L - 1) * N; l.out = rb; l.in_limb_stride = l.out_limb_stride = N;
     l.in_poly_stride = in_poly_stride; l.out_poly_stride = N; l.n_limbs = 1; l.n_polys = n_polys;
-    launch_ntt_inverse(ctx->tabs, logN, lm, l, s);
+    launch_ntt_inverse(tabs_for(ctx, s), logN, lm, l, s);
     prof_mark(ctx, HML_CLS_INTT, s);
     ctx->exec.intt_limbs += n_polys; ctx->exec.kernel_launches += npass;
   }
@@ -1288,7 +1305,7 @@ int rescale_run(hml_ctx *ctx, uint32_t L, const u64 *in, long long in_poly_strid
       f.x = in; f.x_c_stride = in_poly_stride; f.x_b_stride = 0; f.z = nullptr; f.z_mask = 0;
       f.dst = out; f.dst_c_stride = out_poly_stride; f.dst_b_stride = 0; f.cst = lc->qlinv; f.n_c = (int)n_polys;
     }
-    launch_ntt_forward(ctx->tabs, logN, lc->q_lm, l, s);
+    launch_ntt_forward(tabs_for(ctx, s), logN, lc->q_lm, l, s);
     prof_mark(ctx, HML_CLS_NTT, s);
     ctx->exec.ntt_limbs += (uint64_t)n_polys * (L - 1); ctx->exec.kernel_launches += npass;
   }
@@ -1331,6 +1348,7 @@ extern "C" int hml_rescale_shard_begin(hml_ctx *ctx, uint32_t L, uint32_t rank, 
   if ((L - 1) % world != rank) return HML_OK;  // not the owner of the dropped limb
   ShardPlan *sp;
   if ((rc = get_shard_plan(ctx, L, rank, world, &sp))) return rc;
+  ws_enter(ctx, (cudaStream_t)stream);
   const size_t N = ctx->p.N;
   const uint32_t nq = sp->own_q.size();
   LimbMap lm; clear_map(lm);
@@ -1340,7 +1358,7 @@ extern "C" int hml_rescale_shard_begin(hml_ctx *ctx, uint32_t L, uint32_t rank, 
   l.in = (const u64 *)x_own; l.in_limb_stride = N; l.in_poly_stride = (long long)nq * N;
   l.out = (u64 *)r_own - (size_t)(nq - 1) * N; l.out_limb_stride = N; l.out_poly_stride = N;  // position nq-1 lands on r_own
   l.n_limbs = 1; l.n_polys = 2;
-  launch_ntt_inverse(ctx->tabs, ctx->p.logN, lm, l, (cudaStream_t)stream);
+  launch_ntt_inverse(tabs_for(ctx, (cudaStream_t)stream), ctx->p.logN, lm, l, (cudaStream_t)stream);
   prof_mark(ctx, HML_CLS_INTT, (cudaStream_t)stream);
   ctx->exec.intt_limbs += 2; ctx->exec.kernel_launches += ctx->p.logN <= NTT_SMALL_LOG ? 1 : 2;
   return check_launch(ctx, "rescale shard begin");
@@ -1378,7 +1396,7 @@ extern "C" int hml_rescale_shard_end(hml_ctx *ctx, uint32_t L, uint32_t rank, ui
       f.x = (const u64 *)x_own; f.x_c_stride = (long long)nq * N; f.x_b_stride = 0; f.z = nullptr; f.z_mask = 0;
       f.dst = (u64 *)out_own; f.dst_c_stride = (long long)nk * N; f.dst_b_stride = 0; f.cst = sp->qlinv_own; f.n_c = 2;
     }
-    launch_ntt_forward(ctx->tabs, logN, lm, l, s);
+    launch_ntt_forward(tabs_for(ctx, s), logN, lm, l, s);
     prof_mark(ctx, HML_CLS_NTT, s);
     ctx->exec.ntt_limbs += 2ull * nk; ctx->exec.kernel_launches += npass;
   }
@@ -1478,7 +1496,7 @@ int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, const u64 
     l.n_batch = 1;
     l.in = ul; l.out = acc + (size_t)E * N; l.in_limb_stride = l.out_limb_stride = N;
     l.in_poly_stride = N; l.out_poly_stride = (long long)AL * N; l.n_limbs = 1; l.n_polys = 2 * nb;
-    launch_ntt_inverse(ctx->tabs, logN, lc->last_lm, l, s);
+    launch_ntt_inverse(tabs_for(ctx, s), logN, lc->last_lm, l, s);
     prof_mark(ctx, HML_CLS_INTT, s);
     ctx->exec.intt_limbs += 2ull * nb; ctx->exec.kernel_launches += 2;
   }
@@ -1497,7 +1515,7 @@ int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, const u64 
     f.z = d0; f.z_c_stride = (long long)(d1 - d0); f.z_b_stride = (long long)PL; f.z_mask = 3;
     f.dst = ct_out; f.dst_c_stride = (long long)(L - 1) * N; f.dst_b_stride = 2ll * (L - 1) * N;
     f.cst = lc->pinv; f.cst2 = lc->qlinv; f.n_c = 2; f.x_packed = f.z_packed = 1;
-    launch_ntt_forward(ctx->tabs, logN, lc->q_lm, l, s);
+    launch_ntt_forward(tabs_for(ctx, s), logN, lc->q_lm, l, s);
     prof_mark(ctx, HML_CLS_NTT, s);
     ctx->exec.ntt_limbs += 2ull * nb * (L - 1); ctx->exec.kernel_launches += 2;
     ctx->exec.ewe_limbs += 2ull * nb * 4 * (L - 1);

@@ -99,7 +99,8 @@ struct hml_ctx {
 
   double *tw_fwd = nullptr, *tw_inv = nullptr, *tw_fwd_rows = nullptr, *tw_inv_rows = nullptr;
   hml::ModConst *mc = nullptr;
-  hml::NttTables tabs{};
+  hml::NttTables tabs{}, tabs_lane{};   // tabs_lane: the same tables with the second stream lane's queue counters
+  unsigned *ntt_ctrl = nullptr;         // 2 x ntt_fused_ctrl_words()
 
   std::map<uint32_t, hml::LevelConsts> levels;
   std::map<std::vector<uint32_t>, hml::DevBConv> bconv_cache;

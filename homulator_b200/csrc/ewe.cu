@@ -105,6 +105,21 @@ void launch_tensor3(const ModConst *mc, int N, int L, const u64 *a0, const u64 *
 // ------------------------------------------------------------------------------------------------ key-switch inner product
 // The key words of a (limb, coefficient pair) are loaded once and reused for every ciphertext of the batch
 // (the key is 60% of the traffic of an unbatched inner product).
+// An empty asm statement that "uses" every loaded register: all the loads above it must have been ISSUED before any
+// instruction below it (no instruction is emitted, so nothing waits here — the scoreboard stalls at the first real use).
+#define HML_PIN4(v) "+l"(v[0].x), "+l"(v[0].y), "+l"(v[1].x), "+l"(v[1].y)
+template <int NB>
+__device__ __forceinline__ void pin_loads(ulonglong2 (&k)[NB][2]) {
+  if constexpr (NB == 1) asm volatile("" : HML_PIN4(k[0]));
+  else if constexpr (NB == 2) asm volatile("" : HML_PIN4(k[0]), HML_PIN4(k[1]));
+  else if constexpr (NB == 3) asm volatile("" : HML_PIN4(k[0]), HML_PIN4(k[1]), HML_PIN4(k[2]));
+  else if constexpr (NB == 4) asm volatile("" : HML_PIN4(k[0]), HML_PIN4(k[1]), HML_PIN4(k[2]), HML_PIN4(k[3]));
+  else {
+    asm volatile("" : HML_PIN4(k[0]), HML_PIN4(k[1]), HML_PIN4(k[2]), HML_PIN4(k[3]));
+    asm volatile("" : HML_PIN4(k[4]), HML_PIN4(k[5]), HML_PIN4(k[6]), HML_PIN4(k[7]));
+  }
+}
+
 template <int IP_MAX_BETA>
 __global__ void __launch_bounds__(EW_THREADS) k_inner(const ModConst *__restrict__ mc, LimbMap lm, InnerArgs a) {
   pdl_wait();
@@ -136,15 +151,21 @@ __global__ void __launch_bounds__(EW_THREADS) k_inner(const ModConst *__restrict
 #pragma unroll
   for (int j = 0; j < IP_MAX_BETA; ++j)
     if (j < a.beta) tn[j] = ld_digit(0, j);
+  // every key word of the thread is requested before the first one is used: ONE memory round trip for the 3 * beta loads
+  // (converting inside the load loop made ptxas wait for each digit's pair before issuing the next)
+  ulonglong2 kraw[IP_MAX_BETA][2];
+#pragma unroll
+  for (int j = 0; j < IP_MAX_BETA; ++j)
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+      kraw[j][c] = j < a.beta ? ld2(a.evk, (((size_t)j * 2 + c) * a.evk_limbs + kl) * n2 + i2) : make_ulonglong2(0, 0);
+  pin_loads(kraw);
   double k[IP_MAX_BETA][2][2];  // [digit][component][coefficient]
 #pragma unroll
   for (int j = 0; j < IP_MAX_BETA; ++j)
-    if (j < a.beta) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const ulonglong2 kv = ld2(a.evk, (((size_t)j * 2 + c) * a.evk_limbs + kl) * n2 + i2);
-        k[j][c][0] = u64_to_f64(kv.x); k[j][c][1] = u64_to_f64(kv.y);
-      }
+    for (int c = 0; c < 2; ++c) {
+      k[j][c][0] = u64_to_f64(kraw[j][c].x); k[j][c][1] = u64_to_f64(kraw[j][c].y);
     }
   for (int b = 0; b < a.n_batch; ++b) {
     u64 *acc = a.acc + (size_t)b * a.acc_batch_stride;

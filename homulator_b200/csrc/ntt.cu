@@ -1,84 +1,10 @@
 // See ntt.cuh for the algorithm.  sm_100a only.
-#include "ntt.cuh"
-#include "launch.h"
+#include "ntt_core.cuh"
 
 #include <cstdlib>
 #include <cstring>
 
 namespace hml {
-
-// ---- asynchronous copies global -> shared
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-// bulk copy (TMA engine, no tensor map), completion on an mbarrier
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-  // no PTX labels: the helper can be inlined any number of times into one kernel
-  unsigned ok = 0;
-  do {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-// 16-byte per-thread asynchronous copy (LDGSTS), L2 only
-__device__ __forceinline__ void cp_async16(unsigned smem_dst, const void *gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int PENDING>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
-
-// ------------------------------------------------------------------------------------------------
-// The 16-point network.  Level T (0..3) pairs registers D = 8 >> T apart; the 2^T butterfly groups of the
-// level use w[0 .. 2^T).  Four levels = four radix-2 stages on 16 register-resident points; with the
-// registers holding points  base + stride * j  the levels are the stages of distance 8, 4, 2, 1 strides.
-// ------------------------------------------------------------------------------------------------
-template <int T>
-__device__ __forceinline__ void ct_level(double (&a)[16], const double (&w)[8], double q, double qinv) {
-  constexpr int D = 8 >> T;
-#pragma unroll
-  for (int g = 0; g < (1 << T); ++g)
-#pragma unroll
-    for (int o = 0; o < D; ++o) ct_butterfly(a[g * 2 * D + o], a[g * 2 * D + o + D], w[g], q, qinv);
-}
-template <int T>
-__device__ __forceinline__ void gs_level(double (&a)[16], const double (&w)[8], double q, double qinv) {
-  constexpr int D = 8 >> T;
-#pragma unroll
-  for (int g = 0; g < (1 << T); ++g)
-#pragma unroll
-    for (int o = 0; o < D; ++o) gs_butterfly(a[g * 2 * D + o], a[g * 2 * D + o + D], w[g], q, qinv);
-}
-// CNT contiguous twiddles from shared memory (16-byte aligned when CNT >= 2)
-template <int CNT>
-__device__ __forceinline__ void lds_run(double (&w)[8], const double *p) {
-  if constexpr (CNT == 1) {
-    w[0] = p[0];
-  } else {
-#pragma unroll
-    for (int k = 0; k < CNT / 2; ++k) {
-      const double2 v = reinterpret_cast<const double2 *>(p)[k];
-      w[2 * k] = v.x; w[2 * k + 1] = v.y;
-    }
-  }
-}
 
 // ================================================================================ column passes
 // Tile = C adjacent columns x all R1 rows = 16 * NT points for a CTA of NT threads (NT = 256: 32 KB tiles, two CTAs per
@@ -270,39 +196,6 @@ __global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_inv_col
 // Shared-memory rows are stored with their 16-byte chunks XOR-swizzled inside each 128-byte line
 // (chunk c of line g at position c ^ (g & 7)): round A's 8-byte accesses, round B's per-thread 128-byte runs and the
 // coalesced 16-byte output reads are all conflict-free.
-constexpr int ROW_TILE_BYTES = NTT_TILE * 8;
-constexpr int ROW_SMEM_BYTES = 3 * ROW_TILE_BYTES;  // twiddle blob + two data stages
-
-// Byte offsets inside a stage, each family = one per-thread base XOR a compile-time constant (+ a constant):
-//   round A, point l + 16*j:                  (pa ^ ((j & 7) << 4)) + 128 * j
-//   round B, chunk of points 16*l + 2m, 2m+1:  pb ^ (m << 4)
-//   output chunk (line 2m + l/8, chunk l%8):  (pc ^ (((2*m) & 7) << 4)) + 256 * m
-struct RowAddr {
-  unsigned pa, pb, pc;
-  __device__ __forceinline__ unsigned A(int j) const { return (pa ^ ((j & 7) << 4)) + 128 * j; }
-  __device__ __forceinline__ unsigned B(int m) const { return pb ^ (m << 4); }
-  __device__ __forceinline__ unsigned C(int m) const { return (pc ^ (((2 * m) & 7) << 4)) + 256 * m; }
-};
-__device__ __forceinline__ RowAddr row_addr(int lane, int warp) {
-  RowAddr r;
-  const int l = lane & 15, rr = 2 * warp + (lane >> 4);
-  const unsigned base = rr * 2048;
-  r.pa = base + ((l >> 1) << 4) + ((l & 1) << 3);
-  r.pb = base + l * 128 + ((l & 7) << 4);
-  r.pc = base + (l >> 3) * 128 + (((l & 7) ^ (l >> 3)) << 4);
-  return r;
-}
-
-// the warp's two rows (4 KB) of item `src_tile` (pointer to the CTA's first row): 8 chunks per lane
-__device__ __forceinline__ void row_issue(const u64 *src_tile, unsigned stage_smem, int lane, int warp) {
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int qd = lane + 32 * k, g = (qd >> 3) & 15, cpos = qd & 7;
-    const unsigned dst = stage_smem + (2 * warp + (qd >> 7)) * 2048 + g * 128 + ((cpos ^ (g & 7)) << 4);
-    cp_async16(dst, src_tile + (size_t)warp * 512 + 2 * qd);
-  }
-}
-
 // Items (ciphertext b, poly p) of one limb, walked with stride gridDim.z in the linear order b * n_polys + p.
 struct RowItem {
   int b, p;
@@ -680,6 +573,7 @@ void launch_ntt_forward(const NttTables &t, int logN, const LimbMap &lm, const N
     launch_pdl(ntt_small, dim3(1, l.n_limbs * l.n_polys * l.n_batch), 256, sizeof(double) << logN, s, t, logN, lm, l, 0);
     return;
   }
+  if (launch_ntt_fused(false, t, logN, lm, l, t.fused_ctrl, s)) return;
   launch_cols(false, t, logN, lm, l, s);
   launch_rows(false, t, logN, lm, l, s);
 }
@@ -689,6 +583,7 @@ void launch_ntt_inverse(const NttTables &t, int logN, const LimbMap &lm, const N
     launch_pdl(ntt_small, dim3(1, l.n_limbs * l.n_polys * l.n_batch), 256, sizeof(double) << logN, s, t, logN, lm, l, 1);
     return;
   }
+  if (launch_ntt_fused(true, t, logN, lm, l, t.fused_ctrl, s)) return;
   launch_rows(true, t, logN, lm, l, s);
   launch_cols(true, t, logN, lm, l, s);
 }

@@ -42,6 +42,9 @@ struct NttTables {
   const double *fwd, *inv;            // [n_mod][N]
   const double *fwd_rows, *inv_rows;  // [n_mod][N / 4096][4096]
   const ModConst *mc;                 // [n_mod]
+  // queue and dependency counters of the single-launch transform (ntt_fused.cu), ntt_fused_ctrl_words() zero-initialised words;
+  // null: two-kernel transforms.  Launches that may run CONCURRENTLY need distinct blocks.
+  unsigned *fused_ctrl;
 };
 
 // Host: permute one modulus' natural table (N entries) into the row-pass layout.  Per 16-row tile (rows r = 16 *
@@ -87,6 +90,11 @@ struct NttLaunch {
   int out_f64;                // forward only, two-pass rings, no fused epilogue: leave the raw lazy sums (|v| < 10 q) as doubles
                               // in `out` instead of canonical words (consumer: InnerArgs::ext_f64)
 };
+
+// single-launch transform (ntt_fused.cu); returns false when the shape is outside it (the caller runs the two-kernel path)
+bool launch_ntt_fused(bool inverse, const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, unsigned *ctrl, cudaStream_t s);
+size_t ntt_fused_ctrl_words();
+int ntt_fused_enabled();
 
 void launch_ntt_forward(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s);
 void launch_ntt_inverse(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s);
