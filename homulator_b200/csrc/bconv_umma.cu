@@ -254,8 +254,22 @@ struct TileWalk {
 template <int N16, bool FOLD, bool F64, int W, int NT>
 __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
 k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BConvArgs a, const uint8_t *__restrict__ img, int K, int NP,
-             int ND, int tiles_per_batch, int n_tiles, LevelMul lmul) {
+             int ND, int tiles_per_batch, int n_tiles, LevelMul lmul, const BConvJob *__restrict__ jobs, int n_jobs) {
   extern __shared__ __align__(128) unsigned char smem[];
+  // multi-conversion launch: this CTA serves job blockIdx.x % n_jobs; its view of the grid is the CTAs of that job
+  int bx = blockIdx.x, gx = gridDim.x;
+  const BConvJob *job = nullptr;
+  if (n_jobs > 0) {
+    const int jid = blockIdx.x % n_jobs;
+    job = jobs + jid;
+    bx = blockIdx.x / n_jobs; gx = ((int)gridDim.x - jid + n_jobs - 1) / n_jobs;
+    img = job->img; K = job->K; NP = job->NP; ND = job->ND;
+    a.n_src = job->n_src; a.n_dst = job->n_dst;
+    a.in += job->in_off; a.out += job->out_off;
+  }
+  auto src_pos = [&](int i) -> long long { return job ? (long long)job->src_pos[i] : (long long)src_lm.pos[i]; };
+  auto dst_mod = [&](int t) -> int { return job ? (int)job->dst_mod[t] : (int)dst_lm.mod[t]; };
+  auto dst_pos = [&](int t) -> long long { return job ? (long long)job->dst_pos[t] : (long long)dst_lm.pos[t]; };
   // the shuffle tells the compiler that `warp` is warp-uniform: TMEM addresses and target indices then live in uniform registers
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   constexpr int NBUF = NT == 512 ? 2 : 1;    // TMEM accumulator buffers = A operand buffers
@@ -285,7 +299,7 @@ k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BC
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int i = s * 16 + g * 4 + k;
-      soff[s][k] = i < a.n_src ? (a.src_off ? __ldg(a.src_off + i) : (long long)src_lm.pos[i] * a.N) + lr : -1;
+      soff[s][k] = i < a.n_src ? (a.src_off ? __ldg(a.src_off + i) : src_pos(i) * a.N) + lr : -1;
       live[s] |= (i < a.n_src ? 1u : 0u) << k;
       if (i >= a.n_src) {  // padding sources: their staging slots are never written by a copy, they stay zero
 #pragma unroll
@@ -404,8 +418,8 @@ k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BC
     tmem_ld_wait();
   };
 
-  const int n_my = (int)blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const int stride = (int)gridDim.x;
+  const int n_my = bx < n_tiles ? (n_tiles - 1 - bx) / gx + 1 : 0;
+  const int stride = gx;
   // the matrix image (a constant table) starts its trip before the programmatic dependency is resolved: asynchronous 16-byte
   // copies, the OLDEST copy group of every thread, so every later wait_group covers it
   for (uint32_t e = tid; e < (uint32_t)NP * K / 16; e += NT)
@@ -414,7 +428,7 @@ k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BC
   pdl_wait();  // the sources are another kernel's output; the outputs may still be read by one
   if (n_my > 0) {
     TileWalk wl, we;  // the loader runs STAGES tiles ahead of the epilogue
-    wl.init(blockIdx.x, tiles_per_batch);
+    wl.init(bx, tiles_per_batch);
     we = wl;
 #pragma unroll
     for (int d = 0; d < STAGES; ++d) {
@@ -433,11 +447,11 @@ k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BC
     for (int t = tid; t < ND + 4; t += NT) {
       double2 c = make_double2(1.0, 1.0);
       if (t < ntv) {
-        const ModConst m = mc[t < a.n_dst ? dst_lm.mod[t] : a.fold_mod];
+        const ModConst m = mc[t < a.n_dst ? dst_mod(t) : a.fold_mod];
         c = make_double2(m.q, m.qinv);
       }
       tq[t] = c;
-      toff[t] = t < a.n_dst ? (long long)dst_lm.pos[t] * a.N * 8 : 0;
+      toff[t] = t < a.n_dst ? dst_pos(t) * a.N * 8 : 0;
     }
     if (warp == 0) {
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "n"(256 * NBUF) : "memory");
@@ -546,7 +560,45 @@ static void launch_umma_t(const ModConst *mc, const LimbMap &src_lm, const LimbM
   }
   const int grid = std::min(n_tiles, (NT == 512 ? 1 : 2) * std::max(1, n_sm[dev & 63]));
   launch_pdl(k_bconv_umma<N16, FOLD, F64, W, NT>, dim3(grid), dim3(NT), smem, s, mc, src_lm, dst_lm, a, im.img, im.K, im.NP, im.ND, tiles_per_batch, n_tiles,
-             LevelMul{256u, 65536u, 16777216u});
+             LevelMul{256u, 65536u, 16777216u}, (const BConvJob *)nullptr, 0);
+}
+
+// several conversions with <= 16 sources each in one launch (the ModUp digits of a key switch): two CTAs per SM as above
+template <bool F64, int W>
+static void launch_umma_multi_t(const ModConst *mc, const BConvJob *d_jobs, int n_jobs, const BConvArgs &a, int K, int NP, int ND, cudaStream_t s) {
+  constexpr int N16 = 1, NT = 256, STAGES = 3;
+  const int tiles_per_batch = a.N / UMMA_TM, n_tiles = tiles_per_batch * a.n_batches;  // per job
+  const size_t need = (size_t)UMMA_TM * K + (size_t)NP * K + (size_t)(ND + 4) * 24 + 32 + (size_t)STAGES * N16 * 4 * UMMA_THREADS * 8;
+  const size_t smem = std::max<size_t>(need, 80 * 1024);
+  static PerDeviceOnce once;
+  static int n_sm[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (once.first()) {
+    cudaFuncSetAttribute(k_bconv_umma<N16, false, F64, W, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+    cudaDeviceGetAttribute(&n_sm[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int grid = std::max(n_jobs, std::min(n_tiles * n_jobs, 2 * std::max(1, n_sm[dev & 63])));
+  launch_pdl(k_bconv_umma<N16, false, F64, W, NT>, dim3(grid), dim3(NT), smem, s, mc, LimbMap{}, LimbMap{}, a, (const uint8_t *)nullptr, K, NP, ND,
+             tiles_per_batch, n_tiles, LevelMul{256u, 65536u, 16777216u}, d_jobs, n_jobs);
+}
+
+bool launch_bconv_umma_multi(const ModConst *mc, const BConvJob *d_jobs, const BConvImage *ims, const int *n_dst, int n_jobs, const BConvArgs &a,
+                             cudaStream_t s) {
+  if (n_jobs < 2 || n_jobs > 8 || !d_jobs || a.N < 128 || a.N % 128 != 0 || a.step1 || a.fold || a.src_off || !bconv_umma_enabled() ||
+      umma_ctas_per_sm() != 2)
+    return false;
+  int K = 0, NP = 0, ND = 0, waste3 = 0, waste4 = 0;
+  for (int j = 0; j < n_jobs; ++j) {
+    if (!ims[j].img || ims[j].n16 != 1 || ims[j].fold) return false;
+    K = std::max(K, ims[j].K); NP = std::max(NP, ims[j].NP); ND = std::max(ND, ims[j].ND);
+    const int c = (n_dst[j] + 1) / 2;  // targets per epilogue warp
+    waste3 += ((c + 2) / 3) * 3 - c; waste4 += ((c + 3) / 4) * 4 - c;
+  }
+  // the shared-memory carve-up of a CTA follows ITS job's (K, NP, ND); the launch reserves the largest
+  if (waste3 <= waste4) a.out_f64 ? launch_umma_multi_t<true, 3>(mc, d_jobs, n_jobs, a, K, NP, ND, s) : launch_umma_multi_t<false, 3>(mc, d_jobs, n_jobs, a, K, NP, ND, s);
+  else a.out_f64 ? launch_umma_multi_t<true, 4>(mc, d_jobs, n_jobs, a, K, NP, ND, s) : launch_umma_multi_t<false, 4>(mc, d_jobs, n_jobs, a, K, NP, ND, s);
+  return true;
 }
 
 template <int N16, bool FOLD, bool F64>

@@ -239,10 +239,10 @@ extern "C" int hml_ctx_create(const char *cfg_path, uint32_t max_level, uint32_t
 }
 
 static void free_level(LevelConsts &lc) {
-  cudaFree(lc.modup_scale); cudaFree(lc.moddown_scale); cudaFree(lc.pinv); cudaFree(lc.qlinv);
+  cudaFree(lc.modup_scale); cudaFree(lc.moddown_scale); cudaFree(lc.moddown_scale_u); cudaFree(lc.pinv); cudaFree(lc.qlinv);
   for (auto &u : lc.up) { cudaFree(u.d_mat); cudaFree(u.d_img); }
   cudaFree(lc.down.d_mat); cudaFree(lc.merged_rest.d_mat); cudaFree(lc.merged_fold);
-  cudaFree(lc.down.d_img); cudaFree(lc.merged_rest.d_img);
+  cudaFree(lc.down.d_img); cudaFree(lc.merged_rest.d_img); cudaFree(lc.up_jobs);
 }
 
 extern "C" void hml_ctx_destroy(hml_ctx *ctx) {
@@ -371,6 +371,22 @@ int get_level(hml_ctx *ctx, uint32_t L, LevelConsts **out) {
     if ((rc = prepare_bconv(ctx, bt, dst_pos, lc.up.back()))) return rc;
   }
   if ((rc = upload(ctx, up_scale, &lc.modup_scale))) return rc;
+  {  // job table of the merged ModUp launch (sources at yb + j * alpha limbs, targets at ext + j * E limbs)
+    std::vector<BConvJob> jobs(beta);
+    bool ok = beta >= 2;
+    for (uint32_t j = 0; j < beta && ok; ++j) {
+      const HostBConv &hb = lc.up[j];
+      ok = hb.d_img != nullptr && hb.n_src <= 48 && hb.n_dst <= 48;
+      if (!ok) break;
+      BConvJob &jb = jobs[j];
+      memset(&jb, 0, sizeof(jb));
+      for (int i = 0; i < hb.n_src; ++i) jb.src_pos[i] = (uint16_t)i;
+      for (int t = 0; t < hb.n_dst; ++t) { jb.dst_mod[t] = hb.dst_lm.mod[t]; jb.dst_pos[t] = hb.dst_lm.pos[t]; }
+      jb.img = hb.d_img; jb.K = hb.im.K; jb.NP = hb.im.NP; jb.ND = hb.im.ND; jb.n_src = hb.n_src; jb.n_dst = hb.n_dst;
+      jb.in_off = (long long)j * A * p.N; jb.out_off = (long long)j * E * p.N;
+    }
+    if (ok && (rc = upload(ctx, jobs, &lc.up_jobs))) return rc;
+  }
   // ---- ModDown
   {
     std::vector<uint32_t> src, dst;
@@ -392,6 +408,12 @@ int get_level(hml_ctx *ctx, uint32_t L, LevelConsts **out) {
     if ((rc = prepare_bconv(ctx, bt, dst, lc.down))) return rc;
     if ((rc = upload(ctx, sc, &lc.moddown_scale))) return rc;
     if ((rc = upload(ctx, pinv, &lc.pinv))) return rc;
+    // hmult's merged path: the P-limbs plus slot E (modulus q_{L-1}, plain N^-1) in one INTT launch
+    lc.pu_lm = lc.p_lm;
+    lc.pu_lm.mod[A] = (uint16_t)(L - 1); lc.pu_lm.pos[A] = (uint16_t)E;
+    sc.push_back(mk_cst(p.n_inv[L - 1], p.mod[L - 1]));
+    if ((rc = upload(ctx, sc, &lc.moddown_scale_u))) return rc;
+    lc.pinv_last = pinv[L - 1];
   }
   // ---- hmult: ModDown merged with Rescale (matrices with P^-1 folded in and a unit row for the extra source)
   if (L >= 2) {
@@ -611,8 +633,24 @@ int ks_modup(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d,
     prof_mark(ctx, HML_CLS_INTT, s);
     ctx->exec.intt_limbs += (uint64_t)nb * L; ctx->exec.kernel_launches += npass;
   }
-  // K3 (reference :137-188): convert every digit to the limbs of the extended basis it does not own
-  for (uint32_t j = 0; j < beta; ++j) {
+  // K3 (reference :137-188): convert every digit to the limbs of the extended basis it does not own — ONE launch for all
+  // digits when they fit the tcgen05 kernel's multi-conversion form (every CTA serves one digit), else one launch per digit
+  bool merged_up = false;
+  if (lc->up_jobs && beta >= 2) {
+    BConvArgs a{};
+    a.in = yb; a.out = ext; a.step1 = nullptr; a.N = N; a.n_batches = nb;
+    a.in_batch_stride = (long long)L * N; a.out_batch_stride = (long long)beta * E * N; a.out_f64 = npass == 2;
+    std::vector<BConvImage> ims(beta);
+    std::vector<int> nd(beta);
+    for (uint32_t j = 0; j < beta; ++j) { ims[j] = lc->up[j].im; nd[j] = lc->up[j].n_dst; }
+    merged_up = launch_bconv_umma_multi(ctx->mc, lc->up_jobs, ims.data(), nd.data(), (int)beta, a, s);
+    if (merged_up) {
+      prof_mark(ctx, HML_CLS_BCONV, s);
+      ctx->exec.kernel_launches++;
+      for (uint32_t j = 0; j < beta; ++j) ctx->exec.bconv_limb_macs += (uint64_t)lc->up[j].n_src * lc->up[j].n_dst * nb;
+    }
+  }
+  for (uint32_t j = 0; j < beta && !merged_up; ++j) {
     const uint32_t lo = j * A;
     BConvArgs a{};
     a.in = yb + (size_t)lo * N; a.out = ext + (size_t)j * E * N; a.step1 = nullptr;
@@ -638,7 +676,7 @@ int ks_modup(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d,
 // K5..K7: inner product with the key, INTT (+ step-1 scaling) of the P-limbs of both accumulators.  acc [nb][2][AL], AL >= E.
 // galois != 0: the digits are read through the automorphism X -> X^galois (hoisted rotation, see InnerArgs::galois).
 int ks_inner(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d, const u64 *evk, uint32_t evk_q_limbs, const u64 *ext, u64 *acc,
-             uint32_t AL, u64 galois, cudaStream_t s) {
+             uint32_t AL, u64 galois, cudaStream_t s, const MergedU *mu) {
   const Params &p = ctx->p;
   const size_t N = p.N;
   const uint32_t A = p.alpha, E = L + A, beta = lc->beta;
@@ -654,29 +692,36 @@ int ks_inner(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d,
     a.acc_pack_limbs = npass == 2 ? (int)L : 0;  // Q-limb accumulators only feed element-wise epilogues: packed (5 B / coefficient)
     a.galois = (unsigned)(galois & (2ull * N - 1)); a.logN = logN;
     if (a.galois == 1) a.galois = 0;
+    a.u_limb = -1;
+    if (mu) {  // hmult: u[L-1] = acc[L-1] * P^-1 + d[L-1] lands in slot E of each accumulator (host copy of the constant)
+      a.u_limb = (int)L - 1; a.u_slot = (int)E; a.u_add = mu->add; a.u_add_comp_stride = mu->comp_stride; a.u_add_batch_stride = mu->batch_stride;
+      a.u_cst = lc->pinv_last;
+      ctx->exec.ewe_limbs += 4ull * nb;
+    }
     launch_inner_product(ctx->mc, ip, a, s);
     prof_mark(ctx, HML_CLS_EWE, s);
     ctx->exec.ewe_limbs += 2ull * nb * E * beta; ctx->exec.kernel_launches++;
   }
-  // K6 + K7 (reference :417-487): INTT of the P-limbs of both accumulators, in place, BConv step 1 folded in
+  // K6 + K7 (reference :417-487): INTT of the P-limbs of both accumulators, in place, BConv step 1 folded in.  hmult adds
+  // one limb to the same launch: slot E (modulus q_{L-1}) = u[L-1], the Rescale INTT (reference :766-805)
   {
     NttLaunch l{};
     l.in = acc; l.out = acc; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)AL * N;
-    l.n_limbs = A; l.n_polys = 2 * nb; l.post_scale = lc->moddown_scale;  // acc is [nb][2][AL][N]: uniform poly stride
+    l.n_limbs = A + (mu ? 1 : 0); l.n_polys = 2 * nb; l.post_scale = mu ? lc->moddown_scale_u : lc->moddown_scale;  // acc is [nb][2][AL][N]
     l.n_batch = 1;
-    launch_ntt_inverse(tabs_for(ctx, s), logN, lc->p_lm, l, s);
+    launch_ntt_inverse(tabs_for(ctx, s), logN, mu ? lc->pu_lm : lc->p_lm, l, s);
     prof_mark(ctx, HML_CLS_INTT, s);
-    ctx->exec.intt_limbs += 2ull * nb * A; ctx->exec.kernel_launches += npass;
+    ctx->exec.intt_limbs += 2ull * nb * l.n_limbs; ctx->exec.kernel_launches += npass;
   }
   return HML_OK;
 }
 
 // K1..K7.  Buffers: yb [nb][L] | ext [nb][beta][E] | acc [nb][2][AL] with AL >= E limbs per accumulator.
 int ks_front(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d, const u64 *evk, uint32_t evk_q_limbs, u64 *yb,
-             u64 *ext, u64 *acc, uint32_t AL, cudaStream_t s) {
+             u64 *ext, u64 *acc, uint32_t AL, cudaStream_t s, const MergedU *mu) {
   int rc = ks_modup(ctx, lc, L, nb, d, yb, ext, s);
   if (rc) return rc;
-  return ks_inner(ctx, lc, L, nb, d, evk, evk_q_limbs, ext, acc, AL, 0, s);
+  return ks_inner(ctx, lc, L, nb, d, evk, evk_q_limbs, ext, acc, AL, 0, s, mu);
 }
 
 // K8..K10 (+ the caller's addends): ModDown of nb accumulator pairs acc [nb][2][E] -> out_c[b] = (acc_c - NTT(BConv(acc_c; P -> Q))) * P^-1 (+ add_c[b])
@@ -747,7 +792,7 @@ int ks_run(hml_ctx *ctx, uint32_t L, uint32_t nb, BatchPtr d, const u64 *evk, ui
   if (beta > 8) return fail(ctx, HML_ERR_UNSUPPORTED, "more than 8 key-switch digits (ceil(L/alpha) > 8)");
   // workspace, every buffer batch-major: yb [nb][L] | ext [nb][beta][E] | acc [nb][2][E] | vb [nb][2][L]  (limbs of N words)
   u64 *yb = ws, *ext = yb + (size_t)nb * L * N, *acc = ext + (size_t)nb * beta * E * N, *vb = acc + (size_t)nb * 2 * E * N;
-  if ((rc = ks_front(ctx, lc, L, nb, d, evk, evk_q_limbs, yb, ext, acc, E, s))) return rc;
+  if ((rc = ks_front(ctx, lc, L, nb, d, evk, evk_q_limbs, yb, ext, acc, E, s, nullptr))) return rc;
   return ks_tail(ctx, lc, L, nb, acc, vb, out0, out1, add0, add1, s);
 }
 
@@ -933,7 +978,7 @@ static int shard_mid_tail(hml_ctx *ctx, ShardPlan *sp, uint32_t rank, const u64 
   {
     InnerArgs a{};
     a.d = d_own; a.ext = ext; a.evk = evk_own; a.acc = acc; a.N = N; a.n_ext = ne; a.beta = beta;
-    a.evk_limbs = ne; a.n_batch = 1;
+    a.evk_limbs = ne; a.n_batch = 1; a.u_limb = -1;
     launch_inner_product(ctx->mc, sp->e_lm, a, s);
     prof_mark(ctx, HML_CLS_EWE, s);
     ctx->exec.ewe_limbs += 2ull * ne * beta; ctx->exec.kernel_launches++;
@@ -1465,41 +1510,11 @@ int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, const u64 
   if (beta > 8) return fail(ctx, HML_ERR_UNSUPPORTED, "more than 8 key-switch digits (ceil(L/alpha) > 8)");
   // yb [nb][L] | ext [nb][beta][E] | acc [nb][2][E+1] | wb [nb][2][L-1]; yb is free again after ModUp: ul [nb][2][N] reuses it
   u64 *yb = d2 + nb * PL, *ext = yb + (size_t)nb * L * N, *acc = ext + (size_t)nb * beta * E * N, *wb = acc + (size_t)nb * 2 * AL * N;
-  u64 *ul = yb;
-  if ((rc = ks_front(ctx, lc, L, nb, {d2, (long long)PL}, evk, evk_q_limbs, yb, ext, acc, AL, s))) return rc;
+  // u[L-1] = d_c[L-1] + acc_c[L-1] * P^-1 is produced by the inner product itself (slot E of each accumulator) and its INTT
+  // (reference Rescale INTT :766-805) rides in the launch that transforms the P-limbs: no extra launches, no re-reads
+  const MergedU mu{d0, (long long)(d1 - d0), (long long)PL};
+  if ((rc = ks_front(ctx, lc, L, nb, {d2, (long long)PL}, evk, evk_q_limbs, yb, ext, acc, AL, s, &mu))) return rc;
   const int logN = p.logN;
-  if (nb == 1) {  // u[L-1] = d_c[L-1] + acc_c[L-1] * P^-1: one ciphertext -> both components in ONE launch (the poly index is c)
-    SubMulArgs a{};
-    a.x = acc + (size_t)(L - 1) * N; a.x_poly_stride = (long long)AL * N;
-    a.y = nullptr;
-    a.z = d0 + (size_t)(L - 1) * N; a.z_poly_stride = (long long)(d1 - d0);
-    a.out = ul; a.out_poly_stride = (long long)N;
-    a.cst = lc->pinv + (L - 1); a.N = N; a.n_limbs = 1; a.n_polys = 2; a.x_packed = a.z_packed = 1;
-    launch_sub_mul_add(ctx->mc, lc->last_lm, a, s);
-    prof_mark(ctx, HML_CLS_EWE, s);
-    ctx->exec.ewe_limbs += 4; ctx->exec.kernel_launches++;
-  } else {
-    for (int c = 0; c < 2; ++c) {
-      SubMulArgs a{};
-      a.x = acc + ((size_t)c * AL + (L - 1)) * N; a.x_poly_stride = 2ll * AL * N;
-      a.y = nullptr;
-      a.z = (c ? d1 : d0) + (size_t)(L - 1) * N; a.z_poly_stride = (long long)PL;
-      a.out = ul + (size_t)c * N; a.out_poly_stride = 2ll * N;
-      a.cst = lc->pinv + (L - 1); a.N = N; a.n_limbs = 1; a.n_polys = nb; a.x_packed = a.z_packed = 1;
-      launch_sub_mul_add(ctx->mc, lc->last_lm, a, s);
-      prof_mark(ctx, HML_CLS_EWE, s);
-      ctx->exec.ewe_limbs += 2ull * nb; ctx->exec.kernel_launches++;
-    }
-  }
-  {  // INTT_{L-1}(u[L-1]) -> slot E of each accumulator (reference Rescale INTT :766-805)
-    NttLaunch l{};
-    l.n_batch = 1;
-    l.in = ul; l.out = acc + (size_t)E * N; l.in_limb_stride = l.out_limb_stride = N;
-    l.in_poly_stride = N; l.out_poly_stride = (long long)AL * N; l.n_limbs = 1; l.n_polys = 2 * nb;
-    launch_ntt_inverse(tabs_for(ctx, s), logN, lc->last_lm, l, s);
-    prof_mark(ctx, HML_CLS_INTT, s);
-    ctx->exec.intt_limbs += 2ull * nb; ctx->exec.kernel_launches += 2;
-  }
   {  // w_l = v_l * P^-1 + [r]_{q_l}, l < L-1, with r = slot_E - v[L-1] * P^-1 folded on the staged tile (reference K8 :489-519)
     BConvArgs a{};
     a.in = acc; a.in_batch_stride = (long long)AL * N; a.out = wb; a.out_batch_stride = (long long)(L - 1) * N;
@@ -1587,7 +1602,7 @@ int hrot_hoisted_run(hml_ctx *ctx, uint32_t L, const u64 *ct, uint32_t n_rot, co
     launch_automorph(p.logN, L, ct, sb, galois[r], s);  // sigma_r(c0): the addend of the ModDown epilogue
     prof_mark(ctx, HML_CLS_AUTO, s);
     ctx->exec.automorph_limbs += L; ctx->exec.kernel_launches++;
-    if ((rc = ks_inner(ctx, lc, L, 1, c1, (const u64 *)rotkeys[r], evk_q_limbs, ext, acc, E, galois[r], s))) return rc;
+    if ((rc = ks_inner(ctx, lc, L, 1, c1, (const u64 *)rotkeys[r], evk_q_limbs, ext, acc, E, galois[r], s, nullptr))) return rc;
     u64 *o = (u64 *)outs[r];
     if ((rc = ks_tail(ctx, lc, L, 1, acc, vb, {o, 0}, {o + PL, 0}, {sb, 0}, {nullptr, 0}, s))) return rc;
   }

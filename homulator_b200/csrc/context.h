@@ -32,10 +32,14 @@ struct LevelConsts {
   double2 *modup_scale = nullptr;            // [L]
   // K3: per digit, the conversion to the E - a_j other limbs (matrix in 12-bit pieces, kernel-parameter resident)
   std::vector<HostBConv> up;                 // [beta]
+  BConvJob *up_jobs = nullptr;               // [beta] device table of the one-launch form (null: digits launch one by one)
   // K4: limbs = the E extended limbs, polys = the beta digits, skip = the digit that owns the limb
   LimbMap ext_lm;
   // K6+K7 fused: INTT post-scale N^-1 * (P/p_j)^-1 mod p_j;  K8 matrix [alpha][L][3];  K10 constant P^-1 mod q_i
   double2 *moddown_scale = nullptr;          // [alpha]
+  double2 *moddown_scale_u = nullptr;        // [alpha + 1]: the same + plain N^-1 mod q_{L-1} for hmult's extra limb (slot E)
+  LimbMap pu_lm;                             // p_lm + limb alpha -> modulus q_{L-1}, pos = E
+  double2 pinv_last{};                       // P^-1 mod q_{L-1} (host copy, kernel parameter of the inner product)
   HostBConv down;
   double2 *pinv = nullptr;                   // [L]
   // Rescale: q_{L-1}^-1 mod q_l

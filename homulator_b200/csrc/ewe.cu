@@ -120,8 +120,9 @@ __device__ __forceinline__ void pin_loads(ulonglong2 (&k)[NB][2]) {
   }
 }
 
-template <int IP_MAX_BETA>
-__global__ void __launch_bounds__(EW_THREADS) k_inner(const ModConst *__restrict__ mc, LimbMap lm, InnerArgs a) {
+// MULTI: more than one ciphertext per launch (the next ciphertext's digits are prefetched while this one is multiplied)
+template <int IP_MAX_BETA, bool MULTI>
+__global__ void __launch_bounds__(EW_THREADS, 3) k_inner(const ModConst *__restrict__ mc, LimbMap lm, InnerArgs a) {
   pdl_wait();
   const int i2 = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i2 >= a.N / 2) return;
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(EW_THREADS) k_inner(const ModConst *__restrict
     ulonglong2 t[IP_MAX_BETA];
 #pragma unroll
     for (int j = 0; j < IP_MAX_BETA; ++j) t[j] = tn[j];
-    if (b + 1 < a.n_batch) {
+    if (MULTI && b + 1 < a.n_batch) {
 #pragma unroll
       for (int j = 0; j < IP_MAX_BETA; ++j)
         if (j < a.beta) tn[j] = ld_digit(b + 1, j);
@@ -191,23 +192,38 @@ __global__ void __launch_bounds__(EW_THREADS) k_inner(const ModConst *__restrict
         s11 += mulmod_var(t1, k[j][1][1], m.q, m.qinv);
       }
     const size_t comp2 = (a.acc_comp_stride ? (size_t)a.acc_comp_stride : (size_t)a.n_ext * a.N) / 2;
+    const u64 r00 = finish(s00, m), r01 = finish(s01, m), r10 = finish(s10, m), r11 = finish(s11, m);
     if (e < a.acc_pack_limbs) {  // uniform per CTA
-      st_packed2(acc + (size_t)e * a.N, a.N, i2, finish(s00, m), finish(s01, m));
-      st_packed2(acc + 2 * comp2 + (size_t)e * a.N, a.N, i2, finish(s10, m), finish(s11, m));
+      st_packed2(acc + (size_t)e * a.N, a.N, i2, r00, r01);
+      st_packed2(acc + 2 * comp2 + (size_t)e * a.N, a.N, i2, r10, r11);
     } else {
-      st2(acc, (size_t)e * n2 + i2, finish(s00, m), finish(s01, m));
-      st2(acc, comp2 + (size_t)e * n2 + i2, finish(s10, m), finish(s11, m));
+      st2(acc, (size_t)e * n2 + i2, r00, r01);
+      st2(acc, comp2 + (size_t)e * n2 + i2, r10, r11);
+    }
+    if (e == a.u_limb) {  // uniform per CTA: u = acc * P^-1 + d on the limb the rescale drops (no extra launch, no re-read)
+      const u64 *ua = a.u_add + (size_t)b * a.u_add_batch_stride + (size_t)e * a.N;
+      const ulonglong2 d0v = ld_packed2(ua, a.N, i2), d1v = ld_packed2(ua + a.u_add_comp_stride, a.N, i2);
+      const double2 c = a.u_cst;
+      st2(acc, (size_t)a.u_slot * n2 + i2, finish(mulmod_const(u64_to_f64(r00), c.x, c.y, m.q) + u64_to_f64(d0v.x), m),
+          finish(mulmod_const(u64_to_f64(r01), c.x, c.y, m.q) + u64_to_f64(d0v.y), m));
+      st2(acc, comp2 + (size_t)a.u_slot * n2 + i2, finish(mulmod_const(u64_to_f64(r10), c.x, c.y, m.q) + u64_to_f64(d1v.x), m),
+          finish(mulmod_const(u64_to_f64(r11), c.x, c.y, m.q) + u64_to_f64(d1v.y), m));
     }
   }
 }
 
-void launch_inner_product(const ModConst *mc, const LimbMap &lm, const InnerArgs &a, cudaStream_t s) {
+template <bool MULTI>
+static void launch_inner_t(const ModConst *mc, const LimbMap &lm, const InnerArgs &a, cudaStream_t s) {
   const dim3 g = ew_grid(a.N, a.n_ext);
-  if (a.beta <= 1) launch_pdl(k_inner<1>, g, EW_THREADS, 0, s, mc, lm, a);
-  else if (a.beta <= 2) launch_pdl(k_inner<2>, g, EW_THREADS, 0, s, mc, lm, a);
-  else if (a.beta <= 3) launch_pdl(k_inner<3>, g, EW_THREADS, 0, s, mc, lm, a);
-  else if (a.beta <= 4) launch_pdl(k_inner<4>, g, EW_THREADS, 0, s, mc, lm, a);
-  else launch_pdl(k_inner<8>, g, EW_THREADS, 0, s, mc, lm, a);
+  if (a.beta <= 1) launch_pdl(k_inner<1, MULTI>, g, EW_THREADS, 0, s, mc, lm, a);
+  else if (a.beta <= 2) launch_pdl(k_inner<2, MULTI>, g, EW_THREADS, 0, s, mc, lm, a);
+  else if (a.beta <= 3) launch_pdl(k_inner<3, MULTI>, g, EW_THREADS, 0, s, mc, lm, a);
+  else if (a.beta <= 4) launch_pdl(k_inner<4, MULTI>, g, EW_THREADS, 0, s, mc, lm, a);
+  else launch_pdl(k_inner<8, MULTI>, g, EW_THREADS, 0, s, mc, lm, a);
+}
+void launch_inner_product(const ModConst *mc, const LimbMap &lm, const InnerArgs &a, cudaStream_t s) {
+  if (a.n_batch > 1) launch_inner_t<true>(mc, lm, a, s);
+  else launch_inner_t<false>(mc, lm, a, s);
 }
 
 // ------------------------------------------------------------------------------------------------ (x - y) * c (+ z)

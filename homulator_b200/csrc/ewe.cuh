@@ -43,6 +43,13 @@ struct InnerArgs {
   // rotations and the rotated digits never exist in memory.  The key is read in place.
   unsigned galois;
   int logN;
+  // hmult's merged ModDown + Rescale (context.cu, hmult_run): for extended limb e == u_limb the kernel ALSO stores
+  //   u_c = acc_c[e] * u_cst + u_add_c[e]   (canonical words)   into limb slot u_slot of accumulator c,
+  // u_add_c = u_add + c * u_add_comp_stride + b * u_add_batch_stride (packed limbs).  u_limb < 0: off.
+  int u_limb, u_slot;
+  const u64 *u_add;
+  long long u_add_comp_stride, u_add_batch_stride;
+  double2 u_cst;
 };
 void launch_inner_product(const ModConst *mc, const LimbMap &lm, const InnerArgs &a, cudaStream_t s);
 
@@ -90,11 +97,27 @@ struct BConvImage {
   const uint8_t *img = nullptr;   // device, K * NP bytes in the kernel's shared-memory layout
   int K = 0, NP = 0, ND = 0, n16 = 0, fold = 0;
 };
+// One conversion of a multi-conversion launch (tcgen05 kernel): everything that differs between the conversions lives in a
+// device-resident table built once (context.cu), so the three ModUp digits of a key switch run as ONE launch — CTA c serves
+// job c % n_jobs for its whole life (per-CTA matrix image, target table and source offsets stay constant).
+struct BConvJob {
+  uint16_t src_pos[48];       // limb slot of source i inside the job's input (relative to in + in_off)
+  uint16_t dst_mod[48], dst_pos[48];
+  const uint8_t *img;         // operand image (device)
+  int K, NP, ND;
+  int n_src, n_dst;
+  long long in_off, out_off;  // words, added to BConvArgs::in / out
+};
 // host: eligibility (n_src <= 48, 5 * pad8(n_dst + fold) <= 256) and image construction; see bconv_umma.cu
 bool bconv_image_shape(int n_src, int n_dst, int fold, BConvImage &im);
 bool bconv_image_build(const u64 *hat, int n_src, int n_dst, const u64 *dst_q, const u64 *fold, u64 fold_q, std::vector<uint8_t> &img,
                        BConvImage &im);
 void launch_bconv_umma(const ModConst *mc, const LimbMap &src_lm, const LimbMap &dst_lm, const BConvArgs &a, const BConvImage &im, cudaStream_t s);
+// n_jobs conversions in one launch: `a` carries what they share (N, n_batches, batch strides, out_f64; in / out are the bases the
+// jobs' offsets are added to; no step 1, no fold, no peer offsets), d_jobs the device table, ims the host copies of the image
+// shapes.  Returns false (nothing launched) when the jobs cannot share a launch (different slab counts, N % 128 != 0).
+bool launch_bconv_umma_multi(const ModConst *mc, const BConvJob *d_jobs, const BConvImage *ims, const int *n_dst, int n_jobs, const BConvArgs &a,
+                             cudaStream_t s);
 // HML_BCONV_UMMA=0 keeps every conversion on the DMMA kernel
 int bconv_umma_enabled();
 inline int bconv_pad_src(int n_src) { return (n_src + 3) & ~3; }   // k-steps of 4 sources

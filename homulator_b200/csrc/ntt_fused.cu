@@ -32,6 +32,7 @@ constexpr int FUSED_STAGE_BYTES = NTT_TILE * 8 + 2048 + 64;   // tile | column t
 constexpr int FUSED_SMEM_BYTES = ROW_TILE_BYTES + 2 * FUSED_STAGE_BYTES;
 
 struct FusedPlan {
+  int G;        // members per super-job (<= FUSED_G; small launches use 1 so that every tile is its own work item)
   int T;        // tiles per member and pass
   int n_sj;     // super-jobs
   int lag;      // super-jobs between the first pass and the second
@@ -95,8 +96,10 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_fused(NttTables t, int log
   auto is_col = [&](int second) { return INV ? second != 0 : second == 0; };
 
   // thread 0: pop + decode the next item into shared memory
+  int popped = -1;  // thread 0: queue position fetched ahead of its use (the atomic's latency hides behind a unit's arithmetic)
   auto pop = [&]() {
-    const int x = (int)atomicAdd(&ctrl[0], 1u);
+    const int x = popped >= 0 ? popped : (int)atomicAdd(&ctrl[0], 1u);
+    popped = -1;
     ItemDesc d{};
     if (x < fp.n_items) {
       d.valid = 1;
@@ -105,8 +108,8 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_fused(NttTables t, int log
       while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (fp.sj_first[mid] <= d.sj) lo = mid; else hi = mid; }
       d.limb = lo;
       d.mi = lm.mod[lo];
-      d.m0 = (d.sj - fp.sj_first[lo]) * FUSED_G;
-      d.cnt = min(FUSED_G, (int)fp.members[lo] - d.m0);
+      d.m0 = (d.sj - fp.sj_first[lo]) * fp.G;
+      d.cnt = min(fp.G, (int)fp.members[lo] - d.m0);
       d.ready = 1;
       if (d.second) {
         unsigned v;
@@ -410,6 +413,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_fused(NttTables t, int log
   if (cur.valid) {
     if (!cur.ready) wait_ready(cur.sj);
     start_item_loads(cur, 0, stage0_u32, true);
+    if (tid == 0 && cur.cnt == 1) popped = (int)atomicAdd(&ctrl[0], 1u);
   }
   cp_async_commit();
   while (cur.valid) {
@@ -428,6 +432,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_fused(NttTables t, int log
       issued = true;
     }
     cp_async_commit();
+    if (tid == 0 && nxt.valid && nxt_m + 1 == nxt.cnt) popped = (int)atomicAdd(&ctrl[0], 1u);  // needed at the next loop top
     unsigned char *sp = stage0 + stg * FUSED_STAGE_BYTES;
     if (is_col(cur.second)) {
       if constexpr (INV) compute_col_inv(cur, cur_m, sp); else compute_col_fwd(cur, cur_m, sp);
@@ -477,8 +482,12 @@ static int fused_sm_count() {
 
 int ntt_fused_enabled() {
   static const int v = [] {
-    const char *e = getenv("HML_NTT_FUSED");  // 0: the two-kernel transforms of ntt.cu
-    return e && atoi(e) == 0 ? 0 : 1;
+    // Opt-in (HML_NTT_FUSED=1).  Measured on B200 (profiles/ntt_fused_r2.md): the single launch brings the DRAM traffic of a
+    // transform down to the algorithmic 2 W per limb, but one kernel has to run both unit kinds at the row pass's register
+    // budget (two CTAs per SM instead of three for the column units) and pays a block barrier per unit: 0.438 vs 0.370 us per
+    // limb batched, 69 vs 60 us for one ciphertext's 115-limb ModUp launch.  The two-kernel transforms stay the default.
+    const char *e = getenv("HML_NTT_FUSED");
+    return e && atoi(e) == 1 ? 1 : 0;
   }();
   return v;
 }
@@ -486,24 +495,34 @@ int ntt_fused_enabled() {
 static bool make_plan(int logN, const LimbMap &lm, const NttLaunch &l, FusedPlan &fp) {
   fp = FusedPlan{};
   fp.T = 1 << (logN - 12);
-  int sj = 0;
-  for (int i = 0; i < l.n_limbs; ++i) {
-    const int members = l.n_batch * (l.n_polys - (lm.skip[i] != 0xFF && lm.skip[i] < l.n_polys ? 1 : 0));
-    fp.sj_first[i] = (uint16_t)sj;
-    fp.members[i] = (uint16_t)members;
-    if (members > 65535) return false;
-    sj += (members + FUSED_G - 1) / FUSED_G;
-    if (sj > FUSED_MAX_SJ || sj > 65535) return false;
+  static const int g_env = [] { const char *e = getenv("HML_NTT_G"); return e ? atoi(e) : 0; }();
+  // grouping members amortises the row-twiddle blob but makes the work items coarser: group only when the queue stays long
+  const int resident = 2 * fused_sm_count();
+  for (int G = g_env > 0 ? std::min(g_env, FUSED_G) : FUSED_G;; G >>= 1) {
+    int sj = 0;
+    bool ok = true;
+    for (int i = 0; i < l.n_limbs && ok; ++i) {
+      const int members = l.n_batch * (l.n_polys - (lm.skip[i] != 0xFF && lm.skip[i] < l.n_polys ? 1 : 0));
+      fp.sj_first[i] = (uint16_t)sj;
+      fp.members[i] = (uint16_t)members;
+      ok = members <= 65535;
+      sj += (members + G - 1) / G;
+      ok = ok && sj <= FUSED_MAX_SJ;
+    }
+    if (G > 1 && g_env <= 0 && (!ok || sj * fp.T < 8 * resident)) continue;
+    if (!ok) return false;
+    fp.sj_first[l.n_limbs] = (uint16_t)sj;
+    fp.n_sj = sj;
+    fp.G = G;
+    break;
   }
-  fp.sj_first[l.n_limbs] = (uint16_t)sj;
-  fp.n_sj = sj;
-  fp.n_items = 2 * sj * fp.T;
+  fp.n_items = 2 * fp.n_sj * fp.T;
   // enough first-pass items ahead of the first consumer that (a) consumers practically never wait and (b) the intermediate
   // of the super-jobs in between (lag * G * 0.5 MB) stays far below the L2 capacity
   static const int lag_env = [] { const char *e = getenv("HML_NTT_LAG"); return e ? atoi(e) : 0; }();
-  int lag = lag_env > 0 ? lag_env : (3 * 2 * fused_sm_count() + fp.T - 1) / fp.T;
-  fp.lag = std::max(1, std::min(lag, sj));
-  return sj > 0;
+  const int lag = lag_env > 0 ? lag_env : (3 * resident + fp.T - 1) / fp.T;
+  fp.lag = std::max(1, std::min(lag, fp.n_sj));
+  return fp.n_sj > 0;
 }
 
 template <int LOGR1, bool INV>

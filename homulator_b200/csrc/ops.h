@@ -39,12 +39,19 @@ size_t hmult_ws_words(const hml::Params &p, uint32_t L, uint32_t nb);
 size_t hrot_ws_words(const hml::Params &p, uint32_t L, uint32_t nb);
 size_t shard_ws_words(const hml::Params &p, const hml::ShardPlan &sp);
 
+// hmult's merged ModDown + Rescale: the addend d_c[L-1] of u[L-1] = acc_c[L-1] * P^-1 + d_c[L-1] (packed limbs; component c at
+// add + c * comp_stride, ciphertext b at + b * batch_stride)
+struct MergedU {
+  const hml::u64 *add;
+  long long comp_stride, batch_stride;
+};
+
 // K1..K7 of nb key switches sharing one key (ModUp, inner product, INTT of the P-limbs); see context.cu
 int ks_front(hml_ctx *ctx, hml::LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d, const hml::u64 *evk, uint32_t evk_q_limbs, hml::u64 *yb,
-             hml::u64 *ext, hml::u64 *acc, uint32_t AL, cudaStream_t s);
+             hml::u64 *ext, hml::u64 *acc, uint32_t AL, cudaStream_t s, const MergedU *mu = nullptr);
 int ks_modup(hml_ctx *ctx, hml::LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d, hml::u64 *yb, hml::u64 *ext, cudaStream_t s);
 int ks_inner(hml_ctx *ctx, hml::LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d, const hml::u64 *evk, uint32_t evk_q_limbs, const hml::u64 *ext,
-             hml::u64 *acc, uint32_t AL, hml::u64 galois, cudaStream_t s);
+             hml::u64 *acc, uint32_t AL, hml::u64 galois, cudaStream_t s, const MergedU *mu = nullptr);
 int ks_tail(hml_ctx *ctx, hml::LevelConsts *lc, uint32_t L, uint32_t nb, hml::u64 *acc, hml::u64 *vb, BatchOut out0, BatchOut out1, BatchPtr add0,
             BatchPtr add1, cudaStream_t s);
 int hrot_hoisted_run(hml_ctx *ctx, uint32_t L, const hml::u64 *ct, uint32_t n_rot, const uint64_t *const *rotkeys, uint32_t evk_q_limbs,
