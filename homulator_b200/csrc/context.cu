@@ -619,7 +619,22 @@ size_t ks_ws_words(const Params &p, uint32_t L) {
 
 
 // K1..K4: ModUp (INTT + digit scaling, base conversion, NTT of the converted limbs).  Buffers: yb [nb][L] | ext [nb][beta][E].
-int ks_modup(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d, u64 *yb, u64 *ext, cudaStream_t s) {
+// HML_HPIP=0 keeps the inner product in its own kernel (k_inner) everywhere
+static bool hpip_enabled() {
+  static const bool v = [] { const char *e = getenv("HML_HPIP"); return !(e && atoi(e) == 0); }();
+  return v;
+}
+// The fusion pays for ONE ciphertext per launch (measured at the north-star shape: ModUp transform + inner product 112 -> 95 us,
+// hmult 245 -> 233 us, hrotate 249 -> 227 us): there the stand-alone inner product is latency-bound on the 150 MB key.  In a
+// 32-ciphertext chunk the key is read once per chunk and k_inner streams at the HBM rate, while the row pass is bound by the
+// FP64 pipe and the fused multiply-accumulates (+45 % FP64 work) land exactly there: 168 -> 178 us per hmult.  HML_HPIP=2 forces
+// the fusion for every batch size.
+bool ks_uses_hpip(const hml_ctx *ctx, uint32_t L, uint32_t nb) {
+  static const int mode = [] { const char *e = getenv("HML_HPIP"); return e ? atoi(e) : 1; }();
+  return hpip_enabled() && ctx->p.logN > NTT_SMALL_LOG && ctx->p.beta(L) >= 2 && (nb == 1 || mode == 2);
+}
+
+int ks_modup(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d, u64 *yb, u64 *ext, cudaStream_t s, const NttMac *mac) {
   const Params &p = ctx->p;
   const size_t N = p.N;
   const uint32_t A = p.alpha, E = L + A, beta = lc->beta;
@@ -666,6 +681,10 @@ int ks_modup(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d,
     l.n_limbs = E; l.n_polys = beta;  // digit j skips the limbs it owns (LimbMap::skip)
     l.n_batch = nb; l.in_batch_stride = l.out_batch_stride = (long long)beta * E * N;
     l.in_f64 = l.out_f64 = npass == 2;  // doubles in from the conversion, raw lazy doubles out to the inner product
+    if (mac) {  // K5 rides in the row pass (HPIP analogue): the transformed digits are multiplied by the key and never stored
+      l.mac = *mac;
+      ctx->exec.ewe_limbs += 2ull * nb * E * beta;
+    }
     launch_ntt_forward(tabs_for(ctx, s), logN, lc->ext_lm, l, s);
     prof_mark(ctx, HML_CLS_NTT, s);
     ctx->exec.ntt_limbs += (uint64_t)nb * ((uint64_t)beta * E - L); ctx->exec.kernel_launches += npass;
@@ -676,20 +695,23 @@ int ks_modup(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d,
 // K5..K7: inner product with the key, INTT (+ step-1 scaling) of the P-limbs of both accumulators.  acc [nb][2][AL], AL >= E.
 // galois != 0: the digits are read through the automorphism X -> X^galois (hoisted rotation, see InnerArgs::galois).
 int ks_inner(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d, const u64 *evk, uint32_t evk_q_limbs, const u64 *ext, u64 *acc,
-             uint32_t AL, u64 galois, cudaStream_t s, const MergedU *mu) {
+             uint32_t AL, u64 galois, cudaStream_t s, const MergedU *mu, bool ip_done) {
   const Params &p = ctx->p;
   const size_t N = p.N;
   const uint32_t A = p.alpha, E = L + A, beta = lc->beta;
   const int logN = p.logN, npass = logN <= NTT_SMALL_LOG ? 1 : 2;
-  // K5 (reference :294-414): inner product with the key (key words loaded once per batch)
-  {
+  // K5 (reference :294-414): inner product with the key (key words loaded once per batch) — unless the ModUp transform's row
+  // pass has already done it (ks_front with HPIP)
+  if (!ip_done) {
     LimbMap ip = lc->ext_lm;  // pos = limb index inside the key (Q-limbs first, then P-limbs after evk_q_limbs)
     for (uint32_t e = 0; e < E; ++e) ip.pos[e] = (uint16_t)(e < L ? e : evk_q_limbs + (e - L));
     InnerArgs a{};
     a.d = d.ptr; a.ext = ext; a.evk = evk; a.acc = acc; a.N = N; a.n_ext = E; a.beta = beta; a.evk_limbs = evk_q_limbs + A;
     a.n_batch = nb; a.d_batch_stride = d.stride; a.ext_batch_stride = (long long)beta * E * N; a.acc_batch_stride = 2ll * AL * N;
     a.acc_comp_stride = (long long)AL * N; a.ext_f64 = npass == 2;
-    a.acc_pack_limbs = npass == 2 ? (int)L : 0;  // Q-limb accumulators only feed element-wise epilogues: packed (5 B / coefficient)
+    // Q-limb accumulators only feed element-wise epilogues: packed (5 B / coefficient) — but the HPIP path, which some other
+    // call of this level may take, leaves words, and the consumers are told per call (ks_tail's acc_packed)
+    a.acc_pack_limbs = npass == 2 ? (int)L : 0;
     a.galois = (unsigned)(galois & (2ull * N - 1)); a.logN = logN;
     if (a.galois == 1) a.galois = 0;
     a.u_limb = -1;
@@ -717,16 +739,34 @@ int ks_inner(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d,
 }
 
 // K1..K7.  Buffers: yb [nb][L] | ext [nb][beta][E] | acc [nb][2][AL] with AL >= E limbs per accumulator.
+// Two-pass rings with at least two digits fuse the inner product into the ModUp transform (NttMac): the Q-limb accumulators are
+// then 8-byte words (not packed limbs); ks_uses_hpip() tells the consumers.
 int ks_front(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d, const u64 *evk, uint32_t evk_q_limbs, u64 *yb,
              u64 *ext, u64 *acc, uint32_t AL, cudaStream_t s, const MergedU *mu) {
-  int rc = ks_modup(ctx, lc, L, nb, d, yb, ext, s);
+  const Params &p = ctx->p;
+  const size_t N = p.N;
+  const uint32_t A = p.alpha, E = L + A;
+  const bool hpip = ks_uses_hpip(ctx, L, nb);
+  NttMac mac{};
+  if (hpip) {
+    mac.evk = evk; mac.d = d.ptr; mac.acc = acc; mac.d_batch_stride = d.stride; mac.acc_batch_stride = 2ll * AL * N;
+    mac.acc_comp_stride = (long long)AL * N; mac.evk_limbs = (int)(evk_q_limbs + A);
+    for (uint32_t e = 0; e < E; ++e) mac.key_pos[e] = (uint16_t)(e < L ? e : evk_q_limbs + (e - L));
+    mac.u_limb = -1;
+    if (mu) {
+      mac.u_limb = (int)L - 1; mac.u_slot = (int)E; mac.u_add = mu->add; mac.u_add_comp_stride = mu->comp_stride;
+      mac.u_add_batch_stride = mu->batch_stride; mac.u_cst = lc->pinv_last;
+      ctx->exec.ewe_limbs += 4ull * nb;
+    }
+  }
+  int rc = ks_modup(ctx, lc, L, nb, d, yb, ext, s, hpip ? &mac : nullptr);
   if (rc) return rc;
-  return ks_inner(ctx, lc, L, nb, d, evk, evk_q_limbs, ext, acc, AL, 0, s, mu);
+  return ks_inner(ctx, lc, L, nb, d, evk, evk_q_limbs, ext, acc, AL, 0, s, mu, hpip);
 }
 
 // K8..K10 (+ the caller's addends): ModDown of nb accumulator pairs acc [nb][2][E] -> out_c[b] = (acc_c - NTT(BConv(acc_c; P -> Q))) * P^-1 (+ add_c[b])
 int ks_tail(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, u64 *acc, u64 *vb, BatchOut out0, BatchOut out1, BatchPtr add0, BatchPtr add1,
-            cudaStream_t s) {
+            cudaStream_t s, bool acc_packed) {
   const Params &p = ctx->p;
   const size_t N = p.N;
   const uint32_t A = p.alpha, E = L + A;
@@ -748,7 +788,7 @@ int ks_tail(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, u64 *acc, u6
     l.n_limbs = L; l.n_polys = 2 * nb; l.n_batch = 1; l.in_f64 = npass == 2;
     if (fuse) {
       NttFuse &f = l.fuse;
-      f.x = acc; f.x_c_stride = (long long)E * N; f.x_b_stride = 2ll * E * N; f.x_packed = 1;
+      f.x = acc; f.x_c_stride = (long long)E * N; f.x_b_stride = 2ll * E * N; f.x_packed = acc_packed ? 1 : 0;
       const BatchPtr zb = add0.ptr ? add0 : add1;  // component c reads zb.ptr + c * z_c_stride; only masked components are touched
       f.z = zb.ptr; f.z_b_stride = zb.stride;
       f.z_c_stride = (add0.ptr && add1.ptr) ? (long long)(add1.ptr - add0.ptr) : 0;
@@ -770,7 +810,7 @@ int ks_tail(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, u64 *acc, u6
     a.y = vb + (size_t)c * L * N; a.y_poly_stride = 2ll * L * N;
     a.z = add.ptr; a.z_poly_stride = add.stride;
     a.out = out.ptr; a.out_poly_stride = out.stride;
-    a.cst = lc->pinv; a.N = N; a.n_limbs = L; a.n_polys = nb; a.x_packed = npass == 2;
+    a.cst = lc->pinv; a.N = N; a.n_limbs = L; a.n_polys = nb; a.x_packed = acc_packed ? 1 : 0;
     launch_sub_mul_add(ctx->mc, lc->q_lm, a, s);
     prof_mark(ctx, HML_CLS_EWE, s);
     ctx->exec.ewe_limbs += (uint64_t)nb * (L + (a.z ? L : 0)); ctx->exec.kernel_launches++;
@@ -793,7 +833,7 @@ int ks_run(hml_ctx *ctx, uint32_t L, uint32_t nb, BatchPtr d, const u64 *evk, ui
   // workspace, every buffer batch-major: yb [nb][L] | ext [nb][beta][E] | acc [nb][2][E] | vb [nb][2][L]  (limbs of N words)
   u64 *yb = ws, *ext = yb + (size_t)nb * L * N, *acc = ext + (size_t)nb * beta * E * N, *vb = acc + (size_t)nb * 2 * E * N;
   if ((rc = ks_front(ctx, lc, L, nb, d, evk, evk_q_limbs, yb, ext, acc, E, s, nullptr))) return rc;
-  return ks_tail(ctx, lc, L, nb, acc, vb, out0, out1, add0, add1, s);
+  return ks_tail(ctx, lc, L, nb, acc, vb, out0, out1, add0, add1, s, p.logN > NTT_SMALL_LOG && !ks_uses_hpip(ctx, L, nb));
 }
 
 extern "C" int hml_keyswitch(hml_ctx *ctx, uint32_t L, const uint64_t *d, const uint64_t *evk, uint32_t evk_q_limbs,
@@ -1529,7 +1569,7 @@ int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, const u64 
     f.x = acc; f.x_c_stride = (long long)AL * N; f.x_b_stride = 2ll * AL * N;
     f.z = d0; f.z_c_stride = (long long)(d1 - d0); f.z_b_stride = (long long)PL; f.z_mask = 3;
     f.dst = ct_out; f.dst_c_stride = (long long)(L - 1) * N; f.dst_b_stride = 2ll * (L - 1) * N;
-    f.cst = lc->pinv; f.cst2 = lc->qlinv; f.n_c = 2; f.x_packed = f.z_packed = 1;
+    f.cst = lc->pinv; f.cst2 = lc->qlinv; f.n_c = 2; f.x_packed = ks_uses_hpip(ctx, L, nb) ? 0 : 1; f.z_packed = 1;
     launch_ntt_forward(tabs_for(ctx, s), logN, lc->q_lm, l, s);
     prof_mark(ctx, HML_CLS_NTT, s);
     ctx->exec.ntt_limbs += 2ull * nb * (L - 1); ctx->exec.kernel_launches += 2;
@@ -1597,14 +1637,14 @@ int hrot_hoisted_run(hml_ctx *ctx, uint32_t L, const u64 *ct, uint32_t n_rot, co
   if (beta > 8) return fail(ctx, HML_ERR_UNSUPPORTED, "more than 8 key-switch digits (ceil(L/alpha) > 8)");
   u64 *sb = ws, *yb = sb + 2 * PL, *ext = yb + PL, *acc = ext + (size_t)beta * E * N, *vb = acc + 2 * (size_t)E * N;
   const BatchPtr c1{ct + PL, 0};
-  if ((rc = ks_modup(ctx, lc, L, 1, c1, yb, ext, s))) return rc;
+  if ((rc = ks_modup(ctx, lc, L, 1, c1, yb, ext, s, nullptr))) return rc;
   for (uint32_t r = 0; r < n_rot; ++r) {
     launch_automorph(p.logN, L, ct, sb, galois[r], s);  // sigma_r(c0): the addend of the ModDown epilogue
     prof_mark(ctx, HML_CLS_AUTO, s);
     ctx->exec.automorph_limbs += L; ctx->exec.kernel_launches++;
-    if ((rc = ks_inner(ctx, lc, L, 1, c1, (const u64 *)rotkeys[r], evk_q_limbs, ext, acc, E, galois[r], s, nullptr))) return rc;
+    if ((rc = ks_inner(ctx, lc, L, 1, c1, (const u64 *)rotkeys[r], evk_q_limbs, ext, acc, E, galois[r], s, nullptr, false))) return rc;
     u64 *o = (u64 *)outs[r];
-    if ((rc = ks_tail(ctx, lc, L, 1, acc, vb, {o, 0}, {o + PL, 0}, {sb, 0}, {nullptr, 0}, s))) return rc;
+    if ((rc = ks_tail(ctx, lc, L, 1, acc, vb, {o, 0}, {o + PL, 0}, {sb, 0}, {nullptr, 0}, s, p.logN > NTT_SMALL_LOG))) return rc;
   }
   return check_launch(ctx, "hrotate hoisted");
 }

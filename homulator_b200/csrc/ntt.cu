@@ -3,6 +3,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 namespace hml {
 
@@ -212,8 +213,25 @@ struct RowItems {
   }
 };
 
-template <bool INV, bool FUSE>
+// MAC launches (NttMac): a CTA must own ALL members (digits) of a ciphertext's limb tile, so the grid splits the ciphertexts
+// (b = blockIdx.z, + gridDim.z, ...) and walks the digits innermost.
+struct RowItemsB {
+  int n_polys, n_batch, skip, step;
+  __device__ __forceinline__ bool valid(const RowItem &i) const { return i.b < n_batch; }
+  __device__ __forceinline__ int first_p() const { return skip == 0 ? 1 : 0; }
+  __device__ __forceinline__ int last_p() const { return skip == n_polys - 1 ? n_polys - 2 : n_polys - 1; }
+  __device__ __forceinline__ RowItem next(RowItem i) const {
+    ++i.p;
+    if (i.p == skip) ++i.p;
+    if (i.p >= n_polys) { i.p = first_p(); i.b += step; }
+    return i;
+  }
+};
+
+// MODE 0: plain transform; 1: fused element-wise epilogue (NttFuse); 2: fused key-switch inner product (NttMac)
+template <bool INV, int MODE>
 __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN, LimbMap lm, NttLaunch l) {
+  constexpr bool FUSE = MODE == 1, MAC = MODE == 2;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, limb = blockIdx.y;
@@ -240,8 +258,11 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
   auto dst_of = [&](const RowItem &i) -> u64 * {
     return l.out + (long long)i.b * l.out_batch_stride + (long long)i.p * l.out_poly_stride + slot * l.out_limb_stride + tile_off;
   };
-  const RowItems items{l.n_polys, l.n_batch, lm.skip[limb], (int)gridDim.z};
-  RowItem cur = items.next(RowItem{0, (int)blockIdx.z - (int)gridDim.z});
+  using Items = typename std::conditional<MAC, RowItemsB, RowItems>::type;
+  const Items items{l.n_polys, l.n_batch, lm.skip[limb], (int)gridDim.z};
+  RowItem cur;
+  if constexpr (MAC) cur = RowItem{(int)blockIdx.z, items.first_p()};
+  else cur = items.next(RowItem{0, (int)blockIdx.z - (int)gridDim.z});
   RowItem nxt = items.valid(cur) ? items.next(cur) : cur;
   pdl_wait();  // the twiddle blob (a constant table) is already in flight; the data is another kernel's output
   if (items.valid(cur)) row_issue(src_of(cur), data0, lane, warp);
@@ -273,6 +294,22 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
       prefetch(f.x + fc * f.x_c_stride + fb * f.x_b_stride + (size_t)limb * nn, f.x_packed);
       if (f.z != nullptr && ((f.z_mask >> fc) & 1u)) prefetch(f.z + fc * f.z_c_stride + fb * f.z_b_stride + (size_t)limb * nn, f.z_packed);
     }
+    if constexpr (MAC) {
+      // the key words this warp's two rows will be multiplied with (2 x 4 KB, + the own digit's at the first member) start
+      // their trip to L2 now; one 128-byte line per lane
+      const NttMac &mq = l.mac;
+      const size_t nn = (size_t)1 << logN, c0 = tile_off + (size_t)warp * 512 + (size_t)lane * 16;
+      const size_t kl = mq.key_pos[limb];
+      auto pf = [&](const u64 *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); };
+      pf(mq.evk + (((size_t)cur.p * 2 + 0) * mq.evk_limbs + kl) * nn + c0);
+      pf(mq.evk + (((size_t)cur.p * 2 + 1) * mq.evk_limbs + kl) * nn + c0);
+      const int own = lm.skip[limb];
+      if (cur.p == items.first_p() && own != 0xFF) {
+        pf(mq.evk + (((size_t)own * 2 + 0) * mq.evk_limbs + kl) * nn + c0);
+        pf(mq.evk + (((size_t)own * 2 + 1) * mq.evk_limbs + kl) * nn + c0);
+        pf(mq.d + (size_t)cur.b * mq.d_batch_stride + (size_t)limb * nn + c0);
+      }
+    }
     if constexpr (!INV) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) a[j] = *reinterpret_cast<const double *>(data + ad.A(j));
@@ -299,7 +336,84 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
         w[2 * m] = v.x; w[2 * m + 1] = v.y;
       }
       ct_level<3>(a, w, q, qinv);
-      if constexpr (!FUSE) {
+      if constexpr (MAC) {
+        // key-switch inner product on the transform's output (HPIP analogue, see NttMac): the lazy sums go through the
+        // swizzled tile so that every lane works on the 16-byte chunks it loads and stores (256 B per half-warp)
+#pragma unroll
+        for (int m = 0; m < 8; ++m) *reinterpret_cast<double2 *>(data + ad.B(m)) = make_double2(a[2 * m], a[2 * m + 1]);
+        __syncwarp();
+        const NttMac &mq = l.mac;
+        const size_t nn = (size_t)1 << logN;
+        const size_t ci = tile_off + (size_t)rr * 256 + (l16 >> 3) * 16 + (l16 & 7) * 2;
+        const size_t kl = mq.key_pos[limb];
+        const int own = lm.skip[limb];
+        const bool first = cur.p == items.first_p(), last = cur.p == items.last_p();
+        const u64 *k0 = mq.evk + (((size_t)cur.p * 2 + 0) * mq.evk_limbs + kl) * nn + ci;
+        const u64 *k1 = mq.evk + (((size_t)cur.p * 2 + 1) * mq.evk_limbs + kl) * nn + ci;
+        u64 *A0 = mq.acc + (size_t)cur.b * mq.acc_batch_stride + (size_t)limb * nn + ci, *A1 = A0 + mq.acc_comp_stride;
+        const bool with_own = first && own != 0xFF;
+        const u64 *o0 = mq.evk + (((size_t)(with_own ? own : 0) * 2 + 0) * mq.evk_limbs + kl) * nn + ci;
+        const u64 *o1 = mq.evk + (((size_t)(with_own ? own : 0) * 2 + 1) * mq.evk_limbs + kl) * nn + ci;
+        const u64 *dd = mq.d + (size_t)cur.b * mq.d_batch_stride + (size_t)limb * nn + ci;
+        const bool with_u = last && limb == mq.u_limb;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {  // four chunks at a time: every load of the half is in flight before the first product
+          ulonglong2 kv0[4], kv1[4];
+          double2 old0[4], old1[4];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            kv0[m] = __ldg(reinterpret_cast<const ulonglong2 *>(k0 + 32 * (4 * h + m)));
+            kv1[m] = __ldg(reinterpret_cast<const ulonglong2 *>(k1 + 32 * (4 * h + m)));
+          }
+          if (!first) {  // this thread wrote these slots itself while it processed the previous member: plain (coherent) loads
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              old0[m] = *reinterpret_cast<const double2 *>(A0 + 32 * (4 * h + m));
+              old1[m] = *reinterpret_cast<const double2 *>(A1 + 32 * (4 * h + m));
+            }
+          } else if (with_own) {  // the digit that owns this limb contributes the untouched input
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const ulonglong2 dv = __ldg(reinterpret_cast<const ulonglong2 *>(dd + 32 * (4 * h + m)));
+              const ulonglong2 w0 = __ldg(reinterpret_cast<const ulonglong2 *>(o0 + 32 * (4 * h + m)));
+              const ulonglong2 w1 = __ldg(reinterpret_cast<const ulonglong2 *>(o1 + 32 * (4 * h + m)));
+              const double dx = u64_to_f64(dv.x), dy = u64_to_f64(dv.y);
+              old0[m] = make_double2(mulmod_var(dx, u64_to_f64(w0.x), q, qinv), mulmod_var(dy, u64_to_f64(w0.y), q, qinv));
+              old1[m] = make_double2(mulmod_var(dx, u64_to_f64(w1.x), q, qinv), mulmod_var(dy, u64_to_f64(w1.y), q, qinv));
+            }
+          } else {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) old0[m] = old1[m] = make_double2(0.0, 0.0);
+          }
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const int mm = 4 * h + m;
+            const double2 y = *reinterpret_cast<const double2 *>(data + ad.C(mm));
+            const double s00 = old0[m].x + mulmod_var(y.x, u64_to_f64(kv0[m].x), q, qinv);
+            const double s01 = old0[m].y + mulmod_var(y.y, u64_to_f64(kv0[m].y), q, qinv);
+            const double s10 = old1[m].x + mulmod_var(y.x, u64_to_f64(kv1[m].x), q, qinv);
+            const double s11 = old1[m].y + mulmod_var(y.y, u64_to_f64(kv1[m].y), q, qinv);
+            if (!last) {
+              *reinterpret_cast<double2 *>(A0 + 32 * mm) = make_double2(s00, s01);
+              *reinterpret_cast<double2 *>(A1 + 32 * mm) = make_double2(s10, s11);
+            } else {
+              const u64 r00 = f64_to_canonical(reduce_signed(s00, q, qinv), mc.qi), r01 = f64_to_canonical(reduce_signed(s01, q, qinv), mc.qi);
+              const u64 r10 = f64_to_canonical(reduce_signed(s10, q, qinv), mc.qi), r11 = f64_to_canonical(reduce_signed(s11, q, qinv), mc.qi);
+              *reinterpret_cast<ulonglong2 *>(A0 + 32 * mm) = make_ulonglong2(r00, r01);
+              *reinterpret_cast<ulonglong2 *>(A1 + 32 * mm) = make_ulonglong2(r10, r11);
+              if (with_u) {  // hmult: u = acc * P^-1 + d on the limb the rescale drops, into slot u_slot (see InnerArgs::u_limb)
+                const u64 *ua = mq.u_add + (size_t)cur.b * mq.u_add_batch_stride + (size_t)limb * nn;
+                const ulonglong2 d0v = ld_packed2(ua, nn, (ci >> 1) + 16 * mm), d1v = ld_packed2(ua + mq.u_add_comp_stride, nn, (ci >> 1) + 16 * mm);
+                const double2 c = mq.u_cst;
+                const long long so = ((long long)mq.u_slot - limb) * (long long)nn;
+                auto fin = [&](u64 r, u64 dw) { return f64_to_canonical(reduce_signed(mulmod_const(u64_to_f64(r), c.x, c.y, q) + u64_to_f64(dw), q, qinv), mc.qi); };
+                *reinterpret_cast<ulonglong2 *>(A0 + so + 32 * mm) = make_ulonglong2(fin(r00, d0v.x), fin(r01, d0v.y));
+                *reinterpret_cast<ulonglong2 *>(A1 + so + 32 * mm) = make_ulonglong2(fin(r10, d1v.x), fin(r11, d1v.y));
+              }
+            }
+          }
+        }
+      } else if constexpr (!FUSE) {
         // canonical words back through the swizzled tile so that the global stores are 16 bytes per lane, 256 B per half-warp
         if (l.out_f64) {  // uniform: the consumer takes the lazy sums as they are
 #pragma unroll
@@ -536,16 +650,20 @@ static void launch_cols_t(bool inverse, const NttTables &t, int logN, const Limb
   else launch_pdl(ntt_fwd_cols<LOGR1, NT, false>, grid, NT, 2 * K::STAGE_BYTES, s, t, logN, lm, l, total);
 }
 
-static int col_threads() {
+static int col_threads_env() {
   static const int v = [] {
-    const char *e = getenv("HML_COL_NT");  // tuning knob: 128 or 256 threads per column-pass CTA
-    return e && atoi(e) == 128 ? 128 : 256;
+    const char *e = getenv("HML_COL_NT");  // tuning knob: force 128 or 256 threads per column-pass CTA (default: by launch size)
+    const int n = e ? atoi(e) : 0;
+    return n == 128 || n == 256 ? n : 0;
   }();
   return v;
 }
 
 static void launch_cols(bool inverse, const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
-  const bool big = col_threads() == 256;
+  // one ciphertext's worth of limbs is only a few 32 KB tiles per resident CTA: 16 KB tiles (128 threads, six CTAs per SM) fill
+  // the machine more evenly there (measured: 55.9 vs 60.1 us for the 115-limb ModUp launch); big batches prefer 32 KB tiles
+  const long long tiles32 = (long long)l.n_limbs * l.n_polys * l.n_batch << (logN - 12);
+  const bool big = col_threads_env() ? col_threads_env() == 256 : tiles32 >= 6ll * 3 * sm_count();
   switch (logN - NTT_ROW_LOG) {
     case 5: big ? launch_cols_t<5, 256>(inverse, t, logN, lm, l, s) : launch_cols_t<5, 128>(inverse, t, logN, lm, l, s); break;
     case 6: big ? launch_cols_t<6, 256>(inverse, t, logN, lm, l, s) : launch_cols_t<6, 128>(inverse, t, logN, lm, l, s); break;
@@ -557,15 +675,23 @@ static void launch_cols(bool inverse, const NttTables &t, int logN, const LimbMa
 static void launch_rows(bool inverse, const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
   static PerDeviceOnce once;
   if (once.first()) {
-    allow_smem(ntt_rows<false, false>, ROW_SMEM_BYTES);
-    allow_smem(ntt_rows<false, true>, ROW_SMEM_BYTES);
-    allow_smem(ntt_rows<true, false>, ROW_SMEM_BYTES);
+    allow_smem(ntt_rows<false, 0>, ROW_SMEM_BYTES);
+    allow_smem(ntt_rows<false, 1>, ROW_SMEM_BYTES);
+    allow_smem(ntt_rows<false, 2>, ROW_SMEM_BYTES);
+    allow_smem(ntt_rows<true, 0>, ROW_SMEM_BYTES);
   }
   const int tiles = 1 << (logN - NTT_ROW_LOG - 4);
+  if (!inverse && l.mac.evk) {  // the grid splits the ciphertexts; every CTA walks all digits of its (ciphertext, limb, tile)
+    const int per = std::max(1, row_items_target() / std::max(1, l.n_polys));
+    int z = (l.n_batch + per - 1) / per;
+    while (z > 1 && (long long)tiles * l.n_limbs * z > 64ll * sm_count()) --z;
+    launch_pdl(ntt_rows<false, 2>, dim3(tiles, l.n_limbs, std::max(1, z)), NTT_THREADS, ROW_SMEM_BYTES, s, t, logN, lm, l);
+    return;
+  }
   const dim3 grid(tiles, l.n_limbs, row_split(l.n_polys * l.n_batch, tiles * l.n_limbs));
-  if (inverse) launch_pdl(ntt_rows<true, false>, grid, NTT_THREADS, ROW_SMEM_BYTES, s, t, logN, lm, l);
-  else if (l.fuse.x) launch_pdl(ntt_rows<false, true>, grid, NTT_THREADS, ROW_SMEM_BYTES, s, t, logN, lm, l);
-  else launch_pdl(ntt_rows<false, false>, grid, NTT_THREADS, ROW_SMEM_BYTES, s, t, logN, lm, l);
+  if (inverse) launch_pdl(ntt_rows<true, 0>, grid, NTT_THREADS, ROW_SMEM_BYTES, s, t, logN, lm, l);
+  else if (l.fuse.x) launch_pdl(ntt_rows<false, 1>, grid, NTT_THREADS, ROW_SMEM_BYTES, s, t, logN, lm, l);
+  else launch_pdl(ntt_rows<false, 0>, grid, NTT_THREADS, ROW_SMEM_BYTES, s, t, logN, lm, l);
 }
 
 void launch_ntt_forward(const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
@@ -573,7 +699,7 @@ void launch_ntt_forward(const NttTables &t, int logN, const LimbMap &lm, const N
     launch_pdl(ntt_small, dim3(1, l.n_limbs * l.n_polys * l.n_batch), 256, sizeof(double) << logN, s, t, logN, lm, l, 0);
     return;
   }
-  if (launch_ntt_fused(false, t, logN, lm, l, t.fused_ctrl, s)) return;
+  if (!l.mac.evk && launch_ntt_fused(false, t, logN, lm, l, t.fused_ctrl, s)) return;
   launch_cols(false, t, logN, lm, l, s);
   launch_rows(false, t, logN, lm, l, s);
 }

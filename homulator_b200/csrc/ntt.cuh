@@ -74,6 +74,28 @@ struct NttFuse {
   int x_packed, z_packed;       // x / z hold packed limbs (modarith.cuh: 5 bytes per coefficient inside the 8N-byte slot)
 };
 
+// Optional key-switch inner product fused into the ModUp transform's row pass — the GPU counterpart of the reference's HPIP
+// unit, which multiplies the transformed digits by the key as they leave the NTT (InsGen::GenHPIP reference src/InsGen.cpp:356-406,
+// unit HPIP src/Components.cpp:571-668; inner product itself: KeySwitch::InnerProduceOperation src/Operation.cpp:294-414).
+// The launch transforms the beta extended digits (polys) of n_batch ciphertexts; instead of storing NTT(t_j)[e] the row pass
+// accumulates   acc_c[b][e] (+)= NTT(t_j)[e] * evk[j][c][key_pos[e]]   for c = 0, 1, so the transformed digits never reach
+// memory.  The member of (b, e) with the smallest digit index starts the sum (and adds the own-digit term
+// d[b][e] * evk[own][c][..] when e is a Q-limb), the others read-modify-write the 8-byte accumulator slots (lazy doubles,
+// L2-resident between members: one CTA handles all members of a (b, e, tile)), the last one stores canonical words.
+struct NttMac {
+  const u64 *evk;               // [beta][2][evk_limbs][N]; null: no fusion
+  const u64 *d;                 // the untouched evaluation-form input, [>= L][N] per ciphertext
+  u64 *acc;                     // accumulators [n_batch][2][..][N], 8-byte slots
+  long long d_batch_stride, acc_batch_stride, acc_comp_stride;
+  int evk_limbs;
+  uint16_t key_pos[NTT_MAX_LIMBS];
+  // hmult's merged ModDown + Rescale: see InnerArgs::u_limb
+  int u_limb, u_slot;
+  const u64 *u_add;
+  long long u_add_comp_stride, u_add_batch_stride;
+  double2 u_cst;
+};
+
 // ---- launch descriptors (host side, ntt.cu)
 struct NttLaunch {
   const u64 *in;        // [n_polys][n_limbs][N] (poly stride / limb stride in elements below)
@@ -86,6 +108,7 @@ struct NttLaunch {
   // inverse only: per-limb post-scale constant c (folded with N^-1 on the host): out = INTT(in) * c, canonical.
   const double2 *post_scale;  // [n_limbs] (c*ninv mod q, RN(that / q)) or nullptr for plain N^-1
   NttFuse fuse;               // forward only
+  NttMac mac;                 // forward only, two-pass rings, no fused epilogue: see NttMac (n_polys = beta, LimbMap::skip = own digit)
   int in_f64;                 // forward only, two-pass rings: `in` holds signed doubles |v| <= q (BConvArgs::out_f64)
   int out_f64;                // forward only, two-pass rings, no fused epilogue: leave the raw lazy sums (|v| < 10 q) as doubles
                               // in `out` instead of canonical words (consumer: InnerArgs::ext_f64)

@@ -414,3 +414,19 @@ def test_hmult_many_special_primes_dmma_fold():
     assert np.array_equal(to_host(ctx.hmult(L, to_dev(a), to_dev(b), to_dev(evk))), o.hmult(L, a, b, evk, L))
     assert np.array_equal(to_host(ctx.hrotate(L, to_dev(a), to_dev(evk), 5)), o.hrotate(L, a, evk, L, 5))
     Oracle.set_threads(1)
+
+
+@pytest.mark.parametrize("env", [{"HML_NTT_FUSED": "1"}, {"HML_HPIP": "0"}, {"HML_HPIP": "2"}, {"HML_BCONV_UMMA": "0"},
+                                 {"HML_COL_NT": "256", "HML_PDL": "0"}, {"HML_NTT_FUSED": "1", "HML_NTT_G": "1", "HML_NTT_LAG": "1"}],
+                         ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
+def test_alternative_kernel_paths(env):
+    """Every kernel path behind a process-wide switch — the single-launch transform (ntt_fused.cu), the inner product fused
+    into the ModUp transform for every batch size / not at all, the FP64 tensor-core conversion, programmatic dependent launch
+    off — is bit-exact against the oracle too (tests/sp_env_paths.py, one child process per setting)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "sp_env_paths.py")], env=dict(os.environ, **env), capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0 and "ENV_PATHS_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
