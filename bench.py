@@ -336,6 +336,23 @@ def main():
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_us = float(e2e_ms.item()) * 1e3 / (K * Be * world)
     e2e_ok = bool(torch.equal(oh.cuda(), out[:Be]))
+    # the same call with the ciphertexts packed in host memory (5 bytes per coefficient over PCIe instead of the reference's
+    # 8-byte words): reported next to `e2e`, which stays the drop-in uint64 layout
+    ap, bp = ctx.pack_host(ah), ctx.pack_host(bh)
+    op = torch.empty(Be * 2 * (L - 1) * 5 * N_RING, dtype=torch.uint8).pin_memory()
+    for _ in range(2):
+        ctx.hmult_host_packed(L, Be, ap, bp, evk, op)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        ctx.hmult_host_packed(L, Be, ap, bp, evk, op)
+    barrier()
+    e2ep_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device="cuda")
+    if world > 1:
+        dist.all_reduce(e2ep_ms, op=dist.ReduceOp.MAX)
+    e2e_packed_us = float(e2ep_ms.item()) * 1e3 / (K * Be * world)
+    e2e_packed_ok = bool(torch.equal(ctx.unpack_host(op, oh.shape), oh))
+    del ap, bp, op
 
     # ---------------- hrotate, batched (same step shape), all ranks
     out_r = ctx.empty(B, 2, L, N_RING)
@@ -416,6 +433,9 @@ def main():
 
     extra = {"hrotate_batched_us": hrot_batched_us, "hmult_batched_us": us_per_op, "ntt_limbs_per_s": ntt_limbs_per_s, "ntt_us_per_limb": ntt_ms * 1e3 / (n_limbs * n_b),
              "ntt_us_per_limb_single_ciphertext_launch": ntt1_us_per_limb, "e2e_matches_device_path": e2e_ok,
+             "e2e_packed_host_format": {"value": e2e_packed_us, "unit": "us", "h2d_bytes_per_step": 2 * 2 * L * 5 * N_RING * Be,
+                                        "d2h_bytes_per_step": 2 * (L - 1) * 5 * N_RING * Be, "matches_u64_path": e2e_packed_ok,
+                                        "call": "hml_hmult_host_packed (5 bytes per coefficient in pinned host memory)"},
              "bconv_tcgen05": {"kernel": "k_bconv_umma (tcgen05.mma kind::i8, 64 polynomials x 15 -> 35 limbs per launch)",
                                "us_per_launch": bconv_ms * 1e3, "algorithmic_bytes_per_launch": bconv_bytes,
                                "achieved_gbs": bconv_bytes / (bconv_ms * 1e-3) / 1e9, "hbm_frac": bconv_bytes / (bconv_ms * 1e-3) / 1e9 / peak,
@@ -446,8 +466,8 @@ def main():
             "hrotate_single_unfused_bytes_equivalent_over_hbm_peak": aw_r * W_bytes / (hr * 1e-6) / 1e9 / peak,
             # NOT a roofline fraction: SURVEY 8d's UNFUSED byte count divided by the time of the fused / merged schedule (which
             # moves ~0.9 GB per hmult, not 1.32 GB) — can exceed 1; quoted because 8d asks for it
-            "hmult_batched_unfused_bytes_equivalent_over_hbm_peak": aw_m * W_bytes / (us_per_op * 1e-6) / 1e9 / peak,
-            "hrotate_batched_unfused_bytes_equivalent_over_hbm_peak": aw_r * W_bytes / (hrot_batched_us * 1e-6) / 1e9 / peak,
+            "hmult_batched_unfused_bytes_equivalent_over_hbm_peak": aw_m * W_bytes / (us_per_op * 1e-6) / 1e9 / (peak * world),
+            "hrotate_batched_unfused_bytes_equivalent_over_hbm_peak": aw_r * W_bytes / (hrot_batched_us * 1e-6) / 1e9 / (peak * world),
             "homulator_simulated_cycles": {"hrotate_45_35_15": 203651, "hrotate_host_minutes_1core": 235.9, "hmult_host_minutes_1core": 353.4,
                                            "hmult_45_35_15": HMULT_SIM_CYCLES, "note": "unmodified reference CLI, g++ -O2, build container; "
                                            "cycles are machine-independent (BASELINE.md section 2); 1 cycle = 1 ns at an assumed 1 GHz"},

@@ -59,7 +59,8 @@ EXPORTS = [
     "hml_ring_degree", "hml_n_moduli", "hml_get_moduli", "hml_get_roots", "hml_dev_alloc", "hml_dev_free", "hml_h2d",
     "hml_d2h", "hml_sync", "hml_ntt", "hml_intt", "hml_ntt_batch", "hml_intt_batch", "hml_ewe", "hml_automorph", "hml_bconv", "hml_bconv_batch", "hml_keyswitch", "hml_rescale",
     "hml_hmult", "hml_hrotate", "hml_hadd", "hml_pmult", "hml_padd", "hml_hmult_batch", "hml_hrotate_batch",
-    "hml_hmult_host", "hml_hrotate_host", "hml_host_alloc_pinned", "hml_host_free_pinned", "hml_trace_counts",
+    "hml_hmult_host", "hml_hrotate_host", "hml_hmult_host_packed", "hml_hrotate_host_packed", "hml_packed_bytes", "hml_pack_host",
+    "hml_unpack_host", "hml_host_alloc_pinned", "hml_host_free_pinned", "hml_trace_counts",
     "hml_get_counts", "hml_buffer_plan", "hml_exec_counts_get", "hml_exec_counts_reset", "hml_cli_main", "hml_profile_begin", "hml_profile_end",
     "hml_shard_layout", "hml_keyswitch_shard_begin", "hml_keyswitch_shard_mid", "hml_keyswitch_shard_end",
     "hml_keyswitch_shard_mid_p2p", "hml_keyswitch_shard_end_p2p", "hml_shard_signal", "hml_shard_wait", "hml_shard_sync",
@@ -112,6 +113,12 @@ def load_library():
     L.hml_hrotate_batch.argtypes = [vp, u32, u32, vp, vp, u32, u64, vp, vp]
     L.hml_hmult_host.argtypes = [vp, u32, u32, vp, vp, vp, u32, vp]
     L.hml_hrotate_host.argtypes = [vp, u32, u32, vp, vp, u32, u64, vp]
+    L.hml_hmult_host_packed.argtypes = [vp, u32, u32, vp, vp, vp, u32, vp]
+    L.hml_hrotate_host_packed.argtypes = [vp, u32, u32, vp, vp, u32, u64, vp]
+    L.hml_packed_bytes.argtypes = [vp, u64]
+    L.hml_packed_bytes.restype = u64
+    L.hml_pack_host.argtypes = [vp, vp, u64, vp]
+    L.hml_unpack_host.argtypes = [vp, vp, u64, vp]
     L.hml_host_alloc_pinned.argtypes = [vp, u64, C.POINTER(vp)]
     L.hml_host_free_pinned.argtypes = [vp, vp]
     L.hml_trace_counts.argtypes = [C.c_char_p, u32, u32, u32, u32, u32, u32, u32, C.POINTER(_Counts)]
@@ -400,6 +407,30 @@ class Context:
         self._chk(self.lib.hml_hrotate_host(self.h, L, n, ct_host.data_ptr(), _ptr(rotkey_dev), evk_q_limbs or L, galois_elt,
                                             out_host.data_ptr()))
         return out_host
+
+    def pack_host(self, words_host):
+        """CPU tensor of uint64 words [.., N] -> uint8 CPU tensor of packed limbs (5N bytes per limb), pinned."""
+        import torch
+        n_limbs = words_host.numel() // self.N
+        out = torch.empty(self.lib.hml_packed_bytes(self.h, n_limbs), dtype=torch.uint8).pin_memory()
+        self._chk(self.lib.hml_pack_host(self.h, words_host.data_ptr(), n_limbs, out.data_ptr()))
+        return out
+
+    def unpack_host(self, packed_host, shape):
+        import torch
+        out = torch.empty(*shape, dtype=torch.int64)
+        self._chk(self.lib.hml_unpack_host(self.h, packed_host.data_ptr(), out.numel() // self.N, out.data_ptr()))
+        return out
+
+    def hmult_host_packed(self, L, n, a_packed, b_packed, evk_dev, out_packed, evk_q_limbs=None):
+        self._chk(self.lib.hml_hmult_host_packed(self.h, L, n, a_packed.data_ptr(), b_packed.data_ptr(), _ptr(evk_dev), evk_q_limbs or L,
+                                                 out_packed.data_ptr()))
+        return out_packed
+
+    def hrotate_host_packed(self, L, n, ct_packed, rotkey_dev, out_packed, galois_elt=5, evk_q_limbs=None):
+        self._chk(self.lib.hml_hrotate_host_packed(self.h, L, n, ct_packed.data_ptr(), _ptr(rotkey_dev), evk_q_limbs or L, galois_elt,
+                                                   out_packed.data_ptr()))
+        return out_packed
 
     def keyswitch_sharded(self, L, d_own, evk_own, rank, world, all_gather):
         """Limb-sharded key switch (SURVEY.md 8e mode 2).  `all_gather(buf)` must all-gather, in place along dim 0,

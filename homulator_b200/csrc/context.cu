@@ -1769,75 +1769,6 @@ extern "C" int hml_hrotate_batch(hml_ctx *ctx, uint32_t L, uint32_t n, const uin
   });
 }
 
-// ------------------------------------------------------------------------------------------------ host-buffer API
-// Three streams (copy-in, compute, copy-out) and two staging slots: the H2D of item i+1 and the D2H of
-// item i-1 overlap the kernels of item i.
-static int host_pipeline(hml_ctx *ctx, bool is_mult, uint32_t L, uint32_t n, const uint64_t *a_host, const uint64_t *b_host,
-                         const uint64_t *key_dev, uint32_t evk_q_limbs, uint64_t g, uint64_t *out_host) {
-  int rc = check_level(ctx, L, is_mult ? 2 : 1);
-  if (rc) return rc;
-  if (!a_host || (is_mult && !b_host) || !key_dev || !out_host) return fail(ctx, HML_ERR_INVALID, "null buffer");
-  CU_TRY(ctx, cudaSetDevice(ctx->device));
-  if ((rc = ensure_ws(ctx, is_mult ? hmult_ws_words(ctx->p, L, 1) : hrot_ws_words(ctx->p, L, 1)))) return rc;
-  const size_t N = ctx->p.N, in_w = 2 * N * L, out_w = 2 * N * (is_mult ? L - 1 : L);
-  const size_t slot_w = (is_mult ? 2 : 1) * in_w + out_w;
-  if (ctx->stage_words < 2 * slot_w) {
-    CU_TRY(ctx, cudaDeviceSynchronize());
-    if (ctx->stage) CU_TRY(ctx, cudaFree(ctx->stage));
-    ctx->stage = nullptr; ctx->stage_words = 0;
-    CU_TRY(ctx, cudaMalloc((void **)&ctx->stage, 2 * slot_w * 8));
-    ctx->stage_words = 2 * slot_w;
-  }
-  if (!ctx->s_in) {
-    CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
-    CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
-    CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
-  }
-  cudaEvent_t ev_in[2], ev_comp[2], ev_out[2];
-  for (int k = 0; k < 2; ++k) {
-    CU_TRY(ctx, cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
-    CU_TRY(ctx, cudaEventCreateWithFlags(&ev_comp[k], cudaEventDisableTiming));
-    CU_TRY(ctx, cudaEventCreateWithFlags(&ev_out[k], cudaEventDisableTiming));
-  }
-  rc = HML_OK;
-  ws_enter(ctx, ctx->s_comp);  // the workspace may still be in use by an op queued earlier on a caller stream
-  for (uint32_t i = 0; i < n && rc == HML_OK; ++i) {
-    const int k = i & 1;
-    u64 *sa = ctx->stage + k * slot_w, *sb = sa + in_w, *so = sa + (is_mult ? 2 : 1) * in_w;
-    if (i >= 2) cudaStreamWaitEvent(ctx->s_in, ev_comp[k], 0);  // slot inputs free once item i-2 has been computed
-    cudaMemcpyAsync(sa, a_host + i * in_w, in_w * 8, cudaMemcpyHostToDevice, ctx->s_in);
-    if (is_mult) cudaMemcpyAsync(sb, b_host + i * in_w, in_w * 8, cudaMemcpyHostToDevice, ctx->s_in);
-    cudaEventRecord(ev_in[k], ctx->s_in);
-    cudaStreamWaitEvent(ctx->s_comp, ev_in[k], 0);
-    if (i >= 2) cudaStreamWaitEvent(ctx->s_comp, ev_out[k], 0);  // slot output free once item i-2 has been copied out
-    rc = is_mult ? hmult_run(ctx, L, 1, sa, sb, (const u64 *)key_dev, evk_q_limbs, so, ctx->ws, ctx->s_comp)
-                 : hrot_run(ctx, L, 1, sa, (const u64 *)key_dev, evk_q_limbs, g, so, ctx->ws, ctx->s_comp);
-    cudaEventRecord(ev_comp[k], ctx->s_comp);
-    cudaStreamWaitEvent(ctx->s_out, ev_comp[k], 0);
-    cudaMemcpyAsync(out_host + i * out_w, so, out_w * 8, cudaMemcpyDeviceToHost, ctx->s_out);
-    cudaEventRecord(ev_out[k], ctx->s_out);
-  }
-  cudaError_t e1 = cudaStreamSynchronize(ctx->s_in), e2 = cudaStreamSynchronize(ctx->s_comp), e3 = cudaStreamSynchronize(ctx->s_out);
-  for (int k = 0; k < 2; ++k) { cudaEventDestroy(ev_in[k]); cudaEventDestroy(ev_comp[k]); cudaEventDestroy(ev_out[k]); }
-  ctx->have_last = false;  // everything has completed: nothing left to order against
-  if (rc) return rc;
-  for (cudaError_t e : {e1, e2, e3})
-    if (e != cudaSuccess) return fail(ctx, HML_ERR_CUDA, std::string("host pipeline: ") + cudaGetErrorString(e));
-  return HML_OK;
-}
-
-extern "C" int hml_hmult_host(hml_ctx *ctx, uint32_t L, uint32_t n, const uint64_t *a, const uint64_t *b, const uint64_t *evk_dev,
-                              uint32_t evk_q_limbs, uint64_t *out) {
-  if (!ctx) return HML_ERR_INVALID;
-  return host_pipeline(ctx, true, L, n, a, b, evk_dev, evk_q_limbs, 0, out);
-}
-extern "C" int hml_hrotate_host(hml_ctx *ctx, uint32_t L, uint32_t n, const uint64_t *ct, const uint64_t *rk_dev,
-                                uint32_t evk_q_limbs, uint64_t g, uint64_t *out) {
-  if (!ctx) return HML_ERR_INVALID;
-  if (!(g & 1)) return fail(ctx, HML_ERR_INVALID, "galois element must be odd");
-  return host_pipeline(ctx, false, L, n, ct, nullptr, rk_dev, evk_q_limbs, g, out);
-}
-
 // ------------------------------------------------------------------------------------------------ counts
 extern "C" int hml_trace_counts(const char *op, uint32_t N, uint32_t batch_size, uint32_t max_level, uint32_t L, uint32_t alpha,
                                 uint32_t bconv_high, uint32_t bconv_width, hml_counts *out) {

@@ -266,6 +266,17 @@ int hml_hmult_host(hml_ctx *ctx, uint32_t L, uint32_t n, const uint64_t *ct_a_ho
                    const uint64_t *evk_dev, uint32_t evk_q_limbs, uint64_t *ct_out_host);
 int hml_hrotate_host(hml_ctx *ctx, uint32_t L, uint32_t n, const uint64_t *ct_host, const uint64_t *rotkey_dev,
                      uint32_t evk_q_limbs, uint64_t galois_elt, uint64_t *ct_out_host);
+/* The same two calls with the ciphertexts PACKED in host memory: a residue has elementBitWidth <= 36 significant bits, so the
+ * reference's uint64_t words (include/Context.h:8) carry three empty bytes each over PCIe.  Packed limb = N uint32 low words
+ * followed by N high bytes (5N bytes; the compact form of the device's packed limbs); a packed ciphertext = its 2L limbs back
+ * to back.  hml_pack_host / hml_unpack_host convert on the CPU (plain loops; for clients that keep words). */
+uint64_t hml_packed_bytes(const hml_ctx *ctx, uint64_t n_limbs);
+int hml_pack_host(const hml_ctx *ctx, const uint64_t *words, uint64_t n_limbs, void *packed);
+int hml_unpack_host(const hml_ctx *ctx, const void *packed, uint64_t n_limbs, uint64_t *words);
+int hml_hmult_host_packed(hml_ctx *ctx, uint32_t L, uint32_t n, const void *ct_a_packed, const void *ct_b_packed, const uint64_t *evk_dev,
+                          uint32_t evk_q_limbs, void *ct_out_packed);
+int hml_hrotate_host_packed(hml_ctx *ctx, uint32_t L, uint32_t n, const void *ct_packed, const uint64_t *rotkey_dev, uint32_t evk_q_limbs,
+                            uint64_t galois_elt, void *ct_out_packed);
 int hml_host_alloc_pinned(hml_ctx *ctx, uint64_t n_words, uint64_t **out);
 int hml_host_free_pinned(hml_ctx *ctx, uint64_t *ptr);
 

@@ -430,3 +430,29 @@ def test_alternative_kernel_paths(env):
     r = subprocess.run([sys.executable, os.path.join(root, "tests", "sp_env_paths.py")], env=dict(os.environ, **env), capture_output=True, text=True,
                        timeout=900)
     assert r.returncode == 0 and "ENV_PATHS_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_host_buffer_paths_words_and_packed(north_star):
+    """hml_hmult_host / hml_hrotate_host (uint64 words, the reference's layout) and the *_packed variants (5 bytes per
+    coefficient over PCIe) run chunks of 8 ciphertexts through the batched schedule: 11 ciphertexts = one full + one partial
+    chunk, results equal to single calls; pack / unpack round trip on the CPU."""
+    ctx, o, a, b, evk = north_star
+    L, n, N = 35, 11, 65536
+    A = torch.stack([to_dev(a if i % 2 == 0 else b) for i in range(n)])
+    B = torch.stack([to_dev(b if i % 3 == 0 else a) for i in range(n)])
+    K = to_dev(evk)
+    want_m = torch.stack([ctx.hmult(L, A[i], B[i], K) for i in (0, 7, 8, 10)]).cpu()
+    want_r = torch.stack([ctx.hrotate(L, A[i], K, 5) for i in (0, 7, 8, 10)]).cpu()
+    ah, bh = A.cpu().pin_memory(), B.cpu().pin_memory()
+    oh = torch.empty(n, 2, L - 1, N, dtype=torch.int64).pin_memory()
+    ctx.hmult_host(L, ah, bh, K, oh)
+    assert torch.equal(oh[[0, 7, 8, 10]], want_m)
+    ap, bp = ctx.pack_host(ah), ctx.pack_host(bh)
+    assert ap.numel() == n * 2 * L * 5 * N
+    assert torch.equal(ctx.unpack_host(ap, ah.shape), ah)
+    op = torch.empty(n * 2 * (L - 1) * 5 * N, dtype=torch.uint8).pin_memory()
+    ctx.hmult_host_packed(L, n, ap, bp, K, op)
+    assert torch.equal(ctx.unpack_host(op, oh.shape), oh)
+    rp = torch.empty(n * 2 * L * 5 * N, dtype=torch.uint8).pin_memory()
+    ctx.hrotate_host_packed(L, n, ap, K, rp, 5)
+    assert torch.equal(ctx.unpack_host(rp, ah.shape)[[0, 7, 8, 10]], want_r)
