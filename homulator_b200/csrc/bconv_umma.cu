@@ -299,7 +299,8 @@ k_bconv_umma(const ModConst *__restrict__ mc, LimbMap src_lm, LimbMap dst_lm, BC
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int i = s * 16 + g * 4 + k;
-      soff[s][k] = i < a.n_src ? (a.src_off ? __ldg(a.src_off + i) : src_pos(i) * a.N) + lr : -1;
+      const long long *so = job && job->src_off ? job->src_off : a.src_off;
+      soff[s][k] = i < a.n_src ? (so ? __ldg(so + i) : src_pos(i) * a.N) + lr : -1;
       live[s] |= (i < a.n_src ? 1u : 0u) << k;
       if (i >= a.n_src) {  // padding sources: their staging slots are never written by a copy, they stay zero
 #pragma unroll

@@ -252,7 +252,7 @@ extern "C" void hml_ctx_destroy(hml_ctx *ctx) {
   for (auto &kv : ctx->bconv_cache) { cudaFree(kv.second.step1); cudaFree(kv.second.host.d_mat); cudaFree(kv.second.host.d_img); }
   for (auto &kv : ctx->shard_plans) {
     cudaFree(kv.second.scale1); cudaFree(kv.second.scale2); cudaFree(kv.second.pinv); cudaFree(kv.second.down.d_mat); cudaFree(kv.second.down.d_img);
-    cudaFree(kv.second.d_off2); cudaFree(kv.second.qlinv_own);
+    cudaFree(kv.second.d_off2); cudaFree(kv.second.qlinv_own); cudaFree(kv.second.up_jobs);
     for (auto *o : kv.second.d_off1) cudaFree(o);
     for (auto &u : kv.second.up) { cudaFree(u.d_mat); cudaFree(u.d_img); }
   }
@@ -1006,19 +1006,29 @@ static int shard_mid_tail(hml_ctx *ctx, ShardPlan *sp, uint32_t rank, const u64 
   const uint32_t nq = sp->own_q.size(), np = sp->own_p.size(), ne = nq + np, beta = sp->beta;
   const int logN = p.logN, npass = logN <= NTT_SMALL_LOG ? 1 : 2;
   u64 *ext = ctx->ws, *acc = ext + (size_t)beta * ne * N;
+  // one ciphertext's slice per rank: the inner product rides in the ModUp transform's row pass (NttMac) whenever it can
+  const bool hpip = ks_uses_hpip(ctx, sp->L, 1);
   {
     NttLaunch l{};
     l.n_batch = 1;
     l.in = ext; l.out = ext; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)ne * N;
     l.n_limbs = ne; l.n_polys = beta;
+    l.in_f64 = l.out_f64 = npass == 2;
+    if (hpip) {
+      NttMac &m = l.mac;
+      m.evk = evk_own; m.d = d_own; m.acc = acc; m.d_batch_stride = 0; m.acc_batch_stride = 0; m.acc_comp_stride = (long long)ne * N;
+      m.evk_limbs = (int)ne; m.u_limb = -1;
+      for (uint32_t k = 0; k < ne; ++k) m.key_pos[k] = (uint16_t)k;
+      ctx->exec.ewe_limbs += 2ull * ne * beta;
+    }
     launch_ntt_forward(tabs_for(ctx, s), logN, sp->e_lm, l, s);
     prof_mark(ctx, HML_CLS_NTT, s);
     ctx->exec.ntt_limbs += (uint64_t)beta * ne - nq; ctx->exec.kernel_launches += npass;
   }
-  {
+  if (!hpip) {
     InnerArgs a{};
     a.d = d_own; a.ext = ext; a.evk = evk_own; a.acc = acc; a.N = N; a.n_ext = ne; a.beta = beta;
-    a.evk_limbs = ne; a.n_batch = 1; a.u_limb = -1;
+    a.evk_limbs = ne; a.n_batch = 1; a.u_limb = -1; a.ext_f64 = npass == 2;
     launch_inner_product(ctx->mc, sp->e_lm, a, s);
     prof_mark(ctx, HML_CLS_EWE, s);
     ctx->exec.ewe_limbs += 2ull * ne * beta; ctx->exec.kernel_launches++;
@@ -1057,6 +1067,7 @@ extern "C" int hml_keyswitch_shard_mid(hml_ctx *ctx, uint32_t L, uint32_t rank, 
     if (sp->up[j].empty()) continue;
     BConvArgs a{};
     a.in = (const u64 *)gather1; a.out = ext + (size_t)j * ne * N; a.step1 = nullptr; a.N = N; a.n_batches = 1;
+    a.out_f64 = ctx->p.logN > NTT_SMALL_LOG;
     run_bconv(ctx, sp->up[j], sp->up_src[j], a, s);
   }
   return shard_mid_tail(ctx, sp, rank, (const u64 *)d_own, (const u64 *)evk_own, (u64 *)gather2, s);
@@ -1077,19 +1088,30 @@ static int shard_end_run(hml_ctx *ctx, ShardPlan *sp, const u64 *gather2, const 
   {
     BConvArgs a{};
     a.in = gather2; a.out = vb; a.in_batch_stride = (long long)sp->gp * N; a.out_batch_stride = (long long)nq * N;
-    a.step1 = nullptr; a.N = N; a.n_batches = 2; a.src_off = src_off;
+    a.step1 = nullptr; a.N = N; a.n_batches = 2; a.src_off = src_off; a.out_f64 = npass == 2;
     run_bconv(ctx, sp->down, sp->down_src, a, s);
   }
+  const bool fuse = npass == 2;  // two-pass rings: K10 (+ the caller's addends) is the transform's epilogue, as in ks_tail
   {
     NttLaunch l{};
     l.n_batch = 1;
     l.in = vb; l.out = vb; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)nq * N;
-    l.n_limbs = nq; l.n_polys = 2;
+    l.n_limbs = nq; l.n_polys = 2; l.in_f64 = npass == 2;
+    if (fuse) {
+      NttFuse &f = l.fuse;
+      f.x = acc; f.x_c_stride = (long long)ne * N; f.x_b_stride = 0; f.x_packed = 0;
+      f.z = add0_own ? add0_own : add1_own; f.z_b_stride = 0;
+      f.z_c_stride = (add0_own && add1_own) ? (long long)(add1_own - add0_own) : 0;
+      f.z_mask = (add0_own ? 1u : 0u) | (add1_own ? 2u : 0u);
+      f.dst = out0_own; f.dst_c_stride = (long long)(out1_own - out0_own); f.dst_b_stride = 0;
+      f.cst = sp->pinv; f.n_c = 2;
+      ctx->exec.ewe_limbs += 2 * nq;
+    }
     launch_ntt_forward(tabs_for(ctx, s), logN, sp->q_lm, l, s);
     prof_mark(ctx, HML_CLS_NTT, s);
     ctx->exec.ntt_limbs += 2 * nq; ctx->exec.kernel_launches += npass;
   }
-  {  // both outputs in one launch: the "poly" stride of the output is simply the distance between the two buffers
+  if (!fuse) {  // both outputs in one launch: the "poly" stride of the output is simply the distance between the two buffers
     SubMulArgs a{};
     a.x = acc; a.x_poly_stride = (long long)ne * N; a.y = vb; a.y_poly_stride = (long long)nq * N; a.z = nullptr;
     a.out = out0_own; a.out_poly_stride = (long long)(out1_own - out0_own);
@@ -1268,6 +1290,24 @@ static int shard_peer_offsets(hml_ctx *ctx, ShardPlan *sp, const uint64_t *const
       if ((rc = upload(ctx, off, &d))) return rc;
       sp->d_off1.push_back(d);
     }
+    // the one-launch form of the ModUp conversions: every CTA serves one digit and reads its sources from the owners' buffers
+    cudaFree(sp->up_jobs); sp->up_jobs = nullptr;
+    {
+      const uint32_t ne = sp->own_q.size() + sp->own_p.size();
+      std::vector<BConvJob> jobs(sp->beta);
+      bool ok = sp->beta >= 2;
+      for (uint32_t j = 0; j < sp->beta && ok; ++j) {
+        const HostBConv &hb = sp->up[j];
+        ok = !hb.empty() && hb.d_img != nullptr && hb.n_src <= 48 && hb.n_dst <= 48;
+        if (!ok) break;
+        BConvJob &jb = jobs[j];
+        memset(&jb, 0, sizeof(jb));
+        for (int t = 0; t < hb.n_dst; ++t) { jb.dst_mod[t] = hb.dst_lm.mod[t]; jb.dst_pos[t] = hb.dst_lm.pos[t]; }
+        jb.img = hb.d_img; jb.K = hb.im.K; jb.NP = hb.im.NP; jb.ND = hb.im.ND; jb.n_src = hb.n_src; jb.n_dst = hb.n_dst;
+        jb.in_off = 0; jb.out_off = (long long)j * ne * N; jb.src_off = sp->d_off1[j];
+      }
+      if (ok && (rc = upload(ctx, jobs, &sp->up_jobs))) return rc;
+    }
   } else {
     cudaFree(sp->d_off2); sp->d_off2 = nullptr;
     std::vector<long long> off(A);
@@ -1302,11 +1342,25 @@ extern "C" int hml_keyswitch_shard_mid_p2p(hml_ctx *ctx, uint32_t L, uint32_t ra
   const uint32_t ne = sp->own_q.size() + sp->own_p.size(), beta = sp->beta;
   if (ne == 0) return HML_OK;
   u64 *ext = ctx->ws;
-  for (uint32_t j = 0; j < beta; ++j) {
+  bool merged_up = false;
+  if (sp->up_jobs) {
+    BConvArgs a{};
+    a.in = (const u64 *)peers1[rank]; a.out = ext; a.step1 = nullptr; a.N = N; a.n_batches = 1; a.out_f64 = ctx->p.logN > NTT_SMALL_LOG;
+    std::vector<BConvImage> ims(beta);
+    std::vector<int> nd(beta);
+    for (uint32_t j = 0; j < beta; ++j) { ims[j] = sp->up[j].im; nd[j] = sp->up[j].n_dst; }
+    merged_up = launch_bconv_umma_multi(ctx->mc, sp->up_jobs, ims.data(), nd.data(), (int)beta, a, (cudaStream_t)stream);
+    if (merged_up) {
+      prof_mark(ctx, HML_CLS_BCONV, (cudaStream_t)stream);
+      ctx->exec.kernel_launches++;
+      for (uint32_t j = 0; j < beta; ++j) ctx->exec.bconv_limb_macs += (uint64_t)sp->up[j].n_src * sp->up[j].n_dst;
+    }
+  }
+  for (uint32_t j = 0; j < beta && !merged_up; ++j) {
     if (sp->up[j].empty()) continue;
     BConvArgs a{};
     a.in = (const u64 *)peers1[rank]; a.out = ext + (size_t)j * ne * N; a.step1 = nullptr; a.N = N; a.n_batches = 1;
-    a.src_off = sp->d_off1[j];
+    a.src_off = sp->d_off1[j]; a.out_f64 = ctx->p.logN > NTT_SMALL_LOG;
     run_bconv(ctx, sp->up[j], sp->up_src[j], a, (cudaStream_t)stream);
   }
   return shard_mid_tail(ctx, sp, rank, (const u64 *)d_own, (const u64 *)evk_own, (u64 *)gather2_own, (cudaStream_t)stream);

@@ -72,6 +72,7 @@ struct ShardPlan {
   // peer-direct mode (hml_keyswitch_shard_*_p2p): per-source word offsets into the OWNERS' gather buffers, relative to this
   // rank's own buffer, rebuilt whenever the peer pointers change
   std::vector<long long *> d_off1;         // [beta] device arrays [a_j]
+  BConvJob *up_jobs = nullptr;             // [beta] one-launch form of the ModUp conversions (rebuilt with d_off1), or null
   long long *d_off2 = nullptr;             // device array [alpha]
   std::vector<const void *> peers1_sig, peers2_sig;
   // sharded rescale (hml_rescale_shard_*): q_{L-1}^-1 mod q_l for the owned limbs l < L - 1

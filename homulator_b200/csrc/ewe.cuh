@@ -107,6 +107,7 @@ struct BConvJob {
   int K, NP, ND;
   int n_src, n_dst;
   long long in_off, out_off;  // words, added to BConvArgs::in / out
+  const long long *src_off;   // optional device array [n_src]: word offset of every source relative to BConvArgs::in (peer buffers)
 };
 // host: eligibility (n_src <= 48, 5 * pad8(n_dst + fold) <= 256) and image construction; see bconv_umma.cu
 bool bconv_image_shape(int n_src, int n_dst, int fold, BConvImage &im);
