@@ -58,7 +58,7 @@ EXPORTS = [
     "hml_ctx_create", "hml_ctx_create_params", "hml_ctx_destroy", "hml_last_error", "hml_last_create_error",
     "hml_ring_degree", "hml_n_moduli", "hml_get_moduli", "hml_get_roots", "hml_dev_alloc", "hml_dev_free", "hml_h2d",
     "hml_d2h", "hml_sync", "hml_ntt", "hml_intt", "hml_ntt_batch", "hml_intt_batch", "hml_ewe", "hml_automorph", "hml_bconv", "hml_bconv_batch", "hml_keyswitch", "hml_rescale",
-    "hml_hmult", "hml_hrotate", "hml_hadd", "hml_pmult", "hml_padd", "hml_hmult_batch", "hml_hrotate_batch",
+    "hml_hmult", "hml_hrotate", "hml_hadd", "hml_pmult", "hml_padd", "hml_pmult_add", "hml_hmult_batch", "hml_hrotate_batch",
     "hml_hmult_host", "hml_hrotate_host", "hml_hmult_host_packed", "hml_hrotate_host_packed", "hml_packed_bytes", "hml_pack_host",
     "hml_unpack_host", "hml_host_alloc_pinned", "hml_host_free_pinned", "hml_trace_counts",
     "hml_get_counts", "hml_buffer_plan", "hml_exec_counts_get", "hml_exec_counts_reset", "hml_cli_main", "hml_profile_begin", "hml_profile_end",
@@ -109,6 +109,7 @@ def load_library():
     L.hml_hrotate.argtypes = [vp, u32, vp, vp, u32, u64, vp, vp]
     for f in ("hml_hadd", "hml_pmult", "hml_padd"):
         getattr(L, f).argtypes = [vp, u32, vp, vp, vp, vp]
+    L.hml_pmult_add.argtypes = [vp, u32, vp, vp, vp, vp, vp]
     L.hml_hmult_batch.argtypes = [vp, u32, u32, vp, vp, vp, u32, vp, vp]
     L.hml_hrotate_batch.argtypes = [vp, u32, u32, vp, vp, u32, u64, vp, vp]
     L.hml_hmult_host.argtypes = [vp, u32, u32, vp, vp, vp, u32, vp]
@@ -381,6 +382,11 @@ class Context:
     def padd(self, L, ct, pt, out=None):
         out = self.empty(2, L, self.N) if out is None else out
         self._chk(self.lib.hml_padd(self.h, L, _ptr(ct), _ptr(pt), _ptr(out), self._stream()))
+        return out
+
+    def pmult_add(self, L, ct, pt, ct_add, out=None):
+        out = self.empty(2, L, self.N) if out is None else out
+        self._chk(self.lib.hml_pmult_add(self.h, L, _ptr(ct), _ptr(pt), _ptr(ct_add), _ptr(out), self._stream()))
         return out
 
     def hmult_batch(self, L, ct_a, ct_b, evk, evk_q_limbs=None, out=None):

@@ -1741,6 +1741,23 @@ static int ew_ct_op(hml_ctx *ctx, uint32_t L, const uint64_t *a, const uint64_t 
   ctx->exec.ewe_limbs += 2ull * L; ctx->exec.kernel_launches++;
   return check_launch(ctx, "ewe op");
 }
+// out = ct * pt + ct_add: PMULT followed by HADD as ONE element-wise pass — the reference's MULT instruction computes
+// x1 * x2 + x3 * x4 natively (InsGen::GenEWE, reference src/InsGen.cpp:77-125), the two ops just never meet in one trace there.
+// Bit-identical to hml_pmult + hml_hadd (exact arithmetic mod q).  `out` may alias ct_add.
+extern "C" int hml_pmult_add(hml_ctx *ctx, uint32_t L, const uint64_t *ct, const uint64_t *pt, const uint64_t *ct_add, uint64_t *out, void *stream) {
+  int rc = check_level(ctx, L, 1);
+  if (rc) return rc;
+  if (!ct || !pt || !ct_add || !out) return fail(ctx, HML_ERR_INVALID, "null buffer");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  LevelConsts *lc;
+  if ((rc = get_level(ctx, L, &lc))) return rc;
+  const long long PL = (long long)ctx->p.N * L;
+  const long long cs[5] = {PL, 0, PL, 0, PL};
+  launch_ewe(ctx->mc, lc->q_lm, (int)ctx->p.N, (int)L, (const u64 *)ct, (const u64 *)pt, (const u64 *)ct_add, nullptr, 0, (u64 *)out, (cudaStream_t)stream, 2, cs);
+  prof_mark(ctx, HML_CLS_EWE, (cudaStream_t)stream);
+  ctx->exec.ewe_limbs += 4ull * L; ctx->exec.kernel_launches++;
+  return check_launch(ctx, "pmult + hadd");
+}
 extern "C" int hml_hadd(hml_ctx *ctx, uint32_t L, const uint64_t *a, const uint64_t *b, uint64_t *out, void *s) {
   return ew_ct_op(ctx, L, a, b, false, false, out, s);
 }

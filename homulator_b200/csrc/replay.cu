@@ -181,9 +181,29 @@ static int enqueue(hml_replay *rp, cudaStream_t s) {
                     : hml_hrotate(ctx, L, a, key, rp->evk_q_limbs, galois_of(ctx, o.b), dst, st);
         break;
       }
-      case HML_OP_PMULT:
+      case HML_OP_PMULT: {
+        // peephole: "t = a * pt; d = d + t" with t dead afterwards (its next access, if any, is a write) is ONE element-wise
+        // pass d = a * pt + d (hml_pmult_add): the accumulation loops of rotation-heavy traces are made of exactly this pair
+        if (i + 1 < rp->ops.size()) {
+          const hml_trace_op &n = rp->ops[i + 1];
+          const bool pair = n.kind == HML_OP_HADD && n.dst != o.dst && ((n.a == n.dst && n.b == o.dst) || (n.b == n.dst && n.a == o.dst)) && o.a != n.dst;
+          bool dead = pair;
+          for (size_t k = i + 2; k < rp->ops.size() && dead; ++k) {
+            const hml_trace_op &q = rp->ops[k];
+            const bool reads = q.a == o.dst || ((q.kind == HML_OP_HADD || q.kind == HML_OP_HMULT) && q.b == o.dst);
+            if (reads) dead = false;
+            else if (q.dst == o.dst) break;  // overwritten before any read
+          }
+          if (pair && dead) {
+            uint64_t *acc = rp->slot[n.dst];
+            rc = rp->sh ? hml_ew_sharded(rp->sh, L, 3, a, rp->pts[o.b], acc, st) : hml_pmult_add(ctx, L, a, rp->pts[o.b], acc, acc, st);
+            ++i;
+            break;
+          }
+        }
         rc = rp->sh ? hml_ew_sharded(rp->sh, L, 1, a, rp->pts[o.b], dst, st) : hml_pmult(ctx, L, a, rp->pts[o.b], dst, st);
         break;
+      }
       case HML_OP_PADD:
         rc = rp->sh ? hml_ew_sharded(rp->sh, L, 2, a, rp->pts[o.b], dst, st) : hml_padd(ctx, L, a, rp->pts[o.b], dst, st);
         break;

@@ -288,9 +288,10 @@ extern "C" int hml_rescale_sharded(hml_shard *sh, uint32_t L, const uint64_t *x_
   return run_op(sh, ShardOp{SOP_RESCALE, L, (const uint64_t *)x_own, nullptr, nullptr, (uint64_t *)out_own, nullptr, 0}, (cudaStream_t)stream);
 }
 
-// limb-local ciphertext ops on the owned limbs: kind 0 = hadd (b = ct [2][nq][N]), 1 = pmult, 2 = padd (b = pt [nq][N])
+// limb-local ciphertext ops on the owned limbs: kind 0 = hadd (b = ct [2][nq][N]), 1 = pmult, 2 = padd (b = pt [nq][N]),
+// 3 = pmult + hadd in one pass (out = a * b + out: `out_own` is also the addend)
 extern "C" int hml_ew_sharded(hml_shard *sh, uint32_t L, int kind, const uint64_t *a_own, const uint64_t *b_own, uint64_t *out_own, void *stream) {
-  if (!sh || !a_own || !b_own || !out_own || kind < 0 || kind > 2) return HML_ERR_INVALID;
+  if (!sh || !a_own || !b_own || !out_own || kind < 0 || kind > 3) return HML_ERR_INVALID;
   int rc = check_level(sh->ctx, L, 1);
   if (rc) return rc;
   const uint32_t nq = own_q_count(L, sh->rank, sh->world);
@@ -300,8 +301,9 @@ extern "C" int hml_ew_sharded(hml_shard *sh, uint32_t L, int kind, const uint64_
   for (uint32_t k = 0; k < nq; ++k) own[k] = sh->rank + k * sh->world;
   for (int c = 0; c < 2; ++c) {
     const uint64_t *a = a_own + c * PL, *b = kind == 0 ? b_own + c * PL : b_own;
-    rc = kind == 1 ? hml_ewe(sh->ctx, a, b, nullptr, nullptr, 0, out_own + c * PL, own.data(), nq, stream)
-                   : hml_ewe(sh->ctx, a, nullptr, b, nullptr, 0, out_own + c * PL, own.data(), nq, stream);
+    rc = kind == 1   ? hml_ewe(sh->ctx, a, b, nullptr, nullptr, 0, out_own + c * PL, own.data(), nq, stream)
+         : kind == 3 ? hml_ewe(sh->ctx, a, b, out_own + c * PL, nullptr, 0, out_own + c * PL, own.data(), nq, stream)
+                     : hml_ewe(sh->ctx, a, nullptr, b, nullptr, 0, out_own + c * PL, own.data(), nq, stream);
     if (rc) return rc;
   }
   return HML_OK;

@@ -220,7 +220,8 @@ int hml_hrotate_sharded(hml_shard *sh, uint32_t L, const uint64_t *ct_own, const
 int hml_hmult_sharded(hml_shard *sh, uint32_t L, const uint64_t *a_own, const uint64_t *b_own, const uint64_t *evk_own,
                       uint64_t *out_own, void *stream);
 int hml_rescale_sharded(hml_shard *sh, uint32_t L, const uint64_t *x_own, uint64_t *out_own, void *stream);
-/* HADD (kind 0, b = ciphertext), PMULT (1), PADD (2) (b = plaintext [nq][N]) on the owned limbs: no exchange */
+/* HADD (kind 0, b = ciphertext), PMULT (1), PADD (2) (b = plaintext [nq][N]), PMULT + HADD in one pass (3: out = a * b + out)
+ * on the owned limbs: no exchange */
 int hml_ew_sharded(hml_shard *sh, uint32_t L, int kind, const uint64_t *a_own, const uint64_t *b_own, uint64_t *out_own, void *stream);
 /* All ranks of a group driven by ONE host thread, phase by phase (the CLI's [cluster] argument; tests on a one-GPU box).
  * op_kind: 0 keyswitch (a = d_own, out0, out1), 1 hrotate (a = ct_own, out0), 2 hmult (a, b, out0), 3 rescale (a, out0); every
@@ -251,6 +252,10 @@ int hml_hrotate_hoisted(hml_ctx *ctx, uint32_t L, const uint64_t *ct, uint32_t n
 int hml_hadd(hml_ctx *ctx, uint32_t L, const uint64_t *ct_a, const uint64_t *ct_b, uint64_t *ct_out, void *stream);
 int hml_pmult(hml_ctx *ctx, uint32_t L, const uint64_t *ct, const uint64_t *pt, uint64_t *ct_out, void *stream);
 int hml_padd(hml_ctx *ctx, uint32_t L, const uint64_t *ct, const uint64_t *pt, uint64_t *ct_out, void *stream);
+/* ct_out = ct * pt + ct_add: PMULT followed by HADD as one element-wise pass (the reference's MULT instruction is natively
+ * x1 * x2 + x3 * x4, src/InsGen.cpp:77-125); bit-identical to the two calls.  ct_out may alias ct_add.  hml_replay_* uses it
+ * for "t = a * pt; d = d + t" pairs whose t is dead afterwards. */
+int hml_pmult_add(hml_ctx *ctx, uint32_t L, const uint64_t *ct, const uint64_t *pt, const uint64_t *ct_add, uint64_t *ct_out, void *stream);
 
 /* Batched, data-parallel over independent ciphertexts sharing one key (BASELINE.json configs[3]).
  * ct_a, ct_b [n][2][L][N]; ct_out [n][2][L-1][N] (hmult) / [n][2][L][N] (hrotate). */

@@ -61,6 +61,12 @@ def test_hadd_pmult_padd():
     assert np.array_equal(to_host(ctx.hadd(L, to_dev(a), to_dev(b))), o.hadd(L, a, b))
     assert np.array_equal(to_host(ctx.pmult(L, to_dev(a), to_dev(pt))), o.pmult(L, a, pt))
     assert np.array_equal(to_host(ctx.padd(L, to_dev(a), to_dev(pt))), o.padd(L, a, pt))
+    # PMULT followed by HADD in one pass (hml_pmult_add), also in place on the addend
+    want = o.hadd(L, o.pmult(L, a, pt), b)
+    assert np.array_equal(to_host(ctx.pmult_add(L, to_dev(a), to_dev(pt), to_dev(b))), want)
+    acc = to_dev(b)
+    ctx.pmult_add(L, to_dev(a), to_dev(pt), acc, out=acc)
+    assert np.array_equal(to_host(acc), want)
 
 
 def test_evk_all_zero_gives_zero_keyswitch():
