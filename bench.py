@@ -34,6 +34,12 @@ HMULT_SIM_CYCLES = 221716  # the reference's own `Homulator.run config_4.cfg hmu
 WORKLOAD = "hmult config_4.cfg maxLevel=45 currentLevel=35 alpha=15 (BASELINE.json configs[0]/[3])"
 
 
+def bench_config(world):
+    """The workload both arms name: BASELINE.json configs[3], 256 ciphertexts per step over the job."""
+    return {"workload": WORKLOAD, "batch_per_gpu_per_step": max(1, 256 // world), "ciphertexts_per_step": max(1, 256 // world) * world,
+            "l2": "inputs larger than L2 (no flush)"}
+
+
 def measured_peaks():
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -140,7 +146,9 @@ def run_reference(args, real_stdout):
     line = {
         "impl": "reference", "metric": METRIC, "value": us, "unit": "us", "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": us / 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u64 (36-bit residues)", "data": "synthetic", "config": {"workload": WORKLOAD, "batch_per_step": 1},
+        "dtype": "u64 residues (36-bit), arithmetic on the FP64 pipe", "data": "synthetic",
+        # the same `config` as the GPU arm; each step here is a bounded SAMPLE of that step (one hmult), see cpu_baseline.sample
+        "config": bench_config(max(1, args.gpus)),
         "cpu_baseline": {"value": us, "unit": "us", "cores": used, "kind": "port",
                          "sample": "%d hmult at the full config, oracle/oracle.c with OpenMP over limbs" % steps},
         "e2e": {"value": us, "unit": "us", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -431,7 +439,7 @@ def main():
     except Exception:
         pass
 
-    extra = {"hrotate_batched_us": hrot_batched_us, "hmult_batched_us": us_per_op, "ntt_limbs_per_s": ntt_limbs_per_s, "ntt_us_per_limb": ntt_ms * 1e3 / (n_limbs * n_b),
+    extra = {"hrotate_batched_us": hrot_batched_us, "hmult_batched_us": us_per_op, "throughput_hmult_per_s": n_ops / (ms_total * 1e-3), "ntt_limbs_per_s": ntt_limbs_per_s, "ntt_us_per_limb": ntt_ms * 1e3 / (n_limbs * n_b),
              "ntt_us_per_limb_single_ciphertext_launch": ntt1_us_per_limb, "e2e_matches_device_path": e2e_ok,
              "e2e_packed_host_format": {"value": e2e_packed_us, "unit": "us", "h2d_bytes_per_step": 2 * 2 * L * 5 * N_RING * Be,
                                         "d2h_bytes_per_step": 2 * (L - 1) * 5 * N_RING * Be, "matches_u64_path": e2e_packed_ok,
@@ -504,9 +512,7 @@ def main():
         "metric": METRIC, "value": us_per_op, "unit": "us", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64 residues (36-bit), arithmetic on the FP64 pipe", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu_per_step": B, "ciphertexts_per_step": B * world,
-                   "l2": "inputs larger than L2 (no flush)",
-                   "throughput_hmult_per_s": n_ops / (ms_total * 1e-3)},
+        "config": bench_config(world) if args.batch <= 0 else dict(bench_config(world), batch_per_gpu_per_step=B, ciphertexts_per_step=B * world),
         "e2e": {"value": e2e_us, "unit": "us", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                 "batch_per_gpu_per_step": Be},
         "gpu_launches": int(launches),
