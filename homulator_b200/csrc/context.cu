@@ -651,7 +651,7 @@ int ks_modup(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d,
   // K3 (reference :137-188): convert every digit to the limbs of the extended basis it does not own — ONE launch for all
   // digits when they fit the tcgen05 kernel's multi-conversion form (every CTA serves one digit), else one launch per digit
   bool merged_up = false;
-  if (lc->up_jobs && beta >= 2) {
+  if (lc->up_jobs && beta >= 2 && nb <= 4) {  // big chunks amortise the per-launch set-up anyway and run 3 % faster digit by digit
     BConvArgs a{};
     a.in = yb; a.out = ext; a.step1 = nullptr; a.N = N; a.n_batches = nb;
     a.in_batch_stride = (long long)L * N; a.out_batch_stride = (long long)beta * E * N; a.out_f64 = npass == 2;
@@ -715,7 +715,7 @@ int ks_inner(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d,
     a.galois = (unsigned)(galois & (2ull * N - 1)); a.logN = logN;
     if (a.galois == 1) a.galois = 0;
     a.u_limb = -1;
-    if (mu) {  // hmult: u[L-1] = acc[L-1] * P^-1 + d[L-1] lands in slot E of each accumulator (host copy of the constant)
+    if (mu && nb == 1) {  // hmult: u[L-1] = acc[L-1] * P^-1 + d[L-1] lands in slot E of each accumulator (host copy of the constant)
       a.u_limb = (int)L - 1; a.u_slot = (int)E; a.u_add = mu->add; a.u_add_comp_stride = mu->comp_stride; a.u_add_batch_stride = mu->batch_stride;
       a.u_cst = lc->pinv_last;
       ctx->exec.ewe_limbs += 4ull * nb;
@@ -723,6 +723,21 @@ int ks_inner(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d,
     launch_inner_product(ctx->mc, ip, a, s);
     prof_mark(ctx, HML_CLS_EWE, s);
     ctx->exec.ewe_limbs += 2ull * nb * E * beta; ctx->exec.kernel_launches++;
+    if (mu && nb > 1) {
+      // batches keep the inner product's kernel lean (78 registers): u[L-1] = acc[L-1] * P^-1 + d[L-1] -> slot E is two small
+      // element-wise launches per chunk (one per component, every ciphertext of the chunk) instead of a side output
+      for (int c = 0; c < 2; ++c) {
+        SubMulArgs u{};
+        u.x = acc + ((size_t)c * AL + (L - 1)) * N; u.x_poly_stride = 2ll * AL * N;
+        u.y = nullptr;
+        u.z = mu->add + c * mu->comp_stride + (size_t)(L - 1) * N; u.z_poly_stride = mu->batch_stride;
+        u.out = acc + ((size_t)c * AL + E) * N; u.out_poly_stride = 2ll * AL * N;
+        u.cst = lc->pinv + (L - 1); u.N = N; u.n_limbs = 1; u.n_polys = nb; u.x_packed = u.z_packed = 1;
+        launch_sub_mul_add(ctx->mc, lc->last_lm, u, s);
+        prof_mark(ctx, HML_CLS_EWE, s);
+        ctx->exec.ewe_limbs += 2ull * nb; ctx->exec.kernel_launches++;
+      }
+    }
   }
   // K6 + K7 (reference :417-487): INTT of the P-limbs of both accumulators, in place, BConv step 1 folded in.  hmult adds
   // one limb to the same launch: slot E (modulus q_{L-1}) = u[L-1], the Rescale INTT (reference :766-805)

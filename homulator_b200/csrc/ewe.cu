@@ -138,14 +138,15 @@ __global__ void __launch_bounds__(EW_THREADS, 3) k_inner(const ModConst *__restr
   };
   // source slots of this thread's two coefficients under the automorphism (identity when galois == 0)
   unsigned s0 = 2u * i2, s1 = 2u * i2 + 1u;
-  if (a.galois) {
+  const bool gal = !MULTI && a.galois != 0;  // the batched variant stays lean: no automorphism on load, no u side output
+  if (gal) {
     const unsigned sh = 32 - a.logN, m2n = (2u << a.logN) - 1u;
     s0 = __brev((((a.galois * (2u * (__brev(s0) >> sh) + 1u)) & m2n) - 1u) >> 1) >> sh;
     s1 = __brev((((a.galois * (2u * (__brev(s1) >> sh) + 1u)) & m2n) - 1u) >> 1) >> sh;
   }
   auto ld_digit = [&](int b, int j) -> ulonglong2 {
     const u64 *p = digit_ptr(b, j);
-    if (!a.galois) return ld2(p, i2);
+    if (!gal) return ld2(p, i2);
     return make_ulonglong2(__ldg(p + s0), __ldg(p + s1));
   };
   ulonglong2 tn[IP_MAX_BETA];
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(EW_THREADS, 3) k_inner(const ModConst *__restr
       st2(acc, (size_t)e * n2 + i2, r00, r01);
       st2(acc, comp2 + (size_t)e * n2 + i2, r10, r11);
     }
-    if (e == a.u_limb) {  // uniform per CTA: u = acc * P^-1 + d on the limb the rescale drops (no extra launch, no re-read)
+    if (!MULTI && e == a.u_limb) {  // uniform per CTA: u = acc * P^-1 + d on the limb the rescale drops (no extra launch, no re-read)
       const u64 *ua = a.u_add + (size_t)b * a.u_add_batch_stride + (size_t)e * a.N;
       const ulonglong2 d0v = ld_packed2(ua, a.N, i2), d1v = ld_packed2(ua + a.u_add_comp_stride, a.N, i2);
       const double2 c = a.u_cst;
