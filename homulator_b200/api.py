@@ -68,7 +68,7 @@ EXPORTS = [
     "hml_shard_status", "hml_shard_create", "hml_shard_destroy", "hml_shard_handles", "hml_shard_connect_ipc",
     "hml_shard_connect_local", "hml_shard_prepare", "hml_shard_check", "hml_shard_own_limbs", "hml_keyswitch_sharded",
     "hml_hrotate_sharded", "hml_hmult_sharded", "hml_rescale_sharded", "hml_ew_sharded", "hml_group_op", "hml_hrotate_hoisted",
-    "hml_replay_create", "hml_replay_bind", "hml_replay_run", "hml_replay_slot", "hml_replay_destroy",
+    "hml_replay_create", "hml_replay_bind", "hml_replay_run", "hml_replay_slot", "hml_replay_slot_level", "hml_replay_destroy",
 ]
 
 
@@ -163,6 +163,7 @@ def load_library():
     L.hml_replay_bind.argtypes = [vp, vp, C.POINTER(vp), u32, C.POINTER(u32), C.POINTER(vp), u32, vp, u32]
     L.hml_replay_run.argtypes = [vp, vp]
     L.hml_replay_slot.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u32)]
+    L.hml_replay_slot_level.argtypes = [vp, u32, C.POINTER(u32)]
     L.hml_replay_destroy.argtypes = [vp]
     L.hml_dev_alloc.argtypes = [vp, u64, C.POINTER(vp)]
     L.hml_dev_free.argtypes = [vp, vp]

@@ -2,8 +2,10 @@
 //
 // The reference simulates ONE operation per run and cannot chain them ("NotSuppotr the continuous operation simulate",
 // reference src/Operation.cpp:636,675,714); its tree holds no application trace.  A trace here is a list of the five operations
-// the reference's CLI accepts (reference bench_test/bench_micro24.cpp:29-48) over numbered ciphertext slots, all at one level
-// L; it runs on one GPU (hml_ctx) or limb-sharded over a group (hml_shard), as plain launches or as ONE captured CUDA graph,
+// the reference's CLI accepts (reference bench_test/bench_micro24.cpp:29-48) over numbered ciphertext slots; the input enters
+// at level L and every hmult lowers its result by one level, which later ops of the trace may go on using (keys bound in a
+// layout with evk_q_limbs >= L serve every level; a plaintext's first limbs serve the lower levels).  A trace runs on one GPU
+// (hml_ctx) or limb-sharded over a group (hml_shard), as plain launches or as ONE captured CUDA graph,
 // and optionally with hoisted rotations: consecutive hrotate ops that read the same slot share one ModUp
 // (hml_hrotate_hoisted; single-GPU traces only).
 #include <algorithm>
@@ -29,7 +31,9 @@ struct hml_replay {
   uint32_t nq = 0, nk = 0;                 // limbs per polynomial of a slot at level L / of an hmult result (owned limbs when sharded)
   std::vector<hml_trace_op> ops;
   std::vector<uint64_t *> slot;            // device buffers, slot 0 = the bound input
-  std::vector<uint8_t> owned, is_result;   // allocated here / produced by hmult (one level lower, never an input)
+  std::vector<uint8_t> owned;              // allocated here
+  std::vector<uint32_t> op_level;          // level every op runs at (= the level of its sources when it is reached)
+  std::vector<uint32_t> final_level;       // level of every slot after the whole trace (0: never written)
   // bindings
   const uint64_t *x = nullptr, *evk = nullptr;
   std::vector<const uint64_t *> pts, keys;
@@ -60,35 +64,37 @@ extern "C" int hml_replay_create(hml_ctx *ctx, hml_shard *sh, uint32_t L, const 
   for (const hml_trace_op &o : rp->ops)
     if (o.kind == HML_OP_HADD || o.kind == HML_OP_HMULT) ns = std::max(ns, o.b + 1);
   rp->n_slots = ns;
-  rp->slot.assign(ns, nullptr); rp->owned.assign(ns, 0); rp->is_result.assign(ns, 0);
+  rp->slot.assign(ns, nullptr); rp->owned.assign(ns, 0); rp->final_level.assign(ns, 0);
   rp->nq = L; rp->nk = L - 1;
   if (sh && (rc = hml_shard_own_limbs(sh, L, &rp->nq, &rp->nk))) { delete rp; return rc; }
-  // validate: slot 0 is the input; every source must have been written before; hmult results are final
-  std::vector<uint8_t> written(ns, 0);
-  written[0] = 1;
+  // walk the trace once: slot 0 is the input at level L; a source must have been written; the two sources of hadd / hmult
+  // must sit at the same level; hmult lowers its result by one level and cannot run in place
+  std::vector<uint32_t> &lvl = rp->final_level;
+  lvl[0] = L;
   auto bad = [&](const char *m) { delete rp; return fail(ctx, HML_ERR_INVALID, std::string("trace: ") + m); };
   for (const hml_trace_op &o : rp->ops) {
     if (o.kind > HML_OP_HMULT) return bad("unknown operation");
     if (o.dst == 0) return bad("slot 0 is the input and cannot be overwritten");
-    if (!written[o.a] || rp->is_result[o.a]) return bad("source slot not yet written, or an hmult result (one level lower)");
+    if (!lvl[o.a]) return bad("source slot not yet written");
+    const uint32_t la = lvl[o.a];
     if (o.kind == HML_OP_HADD || o.kind == HML_OP_HMULT) {
-      if (!written[o.b] || rp->is_result[o.b]) return bad("second source slot not yet written, or an hmult result");
+      if (!lvl[o.b]) return bad("second source slot not yet written");
+      if (lvl[o.b] != la) return bad("the two sources sit at different levels");
     }
     if (o.kind == HML_OP_HMULT) {
-      if (L < 2) return bad("hmult needs L >= 2");
-      if (written[o.dst] && !rp->is_result[o.dst]) return bad("an hmult result needs a slot of its own");
+      if (la < 2) return bad("hmult needs a source level >= 2");
       if (o.dst == o.a || o.dst == o.b) return bad("hmult cannot run in place");
-      rp->is_result[o.dst] = 1;
-    } else if (rp->is_result[o.dst]) {
-      return bad("slot already holds an hmult result");
     }
-    written[o.dst] = 1;
+    rp->op_level.push_back(la);
+    lvl[o.dst] = o.kind == HML_OP_HMULT ? la - 1 : la;
+    // limb-sharded traces stay at one level: the owner of P-limb j is (level + j) % world, so a rank's key slice is level-specific
+    if (sh && la != L) { delete rp; return fail(ctx, HML_ERR_UNSUPPORTED, "limb-sharded traces cannot go on from an hmult result (key slices are per level)"); }
   }
   cudaSetDevice(ctx->device);
   const size_t N = ctx->p.N;
   for (uint32_t i = 1; i < ns; ++i) {
-    if (!written[i]) continue;
-    const size_t words = 2 * (size_t)std::max<uint32_t>(1, rp->is_result[i] ? rp->nk : rp->nq) * N;
+    if (!lvl[i]) continue;
+    const size_t words = 2 * (size_t)std::max<uint32_t>(1, rp->nq) * N;   // sized for the top level: every lower level fits
     if (cudaMalloc((void **)&rp->slot[i], words * 8) != cudaSuccess) {
       for (uint32_t k = 1; k < ns; ++k) cudaFree(rp->slot[k]);
       delete rp;
@@ -125,6 +131,7 @@ extern "C" int hml_replay_bind(hml_replay *rp, const uint64_t *x, const uint64_t
   rp->evk = evk; rp->evk_q_limbs = evk_q_limbs;
   for (const hml_trace_op &o : rp->ops) {
     if ((o.kind == HML_OP_PMULT || o.kind == HML_OP_PADD) && (o.b >= rp->pts.size() || !rp->pts[o.b])) return rfail(rp, HML_ERR_INVALID, "trace uses a plaintext that is not bound");
+    if ((o.kind == HML_OP_HROTATE || o.kind == HML_OP_HMULT) && evk_q_limbs < rp->L) return rfail(rp, HML_ERR_INVALID, "keys must be laid out for at least the trace's top level (evk_q_limbs >= L)");
     if (o.kind == HML_OP_HROTATE && (!rp->key_of_rot.count(o.b) || !rp->keys[rp->key_of_rot[o.b]]) && !(rp->sh && rp->nq == 0 && rp->key_of_rot.count(o.b)))
       return rfail(rp, HML_ERR_INVALID, "trace uses a rotation whose key is not bound");
     if (o.kind == HML_OP_HMULT && !evk && !(rp->sh && rp->nq == 0)) return rfail(rp, HML_ERR_INVALID, "trace has an hmult but no relinearisation key is bound");
@@ -146,11 +153,11 @@ static uint64_t galois_of(const hml_ctx *ctx, uint32_t r) {
 
 static int enqueue(hml_replay *rp, cudaStream_t s) {
   hml_ctx *ctx = rp->ctx;
-  const uint32_t L = rp->L;
   void *st = (void *)s;
   int rc = HML_OK;
   for (size_t i = 0; i < rp->ops.size() && rc == HML_OK; ++i) {
     const hml_trace_op &o = rp->ops[i];
+    const uint32_t L = rp->op_level[i];
     uint64_t *dst = rp->slot[o.dst];
     const uint64_t *a = rp->slot[o.a];
     switch (o.kind) {
@@ -161,7 +168,7 @@ static int enqueue(hml_replay *rp, cudaStream_t s) {
           std::vector<const uint64_t *> keys;
           std::vector<uint64_t> gs;
           std::vector<uint64_t *> outs;
-          while (j < rp->ops.size() && rp->ops[j].kind == HML_OP_HROTATE && rp->ops[j].a == o.a && rp->ops[j].dst != o.a) {
+          while (j < rp->ops.size() && rp->ops[j].kind == HML_OP_HROTATE && rp->ops[j].a == o.a && rp->ops[j].dst != o.a && rp->op_level[j] == L) {
             bool dup = false;
             for (size_t k = i; k < j; ++k) dup |= rp->ops[k].dst == rp->ops[j].dst;
             if (dup) break;
@@ -186,7 +193,7 @@ static int enqueue(hml_replay *rp, cudaStream_t s) {
         // pass d = a * pt + d (hml_pmult_add): the accumulation loops of rotation-heavy traces are made of exactly this pair
         if (i + 1 < rp->ops.size()) {
           const hml_trace_op &n = rp->ops[i + 1];
-          const bool pair = n.kind == HML_OP_HADD && n.dst != o.dst && ((n.a == n.dst && n.b == o.dst) || (n.b == n.dst && n.a == o.dst)) && o.a != n.dst;
+          const bool pair = n.kind == HML_OP_HADD && n.dst != o.dst && rp->op_level[i + 1] == L && ((n.a == n.dst && n.b == o.dst) || (n.b == n.dst && n.a == o.dst)) && o.a != n.dst;
           bool dead = pair;
           for (size_t k = i + 2; k < rp->ops.size() && dead; ++k) {
             const hml_trace_op &q = rp->ops[k];
@@ -237,7 +244,10 @@ extern "C" int hml_replay_run(hml_replay *rp, void *stream) {
     cudaEventRecord(ev, user);
     cudaStreamWaitEvent(rp->cap_stream, ev, 0);
     cudaEventDestroy(ev);
-    if (rp->sh && (rc = hml_shard_prepare(rp->sh, rp->L))) return rc;
+    if (rp->sh) {  // every level the trace runs at: tables, peer offsets, workspace — nothing may allocate during the capture
+      for (uint32_t l : rp->op_level)
+        if ((rc = hml_shard_prepare(rp->sh, l))) return rc;
+    }
     if (!rp->warm) {
       if ((rc = enqueue(rp, rp->cap_stream))) return rc;
       rp->warm = true;
@@ -258,8 +268,21 @@ extern "C" int hml_replay_run(hml_replay *rp, void *stream) {
 }
 
 extern "C" int hml_replay_slot(hml_replay *rp, uint32_t slot, uint64_t **ptr, uint32_t *n_limbs) {
-  if (!rp || slot >= rp->n_slots || !rp->slot[slot]) return HML_ERR_INVALID;
+  if (!rp || slot >= rp->n_slots || !rp->slot[slot] || !rp->final_level[slot]) return HML_ERR_INVALID;
   if (ptr) *ptr = rp->slot[slot];
-  if (n_limbs) *n_limbs = rp->is_result[slot] ? rp->nk : rp->nq;
+  if (n_limbs) {  // limbs per polynomial of the slot's final content (the rank's owned limbs when sharded)
+    uint32_t nq = rp->final_level[slot];
+    if (rp->sh) {
+      int rc = hml_shard_own_limbs(rp->sh, rp->final_level[slot], &nq, nullptr);
+      if (rc) return rc;
+    }
+    *n_limbs = nq;
+  }
+  return HML_OK;
+}
+
+extern "C" int hml_replay_slot_level(hml_replay *rp, uint32_t slot, uint32_t *level) {
+  if (!rp || !level || slot >= rp->n_slots || !rp->final_level[slot]) return HML_ERR_INVALID;
+  *level = rp->final_level[slot];
   return HML_OK;
 }

@@ -287,9 +287,11 @@ int hml_host_free_pinned(hml_ctx *ctx, uint64_t *ptr);
 
 /* ------------------------------------------------------------------ op-sequence replay (BASELINE.json configs[4])
  * The reference runs one operation per process and cannot chain them (reference src/Operation.cpp:636,675,714).  A trace is
- * a list of the CLI's five operations (reference bench_test/bench_micro24.cpp:29-48) over numbered ciphertext slots at ONE
- * level L: slot 0 is the bound input, every other slot is allocated by the replay object; an hmult result (one level lower)
- * is final — it cannot be read by a later op of the trace.  In-place ops (dst == a) are allowed except for hmult.
+ * a list of the CLI's five operations (reference bench_test/bench_micro24.cpp:29-48) over numbered ciphertext slots: slot 0 is
+ * the bound input at level L, every other slot is allocated by the replay object; an hmult result sits one level lower and
+ * later ops go on from there (the two sources of hadd / hmult must be at the same level; keys bound in a layout with
+ * evk_q_limbs >= L serve every level, a plaintext's first limbs serve the lower ones).  In-place ops (dst == a) are allowed
+ * except for hmult.
  *   HROTATE dst = rotate(a, 5^b)   (needs the key bound for rotation amount b)      PMULT / PADD dst = a (*|+) plaintext[b]
  *   HADD    dst = a + slot b                                                     HMULT dst = rescale(relin(a * slot b))
  * flags: HML_REPLAY_GRAPH — the whole sequence is captured once into a CUDA graph (after a warm-up run) and every run is one
@@ -305,7 +307,8 @@ int hml_replay_bind(hml_replay *rp, const uint64_t *x, const uint64_t *const *pl
                     const uint32_t *rot_amounts, const uint64_t *const *rot_keys, uint32_t n_rot_keys, const uint64_t *evk,
                     uint32_t evk_q_limbs);
 int hml_replay_run(hml_replay *rp, void *stream);
-int hml_replay_slot(hml_replay *rp, uint32_t slot, uint64_t **ptr, uint32_t *n_limbs);   /* n_limbs per polynomial */
+int hml_replay_slot(hml_replay *rp, uint32_t slot, uint64_t **ptr, uint32_t *n_limbs);   /* n_limbs per polynomial (final content) */
+int hml_replay_slot_level(hml_replay *rp, uint32_t slot, uint32_t *level);                /* level of the slot after the trace */
 int hml_replay_destroy(hml_replay *rp);
 
 /* ------------------------------------------------------------------ the count contract

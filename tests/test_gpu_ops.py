@@ -170,9 +170,11 @@ def test_op_objects_mirror_reference_constructor(north_star):
 
 
 def _oracle_replay(o, L, trace, x, pts, keys, evk, hoist=False):
-    """the same trace on the oracle; hoist=True groups consecutive rotations of one source exactly as hml_replay does"""
+    """the same trace on the oracle (keys laid out for level L; a slot's level is its limb count); hoist=True groups
+    consecutive rotations of one source exactly as hml_replay does"""
     N = o.N
     h = {"x": x}
+    lv = lambda name: h[name].shape[1]  # noqa: E731
     i = 0
     while i < len(trace):
         op = trace[i]
@@ -183,22 +185,50 @@ def _oracle_replay(o, L, trace, x, pts, keys, evk, hoist=False):
                         and trace[j][1] not in [t[1] for t in trace[i:j]]:
                     j += 1
             if j - i >= 2:
-                outs = o.hrotate_hoisted(L, h[op[2]], [keys[t[3]] for t in trace[i:j]], L, [pow(5, t[3], 2 * N) for t in trace[i:j]])
+                outs = o.hrotate_hoisted(lv(op[2]), h[op[2]], [keys[t[3]] for t in trace[i:j]], L, [pow(5, t[3], 2 * N) for t in trace[i:j]])
                 for t, out in zip(trace[i:j], outs):
                     h[t[1]] = out
                 i = j
                 continue
-            h[op[1]] = o.hrotate(L, h[op[2]], keys[op[3]], L, pow(5, op[3], 2 * N))
+            h[op[1]] = o.hrotate(lv(op[2]), h[op[2]], keys[op[3]], L, pow(5, op[3], 2 * N))
         elif op[0] == "pmult":
-            h[op[1]] = o.pmult(L, h[op[2]], pts[op[3]])
+            h[op[1]] = o.pmult(lv(op[2]), h[op[2]], np.ascontiguousarray(pts[op[3]][:lv(op[2])]))
         elif op[0] == "padd":
-            h[op[1]] = o.padd(L, h[op[2]], pts[op[3]])
+            h[op[1]] = o.padd(lv(op[2]), h[op[2]], np.ascontiguousarray(pts[op[3]][:lv(op[2])]))
         elif op[0] == "hadd":
-            h[op[1]] = o.hadd(L, h[op[2]], h[op[3]])
+            h[op[1]] = o.hadd(lv(op[2]), h[op[2]], h[op[3]])
         elif op[0] == "hmult":
-            h[op[1]] = o.hmult(L, h[op[2]], h[op[3]], evk, L)
+            h[op[1]] = o.hmult(lv(op[2]), h[op[2]], h[op[3]], evk, L)
         i += 1
     return h
+
+
+def test_replay_across_levels():
+    """a trace that goes on from hmult results: two chained multiplications with rotations, plaintext ops and additions at
+    the lower levels (keys laid out for the top level serve every level; a plaintext's first limbs serve the lower ones)"""
+    N, ML, A, L = 8192, 7, 3, 7
+    ctx, o = hml.Context(N=N, max_level=ML, alpha=A), Oracle(N, 36, ML, A)
+    Oracle.set_threads(0)
+    beta = -(-L // A)
+    trace = [("hrotate", "a", "x", 1), ("hmult", "b", "a", "x"),          # b at L-1
+             ("hrotate", "c", "b", 2), ("pmult", "d", "c", 0), ("hadd", "e", "d", "b"), ("padd", "e", "e", 1),
+             ("hmult", "f", "e", "b"),                                    # f at L-2
+             ("hrotate", "g", "f", 1), ("hrotate", "h", "f", 2), ("hadd", "g", "g", "h")]
+    x = uniform_limbs(o.moduli[:L], N, 1, lead=(2,))
+    pts = {i: uniform_limbs(o.moduli[:L], N, 100 + i) for i in range(2)}
+    keys = {r: uniform_limbs(o.moduli[:L] + o.moduli[ML:], N, 200 + r, lead=(beta, 2)) for r in (1, 2)}
+    evk = uniform_limbs(o.moduli[:L] + o.moduli[ML:], N, 300, lead=(beta, 2))
+    dx, dp, dk, de = to_dev(x), {k: to_dev(v) for k, v in pts.items()}, {k: to_dev(v) for k, v in keys.items()}, to_dev(evk)
+    for graph, hoist in ((False, False), (True, False), (True, True)):
+        want = _oracle_replay(o, L, trace, x, pts, keys, evk, hoist=hoist)
+        rp = hml.Replay(ctx, L, trace, graph=graph, hoist=hoist).bind(dx, dp, dk, de)
+        for _ in range(2):
+            rp.run()
+        for name in ("b", "e", "f", "g"):
+            got = to_host(rp.result(name))
+            assert got.shape == want[name].shape and np.array_equal(got, want[name]), (name, graph, hoist)
+        rp.close()
+    Oracle.set_threads(1)
 
 
 @pytest.mark.parametrize("N,ML,A,L,shape", [(2048, 6, 2, 5, "bsgs"), (8192, 6, 2, 5, "bsgs"), (8192, 7, 3, 7, "rotsum")])
@@ -235,7 +265,7 @@ def test_op_sequence_replay_matches_oracle(N, ML, A, L, shape):
 
 def test_replay_rejects_malformed_traces():
     ctx = hml.Context(N=1024, max_level=4, alpha=2)
-    for bad in ([("hadd", "y", "nope", "x")], [("hmult", "z", "x", "x"), ("hadd", "w", "z", "x")], [("hmult", "x2", "x", "x"), ("pmult", "x2", "x", 0)]):
+    for bad in ([("hadd", "y", "nope", "x")], [("hmult", "z", "x", "x"), ("hadd", "w", "z", "x")], [("hmult", "x2", "x", "x"), ("hmult", "x2", "x2", "x2")]):
         with pytest.raises((hml.HmlError, ValueError)):
             hml.Replay(ctx, 3, bad)
     rp = hml.Replay(ctx, 3, [("hrotate", "a", "x", 1)])
