@@ -439,7 +439,12 @@ def main():
     except Exception:
         pass
 
-    extra = {"hrotate_batched_us": hrot_batched_us, "hmult_batched_us": us_per_op, "throughput_hmult_per_s": n_ops / (ms_total * 1e-3), "ntt_limbs_per_s": ntt_limbs_per_s, "ntt_us_per_limb": ntt_ms * 1e3 / (n_limbs * n_b),
+    # the FP64 butterfly's issue floor (8 DP instructions per butterfly, each holding the issue port for two cycles):
+    # 524288 butterflies x 16 cycles / (592 sub-partitions x 32 lanes) per limb at the clock sampled during the run
+    clk = sampler.summary().get("sm_mhz") or 1965
+    fp64_floor_us = 524288 * 16 / (4 * 148 * 32) / clk
+    extra = {"hrotate_batched_us": hrot_batched_us, "hmult_batched_us": us_per_op, "throughput_hmult_per_s": n_ops / (ms_total * 1e-3),
+             "ntt_fp64_issue_floor_us_per_limb": fp64_floor_us, "ntt_frac_of_fp64_issue_floor": fp64_floor_us / (ntt_ms * 1e3 / (n_limbs * n_b)), "ntt_limbs_per_s": ntt_limbs_per_s, "ntt_us_per_limb": ntt_ms * 1e3 / (n_limbs * n_b),
              "ntt_us_per_limb_single_ciphertext_launch": ntt1_us_per_limb, "e2e_matches_device_path": e2e_ok,
              "e2e_packed_host_format": {"value": e2e_packed_us, "unit": "us", "h2d_bytes_per_step": 2 * 2 * L * 5 * N_RING * Be,
                                         "d2h_bytes_per_step": 2 * (L - 1) * 5 * N_RING * Be, "matches_u64_path": e2e_packed_ok,
