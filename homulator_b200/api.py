@@ -226,7 +226,7 @@ def algorithmic_words(op, L, alpha):
 
 
 def _ptr(t):
-    if t is None:
+    if t is None or t.numel() == 0:
         return None
     if not t.is_cuda or not t.is_contiguous() or t.element_size() != 8:
         raise ValueError("expected a contiguous 64-bit CUDA tensor")

@@ -1722,6 +1722,7 @@ extern "C" int hml_hrotate_hoisted(hml_ctx *ctx, uint32_t L, const uint64_t *ct,
                                    uint32_t evk_q_limbs, const uint64_t *galois_elts, uint64_t *const *ct_outs, void *stream) {
   int rc = check_level(ctx, L, 1);
   if (rc) return rc;
+  if (n_rot == 0) return HML_OK;
   if (!ct || !rotkeys || !galois_elts || !ct_outs) return fail(ctx, HML_ERR_INVALID, "null buffer");
   for (uint32_t r = 0; r < n_rot; ++r) {
     if (!rotkeys[r] || !ct_outs[r] || ct_outs[r] == ct) return fail(ctx, HML_ERR_INVALID, "null key / output, or an output aliasing the input");
@@ -1831,8 +1832,8 @@ extern "C" int hml_hmult_batch(hml_ctx *ctx, uint32_t L, uint32_t n, const uint6
                                const uint64_t *evk, uint32_t evk_q_limbs, uint64_t *ct_out, void *stream) {
   int rc = check_level(ctx, L, 2);
   if (rc) return rc;
+  if (n == 0) return HML_OK;  // an empty batch is a no-op whatever the pointers are
   if (!ct_a || !ct_b || !evk || !ct_out) return fail(ctx, HML_ERR_INVALID, "null buffer");
-  if (n == 0) return HML_OK;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   const size_t N = ctx->p.N, in_w = 2 * N * L, out_w = 2 * N * (L - 1);
   return run_batch_lanes(ctx, n, hmult_ws_words(ctx->p, L, 1), (cudaStream_t)stream, [&](uint32_t i, uint32_t nb, u64 *ws, cudaStream_t s) {
@@ -1845,9 +1846,9 @@ extern "C" int hml_hrotate_batch(hml_ctx *ctx, uint32_t L, uint32_t n, const uin
                                  uint32_t evk_q_limbs, uint64_t galois_elt, uint64_t *ct_out, void *stream) {
   int rc = check_level(ctx, L, 1);
   if (rc) return rc;
+  if (n == 0) return HML_OK;
   if (!ct || !rotkey || !ct_out) return fail(ctx, HML_ERR_INVALID, "null buffer");
   if (!(galois_elt & 1)) return fail(ctx, HML_ERR_INVALID, "galois element must be odd");
-  if (n == 0) return HML_OK;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   const size_t w = 2 * (size_t)ctx->p.N * L;
   return run_batch_lanes(ctx, n, hrot_ws_words(ctx->p, L, 1), (cudaStream_t)stream, [&](uint32_t i, uint32_t nb, u64 *ws, cudaStream_t s) {

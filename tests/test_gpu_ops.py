@@ -492,3 +492,35 @@ def test_host_buffer_paths_words_and_packed(north_star):
     rp = torch.empty(n * 2 * L * 5 * N, dtype=torch.uint8).pin_memory()
     ctx.hrotate_host_packed(L, n, ap, K, rp, 5)
     assert torch.equal(ctx.unpack_host(rp, ah.shape)[[0, 7, 8, 10]], want_r)
+
+
+@pytest.mark.parametrize("L", [45, 31, 16, 2])
+def test_north_star_ring_other_levels(north_star, L):
+    """config_4.cfg's ring at the maximum level (45 = three full digits), at ragged digit shapes (31 = 15 + 15 + 1,
+    16 = 15 + 1) and below one digit (2): hmult (merged ModDown + Rescale, fused inner product), hrotate, and the batched
+    schedule (stand-alone inner product) against the oracle."""
+    ctx, o, a, b, _ = north_star
+    N = 65536
+    beta = -(-L // 15)
+    full = [uniform_limbs(o.moduli[:L], N, 1800 + k, lead=(2,)) for k in range(2)] if L > 35 else None
+    aL = full[0] if full else np.ascontiguousarray(a[:, :L])
+    bL = full[1] if full else np.ascontiguousarray(b[:, :L])
+    evk = uniform_limbs(o.moduli[:L] + o.moduli[45:], N, 1810 + L, lead=(beta, 2))
+    K = to_dev(evk)
+    want_m, want_r = o.hmult(L, aL, bL, evk, L), o.hrotate(L, aL, evk, L, 5)
+    assert np.array_equal(to_host(ctx.hmult(L, to_dev(aL), to_dev(bL), K)), want_m)
+    assert np.array_equal(to_host(ctx.hrotate(L, to_dev(aL), K, 5)), want_r)
+    A2, B2 = torch.stack([to_dev(aL), to_dev(bL)]), torch.stack([to_dev(bL), to_dev(bL)])
+    got = ctx.hmult_batch(L, A2, B2, K)
+    assert np.array_equal(to_host(got[0]), want_m)
+    rot = ctx.hrotate_batch(L, A2, K, 5)
+    assert np.array_equal(to_host(rot[0]), want_r)
+
+
+def test_empty_batches_and_zero_rotations_are_no_ops(north_star):
+    ctx, o, a, b, evk = north_star
+    K = to_dev(evk)
+    empty = ctx.empty(0, 2, 35, 65536)
+    assert ctx.hmult_batch(35, empty, empty, K).shape[0] == 0
+    assert ctx.hrotate_batch(35, empty, K, 5).shape[0] == 0
+    assert ctx.hrotate_hoisted(35, to_dev(a), [], []) == []
