@@ -284,6 +284,16 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; homulator_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    # run this rank's host threads on the CPUs next to its GPU before any pinned buffer is allocated (first touch): with several
+    # ranks per box the host-buffer path is bound by the host's memory and PCIe paths, and remote-socket staging halves it
+    numa = "unset"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        numa = "nvml ideal cpus (%d)" % len(os.sched_getaffinity(0))
+    except Exception as e:  # not fatal: the run proceeds with the inherited affinity
+        numa = "unchanged (%s)" % type(e).__name__
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -519,7 +529,7 @@ def main():
         "dtype": "u64 residues (36-bit), arithmetic on the FP64 pipe", "data": "synthetic",
         "config": bench_config(world) if args.batch <= 0 else dict(bench_config(world), batch_per_gpu_per_step=B, ciphertexts_per_step=B * world),
         "e2e": {"value": e2e_us, "unit": "us", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
-                "batch_per_gpu_per_step": Be},
+                "batch_per_gpu_per_step": Be, "host_cpu_affinity": numa},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "kernel": "ntt_fwd_cols + ntt_rows (forward NTT pair, 32 ciphertexts x 115 limbs per launch)", "achieved": ntt_gbs,
