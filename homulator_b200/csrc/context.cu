@@ -188,13 +188,16 @@ static int ctx_init_device(hml_ctx *ctx) {
   ctx->tabs.fwd = ctx->tw_fwd; ctx->tabs.inv = ctx->tw_inv; ctx->tabs.mc = ctx->mc;
   if (two_pass) {  // queue + dependency counters of the single-launch transform, one block per stream lane
     const size_t words = ntt_fused_ctrl_words();
-    CU_TRY(ctx, cudaMalloc((void **)&ctx->ntt_ctrl, 2 * words * sizeof(unsigned)));
-    CU_TRY(ctx, cudaMemset(ctx->ntt_ctrl, 0, 2 * words * sizeof(unsigned)));
+    CU_TRY(ctx, cudaMalloc((void **)&ctx->ntt_ctrl, (2 * words + 8) * sizeof(unsigned)));
+    CU_TRY(ctx, cudaMemset(ctx->ntt_ctrl, 0, (2 * words + 8) * sizeof(unsigned)));
     ctx->tabs.fused_ctrl = ctx->ntt_ctrl;
+    ctx->tabs.col_ctr = ctx->ntt_ctrl + 2 * words;
     ctx->tabs_lane = ctx->tabs;
     ctx->tabs_lane.fused_ctrl = ctx->ntt_ctrl + words;
+    ctx->tabs_lane.col_ctr = ctx->ntt_ctrl + 2 * words + 4;
   } else {
     ctx->tabs.fused_ctrl = nullptr;
+    ctx->tabs.col_ctr = nullptr;
     ctx->tabs_lane = ctx->tabs;
   }
   return HML_OK;

@@ -84,23 +84,89 @@ __device__ __forceinline__ void col_issue(const ColWork &w, const double *tw_tab
   }
 }
 
-template <int LOGR1, int NT, bool IN_F64>
-__global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_fwd_cols(NttTables t, int logN, LimbMap lm, NttLaunch l, int total) {
+// ---- dynamic tile queue.  Measured with ncu (profiles/r2/ncu_hmult_batch32_r2.txt): with a static split (item i, i + grid, ...)
+// the three persistent CTAs of an SM do not finish together — the warp scheduler favours the older CTA, which runs out of
+// tiles early and leaves its slot empty (achieved occupancy 4.5 of 6 warps per scheduler, FP64 pipe 60 % busy).  With a queue
+// (one atomic counter per launch, popped by thread 0 one tile ahead of its use) every CTA works until the launch is drained.
+// Items are enumerated without the skipped (digit-owned) polys: tile fastest, then the (limb, poly) pairs of a ciphertext —
+// the n_skip leading limbs of the launch have n_polys - 1 members, the others n_polys — then the ciphertexts.
+struct ColSlot {
+  const u64 *in;
+  u64 *out;
+  int mi, limb, tile, valid;
+};
+struct ColQueue {
+  unsigned *ctr;   // [0] next item, [1] CTAs done (the last one zeroes both: the counters are ready for the next launch)
+  int n_skip, pairs;
+};
+template <int LOGR1, int NT>
+__device__ __forceinline__ void col_decode(unsigned wi, int total, const ColQueue &qu, const LimbMap &lm, const NttLaunch &l, bool in_is_out,
+                                           ColSlot &s) {
+  using K = ColCfg<LOGR1, NT>;
+  s.valid = wi < (unsigned)total;
+  if (!s.valid) return;
+  const int tile = wi % K::TILES, r = wi / K::TILES, batch = r / qu.pairs;
+  int rr = r - batch * qu.pairs, limb, poly;
+  const int own_members = qu.n_skip * (l.n_polys - 1);
+  if (rr < own_members) {
+    limb = rr / (l.n_polys - 1); poly = rr - limb * (l.n_polys - 1);
+    poly += poly >= lm.skip[limb];
+  } else {
+    rr -= own_members;
+    limb = qu.n_skip + rr / l.n_polys; poly = rr % l.n_polys;
+  }
+  const long long slot = lm.pos[limb];
+  s.out = l.out + (long long)batch * l.out_batch_stride + (long long)poly * l.out_poly_stride + slot * l.out_limb_stride + tile * K::C;
+  s.in = in_is_out ? s.out : l.in + (long long)batch * l.in_batch_stride + (long long)poly * l.in_poly_stride + slot * l.in_limb_stride + tile * K::C;
+  s.mi = lm.mod[limb]; s.limb = limb; s.tile = tile;
+}
+__device__ __forceinline__ ColWork col_take(const ColSlot &s) {
+  ColWork w;
+  w.in = s.in; w.out = s.out; w.mi = s.mi; w.limb = s.limb; w.tile = s.tile;
+  return w;
+}
+__device__ __forceinline__ void col_queue_exit(const ColQueue &qu) {
+  if (threadIdx.x == 0 && atomicAdd(qu.ctr + 1, 1u) == gridDim.x - 1) { qu.ctr[0] = 0; qu.ctr[1] = 0; __threadfence(); }
+}
+
+template <int LOGR1, int NT, bool IN_F64, bool DYN>
+__global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_fwd_cols(NttTables t, int logN, LimbMap lm, NttLaunch l, int total, ColQueue qu) {
   using K = ColCfg<LOGR1, NT>;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, c = tid % K::C, u = tid / K::C;
   const unsigned smem0 = smem_u32(smem);
+  __shared__ ColSlot slot[2];
   ColWork cur, nxt;
-  ColPos pos = col_pos(blockIdx.x < total ? blockIdx.x : 0, K::TILES, l.n_limbs, l.n_polys);
-  const ColPos step = col_pos(gridDim.x, K::TILES, l.n_limbs, l.n_polys);
-  pdl_wait();
-  bool have = blockIdx.x < total && col_next<LOGR1, NT>(pos, step, true, lm, l, false, cur);
+  ColPos pos, step;
+  unsigned pend = 0;
+  bool have;
+  if constexpr (DYN) {
+    // the first items are static (CTA b takes items b and b + grid: no queue round trip before the first loads); the queue hands out the rest
+    ColSlot first;
+    col_decode<LOGR1, NT>(blockIdx.x, total, qu, lm, l, false, first);
+    have = first.valid;
+    cur = col_take(first);
+    pdl_wait();
+    pend = blockIdx.x + gridDim.x;  // the second item is static too: the first pop of every CTA (a burst on one address when the
+                                    // launch starts) then has a whole tile's time to return
+  } else {
+    pos = col_pos(blockIdx.x < total ? blockIdx.x : 0, K::TILES, l.n_limbs, l.n_polys);
+    step = col_pos(gridDim.x, K::TILES, l.n_limbs, l.n_polys);
+    pdl_wait();
+    have = blockIdx.x < total && col_next<LOGR1, NT>(pos, step, true, lm, l, false, cur);
+  }
   if (have) col_issue<LOGR1, NT>(cur, t.fwd, t.mc, nullptr, logN, smem0);
   cp_async_commit();
   for (int it = 0; have; ++it) {
-    const bool have_next = col_next<LOGR1, NT>(pos, step, false, lm, l, false, nxt);
+    bool have_next;
+    if constexpr (DYN) {
+      if (tid == 0) col_decode<LOGR1, NT>(pend, total, qu, lm, l, false, slot[(it + 1) & 1]);  // the item popped during the previous tile
+    } else {
+      have_next = col_next<LOGR1, NT>(pos, step, false, lm, l, false, nxt);
+    }
     cp_async_wait<0>();
     __syncthreads();  // tile `it` has landed for every thread; everybody is done with the other stage
+    if constexpr (DYN) { have_next = slot[(it + 1) & 1].valid; nxt = col_take(slot[(it + 1) & 1]); }
     if (have_next) col_issue<LOGR1, NT>(nxt, t.fwd, t.mc, nullptr, logN, smem0 + ((it + 1) & 1) * K::STAGE_BYTES);
     cp_async_commit();
     double *data = reinterpret_cast<double *>(smem + (it & 1) * K::STAGE_BYTES);
@@ -120,6 +186,9 @@ __global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_fwd_col
 #pragma unroll
     for (int j = 0; j < 16; ++j) data[tid + NT * j] = a[j];
     __syncthreads();
+    // pop the tile after the next one half a tile before its loads are issued: late enough that the CTAs the scheduler
+    // favours get there first (they are the ones that will have time for it), early enough to hide the round trip
+    if constexpr (DYN) { if (tid == 0 && have_next) pend = 2 * gridDim.x + atomicAdd(qu.ctr, 1u); }
 #pragma unroll
     for (int j = 0; j < 16; ++j) a[j] = data[(16 * u + j) * K::C + c];
     if constexpr (K::SKIP <= 0) { lds_run<1>(w, tw + (1 << (LOGR1 - 4)) + u); ct_level<0>(a, w, q, qinv); }
@@ -131,26 +200,48 @@ __global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_fwd_col
     for (int j = 0; j < 16; ++j) outd[(size_t)(16 * u + j) << NTT_ROW_LOG] = a[j];
     have = have_next; cur = nxt;
   }
+  if constexpr (DYN) col_queue_exit(qu);
 }
 
 // inverse, second pass: raw doubles in `out` -> canonical words, post-scale folded into the N^-1 multiply
-template <int LOGR1, int NT>
-__global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_inv_cols(NttTables t, int logN, LimbMap lm, NttLaunch l, int total) {
+template <int LOGR1, int NT, bool DYN>
+__global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_inv_cols(NttTables t, int logN, LimbMap lm, NttLaunch l, int total, ColQueue qu) {
   using K = ColCfg<LOGR1, NT>;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, c = tid % K::C, u = tid / K::C;
   const unsigned smem0 = smem_u32(smem);
+  __shared__ ColSlot slot[2];
   ColWork cur, nxt;
-  ColPos pos = col_pos(blockIdx.x < total ? blockIdx.x : 0, K::TILES, l.n_limbs, l.n_polys);
-  const ColPos step = col_pos(gridDim.x, K::TILES, l.n_limbs, l.n_polys);
-  pdl_wait();
-  bool have = blockIdx.x < total && col_next<LOGR1, NT>(pos, step, true, lm, l, true, cur);
+  ColPos pos, step;
+  unsigned pend = 0;
+  bool have;
+  if constexpr (DYN) {
+    // the first items are static (CTA b takes items b and b + grid: no queue round trip before the first loads); the queue hands out the rest
+    ColSlot first;
+    col_decode<LOGR1, NT>(blockIdx.x, total, qu, lm, l, true, first);
+    have = first.valid;
+    cur = col_take(first);
+    pdl_wait();
+    pend = blockIdx.x + gridDim.x;  // the second item is static too: the first pop of every CTA (a burst on one address when the
+                                    // launch starts) then has a whole tile's time to return
+  } else {
+    pos = col_pos(blockIdx.x < total ? blockIdx.x : 0, K::TILES, l.n_limbs, l.n_polys);
+    step = col_pos(gridDim.x, K::TILES, l.n_limbs, l.n_polys);
+    pdl_wait();
+    have = blockIdx.x < total && col_next<LOGR1, NT>(pos, step, true, lm, l, true, cur);
+  }
   if (have) col_issue<LOGR1, NT>(cur, t.inv, t.mc, l.post_scale, logN, smem0);
   cp_async_commit();
   for (int it = 0; have; ++it) {
-    const bool have_next = col_next<LOGR1, NT>(pos, step, false, lm, l, true, nxt);
+    bool have_next;
+    if constexpr (DYN) {
+      if (tid == 0) col_decode<LOGR1, NT>(pend, total, qu, lm, l, true, slot[(it + 1) & 1]);  // the item popped during the previous tile
+    } else {
+      have_next = col_next<LOGR1, NT>(pos, step, false, lm, l, true, nxt);
+    }
     cp_async_wait<0>();
     __syncthreads();  // tile `it` has landed for every thread; everybody is done with the other stage
+    if constexpr (DYN) { have_next = slot[(it + 1) & 1].valid; nxt = col_take(slot[(it + 1) & 1]); }
     if (have_next) col_issue<LOGR1, NT>(nxt, t.inv, t.mc, l.post_scale, logN, smem0 + ((it + 1) & 1) * K::STAGE_BYTES);
     cp_async_commit();
     double *data = reinterpret_cast<double *>(smem + (it & 1) * K::STAGE_BYTES);
@@ -167,6 +258,7 @@ __global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_inv_col
 #pragma unroll
     for (int j = 0; j < 16; ++j) data[(16 * u + j) * K::C + c] = a[j];
     __syncthreads();
+    if constexpr (DYN) { if (tid == 0 && have_next) pend = 2 * gridDim.x + atomicAdd(qu.ctr, 1u); }  // see ntt_fwd_cols
 #pragma unroll
     for (int j = 0; j < 16; ++j) a[j] = data[tid + NT * j];
     lds_run<8>(w, tw + 8); gs_level<3>(a, w, q, qinv);
@@ -187,6 +279,7 @@ __global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_inv_col
     }
     have = have_next; cur = nxt;
   }
+  if constexpr (DYN) col_queue_exit(qu);
 }
 
 // ================================================================================ row passes
@@ -633,21 +726,52 @@ static int row_split(int n_items, int ctas_xy) {
   return z < 1 ? 1 : z;
 }
 
+static int col_dynamic_env() {
+  static const int v = [] {
+    const char *e = getenv("HML_COL_DYN");  // 0: static split of the column-pass tiles over the persistent CTAs (round-1 schedule)
+    return e ? atoi(e) : 1;
+  }();
+  return v;
+}
+
 template <int LOGR1, int NT>
 static void launch_cols_t(bool inverse, const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, cudaStream_t s) {
   using K = ColCfg<LOGR1, NT>;
-  const int total = l.n_limbs * l.n_polys * l.n_batch * K::TILES;
   const int resident = K::MIN_CTAS * sm_count();
-  const int grid = total < resident ? total : resident;
   static PerDeviceOnce once;
   if (once.first()) {
-    allow_smem(ntt_fwd_cols<LOGR1, NT, false>, 2 * K::STAGE_BYTES);
-    allow_smem(ntt_fwd_cols<LOGR1, NT, true>, 2 * K::STAGE_BYTES);
-    allow_smem(ntt_inv_cols<LOGR1, NT>, 2 * K::STAGE_BYTES);
+    allow_smem(ntt_fwd_cols<LOGR1, NT, false, false>, 2 * K::STAGE_BYTES);
+    allow_smem(ntt_fwd_cols<LOGR1, NT, true, false>, 2 * K::STAGE_BYTES);
+    allow_smem(ntt_inv_cols<LOGR1, NT, false>, 2 * K::STAGE_BYTES);
+    allow_smem(ntt_fwd_cols<LOGR1, NT, false, true>, 2 * K::STAGE_BYTES);
+    allow_smem(ntt_fwd_cols<LOGR1, NT, true, true>, 2 * K::STAGE_BYTES);
+    allow_smem(ntt_inv_cols<LOGR1, NT, true>, 2 * K::STAGE_BYTES);
   }
-  if (inverse) launch_pdl(ntt_inv_cols<LOGR1, NT>, grid, NT, 2 * K::STAGE_BYTES, s, t, logN, lm, l, total);
-  else if (l.in_f64) launch_pdl(ntt_fwd_cols<LOGR1, NT, true>, grid, NT, 2 * K::STAGE_BYTES, s, t, logN, lm, l, total);
-  else launch_pdl(ntt_fwd_cols<LOGR1, NT, false>, grid, NT, 2 * K::STAGE_BYTES, s, t, logN, lm, l, total);
+  // the queue enumerates the members of the launch without the skipped ones: the limbs that skip a poly must come first
+  ColQueue qu{t.col_ctr, 0, 0};
+  bool dyn = t.col_ctr != nullptr && col_dynamic_env();
+  for (int i = 0; i < l.n_limbs; ++i) {
+    const bool sk = lm.skip[i] < l.n_polys;
+    if (sk && i != qu.n_skip) dyn = false;
+    qu.n_skip += sk;
+  }
+  qu.pairs = qu.n_skip * (l.n_polys - 1) + (l.n_limbs - qu.n_skip) * l.n_polys;
+  if (qu.pairs <= 0) return;
+  const long long total64 = (long long)qu.pairs * l.n_batch * K::TILES;
+  // (with at most two tiles per CTA there is nothing to hand out)
+  const long long min_tiles = 2;
+  if (dyn && total64 > min_tiles * resident && total64 <= 0x3FFFFFFF) {
+    const int total = (int)total64, grid = resident;
+    if (inverse) launch_pdl(ntt_inv_cols<LOGR1, NT, true>, grid, NT, 2 * K::STAGE_BYTES, s, t, logN, lm, l, total, qu);
+    else if (l.in_f64) launch_pdl(ntt_fwd_cols<LOGR1, NT, true, true>, grid, NT, 2 * K::STAGE_BYTES, s, t, logN, lm, l, total, qu);
+    else launch_pdl(ntt_fwd_cols<LOGR1, NT, false, true>, grid, NT, 2 * K::STAGE_BYTES, s, t, logN, lm, l, total, qu);
+    return;
+  }
+  const int total = l.n_limbs * l.n_polys * l.n_batch * K::TILES;
+  const int grid = total < resident ? total : resident;
+  if (inverse) launch_pdl(ntt_inv_cols<LOGR1, NT, false>, grid, NT, 2 * K::STAGE_BYTES, s, t, logN, lm, l, total, qu);
+  else if (l.in_f64) launch_pdl(ntt_fwd_cols<LOGR1, NT, true, false>, grid, NT, 2 * K::STAGE_BYTES, s, t, logN, lm, l, total, qu);
+  else launch_pdl(ntt_fwd_cols<LOGR1, NT, false, false>, grid, NT, 2 * K::STAGE_BYTES, s, t, logN, lm, l, total, qu);
 }
 
 static int col_threads_env() {

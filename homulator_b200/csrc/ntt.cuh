@@ -45,6 +45,8 @@ struct NttTables {
   // queue and dependency counters of the single-launch transform (ntt_fused.cu), ntt_fused_ctrl_words() zero-initialised words;
   // null: two-kernel transforms.  Launches that may run CONCURRENTLY need distinct blocks.
   unsigned *fused_ctrl;
+  // tile queue of the column passes (ntt.cu, ColQueue): two zero-initialised words, same concurrency rule; null: static split
+  unsigned *col_ctr;
 };
 
 // Host: permute one modulus' natural table (N entries) into the row-pass layout.  Per 16-row tile (rows r = 16 *
