@@ -443,6 +443,15 @@ def main():
     bconv_ms = e0.elapsed_time(e1) / reps
     bconv_bytes = float(ALPHA + L) * W_bytes * n_bc
     del xb, ob
+    # the same kernel as it runs INSIDE the op (hml_profile_*: an event after every launch group of one 32-ciphertext chunk):
+    # no step-1 multiply in the packer (the INTT folds it), doubles out (the forward transform's input format).  Bytes per
+    # ciphertext: ModUp L -> beta (L + alpha) - L limbs, ModDown 2 x (alpha (+ the folded source row) -> L - 1)
+    nbp = min(32, B)
+    prof = ctx.profile(lambda: ctx.hmult_batch(L, ct_a[:nbp], ct_b[:nbp], evk, out=out[:nbp]))
+    beta = ctx.beta(L)
+    conv_limbs = (L + (beta * (L + ALPHA) - L)) + 2 * ((ALPHA + 1) + (L - 1))
+    inop_bytes = float(conv_limbs) * W_bytes * nbp
+    inop_us = prof["us"]["BCONV"]
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ntt_traffic.json")))["dram_bytes_per_launch"]
@@ -462,7 +471,13 @@ def main():
              "bconv_tcgen05": {"kernel": "k_bconv_umma (tcgen05.mma kind::i8, 64 polynomials x 15 -> 35 limbs per launch)",
                                "us_per_launch": bconv_ms * 1e3, "algorithmic_bytes_per_launch": bconv_bytes,
                                "achieved_gbs": bconv_bytes / (bconv_ms * 1e-3) / 1e9, "hbm_frac": bconv_bytes / (bconv_ms * 1e-3) / 1e9 / peak,
-                               "limb_macs_per_s": ALPHA * L * n_bc / (bconv_ms * 1e-3)}}
+                               "limb_macs_per_s": ALPHA * L * n_bc / (bconv_ms * 1e-3),
+                               "in_op": {"what": "the two conversion launches of one %d-ciphertext hmult chunk (ModUp 35 -> 115 limbs, "
+                                                 "ModDown 2 x (15 + folded row -> 34)), doubles out, event-timed inside the op" % nbp,
+                                         "us_per_chunk": inop_us, "algorithmic_bytes_per_chunk": inop_bytes,
+                                         "achieved_gbs": inop_bytes / (inop_us * 1e-6) / 1e9,
+                                         "hbm_frac": inop_bytes / (inop_us * 1e-6) / 1e9 / peak}},
+             "hmult_chunk_class_us": dict(prof["us"], total=prof["total_us"], ciphertexts=nbp)}
     if not args.no_extra:
         flush = torch.empty(64 << 20, dtype=torch.int64, device="cuda")  # 512 MiB
 

@@ -637,7 +637,7 @@ bool ks_uses_hpip(const hml_ctx *ctx, uint32_t L, uint32_t nb) {
   return hpip_enabled() && ctx->p.logN > NTT_SMALL_LOG && ctx->p.beta(L) >= 2 && (nb == 1 || mode == 2);
 }
 
-int ks_modup(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d, u64 *yb, u64 *ext, cudaStream_t s, const NttMac *mac) {
+int ks_modup(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d, u64 *yb, u64 *ext, cudaStream_t s, const NttMac *mac, const KsAuto *au) {
   const Params &p = ctx->p;
   const size_t N = p.N;
   const uint32_t A = p.alpha, E = L + A, beta = lc->beta;
@@ -647,6 +647,13 @@ int ks_modup(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d,
     NttLaunch l{};
     l.in = d.ptr; l.out = yb; l.in_limb_stride = l.out_limb_stride = N; l.n_limbs = L; l.n_polys = 1; l.post_scale = lc->modup_scale;
     l.n_batch = nb; l.in_batch_stride = d.stride; l.out_batch_stride = (long long)L * N;
+    if (au) {  // hrotate: d = sigma_g(raw input), permuted while the row pass loads it; sigma_g(d) is kept for K5's own-digit term
+      unsigned gi = 1;
+      const unsigned g8 = (unsigned)(au->g & 255);
+      for (int i = 0; i < 7; ++i) gi = gi * (2u - g8 * gi);  // Newton: g^-1 mod 256 (g odd)
+      l.in_galois = (unsigned)(au->g & (2ull * N - 1)); l.in_ginv8 = gi & 255u;
+      l.side_out = au->sigma_d; l.side_batch_stride = au->sigma_stride;
+    }
     launch_ntt_inverse(tabs_for(ctx, s), logN, lc->q_lm, l, s);
     prof_mark(ctx, HML_CLS_INTT, s);
     ctx->exec.intt_limbs += (uint64_t)nb * L; ctx->exec.kernel_launches += npass;
@@ -760,11 +767,13 @@ int ks_inner(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d,
 // Two-pass rings with at least two digits fuse the inner product into the ModUp transform (NttMac): the Q-limb accumulators are
 // then 8-byte words (not packed limbs); ks_uses_hpip() tells the consumers.
 int ks_front(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d, const u64 *evk, uint32_t evk_q_limbs, u64 *yb,
-             u64 *ext, u64 *acc, uint32_t AL, cudaStream_t s, const MergedU *mu) {
+             u64 *ext, u64 *acc, uint32_t AL, cudaStream_t s, const MergedU *mu, const KsAuto *au) {
   const Params &p = ctx->p;
   const size_t N = p.N;
   const uint32_t A = p.alpha, E = L + A;
   const bool hpip = ks_uses_hpip(ctx, L, nb);
+  const BatchPtr d_raw = d;
+  if (au) d = {au->sigma_d, au->sigma_stride};  // what K5 reads (written by the ModUp INTT)
   NttMac mac{};
   if (hpip) {
     mac.evk = evk; mac.d = d.ptr; mac.acc = acc; mac.d_batch_stride = d.stride; mac.acc_batch_stride = 2ll * AL * N;
@@ -777,14 +786,14 @@ int ks_front(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d,
       ctx->exec.ewe_limbs += 4ull * nb;
     }
   }
-  int rc = ks_modup(ctx, lc, L, nb, d, yb, ext, s, hpip ? &mac : nullptr);
+  int rc = ks_modup(ctx, lc, L, nb, d_raw, yb, ext, s, hpip ? &mac : nullptr, au);
   if (rc) return rc;
   return ks_inner(ctx, lc, L, nb, d, evk, evk_q_limbs, ext, acc, AL, 0, s, mu, hpip);
 }
 
 // K8..K10 (+ the caller's addends): ModDown of nb accumulator pairs acc [nb][2][E] -> out_c[b] = (acc_c - NTT(BConv(acc_c; P -> Q))) * P^-1 (+ add_c[b])
 int ks_tail(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, u64 *acc, u64 *vb, BatchOut out0, BatchOut out1, BatchPtr add0, BatchPtr add1,
-            cudaStream_t s, bool acc_packed) {
+            cudaStream_t s, bool acc_packed, u64 add0_galois) {
   const Params &p = ctx->p;
   const size_t N = p.N;
   const uint32_t A = p.alpha, E = L + A;
@@ -800,6 +809,7 @@ int ks_tail(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, u64 *acc, u6
   // K10 (reference :548-590) (+ the caller's addend: HMULT add :967-1005 / HROTATE add :1339-1357).
   // Two-pass rings fuse K10 into the transform's row pass (NttFuse): v-hat never reaches HBM.
   const bool fuse = npass == 2 && out0.stride == out1.stride && (!add0.ptr || !add1.ptr || add0.stride == add1.stride);
+  if (add0_galois && (!fuse || !add0.ptr || add1.ptr)) return fail(ctx, HML_ERR_INVALID, "automorphism on the addend needs the fused ModDown epilogue");
   {
     NttLaunch l{};
     l.in = vb; l.out = vb; l.in_limb_stride = l.out_limb_stride = N; l.in_poly_stride = l.out_poly_stride = (long long)L * N;
@@ -814,6 +824,7 @@ int ks_tail(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, u64 *acc, u6
       f.z_mask = (add0.ptr ? 1u : 0u) | (add1.ptr ? 2u : 0u);
       f.dst = out0.ptr; f.dst_c_stride = (long long)(out1.ptr - out0.ptr); f.dst_b_stride = out0.stride;
       f.cst = lc->pinv; f.n_c = 2;
+      f.z_galois = (unsigned)(add0_galois & (2ull * N - 1));
     }
     launch_ntt_forward(tabs_for(ctx, s), logN, lc->q_lm, l, s);
     prof_mark(ctx, HML_CLS_NTT, s);
@@ -839,7 +850,7 @@ int ks_tail(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, u64 *acc, u6
 // nb independent key switches sharing one key, one kernel launch per stage:
 // d[b] [L][N] -> out_c[b] = KS_c(d[b]) (+ add_c[b]).  `ws` must hold nb * ks_ws_words().
 int ks_run(hml_ctx *ctx, uint32_t L, uint32_t nb, BatchPtr d, const u64 *evk, uint32_t evk_q_limbs, BatchOut out0,
-           BatchOut out1, BatchPtr add0, BatchPtr add1, u64 *ws, cudaStream_t s) {
+           BatchOut out1, BatchPtr add0, BatchPtr add1, u64 *ws, cudaStream_t s, const KsAuto *au) {
   const Params &p = ctx->p;
   if (evk_q_limbs < L || evk_q_limbs > p.max_level) return fail(ctx, HML_ERR_INVALID, "evk_q_limbs must be in [L, maxLevel]");
   LevelConsts *lc;
@@ -850,8 +861,8 @@ int ks_run(hml_ctx *ctx, uint32_t L, uint32_t nb, BatchPtr d, const u64 *evk, ui
   if (beta > 8) return fail(ctx, HML_ERR_UNSUPPORTED, "more than 8 key-switch digits (ceil(L/alpha) > 8)");
   // workspace, every buffer batch-major: yb [nb][L] | ext [nb][beta][E] | acc [nb][2][E] | vb [nb][2][L]  (limbs of N words)
   u64 *yb = ws, *ext = yb + (size_t)nb * L * N, *acc = ext + (size_t)nb * beta * E * N, *vb = acc + (size_t)nb * 2 * E * N;
-  if ((rc = ks_front(ctx, lc, L, nb, d, evk, evk_q_limbs, yb, ext, acc, E, s, nullptr))) return rc;
-  return ks_tail(ctx, lc, L, nb, acc, vb, out0, out1, add0, add1, s, p.logN > NTT_SMALL_LOG && !ks_uses_hpip(ctx, L, nb));
+  if ((rc = ks_front(ctx, lc, L, nb, d, evk, evk_q_limbs, yb, ext, acc, E, s, nullptr, au))) return rc;
+  return ks_tail(ctx, lc, L, nb, acc, vb, out0, out1, add0, add1, s, p.logN > NTT_SMALL_LOG && !ks_uses_hpip(ctx, L, nb), au ? au->g : 0);
 }
 
 extern "C" int hml_keyswitch(hml_ctx *ctx, uint32_t L, const uint64_t *d, const uint64_t *evk, uint32_t evk_q_limbs,
@@ -1668,6 +1679,17 @@ int hrot_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct, const u64 *rk
                     u64 *ws, cudaStream_t s) {
   const size_t N = ctx->p.N, PL = N * L;
   u64 *sb = ws, *rest = sb + 2 * nb * PL;  // sb [nb][2][L][N]
+  static const bool fuse_auto = [] { const char *e = getenv("HML_AUTO_FUSE"); return !(e && atoi(e) == 0); }();
+  const bool in_place = ct_out < ct + 2 * nb * PL && ct < ct_out + 2 * nb * PL;  // the epilogue would gather c0 rows it has overwritten
+  if (fuse_auto && !in_place && ctx->p.logN > NTT_SMALL_LOG && (g & (2 * N - 1)) != 1) {
+    // two-pass rings: no kernel for the automorphism (reference :1302-1319).  In evaluation order sigma_g maps every 256-slot
+    // row onto one source row (ntt_core.cuh RowSigma), so the ModUp INTT permutes c1 while it loads it (and leaves sigma(c1)
+    // in sb for the inner product's own-digit term) and the ModDown epilogue gathers sigma(c0) from the raw c0
+    const KsAuto au{g, sb + PL, (long long)(2 * PL)};
+    ctx->exec.automorph_limbs += 2ull * nb * L;
+    return ks_run(ctx, L, nb, {ct + PL, (long long)(2 * PL)}, rk, evk_q_limbs, {ct_out, (long long)(2 * PL)}, {ct_out + PL, (long long)(2 * PL)},
+                  {ct, (long long)(2 * PL)}, {nullptr, 0}, rest, s, &au);
+  }
   launch_automorph(ctx->p.logN, 2 * L * nb, ct, sb, g, s);  // reference :1302-1319
   prof_mark(ctx, HML_CLS_AUTO, s);
   ctx->exec.automorph_limbs += 2ull * nb * L; ctx->exec.kernel_launches++;

@@ -357,10 +357,17 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
   if constexpr (MAC) cur = RowItem{(int)blockIdx.z, items.first_p()};
   else cur = items.next(RowItem{0, (int)blockIdx.z - (int)gridDim.z});
   RowItem nxt = items.valid(cur) ? items.next(cur) : cur;
+  // inverse rows may load through an automorphism (NttLaunch::in_galois)
+  auto issue = [&](const RowItem &i, unsigned stage) {
+    if constexpr (INV && MODE == 0) {
+      if (l.in_galois) { row_issue_sigma(src_of(i) - tile_off, stage, lane, warp, (int)blockIdx.x, l.in_galois, l.in_ginv8, logN); return; }
+    }
+    row_issue(src_of(i), stage, lane, warp);
+  };
   pdl_wait();  // the twiddle blob (a constant table) is already in flight; the data is another kernel's output
-  if (items.valid(cur)) row_issue(src_of(cur), data0, lane, warp);
+  if (items.valid(cur)) issue(cur, data0);
   cp_async_commit();
-  if (items.valid(nxt)) row_issue(src_of(nxt), data0 + ROW_TILE_BYTES, lane, warp);
+  if (items.valid(nxt)) issue(nxt, data0 + ROW_TILE_BYTES);
   cp_async_commit();
   mbar_wait(&bar, 0);
   const int l16 = lane & 15, rr = 2 * warp + (lane >> 4);
@@ -385,7 +392,15 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
         if (p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
       };
       prefetch(f.x + fc * f.x_c_stride + fb * f.x_b_stride + (size_t)limb * nn, f.x_packed);
-      if (f.z != nullptr && ((f.z_mask >> fc) & 1u)) prefetch(f.z + fc * f.z_c_stride + fb * f.z_b_stride + (size_t)limb * nn, f.z_packed);
+      if (f.z != nullptr && ((f.z_mask >> fc) & 1u)) {
+        const u64 *zslot = f.z + fc * f.z_c_stride + fb * f.z_b_stride + (size_t)limb * nn;
+        if (f.z_galois) {  // the two source rows of this warp's rows (2 KB each: one line per lane)
+          const RowSigma rs = row_sigma((unsigned)(blockIdx.x * 16 + 2 * warp + (lane >> 4)), f.z_galois, logN - NTT_ROW_LOG);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(zslot + ((size_t)rs.src_row << NTT_ROW_LOG) + (lane & 15) * 16));
+        } else {
+          prefetch(zslot, f.z_packed);
+        }
+      }
     }
     if constexpr (MAC) {
       // the key words this warp's two rows will be multiplied with (2 x 4 KB, + the own digit's at the first member) start
@@ -562,8 +577,17 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
           }
         } else if (has_z) {
           ulonglong2 zv[8];
+          if (f.z_galois) {  // sigma(z): this row's 256 slots come from ONE source row, permuted (RowSigma)
+            const RowSigma rs = row_sigma((unsigned)(blockIdx.x * 16 + rr), f.z_galois, logN - NTT_ROW_LOG);
+            const u64 *zr = zs + ((size_t)rs.src_row << NTT_ROW_LOG);
+            const unsigned k0 = (l16 >> 3) * 16 + (l16 & 7) * 2;
 #pragma unroll
-          for (int m = 0; m < 8; ++m) zv[m] = load_chunk(zs, f.z_packed, m);
+            for (int m = 0; m < 8; ++m)
+              zv[m] = make_ulonglong2(__ldg(zr + sigma_src(k0 + 32 * m, f.z_galois, rs.d)), __ldg(zr + sigma_src(k0 + 32 * m + 1, f.z_galois, rs.d)));
+          } else {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) zv[m] = load_chunk(zs, f.z_packed, m);
+          }
 #pragma unroll
           for (int m = 0; m < 8; ++m) {
             const double2 y = *reinterpret_cast<const double2 *>(data + ad.C(m));
@@ -587,6 +611,11 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
         }
       }
     } else {
+      if (l.side_out != nullptr) {  // the permuted input rows as they sit in the tile, 256 B per half-warp
+        u64 *so = l.side_out + (long long)cur.b * l.side_batch_stride + slot * l.out_limb_stride + tile_off + (size_t)rr * 256 + (l16 >> 3) * 16 + (l16 & 7) * 2;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) *reinterpret_cast<ulonglong2 *>(so + 32 * m) = *reinterpret_cast<const ulonglong2 *>(data + ad.C(m));
+      }
 #pragma unroll
       for (int m = 0; m < 8; ++m) {
         const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(data + ad.B(m));
@@ -618,7 +647,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
       for (int j = 0; j < 16; ++j) outd[16 * j] = reduce_signed(a[j], q, qinv);
     }
     __syncwarp();  // every lane is done with this stage before it is refilled
-    if (items.valid(nn)) row_issue(src_of(nn), data0 + (k & 1) * ROW_TILE_BYTES, lane, warp);
+    if (items.valid(nn)) issue(nn, data0 + (k & 1) * ROW_TILE_BYTES);
     cp_async_commit();
     cur = nxt; nxt = nn;
   }

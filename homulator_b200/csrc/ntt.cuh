@@ -74,6 +74,9 @@ struct NttFuse {
   int n_c;
   unsigned z_mask;              // z is added for component c iff bit c is set
   int x_packed, z_packed;       // x / z hold packed limbs (modarith.cuh: 5 bytes per coefficient inside the 8N-byte slot)
+  unsigned z_galois;            // != 0: z is read through the automorphism X -> X^g, z'[k] = z[sigma_g(k)] (hrotate's sigma(c0)
+                                // addend, reference src/Operation.cpp:1302-1319 + :1339-1357; z must hold plain words).  In
+                                // evaluation order the automorphism maps every 256-slot row onto ONE source row (RowSigma)
 };
 
 // Optional key-switch inner product fused into the ModUp transform's row pass — the GPU counterpart of the reference's HPIP
@@ -111,6 +114,13 @@ struct NttLaunch {
   const double2 *post_scale;  // [n_limbs] (c*ninv mod q, RN(that / q)) or nullptr for plain N^-1
   NttFuse fuse;               // forward only
   NttMac mac;                 // forward only, two-pass rings, no fused epilogue: see NttMac (n_polys = beta, LimbMap::skip = own digit)
+  // inverse only, two-pass rings, n_polys == 1: the input is read through the automorphism X -> X^in_galois (hrotate's
+  // sigma(c1), the key-switch input) while the row pass loads it, and the permuted limbs are also written to side_out
+  // ([n_batch] items side_batch_stride apart, limb slots like `out`) for the inner product's own-digit term.
+  // in_ginv8 = in_galois^-1 mod 256.  0: plain load.
+  unsigned in_galois, in_ginv8;
+  u64 *side_out;
+  long long side_batch_stride;
   int in_f64;                 // forward only, two-pass rings: `in` holds signed doubles |v| <= q (BConvArgs::out_f64)
   int out_f64;                // forward only, two-pass rings, no fused epilogue: leave the raw lazy sums (|v| < 10 q) as doubles
                               // in `out` instead of canonical words (consumer: InnerArgs::ext_f64)

@@ -112,5 +112,47 @@ __device__ __forceinline__ void row_issue(const u64 *src_tile, unsigned stage_sm
   }
 }
 
+// ---- automorphism inside a row pass.  Slot k of a limb holds the evaluation at psi^(2 brev(k) + 1); sigma_g: out[k] = in[k'],
+// brev(k') = g * brev(k) + (g - 1) / 2 (mod N) (k_automorph, ewe.cu).  With k = R * 256 + klo (R = row, h = logN - 8 bits) the
+// natural index is j = brev8(klo) * 2^h + brev_h(R), so
+//   low h bits of j'  = (g * brev_h(R) + (g - 1) / 2) mod 2^h   -> depend on the row only: ONE source row R' per row
+//   high 8 bits of j' = (g * brev8(klo) + d) mod 256,  d = (g * brev_h(R) + (g - 1) / 2) >> h    -> a permutation inside the row
+struct RowSigma {
+  unsigned src_row, d;
+};
+__device__ __forceinline__ RowSigma row_sigma(unsigned R, unsigned g, int h) {
+  const unsigned b = __brev(R) >> (32 - h), t = g * b + ((g - 1u) >> 1);
+  RowSigma r;
+  r.src_row = __brev(t & ((1u << h) - 1u)) >> (32 - h);
+  r.d = t >> h;
+  return r;
+}
+// source slot (inside the source row) of destination slot klo
+__device__ __forceinline__ unsigned sigma_src(unsigned klo, unsigned g, unsigned d) {
+  return __brev((g * (__brev(klo) >> 24) + d) & 255u) >> 24;
+}
+// destination slot of source slot kp (ginv8 = g^-1 mod 256)
+__device__ __forceinline__ unsigned sigma_dst(unsigned kp, unsigned ginv8, unsigned d) {
+  return __brev((ginv8 * ((__brev(kp) >> 24) - d)) & 255u) >> 24;
+}
+__device__ __forceinline__ void cp_async8(unsigned smem_dst, const void *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+// row_issue through the automorphism: the warp's two rows of tile `tile` of the limb at `src_limb`; every instruction reads
+// 256 contiguous bytes of the source row and scatters them to the slots the transform expects
+__device__ __forceinline__ void row_issue_sigma(const u64 *src_limb, unsigned stage_smem, int lane, int warp, int tile, unsigned g,
+                                                unsigned ginv8, int logN) {
+#pragma unroll
+  for (int r2 = 0; r2 < 2; ++r2) {
+    const RowSigma rs = row_sigma((unsigned)(tile * 16 + 2 * warp + r2), g, logN - NTT_ROW_LOG);
+    const u64 *src = src_limb + ((size_t)rs.src_row << NTT_ROW_LOG);
+    const unsigned row0 = stage_smem + (2 * warp + r2) * 2048;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const unsigned kp = lane + 32 * i, klo = sigma_dst(kp, ginv8, rs.d), line = klo >> 4;
+      cp_async8(row0 + line * 128 + ((((klo >> 1) & 7) ^ (line & 7)) << 4) + (klo & 1) * 8, src + kp);
+    }
+  }
+}
 
 }  // namespace hml

@@ -551,6 +551,7 @@ static void launch_fused_t(const NttTables &t, int logN, const LimbMap &lm, cons
 // returns false when the launch shape is outside the fused kernel (the caller falls back to the two-kernel path)
 bool launch_ntt_fused(bool inverse, const NttTables &t, int logN, const LimbMap &lm, const NttLaunch &l, unsigned *ctrl, cudaStream_t s) {
   if (!ctrl || logN <= NTT_SMALL_LOG || logN > 16 || !ntt_fused_enabled()) return false;
+  if (l.in_galois || l.side_out || l.fuse.z_galois) return false;  // automorphism on load: two-kernel path only
   FusedPlan fp;
   if (!make_plan(logN, lm, l, fp)) return false;
   switch (logN - NTT_ROW_LOG) {
