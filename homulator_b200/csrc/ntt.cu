@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(NT, (ColCfg<LOGR1, NT>::MIN_CTAS)) ntt_inv_col
 // Shared-memory rows are stored with their 16-byte chunks XOR-swizzled inside each 128-byte line
 // (chunk c of line g at position c ^ (g & 7)): round A's 8-byte accesses, round B's per-thread 128-byte runs and the
 // coalesced 16-byte output reads are all conflict-free.
-// Items (ciphertext b, poly p) of one limb, walked with stride gridDim.z in the linear order b * n_polys + p.
+// Items (ciphertext b, poly p) of one limb, walked with stride zn (the item splits of the grid) in the linear order b * n_polys + p.
 struct RowItem {
   int b, p;
 };
@@ -307,7 +307,7 @@ struct RowItems {
 };
 
 // MAC launches (NttMac): a CTA must own ALL members (digits) of a ciphertext's limb tile, so the grid splits the ciphertexts
-// (b = blockIdx.z, + gridDim.z, ...) and walks the digits innermost.
+// (b = zi, + zn, ...) and walks the digits innermost.
 struct RowItemsB {
   int n_polys, n_batch, skip, step;
   __device__ __forceinline__ bool valid(const RowItem &i) const { return i.b < n_batch; }
@@ -327,14 +327,17 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
   constexpr bool FUSE = MODE == 1, MAC = MODE == 2;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bar;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, limb = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // grid = (tiles * item splits, limbs), split index fastest: the CTAs that share a (limb, tile) — hence its 32 KB twiddle blob —
+  // are adjacent in launch order, so all but the first of them find the blob in L2 (row-pass reads 2217 -> 1990 MB per launch)
+  const int limb = blockIdx.y, zn = gridDim.x >> (logN - NTT_ROW_LOG - 4), tile_i = blockIdx.x / zn, zi = blockIdx.x - tile_i * zn;
   const int mi = lm.mod[limb];
   const double *blob = reinterpret_cast<const double *>(smem);
   if (tid == 0) mbar_init(&bar, 1);
   __syncthreads();
   if (tid == 0) {
     mbar_expect_tx(&bar, ROW_TILE_BYTES);
-    bulk_g2s(smem, (INV ? t.inv_rows : t.fwd_rows) + ((size_t)mi << logN) + (size_t)blockIdx.x * NTT_TILE, ROW_TILE_BYTES, &bar);
+    bulk_g2s(smem, (INV ? t.inv_rows : t.fwd_rows) + ((size_t)mi << logN) + (size_t)tile_i * NTT_TILE, ROW_TILE_BYTES, &bar);
   }
   const ModConst mc = t.mc[mi];
   const double q = mc.q, qinv = mc.qinv;
@@ -342,7 +345,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
   const RowAddr ad = row_addr(lane, warp);
   const unsigned data0 = smem_u32(smem) + ROW_TILE_BYTES;
   const long long slot = lm.pos[limb];
-  const size_t tile_off = (size_t)blockIdx.x * NTT_TILE;
+  const size_t tile_off = (size_t)tile_i * NTT_TILE;
   // forward rows read the raw doubles pass 1 left in `out`; inverse rows read the canonical input words
   auto src_of = [&](const RowItem &i) -> const u64 * {
     return (INV ? l.in + (long long)i.b * l.in_batch_stride + (long long)i.p * l.in_poly_stride + slot * l.in_limb_stride
@@ -352,15 +355,15 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
     return l.out + (long long)i.b * l.out_batch_stride + (long long)i.p * l.out_poly_stride + slot * l.out_limb_stride + tile_off;
   };
   using Items = typename std::conditional<MAC, RowItemsB, RowItems>::type;
-  const Items items{l.n_polys, l.n_batch, lm.skip[limb], (int)gridDim.z};
+  const Items items{l.n_polys, l.n_batch, lm.skip[limb], zn};
   RowItem cur;
-  if constexpr (MAC) cur = RowItem{(int)blockIdx.z, items.first_p()};
-  else cur = items.next(RowItem{0, (int)blockIdx.z - (int)gridDim.z});
+  if constexpr (MAC) cur = RowItem{zi, items.first_p()};
+  else cur = items.next(RowItem{0, zi - zn});
   RowItem nxt = items.valid(cur) ? items.next(cur) : cur;
   // inverse rows may load through an automorphism (NttLaunch::in_galois)
   auto issue = [&](const RowItem &i, unsigned stage) {
     if constexpr (INV && MODE == 0) {
-      if (l.in_galois) { row_issue_sigma(src_of(i) - tile_off, stage, lane, warp, (int)blockIdx.x, l.in_galois, l.in_ginv8, logN); return; }
+      if (l.in_galois) { row_issue_sigma(src_of(i) - tile_off, stage, lane, warp, tile_i, l.in_galois, l.in_ginv8, logN); return; }
     }
     row_issue(src_of(i), stage, lane, warp);
   };
@@ -395,7 +398,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
       if (f.z != nullptr && ((f.z_mask >> fc) & 1u)) {
         const u64 *zslot = f.z + fc * f.z_c_stride + fb * f.z_b_stride + (size_t)limb * nn;
         if (f.z_galois) {  // the two source rows of this warp's rows (2 KB each: one line per lane)
-          const RowSigma rs = row_sigma((unsigned)(blockIdx.x * 16 + 2 * warp + (lane >> 4)), f.z_galois, logN - NTT_ROW_LOG);
+          const RowSigma rs = row_sigma((unsigned)(tile_i * 16 + 2 * warp + (lane >> 4)), f.z_galois, logN - NTT_ROW_LOG);
           asm volatile("prefetch.global.L2 [%0];" ::"l"(zslot + ((size_t)rs.src_row << NTT_ROW_LOG) + (lane & 15) * 16));
         } else {
           prefetch(zslot, f.z_packed);
@@ -578,7 +581,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
         } else if (has_z) {
           ulonglong2 zv[8];
           if (f.z_galois) {  // sigma(z): this row's 256 slots come from ONE source row, permuted (RowSigma)
-            const RowSigma rs = row_sigma((unsigned)(blockIdx.x * 16 + rr), f.z_galois, logN - NTT_ROW_LOG);
+            const RowSigma rs = row_sigma((unsigned)(tile_i * 16 + rr), f.z_galois, logN - NTT_ROW_LOG);
             const u64 *zr = zs + ((size_t)rs.src_row << NTT_ROW_LOG);
             const unsigned k0 = (l16 >> 3) * 16 + (l16 & 7) * 2;
 #pragma unroll
@@ -838,10 +841,10 @@ static void launch_rows(bool inverse, const NttTables &t, int logN, const LimbMa
     const int per = std::max(1, row_items_target() / std::max(1, l.n_polys));
     int z = (l.n_batch + per - 1) / per;
     while (z > 1 && (long long)tiles * l.n_limbs * z > 64ll * sm_count()) --z;
-    launch_pdl(ntt_rows<false, 2>, dim3(tiles, l.n_limbs, std::max(1, z)), NTT_THREADS, ROW_SMEM_BYTES, s, t, logN, lm, l);
+    launch_pdl(ntt_rows<false, 2>, dim3(tiles * std::max(1, z), l.n_limbs), NTT_THREADS, ROW_SMEM_BYTES, s, t, logN, lm, l);
     return;
   }
-  const dim3 grid(tiles, l.n_limbs, row_split(l.n_polys * l.n_batch, tiles * l.n_limbs));
+  const dim3 grid(tiles * row_split(l.n_polys * l.n_batch, tiles * l.n_limbs), l.n_limbs);
   if (inverse) launch_pdl(ntt_rows<true, 0>, grid, NTT_THREADS, ROW_SMEM_BYTES, s, t, logN, lm, l);
   else if (l.fuse.x) launch_pdl(ntt_rows<false, 1>, grid, NTT_THREADS, ROW_SMEM_BYTES, s, t, logN, lm, l);
   else launch_pdl(ntt_rows<false, 0>, grid, NTT_THREADS, ROW_SMEM_BYTES, s, t, logN, lm, l);

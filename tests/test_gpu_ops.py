@@ -452,8 +452,24 @@ def test_hmult_many_special_primes_dmma_fold():
     Oracle.set_threads(1)
 
 
+def test_hrotate_in_place_and_identity(north_star):
+    """hml_hrotate with ct_out == ct (the epilogue must not gather sigma(c0) from rows it has already overwritten: the library
+    falls back to the automorphism kernel there), several galois elements through the fused loads, and g = 1."""
+    ctx, o, a, b, evk = north_star
+    L = 35
+    K = to_dev(evk)
+    for g in (5, 25, 2 * 65536 - 1, 3 ** 7):
+        want = o.hrotate(L, a, evk, L, g)
+        assert np.array_equal(to_host(ctx.hrotate(L, to_dev(a), K, g)), want), g
+    buf = to_dev(a).clone()
+    ctx.hrotate(L, buf, K, 25, out=buf)
+    assert np.array_equal(to_host(buf), o.hrotate(L, a, evk, L, 25))
+    assert np.array_equal(to_host(ctx.hrotate(L, to_dev(a), K, 1)), o.hrotate(L, a, evk, L, 1))
+
+
 @pytest.mark.parametrize("env", [{"HML_NTT_FUSED": "1"}, {"HML_HPIP": "0"}, {"HML_HPIP": "2"}, {"HML_BCONV_UMMA": "0"},
-                                 {"HML_COL_NT": "256", "HML_PDL": "0"}, {"HML_NTT_FUSED": "1", "HML_NTT_G": "1", "HML_NTT_LAG": "1"}],
+                                 {"HML_COL_NT": "256", "HML_PDL": "0"}, {"HML_NTT_FUSED": "1", "HML_NTT_G": "1", "HML_NTT_LAG": "1"},
+                                 {"HML_COL_DYN": "0", "HML_AUTO_FUSE": "0"}, {"HML_COL_NT": "128"}],
                          ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
 def test_alternative_kernel_paths(env):
     """Every kernel path behind a process-wide switch — the single-launch transform (ntt_fused.cu), the inner product fused
