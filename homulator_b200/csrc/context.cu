@@ -1732,13 +1732,21 @@ int hrot_hoisted_run(hml_ctx *ctx, uint32_t L, const u64 *ct, uint32_t n_rot, co
   u64 *sb = ws, *yb = sb + 2 * PL, *ext = yb + PL, *acc = ext + (size_t)beta * E * N, *vb = acc + 2 * (size_t)E * N;
   const BatchPtr c1{ct + PL, 0};
   if ((rc = ks_modup(ctx, lc, L, 1, c1, yb, ext, s, nullptr))) return rc;
+  static const bool fuse_auto = [] { const char *e = getenv("HML_AUTO_FUSE"); return !(e && atoi(e) == 0); }();
   for (uint32_t r = 0; r < n_rot; ++r) {
-    launch_automorph(p.logN, L, ct, sb, galois[r], s);  // sigma_r(c0): the addend of the ModDown epilogue
-    prof_mark(ctx, HML_CLS_AUTO, s);
-    ctx->exec.automorph_limbs += L; ctx->exec.kernel_launches++;
+    // sigma_r(c0), the addend of the ModDown epilogue: gathered by the epilogue itself on two-pass rings (hrot_run), else a kernel
+    const bool gather = fuse_auto && p.logN > NTT_SMALL_LOG && (galois[r] & (2 * N - 1)) != 1;
+    if (!gather) {
+      launch_automorph(p.logN, L, ct, sb, galois[r], s);
+      prof_mark(ctx, HML_CLS_AUTO, s);
+      ctx->exec.kernel_launches++;
+    }
+    ctx->exec.automorph_limbs += L;
     if ((rc = ks_inner(ctx, lc, L, 1, c1, (const u64 *)rotkeys[r], evk_q_limbs, ext, acc, E, galois[r], s, nullptr, false))) return rc;
     u64 *o = (u64 *)outs[r];
-    if ((rc = ks_tail(ctx, lc, L, 1, acc, vb, {o, 0}, {o + PL, 0}, {sb, 0}, {nullptr, 0}, s, p.logN > NTT_SMALL_LOG))) return rc;
+    if ((rc = ks_tail(ctx, lc, L, 1, acc, vb, {o, 0}, {o + PL, 0}, {gather ? ct : sb, 0}, {nullptr, 0}, s, p.logN > NTT_SMALL_LOG,
+                      gather ? galois[r] : 0)))
+      return rc;
   }
   return check_launch(ctx, "hrotate hoisted");
 }
