@@ -1,6 +1,6 @@
-"""Profiling driver for the batched path: hmult_batch over one chunk of B (default 16) ciphertext pairs.
+"""Profiling driver for the batched path: hmult_batch (or hrotate_batch) over one chunk of B (default 16) ciphertexts.
 
-    python profiles/prof_batch.py [n_warm] [n_prof] [B]
+    python profiles/prof_batch.py [n_warm] [n_prof] [B] [hmult|hrotate]
 """
 import os
 import sys
@@ -20,8 +20,13 @@ evk = ctx.uniform(ctx.ext_mod_idx(L), 3, lead=(3, 2))
 a = ctx.uniform(q, 1, lead=(B, 2))
 b = ctx.uniform(q, 2, lead=(B, 2))
 out = ctx.empty(B, 2, L - 1, ctx.N)
+op = sys.argv[4] if len(sys.argv) > 4 else "hmult"
+out_r = ctx.empty(B, 2, L, ctx.N) if op == "hrotate" else None
 torch.cuda.synchronize()
 for _ in range(n_warm + n_prof):
-    ctx.hmult_batch(L, a, b, evk, out=out)
+    if op == "hrotate":
+        ctx.hrotate_batch(L, a, evk, 5, out=out_r)
+    else:
+        ctx.hmult_batch(L, a, b, evk, out=out)
 torch.cuda.synchronize()
 print("done")
