@@ -37,4 +37,21 @@ for i in range(40):
         print("op rep %d differs" % i)
         break
 print("hmult_batch / hrotate_batch x 32: 40 repetitions identical" if not bad else "MISMATCH")
+# one ciphertext per launch (tile queue of the column passes on few tiles per CTA, automorphism on load, fused inner product),
+# interleaved with batched launches so that the queue counters change hands between launch shapes
+r1, r2 = ctx.hmult(L, a[3], b[3], evk), ctx.hrotate(L, a[5], evk, 25)
+p1, p2 = torch.empty_like(r1), torch.empty_like(r2)
+idx = [ctx.ext_mod_idx(L)[i % 50] for i in range(115)]
+xn = ctx.uniform(idx, 77, lead=(8,))
+rn = ctx.ntt_batch(xn, idx)
+pn = torch.empty_like(rn)
+for i in range(100):
+    ctx.hmult(L, a[3], b[3], evk, out=p1)
+    ctx.ntt_batch(xn, idx, out=pn)
+    ctx.hrotate(L, a[5], evk, 25, out=p2)
+    if not (torch.equal(p1, r1) and torch.equal(p2, r2) and torch.equal(pn, rn)):
+        bad += 1
+        print("single-op rep %d differs" % i)
+        break
+print("hmult / hrotate / ntt_batch interleaved: 100 repetitions identical" if not bad else "MISMATCH")
 sys.exit(1 if bad else 0)
