@@ -372,6 +372,23 @@ def main():
             hm = lat(lambda: ctx.hmult(L, ct_a[0], ct_b[0], evk, out=o1), 20)
             hr = lat(lambda: ctx.hrotate(L, ct_a[0], evk, 5, out=o2), 20)
             del o1, o2
+        # one 32-ciphertext chunk of the batched ops timed alone (a 25 ms burst at full clocks): what the kernels do before the
+        # board reaches its power cap; `value` below is the sustained figure of the 256-ciphertext steps
+        nb32 = min(32, B)
+        ob = ctx.empty(nb32, 2, L, N_RING)
+        burst = {}
+        for name, fn in (("hmult", lambda: ctx.hmult_batch(L, ct_a[:nb32], ct_b[:nb32], evk, out=out[:nb32])),
+                         ("hrotate", lambda: ctx.hrotate_batch(L, ct_a[:nb32], evk, 5, out=ob))):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(3):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            burst[name] = e0.elapsed_time(e1) * 1e3 / (3 * nb32)
+        del ob
         ntt_ms, ntt1_us_per_limb = ntt_pair_ms()
         try:
             import pynvml
@@ -504,6 +521,7 @@ def main():
     extra = {"hrotate_batched_us": hrot_batched_us, "hmult_batched_us": us_per_op, "throughput_hmult_per_s": n_ops / (ms_total * 1e-3),
              "ntt_fp64_issue_floor_us_per_limb": fp64_floor_us, "ntt_frac_of_fp64_issue_floor": fp64_floor_us / (ntt_ms * 1e3 / (n_limbs * n_b)), "ntt_limbs_per_s": ntt_limbs_per_s, "ntt_us_per_limb": ntt_ms * 1e3 / (n_limbs * n_b),
              "ntt_us_per_limb_sustained": ntt_ms_sustained * 1e3 / (n_limbs * n_b), "ntt_sm_mhz_when_timed_alone": ntt_clock,
+             "hmult_batched_us_one_chunk_burst": burst["hmult"], "hrotate_batched_us_one_chunk_burst": burst["hrotate"],
              "ntt_us_per_limb_single_ciphertext_launch": ntt1_us_per_limb, "e2e_matches_device_path": e2e_ok,
              "e2e_packed_host_format": {"value": e2e_packed_us, "unit": "us", "h2d_bytes_per_step": 2 * 2 * L * 5 * N_RING * Be,
                                         "d2h_bytes_per_step": 2 * (L - 1) * 5 * N_RING * Be, "matches_u64_path": e2e_packed_ok,

@@ -237,7 +237,10 @@ int hml_hmult(hml_ctx *ctx, uint32_t L, const uint64_t *ct_a, const uint64_t *ct
               uint32_t evk_q_limbs, uint64_t *ct_out, void *stream);
 /* HROTATE (reference src/Operation.cpp:1271-1358): automorphism of both polys + keyswitch + add.
  * The reference takes no rotation amount; galois_elt is the one addition (5^r mod 2N; r=1 -> 5).
- * ct [2][L][N] -> ct_out [2][L][N] = (sigma(c0) + ks0, ks1), ks = KeySwitch(sigma(c1)). */
+ * ct [2][L][N] -> ct_out [2][L][N] = (sigma(c0) + ks0, ks1), ks = KeySwitch(sigma(c1)).  ct_out may be ct (in place).
+ * The AUTO instruction class (reference InsGen::GenAUTO, src/InsGen.cpp:46-71) is executed inside the key switch's loads on
+ * rings with N >= 8192 (in evaluation order the automorphism maps every 256-slot row onto one source row), by a kernel of its
+ * own otherwise; the executed counts report the 2L limbs either way. */
 int hml_hrotate(hml_ctx *ctx, uint32_t L, const uint64_t *ct, const uint64_t *rotkey, uint32_t evk_q_limbs,
                 uint64_t galois_elt, uint64_t *ct_out, void *stream);
 /* Hoisted rotations: n_rot rotations of ONE ciphertext share one ModUp of c1; the automorphism is
