@@ -330,7 +330,9 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // grid = (tiles * item splits, limbs), split index fastest: the CTAs that share a (limb, tile) — hence its 32 KB twiddle blob —
   // are adjacent in launch order, so all but the first of them find the blob in L2 (row-pass reads 2217 -> 1990 MB per launch)
-  const int limb = blockIdx.y, zn = gridDim.x >> (logN - NTT_ROW_LOG - 4), tile_i = blockIdx.x / zn, zi = blockIdx.x - tile_i * zn;
+  // (MAC launches walk the limbs backwards: the P-limbs, whose CTAs have one more digit to transform, start first)
+  const int limb = MODE == 2 ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+  const int zn = gridDim.x >> (logN - NTT_ROW_LOG - 4), tile_i = blockIdx.x / zn, zi = blockIdx.x - tile_i * zn;
   const int mi = lm.mod[limb];
   const double *blob = reinterpret_cast<const double *>(smem);
   if (tid == 0) mbar_init(&bar, 1);
