@@ -359,7 +359,7 @@ def main():
         ts.sort()
         return ts[len(ts) // 2]
 
-    ntt_ms = ntt1_us_per_limb = ntt_clock = hm = hr = None
+    ntt_ms = ntt1_us_per_limb = ntt_clock = hm = hr = hm_pk = hr_pk = None
     if rank == 0:
         if flush is not None:  # one-ciphertext latencies (L2 flushed), also before the sustained region: a latency figure
             o1, o2 = ctx.empty(2, L - 1, N_RING), ctx.empty(2, L, N_RING)
@@ -368,7 +368,15 @@ def main():
                 ctx.hrotate(L, ct_a[0], evk, 5, out=o2)
             hm = lat(lambda: ctx.hmult(L, ct_a[0], ct_b[0], evk, out=o1), 20)
             hr = lat(lambda: ctx.hrotate(L, ct_a[0], evk, 5, out=o2), 20)
-            del o1, o2
+            # the same with the key handed over packed (hml_key_pack + HML_KEY_PACKED: 94 instead of 150 MB read per key switch)
+            evk_p = ctx.key_pack(evk)
+            kp = L | hml.KEY_PACKED
+            for _ in range(3):
+                ctx.hmult(L, ct_a[0], ct_b[0], evk_p, evk_q_limbs=kp, out=o1)
+                ctx.hrotate(L, ct_a[0], evk_p, 5, evk_q_limbs=kp, out=o2)
+            hm_pk = lat(lambda: ctx.hmult(L, ct_a[0], ct_b[0], evk_p, evk_q_limbs=kp, out=o1), 20)
+            hr_pk = lat(lambda: ctx.hrotate(L, ct_a[0], evk_p, 5, evk_q_limbs=kp, out=o2), 20)
+            del o1, o2, evk_p
         # one 32-ciphertext chunk of the batched ops timed alone (a 25 ms burst at full clocks): what the kernels do before the
         # board reaches its power cap; `value` below is the sustained figure of the 256-ciphertext steps
         nb32 = min(32, B)
@@ -549,6 +557,7 @@ def main():
         aw_m, aw_r = hml.algorithmic_words("hmult", L, ALPHA), hml.algorithmic_words("hrotate", L, ALPHA)
         extra.update({
             "hmult_single_us_l2_flushed": hm, "hrotate_single_us_l2_flushed": hr, "hmult_single_us_l2_flushed_after_sustained_load": hm_late,
+            "hmult_single_us_l2_flushed_packed_key": hm_pk, "hrotate_single_us_l2_flushed_packed_key": hr_pk,
             "hmult_single_unfused_bytes_equivalent_over_hbm_peak": aw_m * W_bytes / (hm * 1e-6) / 1e9 / peak,
             "hrotate_single_unfused_bytes_equivalent_over_hbm_peak": aw_r * W_bytes / (hr * 1e-6) / 1e9 / peak,
             # NOT a roofline fraction: SURVEY 8d's UNFUSED byte count divided by the time of the fused / merged schedule (which

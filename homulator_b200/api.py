@@ -57,7 +57,7 @@ def lib_path():
 EXPORTS = [
     "hml_ctx_create", "hml_ctx_create_params", "hml_ctx_destroy", "hml_last_error", "hml_last_create_error",
     "hml_ring_degree", "hml_n_moduli", "hml_get_moduli", "hml_get_roots", "hml_dev_alloc", "hml_dev_free", "hml_h2d",
-    "hml_d2h", "hml_sync", "hml_ntt", "hml_intt", "hml_ntt_batch", "hml_intt_batch", "hml_ewe", "hml_automorph", "hml_bconv", "hml_bconv_batch", "hml_keyswitch", "hml_rescale",
+    "hml_d2h", "hml_sync", "hml_key_pack", "hml_ntt", "hml_intt", "hml_ntt_batch", "hml_intt_batch", "hml_ewe", "hml_automorph", "hml_bconv", "hml_bconv_batch", "hml_keyswitch", "hml_rescale",
     "hml_hmult", "hml_hrotate", "hml_hadd", "hml_pmult", "hml_padd", "hml_pmult_add", "hml_hmult_batch", "hml_hrotate_batch",
     "hml_hmult_host", "hml_hrotate_host", "hml_hmult_host_packed", "hml_hrotate_host_packed", "hml_packed_bytes", "hml_pack_host",
     "hml_unpack_host", "hml_host_alloc_pinned", "hml_host_free_pinned", "hml_trace_counts",
@@ -70,6 +70,9 @@ EXPORTS = [
     "hml_hrotate_sharded", "hml_hmult_sharded", "hml_rescale_sharded", "hml_ew_sharded", "hml_group_op", "hml_hrotate_hoisted",
     "hml_replay_create", "hml_replay_bind", "hml_replay_run", "hml_replay_slot", "hml_replay_slot_level", "hml_replay_destroy",
 ]
+
+
+KEY_PACKED = 0x80000000  # HML_KEY_PACKED: OR into evk_q_limbs when the key went through Context.key_pack
 
 
 def load_library():
@@ -169,6 +172,7 @@ def load_library():
     L.hml_dev_free.argtypes = [vp, vp]
     L.hml_h2d.argtypes = [vp, vp, vp, u64, vp]
     L.hml_d2h.argtypes = [vp, vp, vp, u64, vp]
+    L.hml_key_pack.argtypes = [vp, vp, u64, vp, vp]
     L.hml_profile_begin.argtypes = [vp, vp]
     L.hml_profile_end.argtypes = [vp, C.POINTER(_Profile)]
     L.hml_sync.argtypes = [vp, vp]
@@ -353,6 +357,14 @@ class Context:
     def hmult(self, L, ct_a, ct_b, evk, evk_q_limbs=None, out=None):
         out = self.empty(2, L - 1, self.N) if out is None else out
         self._chk(self.lib.hml_hmult(self.h, L, _ptr(ct_a), _ptr(ct_b), _ptr(evk), evk_q_limbs or L, _ptr(out), self._stream()))
+        return out
+
+    def key_pack(self, key):
+        """Packed copy of an evaluation / rotation key (hml_key_pack): same shape, every limb slot holds N 32-bit low words + N high
+        bytes.  Pass it with evk_q_limbs = limbs | KEY_PACKED."""
+        import torch
+        out = torch.empty_like(key)
+        self._chk(self.lib.hml_key_pack(self.h, _ptr(key), key.numel() // self.N, _ptr(out), self._stream()))
         return out
 
     def hrotate(self, L, ct, rotkey, galois_elt=5, evk_q_limbs=None, out=None):

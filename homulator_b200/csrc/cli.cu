@@ -91,12 +91,12 @@ static int fill(hml_ctx *ctx, u64 *dev, const std::vector<u64> &limb_mod, u64 se
 extern "C" int hml_cli_main(int argc, char **argv) {
   if (argc < 6) {
     fprintf(stderr, "Usage: %s <configfile> <operationName> <maxExecutionLevel> <currentLevel> <alpha> [cluster]"
-                    " [--iters K] [--warmup W] [--rot R] [--device D] [--no-flush] [--verify]\n", argv[0]);
+                    " [--iters K] [--warmup W] [--rot R] [--device D] [--no-flush] [--verify] [--packed-key]\n", argv[0]);
     return 1;
   }
   const std::string path = argv[1], op = argv[2];
   const uint32_t maxl = (uint32_t)std::atoi(argv[3]), L = (uint32_t)std::atoi(argv[4]), alpha = (uint32_t)std::atoi(argv[5]);
-  int iters = 20, warmup = 3, rot = 1, device = 0, flush = 1, verify = 0, argi = 6;
+  int iters = 20, warmup = 3, rot = 1, device = 0, flush = 1, verify = 0, packed_key = 0, argi = 6;
   long cluster = -1;
   if (argi < argc && argv[argi][0] != '-') cluster = std::atol(argv[argi++]);  // accepted like the reference (bench_micro24.cpp:23-25)
   for (; argi < argc; ++argi) {
@@ -108,6 +108,7 @@ extern "C" int hml_cli_main(int argc, char **argv) {
     else if (f == "--device") val(device);
     else if (f == "--no-flush") flush = 0;
     else if (f == "--verify") verify = 1;
+    else if (f == "--packed-key") packed_key = 1;  // the synthetic key goes through hml_key_pack (HML_KEY_PACKED)
   }
   CfgFile cfg;
   std::string err;
@@ -172,9 +173,19 @@ extern "C" int hml_cli_main(int argc, char **argv) {
   }
   u64 g = 1;
   for (int r = 0; r < rot; ++r) g = (g * 5) % (2 * N);
+  uint64_t *key_pk = nullptr;
+  uint32_t key_limbs = L;
+  if (packed_key && key && cluster < 2) {
+    if (cudaMalloc(&key_pk, key_mod.size() * N * 8) != cudaSuccess || hml_key_pack(ctx, key, key_mod.size(), key_pk, nullptr) != HML_OK || hml_sync(ctx, nullptr) != HML_OK) {
+      fprintf(stderr, "homulator_b200: key packing failed: %s\n", hml_last_error(ctx));
+      return 5;
+    }
+    key_limbs |= HML_KEY_PACKED;
+  }
+  const uint64_t *key_used = key_pk ? key_pk : key;
   auto run = [&]() -> int {
-    if (op == "hmult") return hml_hmult(ctx, L, a, b, key, L, out, nullptr);
-    if (op == "hrotate") return hml_hrotate(ctx, L, a, key, L, g, out, nullptr);
+    if (op == "hmult") return hml_hmult(ctx, L, a, b, key_used, key_limbs, out, nullptr);
+    if (op == "hrotate") return hml_hrotate(ctx, L, a, key_used, key_limbs, g, out, nullptr);
     if (op == "hadd") return hml_hadd(ctx, L, a, b, out, nullptr);
     if (op == "pmult") return hml_pmult(ctx, L, a, b, out, nullptr);
     return hml_padd(ctx, L, a, b, out, nullptr);
@@ -374,7 +385,7 @@ extern "C" int hml_cli_main(int argc, char **argv) {
          (unsigned long long)ex.bconv_limb_macs, (unsigned long long)ex.automorph_limbs, (unsigned long long)ex.kernel_launches,
          prof.us[0], prof.us[1], prof.us[2], prof.us[3], prof.us[4], peak, peak_src.c_str(), cluster, gpus, sharded_us,
          sharded_ok == 1 ? "true" : sharded_ok == 0 ? "false" : "null", prop.name);
-  cudaFree(a); cudaFree(b); cudaFree(out); cudaFree(key); cudaFree(flushbuf);
+  cudaFree(a); cudaFree(b); cudaFree(out); cudaFree(key); cudaFree(key_pk); cudaFree(flushbuf);
   hml_ctx_destroy(ctx);
   return 0;
 }

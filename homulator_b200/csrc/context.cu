@@ -710,13 +710,15 @@ int ks_inner(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d,
   const size_t N = p.N;
   const uint32_t A = p.alpha, E = L + A, beta = lc->beta;
   const int logN = p.logN, npass = logN <= NTT_SMALL_LOG ? 1 : 2;
+  const bool key_packed = (evk_q_limbs & HML_KEY_PACKED) != 0;
+  evk_q_limbs &= ~HML_KEY_PACKED;
   // K5 (reference :294-414): inner product with the key (key words loaded once per batch) — unless the ModUp transform's row
   // pass has already done it (ks_front with HPIP)
   if (!ip_done) {
     LimbMap ip = lc->ext_lm;  // pos = limb index inside the key (Q-limbs first, then P-limbs after evk_q_limbs)
     for (uint32_t e = 0; e < E; ++e) ip.pos[e] = (uint16_t)(e < L ? e : evk_q_limbs + (e - L));
     InnerArgs a{};
-    a.d = d.ptr; a.ext = ext; a.evk = evk; a.acc = acc; a.N = N; a.n_ext = E; a.beta = beta; a.evk_limbs = evk_q_limbs + A;
+    a.d = d.ptr; a.ext = ext; a.evk = evk; a.evk_packed = key_packed ? 1 : 0; a.acc = acc; a.N = N; a.n_ext = E; a.beta = beta; a.evk_limbs = evk_q_limbs + A;
     a.n_batch = nb; a.d_batch_stride = d.stride; a.ext_batch_stride = (long long)beta * E * N; a.acc_batch_stride = 2ll * AL * N;
     a.acc_comp_stride = (long long)AL * N; a.ext_f64 = npass == 2;
     // Q-limb accumulators only feed element-wise epilogues: packed (5 B / coefficient) — but the HPIP path, which some other
@@ -772,11 +774,14 @@ int ks_front(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d,
   const size_t N = p.N;
   const uint32_t A = p.alpha, E = L + A;
   const bool hpip = ks_uses_hpip(ctx, L, nb);
+  const bool key_packed = (evk_q_limbs & HML_KEY_PACKED) != 0;  // ks_inner strips the flag itself
+  const uint32_t evk_flagged = evk_q_limbs;
+  evk_q_limbs &= ~HML_KEY_PACKED;
   const BatchPtr d_raw = d;
   if (au) d = {au->sigma_d, au->sigma_stride};  // what K5 reads (written by the ModUp INTT)
   NttMac mac{};
   if (hpip) {
-    mac.evk = evk; mac.d = d.ptr; mac.acc = acc; mac.d_batch_stride = d.stride; mac.acc_batch_stride = 2ll * AL * N;
+    mac.evk = evk; mac.evk_packed = key_packed ? 1 : 0; mac.d = d.ptr; mac.acc = acc; mac.d_batch_stride = d.stride; mac.acc_batch_stride = 2ll * AL * N;
     mac.acc_comp_stride = (long long)AL * N; mac.evk_limbs = (int)(evk_q_limbs + A);
     for (uint32_t e = 0; e < E; ++e) mac.key_pos[e] = (uint16_t)(e < L ? e : evk_q_limbs + (e - L));
     mac.u_limb = -1;
@@ -788,7 +793,7 @@ int ks_front(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, BatchPtr d,
   }
   int rc = ks_modup(ctx, lc, L, nb, d_raw, yb, ext, s, hpip ? &mac : nullptr, au);
   if (rc) return rc;
-  return ks_inner(ctx, lc, L, nb, d, evk, evk_q_limbs, ext, acc, AL, 0, s, mu, hpip);
+  return ks_inner(ctx, lc, L, nb, d, evk, evk_flagged, ext, acc, AL, 0, s, mu, hpip);
 }
 
 // K8..K10 (+ the caller's addends): ModDown of nb accumulator pairs acc [nb][2][E] -> out_c[b] = (acc_c - NTT(BConv(acc_c; P -> Q))) * P^-1 (+ add_c[b])
@@ -852,7 +857,7 @@ int ks_tail(hml_ctx *ctx, LevelConsts *lc, uint32_t L, uint32_t nb, u64 *acc, u6
 int ks_run(hml_ctx *ctx, uint32_t L, uint32_t nb, BatchPtr d, const u64 *evk, uint32_t evk_q_limbs, BatchOut out0,
            BatchOut out1, BatchPtr add0, BatchPtr add1, u64 *ws, cudaStream_t s, const KsAuto *au) {
   const Params &p = ctx->p;
-  if (evk_q_limbs < L || evk_q_limbs > p.max_level) return fail(ctx, HML_ERR_INVALID, "evk_q_limbs must be in [L, maxLevel]");
+  if ((evk_q_limbs & ~HML_KEY_PACKED) < L || (evk_q_limbs & ~HML_KEY_PACKED) > p.max_level) return fail(ctx, HML_ERR_INVALID, "evk_q_limbs must be in [L, maxLevel]");
   LevelConsts *lc;
   int rc = get_level(ctx, L, &lc);
   if (rc) return rc;
@@ -863,6 +868,17 @@ int ks_run(hml_ctx *ctx, uint32_t L, uint32_t nb, BatchPtr d, const u64 *evk, ui
   u64 *yb = ws, *ext = yb + (size_t)nb * L * N, *acc = ext + (size_t)nb * beta * E * N, *vb = acc + (size_t)nb * 2 * E * N;
   if ((rc = ks_front(ctx, lc, L, nb, d, evk, evk_q_limbs, yb, ext, acc, E, s, nullptr, au))) return rc;
   return ks_tail(ctx, lc, L, nb, acc, vb, out0, out1, add0, add1, s, p.logN > NTT_SMALL_LOG && !ks_uses_hpip(ctx, L, nb), au ? au->g : 0);
+}
+
+extern "C" int hml_key_pack(hml_ctx *ctx, const uint64_t *words_dev, uint64_t n_limbs, uint64_t *packed_dev, void *stream) {
+  if (!ctx) return HML_ERR_INVALID;
+  if (!words_dev || !packed_dev) return fail(ctx, HML_ERR_INVALID, "null buffer");
+  const size_t N = ctx->p.N;
+  if (packed_dev < words_dev + n_limbs * N && words_dev < packed_dev + n_limbs * N) return fail(ctx, HML_ERR_INVALID, "hml_key_pack: buffers overlap");
+  if (n_limbs == 0) return HML_OK;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  launch_pack_limbs((int)N, (size_t)n_limbs, (const u64 *)words_dev, (u64 *)packed_dev, (cudaStream_t)stream);
+  return check_launch(ctx, "key pack");
 }
 
 extern "C" int hml_keyswitch(hml_ctx *ctx, uint32_t L, const uint64_t *d, const uint64_t *evk, uint32_t evk_q_limbs,
@@ -1625,7 +1641,7 @@ int hmult_run(hml_ctx *ctx, uint32_t L, uint32_t nb, const u64 *ct_a, const u64 
     if (rc) return rc;
     return rescale_run(ctx, L, cb, (long long)PL, 2 * nb, ct_out, (long long)(L - 1) * N, rest, s);
   }
-  if (evk_q_limbs < L || evk_q_limbs > p.max_level) return fail(ctx, HML_ERR_INVALID, "evk_q_limbs must be in [L, maxLevel]");
+  if ((evk_q_limbs & ~HML_KEY_PACKED) < L || (evk_q_limbs & ~HML_KEY_PACKED) > p.max_level) return fail(ctx, HML_ERR_INVALID, "evk_q_limbs must be in [L, maxLevel]");
   LevelConsts *lc;
   int rc = get_level(ctx, L, &lc);
   if (rc) return rc;
@@ -1722,7 +1738,7 @@ extern "C" int hml_hrotate(hml_ctx *ctx, uint32_t L, const uint64_t *ct, const u
 int hrot_hoisted_run(hml_ctx *ctx, uint32_t L, const u64 *ct, uint32_t n_rot, const uint64_t *const *rotkeys, uint32_t evk_q_limbs,
                      const uint64_t *galois, uint64_t *const *outs, u64 *ws, cudaStream_t s) {
   const Params &p = ctx->p;
-  if (evk_q_limbs < L || evk_q_limbs > p.max_level) return fail(ctx, HML_ERR_INVALID, "evk_q_limbs must be in [L, maxLevel]");
+  if ((evk_q_limbs & ~HML_KEY_PACKED) < L || (evk_q_limbs & ~HML_KEY_PACKED) > p.max_level) return fail(ctx, HML_ERR_INVALID, "evk_q_limbs must be in [L, maxLevel]");
   LevelConsts *lc;
   int rc = get_level(ctx, L, &lc);
   if (rc) return rc;

@@ -156,12 +156,33 @@ __global__ void __launch_bounds__(EW_THREADS, 3) k_inner(const ModConst *__restr
   // every key word of the thread is requested before the first one is used: ONE memory round trip for the 3 * beta loads
   // (converting inside the load loop made ptxas wait for each digit's pair before issuing the next)
   ulonglong2 kraw[IP_MAX_BETA][2];
+  if (a.evk_packed) {  // uniform: packed key limbs — the raw halves are all requested first, then assembled (kraw.x = the pair's low
+    // words, kraw.y = its two high bytes until the loop below)
 #pragma unroll
-  for (int j = 0; j < IP_MAX_BETA; ++j)
+    for (int j = 0; j < IP_MAX_BETA; ++j)
 #pragma unroll
-    for (int c = 0; c < 2; ++c)
-      kraw[j][c] = j < a.beta ? ld2(a.evk, (((size_t)j * 2 + c) * a.evk_limbs + kl) * n2 + i2) : make_ulonglong2(0, 0);
-  pin_loads(kraw);
+      for (int c = 0; c < 2; ++c) {
+        const u64 *slot = a.evk + (((size_t)j * 2 + c) * a.evk_limbs + kl) * a.N;
+        kraw[j][c] = j < a.beta ? make_ulonglong2(__ldg(reinterpret_cast<const u64 *>(slot) + i2),
+                                                  __ldg(reinterpret_cast<const unsigned short *>(reinterpret_cast<const unsigned char *>(slot) + 4 * (size_t)a.N) + i2))
+                                : make_ulonglong2(0, 0);
+      }
+    pin_loads(kraw);
+#pragma unroll
+    for (int j = 0; j < IP_MAX_BETA; ++j)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const u64 lo = kraw[j][c].x, hi = kraw[j][c].y;
+        kraw[j][c] = make_ulonglong2(((hi & 0xFFull) << 32) | (lo & 0xFFFFFFFFull), ((hi >> 8) << 32) | (lo >> 32));
+      }
+  } else {
+#pragma unroll
+    for (int j = 0; j < IP_MAX_BETA; ++j)
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+        kraw[j][c] = j < a.beta ? ld2(a.evk, (((size_t)j * 2 + c) * a.evk_limbs + kl) * n2 + i2) : make_ulonglong2(0, 0);
+    pin_loads(kraw);
+  }
   double k[IP_MAX_BETA][2][2];  // [digit][component][coefficient]
 #pragma unroll
   for (int j = 0; j < IP_MAX_BETA; ++j)
@@ -268,6 +289,23 @@ __global__ void __launch_bounds__(EW_THREADS) k_automorph(int logN, const u64 *_
 void launch_automorph(int logN, int n_limbs, const u64 *in, u64 *out, u64 g, cudaStream_t s) {
   const unsigned N = 1u << logN;
   launch_pdl(k_automorph, dim3((N + EW_THREADS - 1) / EW_THREADS, n_limbs), EW_THREADS, 0, s, logN, in, out, (unsigned)(g & (2ull * N - 1)));
+}
+
+// words -> packed limbs, slot geometry unchanged (evaluation keys: hml_key_pack)
+__global__ void __launch_bounds__(EW_THREADS) k_pack_limbs(int N, const u64 *__restrict__ in, u64 *__restrict__ out) {
+  pdl_wait();
+  const size_t i2 = (size_t)blockIdx.x * EW_THREADS + threadIdx.x;
+  if (i2 >= (size_t)N / 2) return;
+  const size_t limb = blockIdx.y + (size_t)blockIdx.z * gridDim.y;
+  const ulonglong2 v = ld2(in + limb * N, i2);
+  st_packed2(out + limb * N, N, i2, v.x, v.y);
+}
+void launch_pack_limbs(int N, size_t n_limbs, const u64 *in, u64 *out, cudaStream_t s) {
+  for (size_t done = 0; done < n_limbs;) {  // grid.y * grid.z limbs per launch
+    const size_t rest = n_limbs - done, gy = rest < 256 ? rest : 256, gz = std::min<size_t>(rest / gy, 65535);
+    launch_pdl(k_pack_limbs, dim3((unsigned)((N / 2 + EW_THREADS - 1) / EW_THREADS), (unsigned)gy, (unsigned)gz), EW_THREADS, 0, s, N, in + done * N, out + done * N);
+    done += gy * gz;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ base conversion

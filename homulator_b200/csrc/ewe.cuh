@@ -31,6 +31,7 @@ struct InnerArgs {
   const u64 *d;     // [>= number of owned Q-limbs][N]
   const u64 *ext;   // [beta][n_ext][N]
   const u64 *evk;   // [beta][2][evk_limbs][N]
+  int evk_packed;   // the key's limb slots hold packed limbs (hml_key_pack: 5 of every 8 bytes are read)
   u64 *acc;         // [2][n_ext][N]
   int N, n_ext, beta, evk_limbs;   // beta <= 8
   int n_batch;                     // ciphertexts sharing the key: d / ext / acc advance by the strides below
@@ -68,6 +69,9 @@ void launch_sub_mul_add(const ModConst *mc, const LimbMap &lm, const SubMulArgs 
 
 // out[k] = in[k'],  2*brv(k')+1 = g*(2*brv(k)+1) mod 2N, for n_limbs limbs
 void launch_automorph(int logN, int n_limbs, const u64 *in, u64 *out, u64 g, cudaStream_t s);
+
+// words [n_limbs][N] -> packed limbs inside slots of the same size (modarith.cuh st_packed2); out must not overlap in
+void launch_pack_limbs(int N, size_t n_limbs, const u64 *in, u64 *out, cudaStream_t s);
 
 // Fast base conversion.  in [n_src][N] coefficient form.  If step1 != nullptr the per-source scaling
 // y_i = in_i * hat_inv_i mod s_i is applied inside (step1[i] = (hat_inv_i, RN(hat_inv_i / s_i)));

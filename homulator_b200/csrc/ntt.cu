@@ -321,17 +321,18 @@ struct RowItemsB {
   }
 };
 
-// MODE 0: plain transform; 1: fused element-wise epilogue (NttFuse); 2: fused key-switch inner product (NttMac)
+// MODE 0: plain transform; 1: fused element-wise epilogue (NttFuse); 2: fused key-switch inner product (NttMac); 3: the same
+// with a packed key
 template <bool INV, int MODE>
 __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN, LimbMap lm, NttLaunch l) {
-  constexpr bool FUSE = MODE == 1, MAC = MODE == 2;
+  constexpr bool FUSE = MODE == 1, MAC = MODE >= 2, KPK = MODE == 3;  // MODE 3: MAC with packed key limbs (NttMac::evk_packed)
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // grid = (tiles * item splits, limbs), split index fastest: the CTAs that share a (limb, tile) — hence its 32 KB twiddle blob —
   // are adjacent in launch order, so all but the first of them find the blob in L2 (row-pass reads 2217 -> 1990 MB per launch)
   // (MAC launches walk the limbs backwards: the P-limbs, whose CTAs have one more digit to transform, start first)
-  const int limb = MODE == 2 ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+  const int limb = MAC ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
   const int zn = gridDim.x >> (logN - NTT_ROW_LOG - 4), tile_i = blockIdx.x / zn, zi = blockIdx.x - tile_i * zn;
   const int mi = lm.mod[limb];
   const double *blob = reinterpret_cast<const double *>(smem);
@@ -414,12 +415,21 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
       const size_t nn = (size_t)1 << logN, c0 = tile_off + (size_t)warp * 512 + (size_t)lane * 16;
       const size_t kl = mq.key_pos[limb];
       auto pf = [&](const u64 *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); };
-      pf(mq.evk + (((size_t)cur.p * 2 + 0) * mq.evk_limbs + kl) * nn + c0);
-      pf(mq.evk + (((size_t)cur.p * 2 + 1) * mq.evk_limbs + kl) * nn + c0);
+      // a key limb's share of the warp's 512 coefficients: 4 KB of words, or 2 KB of low words + 512 high bytes when packed
+      auto pf_key = [&](int j, int c) {
+        const u64 *slot = mq.evk + (((size_t)j * 2 + c) * mq.evk_limbs + kl) * nn;
+        if constexpr (!KPK) { pf(slot + c0); return; }
+        const unsigned char *b = reinterpret_cast<const unsigned char *>(slot);
+        const size_t w0 = tile_off + (size_t)warp * 512;
+        if (lane < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + w0 * 4 + lane * 128));
+        else if (lane < 20) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + 4 * nn + w0 + (lane - 16) * 128));
+      };
+      pf_key(cur.p, 0);
+      pf_key(cur.p, 1);
       const int own = lm.skip[limb];
       if (cur.p == items.first_p() && own != 0xFF) {
-        pf(mq.evk + (((size_t)own * 2 + 0) * mq.evk_limbs + kl) * nn + c0);
-        pf(mq.evk + (((size_t)own * 2 + 1) * mq.evk_limbs + kl) * nn + c0);
+        pf_key(own, 0);
+        pf_key(own, 1);
         pf(mq.d + (size_t)cur.b * mq.d_batch_stride + (size_t)limb * nn + c0);
       }
     }
@@ -473,10 +483,27 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
         for (int h = 0; h < 2; ++h) {  // four chunks at a time: every load of the half is in flight before the first product
           ulonglong2 kv0[4], kv1[4];
           double2 old0[4], old1[4];
+          // packed key limbs (NttMac::evk_packed): the pair's low words and its two high bytes, assembled after all loads are out
+          auto ld_key_raw = [&](const u64 *kp, int mm) -> ulonglong2 {
+            const u64 *slot = kp - ci;
+            const size_t i2 = (ci >> 1) + 16 * mm;
+            return make_ulonglong2(__ldg(slot + i2), __ldg(reinterpret_cast<const unsigned short *>(reinterpret_cast<const unsigned char *>(slot) + 4 * nn) + i2));
+          };
+          auto key_join = [](ulonglong2 r) {
+            return make_ulonglong2(((r.y & 0xFFull) << 32) | (r.x & 0xFFFFFFFFull), ((r.y >> 8) << 32) | (r.x >> 32));
+          };
+          if constexpr (KPK) {
 #pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            kv0[m] = __ldg(reinterpret_cast<const ulonglong2 *>(k0 + 32 * (4 * h + m)));
-            kv1[m] = __ldg(reinterpret_cast<const ulonglong2 *>(k1 + 32 * (4 * h + m)));
+            for (int m = 0; m < 4; ++m) {
+              kv0[m] = ld_key_raw(k0, 4 * h + m);
+              kv1[m] = ld_key_raw(k1, 4 * h + m);
+            }
+          } else {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              kv0[m] = __ldg(reinterpret_cast<const ulonglong2 *>(k0 + 32 * (4 * h + m)));
+              kv1[m] = __ldg(reinterpret_cast<const ulonglong2 *>(k1 + 32 * (4 * h + m)));
+            }
           }
           if (!first) {  // this thread wrote these slots itself while it processed the previous member: plain (coherent) loads
 #pragma unroll
@@ -488,8 +515,8 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
               const ulonglong2 dv = __ldg(reinterpret_cast<const ulonglong2 *>(dd + 32 * (4 * h + m)));
-              const ulonglong2 w0 = __ldg(reinterpret_cast<const ulonglong2 *>(o0 + 32 * (4 * h + m)));
-              const ulonglong2 w1 = __ldg(reinterpret_cast<const ulonglong2 *>(o1 + 32 * (4 * h + m)));
+              const ulonglong2 w0 = KPK ? key_join(ld_key_raw(o0, 4 * h + m)) : __ldg(reinterpret_cast<const ulonglong2 *>(o0 + 32 * (4 * h + m)));
+              const ulonglong2 w1 = KPK ? key_join(ld_key_raw(o1, 4 * h + m)) : __ldg(reinterpret_cast<const ulonglong2 *>(o1 + 32 * (4 * h + m)));
               const double dx = u64_to_f64(dv.x), dy = u64_to_f64(dv.y);
               old0[m] = make_double2(mulmod_var(dx, u64_to_f64(w0.x), q, qinv), mulmod_var(dy, u64_to_f64(w0.y), q, qinv));
               old1[m] = make_double2(mulmod_var(dx, u64_to_f64(w1.x), q, qinv), mulmod_var(dy, u64_to_f64(w1.y), q, qinv));
@@ -497,6 +524,10 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_rows(NttTables t, int logN
           } else {
 #pragma unroll
             for (int m = 0; m < 4; ++m) old0[m] = old1[m] = make_double2(0.0, 0.0);
+          }
+          if constexpr (KPK) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) { kv0[m] = key_join(kv0[m]); kv1[m] = key_join(kv1[m]); }
           }
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
@@ -836,6 +867,7 @@ static void launch_rows(bool inverse, const NttTables &t, int logN, const LimbMa
     allow_smem(ntt_rows<false, 0>, ROW_SMEM_BYTES);
     allow_smem(ntt_rows<false, 1>, ROW_SMEM_BYTES);
     allow_smem(ntt_rows<false, 2>, ROW_SMEM_BYTES);
+    allow_smem(ntt_rows<false, 3>, ROW_SMEM_BYTES);
     allow_smem(ntt_rows<true, 0>, ROW_SMEM_BYTES);
   }
   const int tiles = 1 << (logN - NTT_ROW_LOG - 4);
@@ -843,7 +875,8 @@ static void launch_rows(bool inverse, const NttTables &t, int logN, const LimbMa
     const int per = std::max(1, row_items_target() / std::max(1, l.n_polys));
     int z = (l.n_batch + per - 1) / per;
     while (z > 1 && (long long)tiles * l.n_limbs * z > 64ll * sm_count()) --z;
-    launch_pdl(ntt_rows<false, 2>, dim3(tiles * std::max(1, z), l.n_limbs), NTT_THREADS, ROW_SMEM_BYTES, s, t, logN, lm, l);
+    if (l.mac.evk_packed) launch_pdl(ntt_rows<false, 3>, dim3(tiles * std::max(1, z), l.n_limbs), NTT_THREADS, ROW_SMEM_BYTES, s, t, logN, lm, l);
+    else launch_pdl(ntt_rows<false, 2>, dim3(tiles * std::max(1, z), l.n_limbs), NTT_THREADS, ROW_SMEM_BYTES, s, t, logN, lm, l);
     return;
   }
   const dim3 grid(tiles * row_split(l.n_polys * l.n_batch, tiles * l.n_limbs), l.n_limbs);

@@ -89,6 +89,7 @@ struct NttFuse {
 // L2-resident between members: one CTA handles all members of a (b, e, tile)), the last one stores canonical words.
 struct NttMac {
   const u64 *evk;               // [beta][2][evk_limbs][N]; null: no fusion
+  int evk_packed;               // the key's limb slots hold packed limbs (hml_key_pack)
   const u64 *d;                 // the untouched evaluation-form input, [>= L][N] per ciphertext
   u64 *acc;                     // accumulators [n_batch][2][..][N], 8-byte slots
   long long d_batch_stride, acc_batch_stride, acc_comp_stride;

@@ -131,7 +131,9 @@ extern "C" int hml_replay_bind(hml_replay *rp, const uint64_t *x, const uint64_t
   rp->evk = evk; rp->evk_q_limbs = evk_q_limbs;
   for (const hml_trace_op &o : rp->ops) {
     if ((o.kind == HML_OP_PMULT || o.kind == HML_OP_PADD) && (o.b >= rp->pts.size() || !rp->pts[o.b])) return rfail(rp, HML_ERR_INVALID, "trace uses a plaintext that is not bound");
-    if ((o.kind == HML_OP_HROTATE || o.kind == HML_OP_HMULT) && evk_q_limbs < rp->L) return rfail(rp, HML_ERR_INVALID, "keys must be laid out for at least the trace's top level (evk_q_limbs >= L)");
+    if ((o.kind == HML_OP_HROTATE || o.kind == HML_OP_HMULT) && rp->sh && (evk_q_limbs & HML_KEY_PACKED))
+      return rfail(rp, HML_ERR_UNSUPPORTED, "limb-sharded traces take word keys (no HML_KEY_PACKED)");
+    if ((o.kind == HML_OP_HROTATE || o.kind == HML_OP_HMULT) && (evk_q_limbs & ~HML_KEY_PACKED) < rp->L) return rfail(rp, HML_ERR_INVALID, "keys must be laid out for at least the trace's top level (evk_q_limbs >= L)");
     if (o.kind == HML_OP_HROTATE && (!rp->key_of_rot.count(o.b) || !rp->keys[rp->key_of_rot[o.b]]) && !(rp->sh && rp->nq == 0 && rp->key_of_rot.count(o.b)))
       return rfail(rp, HML_ERR_INVALID, "trace uses a rotation whose key is not bound");
     if (o.kind == HML_OP_HMULT && !evk && !(rp->sh && rp->nq == 0)) return rfail(rp, HML_ERR_INVALID, "trace has an hmult but no relinearisation key is bound");

@@ -30,6 +30,10 @@
  *   - evaluation / rotation key layout: [beta][2][evk_q_limbs + alpha][N], Q-limbs first then the alpha
  *     P-limbs; evk_q_limbs is L (the compact per-level layout the reference allocates,
  *     reference src/Operation.cpp:300-304 `IP_Key{c}_{j}` of Level+Alpha limbs) or maxLevel.
+ *     A key may also be handed over PACKED (hml_key_pack: every limb slot keeps its 8N bytes but holds N 32-bit low words
+ *     followed by N high bytes, 5 of every 8 bytes are read): OR HML_KEY_PACKED into the evk_q_limbs argument of the call.
+ *     One ciphertext's key switch reads its 150 MB key once, so this is worth ~4 % of a single hmult / hrotate; the limb-sharded
+ *     entry points take word keys only.
  *   - there is NO CPU fallback: every compute entry point fails with HML_ERR_CUDA when no device
  *     is usable.
  */
@@ -75,6 +79,10 @@ int hml_dev_free(hml_ctx *ctx, uint64_t *ptr);
 int hml_h2d(hml_ctx *ctx, uint64_t *dst_dev, const uint64_t *src_host, uint64_t n_words, void *stream);
 int hml_d2h(hml_ctx *ctx, uint64_t *dst_host, const uint64_t *src_dev, uint64_t n_words, void *stream);
 int hml_sync(hml_ctx *ctx, void *stream);
+/* words [n_limbs][N] -> packed limbs [n_limbs][N-word slots] (device to device, out must not overlap in); for evaluation /
+ * rotation keys: n_limbs = beta * 2 * (evk_q_limbs + alpha).  See HML_KEY_PACKED above. */
+#define HML_KEY_PACKED 0x80000000u
+int hml_key_pack(hml_ctx *ctx, const uint64_t *words_dev, uint64_t n_limbs, uint64_t *packed_dev, void *stream);
 
 /* ------------------------------------------------------------------ primitives
  * One entry point per instruction class of the reference (reference include/Instruction.h:6-20; only

@@ -452,6 +452,30 @@ def test_hmult_many_special_primes_dmma_fold():
     Oracle.set_threads(1)
 
 
+def test_packed_keys(north_star):
+    """hml_key_pack + HML_KEY_PACKED: the same results from a key whose limb slots hold packed limbs (5 of every 8 bytes read) —
+    the fused inner product of one ciphertext, the stand-alone inner product of batches and of hoisted rotations, key switch."""
+    ctx, o, a, b, evk = north_star
+    L = 35
+    K = to_dev(evk)
+    P = ctx.key_pack(K)
+    assert not torch.equal(P, K)
+    kp = L | hml.KEY_PACKED
+    assert np.array_equal(to_host(ctx.hmult(L, to_dev(a), to_dev(b), P, evk_q_limbs=kp)), o.hmult(L, a, b, evk, L))
+    assert np.array_equal(to_host(ctx.hrotate(L, to_dev(a), P, 25, evk_q_limbs=kp)), o.hrotate(L, a, evk, L, 25))
+    w0, w1 = o.keyswitch(L, b[1], evk, L)
+    g0, g1 = ctx.keyswitch(L, to_dev(b[1]), P, kp)
+    assert np.array_equal(to_host(g0), w0) and np.array_equal(to_host(g1), w1)
+    A3, B3 = torch.stack([to_dev(a), to_dev(b), to_dev(a)]), torch.stack([to_dev(b), to_dev(b), to_dev(a)])
+    assert torch.equal(ctx.hmult_batch(L, A3, B3, P, evk_q_limbs=kp), ctx.hmult_batch(L, A3, B3, K))
+    assert torch.equal(ctx.hrotate_batch(L, A3, P, 5, evk_q_limbs=kp), ctx.hrotate_batch(L, A3, K, 5))
+    gs = [5, 25, 125]
+    for x, y in zip(ctx.hrotate_hoisted(L, to_dev(a), [P] * 3, gs, evk_q_limbs=kp), ctx.hrotate_hoisted(L, to_dev(a), [K] * 3, gs)):
+        assert torch.equal(x, y)
+    with pytest.raises(hml.HmlError):
+        ctx._chk(ctx.lib.hml_key_pack(ctx.h, K.data_ptr(), K.numel() // ctx.N, K.data_ptr(), None))  # in place is refused
+
+
 def test_hrotate_in_place_and_identity(north_star):
     """hml_hrotate with ct_out == ct (the epilogue must not gather sigma(c0) from rows it has already overwritten: the library
     falls back to the automorphism kernel there), several galois elements through the fused loads, and g = 1."""
