@@ -320,10 +320,13 @@ def main():
     n_limbs, n_b = 115, 32
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    def ntt_pair_ms(reps=10):
+    def ntt_pair_ms(reps=10, settle=False):
         idx = [ctx.ext_mod_idx(L)[i % (L + ALPHA)] for i in range(n_limbs)]
         bufs = [ctx.uniform(idx, 50 + i, lead=(n_b,)) for i in range(2)]  # 2 x 1.9 GB >> L2: every launch reads from HBM
         dst = ctx.empty(n_b, n_limbs, N_RING)
+        if settle:  # generating the inputs is a burst of its own
+            torch.cuda.synchronize()
+            time.sleep(1.0)
         for i in range(3):
             ctx.ntt_batch(bufs[i % 2], idx, out=dst)
         torch.cuda.synchronize()
@@ -360,7 +363,21 @@ def main():
         return ts[len(ts) // 2]
 
     ntt_ms = ntt1_us_per_limb = ntt_clock = hm = hr = hm_pk = hr_pk = None
+
+    def cool():
+        """The board's power controller averages over about a second: the burst measurements below are separated by short idle
+        gaps so that none of them starts inside the previous one's power-cap tail."""
+        torch.cuda.synchronize()
+        time.sleep(1.0)
+
     if rank == 0:
+        ntt_ms, ntt1_us_per_limb = ntt_pair_ms(settle=True)
+        try:
+            import pynvml
+            ntt_clock = pynvml.nvmlDeviceGetClockInfo(pynvml.nvmlDeviceGetHandleByIndex(local), pynvml.NVML_CLOCK_SM)
+        except Exception:
+            pass
+        cool()
         if flush is not None:  # one-ciphertext latencies (L2 flushed), also before the sustained region: a latency figure
             o1, o2 = ctx.empty(2, L - 1, N_RING), ctx.empty(2, L, N_RING)
             for _ in range(3):
@@ -377,6 +394,7 @@ def main():
             hm_pk = lat(lambda: ctx.hmult(L, ct_a[0], ct_b[0], evk_p, evk_q_limbs=kp, out=o1), 20)
             hr_pk = lat(lambda: ctx.hrotate(L, ct_a[0], evk_p, 5, evk_q_limbs=kp, out=o2), 20)
             del o1, o2, evk_p
+        cool()
         # one 32-ciphertext chunk of the batched ops timed alone (a 25 ms burst at full clocks): what the kernels do before the
         # board reaches its power cap; `value` below is the sustained figure of the 256-ciphertext steps
         nb32 = min(32, B)
@@ -394,12 +412,7 @@ def main():
             torch.cuda.synchronize()
             burst[name] = e0.elapsed_time(e1) * 1e3 / (3 * nb32)
         del ob
-        ntt_ms, ntt1_us_per_limb = ntt_pair_ms()
-        try:
-            import pynvml
-            ntt_clock = pynvml.nvmlDeviceGetClockInfo(pynvml.nvmlDeviceGetHandleByIndex(local), pynvml.NVML_CLOCK_SM)
-        except Exception:
-            pass
+        cool()
 
     # the process group is created only now: while rank 0 timed its kernels alone, the other ranks waited in the rendezvous on
     # the host (in an NCCL barrier their kernels would spin on peer memory next to the measurement: 0.35 -> 0.40 us per limb)
