@@ -1597,12 +1597,12 @@ extern "C" int hml_rescale_shard_end(hml_ctx *ctx, uint32_t L, uint32_t rank, ui
 }
 
 // ------------------------------------------------------------------------------------------------ top-level ops
-// Batched ops run HML_BATCH_CHUNK (default 32) ciphertexts per kernel launch: per-CTA set-up (twiddle staging, conversion matrices,
+// Batched ops run HML_BATCH_CHUNK (default 64; 32 until the end of round 2: 1-2 % slower, burst and sustained) ciphertexts per kernel launch: per-CTA set-up (twiddle staging, conversion matrices,
 // key words) is paid once per chunk instead of once per ciphertext and grids are large enough to hide launch tails.
 static uint32_t batch_chunk() {
   static const uint32_t v = [] {
-    const char *e = getenv("HML_BATCH_CHUNK");  // tuning knob; default 32
-    const int n = e ? atoi(e) : 32;
+    const char *e = getenv("HML_BATCH_CHUNK");  // tuning knob
+    const int n = e ? atoi(e) : 64;
     return (uint32_t)std::min(std::max(n, 1), 64);
   }();
   return v;

@@ -493,7 +493,7 @@ def test_hrotate_in_place_and_identity(north_star):
 
 @pytest.mark.parametrize("env", [{"HML_NTT_FUSED": "1"}, {"HML_HPIP": "0"}, {"HML_HPIP": "2"}, {"HML_BCONV_UMMA": "0"},
                                  {"HML_COL_NT": "256", "HML_PDL": "0"}, {"HML_NTT_FUSED": "1", "HML_NTT_G": "1", "HML_NTT_LAG": "1"},
-                                 {"HML_COL_DYN": "0", "HML_AUTO_FUSE": "0"}, {"HML_COL_NT": "128"}],
+                                 {"HML_COL_DYN": "0", "HML_AUTO_FUSE": "0"}, {"HML_COL_NT": "128"}, {"HML_BATCH_CHUNK": "2"}],
                          ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
 def test_alternative_kernel_paths(env):
     """Every kernel path behind a process-wide switch — the single-launch transform (ntt_fused.cu), the inner product fused
