@@ -363,6 +363,7 @@ def main():
         return ts[len(ts) // 2]
 
     ntt_ms = ntt1_us_per_limb = ntt_clock = hm = hr = hm_pk = hr_pk = None
+    burst = {}
 
     def cool():
         """The board's power controller averages over about a second: the burst measurements below are separated by short idle
@@ -399,7 +400,6 @@ def main():
         # board reaches its power cap; `value` below is the sustained figure of the 256-ciphertext steps
         nb32 = min(32, B)
         ob = ctx.empty(nb32, 2, L, N_RING)
-        burst = {}
         for name, fn in (("hmult", lambda: ctx.hmult_batch(L, ct_a[:nb32], ct_b[:nb32], evk, out=out[:nb32])),
                          ("hrotate", lambda: ctx.hrotate_batch(L, ct_a[:nb32], evk, 5, out=ob))):
             for _ in range(2):
@@ -617,6 +617,10 @@ def main():
         "e2e": {"value": e2e_us, "unit": "us", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                 "batch_per_gpu_per_step": Be, "host_cpu_affinity": numa},
         "gpu_launches": int(launches),
+        # `value` is the SUSTAINED figure: 256 / n_gpus ciphertexts per step keep one GPU busy for over a second, and the boards of
+        # this pool then sit at their 1000 W cap (clocks.sm_mhz vs sm_max_mhz below).  Round 1's line (170 us) was taken with
+        # 32-ciphertext steps at 1965 MHz; the like-for-like figure of this tree is the one-chunk burst below.
+        "value_one_chunk_at_burst_clocks": burst["hmult"] if rank == 0 and burst else None,
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "kernel": "ntt_fwd_cols + ntt_rows (forward NTT pair, 32 ciphertexts x 115 limbs per launch)",
                      "timed": "alone, before and after the step loop, the faster of the two (burst clocks, like the burst peak): extra.ntt_us_per_limb_before_step_loop / _sustained",
